@@ -1,0 +1,109 @@
+/* sdv_b200.h — C-ABI of the B200-native SDV-LOAM tracking / optimisation hot path.
+ *
+ * The reference (ZikangYuan/SDV-LOAM) has NO plugin/FFI layer: the hot path sits behind C++ member
+ * functions called by FullSystem.  Each entry point below names the reference member it replaces (file:line relative
+ * to /root/reference/src); INTEGRATION.md shows the shim classes a maintainer adds to keep those signatures.
+ *
+ * Conventions
+ *   - return 0 on success, negative sdv_status on error; never throws; sdv_last_error() gives the message.
+ *   - NaN/inf in energies propagate unchanged (the reference signals tracking loss through them,
+ *     FullSystem.cpp:862-867, FullSystemOptimize.cpp:472-476).
+ *   - all pointers are HOST pointers owned by the caller and are consumed before the call returns, except the
+ *     `_dev` variants which take device pointers of the context's device.
+ *   - poses: double T[7] = {qw,qx,qy,qz, tx,ty,tz} (Sophus SE3d storage order, unit quaternion).
+ *   - a context is bound to one CUDA device; calls on one context must not overlap (one FullSystem = one context;
+ *     the reference serialises the same calls under trackMutex / mapMutex, FullSystem.h:277-323).
+ */
+#ifndef SDV_B200_H
+#define SDV_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDV_PYR_LEVELS 6            /* util/settings.h:25 PYR_LEVELS */
+#define SDV_MAX_FRAMES_WINDOW 8     /* setting_maxFrames=7 (settings.cpp:56); 8 for the stress config */
+
+typedef enum {
+  SDV_OK = 0, SDV_ERR_ARG = -1, SDV_ERR_CUDA = -2, SDV_ERR_NOFRAME = -3, SDV_ERR_CAPACITY = -4, SDV_ERR_STATE = -5
+} sdv_status;
+
+typedef struct sdv_ctx sdv_ctx;
+
+typedef struct { float fx, fy, cx, cy; } sdv_calib;          /* CalibHessian::value_scaledf, HessianBlocks.h:260-358 */
+
+typedef struct {                                             /* util/settings.cpp globals that reach the hot path */
+  float huberTH;                /* setting_huberTH = 6            settings.cpp:101 */
+  float coarseCutoffTH;         /* setting_coarseCutoffTH = 20    settings.cpp:112 */
+  float affineOptModeA;         /* <0 fix, >=0 optimise           settings.cpp:93 ; mode=1 -> 0 (main.cpp:453) */
+  float affineOptModeB;         /*                                settings.cpp:94 ; mode=1 -> 0 (main.cpp:454) */
+  float outlierTH;              /* setting_outlierTH = 144        settings.cpp:64 */
+  float outlierTHSumComponent;  /* = 2500                         settings.cpp:65 */
+  float idepthFixPrior;         /* = 2500                         settings.cpp */
+  int   max_ref_points;         /* capacity of a tracker reference cloud per level (0 = w*h) */
+  int   n_tracker_slots;        /* reference uses 2 (coarseTracker, coarseTracker_forNewKF; FullSystem.h); batched mode: 2 x sequences */
+  int   max_frames;             /* device-resident frame pyramids kept alive at once */
+  int   cluster_size;           /* CTAs per thread-block cluster in the device-resident LM kernel (0 = default 8) */
+} sdv_settings;
+
+void sdv_default_settings(sdv_settings* s);
+
+/* one per FullSystem (or one per GPU in batched mode) */
+int  sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings* s, int device, sdv_ctx** out);
+void sdv_destroy(sdv_ctx* c);
+const char* sdv_last_error(sdv_ctx* c);
+int  sdv_pyr_levels(int w, int h);                           /* pyrLevelsUsed rule, util/globalCalib.cpp:22-30 */
+int  sdv_sync(sdv_ctx* c);                                   /* drain the context's stream */
+
+/* ---- frames: FrameHessian::makeImages(float* color, CalibHessian*)  FullSystem/HessianBlocks.cpp:107-167 ------------
+ * builds dIp[lvl] = {I,dx,dy} and absSquaredGrad[lvl] for all levels on the device, keyed by a caller-chosen handle. */
+int  sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img_wh, float exposure);
+int  sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs_wh, const float* exposures);
+int  sdv_frame_release(sdv_ctx* c, uint64_t frame);
+/* test hook: copy one level back as AoS {I,dx,dy} (w*h*3 floats) and absSquaredGrad (w*h floats); either may be NULL */
+int  sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out);
+
+/* ---- tracker reference: CoarseTracker::makeK :77-106 is folded into sdv_create ------------------------------------
+ * CoarseTracker::setCoarseTrackingRef / setCTRefForFirstFrame  CoarseTracker.cpp:636-660 -> makeCoarseDepthL0 :258-425.
+ * The PointHessian graph walk (:264-294) stays on the host: the caller passes one row per splat, {u,v,idepth,HdiF},
+ * with round_half[i]=0 for `int(u)` (newest-KF sensor points, :270-271) or 1 for `int(u+0.5f)` (:116-117, :285-286). */
+int  sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const float* pts4, const int32_t* round_half,
+                         float ref_exposure_unused, double ref_a, double ref_b);
+/* direct injection / readback of one level's reference cloud pc_u,pc_v,pc_idepth,pc_color (tests, stress config) */
+int  sdv_tracker_set_cloud(sdv_ctx* c, int slot, uint64_t ref_frame, int lvl, int n, const float* u, const float* v,
+                           const float* idepth, const float* color, double ref_a, double ref_b);
+int  sdv_tracker_get_cloud(sdv_ctx* c, int slot, int lvl, int* n, float* u, float* v, float* idepth, float* color);
+
+/* ---- tracker residual + Gauss-Newton system (one fused kernel launch) ---------------------------------------------
+ * Vec6 CoarseTracker::calcRes(int lvl, const SE3& refToNew, AffLight aff_g2l, float cutoffTH)   CoarseTracker.cpp:486-634
+ * void CoarseTracker::calcGSSSE(int lvl, Mat88& H_out, Vec8& b_out, const SE3&, AffLight)        CoarseTracker.cpp:427-484
+ * calc_res evaluates residuals AND accumulates the 9x9 system of the same pose in one pass; calc_gs returns the
+ * (scaled, /n) H,b of the last calc_res on that slot, exactly the state calcGSSSE would read from buf_warped_*. */
+int  sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, const double T[7], double a, double b,
+                          float cutoffTH, double rs_out[6]);
+int  sdv_tracker_calc_gs(sdv_ctx* c, int slot, int lvl, double H88_out[64], double b8_out[8]);
+
+/* ---- device-resident coarse-to-fine LM ------------------------------------------------------------------------------
+ * bool CoarseTracker::trackNewestCoarse(FrameHessian*, SE3& lastToNew_out, AffLight& aff_g2l_out, int coarsestLvl,
+ *                                       Vec5 minResForAbort, Output3DWrapper*)                  CoarseTracker.cpp:662-838
+ * T_io/ab_io are in-out like lastToNew_out/aff_g2l_out (written only when the call is not aborted, as in the reference);
+ * lastRes = CoarseTracker::lastResiduals, flow = lastFlowIndicators (CoarseTracker.h:57-65). */
+typedef struct {
+  int64_t point_evals[SDV_PYR_LEVELS];   /* sum of pc_n[lvl] over all calcRes evaluations (roofline accounting) */
+  int32_t iterations[SDV_PYR_LEVELS];
+  int32_t accepts[SDV_PYR_LEVELS];
+} sdv_track_stats;
+int  sdv_tracker_track(sdv_ctx* c, int slot, uint64_t new_frame, double T_io[7], double ab_io[2], int coarsest,
+                       const double minResForAbort[5], double lastRes[5], double flow[3], int* good, sdv_track_stats* stats);
+/* batched mode (north_star: independent sequences / Monte-Carlo re-runs): n independent trackNewestCoarse calls in ONE
+ * launch, one thread-block cluster each.  Arrays are n x the single-call shapes. */
+int  sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* new_frames, double* T_io, double* ab_io,
+                             int coarsest, const double* minResForAbort, double* lastRes, double* flow, int32_t* good,
+                             sdv_track_stats* stats);
+/* device time of the last track / track_batch / calc_res launch in milliseconds (CUDA events on the context stream) */
+float sdv_last_kernel_ms(sdv_ctx* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDV_B200_H */

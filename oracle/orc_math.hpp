@@ -1,0 +1,214 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// build, link or call anything under oracle/.
+//
+// PARITY UNPINNED: the reference (ZikangYuan/SDV-LOAM) ships no tests, golden vectors or fixtures
+// for this path and cannot be built here (Eigen3, Boost, ROS, OpenCV, PCL absent),
+// so this restatement is pinned only on (i) the Sophus sample transforms of
+// thirdparty/Sophus/sophus/test_se3.cpp:43-60 through group-law properties and (ii) numpy/scipy
+// closed forms for the small dense factorizations.
+//
+// orc_math.hpp — dependency-free restatement of the L0 math substrate the hot path stands on:
+//   * fixed-size double/float helpers (replaces Eigen fixed-size algebra; Eigen3 is NOT vendored,
+//     README.md:24 "Eigen3 >= 3.2.8", version unpinned)
+//   * SE3/SO3 of Sophus v0.9a: thirdparty/Sophus/sophus/so3.hpp:343-369 (expAndTheta),
+//     :491-531 (logAndTheta), se3.hpp:131-139 (Adj), :407-430 (exp), :560-585 (log),
+//     :162-172 (fastMultiply/inverse), so3.hpp:196-202 (normalize)
+//   * Eigen::Quaternion product / _transformVector / toRotationMatrix (published Eigen algorithms)
+//   * Eigen::LDLT (pivoted, lower, unblocked) + solve, restated from the published algorithm
+//   * Eigen 3x3 cofactor inverse
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace orc {
+
+// ------------------------------------------------------------------ small dense helpers
+struct Vec3d { double v[3]; double& operator[](int i){return v[i];} double operator[](int i) const {return v[i];} };
+struct Mat33d { double m[3][3]; };
+struct Mat33f { float m[3][3]; };
+struct Vec3f { float v[3]; float& operator[](int i){return v[i];} float operator[](int i) const {return v[i];} };
+
+inline Mat33d matmul(const Mat33d& A, const Mat33d& B) {
+  Mat33d C;
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) C.m[i][j] = (A.m[i][0]*B.m[0][j] + A.m[i][1]*B.m[1][j]) + A.m[i][2]*B.m[2][j];
+  return C;
+}
+inline Mat33f matmul(const Mat33f& A, const Mat33f& B) {
+  Mat33f C;
+  for (int i=0;i<3;i++) for (int j=0;j<3;j++) C.m[i][j] = (A.m[i][0]*B.m[0][j] + A.m[i][1]*B.m[1][j]) + A.m[i][2]*B.m[2][j];
+  return C;
+}
+inline Vec3d matvec(const Mat33d& A, const Vec3d& x) {
+  Vec3d y; for (int i=0;i<3;i++) y.v[i] = (A.m[i][0]*x.v[0] + A.m[i][1]*x.v[1]) + A.m[i][2]*x.v[2]; return y;
+}
+inline Vec3f matvec(const Mat33f& A, float x0, float x1, float x2) {
+  Vec3f y; for (int i=0;i<3;i++) y.v[i] = (A.m[i][0]*x0 + A.m[i][1]*x1) + A.m[i][2]*x2; return y;
+}
+inline Mat33f castf(const Mat33d& A) { Mat33f B; for(int i=0;i<3;i++) for(int j=0;j<3;j++) B.m[i][j]=(float)A.m[i][j]; return B; }
+inline Vec3f castf(const Vec3d& a) { Vec3f b; for(int i=0;i<3;i++) b.v[i]=(float)a.v[i]; return b; }
+inline Mat33d identity3() { Mat33d I; std::memset(&I,0,sizeof(I)); I.m[0][0]=I.m[1][1]=I.m[2][2]=1; return I; }
+inline Mat33d hat(const Vec3d& w) {            // so3.hpp:423-431
+  Mat33d O; O.m[0][0]=0; O.m[0][1]=-w.v[2]; O.m[0][2]=w.v[1];
+  O.m[1][0]=w.v[2]; O.m[1][1]=0; O.m[1][2]=-w.v[0];
+  O.m[2][0]=-w.v[1]; O.m[2][1]=w.v[0]; O.m[2][2]=0; return O;
+}
+inline Vec3d cross(const Vec3d& a, const Vec3d& b) {
+  return Vec3d{{a.v[1]*b.v[2]-a.v[2]*b.v[1], a.v[2]*b.v[0]-a.v[0]*b.v[2], a.v[0]*b.v[1]-a.v[1]*b.v[0]}};
+}
+
+// Eigen compute_inverse<Matrix3,3>: cofactor expansion, result = cofactor^T * (1/det)
+template <typename T, typename M>
+inline M inverse3(const M& A) {
+  auto cof = [&](int i, int j) -> T {
+    int i1=(i+1)%3, i2=(i+2)%3, j1=(j+1)%3, j2=(j+2)%3;
+    return A.m[i1][j1]*A.m[i2][j2] - A.m[i1][j2]*A.m[i2][j1];
+  };
+  T c00=cof(0,0), c10=cof(1,0), c20=cof(2,0);
+  T det = (c00*A.m[0][0] + c10*A.m[1][0]) + c20*A.m[2][0];
+  T invdet = T(1)/det;
+  M R;
+  R.m[0][0]=c00*invdet; R.m[0][1]=c10*invdet; R.m[0][2]=c20*invdet;
+  R.m[1][0]=cof(0,1)*invdet; R.m[1][1]=cof(1,1)*invdet; R.m[1][2]=cof(2,1)*invdet;
+  R.m[2][0]=cof(0,2)*invdet; R.m[2][1]=cof(1,2)*invdet; R.m[2][2]=cof(2,2)*invdet;
+  return R;
+}
+
+// ------------------------------------------------------------------ SE3 (Sophus 0.9a semantics)
+static const double kSophusEps = 1e-10;        // sophus.hpp: SophusConstants<double>::epsilon()
+
+struct Quat { double w,x,y,z; };
+inline Quat qmul(const Quat& a, const Quat& b) {
+  return Quat{ a.w*b.w - a.x*b.x - a.y*b.y - a.z*b.z,
+               a.w*b.x + a.x*b.w + a.y*b.z - a.z*b.y,
+               a.w*b.y + a.y*b.w + a.z*b.x - a.x*b.z,
+               a.w*b.z + a.z*b.w + a.x*b.y - a.y*b.x };
+}
+inline Quat qnormalize(const Quat& q) {        // so3.hpp:196-202
+  double len = std::sqrt(q.x*q.x + q.y*q.y + q.z*q.z + q.w*q.w);
+  return Quat{q.w/len, q.x/len, q.y/len, q.z/len};
+}
+inline Vec3d qrot(const Quat& q, const Vec3d& v) {   // Eigen QuaternionBase::_transformVector
+  Vec3d qv{{q.x,q.y,q.z}};
+  Vec3d uv = cross(qv, v); uv.v[0]+=uv.v[0]; uv.v[1]+=uv.v[1]; uv.v[2]+=uv.v[2];
+  Vec3d c = cross(qv, uv);
+  return Vec3d{{ v.v[0] + q.w*uv.v[0] + c.v[0], v.v[1] + q.w*uv.v[1] + c.v[1], v.v[2] + q.w*uv.v[2] + c.v[2] }};
+}
+inline Mat33d qmat(const Quat& q) {             // Eigen QuaternionBase::toRotationMatrix
+  double tx=2*q.x, ty=2*q.y, tz=2*q.z;
+  double twx=tx*q.w, twy=ty*q.w, twz=tz*q.w;
+  double txx=tx*q.x, txy=ty*q.x, txz=tz*q.x;
+  double tyy=ty*q.y, tyz=tz*q.y, tzz=tz*q.z;
+  Mat33d R;
+  R.m[0][0]=1-(tyy+tzz); R.m[0][1]=txy-twz; R.m[0][2]=txz+twy;
+  R.m[1][0]=txy+twz; R.m[1][1]=1-(txx+tzz); R.m[1][2]=tyz-twx;
+  R.m[2][0]=txz-twy; R.m[2][1]=tyz+twx; R.m[2][2]=1-(txx+tyy);
+  return R;
+}
+// Eigen Quaternion(Matrix3) (used by SE3(R,t) constructors)
+inline Quat qfrommat(const Mat33d& M) {
+  Quat q; double t = M.m[0][0]+M.m[1][1]+M.m[2][2];
+  if (t > 0) { t = std::sqrt(t+1.0); q.w = 0.5*t; t = 0.5/t;
+    q.x=(M.m[2][1]-M.m[1][2])*t; q.y=(M.m[0][2]-M.m[2][0])*t; q.z=(M.m[1][0]-M.m[0][1])*t; }
+  else { int i=0; if (M.m[1][1]>M.m[0][0]) i=1; if (M.m[2][2]>M.m[i][i]) i=2; int j=(i+1)%3, k=(j+1)%3;
+    t = std::sqrt(M.m[i][i]-M.m[j][j]-M.m[k][k]+1.0); double qq[3]; qq[i]=0.5*t; t=0.5/t;
+    q.w=(M.m[k][j]-M.m[j][k])*t; qq[j]=(M.m[j][i]+M.m[i][j])*t; qq[k]=(M.m[k][i]+M.m[i][k])*t;
+    q.x=qq[0]; q.y=qq[1]; q.z=qq[2]; }
+  return q;
+}
+
+struct SE3 {
+  Quat q{1,0,0,0}; Vec3d t{{0,0,0}};
+  Mat33d rotationMatrix() const { return qmat(q); }
+  static SE3 fromQuatT(const Quat& q_, const Vec3d& t_) { SE3 s; s.q = qnormalize(q_); s.t = t_; return s; } // so3.hpp:630-633
+  static SE3 exp(const double a[6]) {           // se3.hpp:407-430 ; tangent = [upsilon ; omega]
+    Vec3d ups{{a[0],a[1],a[2]}}, om{{a[3],a[4],a[5]}};
+    double theta_sq = om.v[0]*om.v[0] + om.v[1]*om.v[1] + om.v[2]*om.v[2];
+    double theta = std::sqrt(theta_sq), half = 0.5*theta, imag, real;   // so3.hpp:343-369
+    if (theta < kSophusEps) { double p4 = theta_sq*theta_sq;
+      imag = 0.5 - (1.0/48.0)*theta_sq + (1.0/3840.0)*p4; real = 1.0 - 0.5*theta_sq + (1.0/384.0)*p4; }
+    else { double s = std::sin(half); imag = s/theta; real = std::cos(half); }
+    SE3 r; r.q = qnormalize(Quat{real, imag*om.v[0], imag*om.v[1], imag*om.v[2]});
+    Mat33d Om = hat(om), Om2 = matmul(Om,Om), V;
+    if (theta < kSophusEps) V = qmat(r.q);
+    else { double c1 = (1.0-std::cos(theta))/theta_sq, c2 = (theta-std::sin(theta))/(theta_sq*theta);
+      Mat33d I = identity3();
+      for (int i=0;i<3;i++) for (int j=0;j<3;j++) V.m[i][j] = I.m[i][j] + c1*Om.m[i][j] + c2*Om2.m[i][j]; }
+    r.t = matvec(V, ups); return r;
+  }
+  void log(double out[6]) const {               // se3.hpp:560-585 + so3.hpp:491-531
+    double sqn = q.x*q.x + q.y*q.y + q.z*q.z, n = std::sqrt(sqn), w = q.w, f;
+    if (n < kSophusEps) { double sw = w*w; f = 2.0/w - 2.0*sqn/(w*sw); }
+    else if (std::fabs(w) < kSophusEps) f = (w > 0 ? M_PI/n : -M_PI/n);
+    else f = 2.0*std::atan(n/w)/n;
+    double theta = f*n; Vec3d om{{f*q.x, f*q.y, f*q.z}};
+    Mat33d Om = hat(om), Om2 = matmul(Om,Om), I = identity3(), Vi;
+    double c = (std::fabs(theta) < kSophusEps) ? (1.0/12.0) : (1.0 - theta/(2.0*std::tan(theta/2.0)))/(theta*theta);
+    for (int i=0;i<3;i++) for (int j=0;j<3;j++) Vi.m[i][j] = I.m[i][j] - 0.5*Om.m[i][j] + c*Om2.m[i][j];
+    Vec3d u = matvec(Vi, t);
+    out[0]=u.v[0]; out[1]=u.v[1]; out[2]=u.v[2]; out[3]=om.v[0]; out[4]=om.v[1]; out[5]=om.v[2];
+  }
+  SE3 operator*(const SE3& o) const {           // se3.hpp:162-165,239-243,268-271
+    SE3 r; Vec3d rt = qrot(q, o.t); r.t = Vec3d{{t.v[0]+rt.v[0], t.v[1]+rt.v[1], t.v[2]+rt.v[2]}};
+    r.q = qnormalize(qmul(q, o.q)); return r;
+  }
+  SE3 inverse() const {                         // se3.hpp:169-172
+    SE3 r; r.q = Quat{q.w,-q.x,-q.y,-q.z}; Vec3d m{{-t.v[0],-t.v[1],-t.v[2]}}; r.t = qrot(r.q, m); return r;
+  }
+  void Adj(double A[6][6]) const {              // se3.hpp:131-139
+    Mat33d R = qmat(q), TR = matmul(hat(t), R);
+    for (int i=0;i<3;i++) for (int j=0;j<3;j++) { A[i][j]=R.m[i][j]; A[i+3][j+3]=R.m[i][j]; A[i][j+3]=TR.m[i][j]; A[i+3][j]=0; }
+  }
+};
+
+// ------------------------------------------------------------------ AffLight  (util/NumType.h:139-164)
+struct AffLight { double a=0, b=0; };
+inline void fromToVecExposure(float exposureF, float exposureT, AffLight g2F, AffLight g2T, double out[2]) {
+  if (exposureF==0 || exposureT==0) exposureT = exposureF = 1;
+  double a = std::exp(g2T.a - g2F.a) * exposureT / exposureF;
+  double b = g2T.b - a*g2F.b;
+  out[0]=a; out[1]=b;
+}
+
+// ------------------------------------------------------------------ Eigen::LDLT restatement (double, n<=64)
+// In-place lower unblocked LDLT with symmetric diagonal pivoting, then solve:
+//   x = P^T L^-T D^+ L^-1 P b.  A is row-major n x n (only lower triangle read).
+template <int MAXN>
+inline void ldlt_solve(int n, const double* Ain, const double* b, double* x) {
+  double A[MAXN*MAXN]; int perm[MAXN]; double tmp[MAXN];
+  for (int i=0;i<n;i++) for (int j=0;j<n;j++) A[i*MAXN+j] = Ain[i*n+j];
+  for (int k=0;k<n;k++) {
+    int piv = k; double big = std::fabs(A[k*MAXN+k]);
+    for (int i=k+1;i<n;i++) { double a = std::fabs(A[i*MAXN+i]); if (a > big) { big=a; piv=i; } }
+    perm[k] = piv;
+    if (piv != k) {
+      int s = n-piv-1;
+      for (int j=0;j<k;j++) std::swap(A[k*MAXN+j], A[piv*MAXN+j]);                 // row(k).head(k) <-> row(piv).head(k)
+      for (int i=0;i<s;i++) std::swap(A[(piv+1+i)*MAXN+k], A[(piv+1+i)*MAXN+piv]);  // col(k).tail(s) <-> col(piv).tail(s)
+      std::swap(A[k*MAXN+k], A[piv*MAXN+piv]);
+      for (int i=k+1;i<piv;i++) std::swap(A[i*MAXN+k], A[piv*MAXN+i]);
+    }
+    int rs = n-k-1;
+    if (k > 0) {
+      for (int j=0;j<k;j++) tmp[j] = A[j*MAXN+j]*A[k*MAXN+j];
+      double s=0; for (int j=0;j<k;j++) s += A[k*MAXN+j]*tmp[j];
+      A[k*MAXN+k] -= s;
+      for (int i=0;i<rs;i++) { double s2=0; for (int j=0;j<k;j++) s2 += A[(k+1+i)*MAXN+j]*tmp[j]; A[(k+1+i)*MAXN+k] -= s2; }
+    }
+    double akk = A[k*MAXN+k];
+    if (rs > 0 && std::fabs(akk) > 0) for (int i=0;i<rs;i++) A[(k+1+i)*MAXN+k] /= akk;
+  }
+  double y[MAXN];
+  for (int i=0;i<n;i++) y[i]=b[i];
+  for (int k=0;k<n;k++) std::swap(y[k], y[perm[k]]);                               // P b
+  for (int i=0;i<n;i++) { double s=y[i]; for (int j=0;j<i;j++) s -= A[i*MAXN+j]*y[j]; y[i]=s; }  // L^-1
+  double dmax=0; for (int i=0;i<n;i++) dmax = std::max(dmax, std::fabs(A[i*MAXN+i]));
+  double tol = std::max(dmax*2.220446049250313e-16, 1.0/1.7976931348623157e308);
+  for (int i=0;i<n;i++) { double d=A[i*MAXN+i]; y[i] = (std::fabs(d) > tol) ? y[i]/d : 0.0; }    // D^+
+  for (int i=n-1;i>=0;i--) { double s=y[i]; for (int j=i+1;j<n;j++) s -= A[j*MAXN+i]*y[j]; y[i]=s; } // L^-T
+  for (int k=n-1;k>=0;k--) std::swap(y[k], y[perm[k]]);                            // P^T
+  for (int i=0;i<n;i++) x[i]=y[i];
+}
+
+} // namespace orc

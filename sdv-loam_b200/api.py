@@ -1,0 +1,191 @@
+"""ctypes host mirror of the reference call surface over libsdv_b200.so (include/sdv_b200.h).
+
+Classes keep the reference's member names and argument meaning so parity tests read like calls into the original:
+  Context                      one FullSystem's device state (sdv_create/sdv_destroy)
+  Context.makeImages           FrameHessian::makeImages            src/FullSystem/HessianBlocks.cpp:107-167
+  CoarseTracker.setCoarseTrackingRef / calcRes / calcGSSSE / trackNewestCoarse
+                               src/FullSystem/CoarseTracker.cpp:649-660, 486-634, 427-484, 662-838
+There is no CPU fallback: if the library cannot be loaded this module raises at import time.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import numpy as np
+from .build import library_path
+
+PYR_LEVELS = 6
+
+
+class sdv_calib(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class sdv_settings(C.Structure):
+    _fields_ = [("huberTH", C.c_float), ("coarseCutoffTH", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float),
+                ("outlierTH", C.c_float), ("outlierTHSumComponent", C.c_float), ("idepthFixPrior", C.c_float),
+                ("max_ref_points", C.c_int), ("n_tracker_slots", C.c_int), ("max_frames", C.c_int), ("cluster_size", C.c_int)]
+
+
+class sdv_track_stats(C.Structure):
+    _fields_ = [("point_evals", C.c_int64 * PYR_LEVELS), ("iterations", C.c_int32 * PYR_LEVELS), ("accepts", C.c_int32 * PYR_LEVELS)]
+
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+
+def _load():
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    L = C.CDLL(path)
+    L.sdv_default_settings.argtypes = [C.POINTER(sdv_settings)]
+    L.sdv_create.argtypes = [C.POINTER(sdv_calib), C.c_int, C.c_int, C.c_int, C.POINTER(sdv_settings), C.c_int, C.POINTER(_vp)]
+    L.sdv_destroy.argtypes = [_vp]; L.sdv_destroy.restype = None
+    L.sdv_last_error.argtypes = [_vp]; L.sdv_last_error.restype = C.c_char_p
+    L.sdv_pyr_levels.argtypes = [C.c_int, C.c_int]
+    L.sdv_sync.argtypes = [_vp]
+    L.sdv_frame_upload.argtypes = [_vp, C.c_uint64, _vp, C.c_float]
+    L.sdv_frame_upload_batch.argtypes = [_vp, C.c_int, _u64p, C.POINTER(_vp), _f32p]
+    L.sdv_frame_release.argtypes = [_vp, C.c_uint64]
+    L.sdv_frame_download.argtypes = [_vp, C.c_uint64, C.c_int, _vp, _vp]
+    L.sdv_tracker_set_ref.argtypes = [_vp, C.c_int, C.c_uint64, C.c_int, _f32p, _i32p, C.c_float, C.c_double, C.c_double]
+    L.sdv_tracker_set_cloud.argtypes = [_vp, C.c_int, C.c_uint64, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_double, C.c_double]
+    L.sdv_tracker_get_cloud.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), _vp, _vp, _vp, _vp]
+    L.sdv_tracker_calc_res.argtypes = [_vp, C.c_int, C.c_uint64, C.c_int, _f64p, C.c_double, C.c_double, C.c_float, _f64p]
+    L.sdv_tracker_calc_gs.argtypes = [_vp, C.c_int, C.c_int, _f64p, _f64p]
+    L.sdv_tracker_track.argtypes = [_vp, C.c_int, C.c_uint64, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(sdv_track_stats)]
+    L.sdv_tracker_track_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, C.c_int, _vp, _f64p, _f64p, _i32p, C.POINTER(sdv_track_stats)]
+    L.sdv_last_kernel_ms.argtypes = [_vp]; L.sdv_last_kernel_ms.restype = C.c_float
+    return L
+
+
+LIB = _load()
+
+
+class SdvError(RuntimeError):
+    pass
+
+
+def pyr_levels(w: int, h: int) -> int:
+    return LIB.sdv_pyr_levels(w, h)
+
+
+def default_settings() -> sdv_settings:
+    s = sdv_settings(); LIB.sdv_default_settings(C.byref(s)); return s
+
+
+class Context:
+    def __init__(self, K, w: int, h: int, levels: int | None = None, device: int = 0, **settings):
+        self.w, self.h = w, h
+        self.levels = levels if levels is not None else pyr_levels(w, h)
+        s = default_settings()
+        for k, v in settings.items():
+            if not hasattr(s, k):
+                raise TypeError(f"unknown setting {k}")
+            setattr(s, k, v)
+        self.settings = s
+        cal = sdv_calib(*[float(k) for k in K])
+        self.p = _vp()
+        rc = LIB.sdv_create(C.byref(cal), w, h, self.levels, C.byref(s), device, C.byref(self.p))
+        if rc != 0:
+            msg = LIB.sdv_last_error(self.p).decode() if self.p else "no CUDA device / library"
+            raise SdvError(f"sdv_create failed ({rc}): {msg}")
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SdvError(f"sdv error {rc}: {LIB.sdv_last_error(self.p).decode()}")
+
+    def close(self):
+        if getattr(self, "p", None):
+            LIB.sdv_destroy(self.p); self.p = None
+
+    def __del__(self):
+        self.close()
+
+    def sync(self):
+        self._ck(LIB.sdv_sync(self.p))
+
+    # FrameHessian::makeImages
+    def makeImages(self, frame_id: int, color, exposure: float = 1.0):
+        color = np.ascontiguousarray(color, np.float32)
+        assert color.shape == (self.h, self.w)
+        self._ck(LIB.sdv_frame_upload(self.p, frame_id, color.ctypes.data, exposure))
+
+    def makeImagesBatch(self, frame_ids, host_ptrs, exposures=None):
+        """host_ptrs: list of integer addresses of (h,w) float32 host buffers (pinned for full-rate H2D)."""
+        n = len(frame_ids)
+        ids = np.ascontiguousarray(frame_ids, np.uint64)
+        arr = (_vp * n)(*host_ptrs)
+        ex = np.ones(n, np.float32) if exposures is None else np.ascontiguousarray(exposures, np.float32)
+        self._ck(LIB.sdv_frame_upload_batch(self.p, n, ids, arr, ex))
+
+    def releaseFrame(self, frame_id: int):
+        self._ck(LIB.sdv_frame_release(self.p, frame_id))
+
+    def frameLevel(self, frame_id: int, lvl: int):
+        w, h = self.w >> lvl, self.h >> lvl
+        dI = np.zeros((h, w, 3), np.float32); ab = np.zeros((h, w), np.float32)
+        self._ck(LIB.sdv_frame_download(self.p, frame_id, lvl, dI.ctypes.data, ab.ctypes.data))
+        return dI, ab
+
+    def last_kernel_ms(self) -> float:
+        return float(LIB.sdv_last_kernel_ms(self.p))
+
+    def trackBatch(self, slots, frame_ids, T, ab, coarsest=None, minRes=None):
+        """n independent trackNewestCoarse calls in one launch.  T (n,7), ab (n,2) are updated in place."""
+        n = len(slots)
+        slots = np.ascontiguousarray(slots, np.int32); ids = np.ascontiguousarray(frame_ids, np.uint64)
+        assert T.dtype == np.float64 and T.shape == (n, 7) and T.flags.c_contiguous
+        assert ab.dtype == np.float64 and ab.shape == (n, 2) and ab.flags.c_contiguous
+        lastRes = np.zeros((n, 5)); flow = np.zeros((n, 3)); good = np.zeros(n, np.int32)
+        stats = (sdv_track_stats * n)()
+        mr = None if minRes is None else np.ascontiguousarray(minRes, np.float64).ctypes.data
+        self._ck(LIB.sdv_tracker_track_batch(self.p, n, slots, ids, T, ab, self.levels - 1 if coarsest is None else coarsest,
+                                             mr, lastRes, flow, good, stats))
+        evals = np.array([[s.point_evals[l] for l in range(PYR_LEVELS)] for s in stats], np.int64)
+        its = np.array([[s.iterations[l] for l in range(PYR_LEVELS)] for s in stats], np.int32)
+        acc = np.array([[s.accepts[l] for l in range(PYR_LEVELS)] for s in stats], np.int32)
+        return dict(good=good.astype(bool), lastResiduals=lastRes, flow=flow, evals=evals, iterations=its, accepts=acc)
+
+
+class CoarseTracker:
+    """Mirror of sdv_loam::CoarseTracker (FullSystem/CoarseTracker.h:16-133) bound to one tracker slot of a Context."""
+
+    def __init__(self, ctx: Context, slot: int = 0):
+        self.ctx, self.slot = ctx, slot
+
+    def setCoarseTrackingRef(self, ref_frame_id: int, pts, round_half, ref_a: float = 0.0, ref_b: float = 0.0):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4); rh = np.ascontiguousarray(round_half, np.int32)
+        self.ctx._ck(LIB.sdv_tracker_set_ref(self.ctx.p, self.slot, ref_frame_id, len(pts), pts, rh, 0.0, ref_a, ref_b))
+
+    def setCloud(self, ref_frame_id: int, lvl: int, u, v, idepth, color, ref_a: float = 0.0, ref_b: float = 0.0):
+        a = [np.ascontiguousarray(x, np.float32) for x in (u, v, idepth, color)]
+        self.ctx._ck(LIB.sdv_tracker_set_cloud(self.ctx.p, self.slot, ref_frame_id, lvl, len(a[0]), *a, ref_a, ref_b))
+
+    def cloud(self, lvl: int):
+        n = C.c_int(0)
+        self.ctx._ck(LIB.sdv_tracker_get_cloud(self.ctx.p, self.slot, lvl, C.byref(n), None, None, None, None))
+        a = [np.zeros(max(n.value, 1), np.float32) for _ in range(4)]
+        self.ctx._ck(LIB.sdv_tracker_get_cloud(self.ctx.p, self.slot, lvl, C.byref(n), *[x.ctypes.data for x in a]))
+        return [x[:n.value] for x in a]
+
+    def calcRes(self, new_frame_id: int, lvl: int, T7, a: float, b: float, cutoffTH: float):
+        rs = np.zeros(6)
+        self.ctx._ck(LIB.sdv_tracker_calc_res(self.ctx.p, self.slot, new_frame_id, lvl, np.ascontiguousarray(T7, np.float64), a, b, cutoffTH, rs))
+        return rs
+
+    def calcGSSSE(self, lvl: int):
+        H = np.zeros(64); b = np.zeros(8)
+        self.ctx._ck(LIB.sdv_tracker_calc_gs(self.ctx.p, self.slot, lvl, H, b))
+        return H.reshape(8, 8), b
+
+    def trackNewestCoarse(self, new_frame_id: int, T7, ab, coarsest=None, minRes=None):
+        T = np.array(T7, np.float64).reshape(1, 7); abv = np.array(ab, np.float64).reshape(1, 2)
+        mr = None if minRes is None else np.asarray(minRes, np.float64).reshape(1, 5)
+        r = self.ctx.trackBatch([self.slot], [new_frame_id], T, abv, coarsest, mr)
+        return dict(good=bool(r["good"][0]), T=T[0], ab=abv[0], lastResiduals=r["lastResiduals"][0], flow=r["flow"][0],
+                    evals=r["evals"][0], iterations=r["iterations"][0], accepts=r["accepts"][0])

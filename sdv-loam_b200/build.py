@@ -1,0 +1,35 @@
+"""In-tree build of libsdv_b200.so (nvcc cross-compiles sm_100a without a GPU)."""
+from __future__ import annotations
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libsdv_b200.so")
+
+
+def _stale() -> bool:
+    so = library_path()
+    if not os.path.exists(so):
+        return True
+    t = os.path.getmtime(so)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps.append(os.path.join(_HERE, "..", "include", "sdv_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False) -> str:
+    """Compile every CUDA source for sm_100a (-gencode arch=compute_100a,code=sm_100a -lineinfo) if a toolchain exists."""
+    if force or _stale():
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        if not os.path.exists(nvcc):
+            if os.path.exists(library_path()):
+                return library_path()      # GPU box without rebuild need: use the prebuilt in-tree .so
+            raise RuntimeError("nvcc not found and libsdv_b200.so is not built")
+        if force:
+            subprocess.check_call(["make", "-C", CSRC, "-s", "clean"])
+        subprocess.check_call(["make", "-C", CSRC, "-s", f"NVCC={nvcc}"])
+    return library_path()

@@ -1,0 +1,319 @@
+// sdv_capi.cu — context + extern "C" boundary (include/sdv_b200.h).  Host logic only; all numerics run in the kernels of
+// sdv_kernels.cu / sdv_ba_kernels.cu.  There is deliberately NO CPU fallback: every entry point fails with SDV_ERR_CUDA when
+// the device path is unavailable.
+#include "../../include/sdv_b200.h"
+#include "sdv_ctx.cuh"
+#include <cstdio>
+#include <cstring>
+#include <cstdarg>
+
+using namespace sdv;
+
+namespace sdv {
+int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...) {
+  if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof(c->err), fmt, ap); va_end(ap); }
+  return code;
+}
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(c, SDV_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+extern "C" {
+
+void sdv_default_settings(sdv_settings* s) {
+  s->huberTH = 6; s->coarseCutoffTH = 20; s->affineOptModeA = 0; s->affineOptModeB = 0;
+  s->outlierTH = 12*12; s->outlierTHSumComponent = 50*50; s->idepthFixPrior = 50*50;
+  s->max_ref_points = 0; s->n_tracker_slots = 2; s->max_frames = 16; s->cluster_size = 8;
+}
+
+int sdv_pyr_levels(int w, int h) {               // util/globalCalib.cpp:22-30
+  int wl = w, hl = h, used = 1;
+  while (wl%2==0 && hl%2==0 && wl*hl > 5000 && used < SDV_PYR_LEVELS) { wl/=2; hl/=2; used++; }
+  return used;
+}
+
+const char* sdv_last_error(sdv_ctx* c) { return c ? c->err : "null context"; }
+
+static void make_geom(sdv_ctx* c, const sdv_calib* K) {   // CoarseTracker::makeK (CoarseTracker.cpp:77-106)
+  float fx[SDV_PYR_LEVELS], fy[SDV_PYR_LEVELS], cx[SDV_PYR_LEVELS], cy[SDV_PYR_LEVELS];
+  fx[0]=K->fx; fy[0]=K->fy; cx[0]=K->cx; cy[0]=K->cy;
+  for (int l=1;l<c->levels;l++) {
+    fx[l] = fx[l-1]*0.5; fy[l] = fy[l-1]*0.5;
+    cx[l] = (cx[0]+0.5)/((int)1<<l) - 0.5; cy[l] = (cy[0]+0.5)/((int)1<<l) - 0.5;
+  }
+  for (int l=0;l<c->levels;l++) {
+    LevelGeom& g = c->tc.geom[l]; g.w = c->w>>l; g.h = c->h>>l; g.fx=fx[l]; g.fy=fy[l]; g.cx=cx[l]; g.cy=cy[l];
+    float Km[9] = {fx[l],0,cx[l], 0,fy[l],cy[l], 0,0,1}; inv3f(Km, g.Ki);
+  }
+}
+
+int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings* s_in, int device, sdv_ctx** out) {
+  if (!K || !out || w <= 0 || h <= 0 || levels < 1 || levels > SDV_PYR_LEVELS) return SDV_ERR_ARG;
+  int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) return SDV_ERR_CUDA;
+  sdv_ctx* c = new sdv_ctx(); *out = c; c->err[0] = 0;
+  sdv_settings s; if (s_in) s = *s_in; else sdv_default_settings(&s);
+  if (s.n_tracker_slots < 1) s.n_tracker_slots = 2;
+  if (s.max_frames < 2) s.max_frames = 2;
+  if (s.cluster_size <= 0) s.cluster_size = 8;
+  if (s.cluster_size > 16) s.cluster_size = 16;
+  c->set = s; c->device = device; c->w = w; c->h = h; c->levels = levels;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+  memset(&c->tc, 0, sizeof(c->tc));
+  c->tc.levels = levels; c->tc.huberTH = s.huberTH; c->tc.coarseCutoffTH = s.coarseCutoffTH;
+  c->tc.affineOptModeA = s.affineOptModeA; c->tc.affineOptModeB = s.affineOptModeB;
+  make_geom(c, K);
+  CK(cudaMalloc(&c->tc_dev, sizeof(TrackConst)));
+  CK(cudaMemcpy(c->tc_dev, &c->tc, sizeof(TrackConst), cudaMemcpyHostToDevice));
+  // frame pool
+  size_t texels = 0; for (int l=0;l<levels;l++) { c->lvl_off[l] = texels; texels += (size_t)(w>>l)*(h>>l); }
+  c->frame_texels = texels;
+  c->frames.resize(s.max_frames);
+  for (auto& f : c->frames) { f.used = false; CK(cudaMalloc(&f.base, texels*sizeof(float4))); for (int l=0;l<levels;l++) f.lvl[l] = f.base + c->lvl_off[l]; }
+  CK(cudaMalloc(&c->pyr_scratch, (size_t)w*h*sizeof(float)));
+  // tracker slots
+  c->slots.resize(s.n_tracker_slots);
+  for (auto& t : c->slots) {
+    for (int l=0;l<levels;l++) {
+      size_t cap = (size_t)(w>>l)*(h>>l); if (s.max_ref_points > 0 && (size_t)s.max_ref_points < cap) cap = s.max_ref_points;
+      t.cap[l] = (int)cap; t.npts[l] = 0; CK(cudaMalloc(&t.pts[l], cap*sizeof(float4)));
+    }
+    t.ref_frame = ~0ull; t.has_totals = false;
+  }
+  // step-kernel reduction buffers
+  CK(cudaMalloc(&c->partials, (size_t)step_kernel_max_grid()*kNAcc*sizeof(double)));
+  CK(cudaMalloc(&c->ticket, sizeof(unsigned int))); CK(cudaMemset(c->ticket, 0, sizeof(unsigned int)));
+  CK(cudaMalloc(&c->totals_dev, kNAcc*sizeof(double)));
+  CK(cudaMallocHost(&c->totals_host, kNAcc*sizeof(double)));
+  // coarse-depth work buffers
+  for (int l=0;l<levels;l++) {
+    size_t n = (size_t)(w>>l)*(h>>l);
+    CK(cudaMalloc(&c->cd_id[l], n*sizeof(float))); CK(cudaMalloc(&c->cd_ws[l], n*sizeof(float)));
+    CK(cudaMalloc(&c->cd_id2[l], n*sizeof(float))); CK(cudaMalloc(&c->cd_ws2[l], n*sizeof(float)));
+  }
+  CK(cudaMalloc(&c->cd_owner, (size_t)w*h*sizeof(int)));
+  CK(cudaMalloc(&c->cd_counts, (size_t)(cd_num_blocks(w,h)+1)*sizeof(int)));
+  CK(cudaMalloc(&c->cd_scalars, 8*sizeof(int)));
+  CK(cudaMallocHost(&c->cd_scalars_host, 8*sizeof(int)));
+  c->cd_cap = 0; c->cd_pts4 = nullptr; c->cd_round = nullptr; c->cd_splats = nullptr; c->cd_done = nullptr;
+  c->jobs_cap = 0; c->jobs_dev = nullptr; c->jobs_host = nullptr;
+  c->stage_cap = 0; c->last_ms = 0;
+  return SDV_OK;
+}
+
+void sdv_destroy(sdv_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device); cudaStreamSynchronize(c->st);
+  for (auto& f : c->frames) cudaFree(f.base);
+  for (auto& t : c->slots) for (int l=0;l<c->levels;l++) cudaFree(t.pts[l]);
+  for (int l=0;l<c->levels;l++) { cudaFree(c->cd_id[l]); cudaFree(c->cd_ws[l]); cudaFree(c->cd_id2[l]); cudaFree(c->cd_ws2[l]); }
+  cudaFree(c->cd_owner); cudaFree(c->cd_counts); cudaFree(c->cd_scalars); cudaFreeHost(c->cd_scalars_host);
+  cudaFree(c->cd_pts4); cudaFree(c->cd_round); cudaFree(c->cd_splats); cudaFree(c->cd_done);
+  cudaFree(c->pyr_scratch); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
+  cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
+  for (auto p : c->stage) cudaFree(p);
+  ba_destroy(c);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->st);
+  delete c;
+}
+
+int sdv_sync(sdv_ctx* c) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
+float sdv_last_kernel_ms(sdv_ctx* c) { return c ? c->last_ms : 0.f; }
+
+// ------------------------------------------------------------------------------------------------ frames
+static FrameDev* find_frame(sdv_ctx* c, uint64_t id) { auto it = c->frame_index.find(id); return it == c->frame_index.end() ? nullptr : &c->frames[it->second]; }
+
+static int ensure_stage(sdv_ctx* c, int n) {
+  while ((int)c->stage.size() < n) { float* p = nullptr; CK(cudaMalloc(&p, (size_t)c->w*c->h*sizeof(float))); c->stage.push_back(p); }
+  return SDV_OK;
+}
+
+int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs, const float* exposures) {
+  if (!c || n < 0 || !frames || !imgs) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_stage(c, n); if (rc) return rc;
+  for (int k=0;k<n;k++) {
+    int idx = -1;
+    auto it = c->frame_index.find(frames[k]);
+    if (it != c->frame_index.end()) idx = it->second;
+    else { for (size_t i=0;i<c->frames.size();i++) if (!c->frames[i].used) { idx = (int)i; break; } }
+    if (idx < 0) return ctx_fail(c, SDV_ERR_CAPACITY, "frame pool exhausted (max_frames=%d)", (int)c->frames.size());
+    FrameDev& f = c->frames[idx]; f.used = true; f.id = frames[k]; f.exposure = exposures ? exposures[k] : 1.0f; c->frame_index[frames[k]] = idx;
+    CK(cudaMemcpyAsync(c->stage[k], imgs[k], (size_t)c->w*c->h*sizeof(float), cudaMemcpyHostToDevice, c->st));
+    launch_pyramid(c->stage[k], c->pyr_scratch, f.lvl, c->w, c->h, c->levels, c->st);
+  }
+  CK(cudaGetLastError());
+  return SDV_OK;
+}
+int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposure) {
+  const float* imgs[1] = {img}; return sdv_frame_upload_batch(c, 1, &frame, imgs, &exposure);
+}
+int sdv_frame_release(sdv_ctx* c, uint64_t frame) {
+  if (!c) return SDV_ERR_ARG;
+  auto it = c->frame_index.find(frame); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
+  c->frames[it->second].used = false; c->frame_index.erase(it); return SDV_OK;
+}
+int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out) {
+  if (!c || lvl < 0 || lvl >= c->levels) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  FrameDev* f = find_frame(c, frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
+  int n = (c->w>>lvl)*(c->h>>lvl); float *d3 = nullptr, *da = nullptr;
+  if (dI3_out) CK(cudaMalloc(&d3, (size_t)3*n*sizeof(float)));
+  if (abs_out) CK(cudaMalloc(&da, (size_t)n*sizeof(float)));
+  launch_unpack_level(f->lvl[lvl], d3, da, n, c->st);
+  if (d3) CK(cudaMemcpyAsync(dI3_out, d3, (size_t)3*n*sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  if (da) CK(cudaMemcpyAsync(abs_out, da, (size_t)n*sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  cudaFree(d3); cudaFree(da);
+  return SDV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ tracker reference
+int sdv_tracker_set_cloud(sdv_ctx* c, int slot, uint64_t ref_frame, int lvl, int n, const float* u, const float* v,
+                          const float* idepth, const float* color, double ref_a, double ref_b) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size() || lvl < 0 || lvl >= c->levels || n < 0) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  TrackerSlot& t = c->slots[slot];
+  if (n > t.cap[lvl]) return ctx_fail(c, SDV_ERR_CAPACITY, "cloud of %d points exceeds capacity %d", n, t.cap[lvl]);
+  FrameDev* f = find_frame(c, ref_frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown ref frame");
+  float* tmp = nullptr; CK(cudaMalloc(&tmp, (size_t)4*(n+1)*sizeof(float)));
+  const float* src[4] = {u, v, idepth, color};
+  for (int k=0;k<4;k++) CK(cudaMemcpyAsync(tmp + (size_t)k*n, src[k], (size_t)n*sizeof(float), cudaMemcpyHostToDevice, c->st));
+  launch_pack_cloud(tmp, tmp+n, tmp+2*(size_t)n, tmp+3*(size_t)n, n, t.pts[lvl], c->st);
+  CK(cudaStreamSynchronize(c->st)); cudaFree(tmp);
+  t.npts[lvl] = n; t.ref_frame = ref_frame; t.ref_a = ref_a; t.ref_b = ref_b; t.refExposure = f->exposure; t.has_totals = false;
+  return SDV_OK;
+}
+
+int sdv_tracker_get_cloud(sdv_ctx* c, int slot, int lvl, int* n_out, float* u, float* v, float* idepth, float* color) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size() || lvl < 0 || lvl >= c->levels || !n_out) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  TrackerSlot& t = c->slots[slot]; int n = t.npts[lvl]; *n_out = n;
+  if (!u || n == 0) return SDV_OK;
+  std::vector<float4> h(n);
+  CK(cudaMemcpyAsync(h.data(), t.pts[lvl], (size_t)n*sizeof(float4), cudaMemcpyDeviceToHost, c->st)); CK(cudaStreamSynchronize(c->st));
+  for (int i=0;i<n;i++) { u[i]=h[i].x; v[i]=h[i].y; idepth[i]=h[i].z; color[i]=h[i].w; }
+  return SDV_OK;
+}
+
+int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const float* pts4, const int32_t* round_half,
+                        float /*unused*/, double ref_a, double ref_b) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size() || n < 0 || (n > 0 && (!pts4 || !round_half))) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  TrackerSlot& t = c->slots[slot];
+  FrameDev* f = find_frame(c, ref_frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown ref frame");
+  for (int i=0;i<n;i++) {                                   // the reference would write out of bounds here; we refuse instead
+    int u = round_half[i] ? (int)(pts4[4*i]+0.5f) : (int)pts4[4*i], v = round_half[i] ? (int)(pts4[4*i+1]+0.5f) : (int)pts4[4*i+1];
+    if (u < 0 || v < 0 || u >= c->w || v >= c->h) return ctx_fail(c, SDV_ERR_ARG, "splat %d (%d,%d) outside the image", i, u, v);
+  }
+  if (n > c->cd_cap) {
+    cudaFree(c->cd_pts4); cudaFree(c->cd_round); cudaFree(c->cd_splats); cudaFree(c->cd_done);
+    c->cd_cap = n + n/2 + 1024;
+    CK(cudaMalloc(&c->cd_pts4, (size_t)4*c->cd_cap*sizeof(float))); CK(cudaMalloc(&c->cd_round, (size_t)c->cd_cap*sizeof(int)));
+    CK(cudaMalloc(&c->cd_splats, (size_t)c->cd_cap*sizeof(float4))); CK(cudaMalloc(&c->cd_done, (size_t)c->cd_cap*sizeof(int)));
+  }
+  const int w = c->w, h = c->h;
+  CK(cudaMemsetAsync(c->cd_id[0], 0, (size_t)w*h*sizeof(float), c->st));
+  CK(cudaMemsetAsync(c->cd_ws[0], 0, (size_t)w*h*sizeof(float), c->st));
+  if (n > 0) {
+    CK(cudaMemcpyAsync(c->cd_pts4, pts4, (size_t)4*n*sizeof(float), cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(c->cd_round, round_half, (size_t)n*sizeof(int), cudaMemcpyHostToDevice, c->st));
+    launch_cd_prep(c->cd_pts4, c->cd_round, n, w, c->cd_splats, c->cd_done, c->st);
+    for (int round = 0; round < 64; round++) {              // usually 1-3 rounds: one per multiplicity of colliding splats
+      CK(cudaMemsetAsync(c->cd_scalars, 0, sizeof(int), c->st));
+      launch_cd_round(c->cd_splats, n, c->cd_done, c->cd_owner, c->cd_id[0], c->cd_ws[0], c->cd_scalars, c->st);
+      CK(cudaMemcpyAsync(c->cd_scalars_host, c->cd_scalars, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+      CK(cudaStreamSynchronize(c->st));
+      if (c->cd_scalars_host[0] == 0) break;
+    }
+  }
+  for (int l=1;l<c->levels;l++) launch_cd_pool(c->cd_id[l-1], c->cd_ws[l-1], c->cd_id[l], c->cd_ws[l], w>>l, h>>l, w>>(l-1), c->st);
+  for (int l=0;l<c->levels;l++) {
+    launch_cd_dilate(c->cd_id[l], c->cd_ws[l], c->cd_id2[l], c->cd_ws2[l], w>>l, h>>l, l < 2 ? 1 : 0, c->st);
+    launch_cd_compact(c->cd_id2[l], c->cd_ws2[l], f->lvl[l], w>>l, h>>l, c->cd_counts, c->cd_scalars + 1 + l, t.pts[l], c->st);
+  }
+  CK(cudaMemcpyAsync(c->cd_scalars_host, c->cd_scalars, 8*sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  CK(cudaGetLastError());
+  for (int l=0;l<c->levels;l++) {
+    t.npts[l] = c->cd_scalars_host[1+l];
+    if (t.npts[l] > t.cap[l]) return ctx_fail(c, SDV_ERR_CAPACITY, "level %d cloud (%d) exceeds capacity %d", l, t.npts[l], t.cap[l]);
+  }
+  t.ref_frame = ref_frame; t.ref_a = ref_a; t.ref_b = ref_b; t.refExposure = f->exposure; t.has_totals = false;
+  return SDV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ calcRes / calcGSSSE
+int sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, const double T[7], double a, double b, float cutoffTH, double rs_out[6]) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size() || lvl < 0 || lvl >= c->levels || !T || !rs_out) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  TrackerSlot& t = c->slots[slot];
+  FrameDev* f = find_frame(c, new_frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown new frame");
+  if (t.ref_frame == ~0ull) return ctx_fail(c, SDV_ERR_STATE, "tracker slot %d has no reference", slot);
+  EvalParams ep; make_eval_params(se3_from7(T), a, b, t.refExposure, f->exposure, t.ref_a, t.ref_b, c->tc.geom[lvl], lvl, cutoffTH, c->tc.huberTH, ep);
+  CK(cudaEventRecord(c->ev0, c->st));
+  launch_coarse_res_gs(t.pts[lvl], t.npts[lvl], f->lvl[lvl], c->tc.geom[lvl], ep, c->partials, c->ticket, c->totals_dev, c->st);
+  CK(cudaEventRecord(c->ev1, c->st));
+  CK(cudaMemcpyAsync(c->totals_host, c->totals_dev, kNAcc*sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  memcpy(t.totals, c->totals_host, sizeof(t.totals)); t.has_totals = true;
+  finalize_res(t.totals, rs_out);
+  return SDV_OK;
+}
+int sdv_tracker_calc_gs(sdv_ctx* c, int slot, int /*lvl*/, double H[64], double b[8]) {
+  if (!c || slot < 0 || slot >= (int)c->slots.size() || !H || !b) return SDV_ERR_ARG;
+  TrackerSlot& t = c->slots[slot];
+  if (!t.has_totals) return ctx_fail(c, SDV_ERR_STATE, "calc_gs before calc_res on slot %d", slot);
+  finalize_gs(t.totals, H, b);
+  return SDV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trackNewestCoarse
+int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* new_frames, double* T_io, double* ab_io, int coarsest,
+                            const double* minRes, double* lastRes, double* flow, int32_t* good, sdv_track_stats* stats) {
+  if (!c || n <= 0 || !slots || !new_frames || !T_io || !ab_io || coarsest < 0 || coarsest >= c->levels || coarsest >= 5) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  if (n > c->jobs_cap) {
+    cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host); c->jobs_cap = n;
+    CK(cudaMalloc(&c->jobs_dev, (size_t)n*sizeof(TrackJob))); CK(cudaMallocHost(&c->jobs_host, (size_t)n*sizeof(TrackJob)));
+  }
+  for (int k=0;k<n;k++) {
+    if (slots[k] < 0 || slots[k] >= (int)c->slots.size()) return SDV_ERR_ARG;
+    TrackerSlot& t = c->slots[slots[k]];
+    FrameDev* f = find_frame(c, new_frames[k]); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown new frame (job %d)", k);
+    if (t.ref_frame == ~0ull) return ctx_fail(c, SDV_ERR_STATE, "tracker slot %d has no reference", slots[k]);
+    TrackJob& J = c->jobs_host[k]; memset(&J, 0, sizeof(J));
+    for (int l=0;l<c->levels;l++) { J.img[l] = f->lvl[l]; J.pts[l] = t.pts[l]; J.npts[l] = t.npts[l]; }
+    J.refExposure = t.refExposure; J.newExposure = f->exposure; J.ref_a = t.ref_a; J.ref_b = t.ref_b;
+    for (int i=0;i<7;i++) J.T[i] = T_io[7*k+i];
+    J.ab[0] = ab_io[2*k]; J.ab[1] = ab_io[2*k+1];
+    for (int i=0;i<5;i++) J.minRes[i] = minRes ? minRes[5*k+i] : nan("");
+    J.coarsest = coarsest;
+  }
+  CK(cudaMemcpyAsync(c->jobs_dev, c->jobs_host, (size_t)n*sizeof(TrackJob), cudaMemcpyHostToDevice, c->st));
+  CK(cudaEventRecord(c->ev0, c->st));
+  CK(launch_track_cluster(c->jobs_dev, n, c->tc_dev, c->set.cluster_size, c->st));
+  CK(cudaEventRecord(c->ev1, c->st));
+  CK(cudaMemcpyAsync(c->jobs_host, c->jobs_dev, (size_t)n*sizeof(TrackJob), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  for (int k=0;k<n;k++) {
+    const TrackJob& J = c->jobs_host[k];
+    for (int i=0;i<7;i++) T_io[7*k+i] = J.T[i];
+    ab_io[2*k] = J.ab[0]; ab_io[2*k+1] = J.ab[1];
+    if (lastRes) for (int i=0;i<5;i++) lastRes[5*k+i] = J.lastRes[i];
+    if (flow) for (int i=0;i<3;i++) flow[3*k+i] = J.flow[i];
+    if (good) good[k] = J.good;
+    if (stats) for (int l=0;l<SDV_PYR_LEVELS;l++) { stats[k].point_evals[l] = J.point_evals[l]; stats[k].iterations[l] = J.iterations[l]; stats[k].accepts[l] = J.accepts[l]; }
+  }
+  return SDV_OK;
+}
+int sdv_tracker_track(sdv_ctx* c, int slot, uint64_t new_frame, double T_io[7], double ab_io[2], int coarsest, const double minRes[5],
+                      double lastRes[5], double flow[3], int* good, sdv_track_stats* stats) {
+  int32_t s = slot, g = 0;
+  int rc = sdv_tracker_track_batch(c, 1, &s, &new_frame, T_io, ab_io, coarsest, minRes, lastRes, flow, &g, stats);
+  if (good) *good = g; return rc;
+}
+
+} // extern "C"

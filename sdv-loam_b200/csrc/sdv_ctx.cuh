@@ -1,0 +1,43 @@
+// sdv_ctx.cuh — the context object behind the opaque sdv_ctx handle (host bookkeeping only).
+#pragma once
+#include <vector>
+#include <unordered_map>
+#include "sdv_kernels.cuh"
+#include "../../include/sdv_b200.h"
+
+namespace sdv {
+
+struct FrameDev { uint64_t id; float4* base; float4* lvl[kLevels]; float exposure; bool used; };
+
+struct TrackerSlot {                      // one CoarseTracker instance (reference keeps two: FullSystem.h coarseTracker / coarseTracker_forNewKF)
+  float4* pts[kLevels]; int npts[kLevels]; int cap[kLevels];
+  uint64_t ref_frame; float refExposure; double ref_a, ref_b;   // lastRef, lastRef_aff_g2l
+  double totals[kNAcc]; bool has_totals;                        // reduced sums of the last calc_res (what calcGSSSE reads from buf_warped_*)
+};
+
+struct BAState;                           // sdv_ba.cuh
+
+} // namespace sdv
+
+struct sdv_ctx {
+  int device; cudaStream_t st; cudaEvent_t ev0, ev1;
+  int w, h, levels; sdv_settings set;
+  sdv::TrackConst tc; sdv::TrackConst* tc_dev;
+  size_t lvl_off[sdv::kLevels]; size_t frame_texels;
+  std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
+  std::vector<float*> stage; int stage_cap; float* pyr_scratch;
+  std::vector<sdv::TrackerSlot> slots;
+  double* partials; unsigned int* ticket; double* totals_dev; double* totals_host;
+  float *cd_id[sdv::kLevels], *cd_ws[sdv::kLevels], *cd_id2[sdv::kLevels], *cd_ws2[sdv::kLevels];
+  int* cd_owner; int* cd_counts; int* cd_scalars; int* cd_scalars_host;
+  int cd_cap; float* cd_pts4; int* cd_round; float4* cd_splats; int* cd_done;
+  int jobs_cap; sdv::TrackJob* jobs_dev; sdv::TrackJob* jobs_host;
+  float last_ms;
+  sdv::BAState* ba = nullptr;
+  char err[512];
+};
+
+namespace sdv {
+int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
+void ba_destroy(sdv_ctx* c);
+}

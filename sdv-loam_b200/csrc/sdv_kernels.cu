@@ -1,0 +1,468 @@
+// sdv_kernels.cu — hand-written sm_100a kernels of the tracker path (compiled with --fmad=false).
+//
+//   pyr_grad_kernel / pyr_down_kernel      FrameHessian::makeImages           HessianBlocks.cpp:107-167
+//   coarse_res_gs_kernel                   CoarseTracker::calcRes + calcGSSSE  CoarseTracker.cpp:486-634, 427-484 (one fused pass)
+//   track_cluster_kernel                   CoarseTracker::trackNewestCoarse    CoarseTracker.cpp:662-838 (whole coarse-to-fine LM
+//                                          device-resident: one thread-block cluster per call, DSMEM all-reduce, per-CTA redundant solve)
+//   cd_* kernels                           CoarseTracker::makeCoarseDepthL0    CoarseTracker.cpp:258-425
+#include "sdv_kernels.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace sdv {
+
+// ================================================================================================ pyramid
+// gradient + pack of one level from a planar intensity image (HessianBlocks.cpp:147-165).  Flat-index neighbours on
+// purpose: at x=0 / x=w-1 the reference reads across the row boundary (idx±1), and so do we.
+__global__ void __launch_bounds__(256) pyr_grad_kernel(const float* __restrict__ I, float4* __restrict__ out, int w, int h) {
+  int n = w*h;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
+    float c = I[idx];
+    float dx = 0.f, dy = 0.f, ab = 0.f;
+    if (idx >= w && idx < w*(h-1)) {
+      dx = 0.5f*(I[idx+1] - I[idx-1]);
+      dy = 0.5f*(I[idx+w] - I[idx-w]);
+      if (!isfinite(dx)) dx = 0;
+      if (!isfinite(dy)) dy = 0;
+      ab = dx*dx + dy*dy;
+    }
+    out[idx] = make_float4(c, dx, dy, ab);
+  }
+}
+// 2x2 box filter of intensities (HessianBlocks.cpp:137-145): 0.25f*(((a+b)+c)+d)
+__global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__ Iprev, float* __restrict__ I, int wl, int hl, int wlm1) {
+  int n = wl*hl;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
+    int y = idx / wl, x = idx - y*wl;
+    const float* b = Iprev + 2*x + 2*y*wlm1;
+    float2 r0 = *reinterpret_cast<const float2*>(b);
+    float2 r1 = *reinterpret_cast<const float2*>(b + wlm1);
+    I[idx] = 0.25f * (((r0.x + r0.y) + r1.x) + r1.y);
+  }
+}
+
+void launch_pyramid(const float* color_dev, float* scratch /*>= w*h floats*/, float4* const* levels_out, int w, int h, int levels, cudaStream_t st) {
+  // level 0 straight from the input; level l from the planar intensity of level l-1 kept in `scratch` (ping-pong halves)
+  const float* Iprev = color_dev;
+  float* bufA = scratch; float* bufB = scratch + (size_t)(w/2)*(h/2);
+  int wl = w, hl = h;
+  for (int l = 0; l < levels; l++) {
+    int n = wl*hl; int grid = (n + 255)/256; if (grid > 148*16) grid = 148*16;
+    pyr_grad_kernel<<<grid, 256, 0, st>>>(Iprev, levels_out[l], wl, hl);
+    if (l+1 < levels) {
+      int wn = wl>>1, hn = hl>>1; float* dst = (l & 1) ? bufB : bufA;
+      int gn = (wn*hn + 255)/256; if (gn > 148*16) gn = 148*16;
+      pyr_down_kernel<<<gn, 256, 0, st>>>(Iprev, dst, wn, hn, wl);
+      Iprev = dst; wl = wn; hl = hn;
+    }
+  }
+}
+
+__global__ void unpack_level_kernel(const float4* __restrict__ in, float* dI3, float* ab, int n) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= n) return;
+  float4 t = in[i];
+  if (dI3) { dI3[3*i] = t.x; dI3[3*i+1] = t.y; dI3[3*i+2] = t.z; }
+  if (ab) ab[i] = t.w;
+}
+void launch_unpack_level(const float4* in, float* dI3, float* ab, int n, cudaStream_t st) {
+  unpack_level_kernel<<<(n+255)/256, 256, 0, st>>>(in, dI3, ab, n);
+}
+
+// ================================================================================================ reductions
+// Deterministic CTA reduction of the 51 per-thread partial sums: transpose through shared memory, each warp owns rows,
+// 8 serial adds + xor-butterfly in double.  Fixed order => bit-reproducible run to run.
+template <int THREADS>
+__device__ __forceinline__ void block_reduce_acc(const float (&acc)[kNAcc], float* red, double* out) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < kNAcc; k++) red[k*THREADS + tid] = acc[k];
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31; constexpr int NW = THREADS/32;
+  for (int k = warp; k < kNAcc; k += NW) {
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < NW; j++) s += (double)red[k*THREADS + lane + 32*j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[k] = s;
+  }
+  __syncthreads();
+}
+
+// ================================================================================================ step-wise fused calcRes+calcGSSSE
+// grid-stride over the reference cloud; per-block partials -> global; the last block to finish (ticket) sums the block
+// partials in block order and writes the 51 totals.  One launch per calcRes.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) coarse_res_gs_kernel(const float4* __restrict__ pts, int n, const float4* __restrict__ img,
+                                                               LevelGeom g, EvalParams ep, double* __restrict__ partials,
+                                                               unsigned int* __restrict__ ticket, double* __restrict__ totals) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* red = reinterpret_cast<float*>(smem_raw);
+  __shared__ double bsum[kNAcc];
+  __shared__ bool is_last;
+  float acc[kNAcc];
+#pragma unroll
+  for (int k = 0; k < kNAcc; k++) acc[k] = 0.f;
+  for (int i = blockIdx.x*THREADS + threadIdx.x; i < n; i += gridDim.x*THREADS) eval_point(__ldg(pts + i), i, g, ep, img, acc);
+  block_reduce_acc<THREADS>(acc, red, bsum);
+  if (threadIdx.x < kNAcc) partials[(size_t)blockIdx.x*kNAcc + threadIdx.x] = bsum[threadIdx.x];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) { unsigned int t = atomicAdd(ticket, 1u); is_last = (t == gridDim.x - 1); }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (threadIdx.x < kNAcc) {
+      double s = 0; for (unsigned int b = 0; b < gridDim.x; b++) s += __ldcg(partials + (size_t)b*kNAcc + threadIdx.x);
+      totals[threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+
+constexpr int kStepThreads = 256;
+int step_kernel_max_grid() { return 148*4; }
+void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const LevelGeom& g, const EvalParams& ep,
+                          double* partials, unsigned int* ticket, double* totals, cudaStream_t st) {
+  static bool attr_set = false;
+  size_t smem = (size_t)kNAcc*kStepThreads*sizeof(float);
+  if (!attr_set) { cudaFuncSetAttribute(coarse_res_gs_kernel<kStepThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  int grid = (n + kStepThreads - 1)/kStepThreads; if (grid < 1) grid = 1; if (grid > step_kernel_max_grid()) grid = step_kernel_max_grid();
+  coarse_res_gs_kernel<kStepThreads><<<grid, kStepThreads, smem, st>>>(pts, n, img, g, ep, partials, ticket, totals);
+}
+
+// ================================================================================================ device-resident LM
+struct Ctl {                               // per-CTA copy of the LM state (every CTA of the cluster computes it redundantly and identically)
+  SE3d cur; double a_cur, b_cur;           // refToNew_current, aff_g2l_current
+  SE3d cand; double a_cand, b_cand;        // refToNew_new, aff_g2l_new
+  double H[64], b[8];
+  double resOld[6], resNew[6];
+  double lastRes[5], flow[3];
+  float lambda;
+  int flag;
+  EvalParams ep;
+};
+
+constexpr int kTrackThreads = 256;
+constexpr int kMaxCluster = 16;
+
+__global__ void __launch_bounds__(kTrackThreads, 1) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
+  constexpr int THREADS = kTrackThreads;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  TrackJob& J = jobs[blockIdx.x / C];
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float*  red    = reinterpret_cast<float*>(smem_raw);                                   // [kNAcc][THREADS]
+  double* gather = reinterpret_cast<double*>(smem_raw + (size_t)kNAcc*THREADS*sizeof(float)); // [2][kMaxCluster][kNAcc]
+  double* bsum   = gather + 2*kMaxCluster*kNAcc;                                           // [kNAcc]
+  double* tot    = bsum + kNAcc;                                                           // [kNAcc]
+  __shared__ Ctl ctl;
+  __shared__ TrackConst tc;
+  for (int i = tid; i < (int)(sizeof(TrackConst)/4); i += THREADS) reinterpret_cast<int*>(&tc)[i] = reinterpret_cast<const int*>(tc_g)[i];
+  if (tid == 0) {
+    ctl.cur = se3_from7(J.T); ctl.a_cur = J.ab[0]; ctl.b_cur = J.ab[1];
+    for (int i = 0; i < 5; i++) ctl.lastRes[i] = nan("");
+    for (int i = 0; i < 3; i++) ctl.flow[i] = 1000.0;
+  }
+  long long evals[kLevels]; int iters[kLevels], accs[kLevels];
+#pragma unroll
+  for (int i = 0; i < kLevels; i++) { evals[i] = 0; iters[i] = 0; accs[i] = 0; }
+  __syncthreads();
+
+  int evalCount = 0;
+  // all threads: evaluate the residual + GN system at ctl.ep for level `lvl`; totals (identical in every CTA) land in tot[]
+  auto eval = [&](int lvl) {
+    float acc[kNAcc];
+#pragma unroll
+    for (int k = 0; k < kNAcc; k++) acc[k] = 0.f;
+    const float4* __restrict__ pts = J.pts[lvl]; const int n = J.npts[lvl]; const float4* __restrict__ img = J.img[lvl];
+    const LevelGeom& g = tc.geom[lvl];
+    for (int i = rank*THREADS + tid; i < n; i += C*THREADS) eval_point(__ldg(pts + i), i, g, ctl.ep, img, acc);
+    block_reduce_acc<THREADS>(acc, red, bsum);
+    const int buf = evalCount & 1;
+    for (int k = tid; k < kNAcc*C; k += THREADS) {
+      int r = k / kNAcc, e = k - r*kNAcc;
+      double* dst = cluster.map_shared_rank(gather, r);
+      dst[(buf*kMaxCluster + rank)*kNAcc + e] = bsum[e];
+    }
+    cluster.sync();
+    if (tid < kNAcc) { double s = 0; for (int r = 0; r < C; r++) s += gather[(buf*kMaxCluster + r)*kNAcc + tid]; tot[tid] = s; }
+    __syncthreads();
+    evalCount++; evals[lvl] += n;
+  };
+
+  const int maxIterations[5] = {10,20,50,50,50};           // CoarseTracker.cpp:679
+  const float lambdaExtrapolationLimit = 0.001f;            // :680
+  bool haveRepeated = false, aborted = false;
+  for (int lvl = J.coarsest; lvl >= 0; lvl--) {
+    float levelCutoffRepeat = 1;
+    if (tid == 0) make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl,
+                                   tc.coarseCutoffTH*levelCutoffRepeat, tc.huberTH, ctl.ep);
+    __syncthreads();
+    eval(lvl);
+    if (tid == 0) { finalize_res(tot, ctl.resOld); ctl.flag = (ctl.resOld[5] > 0.6 && levelCutoffRepeat < 50); }
+    __syncthreads();
+    while (ctl.flag) {                                      // :694-701
+      levelCutoffRepeat *= 2;
+      __syncthreads();
+      if (tid == 0) make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl,
+                                     tc.coarseCutoffTH*levelCutoffRepeat, tc.huberTH, ctl.ep);
+      __syncthreads();
+      eval(lvl);
+      if (tid == 0) { finalize_res(tot, ctl.resOld); ctl.flag = (ctl.resOld[5] > 0.6 && levelCutoffRepeat < 50); }
+      __syncthreads();
+    }
+    if (tid == 0) { finalize_gs(tot, ctl.H, ctl.b); ctl.lambda = 0.01f; }
+
+    for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
+      iters[lvl]++;
+      double incn = 0;
+      if (tid == 0) {
+        double Hl[64], nb[8], inc[8];
+        const float lambda = ctl.lambda;
+        for (int i = 0; i < 64; i++) Hl[i] = ctl.H[i];
+        for (int i = 0; i < 8; i++) { Hl[i*8+i] *= (1+lambda); nb[i] = -ctl.b[i]; }
+        const bool fixA = tc.affineOptModeA < 0, fixB = tc.affineOptModeB < 0;
+        if (!fixA && !fixB) ldlt_solve<8>(8, Hl, 8, nb, inc);
+        else if (fixA && fixB) { ldlt_solve<8>(6, Hl, 8, nb, inc); inc[6] = inc[7] = 0; }
+        else if (!fixA && fixB) { ldlt_solve<8>(7, Hl, 8, nb, inc); inc[7] = 0; }
+        else {                                              // fix a only: stitch b into slot 6 (:736-748)
+          double Hs[64], bs[8], x7[7];
+          for (int i = 0; i < 64; i++) Hs[i] = Hl[i];
+          for (int i = 0; i < 8; i++) bs[i] = ctl.b[i];
+          for (int r = 0; r < 8; r++) Hs[r*8+6] = Hs[r*8+7];
+          for (int c = 0; c < 8; c++) Hs[6*8+c] = Hs[7*8+c];
+          bs[6] = bs[7];
+          for (int i = 0; i < 7; i++) bs[i] = -bs[i];
+          ldlt_solve<8>(7, Hs, 8, bs, x7);
+          for (int i = 0; i < 6; i++) inc[i] = x7[i];
+          inc[6] = 0; inc[7] = x7[6];
+        }
+        float extrapFac = 1;
+        if (lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / lambda));
+        for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+        double incScaled[8];
+        for (int i = 0; i < 3; i++) incScaled[i] = inc[i]*1.0f;        // SCALE_XI_ROT   (:755)
+        for (int i = 3; i < 6; i++) incScaled[i] = inc[i]*0.5f;        // SCALE_XI_TRANS (:756)
+        incScaled[6] = inc[6]*10.0f; incScaled[7] = inc[7]*1000.0f;    // SCALE_A, SCALE_B
+        double s = 0; for (int i = 0; i < 8; i++) s += incScaled[i];
+        if (!isfinite(s)) for (int i = 0; i < 8; i++) incScaled[i] = 0;
+        ctl.cand = se3_mul(se3_exp(incScaled), ctl.cur);
+        ctl.a_cand = ctl.a_cur + incScaled[6]; ctl.b_cand = ctl.b_cur + incScaled[7];
+        make_eval_params(ctl.cand, ctl.a_cand, ctl.b_cand, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl,
+                         tc.coarseCutoffTH*levelCutoffRepeat, tc.huberTH, ctl.ep);
+        for (int i = 0; i < 8; i++) incn += inc[i]*inc[i];
+        incn = sqrt(incn);
+      }
+      __syncthreads();
+      eval(lvl);
+      if (tid == 0) {
+        finalize_res(tot, ctl.resNew);
+        bool accept = (ctl.resNew[0]/ctl.resNew[1]) < (ctl.resOld[0]/ctl.resOld[1]);
+        if (accept) {
+          finalize_gs(tot, ctl.H, ctl.b);
+          for (int i = 0; i < 6; i++) ctl.resOld[i] = ctl.resNew[i];
+          ctl.cur = ctl.cand; ctl.a_cur = ctl.a_cand; ctl.b_cur = ctl.b_cand;
+          ctl.lambda *= 0.5f;
+        } else {
+          ctl.lambda *= 4;
+          if (ctl.lambda < lambdaExtrapolationLimit) ctl.lambda = lambdaExtrapolationLimit;
+        }
+        ctl.flag = (accept ? 1 : 0) | ((!(incn > 1e-3)) ? 2 : 0);
+      }
+      __syncthreads();
+      const int f = ctl.flag;
+      __syncthreads();
+      if (f & 1) accs[lvl]++;
+      if (f & 2) break;
+    }
+    if (tid == 0) {
+      ctl.lastRes[lvl] = sqrtf((float)(ctl.resOld[0]/ctl.resOld[1]));
+      ctl.flow[0] = ctl.resOld[2]; ctl.flow[1] = ctl.resOld[3]; ctl.flow[2] = ctl.resOld[4];
+      ctl.flag = (ctl.lastRes[lvl] > 1.5*J.minRes[lvl]) ? 1 : 0;
+    }
+    __syncthreads();
+    const int ab = ctl.flag;
+    __syncthreads();
+    if (ab) { aborted = true; break; }
+    if (levelCutoffRepeat > 1 && !haveRepeated) { lvl++; haveRepeated = true; }
+  }
+
+  if (rank == 0 && tid == 0) {
+    int good = 0;
+    if (!aborted) {
+      se3_to7(ctl.cur, J.T);
+      double a_out = ctl.a_cur, b_out = ctl.b_cur;
+      good = 1;
+      if ((tc.affineOptModeA != 0 && (fabsf((float)a_out) > 1.2f)) || (tc.affineOptModeB != 0 && (fabsf((float)b_out) > 200))) good = 0;
+      if (good) {
+        double rel[2]; aff_from_to(J.refExposure, J.newExposure, J.ref_a, J.ref_b, a_out, b_out, rel);
+        float r0 = (float)rel[0], r1 = (float)rel[1];
+        if ((tc.affineOptModeA == 0 && (fabsf(logf(r0)) > 1.5f)) || (tc.affineOptModeB == 0 && (fabsf(r1) > 200))) good = 0;
+        if (good) { if (tc.affineOptModeA < 0) a_out = 0; if (tc.affineOptModeB < 0) b_out = 0; }
+      }
+      J.ab[0] = a_out; J.ab[1] = b_out;
+    }
+    J.good = good;
+    for (int i = 0; i < 5; i++) J.lastRes[i] = ctl.lastRes[i];
+    for (int i = 0; i < 3; i++) J.flow[i] = ctl.flow[i];
+    for (int i = 0; i < kLevels; i++) { J.point_evals[i] = evals[i]; J.iterations[i] = iters[i]; J.accepts[i] = accs[i]; }
+  }
+  cluster.sync();                                           // keep every CTA's shared memory alive until all remote writes/reads are done
+}
+
+size_t track_kernel_smem() { return (size_t)kNAcc*kTrackThreads*sizeof(float) + (size_t)(2*kMaxCluster*kNAcc + 2*kNAcc)*sizeof(double); }
+
+cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
+  static bool attr_set = false;
+  size_t smem = track_kernel_smem();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(track_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(track_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(njobs*cluster_size)); cfg.blockDim = dim3(kTrackThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, track_cluster_kernel, jobs_dev, tc_dev);
+}
+
+// ================================================================================================ makeCoarseDepthL0
+// (a) splat in POINT ORDER per pixel: round r adds, for every pixel, the not-yet-added point of lowest index, which
+//     reproduces the reference's sequential float `+=` order bit-for-bit even for colliding points (CoarseTracker.cpp:264-294).
+__global__ void cd_owner_kernel(const float4* __restrict__ splats /*{pix as int bits, idepth*w, w, 0}*/, int n, const int* __restrict__ done, int* owner) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= n || done[i]) return;
+  atomicMin(owner + __float_as_int(splats[i].x), i);
+}
+__global__ void cd_apply_kernel(const float4* __restrict__ splats, int n, int* done, int* owner, float* idepth, float* weightSums, int* remaining) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= n || done[i]) return;
+  int pix = __float_as_int(splats[i].x);
+  if (owner[pix] == i) { idepth[pix] += splats[i].y; weightSums[pix] += splats[i].z; done[i] = 1; }
+  else atomicAdd(remaining, 1);
+}
+__global__ void cd_reset_owner_kernel(const float4* __restrict__ splats, int n, int* owner) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= n) return;
+  owner[__float_as_int(splats[i].x)] = 0x7fffffff;
+}
+__global__ void cd_prep_kernel(const float* __restrict__ pts4, const int* __restrict__ round_half, int n, int w, float4* splats, int* done) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= n) return;
+  float pu = pts4[4*i], pv = pts4[4*i+1], id = pts4[4*i+2], HdiF = pts4[4*i+3];
+  int u = round_half[i] ? (int)(pu + 0.5f) : (int)pu;
+  int v = round_half[i] ? (int)(pv + 0.5f) : (int)pv;
+  float weight = sqrtf((float)(1e-3 / ((double)HdiF + 1e-12)));      // sqrtf(1e-3 / (HdiF+1e-12)) — double division, float sqrt (:273)
+  splats[i] = make_float4(__int_as_float(u + w*v), id*weight, weight, 0.f);
+  done[i] = 0;
+}
+// (b) sum-pool to the next level (:296-322)
+__global__ void cd_pool_kernel(const float* __restrict__ id_lm, const float* __restrict__ ws_lm, float* id_l, float* ws_l, int wl, int hl, int wlm1) {
+  int idx = blockIdx.x*blockDim.x + threadIdx.x; if (idx >= wl*hl) return;
+  int y = idx / wl, x = idx - y*wl; int bidx = 2*x + 2*y*wlm1;
+  id_l[idx] = ((id_lm[bidx] + id_lm[bidx+1]) + id_lm[bidx+wlm1]) + id_lm[bidx+wlm1+1];
+  ws_l[idx] = ((ws_lm[bidx] + ws_lm[bidx+1]) + ws_lm[bidx+wlm1]) + ws_lm[bidx+wlm1+1];
+}
+// (c) 1-px dilation into empty cells, reading the pre-dilation weights (:324-375).  diag=1: 4 diagonal neighbours (levels 0,1),
+//     diag=0: 4 axis neighbours.  The reference updates idepth in place but only ever reads cells with bak>0 and writes cells
+//     with bak<=0, so reading the un-dilated idepth array is equivalent.
+__global__ void cd_dilate_kernel(const float* __restrict__ id_in, const float* __restrict__ bak, float* id_out, float* ws_out, int w, int h, int diag) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; int n = w*h; if (i >= n) return;
+  float idv = id_in[i], wsv = bak[i];
+  if (i >= w && i < n - w && bak[i] <= 0) {
+    int o0, o1, o2, o3;
+    if (diag) { o0 = 1+w; o1 = -1-w; o2 = w-1; o3 = -w+1; } else { o0 = 1; o1 = -1; o2 = w; o3 = -w; }
+    float sum = 0, num = 0, numn = 0;
+    if (bak[i+o0] > 0) { sum += id_in[i+o0]; num += bak[i+o0]; numn++; }
+    if (bak[i+o1] > 0) { sum += id_in[i+o1]; num += bak[i+o1]; numn++; }
+    if (bak[i+o2] > 0) { sum += id_in[i+o2]; num += bak[i+o2]; numn++; }
+    if (bak[i+o3] > 0) { sum += id_in[i+o3]; num += bak[i+o3]; numn++; }
+    if (numn > 0) { idv = sum/numn; wsv = num/numn; }
+  }
+  id_out[i] = idv; ws_out[i] = wsv;
+}
+// (d) normalise + raster-order compaction (:378-423): block counts -> exclusive scan -> scatter
+constexpr int kScanThreads = 256, kScanItems = 4;            // 1024 pixels per block, contiguous per thread
+__device__ __forceinline__ bool cd_valid(const float* id, const float* ws, const float4* ref, int i, int w, int h, float& idn, float& col) {
+  int y = i / w, x = i - y*w;
+  if (x < 2 || x >= w-2 || y < 2 || y >= h-2) return false;
+  if (!(ws[i] > 0)) return false;
+  idn = id[i] / ws[i]; col = ref[i].x;
+  return isfinite(col) && (idn > 0);
+}
+__global__ void __launch_bounds__(kScanThreads) cd_count_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, int w, int h, int* blockCounts) {
+  __shared__ int s[kScanThreads/32];
+  int base = (blockIdx.x*kScanThreads + threadIdx.x)*kScanItems; int c = 0, n = w*h;
+  for (int j = 0; j < kScanItems; j++) { int i = base + j; float a, b; if (i < n && cd_valid(id, ws, ref, i, w, h, a, b)) c++; }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < kScanThreads/32; k++) t += s[k]; blockCounts[blockIdx.x] = t; }
+}
+__global__ void cd_scan_kernel(int* blockCounts, int nblocks, int* total) {   // single block exclusive scan (nblocks <= a few thousand)
+  __shared__ int carry;
+  __shared__ int sh[1024];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    int i = base + threadIdx.x; int v = (i < nblocks) ? blockCounts[i] : 0;
+    sh[threadIdx.x] = v; __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0; __syncthreads(); sh[threadIdx.x] += t; __syncthreads(); }
+    int incl = sh[threadIdx.x]; int c = carry;
+    if (i < nblocks) blockCounts[i] = c + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(kScanThreads) cd_emit_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, int w, int h,
+                                                              const int* __restrict__ blockOffsets, float4* out) {
+  __shared__ int s[kScanThreads/32];
+  int base = (blockIdx.x*kScanThreads + threadIdx.x)*kScanItems; int n = w*h;
+  float idn[kScanItems], col[kScanItems]; bool ok[kScanItems]; int c = 0;
+  for (int j = 0; j < kScanItems; j++) { int i = base + j; ok[j] = (i < n) && cd_valid(id, ws, ref, i, w, h, idn[j], col[j]); c += ok[j]; }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; int incl = c;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s[warp] = incl;
+  __syncthreads();
+  int woff = 0; for (int k = 0; k < warp; k++) woff += s[k];
+  int pos = blockOffsets[blockIdx.x] + woff + incl - c;
+  for (int j = 0; j < kScanItems; j++) if (ok[j]) { int i = base + j; int y = i / w, x = i - y*w; out[pos++] = make_float4((float)x, (float)y, idn[j], col[j]); }
+}
+
+int cd_num_blocks(int w, int h) { return (w*h + kScanThreads*kScanItems - 1)/(kScanThreads*kScanItems); }
+
+void launch_cd_prep(const float* pts4, const int* round_half, int n, int w, float4* splats, int* done, cudaStream_t st) {
+  if (n > 0) cd_prep_kernel<<<(n+255)/256, 256, 0, st>>>(pts4, round_half, n, w, splats, done);
+}
+void launch_cd_round(const float4* splats, int n, int* done, int* owner, float* idepth, float* ws, int* remaining, cudaStream_t st) {
+  if (n <= 0) return;
+  int g = (n+255)/256;
+  cd_reset_owner_kernel<<<g, 256, 0, st>>>(splats, n, owner);
+  cd_owner_kernel<<<g, 256, 0, st>>>(splats, n, done, owner);
+  cd_apply_kernel<<<g, 256, 0, st>>>(splats, n, done, owner, idepth, ws, remaining);
+}
+void launch_cd_pool(const float* id_lm, const float* ws_lm, float* id_l, float* ws_l, int wl, int hl, int wlm1, cudaStream_t st) {
+  cd_pool_kernel<<<(wl*hl+255)/256, 256, 0, st>>>(id_lm, ws_lm, id_l, ws_l, wl, hl, wlm1);
+}
+void launch_cd_dilate(const float* id_in, const float* bak, float* id_out, float* ws_out, int w, int h, int diag, cudaStream_t st) {
+  cd_dilate_kernel<<<(w*h+255)/256, 256, 0, st>>>(id_in, bak, id_out, ws_out, w, h, diag);
+}
+void launch_cd_compact(const float* id, const float* ws, const float4* ref, int w, int h, int* blockCounts, int* total, float4* out, cudaStream_t st) {
+  int nb = cd_num_blocks(w, h);
+  cd_count_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, w, h, blockCounts);
+  cd_scan_kernel<<<1, 1024, 0, st>>>(blockCounts, nb, total);
+  cd_emit_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, w, h, blockCounts, out);
+}
+
+__global__ void pack_cloud_kernel(const float* u, const float* v, const float* id, const float* col, int n, float4* out) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i < n) out[i] = make_float4(u[i], v[i], id[i], col[i]);
+}
+void launch_pack_cloud(const float* u, const float* v, const float* id, const float* col, int n, float4* out, cudaStream_t st) {
+  if (n > 0) pack_cloud_kernel<<<(n+255)/256, 256, 0, st>>>(u, v, id, col, n, out);
+}
+
+} // namespace sdv

@@ -1,0 +1,29 @@
+// sdv_kernels.cuh — launcher declarations (host side of sdv_kernels.cu / sdv_ba_kernels.cu)
+#pragma once
+#include "sdv_device.cuh"
+
+namespace sdv {
+
+// pyramid (FrameHessian::makeImages, HessianBlocks.cpp:107-167)
+void launch_pyramid(const float* color_dev, float* scratch, float4* const* levels_out, int w, int h, int levels, cudaStream_t st);
+void launch_unpack_level(const float4* in, float* dI3, float* ab, int n, cudaStream_t st);
+
+// fused calcRes + calcGSSSE, one launch (CoarseTracker.cpp:486-634, 427-484)
+int  step_kernel_max_grid();
+void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const LevelGeom& g, const EvalParams& ep,
+                          double* partials, unsigned int* ticket, double* totals, cudaStream_t st);
+
+// device-resident trackNewestCoarse (CoarseTracker.cpp:662-838): njobs clusters of cluster_size CTAs
+size_t track_kernel_smem();
+cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st);
+
+// makeCoarseDepthL0 (CoarseTracker.cpp:258-425)
+int  cd_num_blocks(int w, int h);
+void launch_cd_prep(const float* pts4, const int* round_half, int n, int w, float4* splats, int* done, cudaStream_t st);
+void launch_cd_round(const float4* splats, int n, int* done, int* owner, float* idepth, float* ws, int* remaining, cudaStream_t st);
+void launch_cd_pool(const float* id_lm, const float* ws_lm, float* id_l, float* ws_l, int wl, int hl, int wlm1, cudaStream_t st);
+void launch_cd_dilate(const float* id_in, const float* bak, float* id_out, float* ws_out, int w, int h, int diag, cudaStream_t st);
+void launch_cd_compact(const float* id, const float* ws, const float4* ref, int w, int h, int* blockCounts, int* total, float4* out, cudaStream_t st);
+void launch_pack_cloud(const float* u, const float* v, const float* id, const float* col, int n, float4* out, cudaStream_t st);
+
+} // namespace sdv
