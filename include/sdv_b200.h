@@ -43,7 +43,9 @@ typedef struct {                                             /* util/settings.cp
   int   max_ref_points;         /* capacity of a tracker reference cloud per level (0 = w*h) */
   int   n_tracker_slots;        /* reference uses 2 (coarseTracker, coarseTracker_forNewKF; FullSystem.h); batched mode: 2 x sequences */
   int   max_frames;             /* device-resident frame pyramids kept alive at once */
-  int   cluster_size;           /* CTAs per thread-block cluster in the device-resident LM kernel (0 = default 8) */
+  int   cluster_size;           /* CTAs per thread-block cluster per trackNewestCoarse call in the device-resident LM kernel
+                                   (default 1 = batched-throughput mode; 8..16 = low-latency single-sequence mode) */
+  int   track_threads;          /* threads per CTA of that kernel: 128 (default, 4 jobs resident per SM), 64 or 256 */
 } sdv_settings;
 
 void sdv_default_settings(sdv_settings* s);

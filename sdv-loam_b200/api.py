@@ -23,7 +23,8 @@ class sdv_calib(C.Structure):
 class sdv_settings(C.Structure):
     _fields_ = [("huberTH", C.c_float), ("coarseCutoffTH", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float),
                 ("outlierTH", C.c_float), ("outlierTHSumComponent", C.c_float), ("idepthFixPrior", C.c_float),
-                ("max_ref_points", C.c_int), ("n_tracker_slots", C.c_int), ("max_frames", C.c_int), ("cluster_size", C.c_int)]
+                ("max_ref_points", C.c_int), ("n_tracker_slots", C.c_int), ("max_frames", C.c_int), ("cluster_size", C.c_int),
+                ("track_threads", C.c_int)]
 
 
 class sdv_track_stats(C.Structure):

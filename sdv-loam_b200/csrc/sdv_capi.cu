@@ -22,7 +22,7 @@ extern "C" {
 void sdv_default_settings(sdv_settings* s) {
   s->huberTH = 6; s->coarseCutoffTH = 20; s->affineOptModeA = 0; s->affineOptModeB = 0;
   s->outlierTH = 12*12; s->outlierTHSumComponent = 50*50; s->idepthFixPrior = 50*50;
-  s->max_ref_points = 0; s->n_tracker_slots = 2; s->max_frames = 16; s->cluster_size = 8;
+  s->max_ref_points = 0; s->n_tracker_slots = 2; s->max_frames = 16; s->cluster_size = 1; s->track_threads = 128;
 }
 
 int sdv_pyr_levels(int w, int h) {               // util/globalCalib.cpp:22-30
@@ -53,7 +53,8 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   sdv_settings s; if (s_in) s = *s_in; else sdv_default_settings(&s);
   if (s.n_tracker_slots < 1) s.n_tracker_slots = 2;
   if (s.max_frames < 2) s.max_frames = 2;
-  if (s.cluster_size <= 0) s.cluster_size = 8;
+  if (s.cluster_size <= 0) s.cluster_size = 1;
+  if (s.track_threads != 64 && s.track_threads != 256) s.track_threads = 128;
   if (s.cluster_size > 16) s.cluster_size = 16;
   c->set = s; c->device = device; c->w = w; c->h = h; c->levels = levels;
   CK(cudaSetDevice(device));
@@ -293,7 +294,7 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
   }
   CK(cudaMemcpyAsync(c->jobs_dev, c->jobs_host, (size_t)n*sizeof(TrackJob), cudaMemcpyHostToDevice, c->st));
   CK(cudaEventRecord(c->ev0, c->st));
-  CK(launch_track_cluster(c->jobs_dev, n, c->tc_dev, c->set.cluster_size, c->st));
+  CK(launch_track_cluster(c->jobs_dev, n, c->tc_dev, c->set.cluster_size, c->set.track_threads, c->st));
   CK(cudaEventRecord(c->ev1, c->st));
   CK(cudaMemcpyAsync(c->jobs_host, c->jobs_dev, (size_t)n*sizeof(TrackJob), cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());

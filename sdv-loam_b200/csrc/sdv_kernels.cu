@@ -6,6 +6,7 @@
 //                                          device-resident: one thread-block cluster per call, DSMEM all-reduce, per-CTA redundant solve)
 //   cd_* kernels                           CoarseTracker::makeCoarseDepthL0    CoarseTracker.cpp:258-425
 #include "sdv_kernels.cuh"
+#include "sdv_warp_solve.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -143,11 +144,13 @@ struct Ctl {                               // per-CTA copy of the LM state (ever
   EvalParams ep;
 };
 
-constexpr int kTrackThreads = 256;
 constexpr int kMaxCluster = 16;
 
-__global__ void __launch_bounds__(kTrackThreads, 1) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
-  constexpr int THREADS = kTrackThreads;
+// THREADS x MINB chosen so that several jobs are resident per SM: one job's (single-warp, latency-bound) LM control step
+// overlaps the point sweeps of the others.  <128,4> is the batched-throughput configuration (cluster size 1);
+// <256,1> with a cluster of 8-16 CTAs is the low-latency single-sequence configuration.
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
@@ -182,14 +185,18 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_cluster_kernel(TrackJo
     const LevelGeom& g = tc.geom[lvl];
     for (int i = rank*THREADS + tid; i < n; i += C*THREADS) eval_point(__ldg(pts + i), i, g, ctl.ep, img, acc);
     block_reduce_acc<THREADS>(acc, red, bsum);
-    const int buf = evalCount & 1;
-    for (int k = tid; k < kNAcc*C; k += THREADS) {
-      int r = k / kNAcc, e = k - r*kNAcc;
-      double* dst = cluster.map_shared_rank(gather, r);
-      dst[(buf*kMaxCluster + rank)*kNAcc + e] = bsum[e];
+    if (C > 1) {
+      const int buf = evalCount & 1;
+      for (int k = tid; k < kNAcc*C; k += THREADS) {
+        int r = k / kNAcc, e = k - r*kNAcc;
+        double* dst = cluster.map_shared_rank(gather, r);
+        dst[(buf*kMaxCluster + rank)*kNAcc + e] = bsum[e];
+      }
+      cluster.sync();
+      if (tid < kNAcc) { double s = 0; for (int r = 0; r < C; r++) s += gather[(buf*kMaxCluster + r)*kNAcc + tid]; tot[tid] = s; }
+    } else {
+      if (tid < kNAcc) tot[tid] = bsum[tid];
     }
-    cluster.sync();
-    if (tid < kNAcc) { double s = 0; for (int r = 0; r < C; r++) s += gather[(buf*kMaxCluster + r)*kNAcc + tid]; tot[tid] = s; }
     __syncthreads();
     evalCount++; evals[lvl] += n;
   };
@@ -220,42 +227,56 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_cluster_kernel(TrackJo
     for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
       iters[lvl]++;
       double incn = 0;
-      if (tid == 0) {
-        double Hl[64], nb[8], inc[8];
+      if (tid < 32) {                                        // warp 0: propose the LM step (CoarseTracker.cpp:722-765)
+        const int r = tid & 7;
         const float lambda = ctl.lambda;
-        for (int i = 0; i < 64; i++) Hl[i] = ctl.H[i];
-        for (int i = 0; i < 8; i++) { Hl[i*8+i] *= (1+lambda); nb[i] = -ctl.b[i]; }
         const bool fixA = tc.affineOptModeA < 0, fixB = tc.affineOptModeB < 0;
-        if (!fixA && !fixB) ldlt_solve<8>(8, Hl, 8, nb, inc);
-        else if (fixA && fixB) { ldlt_solve<8>(6, Hl, 8, nb, inc); inc[6] = inc[7] = 0; }
-        else if (!fixA && fixB) { ldlt_solve<8>(7, Hl, 8, nb, inc); inc[7] = 0; }
-        else {                                              // fix a only: stitch b into slot 6 (:736-748)
-          double Hs[64], bs[8], x7[7];
-          for (int i = 0; i < 64; i++) Hs[i] = Hl[i];
-          for (int i = 0; i < 8; i++) bs[i] = ctl.b[i];
-          for (int r = 0; r < 8; r++) Hs[r*8+6] = Hs[r*8+7];
-          for (int c = 0; c < 8; c++) Hs[6*8+c] = Hs[7*8+c];
-          bs[6] = bs[7];
-          for (int i = 0; i < 7; i++) bs[i] = -bs[i];
-          ldlt_solve<8>(7, Hs, 8, bs, x7);
-          for (int i = 0; i < 6; i++) inc[i] = x7[i];
-          inc[6] = 0; inc[7] = x7[6];
+        const int nv = (!fixA && !fixB) ? 8 : ((fixA && fixB) ? 6 : 7);
+        const bool stitch = fixA && !fixB;                   // fix a only: b takes slot 6 (:736-748)
+        const int rr = (stitch && r == 6) ? 7 : r;
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int cc = (stitch && j == 6) ? 7 : j;
+          double hv = ctl.H[rr*8 + cc];
+          if (rr == cc) hv *= (1 + lambda);
+          a[j] = (r < nv && j < nv) ? hv : ((r == j) ? 1.0 : 0.0);
         }
+        double rhs = (r < nv) ? -ctl.b[rr] : 0.0;
+        const double x = warp_ldlt_solve8(a, rhs);
+        double inc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) inc[j] = __shfl_sync(0xffffffffu, x, j, 8);
+        if (fixA && fixB) { inc[6] = 0; inc[7] = 0; }
+        else if (!fixA && fixB) { inc[7] = 0; }
+        else if (stitch) { inc[7] = inc[6]; inc[6] = 0; }
         float extrapFac = 1;
         if (lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / lambda));
+#pragma unroll
         for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
         double incScaled[8];
+#pragma unroll
         for (int i = 0; i < 3; i++) incScaled[i] = inc[i]*1.0f;        // SCALE_XI_ROT   (:755)
+#pragma unroll
         for (int i = 3; i < 6; i++) incScaled[i] = inc[i]*0.5f;        // SCALE_XI_TRANS (:756)
         incScaled[6] = inc[6]*10.0f; incScaled[7] = inc[7]*1000.0f;    // SCALE_A, SCALE_B
-        double s = 0; for (int i = 0; i < 8; i++) s += incScaled[i];
-        if (!isfinite(s)) for (int i = 0; i < 8; i++) incScaled[i] = 0;
-        ctl.cand = se3_mul(se3_exp(incScaled), ctl.cur);
-        ctl.a_cand = ctl.a_cur + incScaled[6]; ctl.b_cand = ctl.b_cur + incScaled[7];
-        make_eval_params(ctl.cand, ctl.a_cand, ctl.b_cand, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl,
-                         tc.coarseCutoffTH*levelCutoffRepeat, tc.huberTH, ctl.ep);
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += incScaled[i];
+        if (!isfinite(s)) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) incScaled[i] = 0;
+        }
+        const SE3d cand = se3_mul(se3_exp(incScaled), ctl.cur);
+        const double a_cand = ctl.a_cur + incScaled[6], b_cand = ctl.b_cur + incScaled[7];
+        EvalParams ep;
+        make_eval_params(cand, a_cand, b_cand, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl,
+                         tc.coarseCutoffTH*levelCutoffRepeat, tc.huberTH, ep);
+#pragma unroll
         for (int i = 0; i < 8; i++) incn += inc[i]*inc[i];
         incn = sqrt(incn);
+        __syncwarp();
+        if (tid == 0) { ctl.cand = cand; ctl.a_cand = a_cand; ctl.b_cand = b_cand; ctl.ep = ep; }
       }
       __syncthreads();
       eval(lvl);
@@ -311,25 +332,34 @@ __global__ void __launch_bounds__(kTrackThreads, 1) track_cluster_kernel(TrackJo
     for (int i = 0; i < 3; i++) J.flow[i] = ctl.flow[i];
     for (int i = 0; i < kLevels; i++) { J.point_evals[i] = evals[i]; J.iterations[i] = iters[i]; J.accepts[i] = accs[i]; }
   }
-  cluster.sync();                                           // keep every CTA's shared memory alive until all remote writes/reads are done
+  if (C > 1) cluster.sync();                                // keep every CTA's shared memory alive until all remote writes/reads are done
 }
 
-size_t track_kernel_smem() { return (size_t)kNAcc*kTrackThreads*sizeof(float) + (size_t)(2*kMaxCluster*kNAcc + 2*kNAcc)*sizeof(double); }
+template <int THREADS>
+static size_t track_kernel_smem() { return (size_t)kNAcc*THREADS*sizeof(float) + (size_t)(2*kMaxCluster*kNAcc + 2*kNAcc)*sizeof(double); }
 
-cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
+template <int THREADS, int MINB>
+static cudaError_t launch_track_t(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
   static bool attr_set = false;
-  size_t smem = track_kernel_smem();
+  size_t smem = track_kernel_smem<THREADS>();
+  auto kern = track_cluster_kernel<THREADS, MINB>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(track_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(track_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e != cudaSuccess) return e;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(njobs*cluster_size)); cfg.blockDim = dim3(kTrackThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(njobs*cluster_size)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, track_cluster_kernel, jobs_dev, tc_dev);
+  return cudaLaunchKernelEx(&cfg, kern, jobs_dev, tc_dev);
+}
+// threads: 128 (throughput, 4 jobs resident per SM) or 256 (latency)
+cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, int threads, cudaStream_t st) {
+  if (threads == 256) return launch_track_t<256, 1>(jobs_dev, njobs, tc_dev, cluster_size, st);
+  if (threads == 64)  return launch_track_t<64, 8>(jobs_dev, njobs, tc_dev, cluster_size, st);
+  return launch_track_t<128, 4>(jobs_dev, njobs, tc_dev, cluster_size, st);
 }
 
 // ================================================================================================ makeCoarseDepthL0

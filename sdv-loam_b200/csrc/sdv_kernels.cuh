@@ -14,8 +14,7 @@ void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const Lev
                           double* partials, unsigned int* ticket, double* totals, cudaStream_t st);
 
 // device-resident trackNewestCoarse (CoarseTracker.cpp:662-838): njobs clusters of cluster_size CTAs
-size_t track_kernel_smem();
-cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st);
+cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, int threads, cudaStream_t st);
 
 // makeCoarseDepthL0 (CoarseTracker.cpp:258-425)
 int  cd_num_blocks(int w, int h);

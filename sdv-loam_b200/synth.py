@@ -111,7 +111,8 @@ def render(world: World, R, t, K=KITTI_K, wh=KITTI_WH, gain: float = 1.0, bias: 
     img = gain * img + bias
     if noise > 0:
         img = img + np.random.default_rng(seed).normal(0, noise, img.shape)
-    return np.clip(img, 0, 255).astype(np.float32), np.where(idx >= 0, lam, 0.0)
+    # mono8 like the reference's ingest (sensor_msgs/Image mono8 -> float, DatasetReader.h:152-155)
+    return np.rint(np.clip(img, 0, 255)).astype(np.float32), np.where(idx >= 0, lam, 0.0)
 
 
 def lidar_pixels(world: World, R, t, K=KITTI_K, wh=KITTI_WH, beams: int = 64, az: int = 1800, seed: int = 0, range_noise: float = 0.0):

@@ -31,13 +31,18 @@ print("oracle", ro['good'], orc.se3_log(ro['T']), ro['ab'], ro['lastResiduals'],
 print("gpu   ", rg['good'], orc.se3_log(rg['T']), rg['ab'], rg['lastResiduals'], rg['iterations'], rg['accepts'], "kernel ms", ctx.last_kernel_ms(), "wall", t1-t0)
 print("pose diff", orc.se3_log(orc.se3_mul(rg['T'], orc.se3_inv(ro['T']))))
 # batch throughput
-for B in (1,8,18,36,72):
-    ctx2=api.Context(synth.KITTI_K,w,h,n_tracker_slots=B,max_frames=2*B+2)
+for th in (64,128,256):
+ for cs in (1,2,8):
+  if th==64 and cs>1: continue
+  for B in (1,148,592,1184):
+    ctx2=api.Context(synth.KITTI_K,w,h,n_tracker_slots=B,max_frames=2*B+2,cluster_size=cs,track_threads=th)
     for i in range(B):
         ctx2.makeImages(2*i,seq.images[0]); ctx2.makeImages(2*i+1,seq.images[1])
         api.CoarseTracker(ctx2,i).setCoarseTrackingRef(2*i,p4,rh)
     for rep in range(3):
         T=np.tile(T0,(B,1)); ab=np.zeros((B,2))
         r=ctx2.trackBatch(list(range(B)),[2*i+1 for i in range(B)],T,ab)
-    print("batch",B,"kernel ms",ctx2.last_kernel_ms(),"fps",B/ctx2.last_kernel_ms()*1e3, "evals", r['evals'].sum())
+    d=np.abs(T-ro['T']).max()
+    ms=ctx2.last_kernel_ms()
+    print("threads",th,"cluster",cs,"batch",B,"kernel ms",round(ms,4),"fps",round(B/ms*1e3), "alg GB/s", round(r['evals'].sum()*64/ms/1e6,1), "maxdiff vs oracle", d, flush=True)
     ctx2.close()

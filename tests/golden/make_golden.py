@@ -1,0 +1,49 @@
+"""Generates tests/golden/*.npz.
+
+The reference ships no golden vectors and cannot be built or imported here, so these fixtures are
+REGRESSION PINS OF THE ORACLE (oracle/, parity unpinned), not reference outputs: they freeze the oracle's results on small
+seeded inputs so that (a) any drift of the oracle is caught on CPU and (b) the CUDA path is compared against a committed
+vector as well as against the live oracle.  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sdv_loam_b200  # noqa
+from sdv_loam_b200 import synth
+import orc
+
+WH = (640, 192); K = (383.4, 383.4, 312.0, 97.0)
+
+
+def main():
+    seq = synth.Sequence(2, seed=4242, K=K, wh=WH)
+    w, h = WH; L = orc.lib().orc_pyr_levels(w, h)
+    img0, img1 = seq.images
+    pts = synth.select_points(img0, seq.clouds[0], 600, seed=1)
+    p4 = np.concatenate([pts, np.full((len(pts), 1), 2e-3, np.float32)], 1).astype(np.float32)
+    rh = (np.arange(len(pts)) % 3 == 0).astype(np.int32)
+    f0, f1 = orc.Frame(img0, L), orc.Frame(img1, L)
+    tr = orc.CoarseTracker(w, h, L, K); tr.setCoarseTrackingRef(f0, p4, rh, 0.01, -1.5)
+    out = dict(img0=img0.astype(np.uint8), img1=img1.astype(np.uint8), pts4=p4, round_half=rh, K=np.array(K), ref_ab=np.array([0.01, -1.5]))
+    out["pyr_checksum"] = np.array([f1.dI(l).astype(np.float64).sum() for l in range(L)])
+    out["abs_checksum"] = np.array([f1.absSquaredGrad(l).astype(np.float64).sum() for l in range(L)])
+    out["pc_n"] = np.array([len(tr.cloud(l)[0]) for l in range(L)])
+    for l in range(L):
+        u, v, idp, col = tr.cloud(l); out[f"cloud{l}"] = np.stack([u, v, idp, col])
+    T = orc.se3_exp([0.01, -0.005, -0.45, 0.002, -0.003, 0.001])
+    for l in range(L):
+        rs = tr.calcRes(f1, l, T, 0.02, 1.0, 20.0); H, b = tr.calcGSSSE(l, T, 0.02, 1.0)
+        out[f"rs{l}"] = rs; out[f"H{l}"] = H; out[f"b{l}"] = b
+    out["T_eval"] = T
+    r = tr.trackNewestCoarse(f1, np.array([1, 0, 0, 0, 0, 0, 0.0]), [0.0, 0.0], L - 1)
+    out.update(track_good=np.array(r["good"]), track_T=r["T"], track_ab=r["ab"], track_lastRes=r["lastResiduals"], track_flow=r["flow"],
+               track_iterations=r["iterations"], track_accepts=r["accepts"], track_evals=r["evals"])
+    Rgt, tgt = synth.rel_pose(seq.R[0], seq.t[0], seq.R[1], seq.t[1])
+    out["T_gt"] = orc.se3_from_rt(Rgt, tgt)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tracker_small.npz"), **out)
+    print("track:", r["good"], orc.se3_log(r["T"]), "gt", orc.se3_log(out["T_gt"]), r["iterations"], r["accepts"], out["pc_n"])
+
+
+if __name__ == "__main__":
+    main()

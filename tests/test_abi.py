@@ -1,0 +1,47 @@
+"""The C-ABI library loads and exports every symbol include/sdv_b200.h declares (no compute calls; CPU-only)."""
+import ctypes
+import os
+import re
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "sdv_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import sdv_loam_b200
+    path = sdv_loam_b200.build_library()
+    lib = ctypes.CDLL(path)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in sdv_b200.h but not exported: {missing}"
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device sdv_create must fail loudly (SDV_ERR_CUDA), never fall back to a CPU path."""
+    from conftest import has_gpu
+    if has_gpu():
+        pytest.skip("GPU present")
+    from sdv_loam_b200 import api
+    with pytest.raises(api.SdvError):
+        api.Context((700.0, 700.0, 600.0, 180.0), 1200, 360)
+
+
+def test_pyr_levels_rule():
+    from sdv_loam_b200 import api
+    assert api.pyr_levels(1200, 360) == 4 and api.pyr_levels(1920, 1200) == 5 and api.pyr_levels(1400, 360) == 4
+
+
+def test_product_does_not_import_oracle():
+    pk = os.path.join(ROOT, "sdv-loam_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import orc" not in txt and "liborc" not in txt and "oracle/" not in txt.replace("independent of oracle/", ""), f

@@ -1,0 +1,196 @@
+"""GPU parity tests (-m gpu): CUDA path through the C-ABI vs the CPU oracle and the committed golden fixture.
+
+Tolerances (north_star): energy 1e-4 relative, pose 1e-3 m / 1e-3 rad.  We hold the kernels to much tighter bounds:
+pyramid and reference cloud bit-exact; counts exact; E, H, b 2e-5 relative; LM pose 1e-5.
+"""
+import os
+import numpy as np
+import pytest
+import orc
+from conftest import SMALL_K, SMALL_WH
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tracker_small.npz")
+ID7 = np.array([1, 0, 0, 0, 0, 0, 0.0])
+
+
+def _api():
+    import sdv_loam_b200  # noqa
+    from sdv_loam_b200 import api, synth
+    return api, synth
+
+
+def _pts(synth, seq, n, hdi=1e-3):
+    pts = synth.select_points(seq.images[0], seq.clouds[0], n)
+    return np.concatenate([pts, np.full((len(pts), 1), hdi, np.float32)], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("wh", [(640, 192), (1200, 360), (1400, 360), (1920, 1200), (96, 64)])
+def test_pyramid_bit_exact(wh):
+    """T1: makeImages on random images of the SURVEY §8 sizes — every level bit-exact, incl. the flat-index border wrap."""
+    api, _ = _api()
+    w, h = wh; L = api.pyr_levels(w, h)
+    img = np.random.default_rng(w * 7 + h).uniform(0, 255, (h, w)).astype(np.float32)
+    img[3, 5] = np.inf; img[h // 2, w // 2] = np.nan                       # non-finite gradients are zeroed (HessianBlocks.cpp:152-153)
+    ctx = api.Context((500.0, 500.0, w / 2.0, h / 2.0), w, h, max_frames=2)
+    ctx.makeImages(7, img); f = orc.Frame(img, L)
+    for l in range(L):
+        dI, ab = ctx.frameLevel(7, l); oI = f.dI(l); oa = f.absSquaredGrad(l)
+        inner = slice(1, (h >> l) - 1)                                      # rows 0 / h-1: dx,dy uninitialised in the reference
+        assert np.array_equal(dI[..., 0], oI[..., 0], equal_nan=True)
+        assert np.array_equal(dI[inner], oI[inner], equal_nan=True) and np.array_equal(ab[inner], oa[inner], equal_nan=True)
+    ctx.close()
+
+
+def test_coarse_depth_bit_exact(kitti_seq):
+    """T2: makeCoarseDepthL0 — colliding splats, both rounding rules, mixed weights; clouds identical on every level."""
+    api, synth = _api()
+    w, h = synth.KITTI_WH; L = 4
+    rng = np.random.default_rng(5)
+    p4 = _pts(synth, kitti_seq, 3000); n = len(p4)
+    p4[:, 3] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-1), n)).astype(np.float32)
+    dup = p4[rng.integers(0, n, 400)].copy(); dup[:, 2] *= rng.uniform(0.8, 1.2, 400).astype(np.float32)   # collisions
+    p4 = np.concatenate([p4, dup, dup[:50]]).astype(np.float32)
+    rh = (rng.uniform(size=len(p4)) < 0.4).astype(np.int32)
+    ctx = api.Context(synth.KITTI_K, w, h, max_frames=2); ctx.makeImages(0, kitti_seq.images[0])
+    tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(0, p4, rh, 0.0, 0.0)
+    f0 = orc.Frame(kitti_seq.images[0], L); otr = orc.CoarseTracker(w, h, L, synth.KITTI_K); otr.setCoarseTrackingRef(f0, p4, rh)
+    for l in range(L):
+        a, b = tr.cloud(l), otr.cloud(l)
+        assert len(a[0]) == len(b[0]) > 0
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    # empty reference: no points on any level, calcRes returns nE = 0 and NaN saturation ratio like the reference (0/0)
+    tr.setCoarseTrackingRef(0, np.zeros((0, 4), np.float32), np.zeros(0, np.int32))
+    assert all(len(tr.cloud(l)[0]) == 0 for l in range(L))
+    ctx.makeImages(1, kitti_seq.images[1])
+    rs = tr.calcRes(1, 0, ID7, 0, 0, 20.0)
+    assert rs[0] == 0 and rs[1] == 0 and np.isnan(rs[5])
+    with pytest.raises(api.SdvError):
+        tr.setCoarseTrackingRef(0, np.array([[1e6, 5, 0.1, 1e-3]], np.float32), np.zeros(1, np.int32))   # out-of-image splat refused
+    ctx.close()
+
+
+def _pair(api, synth, seq, K, wh, n, **ctxkw):
+    w, h = wh; L = api.pyr_levels(w, h)
+    p4 = _pts(synth, seq, n); rh = np.zeros(len(p4), np.int32)
+    ctx = api.Context(K, w, h, **ctxkw); ctx.makeImages(0, seq.images[0]); ctx.makeImages(1, seq.images[1])
+    tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(0, p4, rh, 0.0, 1.0)
+    f0, f1 = orc.Frame(seq.images[0], L), orc.Frame(seq.images[1], L)
+    otr = orc.CoarseTracker(w, h, L, K); otr.setCoarseTrackingRef(f0, p4, rh, 0.0, 1.0)
+    return ctx, tr, otr, f1, L
+
+
+@pytest.mark.parametrize("pose", ["identity", "near", "far", "behind"])
+def test_calcres_and_gs_vs_oracle(kitti_seq, pose):
+    """T3/T4: fused calcRes+calcGSSSE at/near/far from the optimum, all levels, two cutoffs."""
+    api, synth = _api()
+    ctx, tr, otr, f1, L = _pair(api, synth, kitti_seq, synth.KITTI_K, synth.KITTI_WH, 2000)
+    Tgt = orc.se3_from_rt(*synth.rel_pose(kitti_seq.R[0], kitti_seq.t[0], kitti_seq.R[1], kitti_seq.t[1]))
+    T = {"identity": ID7, "near": orc.se3_mul(orc.se3_exp([0.01, 0.0, 0.02, 1e-3, -1e-3, 5e-4]), Tgt),
+         "far": orc.se3_exp([0.3, -0.1, 0.5, 0.02, 0.03, -0.01]), "behind": orc.se3_exp([0, 0, -40.0, 0, 0, 0])}[pose]
+    for l in range(L):
+        for cutoff, (a, b) in ((20.0, (0.0, 0.0)), (40.0, (0.03, -2.0))):
+            ro = otr.calcRes(f1, l, T, a, b, cutoff); Ho, bo = otr.calcGSSSE(l, T, a, b)
+            rg = tr.calcRes(1, l, T, a, b, cutoff); Hg, bg = tr.calcGSSSE(l)
+            assert rg[1] == ro[1] and np.isclose(rg[5], ro[5], rtol=1e-6, equal_nan=True), (l, ro, rg)      # nE, nSat exact
+            assert np.isclose(rg[0], ro[0], rtol=2e-5) and np.allclose(rg[2:5], ro[2:5], rtol=1e-4, atol=1e-7)
+            if ro[1] - round(ro[5] * ro[1]) > 0:
+                assert np.linalg.norm(Hg - Ho) <= 2e-5 * np.linalg.norm(Ho) and np.linalg.norm(bg - bo) <= 2e-5 * np.linalg.norm(bo) + 1e-9
+            else:
+                assert np.all(np.isnan(Hg)) == np.all(np.isnan(Ho))
+    ctx.close()
+
+
+def test_golden_fixture_on_gpu():
+    """CUDA path vs the committed vectors (tests/golden/tracker_small.npz)."""
+    api, _ = _api()
+    g = np.load(GOLD); w, h = SMALL_WH; L = 4; K = tuple(g["K"])
+    ctx = api.Context(K, w, h, max_frames=2)
+    ctx.makeImages(0, g["img0"].astype(np.float32)); ctx.makeImages(1, g["img1"].astype(np.float32))
+    tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(0, g["pts4"], g["round_half"], *g["ref_ab"])
+    for l in range(L):
+        assert np.array_equal(np.stack(tr.cloud(l)), g[f"cloud{l}"])
+        dI, ab = ctx.frameLevel(1, l)
+        assert np.isclose(dI.astype(np.float64).sum(), g["pyr_checksum"][l], rtol=1e-12)
+        rs = tr.calcRes(1, l, g["T_eval"], 0.02, 1.0, 20.0); H, b = tr.calcGSSSE(l)
+        assert rs[1] == g[f"rs{l}"][1] and np.isclose(rs[0], g[f"rs{l}"][0], rtol=2e-5)
+        assert np.linalg.norm(H - g[f"H{l}"]) <= 2e-5 * np.linalg.norm(g[f"H{l}"])
+    r = tr.trackNewestCoarse(1, ID7, [0.0, 0.0])
+    assert r["good"] == bool(g["track_good"])
+    assert np.array_equal(r["iterations"], g["track_iterations"]) and np.array_equal(r["accepts"], g["track_accepts"])
+    assert np.allclose(r["T"], g["track_T"], atol=1e-5) and np.allclose(r["ab"], g["track_ab"], atol=1e-3)
+    assert np.allclose(r["lastResiduals"], g["track_lastRes"], rtol=1e-4, equal_nan=True)
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfg", [(128, 1), (64, 1), (256, 1), (128, 2), (256, 8), (256, 16)])
+def test_track_vs_oracle_all_launch_configs(kitti_seq, cfg):
+    """T5: device-resident trackNewestCoarse — same accept/reject sequence, pose 1e-5, residuals 1e-4 rel — for every
+    (threads, cluster size) configuration, incl. the DSMEM all-reduce path (cluster > 1)."""
+    api, synth = _api()
+    ctx, tr, otr, f1, L = _pair(api, synth, kitti_seq, synth.KITTI_K, synth.KITTI_WH, 2000, track_threads=cfg[0], cluster_size=cfg[1])
+    for T0, ab0 in ((ID7, (0.0, 0.0)), (orc.se3_exp([0.05, 0.02, -0.8, 0.004, -0.006, 0.002]), (0.02, 1.0))):
+        ro = otr.trackNewestCoarse(f1, T0, ab0, L - 1)
+        rg = tr.trackNewestCoarse(1, T0, ab0)
+        assert rg["good"] == ro["good"]
+        assert np.array_equal(rg["iterations"], ro["iterations"]) and np.array_equal(rg["accepts"], ro["accepts"]), (ro, rg)
+        assert np.array_equal(rg["evals"], ro["evals"])
+        err = orc.se3_log(orc.se3_mul(rg["T"], orc.se3_inv(ro["T"])))
+        assert np.abs(err).max() < 1e-5 and np.allclose(rg["ab"], ro["ab"], atol=1e-3)
+        assert np.allclose(rg["lastResiduals"], ro["lastResiduals"], rtol=1e-4, equal_nan=True)
+        assert np.allclose(rg["flow"], ro["flow"], rtol=1e-3, atol=1e-6)
+    # abort path (CoarseTracker.cpp:810): outputs untouched, finer levels NaN
+    ra = tr.trackNewestCoarse(1, ID7, (0.0, 0.0), minRes=np.full(5, 1e-3))
+    assert not ra["good"] and np.array_equal(ra["T"], ID7) and np.isnan(ra["lastResiduals"][0]) and np.isfinite(ra["lastResiduals"][L - 1])
+    ctx.close()
+
+
+def test_track_fixed_affine_modes(small_seq):
+    """affineOptModeA/B < 0 branches of the LM solve (CoarseTracker.cpp:726-748): 6x6, 7x7 and stitched 7x7."""
+    api, synth = _api()
+    for modes in ((-1.0, -1.0), (0.0, -1.0), (-1.0, 0.0)):
+        ctx, tr, otr, f1, L = _pair(api, synth, small_seq, SMALL_K, SMALL_WH, 800, affineOptModeA=modes[0], affineOptModeB=modes[1])
+        otr.settings(affA=modes[0], affB=modes[1])
+        ro = otr.trackNewestCoarse(f1, ID7, (0.0, 0.0), L - 1); rg = tr.trackNewestCoarse(1, ID7, (0.0, 0.0))
+        assert rg["good"] == ro["good"] and np.array_equal(rg["iterations"], ro["iterations"]) and np.array_equal(rg["accepts"], ro["accepts"])
+        assert np.abs(orc.se3_log(orc.se3_mul(rg["T"], orc.se3_inv(ro["T"])))).max() < 1e-5 and np.allclose(rg["ab"], ro["ab"], atol=1e-3)
+        ctx.close()
+
+
+def test_batch_equals_single_and_is_deterministic(kitti_seq):
+    """Batched mode: n jobs in one launch give bit-identical results to n single calls, and run-to-run (fixed-order reductions)."""
+    api, synth = _api()
+    w, h = synth.KITTI_WH; B = 5
+    ctx = api.Context(synth.KITTI_K, w, h, n_tracker_slots=B, max_frames=2 * B)
+    p4 = _pts(synth, kitti_seq, 2000)
+    for i in range(B):
+        ctx.makeImages(2 * i, kitti_seq.images[i % 2]); ctx.makeImages(2 * i + 1, kitti_seq.images[1 + i % 2])
+        api.CoarseTracker(ctx, i).setCoarseTrackingRef(2 * i, p4[: 1500 + 100 * i], np.zeros(1500 + 100 * i, np.int32))
+    singles = [api.CoarseTracker(ctx, i).trackNewestCoarse(2 * i + 1, ID7, (0.0, 0.0)) for i in range(B)]
+    for _ in range(2):
+        T = np.tile(ID7, (B, 1)); ab = np.zeros((B, 2))
+        r = ctx.trackBatch(list(range(B)), [2 * i + 1 for i in range(B)], T, ab)
+        for i in range(B):
+            assert np.array_equal(T[i], singles[i]["T"]) and np.array_equal(ab[i], singles[i]["ab"])
+            assert np.array_equal(r["lastResiduals"][i], singles[i]["lastResiduals"], equal_nan=True)
+    ctx.close()
+
+
+def test_properties_full_size(kitti_seq):
+    """Size-independent properties at BASELINE size: (i) self-alignment keeps identity with ~0 energy; (ii) energy is
+    invariant to a joint brightness offset absorbed by b; (iii) tracking converges to ground truth within tolerance."""
+    api, synth = _api()
+    w, h = synth.KITTI_WH
+    ctx = api.Context(synth.KITTI_K, w, h, max_frames=4)
+    ctx.makeImages(0, kitti_seq.images[0]); ctx.makeImages(1, kitti_seq.images[1]); ctx.makeImages(2, np.clip(kitti_seq.images[1] + 7.0, 0, 400))
+    p4 = _pts(synth, kitti_seq, 2000); tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(0, p4, np.zeros(len(p4), np.int32))
+    r = tr.trackNewestCoarse(0, ID7, (0.0, 0.0))
+    assert r["good"] and np.abs(orc.se3_log(r["T"])).max() < 1e-4 and r["lastResiduals"][0] < 0.05
+    r1 = tr.trackNewestCoarse(1, ID7, (0.0, 0.0)); r2 = tr.trackNewestCoarse(2, ID7, (0.0, 0.0))
+    assert np.abs(orc.se3_log(orc.se3_mul(r1["T"], orc.se3_inv(r2["T"])))).max() < 2e-4 and abs((r2["ab"][1] - r1["ab"][1]) - 7.0) < 0.05
+    assert np.isclose(r1["lastResiduals"][0], r2["lastResiduals"][0], rtol=1e-3)
+    Tgt = orc.se3_from_rt(*synth.rel_pose(kitti_seq.R[0], kitti_seq.t[0], kitti_seq.R[1], kitti_seq.t[1]))
+    err = orc.se3_log(orc.se3_mul(r1["T"], orc.se3_inv(Tgt)))
+    assert np.linalg.norm(err[:3]) < 5e-3 and np.linalg.norm(err[3:]) < 5e-4
+    ctx.close()
