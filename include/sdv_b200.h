@@ -61,6 +61,13 @@ int  sdv_sync(sdv_ctx* c);                                   /* drain the contex
  * builds dIp[lvl] = {I,dx,dy} and absSquaredGrad[lvl] for all levels on the device, keyed by a caller-chosen handle. */
 int  sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img_wh, float exposure);
 int  sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs_wh, const float* exposures);
+/* Uploads are ASYNCHRONOUS on a dedicated ingest stream so that they overlap the tracking of the previous batch: pinned host
+ * buffers must stay valid until the next call that synchronises (sdv_sync, any tracker/BA call, sdv_frame_download).
+ * _u8: level-0 input in the sensor wire format (sensor_msgs/Image mono8, what src/main.cpp:537-560 receives) — the
+ * u8->float conversion of the ingest (DatasetReader.h:152-155, Undistort crop without photometric calibration) is fused
+ * into the level-0 kernel; 4x less PCIe traffic.   _dev: level-0 images already in device memory (kernel-only timing). */
+int  sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs_wh, const float* exposures);
+int  sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int is_u8, const float* exposures);
 int  sdv_frame_release(sdv_ctx* c, uint64_t frame);
 /* test hook: copy one level back as AoS {I,dx,dy} (w*h*3 floats) and absSquaredGrad (w*h floats); either may be NULL */
 int  sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out);
@@ -104,6 +111,10 @@ int  sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint
                              sdv_track_stats* stats);
 /* device time of the last track / track_batch / calc_res launch in milliseconds (CUDA events on the context stream) */
 float sdv_last_kernel_ms(sdv_ctx* c);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long sdv_launch_count(sdv_ctx* c);
+/* bytes copied H2D and again D2H per trackNewestCoarse job (the job descriptor carries inputs and results) */
+int  sdv_track_job_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,10 @@ def _load():
     L.sdv_sync.argtypes = [_vp]
     L.sdv_frame_upload.argtypes = [_vp, C.c_uint64, _vp, C.c_float]
     L.sdv_frame_upload_batch.argtypes = [_vp, C.c_int, _u64p, C.POINTER(_vp), _f32p]
+    L.sdv_frame_upload_batch_u8.argtypes = [_vp, C.c_int, _u64p, C.POINTER(_vp), _f32p]
+    L.sdv_frame_build_batch_dev.argtypes = [_vp, C.c_int, _u64p, C.POINTER(_vp), C.c_int, _f32p]
+    L.sdv_track_job_bytes.argtypes = []
+    L.sdv_launch_count.argtypes = [_vp]; L.sdv_launch_count.restype = C.c_longlong
     L.sdv_frame_release.argtypes = [_vp, C.c_uint64]
     L.sdv_frame_download.argtypes = [_vp, C.c_uint64, C.c_int, _vp, _vp]
     L.sdv_tracker_set_ref.argtypes = [_vp, C.c_int, C.c_uint64, C.c_int, _f32p, _i32p, C.c_float, C.c_double, C.c_double]
@@ -69,6 +73,11 @@ LIB = _load()
 
 class SdvError(RuntimeError):
     pass
+
+
+def track_job_bytes() -> int:
+    """bytes copied H2D and D2H per trackNewestCoarse job descriptor"""
+    return int(LIB.sdv_track_job_bytes())
 
 
 def pyr_levels(w: int, h: int) -> int:
@@ -116,13 +125,22 @@ class Context:
         assert color.shape == (self.h, self.w)
         self._ck(LIB.sdv_frame_upload(self.p, frame_id, color.ctypes.data, exposure))
 
-    def makeImagesBatch(self, frame_ids, host_ptrs, exposures=None):
-        """host_ptrs: list of integer addresses of (h,w) float32 host buffers (pinned for full-rate H2D)."""
+    def makeImagesBatch(self, frame_ids, ptrs, exposures=None, u8=False, device=False):
+        """Batched makeImages.  ptrs: integer addresses of (h,w) buffers — host (pinned for full-rate, asynchronous H2D)
+        or device (device=True); float32, or mono8 when u8=True.  Asynchronous: see sdv_b200.h."""
         n = len(frame_ids)
         ids = np.ascontiguousarray(frame_ids, np.uint64)
-        arr = (_vp * n)(*host_ptrs)
+        arr = (_vp * n)(*ptrs)
         ex = np.ones(n, np.float32) if exposures is None else np.ascontiguousarray(exposures, np.float32)
-        self._ck(LIB.sdv_frame_upload_batch(self.p, n, ids, arr, ex))
+        if device:
+            self._ck(LIB.sdv_frame_build_batch_dev(self.p, n, ids, arr, 1 if u8 else 0, ex))
+        elif u8:
+            self._ck(LIB.sdv_frame_upload_batch_u8(self.p, n, ids, arr, ex))
+        else:
+            self._ck(LIB.sdv_frame_upload_batch(self.p, n, ids, arr, ex))
+
+    def launch_count(self) -> int:
+        return int(LIB.sdv_launch_count(self.p))
 
     def releaseFrame(self, frame_id: int):
         self._ck(LIB.sdv_frame_release(self.p, frame_id))

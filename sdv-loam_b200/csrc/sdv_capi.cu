@@ -59,6 +59,9 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   c->set = s; c->device = device; c->w = w; c->h = h; c->levels = levels;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming)); c->ingest_pending = false; c->launches = 0;
+  c->pyr_batch_dev = nullptr; c->pyr_batch_host = nullptr;
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
   memset(&c->tc, 0, sizeof(c->tc));
   c->tc.levels = levels; c->tc.huberTH = s.huberTH; c->tc.coarseCutoffTH = s.coarseCutoffTH;
@@ -71,7 +74,6 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   c->frame_texels = texels;
   c->frames.resize(s.max_frames);
   for (auto& f : c->frames) { f.used = false; CK(cudaMalloc(&f.base, texels*sizeof(float4))); for (int l=0;l<levels;l++) f.lvl[l] = f.base + c->lvl_off[l]; }
-  CK(cudaMalloc(&c->pyr_scratch, (size_t)w*h*sizeof(float)));
   // tracker slots
   c->slots.resize(s.n_tracker_slots);
   for (auto& t : c->slots) {
@@ -104,35 +106,48 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
 
 void sdv_destroy(sdv_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device); cudaStreamSynchronize(c->st);
+  cudaSetDevice(c->device); cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st);
   for (auto& f : c->frames) cudaFree(f.base);
   for (auto& t : c->slots) for (int l=0;l<c->levels;l++) cudaFree(t.pts[l]);
   for (int l=0;l<c->levels;l++) { cudaFree(c->cd_id[l]); cudaFree(c->cd_ws[l]); cudaFree(c->cd_id2[l]); cudaFree(c->cd_ws2[l]); }
   cudaFree(c->cd_owner); cudaFree(c->cd_counts); cudaFree(c->cd_scalars); cudaFreeHost(c->cd_scalars_host);
   cudaFree(c->cd_pts4); cudaFree(c->cd_round); cudaFree(c->cd_splats); cudaFree(c->cd_done);
-  cudaFree(c->pyr_scratch); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
+  cudaFree(c->pyr_batch_dev); cudaFreeHost(c->pyr_batch_host); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
   for (auto p : c->stage) cudaFree(p);
   ba_destroy(c);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaStreamDestroy(c->st);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_in); cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_in);
   delete c;
 }
 
-int sdv_sync(sdv_ctx* c) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
+int sdv_sync(sdv_ctx* c) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st_in)); CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
+long long sdv_launch_count(sdv_ctx* c) { return c ? c->launches : 0; }
+int sdv_track_job_bytes(void) { return (int)sizeof(TrackJob); }
 float sdv_last_kernel_ms(sdv_ctx* c) { return c ? c->last_ms : 0.f; }
 
 // ------------------------------------------------------------------------------------------------ frames
 static FrameDev* find_frame(sdv_ctx* c, uint64_t id) { auto it = c->frame_index.find(id); return it == c->frame_index.end() ? nullptr : &c->frames[it->second]; }
 
 static int ensure_stage(sdv_ctx* c, int n) {
-  while ((int)c->stage.size() < n) { float* p = nullptr; CK(cudaMalloc(&p, (size_t)c->w*c->h*sizeof(float))); c->stage.push_back(p); }
+  size_t fl = (size_t)c->w*c->h + pyramid_scratch_floats(c->w, c->h, c->levels);
+  while ((int)c->stage.size() < n) { float* p = nullptr; CK(cudaMalloc(&p, fl*sizeof(float))); c->stage.push_back(p); }
+  if (n > c->stage_cap) {
+    cudaFree(c->pyr_batch_dev); cudaFreeHost(c->pyr_batch_host); c->stage_cap = n;
+    CK(cudaMalloc(&c->pyr_batch_dev, (size_t)n*sizeof(PyrBatchHost))); CK(cudaMallocHost(&c->pyr_batch_host, (size_t)n*sizeof(PyrBatchHost)));
+  }
   return SDV_OK;
 }
 
-int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs, const float* exposures) {
+// kind: 0 host float, 1 host mono8, 2 device float, 3 device mono8.  Everything is enqueued on the ingest stream; the compute
+// stream picks it up through ev_in at the next tracker / BA call, so an upload overlaps the tracking of the previous batch.
+static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs, const float* exposures, int kind) {
   if (!c || n < 0 || !frames || !imgs) return SDV_ERR_ARG;
+  if (n == 0) return SDV_OK;
   CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->st_in));            // previous ingest (descriptor + staging buffers are reused) must have drained
   int rc = ensure_stage(c, n); if (rc) return rc;
+  const bool u8 = (kind & 1), dev = (kind & 2);
+  const size_t px = (size_t)c->w*c->h;
   for (int k=0;k<n;k++) {
     int idx = -1;
     auto it = c->frame_index.find(frames[k]);
@@ -140,11 +155,31 @@ int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const floa
     else { for (size_t i=0;i<c->frames.size();i++) if (!c->frames[i].used) { idx = (int)i; break; } }
     if (idx < 0) return ctx_fail(c, SDV_ERR_CAPACITY, "frame pool exhausted (max_frames=%d)", (int)c->frames.size());
     FrameDev& f = c->frames[idx]; f.used = true; f.id = frames[k]; f.exposure = exposures ? exposures[k] : 1.0f; c->frame_index[frames[k]] = idx;
-    CK(cudaMemcpyAsync(c->stage[k], imgs[k], (size_t)c->w*c->h*sizeof(float), cudaMemcpyHostToDevice, c->st));
-    launch_pyramid(c->stage[k], c->pyr_scratch, f.lvl, c->w, c->h, c->levels, c->st);
+    PyrBatchHost& b = c->pyr_batch_host[k];
+    b.scratch = c->stage[k] + px; b.out = f.base;
+    if (dev) b.src = imgs[k];
+    else { b.src = c->stage[k]; CK(cudaMemcpyAsync(c->stage[k], imgs[k], px*(u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, c->st_in)); }
   }
+  CK(cudaMemcpyAsync(c->pyr_batch_dev, c->pyr_batch_host, (size_t)n*sizeof(PyrBatchHost), cudaMemcpyHostToDevice, c->st_in));
+  launch_pyramid_batch(c->pyr_batch_dev, n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev_in, c->st_in)); c->ingest_pending = true;
+  c->launches += 2*c->levels - 1;
   return SDV_OK;
+}
+static int join_ingest(sdv_ctx* c) {              // make the compute stream see every upload enqueued so far
+  if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
+  return SDV_OK;
+}
+
+int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs, const float* exposures) {
+  return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 0);
+}
+int sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs, const float* exposures) {
+  return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 1);
+}
+int sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int is_u8, const float* exposures) {
+  return frame_ingest(c, n, frames, imgs_dev, exposures, 2 | (is_u8 ? 1 : 0));
 }
 int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposure) {
   const float* imgs[1] = {img}; return sdv_frame_upload_batch(c, 1, &frame, imgs, &exposure);
@@ -158,6 +193,7 @@ int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, floa
   if (!c || lvl < 0 || lvl >= c->levels) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   FrameDev* f = find_frame(c, frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
   int n = (c->w>>lvl)*(c->h>>lvl); float *d3 = nullptr, *da = nullptr;
   if (dI3_out) CK(cudaMalloc(&d3, (size_t)3*n*sizeof(float)));
   if (abs_out) CK(cudaMalloc(&da, (size_t)n*sizeof(float)));
@@ -177,6 +213,7 @@ int sdv_tracker_set_cloud(sdv_ctx* c, int slot, uint64_t ref_frame, int lvl, int
   TrackerSlot& t = c->slots[slot];
   if (n > t.cap[lvl]) return ctx_fail(c, SDV_ERR_CAPACITY, "cloud of %d points exceeds capacity %d", n, t.cap[lvl]);
   FrameDev* f = find_frame(c, ref_frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown ref frame");
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
   float* tmp = nullptr; CK(cudaMalloc(&tmp, (size_t)4*(n+1)*sizeof(float)));
   const float* src[4] = {u, v, idepth, color};
   for (int k=0;k<4;k++) CK(cudaMemcpyAsync(tmp + (size_t)k*n, src[k], (size_t)n*sizeof(float), cudaMemcpyHostToDevice, c->st));
@@ -213,6 +250,7 @@ int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const f
     CK(cudaMalloc(&c->cd_pts4, (size_t)4*c->cd_cap*sizeof(float))); CK(cudaMalloc(&c->cd_round, (size_t)c->cd_cap*sizeof(int)));
     CK(cudaMalloc(&c->cd_splats, (size_t)c->cd_cap*sizeof(float4))); CK(cudaMalloc(&c->cd_done, (size_t)c->cd_cap*sizeof(int)));
   }
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
   const int w = c->w, h = c->h;
   CK(cudaMemsetAsync(c->cd_id[0], 0, (size_t)w*h*sizeof(float), c->st));
   CK(cudaMemsetAsync(c->cd_ws[0], 0, (size_t)w*h*sizeof(float), c->st));
@@ -252,7 +290,9 @@ int sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, cons
   FrameDev* f = find_frame(c, new_frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown new frame");
   if (t.ref_frame == ~0ull) return ctx_fail(c, SDV_ERR_STATE, "tracker slot %d has no reference", slot);
   EvalParams ep; make_eval_params(se3_from7(T), a, b, t.refExposure, f->exposure, t.ref_a, t.ref_b, c->tc.geom[lvl], lvl, cutoffTH, c->tc.huberTH, ep);
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
   CK(cudaEventRecord(c->ev0, c->st));
+  c->launches += 1;
   launch_coarse_res_gs(t.pts[lvl], t.npts[lvl], f->lvl[lvl], c->tc.geom[lvl], ep, c->partials, c->ticket, c->totals_dev, c->st);
   CK(cudaEventRecord(c->ev1, c->st));
   CK(cudaMemcpyAsync(c->totals_host, c->totals_dev, kNAcc*sizeof(double), cudaMemcpyDeviceToHost, c->st));
@@ -292,6 +332,8 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
     for (int i=0;i<5;i++) J.minRes[i] = minRes ? minRes[5*k+i] : nan("");
     J.coarsest = coarsest;
   }
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
+  c->launches += 1;
   CK(cudaMemcpyAsync(c->jobs_dev, c->jobs_host, (size_t)n*sizeof(TrackJob), cudaMemcpyHostToDevice, c->st));
   CK(cudaEventRecord(c->ev0, c->st));
   CK(launch_track_cluster(c->jobs_dev, n, c->tc_dev, c->set.cluster_size, c->set.track_threads, c->st));

@@ -20,12 +20,12 @@ struct BAState;                           // sdv_ba.cuh
 } // namespace sdv
 
 struct sdv_ctx {
-  int device; cudaStream_t st; cudaEvent_t ev0, ev1;
+  int device; cudaStream_t st, st_in; cudaEvent_t ev0, ev1, ev_in; bool ingest_pending; long long launches;
   int w, h, levels; sdv_settings set;
   sdv::TrackConst tc; sdv::TrackConst* tc_dev;
   size_t lvl_off[sdv::kLevels]; size_t frame_texels;
   std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
-  std::vector<float*> stage; int stage_cap; float* pyr_scratch;
+  std::vector<float*> stage; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev; sdv::PyrBatchHost* pyr_batch_host;
   std::vector<sdv::TrackerSlot> slots;
   double* partials; unsigned int* ticket; double* totals_dev; double* totals_host;
   float *cd_id[sdv::kLevels], *cd_ws[sdv::kLevels], *cd_id2[sdv::kLevels], *cd_ws2[sdv::kLevels];

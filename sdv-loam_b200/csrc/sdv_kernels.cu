@@ -13,16 +13,27 @@ namespace cg = cooperative_groups;
 namespace sdv {
 
 // ================================================================================================ pyramid
+// Batched over frames (blockIdx.y = frame of the batch): one launch per level for the whole batch.
 // gradient + pack of one level from a planar intensity image (HessianBlocks.cpp:147-165).  Flat-index neighbours on
 // purpose: at x=0 / x=w-1 the reference reads across the row boundary (idx±1), and so do we.
-__global__ void __launch_bounds__(256) pyr_grad_kernel(const float* __restrict__ I, float4* __restrict__ out, int w, int h) {
-  int n = w*h;
+struct PyrBatch { const void* src; float* scratch; float4* out; };   // per frame: level-0 input (float or u8), planar scratch, pyramid base
+
+template <typename T> __device__ __forceinline__ float px_load(const T* p, int i);
+template <> __device__ __forceinline__ float px_load<float>(const float* p, int i) { return __ldg(p + i); }
+template <> __device__ __forceinline__ float px_load<unsigned char>(const unsigned char* p, int i) { return (float)__ldg(p + i); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pyr_grad_kernel(const PyrBatch* __restrict__ batch, int use_scratch, size_t scratch_off, size_t out_off, int w, int h) {
+  const PyrBatch b = batch[blockIdx.y];
+  const T* I = use_scratch ? reinterpret_cast<const T*>(b.scratch + scratch_off) : reinterpret_cast<const T*>(b.src);
+  float4* out = b.out + out_off;
+  const int n = w*h;
   for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
-    float c = I[idx];
+    float c = px_load<T>(I, idx);
     float dx = 0.f, dy = 0.f, ab = 0.f;
     if (idx >= w && idx < w*(h-1)) {
-      dx = 0.5f*(I[idx+1] - I[idx-1]);
-      dy = 0.5f*(I[idx+w] - I[idx-w]);
+      dx = 0.5f*(px_load<T>(I, idx+1) - px_load<T>(I, idx-1));
+      dy = 0.5f*(px_load<T>(I, idx+w) - px_load<T>(I, idx-w));
       if (!isfinite(dx)) dx = 0;
       if (!isfinite(dy)) dy = 0;
       ab = dx*dx + dy*dy;
@@ -31,30 +42,38 @@ __global__ void __launch_bounds__(256) pyr_grad_kernel(const float* __restrict__
   }
 }
 // 2x2 box filter of intensities (HessianBlocks.cpp:137-145): 0.25f*(((a+b)+c)+d)
-__global__ void __launch_bounds__(256) pyr_down_kernel(const float* __restrict__ Iprev, float* __restrict__ I, int wl, int hl, int wlm1) {
-  int n = wl*hl;
+template <typename T>
+__global__ void __launch_bounds__(256) pyr_down_kernel(const PyrBatch* __restrict__ batch, int src_is_scratch, size_t src_off, size_t dst_off, int wl, int hl, int wlm1) {
+  const PyrBatch b = batch[blockIdx.y];
+  const T* Iprev = src_is_scratch ? reinterpret_cast<const T*>(b.scratch + src_off) : reinterpret_cast<const T*>(b.src);
+  float* I = b.scratch + dst_off;
+  const int n = wl*hl;
   for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
     int y = idx / wl, x = idx - y*wl;
-    const float* b = Iprev + 2*x + 2*y*wlm1;
-    float2 r0 = *reinterpret_cast<const float2*>(b);
-    float2 r1 = *reinterpret_cast<const float2*>(b + wlm1);
-    I[idx] = 0.25f * (((r0.x + r0.y) + r1.x) + r1.y);
+    int bi = 2*x + 2*y*wlm1;
+    float a0 = px_load<T>(Iprev, bi), a1 = px_load<T>(Iprev, bi+1), a2 = px_load<T>(Iprev, bi+wlm1), a3 = px_load<T>(Iprev, bi+wlm1+1);
+    I[idx] = 0.25f * (((a0 + a1) + a2) + a3);
   }
 }
 
-void launch_pyramid(const float* color_dev, float* scratch /*>= w*h floats*/, float4* const* levels_out, int w, int h, int levels, cudaStream_t st) {
-  // level 0 straight from the input; level l from the planar intensity of level l-1 kept in `scratch` (ping-pong halves)
-  const float* Iprev = color_dev;
-  float* bufA = scratch; float* bufB = scratch + (size_t)(w/2)*(h/2);
-  int wl = w, hl = h;
+size_t pyramid_scratch_floats(int w, int h, int levels) { size_t n = 0; for (int l = 1; l < levels; l++) n += (size_t)(w>>l)*(h>>l); return n + 4; }
+
+// batch_dev: nframes PyrBatch descriptors in device memory.  src_u8: level-0 input is mono8 (sensor_msgs/Image wire format) instead of float.
+void launch_pyramid_batch(const void* batch_dev_v, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st) {
+  const PyrBatch* batch_dev = reinterpret_cast<const PyrBatch*>(batch_dev_v);
+  if (nframes <= 0) return;
+  size_t soff = 0, prev_soff = 0; int wl = w, hl = h;
   for (int l = 0; l < levels; l++) {
-    int n = wl*hl; int grid = (n + 255)/256; if (grid > 148*16) grid = 148*16;
-    pyr_grad_kernel<<<grid, 256, 0, st>>>(Iprev, levels_out[l], wl, hl);
+    int n = wl*hl; int gx = (n + 255)/256; int cap = (148*16 + nframes - 1)/nframes; if (cap < 4) cap = 4; if (gx > cap) gx = cap;
+    dim3 grid(gx, nframes);
+    if (l == 0 && src_u8) pyr_grad_kernel<unsigned char><<<grid, 256, 0, st>>>(batch_dev, 0, 0, lvl_off[0], wl, hl);
+    else pyr_grad_kernel<float><<<grid, 256, 0, st>>>(batch_dev, l > 0, prev_soff, lvl_off[l], wl, hl);
     if (l+1 < levels) {
-      int wn = wl>>1, hn = hl>>1; float* dst = (l & 1) ? bufB : bufA;
-      int gn = (wn*hn + 255)/256; if (gn > 148*16) gn = 148*16;
-      pyr_down_kernel<<<gn, 256, 0, st>>>(Iprev, dst, wn, hn, wl);
-      Iprev = dst; wl = wn; hl = hn;
+      int wn = wl>>1, hn = hl>>1; int gn = (wn*hn + 255)/256; if (gn > cap) gn = cap;
+      dim3 g2(gn, nframes);
+      if (l == 0 && src_u8) pyr_down_kernel<unsigned char><<<g2, 256, 0, st>>>(batch_dev, 0, 0, soff, wn, hn, wl);
+      else pyr_down_kernel<float><<<g2, 256, 0, st>>>(batch_dev, l > 0, prev_soff, soff, wn, hn, wl);
+      prev_soff = soff; soff += (size_t)wn*hn; wl = wn; hl = hn;
     }
   }
 }

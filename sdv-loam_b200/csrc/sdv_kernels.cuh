@@ -5,7 +5,9 @@
 namespace sdv {
 
 // pyramid (FrameHessian::makeImages, HessianBlocks.cpp:107-167)
-void launch_pyramid(const float* color_dev, float* scratch, float4* const* levels_out, int w, int h, int levels, cudaStream_t st);
+struct PyrBatchHost { const void* src; float* scratch; float4* out; };   // mirrors PyrBatch in sdv_kernels.cu
+size_t pyramid_scratch_floats(int w, int h, int levels);
+void launch_pyramid_batch(const void* batch_dev, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st);
 void launch_unpack_level(const float4* in, float* dI3, float* ab, int n, cudaStream_t st);
 
 // fused calcRes + calcGSSSE, one launch (CoarseTracker.cpp:486-634, 427-484)
