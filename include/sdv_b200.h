@@ -116,6 +116,51 @@ long long sdv_launch_count(sdv_ctx* c);
 /* bytes copied H2D and again D2H per trackNewestCoarse job (the job descriptor carries inputs and results) */
 int  sdv_track_job_bytes(void);
 
+
+/* =====================================================================================================================
+ * Sliding-window back-end: EnergyFunctional + FullSystem::optimize on a FLATTENED window.
+ * The reference's pointer graph (FrameHessian -> PointHessian -> PointFrameResidual and the EF* mirrors) stays on the host;
+ * the caller passes it in the reference's own iteration order — frames = ef->frames, points = ef->allPoints (contiguous per
+ * host frame, EnergyFunctional.cpp:761-782), residuals grouped per point in residualsAll order (res_begin is the CSR row
+ * pointer).  This is the makeIDX / insertFrame / insertPoint / insertResidual surface (EnergyFunctional.h:51-72) in one call.
+ * ===================================================================================================================== */
+/* frames + calibration + marginalisation prior:  EnergyFunctional::insertFrame :365-398, setAdjointsF :21-71, HM/bM :88-89.
+ * state10 / state_zero10 = FrameHessian::state / state_zero (Vec10: 6 pose, a, b, 2 unused; HessianBlocks.h:141-175),
+ * T_evalPT7 = worldToCam_evalPT, calib_value_scaled = CalibHessian::value_scaled {fx,fy,cx,cy}; HM (dim x dim, row-major), bM may be NULL. */
+int  sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const double* T_evalPT7, const double* state10, const double* state_zero10,
+                       const float* ab_exposure, const int32_t* frameID, const float* frameEnergyTH, const double calib_value_scaled[4],
+                       const double* HM, const double* bM);
+/* points + residuals: PointHessian {u,v,idepth,idepth_zero,color[8],weights[8],hasDepthPrior,isFromSensor} (HessianBlocks.h:361-465),
+ * PointFrameResidual {host,target,hasMatcher,matcher,isNew} (Residuals.h:30-83).  Runs setPrecalcValues (FullSystem.cpp:1358-1368). */
+int  sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, const float* idepth_zero, const float* color8, const float* weights8,
+                       const int32_t* host, const int32_t* hasDepthPrior, const int32_t* isFromSensor, const int32_t* res_begin,
+                       int nR, const int32_t* r_point, const int32_t* r_host, const int32_t* r_target, const int32_t* r_hasMatcher,
+                       const float* r_matcher, const int32_t* r_isNew);
+/* Vec3 FullSystem::linearizeAll(bool fixLinearization)  FullSystemOptimize.cpp:99-159 -> PointFrameResidual::linearize Residuals.cpp:60-224
+ * (+ setNewFrameEnergyTH :63-97; with fix: applyRes + the isNew / toRemove bookkeeping of linearizeAll_Reductor :23-55) */
+int  sdv_ba_reset_oob(sdv_ctx* c);                                 /* PointFrameResidual::resetOOB on every residual (optimize :361-362) */
+int  sdv_ba_linearize(sdv_ctx* c, int fix, double* energy_out);
+int  sdv_ba_apply_res(sdv_ctx* c);                                 /* applyRes_Reductor :57-61 -> Residuals.cpp:252-274, EFResidual::takeDataF */
+int  sdv_ba_energy(sdv_ctx* c, double* EL_out, double* EM_out);    /* EnergyFunctional::calcLEnergyF_MT :333-350, calcMEnergyF :284-293 */
+/* void EnergyFunctional::solveSystemF(int iteration, double lambda, CalibHessian*)  EnergyFunctional.cpp:650-759
+ * (accumulateAF/LF/SCF, stitch, diag-scaled LDLT, orthogonalize for iteration>=2, resubstituteF_MT); x_out[CPARS+6nF] = ef->lastX */
+int  sdv_ba_solve(sdv_ctx* c, int iteration, double lambda, double* x_out);
+int  sdv_ba_backup(sdv_ctx* c);                                    /* FullSystem::backupState  FullSystemOptimize.cpp:255-300 */
+int  sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak_out);   /* doStepFromBackup :165-250 / loadSateBackup :303-321 */
+/* float FullSystem::optimize(int mnumOptIts)  FullSystemOptimize.cpp:344-502 — the whole GN loop incl. the final re-anchoring and
+ * linearizeAll(true).  Returns sqrt(lastEnergy / resInA) like the reference. */
+int  sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out);
+/* read-back of what the reference leaves in FrameHessian/CalibHessian, PointHessian/EFPoint, PointFrameResidual/EFResidual, EnergyFunctional */
+int  sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* step10, float* frameEnergyTH, double* PRE_worldToCam7,
+                       double calib_value[4], double calib_step[4]);
+int  sdv_ba_get_points(sdv_ctx* c, float* idepth, float* step, float* HdiF, float* bdSumF, float* maxRelBaseline, int32_t* numGoodResiduals, float* idepth_hessian);
+/* J24 per residual: {resF[2], Jpdxi[0][6], Jpdxi[1][6], Jpdc[0][4], Jpdc[1][4], Jpdd[2]} = the live part of RawResidualJacobian.h:7-36;
+ * energies3 = {state_energy, state_NewEnergy, state_NewEnergyWithOutlier}; states: 0 IN, 1 OOB, 2 OUTLIER (Residuals.h:21) */
+int  sdv_ba_get_residuals(sdv_ctx* c, int32_t* state_state, int32_t* state_NewState, float* energies3, int32_t* isActive, float* J24, float* efJ24,
+                          float* JpJdF8, float* center3, int32_t* toRemove);
+int  sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
+int  sdv_ba_get_precalc(sdv_ctx* c, int host, int target, float out27[27], double adHost36[36], double adTarget36[36], float adHTdelta6[6]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,3 +159,106 @@ class CoarseTracker:
     def __del__(self):
         if getattr(self, "p", None):
             lib().orc_tracker_destroy(self.p); self.p = None
+
+
+# ------------------------------------------------------------------------------------------------ back-end window
+def _ba_protos():
+    L = lib()
+    if getattr(L, "_ba_done", False):
+        return L
+    L.orc_ba_create.restype = C.c_void_p; L.orc_ba_create.argtypes = [C.c_int, C.c_int]
+    L.orc_ba_destroy.argtypes = [C.c_void_p]
+    L.orc_ba_set_calib.argtypes = [C.c_void_p, _f64p]
+    L.orc_ba_add_frame.argtypes = [C.c_void_p, C.c_void_p, _f64p, _f64p, _f64p, C.c_float, C.c_int, C.c_float]
+    L.orc_ba_set_points.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p, _i32p]
+    L.orc_ba_set_residuals.argtypes = [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _f32p, _i32p]
+    L.orc_ba_set_prior.argtypes = [C.c_void_p, _f64p, _f64p]
+    for nm in ("orc_ba_init", "orc_ba_reset_oob", "orc_ba_apply_res", "orc_ba_backup", "orc_ba_load_backup"):
+        getattr(L, nm).argtypes = [C.c_void_p]
+    L.orc_ba_linearize_all.argtypes = [C.c_void_p, C.c_int]; L.orc_ba_linearize_all.restype = C.c_double
+    L.orc_ba_energy_L.argtypes = [C.c_void_p]; L.orc_ba_energy_L.restype = C.c_double
+    L.orc_ba_energy_M.argtypes = [C.c_void_p]; L.orc_ba_energy_M.restype = C.c_double
+    L.orc_ba_get_residuals.argtypes = [C.c_void_p, _i32p, _i32p, _f64p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p]
+    L.orc_ba_accumulate.argtypes = [C.c_void_p, _f64p, _f64p, _f64p, _f64p]
+    L.orc_ba_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, _f64p, _f64p, _f64p]
+    L.orc_ba_do_step.argtypes = [C.c_void_p, C.c_float]
+    L.orc_ba_get_points.argtypes = [C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p]
+    L.orc_ba_get_frames.argtypes = [C.c_void_p, _f64p, _f64p, _f64p, _f32p, _f64p]
+    L.orc_ba_get_calib.argtypes = [C.c_void_p, _f64p, _f64p]
+    L.orc_ba_get_precalc.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p]
+    L.orc_ba_optimize.argtypes = [C.c_void_p, C.c_int, _i32p]; L.orc_ba_optimize.restype = C.c_float
+    L.orc_ba_linearize_calls.argtypes = [C.c_void_p]; L.orc_ba_linearize_calls.restype = C.c_longlong
+    L._ba_done = True
+    return L
+
+
+class BAWindow:
+    """The flattened sliding window of synth.make_ba_window() loaded into the oracle back-end (orc_ba.hpp)."""
+
+    def __init__(self, win: dict, frames):
+        L = _ba_protos(); self.L = L; self.win = win; self._frames = frames
+        w, h = win["wh"]; self.nF = win["nF"]; self.nP = len(win["uv"]); self.nR = len(win["r_point"]); self.n = 4 + 6 * self.nF
+        self.p = L.orc_ba_create(w, h)
+        L.orc_ba_set_calib(self.p, np.ascontiguousarray(win["K"], np.float64))
+        for i in range(self.nF):
+            L.orc_ba_add_frame(self.p, frames[i].p, np.ascontiguousarray(win["T_eval"][i]), np.ascontiguousarray(win["state"][i]),
+                               np.ascontiguousarray(win["state_zero"][i]), float(win["ab_exposure"][i]), int(win["frameID"][i]), float(win["frameEnergyTH"][i]))
+        c = lambda k, t: np.ascontiguousarray(win[k], t)
+        L.orc_ba_set_points(self.p, self.nP, c("uv", np.float32), c("idepth", np.float32), c("idepth_zero", np.float32), c("color", np.float32),
+                            c("weights", np.float32), c("host", np.int32), c("hasDepthPrior", np.int32), c("isFromSensor", np.int32), c("res_begin", np.int32))
+        L.orc_ba_set_residuals(self.p, self.nR, c("r_point", np.int32), c("r_host", np.int32), c("r_target", np.int32), c("r_hasMatcher", np.int32),
+                               c("r_matcher", np.float32), c("r_isNew", np.int32))
+        L.orc_ba_set_prior(self.p, c("HM", np.float64), c("bM", np.float64))
+        L.orc_ba_init(self.p)
+
+    def reset_oob(self): self.L.orc_ba_reset_oob(self.p)
+    def linearizeAll(self, fix=False): return self.L.orc_ba_linearize_all(self.p, 1 if fix else 0)
+    def applyRes(self): self.L.orc_ba_apply_res(self.p)
+    def calcLEnergy(self): return self.L.orc_ba_energy_L(self.p)
+    def calcMEnergy(self): return self.L.orc_ba_energy_M(self.p)
+    def backupState(self): self.L.orc_ba_backup(self.p)
+    def doStepFromBackup(self, f=1.0): return bool(self.L.orc_ba_do_step(self.p, f))
+    def loadStateBackup(self): self.L.orc_ba_load_backup(self.p)
+
+    def residuals(self):
+        n = self.nR
+        o = dict(state=np.zeros(n, np.int32), new_state=np.zeros(n, np.int32), energies=np.zeros((n, 3)), active=np.zeros(n, np.int32),
+                 J=np.zeros((n, 24), np.float32), efJ=np.zeros((n, 24), np.float32), JpJdF=np.zeros((n, 8), np.float32),
+                 center=np.zeros((n, 3), np.float32), toRemove=np.zeros(n, np.int32))
+        self.L.orc_ba_get_residuals(self.p, o["state"], o["new_state"], o["energies"], o["active"], o["J"], o["efJ"], o["JpJdF"], o["center"], o["toRemove"])
+        return o
+
+    def accumulate(self):
+        n = self.n; HA = np.zeros((n, n)); bA = np.zeros(n); Hsc = np.zeros((n, n)); bsc = np.zeros(n)
+        self.L.orc_ba_accumulate(self.p, HA, bA, Hsc, bsc); return HA, bA, Hsc, bsc
+
+    def solveSystem(self, iteration, lam):
+        n = self.n; x = np.zeros(n); HS = np.zeros((n, n)); bS = np.zeros(n)
+        self.L.orc_ba_solve(self.p, iteration, lam, x, HS, bS); return x, HS, bS
+
+    def points(self):
+        n = self.nP
+        o = dict(idepth=np.zeros(n, np.float32), step=np.zeros(n, np.float32), HdiF=np.zeros(n, np.float32), bdSumF=np.zeros(n, np.float32),
+                 maxRelBaseline=np.zeros(n, np.float32), numGood=np.zeros(n, np.int32), idepth_hessian=np.zeros(n, np.float32))
+        self.L.orc_ba_get_points(self.p, o["idepth"], o["step"], o["HdiF"], o["bdSumF"], o["maxRelBaseline"], o["numGood"], o["idepth_hessian"]); return o
+
+    def frames(self):
+        n = self.nF
+        o = dict(T_eval=np.zeros((n, 7)), state=np.zeros((n, 10)), step=np.zeros((n, 10)), frameEnergyTH=np.zeros(n, np.float32), PRE_worldToCam=np.zeros((n, 7)))
+        self.L.orc_ba_get_frames(self.p, o["T_eval"], o["state"], o["step"], o["frameEnergyTH"], o["PRE_worldToCam"]); return o
+
+    def calib(self):
+        v = np.zeros(4); s = np.zeros(4); self.L.orc_ba_get_calib(self.p, v, s); return v, s
+
+    def precalc(self, host, target):
+        o = np.zeros(27, np.float32); aH = np.zeros(36); aT = np.zeros(36); d = np.zeros(6, np.float32)
+        self.L.orc_ba_get_precalc(self.p, host, target, o, aH, aT, d)
+        return dict(KRKi=o[:9].reshape(3, 3), Kt=o[9:12], R0=o[12:21].reshape(3, 3), t0=o[21:24], aff=o[24:26], b0=o[26], adHost=aH.reshape(6, 6), adTarget=aT.reshape(6, 6), adHTdelta=d)
+
+    def optimize(self, its=6):
+        st = np.zeros(2, np.int32); rmse = self.L.orc_ba_optimize(self.p, its, st)
+        return dict(rmse=float(rmse), iterations=int(st[0]), accepts=int(st[1]), linearize_calls=int(self.L.orc_ba_linearize_calls(self.p)))
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            self.L.orc_ba_destroy(self.p); self.p = None

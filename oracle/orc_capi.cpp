@@ -90,3 +90,73 @@ int orc_tracker_track(void* t, void* new_frame, double T_io[7], double ab_io[2],
 }
 
 } // extern "C"
+
+// ================================================================================================ back-end (BA) window
+#include "orc_ba.hpp"
+extern "C" {
+void* orc_ba_create(int w, int h) { BAWindow* b = new BAWindow(); b->w=w; b->h=h; return b; }
+void orc_ba_destroy(void* p) { delete (BAWindow*)p; }
+void orc_ba_set_calib(void* p, const double vs[4]) { ((BAWindow*)p)->setCalibScaled(vs); }
+void orc_ba_add_frame(void* p, void* img, const double T_eval[7], const double state[10], const double state_zero[10], float ab_exposure, int frameID, float frameEnergyTH) {
+  BAWindow* b=(BAWindow*)p; BAFrame f; f.worldToCam_evalPT = se3_from(T_eval);
+  for (int i=0;i<10;i++) { f.state[i]=state[i]; f.state_zero[i]=state_zero[i]; f.state_backup[i]=state[i]; f.step[i]=0; }
+  f.ab_exposure=ab_exposure; f.frameID=frameID; f.frameEnergyTH=frameEnergyTH; f.img=(Frame*)img; b->frames.push_back(f);
+}
+void orc_ba_set_points(void* p, int nP, const float* uv, const float* idepth, const float* idepth_zero, const float* color, const float* weights,
+                       const int* host, const int* hasDepthPrior, const int* isFromSensor, const int* res_begin) {
+  BAWindow* b=(BAWindow*)p; b->points.assign(nP, BAPoint());
+  for (int i=0;i<nP;i++) { BAPoint& q=b->points[i]; q.u=uv[2*i]; q.v=uv[2*i+1]; q.idepth=idepth[i]; q.idepth_zero=idepth_zero[i];
+    for (int k=0;k<8;k++) { q.color[k]=color[8*i+k]; q.weights[k]=weights[8*i+k]; }
+    q.host=host[i]; q.hasDepthPrior=hasDepthPrior[i]; q.isFromSensor=isFromSensor[i]; q.res_begin=res_begin[i]; q.res_end=res_begin[i+1]; }
+}
+void orc_ba_set_residuals(void* p, int nR, const int* point, const int* host, const int* target, const int* hasMatcher, const float* matcher, const int* isNew) {
+  BAWindow* b=(BAWindow*)p; b->res.assign(nR, BARes());
+  for (int i=0;i<nR;i++) { BARes& r=b->res[i]; std::memset(&r.J,0,sizeof(RawJ)); std::memset(&r.efJ,0,sizeof(RawJ)); std::memset(r.JpJdF,0,sizeof(r.JpJdF));
+    std::memset(r.centerProjectedTo,0,sizeof(r.centerProjectedTo)); std::memset(r.projectedTo,0,sizeof(r.projectedTo));
+    r.point=point[i]; r.host=host[i]; r.target=target[i]; r.hasMatcher=hasMatcher[i]; r.matcher[0]=matcher[2*i]; r.matcher[1]=matcher[2*i+1]; r.isNew=isNew[i]; }
+}
+void orc_ba_set_prior(void* p, const double* HM, const double* bM) { BAWindow* b=(BAWindow*)p; int n=b->dim(); b->HM.assign(HM,HM+(size_t)n*n); b->bM.assign(bM,bM+n); }
+void orc_ba_init(void* p) { ((BAWindow*)p)->init(); }
+void orc_ba_reset_oob(void* p) { for (auto& r : ((BAWindow*)p)->res) { r.state_NewEnergy=r.state_energy=0; r.state_NewState=RS_OUTLIER; r.state_state=RS_IN; } }
+double orc_ba_linearize_all(void* p, int fix) { return ((BAWindow*)p)->linearizeAll(fix!=0); }
+void orc_ba_apply_res(void* p) { BAWindow* b=(BAWindow*)p; for (auto& r : b->res) b->applyRes(r); }
+double orc_ba_energy_L(void* p) { return ((BAWindow*)p)->calcLEnergy(); }
+double orc_ba_energy_M(void* p) { return ((BAWindow*)p)->calcMEnergy(); }
+// J layout per residual: 24 floats {resF[2], Jpdxi[0][6], Jpdxi[1][6], Jpdc[0][4], Jpdc[1][4], Jpdd[2]}
+static void packJ(const RawJ& J, float* o) { o[0]=J.resF[0]; o[1]=J.resF[1]; for(int i=0;i<6;i++){o[2+i]=J.Jpdxi[0][i]; o[8+i]=J.Jpdxi[1][i];} for(int i=0;i<4;i++){o[14+i]=J.Jpdc[0][i]; o[18+i]=J.Jpdc[1][i];} o[22]=J.Jpdd[0]; o[23]=J.Jpdd[1]; }
+void orc_ba_get_residuals(void* p, int* state_state, int* state_NewState, double* energies3, int* isActive, float* J24, float* efJ24, float* JpJdF8, float* center3, int* toRemove) {
+  BAWindow* b=(BAWindow*)p; int n=(int)b->res.size();
+  for (int i=0;i<n;i++) { const BARes& r=b->res[i]; state_state[i]=r.state_state; state_NewState[i]=r.state_NewState;
+    energies3[3*i]=r.state_energy; energies3[3*i+1]=r.state_NewEnergy; energies3[3*i+2]=r.state_NewEnergyWithOutlier; isActive[i]=r.isActive;
+    packJ(r.J, J24+24*i); packJ(r.efJ, efJ24+24*i); for(int k=0;k<8;k++) JpJdF8[8*i+k]=r.JpJdF[k]; for(int k=0;k<3;k++) center3[3*i+k]=r.centerProjectedTo[k]; toRemove[i]=r.toRemove; }
+}
+void orc_ba_accumulate(void* p, double* HA, double* bA, double* Hsc, double* bsc) {
+  BAWindow* b=(BAWindow*)p; std::vector<double> h1,b1,h2,b2; b->accumulateA(h1,b1); b->accumulateSC(h2,b2);
+  std::copy(h1.begin(),h1.end(),HA); std::copy(b1.begin(),b1.end(),bA); std::copy(h2.begin(),h2.end(),Hsc); std::copy(b2.begin(),b2.end(),bsc);
+}
+void orc_ba_solve(void* p, int iteration, double lambda, double* x, double* HS, double* bS) {
+  BAWindow* b=(BAWindow*)p; b->solveSystem(iteration, lambda); int n=b->dim();
+  std::copy(b->lastX.begin(), b->lastX.end(), x); if (HS) std::copy(b->lastHS.begin(), b->lastHS.end(), HS); if (bS) std::copy(b->lastbS.begin(), b->lastbS.end(), bS); (void)n;
+}
+void orc_ba_backup(void* p) { ((BAWindow*)p)->backupState(); }
+int  orc_ba_do_step(void* p, float stepfac) { return ((BAWindow*)p)->doStepFromBackup(stepfac) ? 1 : 0; }
+void orc_ba_load_backup(void* p) { ((BAWindow*)p)->loadStateBackup(); }
+void orc_ba_get_points(void* p, float* idepth, float* step, float* HdiF, float* bdSumF, float* maxRelBaseline, int* numGood, float* idepth_hessian) {
+  BAWindow* b=(BAWindow*)p; int n=(int)b->points.size();
+  for (int i=0;i<n;i++) { const BAPoint& q=b->points[i]; idepth[i]=q.idepth; step[i]=q.step; HdiF[i]=q.HdiF; bdSumF[i]=q.bdSumF; maxRelBaseline[i]=q.maxRelBaseline; numGood[i]=q.numGoodResiduals; idepth_hessian[i]=q.idepth_hessian; }
+}
+void orc_ba_get_frames(void* p, double* T_eval7, double* state10, double* step10, float* frameEnergyTH, double* PRE_w2c7) {
+  BAWindow* b=(BAWindow*)p; int n=b->nF();
+  for (int i=0;i<n;i++) { const BAFrame& f=b->frames[i]; se3_to(f.worldToCam_evalPT, T_eval7+7*i); se3_to(f.PRE_worldToCam, PRE_w2c7+7*i);
+    for (int k=0;k<10;k++) { state10[10*i+k]=f.state[k]; step10[10*i+k]=f.step[k]; } frameEnergyTH[i]=f.frameEnergyTH; }
+}
+void orc_ba_get_calib(void* p, double value[4], double step[4]) { BAWindow* b=(BAWindow*)p; for (int i=0;i<4;i++) { value[i]=b->c_value[i]; step[i]=b->c_step[i]; } }
+void orc_ba_get_precalc(void* p, int host, int target, float* out /*9 KRKi, 3 Kt, 9 R0, 3 t0, 2 aff, 1 b0 = 27*/, double* adH36, double* adT36, float* adHTdelta6) {
+  BAWindow* b=(BAWindow*)p; int n=b->nF(); const Precalc& c=b->precalc[(size_t)host*n+target];
+  for(int i=0;i<3;i++) for(int j=0;j<3;j++) { out[i*3+j]=c.PRE_KRKiTll.m[i][j]; out[12+i*3+j]=c.PRE_RTll_0.m[i][j]; }
+  for(int i=0;i<3;i++) { out[9+i]=c.PRE_KtTll.v[i]; out[21+i]=c.PRE_tTll_0.v[i]; } out[24]=c.PRE_aff_mode[0]; out[25]=c.PRE_aff_mode[1]; out[26]=c.PRE_b0_mode;
+  int idx=host+target*n; for(int i=0;i<36;i++) { adH36[i]=b->adHost[(size_t)idx*36+i]; adT36[i]=b->adTarget[(size_t)idx*36+i]; } for(int i=0;i<6;i++) adHTdelta6[i]=b->adHTdeltaF[(size_t)idx*6+i];
+}
+float orc_ba_optimize(void* p, int its, int* stats2) { BAWindow* b=(BAWindow*)p; float r=b->optimize(its); if (stats2) { stats2[0]=b->opt_iterations; stats2[1]=b->opt_accepts; } return r; }
+long long orc_ba_linearize_calls(void* p) { return ((BAWindow*)p)->linearize_calls; }
+}

@@ -208,3 +208,91 @@ class CoarseTracker:
         r = self.ctx.trackBatch([self.slot], [new_frame_id], T, abv, coarsest, mr)
         return dict(good=bool(r["good"][0]), T=T[0], ab=abv[0], lastResiduals=r["lastResiduals"][0], flow=r["flow"][0],
                     evals=r["evals"][0], iterations=r["iterations"][0], accepts=r["accepts"][0])
+
+
+# ------------------------------------------------------------------------------------------------ back-end
+def _ba_protos():
+    L = LIB
+    if getattr(L, "_ba_done", False):
+        return
+    L.sdv_ba_set_window.argtypes = [_vp, C.c_int, _u64p, _f64p, _f64p, _f64p, _f32p, _i32p, _f32p, _f64p, _f64p, _f64p]
+    L.sdv_ba_set_points.argtypes = [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p, _i32p, C.c_int, _i32p, _i32p, _i32p, _i32p, _f32p, _i32p]
+    L.sdv_ba_reset_oob.argtypes = [_vp]; L.sdv_ba_apply_res.argtypes = [_vp]; L.sdv_ba_backup.argtypes = [_vp]
+    L.sdv_ba_linearize.argtypes = [_vp, C.c_int, C.POINTER(C.c_double)]
+    L.sdv_ba_energy.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.sdv_ba_solve.argtypes = [_vp, C.c_int, C.c_double, _f64p]
+    L.sdv_ba_step.argtypes = [_vp, C.c_float, C.c_int, C.POINTER(C.c_int)]
+    L.sdv_ba_optimize.argtypes = [_vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.sdv_ba_get_frames.argtypes = [_vp, _f64p, _f64p, _f64p, _f32p, _f64p, _f64p, _f64p]
+    L.sdv_ba_get_points.argtypes = [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p]
+    L.sdv_ba_get_residuals.argtypes = [_vp, _i32p, _i32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p]
+    L.sdv_ba_get_system.argtypes = [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
+    L.sdv_ba_get_precalc.argtypes = [_vp, C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p]
+    L._ba_done = True
+
+
+class EnergyFunctional:
+    """Mirror of the reference back-end surface (OptimizationBackend/EnergyFunctional.h:51-72 + FullSystem::optimize/linearizeAll)
+    over a flattened window dict (see sdv_b200.h; synth.make_ba_window builds one).  frame_ids[i] = device frame handle of KF i."""
+
+    def __init__(self, ctx: Context, win: dict, frame_ids):
+        _ba_protos(); self.ctx = ctx; self.win = win
+        self.nF = win["nF"]; self.nP = len(win["uv"]); self.nR = len(win["r_point"]); self.n = 4 + 6 * self.nF
+        c = lambda k, t: np.ascontiguousarray(win[k], t)
+        ctx._ck(LIB.sdv_ba_set_window(ctx.p, self.nF, np.ascontiguousarray(frame_ids, np.uint64), c("T_eval", np.float64), c("state", np.float64),
+                                      c("state_zero", np.float64), c("ab_exposure", np.float32), c("frameID", np.int32), c("frameEnergyTH", np.float32),
+                                      c("K", np.float64), c("HM", np.float64), c("bM", np.float64)))
+        ctx._ck(LIB.sdv_ba_set_points(ctx.p, self.nP, c("uv", np.float32), c("idepth", np.float32), c("idepth_zero", np.float32), c("color", np.float32),
+                                      c("weights", np.float32), c("host", np.int32), c("hasDepthPrior", np.int32), c("isFromSensor", np.int32), c("res_begin", np.int32),
+                                      self.nR, c("r_point", np.int32), c("r_host", np.int32), c("r_target", np.int32), c("r_hasMatcher", np.int32),
+                                      c("r_matcher", np.float32), c("r_isNew", np.int32)))
+
+    def reset_oob(self): self.ctx._ck(LIB.sdv_ba_reset_oob(self.ctx.p))
+    def linearizeAll(self, fix=False):
+        e = C.c_double(0); self.ctx._ck(LIB.sdv_ba_linearize(self.ctx.p, 1 if fix else 0, C.byref(e))); return e.value
+    def applyRes(self): self.ctx._ck(LIB.sdv_ba_apply_res(self.ctx.p))
+    def energies(self):
+        a, b = C.c_double(0), C.c_double(0); self.ctx._ck(LIB.sdv_ba_energy(self.ctx.p, C.byref(a), C.byref(b))); return a.value, b.value
+    def calcLEnergy(self): return self.energies()[0]
+    def calcMEnergy(self): return self.energies()[1]
+    def backupState(self): self.ctx._ck(LIB.sdv_ba_backup(self.ctx.p))
+    def doStepFromBackup(self, f=1.0):
+        cb = C.c_int(0); self.ctx._ck(LIB.sdv_ba_step(self.ctx.p, f, 0, C.byref(cb))); return bool(cb.value)
+    def loadStateBackup(self):
+        cb = C.c_int(0); self.ctx._ck(LIB.sdv_ba_step(self.ctx.p, 1.0, 1, C.byref(cb)))
+
+    def solveSystem(self, iteration, lam):
+        n = self.n; x = np.zeros(n); self.ctx._ck(LIB.sdv_ba_solve(self.ctx.p, iteration, lam, x))
+        HA = np.zeros((n, n)); bA = np.zeros(n); Hsc = np.zeros((n, n)); bsc = np.zeros(n); HS = np.zeros((n, n)); bS = np.zeros(n)
+        self.ctx._ck(LIB.sdv_ba_get_system(self.ctx.p, HA, bA, Hsc, bsc, HS, bS))
+        return x, HS, bS, (HA, bA, Hsc, bsc)
+
+    def optimize(self, its=6):
+        r = C.c_float(0); i = C.c_int32(0); a = C.c_int32(0)
+        self.ctx._ck(LIB.sdv_ba_optimize(self.ctx.p, its, C.byref(r), C.byref(i), C.byref(a)))
+        return dict(rmse=float(r.value), iterations=int(i.value), accepts=int(a.value), ms=self.ctx.last_kernel_ms())
+
+    def residuals(self):
+        n = self.nR
+        o = dict(state=np.zeros(n, np.int32), new_state=np.zeros(n, np.int32), energies=np.zeros((n, 3), np.float32), active=np.zeros(n, np.int32),
+                 J=np.zeros((n, 24), np.float32), efJ=np.zeros((n, 24), np.float32), JpJdF=np.zeros((n, 8), np.float32),
+                 center=np.zeros((n, 3), np.float32), toRemove=np.zeros(n, np.int32))
+        self.ctx._ck(LIB.sdv_ba_get_residuals(self.ctx.p, o["state"], o["new_state"], o["energies"], o["active"], o["J"], o["efJ"], o["JpJdF"], o["center"], o["toRemove"]))
+        return o
+
+    def points(self):
+        n = self.nP
+        o = dict(idepth=np.zeros(n, np.float32), step=np.zeros(n, np.float32), HdiF=np.zeros(n, np.float32), bdSumF=np.zeros(n, np.float32),
+                 maxRelBaseline=np.zeros(n, np.float32), numGood=np.zeros(n, np.int32), idepth_hessian=np.zeros(n, np.float32))
+        self.ctx._ck(LIB.sdv_ba_get_points(self.ctx.p, o["idepth"], o["step"], o["HdiF"], o["bdSumF"], o["maxRelBaseline"], o["numGood"], o["idepth_hessian"])); return o
+
+    def frames(self):
+        n = self.nF
+        o = dict(T_eval=np.zeros((n, 7)), state=np.zeros((n, 10)), step=np.zeros((n, 10)), frameEnergyTH=np.zeros(n, np.float32), PRE_worldToCam=np.zeros((n, 7)),
+                 calib_value=np.zeros(4), calib_step=np.zeros(4))
+        self.ctx._ck(LIB.sdv_ba_get_frames(self.ctx.p, o["T_eval"], o["state"], o["step"], o["frameEnergyTH"], o["PRE_worldToCam"], o["calib_value"], o["calib_step"])); return o
+
+    def precalc(self, host, target):
+        o = np.zeros(27, np.float32); aH = np.zeros(36); aT = np.zeros(36); d = np.zeros(6, np.float32)
+        self.ctx._ck(LIB.sdv_ba_get_precalc(self.ctx.p, host, target, o, aH, aT, d))
+        return dict(KRKi=o[:9].reshape(3, 3), Kt=o[9:12], R0=o[12:21].reshape(3, 3), t0=o[21:24], aff=o[24:26], b0=o[26], adHost=aH.reshape(6, 6), adTarget=aT.reshape(6, 6), adHTdelta=d)

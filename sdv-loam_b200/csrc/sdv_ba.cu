@@ -1,3 +1,299 @@
-// sdv_ba.cu — sliding-window back-end (placeholder until the BA kernels land; keeps the link closed)
+// sdv_ba.cu — host side of the sliding-window back-end: window upload (the makeIDX mirror), the Gauss-Newton loop of
+// FullSystem::optimize (FullSystemOptimize.cpp:344-502) driven over the kernels of sdv_ba_kernels.cu, and the C-ABI.
+// Only control flow lives here (accept/reject, lambda schedule, break test); every number is produced on the device.
+#include "../../include/sdv_b200.h"
 #include "sdv_ctx.cuh"
-namespace sdv { void ba_destroy(sdv_ctx*) {} }
+#include "sdv_ba.cuh"
+#include <cstring>
+#include <cstddef>
+#include <vector>
+#include <cmath>
+
+using namespace sdv;
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(c, SDV_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+
+namespace sdv {
+void ba_destroy(sdv_ctx* c) {
+  if (!c || !c->ba) return;
+  BAState* b = c->ba;
+  cudaFree(b->hdr); cudaFreeHost(b->hdr_host); cudaFree(b->pool); cudaFree(b->partials); cudaFree(b->thbuf); cudaFree(b->thcount);
+  delete b; c->ba = nullptr;
+}
+}
+
+static int ba_get(sdv_ctx* c, BAState** out) {
+  if (!c->ba) {
+    BAState* b = new BAState(); memset(b, 0, sizeof(*b)); c->ba = b;
+    CK(cudaMalloc(&b->hdr, sizeof(BAHeader))); CK(cudaMemset(b->hdr, 0, sizeof(BAHeader)));
+    CK(cudaMallocHost(&b->hdr_host, sizeof(BAHeader))); memset(b->hdr_host, 0, sizeof(BAHeader));
+    CK(cudaMalloc(&b->thcount, sizeof(int))); CK(cudaMemset(b->thcount, 0, sizeof(int)));
+  }
+  *out = c->ba; return SDV_OK;
+}
+
+template <typename T> static T* bump(char*& p, size_t n) { T* r = reinterpret_cast<T*>(p); p += ((n*sizeof(T) + 255)/256)*256; return r; }
+
+static size_t ba_layout(BAState* b, char* base, int cp, int cr) {
+  char* p = base;
+  BAPointsDev& P = b->P; BAResDev& R = b->R;
+  P.uv = bump<float2>(p, cp); P.idepth = bump<float>(p, cp); P.idepth_zero = bump<float>(p, cp); P.idepth_backup = bump<float>(p, cp); P.step = bump<float>(p, cp);
+  P.color = bump<float>(p, (size_t)cp*8); P.weights = bump<float>(p, (size_t)cp*8);
+  P.host = bump<int>(p, cp); P.hasDepthPrior = bump<int>(p, cp); P.isFromSensor = bump<int>(p, cp); P.res_begin = bump<int>(p, cp+1);
+  P.priorF = bump<float>(p, cp); P.deltaF = bump<float>(p, cp); P.HdiF = bump<float>(p, cp); P.bdSumF = bump<float>(p, cp);
+  P.Hdd_accAF = bump<float>(p, cp); P.bd_accAF = bump<float>(p, cp); P.Hcd_accAF = bump<float>(p, (size_t)cp*4);
+  P.idepth_hessian = bump<float>(p, cp); P.maxRelBaseline = bump<float>(p, cp); P.numGoodResiduals = bump<int>(p, cp); P.ngood = bump<int>(p, cp);
+  P.res_of_target = bump<int>(p, (size_t)cp*kMaxF);
+  R.point = bump<int>(p, cr); R.host = bump<int>(p, cr); R.target = bump<int>(p, cr); R.hasMatcher = bump<int>(p, cr); R.matcher = bump<float2>(p, cr); R.isNew = bump<int>(p, cr);
+  R.state_state = bump<int>(p, cr); R.state_NewState = bump<int>(p, cr); R.state_energy = bump<float>(p, cr); R.state_NewEnergy = bump<float>(p, cr); R.state_NewEnergyWithOutlier = bump<float>(p, cr);
+  R.isActive = bump<int>(p, cr); R.toRemove = bump<int>(p, cr);
+  R.J = bump<float>(p, (size_t)cr*24); R.efJ = bump<float>(p, (size_t)cr*24); R.JpJdF = bump<float>(p, (size_t)cr*8); R.center = bump<float>(p, (size_t)cr*3);
+  R.pair_begin = bump<int>(p, kMaxF*kMaxF+1); R.pair_res = bump<int>(p, cr); R.host_begin = bump<int>(p, kMaxF+1);
+  return (size_t)(p - base);
+}
+static int ba_alloc(sdv_ctx* c, BAState* b, int nP, int nR, int nF) {
+  if (nP <= b->capP && nR <= b->capR) return SDV_OK;
+  int cp = nP + nP/4 + 256, cr = nR + nR/4 + 1024;
+  cudaFree(b->pool); cudaFree(b->partials); cudaFree(b->thbuf); b->pool = nullptr; b->partials = nullptr; b->thbuf = nullptr; b->capP = b->capR = 0;
+  size_t bytes = ba_layout(b, nullptr, cp, cr);
+  CK(cudaMalloc(&b->pool, bytes)); CK(cudaMemset(b->pool, 0, bytes)); b->pool_bytes = bytes;
+  ba_layout(b, (char*)b->pool, cp, cr);
+  CK(cudaMalloc(&b->partials, (size_t)((cr + 127)/128 + 1)*sizeof(double)));
+  CK(cudaMalloc(&b->thbuf, (size_t)cr*sizeof(float)));
+  b->capP = cp; b->capR = cr; (void)nF;
+  return SDV_OK;
+}
+
+static int ba_pull_scalars(sdv_ctx* c, BAState* b) {                        // energyP .. ticket
+  const size_t off = offsetof(BAHeader, energyP), len = sizeof(BAHeader) - off;
+  CK(cudaMemcpyAsync((char*)b->hdr_host + off, (char*)b->hdr + off, len, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  return SDV_OK;
+}
+
+extern "C" {
+
+int sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const double* T_evalPT7, const double* state10, const double* state_zero10,
+                      const float* ab_exposure, const int32_t* frameID, const float* frameEnergyTH, const double calib_value_scaled[4],
+                      const double* HM, const double* bM) {
+  if (!c || nF < 1 || nF > SDV_MAX_FRAMES_WINDOW || !frame_ids || !T_evalPT7 || !state10 || !state_zero10 || !calib_value_scaled) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  BAState* b; int rc = ba_get(c, &b); if (rc) return rc;
+  BAHeader* H = b->hdr_host; memset(H, 0, sizeof(BAHeader));
+  H->nF = nF; H->w = c->w; H->h = c->h; H->dim = kCP + 6*nF; b->nF = nF;
+  BASettingsDev& s = H->set;
+  s.huberTH = c->set.huberTH; s.outlierTHSumComponent = c->set.outlierTHSumComponent; s.idepthFixPrior = c->set.idepthFixPrior;
+  s.initialRotPrior = 1e11f; s.initialTransPrior = 1e10f; s.initialCalibHessian = 5e9f;            // settings.cpp:23-27
+  s.frameEnergyTHConstWeight = 0.5f; s.frameEnergyTHN = 0.7f; s.frameEnergyTHFacMedian = 1.5f; s.overallEnergyTHWeight = 1;   // :108-111
+  s.thOptIterations = 1.2f; s.minOptIterations = 1; s.solverModeDelta = 0.00001;                  // :56-57, :35
+  BACalibDev& cal = H->calib;                                                                       // CalibHessian ctor: setValueScaled + value_zero = value
+  const float SFI = 1.0f/50.0f;
+  for (int i=0;i<4;i++) { cal.value_scaled[i] = calib_value_scaled[i]; cal.sf[i] = (float)calib_value_scaled[i]; cal.value[i] = SFI*calib_value_scaled[i];
+    cal.value_zero[i] = cal.value[i]; cal.vmvz[i] = 0; cal.step[i] = 0; cal.value_backup[i] = cal.value[i]; }
+  cal.si[0] = 1.0f/cal.sf[0]; cal.si[1] = 1.0f/cal.sf[1]; cal.si[2] = -cal.sf[2]/cal.sf[0]; cal.si[3] = -cal.sf[3]/cal.sf[1];
+  for (int f=0; f<nF; f++) {
+    auto it = c->frame_index.find(frame_ids[f]); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "BA frame %d: unknown frame handle", f);
+    BAFrameDev& F = H->frames[f];
+    F.evalPT = se3_from7(T_evalPT7 + 7*f);
+    for (int i=0;i<10;i++) { F.state[i] = state10[10*f+i]; F.state_zero[i] = state_zero10[10*f+i]; F.state_backup[i] = F.state[i]; F.step[i] = 0; }
+    F.ab_exposure = ab_exposure ? ab_exposure[f] : 1.0f; F.frameID = frameID ? frameID[f] : f; F.frameEnergyTH = frameEnergyTH ? frameEnergyTH[f] : 8*8*8;
+    F.img0 = c->frames[it->second].lvl[0];
+  }
+  const int N = H->dim;
+  if (HM) memcpy(H->HM, HM, (size_t)N*N*sizeof(double));
+  if (bM) memcpy(H->bM, bM, (size_t)N*sizeof(double));
+  CK(cudaMemcpyAsync(b->hdr, H, sizeof(BAHeader), cudaMemcpyHostToDevice, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return SDV_OK;
+}
+
+int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, const float* idepth_zero, const float* color8, const float* weights8,
+                      const int32_t* host, const int32_t* hasDepthPrior, const int32_t* isFromSensor, const int32_t* res_begin,
+                      int nR, const int32_t* r_point, const int32_t* r_host, const int32_t* r_target, const int32_t* r_hasMatcher,
+                      const float* r_matcher, const int32_t* r_isNew) {
+  if (!c || !c->ba || nP < 0 || nR < 0) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device));
+  BAState* b = c->ba; const int nF = b->nF;
+  int rc = ba_alloc(c, b, nP, nR, nF); if (rc) return rc;
+  // ---- makeIDX mirror (EnergyFunctional.cpp:761-782): validate the flattening and build the index lists the kernels walk
+  std::vector<int> rot((size_t)nP*kMaxF, -1), pair_begin(kMaxF*kMaxF+1, 0), pair_res(nR), host_begin(kMaxF+1, 0);
+  for (int p=0;p<nP;p++) {
+    if (host[p] < 0 || host[p] >= nF || (p > 0 && host[p] < host[p-1])) return ctx_fail(c, SDV_ERR_ARG, "points must be grouped by host frame in frame order (ef->allPoints order)");
+    if (res_begin[p] > res_begin[p+1]) return ctx_fail(c, SDV_ERR_ARG, "res_begin not monotone");
+    for (int r=res_begin[p]; r<res_begin[p+1]; r++) {
+      if (r_point[r] != p || r_host[r] != host[p] || r_target[r] < 0 || r_target[r] >= nF || r_target[r] == host[p]) return ctx_fail(c, SDV_ERR_ARG, "residual %d inconsistent with its point", r);
+      if (rot[(size_t)p*kMaxF + r_target[r]] >= 0) return ctx_fail(c, SDV_ERR_ARG, "two residuals of point %d share a target", p);
+      rot[(size_t)p*kMaxF + r_target[r]] = r;
+    }
+    host_begin[host[p]+1] = p+1;
+  }
+  if (nP > 0 && (res_begin[0] != 0 || res_begin[nP] != nR)) return ctx_fail(c, SDV_ERR_ARG, "res_begin must span all residuals");
+  for (int f=1; f<=nF; f++) if (host_begin[f] < host_begin[f-1]) host_begin[f] = host_begin[f-1];
+  for (int r=0;r<nR;r++) pair_begin[r_host[r] + nF*r_target[r] + 1]++;
+  for (int k=0;k<nF*nF;k++) pair_begin[k+1] += pair_begin[k];
+  { std::vector<int> cur(pair_begin.begin(), pair_begin.end()-1); for (int r=0;r<nR;r++) pair_res[cur[r_host[r] + nF*r_target[r]]++] = r; }
+  BAPointsDev& P = b->P; BAResDev& R = b->R; cudaStream_t st = c->st;
+#define UP(dst, src, n, T) do { if ((n) > 0) CK(cudaMemcpyAsync(dst, src, (size_t)(n)*sizeof(T), cudaMemcpyHostToDevice, st)); } while (0)
+  UP(P.uv, uv, (size_t)nP*2, float); UP(P.idepth, idepth, nP, float); UP(P.idepth_zero, idepth_zero, nP, float); UP(P.idepth_backup, idepth, nP, float);
+  UP(P.color, color8, (size_t)nP*8, float); UP(P.weights, weights8, (size_t)nP*8, float);
+  UP(P.host, host, nP, int); UP(P.hasDepthPrior, hasDepthPrior, nP, int); UP(P.isFromSensor, isFromSensor, nP, int); UP(P.res_begin, res_begin, nP+1, int);
+  UP(P.res_of_target, rot.data(), (size_t)nP*kMaxF, int);
+  UP(R.point, r_point, nR, int); UP(R.host, r_host, nR, int); UP(R.target, r_target, nR, int); UP(R.hasMatcher, r_hasMatcher, nR, int);
+  UP(R.matcher, r_matcher, (size_t)nR*2, float); UP(R.isNew, r_isNew, nR, int);
+  UP(R.pair_begin, pair_begin.data(), nF*nF+1, int); UP(R.pair_res, pair_res.data(), nR, int); UP(R.host_begin, host_begin.data(), nF+1, int);
+#undef UP
+  if (nP > 0) { CK(cudaMemsetAsync(P.step, 0, (size_t)nP*sizeof(float), st)); CK(cudaMemsetAsync(P.maxRelBaseline, 0, (size_t)nP*sizeof(float), st)); CK(cudaMemsetAsync(P.numGoodResiduals, 0, (size_t)nP*sizeof(int), st)); }
+  if (nR > 0) { CK(cudaMemsetAsync(R.isActive, 0, (size_t)nR*sizeof(int), st)); CK(cudaMemsetAsync(R.toRemove, 0, (size_t)nR*sizeof(int), st));
+    CK(cudaMemsetAsync(R.J, 0, (size_t)nR*24*sizeof(float), st)); CK(cudaMemsetAsync(R.efJ, 0, (size_t)nR*24*sizeof(float), st)); CK(cudaMemsetAsync(R.JpJdF, 0, (size_t)nR*8*sizeof(float), st));
+    CK(cudaMemsetAsync(R.center, 0, (size_t)nR*3*sizeof(float), st)); }
+  b->nP = nP; b->nR = nR;
+  b->hdr_host->nP = nP; b->hdr_host->nR = nR;
+  CK(cudaMemcpyAsync(&b->hdr->nP, &b->hdr_host->nP, 2*sizeof(int), cudaMemcpyHostToDevice, st));
+  if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
+  launch_ba_setup(b->hdr, P, nP, st);
+  launch_ba_reset_oob(R, nR, st);
+  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
+  c->launches += 3;
+  return SDV_OK;
+}
+
+int sdv_ba_reset_oob(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); launch_ba_reset_oob(c->ba->R, c->ba->nR, c->st); c->launches++; return SDV_OK; }
+
+int sdv_ba_linearize(sdv_ctx* c, int fix, double* energy) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  launch_ba_linearize(b->hdr, b->P, b->R, b->nR, fix, b->partials, b->thbuf, b->thcount, c->st); c->launches += 2;
+  int rc = ba_pull_scalars(c, b); if (rc) return rc;
+  if (energy) *energy = b->hdr_host->energyP;
+  return SDV_OK;
+}
+int sdv_ba_apply_res(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); launch_ba_apply(c->ba->R, c->ba->nR, c->st); c->launches++; CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
+int sdv_ba_energy(sdv_ctx* c, double* EL, double* EM) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  launch_ba_energies(b->hdr, b->P, b->nP, c->st); c->launches++;
+  int rc = ba_pull_scalars(c, b); if (rc) return rc;
+  if (EL) *EL = b->hdr_host->energyL; if (EM) *EM = b->hdr_host->energyM;
+  return SDV_OK;
+}
+int sdv_ba_solve(sdv_ctx* c, int iteration, double lambda, double* x_out) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  launch_ba_accumulate(b->hdr, b->P, b->R, b->nF, b->nP, c->st);
+  launch_ba_solve(b->hdr, b->P, b->R, b->nP, iteration, lambda, c->st); c->launches += 5;
+  if (x_out) { CK(cudaMemcpyAsync(x_out, b->hdr->lastX, (size_t)(kCP+6*b->nF)*sizeof(double), cudaMemcpyDeviceToHost, c->st)); }
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  return SDV_OK;
+}
+int sdv_ba_backup(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); launch_ba_backup(c->ba->hdr, c->ba->P, c->ba->nP, c->st); c->launches++; return SDV_OK; }
+int sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  launch_ba_step(b->hdr, b->P, b->nP, stepfac, load_backup, c->st); c->launches += 2;
+  int rc = ba_pull_scalars(c, b); if (rc) return rc;
+  if (canbreak) *canbreak = b->hdr_host->canbreak;
+  return SDV_OK;
+}
+
+/* float FullSystem::optimize(int mnumOptIts)   FullSystemOptimize.cpp:344-502 */
+int sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; cudaStream_t st = c->st; int rc;
+  const int nF = b->nF;
+  if (nF < 2) { if (rmse_out) *rmse_out = 0; return SDV_OK; }
+  if (nF < 3) mnumOptIts = 100;
+  if (nF < 4) mnumOptIts = 75;
+  CK(cudaEventRecord(c->ev0, st));
+  b->opt_iterations = b->opt_accepts = 0;
+  launch_ba_reset_oob(b->R, b->nR, st);
+  launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 0, b->partials, b->thbuf, b->thcount, st);
+  launch_ba_energies(b->hdr, b->P, b->nP, st); c->launches += 4;
+  if ((rc = ba_pull_scalars(c, b))) return rc;
+  double lastEnergy = b->hdr_host->energyP, lastEnergyL = b->hdr_host->energyL, lastEnergyM = b->hdr_host->energyM;
+  launch_ba_apply(b->R, b->nR, st); c->launches++;
+  double lambda = 1e-1;
+  for (int iteration = 0; iteration < mnumOptIts; iteration++) {
+    b->opt_iterations++;
+    launch_ba_backup(b->hdr, b->P, b->nP, st);
+    launch_ba_accumulate(b->hdr, b->P, b->R, nF, b->nP, st);
+    launch_ba_solve(b->hdr, b->P, b->R, b->nP, iteration, lambda, st);
+    launch_ba_step(b->hdr, b->P, b->nP, 1.0f, 0, st);
+    launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 0, b->partials, b->thbuf, b->thcount, st);
+    launch_ba_energies(b->hdr, b->P, b->nP, st); c->launches += 11;
+    if ((rc = ba_pull_scalars(c, b))) return rc;
+    const bool canbreak = b->hdr_host->canbreak != 0;
+    const double newEnergy = b->hdr_host->energyP, newEnergyL = b->hdr_host->energyL, newEnergyM = b->hdr_host->energyM;
+    if (newEnergy + 0 + newEnergyL + newEnergyM < lastEnergy + 0 + lastEnergyL + lastEnergyM) {
+      b->opt_accepts++;
+      launch_ba_apply(b->R, b->nR, st); c->launches++;
+      lastEnergy = newEnergy; lastEnergyL = newEnergyL; lastEnergyM = newEnergyM; lambda *= 0.25;
+    } else {
+      launch_ba_step(b->hdr, b->P, b->nP, 1.0f, 1, st);                      // loadSateBackup
+      launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 0, b->partials, b->thbuf, b->thcount, st);
+      launch_ba_energies(b->hdr, b->P, b->nP, st); c->launches += 5;
+      if ((rc = ba_pull_scalars(c, b))) return rc;
+      lastEnergy = b->hdr_host->energyP; lastEnergyL = b->hdr_host->energyL; lastEnergyM = b->hdr_host->energyM;
+      lambda *= 1e2;
+    }
+    if (canbreak && iteration >= 1) break;                                   // setting_minOptIterations = 1
+  }
+  launch_ba_reanchor(b->hdr, b->P, b->nP, st);
+  launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 1, b->partials, b->thbuf, b->thcount, st); c->launches += 4;
+  CK(cudaEventRecord(c->ev1, st));
+  if ((rc = ba_pull_scalars(c, b))) return rc;
+  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (rmse_out) *rmse_out = sqrtf((float)(b->hdr_host->energyP / b->hdr_host->resInA));
+  if (iterations_out) *iterations_out = b->opt_iterations;
+  if (accepts_out) *accepts_out = b->opt_accepts;
+  return SDV_OK;
+}
+
+// ---- read-back (what the reference leaves in FrameHessian / PointHessian / PointFrameResidual / EnergyFunctional)
+int sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* step10, float* frameEnergyTH, double* PRE_worldToCam7, double calib_value[4], double calib_step[4]) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  CK(cudaMemcpyAsync(b->hdr_host, b->hdr, offsetof(BAHeader, precalc), cudaMemcpyDeviceToHost, c->st)); CK(cudaStreamSynchronize(c->st));
+  const BAHeader* H = b->hdr_host;
+  for (int f=0; f<b->nF; f++) { const BAFrameDev& F = H->frames[f];
+    if (T_evalPT7) se3_to7(F.evalPT, T_evalPT7 + 7*f); if (PRE_worldToCam7) se3_to7(F.PRE_w2c, PRE_worldToCam7 + 7*f);
+    for (int i=0;i<10;i++) { if (state10) state10[10*f+i] = F.state[i]; if (step10) step10[10*f+i] = F.step[i]; }
+    if (frameEnergyTH) frameEnergyTH[f] = F.frameEnergyTH; }
+  for (int i=0;i<4;i++) { if (calib_value) calib_value[i] = H->calib.value[i]; if (calib_step) calib_step[i] = H->calib.step[i]; }
+  return SDV_OK;
+}
+int sdv_ba_get_points(sdv_ctx* c, float* idepth, float* step, float* HdiF, float* bdSumF, float* maxRelBaseline, int32_t* numGoodResiduals, float* idepth_hessian) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int n = b->nP; const BAPointsDev& P = b->P;
+#define DN(dst, src, T) do { if (dst && n > 0) CK(cudaMemcpyAsync(dst, src, (size_t)n*sizeof(T), cudaMemcpyDeviceToHost, c->st)); } while (0)
+  DN(idepth, P.idepth, float); DN(step, P.step, float); DN(HdiF, P.HdiF, float); DN(bdSumF, P.bdSumF, float); DN(maxRelBaseline, P.maxRelBaseline, float);
+  DN(numGoodResiduals, P.numGoodResiduals, int); DN(idepth_hessian, P.idepth_hessian, float);
+#undef DN
+  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+}
+int sdv_ba_get_residuals(sdv_ctx* c, int32_t* state_state, int32_t* state_NewState, float* energies3, int32_t* isActive, float* J24, float* efJ24,
+                         float* JpJdF8, float* center3, int32_t* toRemove) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int n = b->nR; const BAResDev& R = b->R;
+  if (n == 0) return SDV_OK;
+  std::vector<float> e0(n), e1(n), e2(n);
+#define DN(dst, src, cnt, T) do { if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt)*sizeof(T), cudaMemcpyDeviceToHost, c->st)); } while (0)
+  DN(state_state, R.state_state, n, int); DN(state_NewState, R.state_NewState, n, int); DN(isActive, R.isActive, n, int); DN(toRemove, R.toRemove, n, int);
+  DN(J24, R.J, (size_t)n*24, float); DN(efJ24, R.efJ, (size_t)n*24, float); DN(JpJdF8, R.JpJdF, (size_t)n*8, float); DN(center3, R.center, (size_t)n*3, float);
+  DN(e0.data(), R.state_energy, n, float); DN(e1.data(), R.state_NewEnergy, n, float); DN(e2.data(), R.state_NewEnergyWithOutlier, n, float);
+#undef DN
+  CK(cudaStreamSynchronize(c->st));
+  if (energies3) for (int i=0;i<n;i++) { energies3[3*i] = e0[i]; energies3[3*i+1] = e1[i]; energies3[3*i+2] = e2[i]; }
+  return SDV_OK;
+}
+int sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int N = kCP + 6*b->nF;
+#define DN(dst, src, cnt) do { if (dst) CK(cudaMemcpyAsync(dst, b->hdr->src, (size_t)(cnt)*sizeof(double), cudaMemcpyDeviceToHost, c->st)); } while (0)
+  DN(HA, HA, N*N); DN(bA, bA, N); DN(Hsc, Hsc, N*N); DN(bsc, bsc, N); DN(lastHS, lastHS, N*N); DN(lastbS, lastbS, N);
+#undef DN
+  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+}
+int sdv_ba_get_precalc(sdv_ctx* c, int host, int target, float out27[27], double adHost36[36], double adTarget36[36], float adHTdelta6[6]) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int nF = b->nF;
+  if (host < 0 || target < 0 || host >= nF || target >= nF) return SDV_ERR_ARG;
+  PrecalcDev p; CK(cudaMemcpy(&p, &b->hdr->precalc[host*nF+target], sizeof(p), cudaMemcpyDeviceToHost));
+  for (int i=0;i<9;i++) { out27[i] = p.KRKi[i]; out27[12+i] = p.R0[i]; } for (int i=0;i<3;i++) { out27[9+i] = p.Kt[i]; out27[21+i] = p.t0[i]; }
+  out27[24] = p.aff[0]; out27[25] = p.aff[1]; out27[26] = p.b0;
+  const int idx = host + target*nF;
+  CK(cudaMemcpy(adHost36, b->hdr->adHost + idx*36, 36*sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(adTarget36, b->hdr->adTarget + idx*36, 36*sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(adHTdelta6, b->hdr->adHTdeltaF + idx*6, 6*sizeof(float), cudaMemcpyDeviceToHost));
+  return SDV_OK;
+}
+
+} // extern "C"

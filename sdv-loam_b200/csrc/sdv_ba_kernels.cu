@@ -1,0 +1,670 @@
+// sdv_ba_kernels.cu — sm_100a kernels of the sliding-window back-end (compiled with --fmad=false).
+//
+//   ba_frames_kernel        FrameHessian::setState/setStateZero, EFFrame::takeData, EnergyFunctional::setAdjointsF/setDeltaF,
+//                           FrameFramePrecalc::set           HessianBlocks.h:141-183, HessianBlocks.cpp:52-82,169-195, EnergyFunctional.cpp:21-71,131-156
+//   ba_linearize_kernel     PointFrameResidual::linearize (+ applyRes when fixing)       Residuals.cpp:60-224, 252-274
+//   ba_energy_th_kernel     FullSystem::setNewFrameEnergyTH (exact k-th element by radix select)   FullSystemOptimize.cpp:63-97
+//   ba_point_acc_kernel     per-point part of AccumulatedTopHessianSSE::addPoint<0> + head of AccumulatedSCHessianSSE::addPoint
+//   ba_acc_top_kernel       AccumulatorApprox buckets per (host,target)                  AccumulatedTopHessian.cpp:13-112, MatrixAccumulators.h:560-932
+//   ba_acc_sc_kernel        accD/accE/accEB/accHcc/accbc                                  AccumulatedSCHessian.cpp:10-62
+//   ba_solve_kernel         stitchDouble*, solveSystemF, orthogonalize, resubstituteF_MT head   AccumulatedTopHessian.cpp:181-242, AccumulatedSCHessian.cpp:64-135,
+//                                                                                         EnergyFunctional.cpp:650-759, 615-648, 221-248
+//   ba_resub_kernel         EnergyFunctional::resubstituteFPt                             EnergyFunctional.cpp:250-282
+//   ba_step_* / ba_backup   FullSystem::doStepFromBackup / backupState / loadSateBackup   FullSystemOptimize.cpp:165-321
+//
+// Accumulation kernels are "entry-parallel, item-sequential": one thread owns one accumulator cell and walks the items in the
+// reference's order with the reference's 1 / 1k / 1M float tiers, so every float sum is bit-identical to the CPU path's.
+#include "sdv_ba.cuh"
+
+namespace sdv {
+
+__constant__ int c_pattern[8][2] = {{0,-2},{-1,-1},{1,-1},{-2,0},{0,0},{2,0},{-1,1},{0,2}};   // settings.cpp:250
+
+// ================================================================================================ frames / pairs
+__device__ void frame_set_state(BAFrameDev& f) {                          // HessianBlocks.h:141-153
+  for (int i=0;i<3;i++) f.state_scaled[i] = 0.5f*f.state[i];
+  for (int i=3;i<6;i++) f.state_scaled[i] = 1.0f*f.state[i];
+  f.state_scaled[6] = 10.0f*f.state[6]; f.state_scaled[7] = 1000.0f*f.state[7]; f.state_scaled[8] = 10.0f*f.state[8]; f.state_scaled[9] = 1000.0f*f.state[9];
+  f.PRE_w2c = se3_mul(se3_exp(f.state_scaled), f.evalPT);
+  f.PRE_c2w = se3_inv(f.PRE_w2c);
+}
+__device__ void frame_set_state_zero(BAFrameDev& f) {                     // HessianBlocks.cpp:52-82
+  SE3d T = f.evalPT, Ti = se3_inv(T);
+  for (int i=0;i<6;i++) {
+    double e[6]={0,0,0,0,0,0}, m[6]={0,0,0,0,0,0}; e[i]=1e-3; m[i]=-1e-3;
+    SE3d P = se3_mul(se3_mul(T, se3_exp(e)), Ti), M = se3_mul(se3_mul(T, se3_exp(m)), Ti);
+    double lp[6], lm[6]; se3_log(P, lp); se3_log(M, lm);
+    for (int r=0;r<6;r++) f.nullspaces_pose[r*6+i] = (lp[r]-lm[r])/(2e-3);
+  }
+  SE3d P = T; for (int i=0;i<3;i++) P.t[i] *= 1.00001; P = se3_mul(P, Ti);
+  SE3d M = T; for (int i=0;i<3;i++) M.t[i] /= 1.00001; M = se3_mul(M, Ti);
+  double lp[6], lm[6]; se3_log(P, lp); se3_log(M, lm);
+  for (int r=0;r<6;r++) f.nullspaces_scale[r] = (lp[r]-lm[r])/(2e-3);
+}
+
+// flags: 1 setState, 2 setStateZero, 4 takeData(prior), 8 adjoints, 16 precalc+deltas, 32 re-anchor newest frame first,
+//        64 = this is doStepFromBackup/loadSateBackup: first apply calib/frame steps (stepfac) or restore the backups
+__global__ void __launch_bounds__(64) ba_frames_kernel(BAHeader* __restrict__ H, int flags, float stepfac, int load_backup) {
+  const int tid = threadIdx.x; const int nF = H->nF;
+  if (flags & 64) {
+    if (tid == 0) {
+      BACalibDev& c = H->calib; double v[4];
+      for (int i=0;i<4;i++) v[i] = load_backup ? c.value_backup[i] : c.value_backup[i] + stepfac*c.step[i];
+      for (int i=0;i<4;i++) c.value[i] = v[i];                              // CalibHessian::setValue (HessianBlocks.h:305-320)
+      c.value_scaled[0] = 50.0f*v[0]; c.value_scaled[1] = 50.0f*v[1]; c.value_scaled[2] = 50.0f*v[2]; c.value_scaled[3] = 50.0f*v[3];
+      for (int i=0;i<4;i++) c.sf[i] = (float)c.value_scaled[i];
+      c.si[0] = 1.0f/c.sf[0]; c.si[1] = 1.0f/c.sf[1]; c.si[2] = -c.sf[2]/c.sf[0]; c.si[3] = -c.sf[3]/c.sf[1];
+      for (int i=0;i<4;i++) c.vmvz[i] = c.value[i] - c.value_zero[i];
+      if (!load_backup) {                                                   // doStepFromBackup sums (FullSystemOptimize.cpp:173-249)
+        float sumT = 0, sumR = 0;
+        for (int f=0; f<nF; f++) { const double* s = H->frames[f].step;
+          sumT += s[0]*s[0]+s[1]*s[1]+s[2]*s[2]; sumR += s[3]*s[3]+s[4]*s[4]+s[5]*s[5]; }
+        sumR /= nF; sumT /= nF;
+        float sumNID = H->sums[1] / H->sums[2];                             // sumNID /= numID   (sums[] filled by ba_step_points_kernel)
+        H->canbreak = (sqrtf(sumR) < 0.00005*H->set.thOptIterations && sqrtf(sumT)*sumNID < 0.00005*H->set.thOptIterations) ? 1 : 0;
+      }
+    }
+    if (tid < nF) { BAFrameDev& f = H->frames[tid];
+      if (load_backup) { for (int i=0;i<10;i++) f.state[i] = f.state_backup[i]; }
+      else { for (int i=6;i<10;i++) f.step[i] = 0; for (int i=0;i<10;i++) f.state[i] = f.state_backup[i] + (double)stepfac*f.step[i]; } }
+    __syncthreads();
+  }
+  if ((flags & 32) && tid == nF-1) {                                        // optimize() tail: setEvalPT(PRE_worldToCam, [0..,a,b,0,0])  (FullSystemOptimize.cpp:460-464)
+    BAFrameDev& f = H->frames[tid]; double a = f.state[6], b = f.state[7];
+    f.evalPT = f.PRE_w2c;
+    for (int i=0;i<10;i++) { f.state[i] = 0; f.state_zero[i] = 0; }
+    f.state[6] = a; f.state[7] = b; f.state_zero[6] = a; f.state_zero[7] = b;
+    frame_set_state(f); frame_set_state_zero(f);
+  }
+  if (tid < nF) {
+    BAFrameDev& f = H->frames[tid];
+    if (flags & 1) frame_set_state(f);
+    if (flags & 2) frame_set_state_zero(f);
+    if (flags & 4) {                                                        // EFFrame::takeData + getPrior (HessianBlocks.h:220-252)
+      for (int i=0;i<6;i++) f.prior[i] = 0;
+      if (f.frameID == 0) { for (int i=0;i<3;i++) f.prior[i] = H->set.initialTransPrior; for (int i=3;i<6;i++) f.prior[i] = H->set.initialRotPrior; }
+    }
+    for (int i=0;i<6;i++) { f.delta[i] = f.state[i] - f.state_zero[i]; f.delta_prior[i] = f.state[i]; }
+  }
+  if (tid == 0) { for (int i=0;i<4;i++) { H->calib.cDeltaF[i] = (float)H->calib.vmvz[i]; H->calib.cPrior[i] = H->set.initialCalibHessian; } }
+  __syncthreads();
+  if (tid < nF*nF) {
+    const int h = tid % nF, t = tid / nF; const int idx = h + t*nF;
+    const BAFrameDev& host = H->frames[h]; const BAFrameDev& target = H->frames[t];
+    if (flags & 8) {                                                        // setAdjointsF (EnergyFunctional.cpp:30-52,61-66)
+      SE3d hostToTarget = se3_mul(target.evalPT, se3_inv(host.evalPT));
+      double Ad[36]; se3_adj(hostToTarget, Ad);
+      double* AH = H->adHost + idx*36; double* AT = H->adTarget + idx*36;
+      for (int r=0;r<6;r++) for (int c=0;c<6;c++) { AH[r*6+c] = -Ad[c*6+r]; AT[r*6+c] = (r==c) ? 1.0 : 0.0; }
+      for (int r=0;r<3;r++) for (int c=0;c<6;c++) { AH[r*6+c] *= 0.5f; AT[r*6+c] *= 0.5f; }
+      for (int r=3;r<6;r++) for (int c=0;c<6;c++) { AH[r*6+c] *= 1.0f; AT[r*6+c] *= 1.0f; }
+      for (int i=0;i<36;i++) { H->adHostF[idx*36+i] = (float)AH[i]; H->adTargetF[idx*36+i] = (float)AT[i]; }
+    }
+    if (flags & 16) {                                                       // FrameFramePrecalc::set (HessianBlocks.cpp:169-195)
+      PrecalcDev& p = H->precalc[h*nF + t];
+      const BACalibDev& c = H->calib;
+      float K[9] = {c.sf[0],0,c.sf[2], 0,c.sf[1],c.sf[3], 0,0,1}, Ki[9]; inv3f(K, Ki);
+      SE3d l0 = se3_mul(target.evalPT, se3_inv(host.evalPT));
+      double R0[9]; qmat(l0.q, R0); for (int i=0;i<9;i++) p.R0[i] = (float)R0[i]; for (int i=0;i<3;i++) p.t0[i] = (float)l0.t[i];
+      SE3d l = se3_mul(target.PRE_w2c, host.PRE_c2w);
+      double Rd[9]; qmat(l.q, Rd); float R[9], tl[3], KR[9]; for (int i=0;i<9;i++) R[i] = (float)Rd[i]; for (int i=0;i<3;i++) tl[i] = (float)l.t[i];
+      for (int i=0;i<3;i++) for (int j=0;j<3;j++) KR[i*3+j] = (K[i*3]*R[j] + K[i*3+1]*R[3+j]) + K[i*3+2]*R[6+j];
+      for (int i=0;i<3;i++) for (int j=0;j<3;j++) p.KRKi[i*3+j] = (KR[i*3]*Ki[j] + KR[i*3+1]*Ki[3+j]) + KR[i*3+2]*Ki[6+j];
+      for (int i=0;i<3;i++) p.Kt[i] = (K[i*3]*tl[0] + K[i*3+1]*tl[1]) + K[i*3+2]*tl[2];
+      double aff[2]; aff_from_to(host.ab_exposure, target.ab_exposure, host.state_scaled[6], host.state_scaled[7], target.state_scaled[6], target.state_scaled[7], aff);
+      p.aff[0] = (float)aff[0]; p.aff[1] = (float)aff[1];
+      p.b0 = (float)(host.state_zero[7]*1000.0f);
+      // setDeltaF (EnergyFunctional.cpp:135-142)
+      float dh[6], dt[6];
+      for (int i=0;i<6;i++) { dh[i] = (float)(host.state[i]-host.state_zero[i]); dt[i] = (float)(target.state[i]-target.state_zero[i]); }
+      for (int j=0;j<6;j++) { float s1 = 0, s2 = 0;
+        for (int i=0;i<6;i++) { s1 += dh[i]*H->adHostF[idx*36+i*6+j]; s2 += dt[i]*H->adTargetF[idx*36+i*6+j]; }
+        H->adHTdeltaF[idx*6+j] = s1 + s2; }
+    }
+  }
+}
+
+__global__ void ba_points_setup_kernel(const BAHeader* __restrict__ H, BAPointsDev P, int nP, int take_data) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= nP) return;
+  if (take_data) P.priorF[i] = P.hasDepthPrior[i] ? H->set.idepthFixPrior*1.0f*1.0f : 0.0f;       // EFPoint::takeData (EnergyFunctionalStructs.cpp:40-46)
+  P.deltaF[i] = P.idepth[i] - P.idepth_zero[i];
+}
+
+__global__ void ba_reset_oob_kernel(BAResDev R, int nR) {                  // PointFrameResidual::resetOOB (Residuals.h:66-73)
+  int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= nR) return;
+  R.state_NewEnergy[i] = 0; R.state_energy[i] = 0; R.state_NewState[i] = RS_OUTLIER; R.state_state[i] = RS_IN;
+}
+
+// ================================================================================================ linearize
+__device__ __forceinline__ void apply_res(BAResDev& R, int r) {            // Residuals.cpp:252-274 (copyJacobians = true) + takeDataF
+  if (R.state_state[r] == RS_OOB) return;
+  if (R.state_NewState[r] == RS_IN) {
+    R.isActive[r] = 1;
+    float J[24];
+#pragma unroll
+    for (int k=0;k<24;k++) { J[k] = R.J[(size_t)r*24+k]; R.efJ[(size_t)r*24+k] = J[k]; }
+#pragma unroll
+    for (int i=0;i<6;i++) R.JpJdF[(size_t)r*8+i] = J[2+i]*J[22] + J[8+i]*J[23];
+    R.JpJdF[(size_t)r*8+6] = 0; R.JpJdF[(size_t)r*8+7] = 0;
+  } else R.isActive[r] = 0;
+  R.state_state[r] = R.state_NewState[r]; R.state_energy[r] = R.state_NewEnergy[r];
+}
+
+constexpr int kLinThreads = 128;
+__global__ void __launch_bounds__(kLinThreads) ba_linearize_kernel(BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nR, int fix,
+                                                                 double* __restrict__ partials, float* __restrict__ thbuf, int* __restrict__ thcount) {
+  const int r = blockIdx.x*kLinThreads + threadIdx.x;
+  double energy = 0;
+  if (r < nR) {
+    R.state_NewEnergyWithOutlier[r] = -1;
+    bool done = false;
+    if (R.state_state[r] == RS_OOB) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+    const int nF = H->nF; const int hI = R.host[r], tI = R.target[r], pI = R.point[r];
+    const PrecalcDev& pc = H->precalc[hI*nF + tI];
+    const float wM3G = (float)(H->w - 3), hM3G = (float)(H->h - 3);
+    const float fxl = H->calib.sf[0], fyl = H->calib.sf[1], cxl = H->calib.sf[2], cyl = H->calib.sf[3], fxli = H->calib.si[0], fyli = H->calib.si[1];
+    float J[24]; float Ku = 0, Kv = 0;
+    if (!done && !R.hasMatcher[r]) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+    const float2 uv = P.uv[pI];
+    if (!done) {
+      const float idz = P.idepth_zero[pI]*1.0f;                                     // idepth_zero_scaled
+      float KliP0 = (uv.x+0-cxl)*fxli, KliP1 = (uv.y+0-cyl)*fyli, KliP2 = 1;
+      float p0 = ((pc.R0[0]*KliP0 + pc.R0[1]*KliP1) + pc.R0[2]*KliP2) + pc.t0[0]*idz;
+      float p1 = ((pc.R0[3]*KliP0 + pc.R0[4]*KliP1) + pc.R0[5]*KliP2) + pc.t0[1]*idz;
+      float p2 = ((pc.R0[6]*KliP0 + pc.R0[7]*KliP1) + pc.R0[8]*KliP2) + pc.t0[2]*idz;
+      float drescale = 1.0f/p2; float new_idepth = idz*drescale;
+      float u = p0*drescale, v = p1*drescale;
+      Ku = u*fxl + cxl; Kv = v*fyl + cyl;
+      if (!(drescale > 0) || !(Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G)) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+      else {
+        R.center[(size_t)r*3] = Ku; R.center[(size_t)r*3+1] = Kv; R.center[(size_t)r*3+2] = new_idepth;
+        float d_d_x = drescale * (pc.t0[0]-pc.t0[2]*u)*1.0f*fxl;
+        float d_d_y = drescale * (pc.t0[1]-pc.t0[2]*v)*1.0f*fyl;
+        float cx2 = drescale*(pc.R0[6]*u-pc.R0[0]);
+        float cx3 = fxl * drescale*(pc.R0[7]*u-pc.R0[1]) * fyli;
+        float cx0 = KliP0*cx2, cx1 = KliP1*cx3;
+        float cy2 = fyl * drescale*(pc.R0[6]*v-pc.R0[3]) * fxli;
+        float cy3 = drescale*(pc.R0[7]*v-pc.R0[4]);
+        float cy0 = KliP0*cy2, cy1 = KliP1*cy3;
+        cx0 = (cx0+u)*50.0f; cx1 *= 50.0f; cx2 = (cx2+1)*50.0f; cx3 *= 50.0f;
+        cy0 *= 50.0f; cy1 = (cy1+v)*50.0f; cy2 *= 50.0f; cy3 = (cy3+1)*50.0f;
+        J[2] = new_idepth*fxl; J[3] = 0; J[4] = -new_idepth*u*fxl; J[5] = -u*v*fxl; J[6] = (1+u*u)*fxl; J[7] = -v*fxl;
+        J[8] = 0; J[9] = new_idepth*fyl; J[10] = -new_idepth*v*fyl; J[11] = -(1+v*v)*fyl; J[12] = u*v*fyl; J[13] = u*fyl;
+        J[14] = cx0; J[15] = cx1; J[16] = cx2; J[17] = cx3; J[18] = cy0; J[19] = cy1; J[20] = cy2; J[21] = cy3;
+        J[22] = d_d_x; J[23] = d_d_y;
+      }
+    }
+    if (!done) {
+      // photometric 8-pattern outlier gate at the CURRENT pose (Residuals.cpp:157-194)
+      const float4* __restrict__ img = H->frames[tI].img0; const int wI = H->w;
+      const float ids = P.idepth[pI]*1.0f; const float a0 = pc.aff[0], a1 = pc.aff[1];
+      float wJI2_sum = 0, energyLeft2 = 0.0f;
+      for (int idx = 0; idx < 8; idx++) {
+        float x = uv.x + c_pattern[idx][0], y = uv.y + c_pattern[idx][1];
+        float q0 = ((pc.KRKi[0]*x + pc.KRKi[1]*y) + pc.KRKi[2]*1.0f) + pc.Kt[0]*ids;
+        float q1 = ((pc.KRKi[3]*x + pc.KRKi[4]*y) + pc.KRKi[5]*1.0f) + pc.Kt[1]*ids;
+        float q2 = ((pc.KRKi[6]*x + pc.KRKi[7]*y) + pc.KRKi[8]*1.0f) + pc.Kt[2]*ids;
+        float Ku2 = q0/q2, Kv2 = q1/q2;
+        if (!(Ku2 > 1.1f && Kv2 > 1.1f && Ku2 < wM3G && Kv2 < hM3G)) break;
+        int ix = (int)Ku2, iy = (int)Kv2; float dx = Ku2-ix, dy = Kv2-iy, dxdy = dx*dy;
+        const float4* bp = img + ix + iy*wI;
+        float4 p00 = __ldg(bp), p10 = __ldg(bp+1), p01 = __ldg(bp+wI), p11 = __ldg(bp+1+wI);
+        float w11 = dxdy, w01 = dy-dxdy, w10 = dx-dxdy, w00 = 1-dx-dy+dxdy;
+        float h0 = ((w11*p11.x + w01*p01.x) + w10*p10.x) + w00*p00.x;
+        float h1 = ((w11*p11.y + w01*p01.y) + w10*p10.y) + w00*p00.y;
+        float h2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
+        float residual = h0 - (a0*P.color[(size_t)pI*8+idx] + a1);
+        if (!isfinite(h0)) break;
+        float wgt = sqrtf(H->set.outlierTHSumComponent / (H->set.outlierTHSumComponent + (h1*h1 + h2*h2)));
+        wgt = 0.5f*(wgt + P.weights[(size_t)pI*8+idx]);
+        float hw = fabsf(residual) < H->set.huberTH ? 1 : H->set.huberTH / fabsf(residual);
+        energyLeft2 += wgt*wgt*hw*residual*residual*(2-hw);
+        if (hw < 1) hw = sqrtf(hw);
+        hw = hw*wgt; h1 *= hw; h2 *= hw;
+        wJI2_sum += hw*hw*(h1*h1 + h2*h2);
+      }
+      const float2 m = R.matcher[r];
+      float res0 = Ku - m.x, res1 = Kv - m.y;
+      float nrm = sqrtf(res0*res0 + res1*res1);
+      float hw = fabsf(nrm) < H->set.huberTH ? 1 : H->set.huberTH / fabsf(nrm);
+      float energyLeft = hw * (res0*res0 + res1*res1)*(2-hw);
+      if (hw < 1) hw = sqrtf(hw);
+      J[0] = res0*hw; J[1] = res1*hw;
+#pragma unroll
+      for (int k=2;k<24;k++) J[k] = J[k]*hw;
+#pragma unroll
+      for (int k=0;k<24;k++) R.J[(size_t)r*24+k] = J[k];
+      R.state_NewEnergyWithOutlier[r] = energyLeft2;
+      float th = fmaxf(H->frames[hI].frameEnergyTH, H->frames[tI].frameEnergyTH);
+      if (energyLeft2 > th || wJI2_sum < 2) { R.state_NewEnergy[r] = th; R.state_NewState[r] = RS_OUTLIER; }
+      else { R.state_NewEnergy[r] = energyLeft2; R.state_NewState[r] = RS_IN; }
+      energy = energyLeft;
+      if (tI == nF-1) { int slot = atomicAdd(thcount, 1); thbuf[slot] = energyLeft2; }       // setNewFrameEnergyTH candidates (order-free)
+    }
+    if (fix) {                                                              // linearizeAll_Reductor, fixLinearization branch (FullSystemOptimize.cpp:30-53)
+      apply_res(R, r);
+      if (R.isActive[r]) {
+        if (R.isNew[r]) {
+          const float ids = P.idepth[pI]*1.0f;
+          float i0 = (pc.KRKi[0]*uv.x + pc.KRKi[1]*uv.y) + pc.KRKi[2]*1.0f, i1 = (pc.KRKi[3]*uv.x + pc.KRKi[4]*uv.y) + pc.KRKi[5]*1.0f, i2 = (pc.KRKi[6]*uv.x + pc.KRKi[7]*uv.y) + pc.KRKi[8]*1.0f;
+          float q0 = i0 + pc.Kt[0]*ids, q1 = i1 + pc.Kt[1]*ids, q2 = i2 + pc.Kt[2]*ids;
+          float ddx = i0/i2 - q0/q2, ddy = i1/i2 - q1/q2;
+          float relBS = (float)(0.01*(double)sqrtf(ddx*ddx + ddy*ddy));
+          atomicMax(reinterpret_cast<int*>(P.maxRelBaseline + pI), __float_as_int(relBS));   // non-negative floats: int order == float order
+          atomicAdd(P.numGoodResiduals + pI, 1);
+        }
+      } else R.toRemove[r] = 1;
+    }
+  }
+  // deterministic energy reduction (double): warp butterfly -> block -> last block sums the block partials in order
+  __shared__ double wsum[kLinThreads/32]; __shared__ bool is_last;
+  for (int o=16;o>0;o>>=1) energy += __shfl_xor_sync(0xffffffffu, energy, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x>>5] = energy;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0; for (int k=0;k<kLinThreads/32;k++) s += wsum[k];
+    partials[blockIdx.x] = s; __threadfence();
+    unsigned int t = atomicAdd(&H->ticket, 1u); is_last = (t == gridDim.x-1);
+    if (is_last) { __threadfence(); double tot = 0; for (unsigned int b=0;b<gridDim.x;b++) tot += __ldcg(partials+b); H->energyP = tot; H->ticket = 0; }
+  }
+}
+
+// exact k-th smallest (std::nth_element value) of n non-negative floats by 4x8-bit radix select, then the threshold formula
+__global__ void __launch_bounds__(1024) ba_energy_th_kernel(BAHeader* __restrict__ H, const float* __restrict__ buf, int* __restrict__ count) {
+  __shared__ unsigned int hist[256]; __shared__ unsigned int prefix, kk, sel_mask;
+  const int n = *count; BAFrameDev& nf = H->frames[H->nF-1];
+  if (n == 0) { if (threadIdx.x == 0) { nf.frameEnergyTH = 12*12*8; *count = 0; } return; }
+  if (threadIdx.x == 0) { prefix = 0; sel_mask = 0; kk = (unsigned int)(int)(H->set.frameEnergyTHN * n); }
+  __syncthreads();
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const unsigned int pf = prefix, mk = sel_mask;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { unsigned int key = __float_as_uint(buf[i]); if ((key & mk) == pf) atomicAdd(&hist[(key >> shift) & 255u], 1u); }
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned int k = kk, b = 0; for (; b < 256; b++) { if (k < hist[b]) break; k -= hist[b]; }
+      kk = k; prefix = pf | (b << shift); sel_mask = mk | (255u << shift); }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float nthElement = sqrtf(__uint_as_float(prefix));                       // FullSystemOptimize.cpp:91-96
+    float th = nthElement*H->set.frameEnergyTHFacMedian;
+    th = 26.0f*H->set.frameEnergyTHConstWeight + th*(1-H->set.frameEnergyTHConstWeight);
+    th = th*th; th *= H->set.overallEnergyTHWeight*H->set.overallEnergyTHWeight;
+    nf.frameEnergyTH = th; *count = 0;
+  }
+}
+
+__global__ void ba_apply_kernel(BAResDev R, int nR) { int r = blockIdx.x*blockDim.x + threadIdx.x; if (r < nR) apply_res(R, r); }
+
+// ================================================================================================ energies
+__global__ void __launch_bounds__(256) ba_energies_kernel(BAHeader* __restrict__ H, BAPointsDev P, int nP) {
+  __shared__ double sh[256];
+  const int tid = threadIdx.x; const int nF = H->nF, N = H->dim;
+  // calcLEnergyPt: chunks of 50 points, float Accumulator11 per chunk (EnergyFunctional.cpp:295-331)
+  double mine = 0; const int nchunks = (nP + 49)/50;
+  for (int c = tid; c < nchunks; c += 256) { float acc = 0; for (int i = c*50; i < min(c*50+50, nP); i++) acc += P.deltaF[i]*P.deltaF[i]*P.priorF[i]; mine += (double)((acc + 0.0f) + 0.0f); }
+  sh[tid] = mine; __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) sh[tid] += sh[tid+o]; __syncthreads(); }
+  if (tid == 0) {
+    double E = 0;
+    for (int f=0; f<nF; f++) for (int i=0;i<6;i++) E += (H->frames[f].delta_prior[i]*H->frames[f].prior[i])*H->frames[f].delta_prior[i];
+    float s = 0; for (int i=0;i<4;i++) s += (H->calib.cDeltaF[i]*(float)H->calib.cPrior[i])*H->calib.cDeltaF[i];
+    H->energyL = (E + s) + sh[0];
+  }
+  __syncthreads();
+  // calcMEnergyF: delta . (2 bM + HM delta)   (:284-293)
+  double d_i = 0, row = 0;
+  if (tid < N) {
+    for (int j=0;j<N;j++) { double dj = (j < 4) ? (double)H->calib.cDeltaF[j] : H->frames[(j-4)/6].delta[(j-4)%6]; row += H->HM[tid*N+j]*dj; }
+    d_i = (tid < 4) ? (double)H->calib.cDeltaF[tid] : H->frames[(tid-4)/6].delta[(tid-4)%6];
+    sh[tid] = d_i*(2*H->bM[tid] + row);
+  }
+  __syncthreads();
+  if (tid == 0) { double e = 0; for (int i=0;i<N;i++) e += sh[i]; H->energyM = e; }
+}
+
+// ================================================================================================ accumulation
+// per point: Hdd/bd/Hcd sums over its active residuals in order (addPoint<0>), then HdiF / bdSumF (SC addPoint head)
+__global__ void ba_point_acc_kernel(const BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nP) {
+  int p = blockIdx.x*blockDim.x + threadIdx.x; if (p >= nP) return;
+  float bd = 0, Hdd = 0, Hcd[4] = {0,0,0,0}; int ngood = 0;
+  for (int r = P.res_begin[p]; r < P.res_begin[p+1]; r++) {
+    if (!R.isActive[r]) continue;
+    const float* J = R.efJ + (size_t)r*24; ngood++;
+    bd += J[0]*J[22] + J[1]*J[23];
+    Hdd += J[22]*J[22] + J[23]*J[23];
+    for (int i=0;i<4;i++) Hcd[i] += J[14+i]*J[22] + J[18+i]*J[23];
+  }
+  P.Hdd_accAF[p] = Hdd; P.bd_accAF[p] = bd; for (int i=0;i<4;i++) P.Hcd_accAF[(size_t)p*4+i] = Hcd[i];
+  P.ngood[p] = ngood;
+  if (ngood == 0) { P.HdiF[p] = 0; P.bdSumF[p] = 0; P.idepth_hessian[p] = 0; P.maxRelBaseline[p] = 0; return; }   // AccumulatedSCHessian.cpp:12-21
+  float Hh = Hdd + 0.0f + P.priorF[p]; if (Hh < 1e-10) Hh = 1e-10;
+  P.idepth_hessian[p] = Hh; P.HdiF[p] = (float)(1.0 / (double)Hh);
+  float bs = bd + 0.0f; bs += P.priorF[p]*P.deltaF[p]; P.bdSumF[p] = bs;
+}
+
+struct Tier { float d, d1k, d1m, n1, n1k; };
+__device__ __forceinline__ void tier_shift(Tier& t) {                       // shiftUp(false) after numIn1++ (MatrixAccumulators.h:897-931)
+  if (t.n1 > 1000) { t.d1k = t.d + t.d1k; t.n1k += t.n1; t.n1 = 0; t.d = 0; }
+  if (t.n1k > 1000) { t.d1m = t.d1k + t.d1m; t.n1k = 0; t.d1k = 0; }
+}
+__device__ __forceinline__ float tier_finish(Tier& t) { t.d1k = t.d + t.d1k; t.d1m = t.d1k + t.d1m; return t.d1m; }
+
+// one CTA per (host,target) bucket; thread e < 66 owns one cell of AccumulatorApprox and walks the pair's residuals in order
+constexpr int kTopChunk = 32;
+__global__ void __launch_bounds__(96) ba_acc_top_kernel(BAHeader* __restrict__ H, BAResDev R) {
+  const int pair = blockIdx.x; const int e = threadIdx.x;
+  __shared__ float sJ[kTopChunk][24]; __shared__ int sAct[kTopChunk];
+  int ei = 0, ej = 0;                                                        // cell (j row, i col) of the 10x10 upper triangle, Data[] order
+  if (e < 55) { int k = e; int j = 0; while (k >= 10 - j) { k -= 10 - j; j++; } ej = j; ei = j + k; }
+  else if (e < 65) { ei = e - 55; }
+  Tier t = {0,0,0,0,0}; int num = 0;
+  const int b0 = R.pair_begin[pair], b1 = R.pair_begin[pair+1];
+  for (int base = b0; base < b1; base += kTopChunk) {
+    const int cnt = min(kTopChunk, b1 - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt*24; k += 96) { int q = k/24, c = k - q*24; int r = R.pair_res[base+q]; sJ[q][c] = R.efJ[(size_t)r*24+c]; }
+    if (threadIdx.x < cnt) sAct[threadIdx.x] = R.isActive[R.pair_res[base+threadIdx.x]];
+    __syncthreads();
+    if (e < kNTop) {
+      for (int q = 0; q < cnt; q++) {
+        if (!sAct[q]) continue;
+        const float* J = sJ[q]; num++;
+        // x = [Jpdc[0](4) ; Jpdxi[0](6)], y = [Jpdc[1] ; Jpdxi[1]]
+        if (e < 55) {
+          float xi = (ei < 4) ? J[14+ei] : J[2+ei-4], xj = (ej < 4) ? J[14+ej] : J[2+ej-4];
+          float yi = (ei < 4) ? J[18+ei] : J[8+ei-4], yj = (ej < 4) ? J[18+ej] : J[8+ej-4];
+          t.d += 1.0f*xi*xj + 1.0f*yi*yj + 0.0f*(xi*yj + yi*xj);            // update(x4,x6,y4,y6, a=1,b=0,c=1)
+          t.n1 += 1; tier_shift(t);
+        } else {
+          t.n1 += 1; tier_shift(t);                                          // the tier shift happens inside update(), before TopRight/BotRight are touched
+          if (e < 65) { float xi = (ei < 4) ? J[14+ei] : J[2+ei-4], yi = (ei < 4) ? J[18+ei] : J[8+ei-4]; t.d += xi*J[0] + yi*J[1]; }
+          else t.d += J[0]*J[0] + J[1]*J[1];
+        }
+      }
+    }
+  }
+  if (e < kNTop) H->accTop[pair*kNTop + e] = tier_finish(t);
+  if (e == 0) H->accTopNum[pair] = num;
+}
+
+// one CTA per host frame: accD (t1,t2,6x6), accE (t1,6x4), accEB (t1,6); CTA 0 also owns accHcc/accbc over all points
+__global__ void __launch_bounds__(256) ba_acc_sc_kernel(BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nP) {
+  const int h = blockIdx.x; const int nF = H->nF; const int nF2 = nF*nF;
+  const int p0 = R.host_begin[h], p1 = R.host_begin[h+1];
+  const int nD = nF2*36, nE = nF*24, nEB = nF*6;
+  for (int e = threadIdx.x; e < nD + nE + nEB; e += 256) {
+    Tier t = {0,0,0,0,0}; int num = 0;
+    int kind, t1, t2 = 0, i, j = 0;
+    if (e < nD) { kind = 0; int q = e/36; t1 = q % nF; t2 = q / nF; i = (e%36)/6; j = e%6; }
+    else if (e < nD + nE) { kind = 1; int q = e - nD; t1 = q/24; i = (q%24)/4; j = q%4; }
+    else { kind = 2; int q = e - nD - nE; t1 = q/6; i = q%6; }
+    for (int p = p0; p < p1; p++) {
+      if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
+      const int r1 = P.res_of_target[(size_t)p*kMaxF + t1]; if (r1 < 0 || !R.isActive[r1]) continue;
+      const float Hdi = P.HdiF[p]; const float wl = Hdi*R.JpJdF[(size_t)r1*8+i];
+      if (kind == 0) { const int r2 = P.res_of_target[(size_t)p*kMaxF + t2]; if (r2 < 0 || !R.isActive[r2]) continue;
+        t.d += wl*R.JpJdF[(size_t)r2*8+j]; }                                // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
+      else if (kind == 1) t.d += wl*(P.Hcd_accAF[(size_t)p*4+j] + 0.0f);
+      else t.d += (Hdi*P.bdSumF[p])*R.JpJdF[(size_t)r1*8+i];                // accEB.update(r1->JpJdF, HdiF*bdSumF): A += w*L
+      num++; t.n1 += 1; tier_shift(t);
+    }
+    float v = tier_finish(t);
+    if (kind == 0) { int b = h + nF*t1 + nF2*t2; H->accD[b*36 + i*6 + j] = v; if (i == 0 && j == 0) H->accDNum[b] = num; }
+    else if (kind == 1) H->accE[(h + nF*t1)*24 + i*4 + j] = v;
+    else H->accEB[(h + nF*t1)*6 + i] = v;
+  }
+  if (h == 0 && threadIdx.x < 20) {
+    const int e = threadIdx.x; Tier t = {0,0,0,0,0};
+    for (int p = 0; p < nP; p++) {
+      if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
+      const float Hdi = P.HdiF[p];
+      if (e < 16) t.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e%4] + 0.0f);
+      else t.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e-16] + 0.0f);
+      t.n1 += 1; tier_shift(t);
+    }
+    float v = tier_finish(t); if (e < 16) H->accHcc[e] = v; else H->accbc[e-16] = v;
+  }
+}
+
+// ================================================================================================ stitch + solve (single CTA)
+__device__ __forceinline__ void mm66_elem(const double* A, const double* B, double* C, int e) { int i = e/6, j = e%6; double s = 0; for (int k=0;k<6;k++) s += A[i*6+k]*B[k*6+j]; C[e] = s; }
+__device__ __forceinline__ void mm66T_elem(const double* A, const double* B, double* C, int e) { int i = e/6, j = e%6; double s = 0; for (int k=0;k<6;k++) s += A[i*6+k]*B[j*6+k]; C[e] = s; }
+
+constexpr int kSolveThreads = 256;
+__global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(BAHeader* __restrict__ H, int iteration, double lambda) {
+  const int tid = threadIdx.x; const int nF = H->nF, N = H->dim, nF2 = nF*nF;
+  __shared__ double sA[kMaxDim*kMaxDim];                                    // working matrix (HFinal scaled -> LDLT in place)
+  __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim];
+  __shared__ double T1[36], T2[36], T3[36], accH66[36], accH64[24], accb[10], acc44[16];
+  __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double sred[kSolveThreads];
+  double* HA = H->HA; double* Hsc = H->Hsc;
+  for (int i = tid; i < N*N; i += kSolveThreads) { HA[i] = 0; Hsc[i] = 0; }
+  for (int i = tid; i < N; i += kSolveThreads) { H->bA[i] = 0; H->bsc[i] = 0; }
+  __syncthreads();
+  // ---- top stitch (AccumulatedTopHessian.cpp:181-242): pairs in order k = h + nF*t, each block update parallel over its elements
+  int resInA = 0;
+  for (int k = 0; k < nF2; k++) {
+    const int h = k % nF, t = k / nF, hIdx = kCP + h*6, tIdx = kCP + t*6;
+    const float* a = H->accTop + k*kNTop; const bool empty = (H->accTopNum[k] == 0); resInA += H->accTopNum[k];
+    if (tid < 36) { int r = 4 + tid/6, c = 4 + tid%6; int lo = min(r,c), hi = max(r,c); int off = lo*10 - lo*(lo-1)/2 + (hi-lo); accH66[tid] = empty ? 0.0 : (double)a[off]; }
+    else if (tid < 60) { int q = tid-36; int r = 4 + q/4, c = q%4; int off = c*10 - c*(c-1)/2 + (r-c); accH64[q] = empty ? 0.0 : (double)a[off]; }
+    else if (tid < 76) { int q = tid-60; int r = q/4, c = q%4; int lo = min(r,c), hi = max(r,c); int off = lo*10 - lo*(lo-1)/2 + (hi-lo); acc44[q] = empty ? 0.0 : (double)a[off]; }
+    else if (tid < 86) { accb[tid-76] = empty ? 0.0 : (double)a[55 + tid-76]; }
+    __syncthreads();
+    const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36;
+    if (tid < 36) mm66_elem(AH, accH66, T1, tid); else if (tid >= 64 && tid < 100) mm66_elem(AT, accH66, T3, tid-64);
+    __syncthreads();
+    if (tid < 36) { mm66T_elem(T1, AH, T2, tid); HA[(hIdx+tid/6)*N + hIdx+tid%6] += T2[tid]; }
+    __syncthreads();
+    if (tid < 36) { mm66T_elem(T1, AT, T2, tid); HA[(hIdx+tid/6)*N + tIdx+tid%6] += T2[tid]; }
+    __syncthreads();
+    if (tid < 36) { mm66T_elem(T3, AT, T2, tid); HA[(tIdx+tid/6)*N + tIdx+tid%6] += T2[tid]; }
+    __syncthreads();
+    if (tid < 24) { int r = tid/4, c = tid%4; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*accH64[q*4+c]; HA[(hIdx+r)*N + c] += s1; }
+    __syncthreads();
+    if (tid < 24) { int r = tid/4, c = tid%4; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*accH64[q*4+c]; HA[(tIdx+r)*N + c] += s2; }
+    if (tid >= 32 && tid < 48) { int q = tid-32; HA[(q/4)*N + q%4] += acc44[q]; }
+    if (tid >= 64 && tid < 70) { int r = tid-64; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*accb[4+q]; H->bA[hIdx+r] += s1; }
+    __syncthreads();
+    if (tid >= 64 && tid < 70) { int r = tid-64; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*accb[4+q]; H->bA[tIdx+r] += s2; }
+    if (tid >= 96 && tid < 100) H->bA[tid-96] += accb[tid-96];
+    __syncthreads();
+  }
+  if (tid < 4) { HA[tid*N+tid] += H->calib.cPrior[tid]; H->bA[tid] += H->calib.cPrior[tid]*(double)H->calib.cDeltaF[tid]; }
+  if (tid >= 32 && tid < 32 + 6*nF) { int q = tid-32, f = q/6, i = q%6, d = kCP + f*6 + i; HA[d*N+d] += H->frames[f].prior[i]; H->bA[d] += H->frames[f].prior[i]*H->frames[f].delta_prior[i]; }
+  __syncthreads();
+  for (int h = 0; h < nF; h++) {                                            // AccumulatedTopHessian.h:100-113
+    const int hIdx = kCP + h*6;
+    if (tid < 24) { int r = tid/6, c = tid%6; HA[r*N + hIdx+c] = HA[(hIdx+c)*N + r]; }
+    for (int t = h+1; t < nF; t++) { const int tIdx = kCP + t*6;
+      if (tid < 36) { int r = tid/6, c = tid%6; HA[(hIdx+r)*N + tIdx+c] += HA[(tIdx+c)*N + hIdx+r]; }
+      __syncthreads();
+      if (tid < 36) { int r = tid/6, c = tid%6; HA[(tIdx+r)*N + hIdx+c] = HA[(hIdx+c)*N + tIdx+r]; } }
+    __syncthreads();
+  }
+  // ---- SC stitch (AccumulatedSCHessian.cpp:64-135)
+  for (int k = 0; k < nF2; k++) {
+    const int i = k % nF, j = k / nF, iIdx = kCP + i*6, jIdx = kCP + j*6, ij = i + nF*j;
+    const double* AHij = H->adHost + ij*36; const double* ATij = H->adTarget + ij*36;
+    if (tid < 24) { int r = tid/4, c = tid%4; double s1 = 0; for (int q=0;q<6;q++) s1 += AHij[r*6+q]*(double)H->accE[ij*24+q*4+c]; Hsc[(iIdx+r)*N + c] += s1; }
+    if (tid >= 32 && tid < 38) { int r = tid-32; double s1 = 0; for (int q=0;q<6;q++) s1 += AHij[r*6+q]*(double)H->accEB[ij*6+q]; H->bsc[iIdx+r] += s1; }
+    __syncthreads();
+    if (tid < 24) { int r = tid/4, c = tid%4; double s2 = 0; for (int q=0;q<6;q++) s2 += ATij[r*6+q]*(double)H->accE[ij*24+q*4+c]; Hsc[(jIdx+r)*N + c] += s2; }
+    if (tid >= 32 && tid < 38) { int r = tid-32; double s2 = 0; for (int q=0;q<6;q++) s2 += ATij[r*6+q]*(double)H->accEB[ij*6+q]; H->bsc[jIdx+r] += s2; }
+    __syncthreads();
+    for (int k2 = 0; k2 < nF; k2++) {
+      const int kIdx = kCP + k2*6, ik = i + nF*k2, b = ij + k2*nF2;
+      if (H->accDNum[b] == 0) continue;                                    // uniform branch
+      const double* AHik = H->adHost + ik*36; const double* ATik = H->adTarget + ik*36;
+      if (tid < 36) accH66[tid] = (double)H->accD[b*36+tid];
+      __syncthreads();
+      if (tid < 36) mm66_elem(AHij, accH66, T1, tid); else if (tid >= 64 && tid < 100) mm66_elem(ATij, accH66, T3, tid-64);
+      __syncthreads();
+      if (tid < 36) { mm66T_elem(T1, AHik, T2, tid); Hsc[(iIdx+tid/6)*N + iIdx+tid%6] += T2[tid]; }
+      __syncthreads();
+      if (tid < 36) { mm66T_elem(T3, ATik, T2, tid); Hsc[(jIdx+tid/6)*N + kIdx+tid%6] += T2[tid]; }
+      __syncthreads();
+      if (tid < 36) { mm66T_elem(T3, AHik, T2, tid); Hsc[(jIdx+tid/6)*N + iIdx+tid%6] += T2[tid]; }
+      __syncthreads();
+      if (tid < 36) { mm66T_elem(T1, ATik, T2, tid); Hsc[(iIdx+tid/6)*N + kIdx+tid%6] += T2[tid]; }
+      __syncthreads();
+    }
+  }
+  if (tid < 16) Hsc[(tid/4)*N + tid%4] += (double)H->accHcc[tid];
+  if (tid >= 32 && tid < 36) H->bsc[tid-32] += (double)H->accbc[tid-32];
+  __syncthreads();
+  for (int h = 0; h < nF; h++) { const int hIdx = kCP + h*6; if (tid < 24) { int r = tid/6, c = tid%6; Hsc[r*N + hIdx+c] = Hsc[(hIdx+c)*N + r]; } }
+  __syncthreads();
+  // ---- HFinal / bFinal, damping, diagonal pre-scaling (EnergyFunctional.cpp:668-744)
+  if (tid < N) {
+    double s = 0; for (int j=0;j<N;j++) { double dj = (j < 4) ? (double)H->calib.cDeltaF[j] : H->frames[(j-4)/6].delta[(j-4)%6]; s += H->HM[tid*N+j]*dj; }
+    double bf = H->bA[tid] + (H->bM[tid] + s) - H->bsc[tid]; H->lastbS[tid] = bf; sb[tid] = bf;
+  }
+  for (int i = tid; i < N*N; i += kSolveThreads) { double v = HA[i] + H->HM[i] - Hsc[i]; H->lastHS[i] = v; sA[i] = v; }
+  __syncthreads();
+  if (tid < N) { sA[tid*N+tid] *= (1+lambda); }
+  __syncthreads();
+  if (tid < N) sv[tid] = 1.0/sqrt(sA[tid*N+tid] + 10);
+  __syncthreads();
+  for (int i = tid; i < N*N; i += kSolveThreads) { int r = i/N, c = i%N; sA[i] = sv[r]*sA[i]*sv[c]; }
+  if (tid < N) sb[tid] = sv[tid]*sb[tid];
+  __syncthreads();
+  // ---- pivoted LDLT, left-looking like Eigen's unblocked kernel: every dot product is evaluated by ONE thread in index order
+  for (int k = 0; k < N; k++) {
+    if (tid == 0) { int piv = k; double big = fabs(sA[k*N+k]); for (int i=k+1;i<N;i++) { double a = fabs(sA[i*N+i]); if (a > big) { big = a; piv = i; } } spiv = piv; sperm[k] = piv; }
+    __syncthreads();
+    const int piv = spiv;
+    if (piv != k) {
+      if (tid < k) { double s = sA[k*N+tid]; sA[k*N+tid] = sA[piv*N+tid]; sA[piv*N+tid] = s; }
+      else if (tid > piv && tid < N) { double s = sA[tid*N+k]; sA[tid*N+k] = sA[tid*N+piv]; sA[tid*N+piv] = s; }
+      else if (tid > k && tid < piv) { double s = sA[tid*N+k]; sA[tid*N+k] = sA[piv*N+tid]; sA[piv*N+tid] = s; }
+      else if (tid == k) { double s = sA[k*N+k]; sA[k*N+k] = sA[piv*N+piv]; sA[piv*N+piv] = s; }
+      __syncthreads();
+    }
+    if (tid < k) stmp[tid] = sA[tid*N+tid]*sA[k*N+tid];
+    __syncthreads();
+    if (tid == k && k > 0) { double s = 0; for (int j=0;j<k;j++) s += sA[k*N+j]*stmp[j]; sA[k*N+k] -= s; }
+    if (tid > k && tid < N && k > 0) { double s2 = 0; for (int j=0;j<k;j++) s2 += sA[tid*N+j]*stmp[j]; sA[tid*N+k] -= s2; }
+    __syncthreads();
+    const double akk = sA[k*N+k];
+    if (tid > k && tid < N && fabs(akk) > 0) sA[tid*N+k] /= akk;
+    __syncthreads();
+  }
+  if (tid == 0) {                                                           // solve: P, L^-1, D^+, L^-T, P^T  (sequential, reference order)
+    for (int i=0;i<N;i++) sx[i] = sb[i];
+    for (int k=0;k<N;k++) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; }
+    for (int i=0;i<N;i++) { double s = sx[i]; for (int j=0;j<i;j++) s -= sA[i*N+j]*sx[j]; sx[i] = s; }
+    double dmax = 0; for (int i=0;i<N;i++) dmax = fmax(dmax, fabs(sA[i*N+i]));
+    double tol = fmax(dmax*2.220446049250313e-16, 1.0/1.7976931348623157e308);
+    for (int i=0;i<N;i++) { double d = sA[i*N+i]; sx[i] = (fabs(d) > tol) ? sx[i]/d : 0.0; }
+    for (int i=N-1;i>=0;i--) { double s = sx[i]; for (int j=i+1;j<N;j++) s -= sA[j*N+i]*sx[j]; sx[i] = s; }
+    for (int k=N-1;k>=0;k--) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; }
+    for (int i=0;i<N;i++) sx[i] = sv[i]*sx[i];
+  }
+  __syncthreads();
+  // ---- orthogonalize x against the pose+scale nullspaces for iteration >= 2 (EnergyFunctional.cpp:615-648, 746-750)
+  if (iteration >= 2) {
+    const int m = 7; double* A = sA;                                        // reuse: N x 7 column-major-by-column in sA
+    for (int e = tid; e < N*m; e += kSolveThreads) { int r = e % N, i = e / N; double v = 0;
+      if (r >= kCP) { int f = (r-kCP)/6, q = (r-kCP)%6; v = (i < 6) ? H->frames[f].nullspaces_pose[q*6+i] : H->frames[f].nullspaces_scale[q]; v *= (q < 3) ? (double)(1.0f/0.5f) : (double)(1.0f/1.0f); }
+      A[i*N + r] = v; }
+    __syncthreads();
+    if (tid < m) { double nr = 0; for (int r=0;r<N;r++) nr += A[tid*N+r]*A[tid*N+r]; nr = sqrt(nr); for (int r=0;r<N;r++) A[tid*N+r] /= nr; }
+    __syncthreads();
+    if (tid == 0) {                                                         // one-sided Jacobi (Hestenes); 7 columns, tiny
+      for (int sweep = 0; sweep < 60; sweep++) { double off = 0;
+        for (int p=0;p<m;p++) for (int q=p+1;q<m;q++) {
+          double al = 0, be = 0, ga = 0; for (int r=0;r<N;r++) { double ap = A[p*N+r], aq = A[q*N+r]; al += ap*ap; be += aq*aq; ga += ap*aq; }
+          if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17*sqrt(al*be)) continue;
+          off = fmax(off, fabs(ga)/sqrt(al*be + 1e-300));
+          double zeta = (be-al)/(2*ga), tt = ((zeta >= 0) ? 1.0 : -1.0)/(fabs(zeta) + sqrt(1+zeta*zeta)), c = 1/sqrt(1+tt*tt), s = c*tt;
+          for (int r=0;r<N;r++) { double ap = A[p*N+r], aq = A[q*N+r]; A[p*N+r] = c*ap - s*aq; A[q*N+r] = s*ap + c*aq; } }
+        if (off < 1e-15) break; }
+      double svals[7], maxSv = 0; for (int i=0;i<m;i++) { double nr = 0; for (int r=0;r<N;r++) nr += A[i*N+r]*A[i*N+r]; svals[i] = sqrt(nr); maxSv = fmax(maxSv, svals[i]); }
+      for (int r=0;r<N;r++) stmp[r] = 0;
+      for (int i=0;i<m;i++) { if (!(svals[i] > H->set.solverModeDelta*maxSv)) continue;
+        double dot = 0; for (int r=0;r<N;r++) dot += (A[i*N+r]/svals[i])*sx[r];
+        for (int r=0;r<N;r++) stmp[r] += (A[i*N+r]/svals[i])*dot; }
+      for (int r=0;r<N;r++) sx[r] -= stmp[r];
+    }
+    __syncthreads();
+  }
+  // ---- lastX, steps, xAd (resubstituteF_MT head, EnergyFunctional.cpp:221-248)
+  if (tid < N) { H->lastX[tid] = sx[tid]; H->xF[tid] = (float)sx[tid]; }
+  if (tid < 4) H->calib.step[tid] = -sx[tid];
+  if (tid >= 32 && tid < 32 + nF) { BAFrameDev& f = H->frames[tid-32]; for (int i=0;i<6;i++) f.step[i] = -sx[kCP + 6*(tid-32) + i]; for (int i=6;i<10;i++) f.step[i] = 0; }
+  if (tid == 0) H->resInA = resInA;
+  __syncthreads();
+  for (int e = tid; e < nF2*6; e += kSolveThreads) { int pr = e/6, j = e%6, h = pr / nF, t = pr % nF;       // xAd[nF*h + t]
+    float s1 = 0, s2 = 0; for (int i=0;i<6;i++) { s1 += H->xF[kCP+6*h+i]*H->adHostF[(h+nF*t)*36+i*6+j]; s2 += H->xF[kCP+6*t+i]*H->adTargetF[(h+nF*t)*36+i*6+j]; }
+    H->xAd[(nF*h+t)*6+j] = s1 + s2; }
+  (void)sred;
+}
+
+__global__ void ba_resub_kernel(const BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nP) {     // resubstituteFPt (:250-282)
+  int p = blockIdx.x*blockDim.x + threadIdx.x; if (p >= nP) return;
+  if (P.ngood[p] == 0) { P.step[p] = 0; return; }
+  const int nF = H->nF;
+  float b = P.bdSumF[p];
+  { float s = 0; for (int i=0;i<4;i++) s += H->xF[i]*P.Hcd_accAF[(size_t)p*4+i]; b -= s; }
+  for (int r = P.res_begin[p]; r < P.res_begin[p+1]; r++) { if (!R.isActive[r]) continue;
+    const float* xa = H->xAd + (R.host[r]*nF + R.target[r])*6; float s = 0; for (int i=0;i<6;i++) s += xa[i]*R.JpJdF[(size_t)r*8+i]; b -= s; }
+  P.step[p] = P.isFromSensor[p] ? 0.0f : -b*P.HdiF[p];
+}
+
+// ================================================================================================ backup / step
+__global__ void ba_backup_kernel(BAHeader* __restrict__ H, BAPointsDev P, int nP) {
+  int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < nP) P.idepth_backup[i] = P.idepth[i];
+  if (i < H->nF) for (int k=0;k<10;k++) H->frames[i].state_backup[k] = H->frames[i].state[k];
+  if (i == 0) for (int k=0;k<4;k++) H->calib.value_backup[k] = H->calib.value[k];
+}
+// points part of doStepFromBackup / loadSateBackup + the float sums the break test needs (single CTA keeps the reduction fixed-order)
+__global__ void __launch_bounds__(1024) ba_step_points_kernel(BAHeader* __restrict__ H, BAPointsDev P, int nP, float stepfac, int load_backup) {
+  __shared__ float s1[1024], s2[1024];
+  float sumID = 0, sumNID = 0;
+  for (int i = threadIdx.x; i < nP; i += 1024) {
+    float nv = load_backup ? P.idepth_backup[i] : P.idepth_backup[i] + stepfac*P.step[i];
+    P.idepth[i] = nv; P.idepth_zero[i] = nv; P.deltaF[i] = nv - nv;
+    sumID += P.step[i]*P.step[i]; sumNID += fabsf(P.idepth_backup[i]);
+  }
+  s1[threadIdx.x] = sumID; s2[threadIdx.x] = sumNID; __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) { if (threadIdx.x < o) { s1[threadIdx.x] += s1[threadIdx.x+o]; s2[threadIdx.x] += s2[threadIdx.x+o]; } __syncthreads(); }
+  if (threadIdx.x == 0) { H->sums[0] = s1[0]; H->sums[1] = s2[0]; H->sums[2] = (float)nP; }
+}
+
+// ================================================================================================ launchers
+void launch_ba_setup(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) {
+  ba_frames_kernel<<<1, 64, 0, st>>>(hdr, 1|2|4|8|16, 0.f, 0);
+  if (nP > 0) ba_points_setup_kernel<<<(nP+255)/256, 256, 0, st>>>(hdr, P, nP, 1);
+}
+void launch_ba_reset_oob(BAResDev R, int nR, cudaStream_t st) { if (nR > 0) ba_reset_oob_kernel<<<(nR+255)/256, 256, 0, st>>>(R, nR); }
+void launch_ba_linearize(BAHeader* hdr, BAPointsDev P, BAResDev R, int nR, int fix, double* partials, float* thbuf, int* thcount, cudaStream_t st) {
+  int grid = (nR + kLinThreads - 1)/kLinThreads; if (grid < 1) grid = 1;
+  ba_linearize_kernel<<<grid, kLinThreads, 0, st>>>(hdr, P, R, nR, fix, partials, thbuf, thcount);
+  ba_energy_th_kernel<<<1, 1024, 0, st>>>(hdr, thbuf, thcount);
+}
+void launch_ba_apply(BAResDev R, int nR, cudaStream_t st) { if (nR > 0) ba_apply_kernel<<<(nR+255)/256, 256, 0, st>>>(R, nR); }
+void launch_ba_energies(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) { ba_energies_kernel<<<1, 256, 0, st>>>(hdr, P, nP); }
+void launch_ba_accumulate(BAHeader* hdr, BAPointsDev P, BAResDev R, int nF, int nP, cudaStream_t st) {
+  if (nP > 0) ba_point_acc_kernel<<<(nP+127)/128, 128, 0, st>>>(hdr, P, R, nP);
+  ba_acc_top_kernel<<<nF*nF, 96, 0, st>>>(hdr, R);
+  ba_acc_sc_kernel<<<nF, 256, 0, st>>>(hdr, P, R, nP);
+}
+void launch_ba_solve(BAHeader* hdr, BAPointsDev P, BAResDev R, int nP, int iteration, double lambda, cudaStream_t st) {
+  ba_solve_kernel<<<1, kSolveThreads, 0, st>>>(hdr, iteration, lambda);
+  if (nP > 0) ba_resub_kernel<<<(nP+127)/128, 128, 0, st>>>(hdr, P, R, nP);
+}
+void launch_ba_backup(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) { int n = nP > kMaxF ? nP : kMaxF; ba_backup_kernel<<<(n+255)/256, 256, 0, st>>>(hdr, P, nP); }
+void launch_ba_step(BAHeader* hdr, BAPointsDev P, int nP, float stepfac, int load_backup, cudaStream_t st) {
+  ba_step_points_kernel<<<1, 1024, 0, st>>>(hdr, P, nP, stepfac, load_backup);
+  ba_frames_kernel<<<1, 64, 0, st>>>(hdr, 64|1|16, stepfac, load_backup);
+}
+void launch_ba_reanchor(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) {
+  ba_frames_kernel<<<1, 64, 0, st>>>(hdr, 32|8|16, 0.f, 0);
+  if (nP > 0) ba_points_setup_kernel<<<(nP+255)/256, 256, 0, st>>>(hdr, P, nP, 0);
+}
+
+} // namespace sdv

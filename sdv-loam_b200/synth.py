@@ -184,3 +184,87 @@ class Sequence:
             img, _ = render(self.world, self.R[i], self.t[i], K, wh, gain=g, bias=b, noise=noise, seed=seed * 1000 + i)
             self.images.append(img)
             self.clouds.append(lidar_pixels(self.world, self.R[i], self.t[i], K, wh, beams=beams))
+
+
+# ------------------------------------------------------------------------------------------------ back-end (BA) window
+PATTERN8 = np.array([[0, -2], [-1, -1], [1, -1], [-2, 0], [0, 0], [2, 0], [-1, 1], [0, 2]])   # src/util/settings.cpp:250
+
+
+def _quat_from_R(R):
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2; return np.array([0.25 * s, (R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s])
+    i = int(np.argmax(np.diag(R))); j, k = (i + 1) % 3, (i + 2) % 3
+    s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+    q = np.zeros(4); q[0] = (R[k, j] - R[j, k]) / s; q[1 + i] = 0.25 * s; q[1 + j] = (R[j, i] + R[i, j]) / s; q[1 + k] = (R[k, i] + R[i, k]) / s
+    return q
+
+
+def make_ba_window(seq: "Sequence", kf_idx, n_per_frame: int = 250, seed: int = 0, sensor_frac: float = 0.7, pose_noise=(0.02, 0.002),
+                   match_noise: float = 0.3, idepth_noise: float = 0.03, prior_scale: float = 0.0, no_matcher_frac: float = 0.03):
+    """Flattened sliding window in the reference's iteration order (frames = ef->frames, points = ef->allPoints,
+    residuals grouped per point).  Stands in for the host-side bookkeeping that is out of scope (point activation,
+    Reprojector matches, marginalisation prior):
+      * keyframes kf_idx of `seq`, evaluation-point poses = ground truth perturbed by pose_noise (m, rad) except frame 0
+      * points: integer host pixels on LiDAR hits (isFromSensor, fixed depth) or vision-only (noisy idepth)
+      * one residual per (point, other keyframe in view); matcher = ground-truth reprojection + match_noise px
+    Returns a dict of numpy arrays consumed by both the oracle (orc.BAWindow) and the CUDA path (api.BAWindow)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = seq.K; w, h = seq.wh; nF = len(kf_idx)
+    Rw2c = [seq.R[k].T for k in kf_idx]; tw2c = [-seq.R[k].T @ seq.t[k] for k in kf_idx]
+    T_eval = np.zeros((nF, 7)); state = np.zeros((nF, 10)); state_zero = np.zeros((nF, 10))
+    for i in range(nF):
+        R, t = Rw2c[i], tw2c[i]
+        if i > 0:
+            dR = _rot(*rng.normal(0, pose_noise[1], 3)); R = dR @ R; t = dR @ t + rng.normal(0, pose_noise[0], 3)
+        T_eval[i, :4] = _quat_from_R(R); T_eval[i, 4:] = t
+    uv, idp, color, weights, host, hasPrior, fromSensor, res_begin = [], [], [], [], [], [], [], [0]
+    r_point, r_host, r_target, r_hasM, r_match, r_new = [], [], [], [], [], []
+    for hi, k in enumerate(kf_idx):
+        img = seq.images[k]; cloud = seq.clouds[k]
+        sel = select_points(img, cloud, n_per_frame, seed=seed + hi)
+        gx = np.zeros_like(img); gy = np.zeros_like(img)
+        gx[:, 1:-1] = 0.5 * (img[:, 2:] - img[:, :-2]); gy[1:-1, :] = 0.5 * (img[2:, :] - img[:-2, :])
+        for (pu, pv, pid) in sel:
+            u, v = int(pu), int(pv)                                      # ImmaturePoint truncates LiDAR sub-pixel coordinates (ImmaturePoint.cpp:8)
+            if u < 4 or v < 4 or u >= w - 5 or v >= h - 5:
+                continue
+            d_true = 1.0 / pid
+            sensor = rng.uniform() < sensor_frac
+            idepth = pid if sensor else pid * (1.0 + rng.normal(0, idepth_noise))
+            Xc = np.array([(u - cx) / fx, (v - cy) / fy, 1.0]) * d_true
+            Xw = seq.R[k] @ Xc + seq.t[k]
+            pidx = len(uv); nres = 0
+            for ti in range(nF):
+                if ti == hi:
+                    continue
+                Xt = Rw2c[ti] @ Xw + tw2c[ti]
+                if Xt[2] < 0.5:
+                    continue
+                Ku, Kv = fx * Xt[0] / Xt[2] + cx, fy * Xt[1] / Xt[2] + cy
+                if not (Ku > 6 and Kv > 6 and Ku < w - 7 and Kv < h - 7):
+                    continue
+                r_point.append(pidx); r_host.append(hi); r_target.append(ti)
+                r_hasM.append(0 if rng.uniform() < no_matcher_frac else 1)
+                r_match.append([Ku + rng.normal(0, match_noise), Kv + rng.normal(0, match_noise)]); r_new.append(1); nres += 1
+            if nres == 0:
+                continue
+            uv.append([u, v]); idp.append(idepth)
+            pu8, pv8 = u + PATTERN8[:, 0], v + PATTERN8[:, 1]
+            color.append(img[pv8, pu8]); g2 = gx[pv8, pu8] ** 2 + gy[pv8, pu8] ** 2
+            weights.append(np.sqrt(2500.0 / (2500.0 + g2)))              # setting_outlierTHSumComponent weighting of the host pattern
+            host.append(hi); hasPrior.append(1 if sensor else 0); fromSensor.append(1 if sensor else 0)
+            res_begin.append(len(r_point))
+    n = 4 + 6 * nF
+    if prior_scale > 0:
+        A = rng.normal(size=(n + 4, n)); HM = prior_scale * (A.T @ A); bM = prior_scale * rng.normal(size=n)
+    else:
+        HM = np.zeros((n, n)); bM = np.zeros(n)
+    return dict(nF=nF, kf_idx=list(kf_idx), K=np.array(seq.K, np.float64), wh=(w, h), T_eval=T_eval, state=state, state_zero=state_zero,
+                ab_exposure=np.ones(nF, np.float32), frameID=np.arange(nF, dtype=np.int32), frameEnergyTH=np.full(nF, 8 * 8 * 8, np.float32),
+                uv=np.array(uv, np.float32), idepth=np.array(idp, np.float32), idepth_zero=np.array(idp, np.float32),
+                color=np.array(color, np.float32), weights=np.array(weights, np.float32), host=np.array(host, np.int32),
+                hasDepthPrior=np.array(hasPrior, np.int32), isFromSensor=np.array(fromSensor, np.int32), res_begin=np.array(res_begin, np.int32),
+                r_point=np.array(r_point, np.int32), r_host=np.array(r_host, np.int32), r_target=np.array(r_target, np.int32),
+                r_hasMatcher=np.array(r_hasM, np.int32), r_matcher=np.array(r_match, np.float32), r_isNew=np.array(r_new, np.int32),
+                HM=HM, bM=bM, T_gt=np.array([np.concatenate([_quat_from_R(Rw2c[i]), tw2c[i]]) for i in range(nF)]))
