@@ -47,3 +47,23 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def main_ba():
+    """Back-end fixture: same window as tests/test_oracle_ba.py::window (seed-identical), frozen oracle outputs of optimize()."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import cached_sequence
+    seq = cached_sequence(5, 3000, K, WH)
+    win = synth.make_ba_window(seq, [0, 1, 2, 3, 4], n_per_frame=120, seed=5, pose_noise=(0.004, 0.0003), match_noise=0.15, prior_scale=1e-2)
+    frames = [orc.Frame(seq.images[k], 4) for k in win["kf_idx"]]
+    ba = orc.BAWindow(win, frames); r = ba.optimize(6)
+    fr = ba.frames(); pts = ba.points(); rs = ba.residuals()
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ba_small.npz"), iterations=r["iterations"], accepts=r["accepts"], rmse=r["rmse"],
+                        T_eval=fr["T_eval"], state=fr["state"], frameEnergyTH=fr["frameEnergyTH"], idepth=pts["idepth"], res_state=rs["state"],
+                        images=np.stack([seq.images[k] for k in win["kf_idx"]]).astype(np.uint8),
+                        **{"win_" + k: np.asarray(v) for k, v in win.items() if k not in ("wh", "kf_idx")})
+    print("ba:", r, np.bincount(rs["state"], minlength=3))
+
+
+if __name__ == "__main__" and "--ba" in sys.argv or __name__ == "__main__":
+    main_ba()
