@@ -232,22 +232,25 @@ def main():
     host_in = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.float32).pin_memory()
     for k in range(N_FRAMES - 1):
         host_in[k].copy_(torch.from_numpy(frames_np[k]).expand(B, h, w))
-    slots = list(range(B))
+    slots = np.arange(B, dtype=np.int32)
+    ids_par = [np.arange(B, dtype=np.uint64) * 2 + p for p in (0, 1)]       # frame handles alternate between two pool slots per sequence
+    stride = h * w * 4
+    dev_ptrs = [np.uint64(dev_in[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(stride) for k in range(N_FRAMES - 1)]
+    host_ptrs = None
 
     def frame_ids(step):
-        return [2 * b + (step & 1) for b in range(B)]
+        return ids_par[step & 1]
 
     def step_dev(step):
-        k = step % (N_FRAMES - 1)
-        base = dev_in[k].data_ptr(); stride = h * w * 4
-        ctx.makeImagesBatch(frame_ids(step), [base + b * stride for b in range(B)], device=True)
+        ctx.makeImagesBatch(frame_ids(step), dev_ptrs[step % (N_FRAMES - 1)], device=True, adopt=True)   # zero-copy: level-0 plane = the resident input
         T = inits[step].copy(); ab = np.zeros((B, 2))
         r = ctx.trackBatch(slots, frame_ids(step), T, ab)
         return r, T
 
+    host_ptrs = [np.uint64(host_in[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(stride) for k in range(N_FRAMES - 1)]
+
     def upload_host(step):
-        base = host_in[step % (N_FRAMES - 1)].data_ptr(); stride = h * w * 4
-        ctx.makeImagesBatch(frame_ids(step), [base + b * stride for b in range(B)])
+        ctx.makeImagesBatch(frame_ids(step), host_ptrs[step % (N_FRAMES - 1)])
 
     def barrier():
         torch.cuda.synchronize(); ctx.sync()

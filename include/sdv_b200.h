@@ -46,6 +46,8 @@ typedef struct {                                             /* util/settings.cp
   int   cluster_size;           /* CTAs per thread-block cluster per trackNewestCoarse call in the device-resident LM kernel
                                    (default 1 = batched-throughput mode; 8..16 = low-latency single-sequence mode) */
   int   track_threads;          /* threads per CTA of that kernel: 128 (default, 4 jobs resident per SM), 64 or 256 */
+  int   max_kf_images;          /* pool of packed level-0 {I,dx,dy} images, built on demand for keyframes entering the BA window
+                                   (0 = SDV_MAX_FRAMES_WINDOW + 4); tracked-only frames never materialise them */
 } sdv_settings;
 
 void sdv_default_settings(sdv_settings* s);
@@ -58,7 +60,9 @@ int  sdv_pyr_levels(int w, int h);                           /* pyrLevelsUsed ru
 int  sdv_sync(sdv_ctx* c);                                   /* drain the context's stream */
 
 /* ---- frames: FrameHessian::makeImages(float* color, CalibHessian*)  FullSystem/HessianBlocks.cpp:107-167 ------------
- * builds dIp[lvl] = {I,dx,dy} and absSquaredGrad[lvl] for all levels on the device, keyed by a caller-chosen handle. */
+ * builds the pyramid on the device, keyed by a caller-chosen handle: level 0 is kept as the planar intensity image (its {dx,dy} are
+ * formed on the fly, bit-identically, by the tracker; packed level-0 texels are built lazily when the frame enters a BA window),
+ * levels >= 1 as packed {I,dx,dy,absSquaredGrad} texels. */
 int  sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img_wh, float exposure);
 int  sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs_wh, const float* exposures);
 /* Uploads are ASYNCHRONOUS on a dedicated ingest stream so that they overlap the tracking of the previous batch: pinned host
@@ -67,7 +71,9 @@ int  sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const flo
  * u8->float conversion of the ingest (DatasetReader.h:152-155, Undistort crop without photometric calibration) is fused
  * into the level-0 kernel; 4x less PCIe traffic.   _dev: level-0 images already in device memory (kernel-only timing). */
 int  sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs_wh, const float* exposures);
-int  sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int is_u8, const float* exposures);
+int  sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int fmt, const float* exposures);
+/* fmt: 0 float (copied into frame storage), 1 mono8, 2 float ADOPTED as the frame's level-0 plane (zero copy: the buffer must stay
+ * valid and unmodified until sdv_frame_release / the handle is re-uploaded — for producers that already write into device memory). */
 int  sdv_frame_release(sdv_ctx* c, uint64_t frame);
 /* test hook: copy one level back as AoS {I,dx,dy} (w*h*3 floats) and absSquaredGrad (w*h floats); either may be NULL */
 int  sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out);

@@ -24,12 +24,15 @@ class sdv_settings(C.Structure):
     _fields_ = [("huberTH", C.c_float), ("coarseCutoffTH", C.c_float), ("affineOptModeA", C.c_float), ("affineOptModeB", C.c_float),
                 ("outlierTH", C.c_float), ("outlierTHSumComponent", C.c_float), ("idepthFixPrior", C.c_float),
                 ("max_ref_points", C.c_int), ("n_tracker_slots", C.c_int), ("max_frames", C.c_int), ("cluster_size", C.c_int),
-                ("track_threads", C.c_int)]
+                ("track_threads", C.c_int), ("max_kf_images", C.c_int)]
 
 
 class sdv_track_stats(C.Structure):
     _fields_ = [("point_evals", C.c_int64 * PYR_LEVELS), ("iterations", C.c_int32 * PYR_LEVELS), ("accepts", C.c_int32 * PYR_LEVELS)]
 
+
+TRACK_STATS_DTYPE = np.dtype([("point_evals", np.int64, PYR_LEVELS), ("iterations", np.int32, PYR_LEVELS), ("accepts", np.int32, PYR_LEVELS)])
+assert TRACK_STATS_DTYPE.itemsize == C.sizeof(sdv_track_stats)
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
@@ -125,19 +128,29 @@ class Context:
         assert color.shape == (self.h, self.w)
         self._ck(LIB.sdv_frame_upload(self.p, frame_id, color.ctypes.data, exposure))
 
-    def makeImagesBatch(self, frame_ids, ptrs, exposures=None, u8=False, device=False):
+    def makeImagesBatch(self, frame_ids, ptrs, exposures=None, u8=False, device=False, adopt=False):
         """Batched makeImages.  ptrs: integer addresses of (h,w) buffers — host (pinned for full-rate, asynchronous H2D)
-        or device (device=True); float32, or mono8 when u8=True.  Asynchronous: see sdv_b200.h."""
+        or device (device=True); float32, or mono8 when u8=True.  A uint64 numpy array of addresses avoids per-call list work.
+        Asynchronous: see sdv_b200.h."""
         n = len(frame_ids)
         ids = np.ascontiguousarray(frame_ids, np.uint64)
-        arr = (_vp * n)(*ptrs)
-        ex = np.ones(n, np.float32) if exposures is None else np.ascontiguousarray(exposures, np.float32)
+        if isinstance(ptrs, np.ndarray):
+            parr = np.ascontiguousarray(ptrs, np.uint64); arr = parr.ctypes.data_as(C.POINTER(_vp))
+        else:
+            arr = (_vp * n)(*ptrs)
+        ex = self._ones(n) if exposures is None else np.ascontiguousarray(exposures, np.float32)
         if device:
-            self._ck(LIB.sdv_frame_build_batch_dev(self.p, n, ids, arr, 1 if u8 else 0, ex))
+            self._ck(LIB.sdv_frame_build_batch_dev(self.p, n, ids, arr, 1 if u8 else (2 if adopt else 0), ex))
         elif u8:
             self._ck(LIB.sdv_frame_upload_batch_u8(self.p, n, ids, arr, ex))
         else:
             self._ck(LIB.sdv_frame_upload_batch(self.p, n, ids, arr, ex))
+
+    def _ones(self, n):
+        o = getattr(self, "_ones_cache", None)
+        if o is None or len(o) != n:
+            o = self._ones_cache = np.ones(n, np.float32)
+        return o
 
     def launch_count(self) -> int:
         return int(LIB.sdv_launch_count(self.p))
@@ -155,20 +168,18 @@ class Context:
         return float(LIB.sdv_last_kernel_ms(self.p))
 
     def trackBatch(self, slots, frame_ids, T, ab, coarsest=None, minRes=None):
-        """n independent trackNewestCoarse calls in one launch.  T (n,7), ab (n,2) are updated in place."""
+        """n independent trackNewestCoarse calls in one launch.  T (n,7), ab (n,2) are updated in place.
+        slots / frame_ids may be pre-built contiguous int32 / uint64 arrays (no per-call Python work beyond the C call)."""
         n = len(slots)
         slots = np.ascontiguousarray(slots, np.int32); ids = np.ascontiguousarray(frame_ids, np.uint64)
         assert T.dtype == np.float64 and T.shape == (n, 7) and T.flags.c_contiguous
         assert ab.dtype == np.float64 and ab.shape == (n, 2) and ab.flags.c_contiguous
-        lastRes = np.zeros((n, 5)); flow = np.zeros((n, 3)); good = np.zeros(n, np.int32)
-        stats = (sdv_track_stats * n)()
+        lastRes = np.empty((n, 5)); flow = np.empty((n, 3)); good = np.empty(n, np.int32)
+        stats = np.empty(n, TRACK_STATS_DTYPE)
         mr = None if minRes is None else np.ascontiguousarray(minRes, np.float64).ctypes.data
         self._ck(LIB.sdv_tracker_track_batch(self.p, n, slots, ids, T, ab, self.levels - 1 if coarsest is None else coarsest,
-                                             mr, lastRes, flow, good, stats))
-        evals = np.array([[s.point_evals[l] for l in range(PYR_LEVELS)] for s in stats], np.int64)
-        its = np.array([[s.iterations[l] for l in range(PYR_LEVELS)] for s in stats], np.int32)
-        acc = np.array([[s.accepts[l] for l in range(PYR_LEVELS)] for s in stats], np.int32)
-        return dict(good=good.astype(bool), lastResiduals=lastRes, flow=flow, evals=evals, iterations=its, accepts=acc)
+                                             mr, lastRes, flow, good, stats.ctypes.data_as(C.POINTER(sdv_track_stats))))
+        return dict(good=good.astype(bool), lastResiduals=lastRes, flow=flow, evals=stats["point_evals"], iterations=stats["iterations"], accepts=stats["accepts"])
 
 
 class CoarseTracker:

@@ -8,7 +8,8 @@ CSRC = os.path.join(_HERE, "csrc")
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libsdv_b200.so")
+    # SDV_B200_LIB: explicit library override (used by the tuning scripts to A/B kernel variants)
+    return os.environ.get("SDV_B200_LIB") or os.path.join(_HERE, "libsdv_b200.so")
 
 
 def _stale() -> bool:

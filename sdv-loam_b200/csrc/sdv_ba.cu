@@ -96,6 +96,7 @@ int sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const doubl
     F.evalPT = se3_from7(T_evalPT7 + 7*f);
     for (int i=0;i<10;i++) { F.state[i] = state10[10*f+i]; F.state_zero[i] = state_zero10[10*f+i]; F.state_backup[i] = F.state[i]; F.step[i] = 0; }
     F.ab_exposure = ab_exposure ? ab_exposure[f] : 1.0f; F.frameID = frameID ? frameID[f] : f; F.frameEnergyTH = frameEnergyTH ? frameEnergyTH[f] : 8*8*8;
+    { int rc0 = ensure_lvl0(c, c->frames[it->second]); if (rc0) return rc0; }
     F.img0 = c->frames[it->second].lvl[0];
   }
   const int N = H->dim;

@@ -22,7 +22,7 @@ extern "C" {
 void sdv_default_settings(sdv_settings* s) {
   s->huberTH = 6; s->coarseCutoffTH = 20; s->affineOptModeA = 0; s->affineOptModeB = 0;
   s->outlierTH = 12*12; s->outlierTHSumComponent = 50*50; s->idepthFixPrior = 50*50;
-  s->max_ref_points = 0; s->n_tracker_slots = 2; s->max_frames = 16; s->cluster_size = 1; s->track_threads = 128;
+  s->max_ref_points = 0; s->n_tracker_slots = 2; s->max_frames = 16; s->cluster_size = 1; s->track_threads = 128; s->max_kf_images = 0;
 }
 
 int sdv_pyr_levels(int w, int h) {               // util/globalCalib.cpp:22-30
@@ -69,11 +69,18 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   make_geom(c, K);
   CK(cudaMalloc(&c->tc_dev, sizeof(TrackConst)));
   CK(cudaMemcpy(c->tc_dev, &c->tc, sizeof(TrackConst), cudaMemcpyHostToDevice));
-  // frame pool
-  size_t texels = 0; for (int l=0;l<levels;l++) { c->lvl_off[l] = texels; texels += (size_t)(w>>l)*(h>>l); }
+  // frame pool: level-0 intensity plane + packed texels of levels >= 1 per frame; packed level-0 texels come from a small keyframe pool
+  size_t texels = 0; c->lvl_off[0] = 0; for (int l=1;l<levels;l++) { c->lvl_off[l] = texels; texels += (size_t)(w>>l)*(h>>l); }
   c->frame_texels = texels;
   c->frames.resize(s.max_frames);
-  for (auto& f : c->frames) { f.used = false; CK(cudaMalloc(&f.base, texels*sizeof(float4))); for (int l=0;l<levels;l++) f.lvl[l] = f.base + c->lvl_off[l]; }
+  for (auto& f : c->frames) {
+    f.used = false; f.adopted = false; f.lvl0_slot = -1; f.base = nullptr;
+    CK(cudaMalloc(&f.I0_own, (size_t)w*h*sizeof(float))); f.I0 = f.I0_own;
+    if (texels) CK(cudaMalloc(&f.base, texels*sizeof(float4)));
+    f.lvl[0] = nullptr; for (int l=1;l<levels;l++) f.lvl[l] = f.base + c->lvl_off[l];
+  }
+  { int nkf = s.max_kf_images > 0 ? s.max_kf_images : SDV_MAX_FRAMES_WINDOW + 4; if (nkf > s.max_frames) nkf = s.max_frames;
+    c->lvl0_pool.resize(nkf); for (int i=0;i<nkf;i++) { CK(cudaMalloc(&c->lvl0_pool[i], (size_t)w*h*sizeof(float4))); c->lvl0_free.push_back(nkf-1-i); } }
   // tracker slots
   c->slots.resize(s.n_tracker_slots);
   for (auto& t : c->slots) {
@@ -107,7 +114,8 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
 void sdv_destroy(sdv_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device); cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st);
-  for (auto& f : c->frames) cudaFree(f.base);
+  for (auto& f : c->frames) { cudaFree(f.base); cudaFree(f.I0_own); }
+  for (auto p : c->lvl0_pool) cudaFree(p);
   for (auto& t : c->slots) for (int l=0;l<c->levels;l++) cudaFree(t.pts[l]);
   for (int l=0;l<c->levels;l++) { cudaFree(c->cd_id[l]); cudaFree(c->cd_ws[l]); cudaFree(c->cd_id2[l]); cudaFree(c->cd_ws2[l]); }
   cudaFree(c->cd_owner); cudaFree(c->cd_counts); cudaFree(c->cd_scalars); cudaFreeHost(c->cd_scalars_host);
@@ -138,16 +146,21 @@ static int ensure_stage(sdv_ctx* c, int n) {
   return SDV_OK;
 }
 
-// kind: 0 host float, 1 host mono8, 2 device float, 3 device mono8.  Everything is enqueued on the ingest stream; the compute
-// stream picks it up through ev_in at the next tracker / BA call, so an upload overlaps the tracking of the previous batch.
+static void frame_drop_lvl0(sdv_ctx* c, FrameDev& f) { if (f.lvl0_slot >= 0) { c->lvl0_free.push_back(f.lvl0_slot); f.lvl0_slot = -1; } f.lvl[0] = nullptr; }
+
+// kind bit0: mono8 input, bit1: input already in device memory, bit2: adopt the (device, float) buffer as the frame's level-0 plane.
+// Everything is enqueued on the ingest stream; the compute stream picks it up through ev_in at the next tracker / BA call, so an
+// upload overlaps the tracking of the previous batch.  Level 0 stays a planar intensity image: a pinned-host float upload lands
+// directly in frame storage and only levels >= 1 are built (gradients of level 0 are formed on the fly by the consumers).
 static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs, const float* exposures, int kind) {
   if (!c || n < 0 || !frames || !imgs) return SDV_ERR_ARG;
   if (n == 0) return SDV_OK;
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st_in));            // previous ingest (descriptor + staging buffers are reused) must have drained
   int rc = ensure_stage(c, n); if (rc) return rc;
-  const bool u8 = (kind & 1), dev = (kind & 2);
+  const bool u8 = (kind & 1), dev = (kind & 2), adopt = (kind & 4) && dev && !u8;
   const size_t px = (size_t)c->w*c->h;
+  if (c->levels > 1 && ((c->w | c->h) & 1)) return ctx_fail(c, SDV_ERR_ARG, "pyramid needs even image sizes");
   for (int k=0;k<n;k++) {
     int idx = -1;
     auto it = c->frame_index.find(frames[k]);
@@ -155,22 +168,38 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
     else { for (size_t i=0;i<c->frames.size();i++) if (!c->frames[i].used) { idx = (int)i; break; } }
     if (idx < 0) return ctx_fail(c, SDV_ERR_CAPACITY, "frame pool exhausted (max_frames=%d)", (int)c->frames.size());
     FrameDev& f = c->frames[idx]; f.used = true; f.id = frames[k]; f.exposure = exposures ? exposures[k] : 1.0f; c->frame_index[frames[k]] = idx;
+    frame_drop_lvl0(c, f);
+    f.adopted = adopt; f.I0 = adopt ? const_cast<float*>(reinterpret_cast<const float*>(imgs[k])) : f.I0_own;
     PyrBatchHost& b = c->pyr_batch_host[k];
-    b.scratch = c->stage[k] + px; b.out = f.base;
+    b.scratch = c->stage[k] + px; b.out = f.base; b.I0 = f.I0;
     if (dev) b.src = imgs[k];
-    else { b.src = c->stage[k]; CK(cudaMemcpyAsync(c->stage[k], imgs[k], px*(u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, c->st_in)); }
+    else if (u8) { b.src = c->stage[k]; CK(cudaMemcpyAsync(c->stage[k], imgs[k], px, cudaMemcpyHostToDevice, c->st_in)); }
+    else { b.src = f.I0; CK(cudaMemcpyAsync(f.I0, imgs[k], px*sizeof(float), cudaMemcpyHostToDevice, c->st_in)); }
   }
   CK(cudaMemcpyAsync(c->pyr_batch_dev, c->pyr_batch_host, (size_t)n*sizeof(PyrBatchHost), cudaMemcpyHostToDevice, c->st_in));
-  launch_pyramid_batch(c->pyr_batch_dev, n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in);
+  if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev, n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in); c->launches += 2*(c->levels - 1); }
+  else if (u8 || (dev && !adopt)) { launch_pyramid_copy0(c->pyr_batch_dev, n, u8, c->w, c->h, c->st_in); c->launches += 1; }
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev_in, c->st_in)); c->ingest_pending = true;
-  c->launches += 2*c->levels - 1;
   return SDV_OK;
 }
-static int join_ingest(sdv_ctx* c) {              // make the compute stream see every upload enqueued so far
+}  // extern "C"
+namespace sdv {
+int join_ingest(sdv_ctx* c) {                     // make the compute stream see every upload enqueued so far
   if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
   return SDV_OK;
 }
+int ensure_lvl0(sdv_ctx* c, FrameDev& f) {        // FrameHessian::dI of a keyframe: packed level-0 texels, built once on demand
+  if (f.lvl[0]) return SDV_OK;
+  if (c->lvl0_free.empty()) return ctx_fail(c, SDV_ERR_CAPACITY, "keyframe level-0 image pool exhausted (max_kf_images=%d)", (int)c->lvl0_pool.size());
+  int rc = join_ingest(c); if (rc) return rc;
+  f.lvl0_slot = c->lvl0_free.back(); c->lvl0_free.pop_back(); f.lvl[0] = c->lvl0_pool[f.lvl0_slot];
+  launch_pyramid_level0_texels(f.I0, f.lvl[0], c->w, c->h, c->st); c->launches += 1;
+  CK(cudaGetLastError());
+  return SDV_OK;
+}
+}
+extern "C" {
 
 int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs, const float* exposures) {
   return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 0);
@@ -178,8 +207,9 @@ int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const floa
 int sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs, const float* exposures) {
   return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 1);
 }
-int sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int is_u8, const float* exposures) {
-  return frame_ingest(c, n, frames, imgs_dev, exposures, 2 | (is_u8 ? 1 : 0));
+int sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int fmt, const float* exposures) {
+  if (fmt < 0 || fmt > 2) return SDV_ERR_ARG;
+  return frame_ingest(c, n, frames, imgs_dev, exposures, 2 | (fmt == 1 ? 1 : 0) | (fmt == 2 ? 4 : 0));
 }
 int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposure) {
   const float* imgs[1] = {img}; return sdv_frame_upload_batch(c, 1, &frame, imgs, &exposure);
@@ -187,13 +217,14 @@ int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposur
 int sdv_frame_release(sdv_ctx* c, uint64_t frame) {
   if (!c) return SDV_ERR_ARG;
   auto it = c->frame_index.find(frame); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
-  c->frames[it->second].used = false; c->frame_index.erase(it); return SDV_OK;
+  FrameDev& f = c->frames[it->second]; f.used = false; frame_drop_lvl0(c, f); f.adopted = false; f.I0 = f.I0_own; c->frame_index.erase(it); return SDV_OK;
 }
 int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out) {
   if (!c || lvl < 0 || lvl >= c->levels) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   FrameDev* f = find_frame(c, frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
   { int rcj = join_ingest(c); if (rcj) return rcj; }
+  if (lvl == 0) { int rc0 = ensure_lvl0(c, *f); if (rc0) return rc0; }
   int n = (c->w>>lvl)*(c->h>>lvl); float *d3 = nullptr, *da = nullptr;
   if (dI3_out) CK(cudaMalloc(&d3, (size_t)3*n*sizeof(float)));
   if (abs_out) CK(cudaMalloc(&da, (size_t)n*sizeof(float)));
@@ -269,7 +300,7 @@ int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const f
   for (int l=1;l<c->levels;l++) launch_cd_pool(c->cd_id[l-1], c->cd_ws[l-1], c->cd_id[l], c->cd_ws[l], w>>l, h>>l, w>>(l-1), c->st);
   for (int l=0;l<c->levels;l++) {
     launch_cd_dilate(c->cd_id[l], c->cd_ws[l], c->cd_id2[l], c->cd_ws2[l], w>>l, h>>l, l < 2 ? 1 : 0, c->st);
-    launch_cd_compact(c->cd_id2[l], c->cd_ws2[l], f->lvl[l], w>>l, h>>l, c->cd_counts, c->cd_scalars + 1 + l, t.pts[l], c->st);
+    launch_cd_compact(c->cd_id2[l], c->cd_ws2[l], l == 0 ? nullptr : f->lvl[l], l == 0 ? f->I0 : nullptr, w>>l, h>>l, c->cd_counts, c->cd_scalars + 1 + l, t.pts[l], c->st);
   }
   CK(cudaMemcpyAsync(c->cd_scalars_host, c->cd_scalars, 8*sizeof(int), cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
@@ -293,7 +324,7 @@ int sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, cons
   { int rcj = join_ingest(c); if (rcj) return rcj; }
   CK(cudaEventRecord(c->ev0, c->st));
   c->launches += 1;
-  launch_coarse_res_gs(t.pts[lvl], t.npts[lvl], f->lvl[lvl], c->tc.geom[lvl], ep, c->partials, c->ticket, c->totals_dev, c->st);
+  launch_coarse_res_gs(t.pts[lvl], t.npts[lvl], lvl == 0 ? nullptr : f->lvl[lvl], lvl == 0 ? f->I0 : nullptr, c->tc.geom[lvl], ep, c->partials, c->ticket, c->totals_dev, c->st);
   CK(cudaEventRecord(c->ev1, c->st));
   CK(cudaMemcpyAsync(c->totals_host, c->totals_dev, kNAcc*sizeof(double), cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
@@ -325,7 +356,8 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
     FrameDev* f = find_frame(c, new_frames[k]); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown new frame (job %d)", k);
     if (t.ref_frame == ~0ull) return ctx_fail(c, SDV_ERR_STATE, "tracker slot %d has no reference", slots[k]);
     TrackJob& J = c->jobs_host[k]; memset(&J, 0, sizeof(J));
-    for (int l=0;l<c->levels;l++) { J.img[l] = f->lvl[l]; J.pts[l] = t.pts[l]; J.npts[l] = t.npts[l]; }
+    J.img0 = f->I0;
+    for (int l=0;l<c->levels;l++) { J.img[l] = (l == 0) ? nullptr : f->lvl[l]; J.pts[l] = t.pts[l]; J.npts[l] = t.npts[l]; }
     J.refExposure = t.refExposure; J.newExposure = f->exposure; J.ref_a = t.ref_a; J.ref_b = t.ref_b;
     for (int i=0;i<7;i++) J.T[i] = T_io[7*k+i];
     J.ab[0] = ab_io[2*k]; J.ab[1] = ab_io[2*k+1];

@@ -7,7 +7,12 @@
 
 namespace sdv {
 
-struct FrameDev { uint64_t id; float4* base; float4* lvl[kLevels]; float exposure; bool used; };
+struct FrameDev {                         // one FrameHessian's images on the device
+  uint64_t id; float exposure; bool used;
+  float* I0; float* I0_own; bool adopted;  // level-0 intensity plane (own storage, or an adopted caller buffer)
+  float4* base; float4* lvl[kLevels];     // packed {I,dx,dy,|grad|^2} texels of levels >= 1 (lvl[0] = lazily built level-0 texels or nullptr)
+  int lvl0_slot;                          // index into the keyframe level-0 texel pool, -1 if not built
+};
 
 struct TrackerSlot {                      // one CoarseTracker instance (reference keeps two: FullSystem.h coarseTracker / coarseTracker_forNewKF)
   float4* pts[kLevels]; int npts[kLevels]; int cap[kLevels];
@@ -26,6 +31,7 @@ struct sdv_ctx {
   size_t lvl_off[sdv::kLevels]; size_t frame_texels;
   std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
   std::vector<float*> stage; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev; sdv::PyrBatchHost* pyr_batch_host;
+  std::vector<float4*> lvl0_pool; std::vector<int> lvl0_free;
   std::vector<sdv::TrackerSlot> slots;
   double* partials; unsigned int* ticket; double* totals_dev; double* totals_host;
   float *cd_id[sdv::kLevels], *cd_ws[sdv::kLevels], *cd_id2[sdv::kLevels], *cd_ws2[sdv::kLevels];
@@ -40,4 +46,6 @@ struct sdv_ctx {
 namespace sdv {
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
 void ba_destroy(sdv_ctx* c);
+int  ensure_lvl0(sdv_ctx* c, FrameDev& f);     // build the packed level-0 texels of a frame on demand (keyframes / read-back)
+int  join_ingest(sdv_ctx* c);
 }

@@ -16,66 +16,83 @@ namespace sdv {
 // Batched over frames (blockIdx.y = frame of the batch): one launch per level for the whole batch.
 // gradient + pack of one level from a planar intensity image (HessianBlocks.cpp:147-165).  Flat-index neighbours on
 // purpose: at x=0 / x=w-1 the reference reads across the row boundary (idx±1), and so do we.
-struct PyrBatch { const void* src; float* scratch; float4* out; };   // per frame: level-0 input (float or u8), planar scratch, pyramid base
+struct PyrBatch { const void* src; float* I0; float* scratch; float4* out; };   // per frame: level-0 input (float/u8; may equal I0), level-0 plane, planar scratch, base of levels >= 1
 
 template <typename T> __device__ __forceinline__ float px_load(const T* p, int i);
 template <> __device__ __forceinline__ float px_load<float>(const float* p, int i) { return __ldg(p + i); }
 template <> __device__ __forceinline__ float px_load<unsigned char>(const unsigned char* p, int i) { return (float)__ldg(p + i); }
 
-template <typename T>
-__global__ void __launch_bounds__(256) pyr_grad_kernel(const PyrBatch* __restrict__ batch, int use_scratch, size_t scratch_off, size_t out_off, int w, int h) {
-  const PyrBatch b = batch[blockIdx.y];
-  const T* I = use_scratch ? reinterpret_cast<const T*>(b.scratch + scratch_off) : reinterpret_cast<const T*>(b.src);
-  float4* out = b.out + out_off;
-  const int n = w*h;
-  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
-    float c = px_load<T>(I, idx);
-    float dx = 0.f, dy = 0.f, ab = 0.f;
-    if (idx >= w && idx < w*(h-1)) {
-      dx = 0.5f*(px_load<T>(I, idx+1) - px_load<T>(I, idx-1));
-      dy = 0.5f*(px_load<T>(I, idx+w) - px_load<T>(I, idx-w));
-      if (!isfinite(dx)) dx = 0;
-      if (!isfinite(dy)) dy = 0;
-      ab = dx*dx + dy*dy;
-    }
-    out[idx] = make_float4(c, dx, dy, ab);
+__device__ __forceinline__ float4 grad_texel(const float* __restrict__ I, int idx, int w, int h) {
+  float c = __ldg(I + idx); float dx = 0.f, dy = 0.f, ab = 0.f;
+  if (idx >= w && idx < w*(h-1)) {
+    dx = 0.5f*(__ldg(I + idx+1) - __ldg(I + idx-1));
+    dy = 0.5f*(__ldg(I + idx+w) - __ldg(I + idx-w));
+    if (!isfinite(dx)) dx = 0;
+    if (!isfinite(dy)) dy = 0;
+    ab = dx*dx + dy*dy;
   }
+  return make_float4(c, dx, dy, ab);
 }
-// 2x2 box filter of intensities (HessianBlocks.cpp:137-145): 0.25f*(((a+b)+c)+d)
-template <typename T>
-__global__ void __launch_bounds__(256) pyr_down_kernel(const PyrBatch* __restrict__ batch, int src_is_scratch, size_t src_off, size_t dst_off, int wl, int hl, int wlm1) {
+// packed {I,dx,dy,|grad|^2} texels of one level >= 1 from its planar intensity in scratch
+__global__ void __launch_bounds__(256) pyr_grad_kernel(const PyrBatch* __restrict__ batch, size_t scratch_off, size_t out_off, int w, int h) {
   const PyrBatch b = batch[blockIdx.y];
-  const T* Iprev = src_is_scratch ? reinterpret_cast<const T*>(b.scratch + src_off) : reinterpret_cast<const T*>(b.src);
+  const float* I = b.scratch + scratch_off; float4* out = b.out + out_off; const int n = w*h;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) out[idx] = grad_texel(I, idx, w, h);
+}
+// level-0 packed texels on demand (keyframes entering the BA window, debugging read-back)
+__global__ void __launch_bounds__(256) pyr_grad0_kernel(const float* __restrict__ I, float4* __restrict__ out, int w, int h) {
+  const int n = w*h;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) out[idx] = grad_texel(I, idx, w, h);
+}
+// 2x2 box filter of intensities (HessianBlocks.cpp:137-145): 0.25f*(((a+b)+c)+d).  Level 1 reads the level-0 input (float or mono8) and,
+// when that input is not already the frame's own plane, also materialises the level-0 float plane in the same pass.
+template <typename T>
+__global__ void __launch_bounds__(256) pyr_down_kernel(const PyrBatch* __restrict__ batch, int from_src, size_t src_off, size_t dst_off, int wl, int hl, int wlm1) {
+  const PyrBatch b = batch[blockIdx.y];
+  const T* Iprev = from_src ? reinterpret_cast<const T*>(b.src) : reinterpret_cast<const T*>(b.scratch + src_off);
   float* I = b.scratch + dst_off;
+  float* I0 = (from_src && reinterpret_cast<const void*>(b.I0) != b.src) ? b.I0 : nullptr;
   const int n = wl*hl;
   for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
     int y = idx / wl, x = idx - y*wl;
     int bi = 2*x + 2*y*wlm1;
     float a0 = px_load<T>(Iprev, bi), a1 = px_load<T>(Iprev, bi+1), a2 = px_load<T>(Iprev, bi+wlm1), a3 = px_load<T>(Iprev, bi+wlm1+1);
     I[idx] = 0.25f * (((a0 + a1) + a2) + a3);
+    if (I0) { I0[bi] = a0; I0[bi+1] = a1; I0[bi+wlm1] = a2; I0[bi+wlm1+1] = a3; }
   }
 }
 
 size_t pyramid_scratch_floats(int w, int h, int levels) { size_t n = 0; for (int l = 1; l < levels; l++) n += (size_t)(w>>l)*(h>>l); return n + 4; }
 
 // batch_dev: nframes PyrBatch descriptors in device memory.  src_u8: level-0 input is mono8 (sensor_msgs/Image wire format) instead of float.
+// Requires even w,h whenever levels > 1 (pyrLevelsUsed only halves even sizes, globalCalib.cpp:24).
 void launch_pyramid_batch(const void* batch_dev_v, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st) {
   const PyrBatch* batch_dev = reinterpret_cast<const PyrBatch*>(batch_dev_v);
   if (nframes <= 0) return;
   size_t soff = 0, prev_soff = 0; int wl = w, hl = h;
-  for (int l = 0; l < levels; l++) {
-    int n = wl*hl; int gx = (n + 255)/256; int cap = (148*16 + nframes - 1)/nframes; if (cap < 4) cap = 4; if (gx > cap) gx = cap;
-    dim3 grid(gx, nframes);
-    if (l == 0 && src_u8) pyr_grad_kernel<unsigned char><<<grid, 256, 0, st>>>(batch_dev, 0, 0, lvl_off[0], wl, hl);
-    else pyr_grad_kernel<float><<<grid, 256, 0, st>>>(batch_dev, l > 0, prev_soff, lvl_off[l], wl, hl);
-    if (l+1 < levels) {
-      int wn = wl>>1, hn = hl>>1; int gn = (wn*hn + 255)/256; if (gn > cap) gn = cap;
-      dim3 g2(gn, nframes);
-      if (l == 0 && src_u8) pyr_down_kernel<unsigned char><<<g2, 256, 0, st>>>(batch_dev, 0, 0, soff, wn, hn, wl);
-      else pyr_down_kernel<float><<<g2, 256, 0, st>>>(batch_dev, l > 0, prev_soff, soff, wn, hn, wl);
-      prev_soff = soff; soff += (size_t)wn*hn; wl = wn; hl = hn;
-    }
+  int cap = (148*16 + nframes - 1)/nframes; if (cap < 4) cap = 4;
+  for (int l = 0; l + 1 < levels; l++) {
+    int wn = wl>>1, hn = hl>>1; int gn = (wn*hn + 255)/256; if (gn > cap) gn = cap;
+    dim3 g2(gn, nframes);
+    if (l == 0 && src_u8) pyr_down_kernel<unsigned char><<<g2, 256, 0, st>>>(batch_dev, 1, 0, soff, wn, hn, wl);
+    else pyr_down_kernel<float><<<g2, 256, 0, st>>>(batch_dev, l == 0, prev_soff, soff, wn, hn, wl);
+    pyr_grad_kernel<<<g2, 256, 0, st>>>(batch_dev, soff, lvl_off[l+1], wn, hn);
+    prev_soff = soff; soff += (size_t)wn*hn; wl = wn; hl = hn;
   }
+}
+// levels == 1 or odd sizes: the level-0 plane still has to be materialised from a foreign / mono8 source
+template <typename T> __global__ void pyr_copy0_kernel(const PyrBatch* __restrict__ batch, int n) {
+  const PyrBatch b = batch[blockIdx.y]; if (reinterpret_cast<const void*>(b.I0) == b.src) return;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) b.I0[idx] = px_load<T>(reinterpret_cast<const T*>(b.src), idx);
+}
+void launch_pyramid_copy0(const void* batch_dev_v, int nframes, bool src_u8, int w, int h, cudaStream_t st) {
+  const PyrBatch* batch_dev = reinterpret_cast<const PyrBatch*>(batch_dev_v); if (nframes <= 0) return;
+  dim3 g((w*h + 255)/256 > 1024 ? 1024 : (w*h + 255)/256, nframes);
+  if (src_u8) pyr_copy0_kernel<unsigned char><<<g, 256, 0, st>>>(batch_dev, w*h); else pyr_copy0_kernel<float><<<g, 256, 0, st>>>(batch_dev, w*h);
+}
+void launch_pyramid_level0_texels(const float* I0, float4* out, int w, int h, cudaStream_t st) {
+  int n = w*h; int grid = (n + 255)/256; if (grid > 148*16) grid = 148*16;
+  pyr_grad0_kernel<<<grid, 256, 0, st>>>(I0, out, w, h);
 }
 
 __global__ void unpack_level_kernel(const float4* __restrict__ in, float* dI3, float* ab, int n) {
@@ -113,7 +130,7 @@ __device__ __forceinline__ void block_reduce_acc(const float (&acc)[kNAcc], floa
 // grid-stride over the reference cloud; per-block partials -> global; the last block to finish (ticket) sums the block
 // partials in block order and writes the 51 totals.  One launch per calcRes.
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) coarse_res_gs_kernel(const float4* __restrict__ pts, int n, const float4* __restrict__ img,
+__global__ void __launch_bounds__(THREADS) coarse_res_gs_kernel(const float4* __restrict__ pts, int n, const float4* __restrict__ img, const float* __restrict__ I0,
                                                                LevelGeom g, EvalParams ep, double* __restrict__ partials,
                                                                unsigned int* __restrict__ ticket, double* __restrict__ totals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -123,7 +140,19 @@ __global__ void __launch_bounds__(THREADS) coarse_res_gs_kernel(const float4* __
   float acc[kNAcc];
 #pragma unroll
   for (int k = 0; k < kNAcc; k++) acc[k] = 0.f;
-  for (int i = blockIdx.x*THREADS + threadIdx.x; i < n; i += gridDim.x*THREADS) eval_point(__ldg(pts + i), i, g, ep, img, acc);
+  {
+    const int stride = gridDim.x*THREADS; int i = blockIdx.x*THREADS + threadIdx.x;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 pc = (i < n) ? __ldg(pts + i) : zero4;
+    float4 pn = (i + stride < n) ? __ldg(pts + i + stride) : zero4;
+    if (i < n) prefetch_taps(pc, g, ep, img);
+    for (; i < n; i += stride) {
+      const float4 pn2 = (i + 2*stride < n) ? __ldg(pts + i + 2*stride) : zero4;
+      if (i + stride < n) prefetch_taps(pn, g, ep, img);
+      eval_point(pc, i, g, ep, img, I0, acc);
+      pc = pn; pn = pn2;
+    }
+  }
   block_reduce_acc<THREADS>(acc, red, bsum);
   if (threadIdx.x < kNAcc) partials[(size_t)blockIdx.x*kNAcc + threadIdx.x] = bsum[threadIdx.x];
   __threadfence();
@@ -142,13 +171,13 @@ __global__ void __launch_bounds__(THREADS) coarse_res_gs_kernel(const float4* __
 
 constexpr int kStepThreads = 256;
 int step_kernel_max_grid() { return 148*4; }
-void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const LevelGeom& g, const EvalParams& ep,
+void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const float* I0, const LevelGeom& g, const EvalParams& ep,
                           double* partials, unsigned int* ticket, double* totals, cudaStream_t st) {
   static bool attr_set = false;
   size_t smem = (size_t)kNAcc*kStepThreads*sizeof(float);
   if (!attr_set) { cudaFuncSetAttribute(coarse_res_gs_kernel<kStepThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
   int grid = (n + kStepThreads - 1)/kStepThreads; if (grid < 1) grid = 1; if (grid > step_kernel_max_grid()) grid = step_kernel_max_grid();
-  coarse_res_gs_kernel<kStepThreads><<<grid, kStepThreads, smem, st>>>(pts, n, img, g, ep, partials, ticket, totals);
+  coarse_res_gs_kernel<kStepThreads><<<grid, kStepThreads, smem, st>>>(pts, n, img, I0, g, ep, partials, ticket, totals);
 }
 
 // ================================================================================================ device-resident LM
@@ -200,9 +229,22 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
     float acc[kNAcc];
 #pragma unroll
     for (int k = 0; k < kNAcc; k++) acc[k] = 0.f;
-    const float4* __restrict__ pts = J.pts[lvl]; const int n = J.npts[lvl]; const float4* __restrict__ img = J.img[lvl];
+    const float4* __restrict__ pts = J.pts[lvl]; const int n = J.npts[lvl];
+    const float4* __restrict__ img = (lvl == 0) ? nullptr : J.img[lvl]; const float* __restrict__ I0 = (lvl == 0) ? J.img0 : nullptr;
     const LevelGeom& g = tc.geom[lvl];
-    for (int i = rank*THREADS + tid; i < n; i += C*THREADS) eval_point(__ldg(pts + i), i, g, ctl.ep, img, acc);
+    {                                                      // 3-deep software pipeline: point k+2 in flight, taps of k+1 prefetched, k evaluated
+      const int stride = C*THREADS; int i = rank*THREADS + tid;
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 pc = (i < n) ? __ldg(pts + i) : zero4;
+      float4 pn = (i + stride < n) ? __ldg(pts + i + stride) : zero4;
+      if (i < n) prefetch_taps(pc, g, ctl.ep, img);
+      for (; i < n; i += stride) {
+        const float4 pn2 = (i + 2*stride < n) ? __ldg(pts + i + 2*stride) : zero4;
+        if (i + stride < n) prefetch_taps(pn, g, ctl.ep, img);
+        eval_point(pc, i, g, ctl.ep, img, I0, acc);
+        pc = pn; pn = pn2;
+      }
+    }
     block_reduce_acc<THREADS>(acc, red, bsum);
     if (C > 1) {
       const int buf = evalCount & 1;
@@ -434,17 +476,17 @@ __global__ void cd_dilate_kernel(const float* __restrict__ id_in, const float* _
 }
 // (d) normalise + raster-order compaction (:378-423): block counts -> exclusive scan -> scatter
 constexpr int kScanThreads = 256, kScanItems = 4;            // 1024 pixels per block, contiguous per thread
-__device__ __forceinline__ bool cd_valid(const float* id, const float* ws, const float4* ref, int i, int w, int h, float& idn, float& col) {
+__device__ __forceinline__ bool cd_valid(const float* id, const float* ws, const float4* ref, const float* ref0, int i, int w, int h, float& idn, float& col) {
   int y = i / w, x = i - y*w;
   if (x < 2 || x >= w-2 || y < 2 || y >= h-2) return false;
   if (!(ws[i] > 0)) return false;
-  idn = id[i] / ws[i]; col = ref[i].x;
+  idn = id[i] / ws[i]; col = ref0 ? ref0[i] : ref[i].x;
   return isfinite(col) && (idn > 0);
 }
-__global__ void __launch_bounds__(kScanThreads) cd_count_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, int w, int h, int* blockCounts) {
+__global__ void __launch_bounds__(kScanThreads) cd_count_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, const float* __restrict__ ref0, int w, int h, int* blockCounts) {
   __shared__ int s[kScanThreads/32];
   int base = (blockIdx.x*kScanThreads + threadIdx.x)*kScanItems; int c = 0, n = w*h;
-  for (int j = 0; j < kScanItems; j++) { int i = base + j; float a, b; if (i < n && cd_valid(id, ws, ref, i, w, h, a, b)) c++; }
+  for (int j = 0; j < kScanItems; j++) { int i = base + j; float a, b; if (i < n && cd_valid(id, ws, ref, ref0, i, w, h, a, b)) c++; }
   for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
   __syncthreads();
@@ -467,12 +509,12 @@ __global__ void cd_scan_kernel(int* blockCounts, int nblocks, int* total) {   //
   }
   if (threadIdx.x == 0) *total = carry;
 }
-__global__ void __launch_bounds__(kScanThreads) cd_emit_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, int w, int h,
+__global__ void __launch_bounds__(kScanThreads) cd_emit_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, const float* __restrict__ ref0, int w, int h,
                                                               const int* __restrict__ blockOffsets, float4* out) {
   __shared__ int s[kScanThreads/32];
   int base = (blockIdx.x*kScanThreads + threadIdx.x)*kScanItems; int n = w*h;
   float idn[kScanItems], col[kScanItems]; bool ok[kScanItems]; int c = 0;
-  for (int j = 0; j < kScanItems; j++) { int i = base + j; ok[j] = (i < n) && cd_valid(id, ws, ref, i, w, h, idn[j], col[j]); c += ok[j]; }
+  for (int j = 0; j < kScanItems; j++) { int i = base + j; ok[j] = (i < n) && cd_valid(id, ws, ref, ref0, i, w, h, idn[j], col[j]); c += ok[j]; }
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5; int incl = c;
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
   if (lane == 31) s[warp] = incl;
@@ -500,11 +542,11 @@ void launch_cd_pool(const float* id_lm, const float* ws_lm, float* id_l, float* 
 void launch_cd_dilate(const float* id_in, const float* bak, float* id_out, float* ws_out, int w, int h, int diag, cudaStream_t st) {
   cd_dilate_kernel<<<(w*h+255)/256, 256, 0, st>>>(id_in, bak, id_out, ws_out, w, h, diag);
 }
-void launch_cd_compact(const float* id, const float* ws, const float4* ref, int w, int h, int* blockCounts, int* total, float4* out, cudaStream_t st) {
+void launch_cd_compact(const float* id, const float* ws, const float4* ref, const float* ref0, int w, int h, int* blockCounts, int* total, float4* out, cudaStream_t st) {
   int nb = cd_num_blocks(w, h);
-  cd_count_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, w, h, blockCounts);
+  cd_count_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, ref0, w, h, blockCounts);
   cd_scan_kernel<<<1, 1024, 0, st>>>(blockCounts, nb, total);
-  cd_emit_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, w, h, blockCounts, out);
+  cd_emit_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, ref0, w, h, blockCounts, out);
 }
 
 __global__ void pack_cloud_kernel(const float* u, const float* v, const float* id, const float* col, int n, float4* out) {
