@@ -156,6 +156,11 @@ int  sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak_out);
 /* float FullSystem::optimize(int mnumOptIts)  FullSystemOptimize.cpp:344-502 — the whole GN loop incl. the final re-anchoring and
  * linearizeAll(true).  Returns sqrt(lastEnergy / resInA) like the reference. */
 int  sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out);
+/* Batched mode: a context holds any number of independent windows (one per resident sequence).  sdv_ba_select picks the window the
+ * set_ / get_ / step-wise calls address (default 0); sdv_ba_optimize_batch runs FullSystem::optimize on n windows at once — every
+ * kernel is launched once for all windows and the accept/reject/break decisions are taken on the device. */
+int  sdv_ba_select(sdv_ctx* c, int window);
+int  sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out);
 /* read-back of what the reference leaves in FrameHessian/CalibHessian, PointHessian/EFPoint, PointFrameResidual/EFResidual, EnergyFunctional */
 int  sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* step10, float* frameEnergyTH, double* PRE_worldToCam7,
                        double calib_value[4], double calib_step[4]);

@@ -234,6 +234,8 @@ def _ba_protos():
     L.sdv_ba_solve.argtypes = [_vp, C.c_int, C.c_double, _f64p]
     L.sdv_ba_step.argtypes = [_vp, C.c_float, C.c_int, C.POINTER(C.c_int)]
     L.sdv_ba_optimize.argtypes = [_vp, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.sdv_ba_select.argtypes = [_vp, C.c_int]
+    L.sdv_ba_optimize_batch.argtypes = [_vp, C.c_int, _i32p, C.c_int, _f32p, _i32p, _i32p]
     L.sdv_ba_get_frames.argtypes = [_vp, _f64p, _f64p, _f64p, _f32p, _f64p, _f64p, _f64p]
     L.sdv_ba_get_points.argtypes = [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p]
     L.sdv_ba_get_residuals.argtypes = [_vp, _i32p, _i32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p]
@@ -246,8 +248,9 @@ class EnergyFunctional:
     """Mirror of the reference back-end surface (OptimizationBackend/EnergyFunctional.h:51-72 + FullSystem::optimize/linearizeAll)
     over a flattened window dict (see sdv_b200.h; synth.make_ba_window builds one).  frame_ids[i] = device frame handle of KF i."""
 
-    def __init__(self, ctx: Context, win: dict, frame_ids):
-        _ba_protos(); self.ctx = ctx; self.win = win
+    def __init__(self, ctx: Context, win: dict, frame_ids, window: int = 0):
+        _ba_protos(); self.ctx = ctx; self.win = win; self.window = window
+        ctx._ck(LIB.sdv_ba_select(ctx.p, window))
         self.nF = win["nF"]; self.nP = len(win["uv"]); self.nR = len(win["r_point"]); self.n = 4 + 6 * self.nF
         c = lambda k, t: np.ascontiguousarray(win[k], t)
         ctx._ck(LIB.sdv_ba_set_window(ctx.p, self.nF, np.ascontiguousarray(frame_ids, np.uint64), c("T_eval", np.float64), c("state", np.float64),
@@ -258,33 +261,34 @@ class EnergyFunctional:
                                       self.nR, c("r_point", np.int32), c("r_host", np.int32), c("r_target", np.int32), c("r_hasMatcher", np.int32),
                                       c("r_matcher", np.float32), c("r_isNew", np.int32)))
 
-    def reset_oob(self): self.ctx._ck(LIB.sdv_ba_reset_oob(self.ctx.p))
+    def _sel(self): self.ctx._ck(LIB.sdv_ba_select(self.ctx.p, self.window))
+    def reset_oob(self): self._sel(); self.ctx._ck(LIB.sdv_ba_reset_oob(self.ctx.p))
     def linearizeAll(self, fix=False):
-        e = C.c_double(0); self.ctx._ck(LIB.sdv_ba_linearize(self.ctx.p, 1 if fix else 0, C.byref(e))); return e.value
-    def applyRes(self): self.ctx._ck(LIB.sdv_ba_apply_res(self.ctx.p))
+        self._sel(); e = C.c_double(0); self.ctx._ck(LIB.sdv_ba_linearize(self.ctx.p, 1 if fix else 0, C.byref(e))); return e.value
+    def applyRes(self): self._sel(); self.ctx._ck(LIB.sdv_ba_apply_res(self.ctx.p))
     def energies(self):
-        a, b = C.c_double(0), C.c_double(0); self.ctx._ck(LIB.sdv_ba_energy(self.ctx.p, C.byref(a), C.byref(b))); return a.value, b.value
+        self._sel(); a, b = C.c_double(0), C.c_double(0); self.ctx._ck(LIB.sdv_ba_energy(self.ctx.p, C.byref(a), C.byref(b))); return a.value, b.value
     def calcLEnergy(self): return self.energies()[0]
     def calcMEnergy(self): return self.energies()[1]
-    def backupState(self): self.ctx._ck(LIB.sdv_ba_backup(self.ctx.p))
+    def backupState(self): self._sel(); self.ctx._ck(LIB.sdv_ba_backup(self.ctx.p))
     def doStepFromBackup(self, f=1.0):
-        cb = C.c_int(0); self.ctx._ck(LIB.sdv_ba_step(self.ctx.p, f, 0, C.byref(cb))); return bool(cb.value)
+        self._sel(); cb = C.c_int(0); self.ctx._ck(LIB.sdv_ba_step(self.ctx.p, f, 0, C.byref(cb))); return bool(cb.value)
     def loadStateBackup(self):
-        cb = C.c_int(0); self.ctx._ck(LIB.sdv_ba_step(self.ctx.p, 1.0, 1, C.byref(cb)))
+        self._sel(); cb = C.c_int(0); self.ctx._ck(LIB.sdv_ba_step(self.ctx.p, 1.0, 1, C.byref(cb)))
 
     def solveSystem(self, iteration, lam):
-        n = self.n; x = np.zeros(n); self.ctx._ck(LIB.sdv_ba_solve(self.ctx.p, iteration, lam, x))
+        self._sel(); n = self.n; x = np.zeros(n); self.ctx._ck(LIB.sdv_ba_solve(self.ctx.p, iteration, lam, x))
         HA = np.zeros((n, n)); bA = np.zeros(n); Hsc = np.zeros((n, n)); bsc = np.zeros(n); HS = np.zeros((n, n)); bS = np.zeros(n)
         self.ctx._ck(LIB.sdv_ba_get_system(self.ctx.p, HA, bA, Hsc, bsc, HS, bS))
         return x, HS, bS, (HA, bA, Hsc, bsc)
 
     def optimize(self, its=6):
-        r = C.c_float(0); i = C.c_int32(0); a = C.c_int32(0)
+        self._sel(); r = C.c_float(0); i = C.c_int32(0); a = C.c_int32(0)
         self.ctx._ck(LIB.sdv_ba_optimize(self.ctx.p, its, C.byref(r), C.byref(i), C.byref(a)))
         return dict(rmse=float(r.value), iterations=int(i.value), accepts=int(a.value), ms=self.ctx.last_kernel_ms())
 
     def residuals(self):
-        n = self.nR
+        self._sel(); n = self.nR
         o = dict(state=np.zeros(n, np.int32), new_state=np.zeros(n, np.int32), energies=np.zeros((n, 3), np.float32), active=np.zeros(n, np.int32),
                  J=np.zeros((n, 24), np.float32), efJ=np.zeros((n, 24), np.float32), JpJdF=np.zeros((n, 8), np.float32),
                  center=np.zeros((n, 3), np.float32), toRemove=np.zeros(n, np.int32))
@@ -292,18 +296,26 @@ class EnergyFunctional:
         return o
 
     def points(self):
-        n = self.nP
+        self._sel(); n = self.nP
         o = dict(idepth=np.zeros(n, np.float32), step=np.zeros(n, np.float32), HdiF=np.zeros(n, np.float32), bdSumF=np.zeros(n, np.float32),
                  maxRelBaseline=np.zeros(n, np.float32), numGood=np.zeros(n, np.int32), idepth_hessian=np.zeros(n, np.float32))
         self.ctx._ck(LIB.sdv_ba_get_points(self.ctx.p, o["idepth"], o["step"], o["HdiF"], o["bdSumF"], o["maxRelBaseline"], o["numGood"], o["idepth_hessian"])); return o
 
     def frames(self):
-        n = self.nF
+        self._sel(); n = self.nF
         o = dict(T_eval=np.zeros((n, 7)), state=np.zeros((n, 10)), step=np.zeros((n, 10)), frameEnergyTH=np.zeros(n, np.float32), PRE_worldToCam=np.zeros((n, 7)),
                  calib_value=np.zeros(4), calib_step=np.zeros(4))
         self.ctx._ck(LIB.sdv_ba_get_frames(self.ctx.p, o["T_eval"], o["state"], o["step"], o["frameEnergyTH"], o["PRE_worldToCam"], o["calib_value"], o["calib_step"])); return o
 
     def precalc(self, host, target):
-        o = np.zeros(27, np.float32); aH = np.zeros(36); aT = np.zeros(36); d = np.zeros(6, np.float32)
+        self._sel(); o = np.zeros(27, np.float32); aH = np.zeros(36); aT = np.zeros(36); d = np.zeros(6, np.float32)
         self.ctx._ck(LIB.sdv_ba_get_precalc(self.ctx.p, host, target, o, aH, aT, d))
         return dict(KRKi=o[:9].reshape(3, 3), Kt=o[9:12], R0=o[12:21].reshape(3, 3), t0=o[21:24], aff=o[24:26], b0=o[26], adHost=aH.reshape(6, 6), adTarget=aT.reshape(6, 6), adHTdelta=d)
+
+
+def optimize_batch(ctx: Context, windows, its: int = 6):
+    """FullSystem::optimize on several windows of one context in one device-resident schedule."""
+    _ba_protos(); w = np.ascontiguousarray(windows, np.int32); n = len(w)
+    rmse = np.zeros(n, np.float32); it = np.zeros(n, np.int32); acc = np.zeros(n, np.int32)
+    ctx._ck(LIB.sdv_ba_optimize_batch(ctx.p, n, w, its, rmse, it, acc))
+    return dict(rmse=rmse, iterations=it, accepts=acc, ms=ctx.last_kernel_ms())

@@ -14,20 +14,27 @@ using namespace sdv;
 
 namespace sdv {
 void ba_destroy(sdv_ctx* c) {
-  if (!c || !c->ba) return;
-  BAState* b = c->ba;
-  cudaFree(b->hdr); cudaFreeHost(b->hdr_host); cudaFree(b->pool); cudaFree(b->partials); cudaFree(b->thbuf); cudaFree(b->thcount);
-  delete b; c->ba = nullptr;
+  if (!c) return;
+  for (BAState* b : c->ba_windows) { if (!b) continue;
+    cudaFree(b->hdr); cudaFreeHost(b->hdr_host); cudaFree(b->pool); cudaFree(b->partials); cudaFree(b->thbuf); cudaFree(b->thcount); delete b; }
+  c->ba_windows.clear(); c->ba = nullptr;
+  cudaFree(c->ba_wins_dev); cudaFreeHost(c->ba_wins_host); c->ba_wins_dev = c->ba_wins_host = nullptr;
 }
 }
 
-static int ba_get(sdv_ctx* c, BAState** out) {
-  if (!c->ba) {
-    BAState* b = new BAState(); memset(b, 0, sizeof(*b)); c->ba = b;
+static int ba_select(sdv_ctx* c, int window) {
+  if (window < 0 || window > 1<<20) return SDV_ERR_ARG;
+  if ((int)c->ba_windows.size() <= window) c->ba_windows.resize(window+1, nullptr);
+  if (!c->ba_windows[window]) {
+    BAState* b = new BAState(); memset(b, 0, sizeof(*b)); c->ba_windows[window] = b;
     CK(cudaMalloc(&b->hdr, sizeof(BAHeader))); CK(cudaMemset(b->hdr, 0, sizeof(BAHeader)));
     CK(cudaMallocHost(&b->hdr_host, sizeof(BAHeader))); memset(b->hdr_host, 0, sizeof(BAHeader));
     CK(cudaMalloc(&b->thcount, sizeof(int))); CK(cudaMemset(b->thcount, 0, sizeof(int)));
   }
+  c->ba = c->ba_windows[window]; return SDV_OK;
+}
+static int ba_get(sdv_ctx* c, BAState** out) {
+  if (!c->ba) { int rc = ba_select(c, 0); if (rc) return rc; }
   *out = c->ba; return SDV_OK;
 }
 
@@ -63,7 +70,21 @@ static int ba_alloc(sdv_ctx* c, BAState* b, int nP, int nR, int nF) {
   return SDV_OK;
 }
 
-static int ba_pull_scalars(sdv_ctx* c, BAState* b) {                        // energyP .. ticket
+static BAWinDev win_of(const BAState* b) { BAWinDev w; w.hdr = b->hdr; w.P = b->P; w.R = b->R; w.partials = b->partials; w.thbuf = b->thbuf; w.thcount = b->thcount; return w; }
+// device array of window descriptors for one (batched) launch sequence; maxP/maxR size the grids
+static int ba_wins(sdv_ctx* c, int n, BAState* const* bs, const BAWinDev** out, int* maxP, int* maxR) {
+  if (n > c->ba_wins_cap) { cudaFree(c->ba_wins_dev); cudaFreeHost(c->ba_wins_host); c->ba_wins_cap = n + 16;
+    CK(cudaMalloc(&c->ba_wins_dev, (size_t)c->ba_wins_cap*sizeof(BAWinDev))); CK(cudaMallocHost(&c->ba_wins_host, (size_t)c->ba_wins_cap*sizeof(BAWinDev))); }
+  BAWinDev* h = (BAWinDev*)c->ba_wins_host; int mp = 1, mr = 1;
+  CK(cudaStreamSynchronize(c->st));                                          // the pinned staging array may still feed a previous launch sequence
+  for (int i=0;i<n;i++) { h[i] = win_of(bs[i]); if (bs[i]->nP > mp) mp = bs[i]->nP; if (bs[i]->nR > mr) mr = bs[i]->nR; }
+  CK(cudaMemcpyAsync(c->ba_wins_dev, h, (size_t)n*sizeof(BAWinDev), cudaMemcpyHostToDevice, c->st));
+  *out = (const BAWinDev*)c->ba_wins_dev; if (maxP) *maxP = mp; if (maxR) *maxR = mr;
+  return SDV_OK;
+}
+#define WIN1() const BAWinDev* wins; int maxP, maxR; { int rcw = ba_wins(c, 1, &b, &wins, &maxP, &maxR); if (rcw) return rcw; }
+
+static int ba_pull_scalars(sdv_ctx* c, BAState* b) {                        // energyP .. end of header
   const size_t off = offsetof(BAHeader, energyP), len = sizeof(BAHeader) - off;
   CK(cudaMemcpyAsync((char*)b->hdr_host + off, (char*)b->hdr + off, len, cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
@@ -150,97 +171,110 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
   b->hdr_host->nP = nP; b->hdr_host->nR = nR;
   CK(cudaMemcpyAsync(&b->hdr->nP, &b->hdr_host->nP, 2*sizeof(int), cudaMemcpyHostToDevice, st));
   if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
-  launch_ba_setup(b->hdr, P, nP, st);
-  launch_ba_reset_oob(R, nR, st);
+  { WIN1(); launch_ba_setup(wins, 1, maxP, st); launch_ba_reset_oob(wins, 1, maxR, st); }
   CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   c->launches += 3;
   return SDV_OK;
 }
 
-int sdv_ba_reset_oob(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); launch_ba_reset_oob(c->ba->R, c->ba->nR, c->st); c->launches++; return SDV_OK; }
+int sdv_ba_select(sdv_ctx* c, int window) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); return ba_select(c, window); }
+
+int sdv_ba_reset_oob(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_reset_oob(wins, 1, maxR, c->st); c->launches++; return SDV_OK; }
 
 int sdv_ba_linearize(sdv_ctx* c, int fix, double* energy) {
-  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  launch_ba_linearize(b->hdr, b->P, b->R, b->nR, fix, b->partials, b->thbuf, b->thcount, c->st); c->launches += 2;
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
+  launch_ba_linearize(wins, 1, maxR, fix, GATE_ALWAYS, c->st); c->launches += 2;
   int rc = ba_pull_scalars(c, b); if (rc) return rc;
   if (energy) *energy = b->hdr_host->energyP;
   return SDV_OK;
 }
-int sdv_ba_apply_res(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); launch_ba_apply(c->ba->R, c->ba->nR, c->st); c->launches++; CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
+int sdv_ba_apply_res(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_apply(wins, 1, maxR, GATE_ALWAYS, c->st); c->launches++; CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
 int sdv_ba_energy(sdv_ctx* c, double* EL, double* EM) {
-  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  launch_ba_energies(b->hdr, b->P, b->nP, c->st); c->launches++;
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
+  launch_ba_energies(wins, 1, GATE_ALWAYS, c->st); c->launches++;
   int rc = ba_pull_scalars(c, b); if (rc) return rc;
   if (EL) *EL = b->hdr_host->energyL; if (EM) *EM = b->hdr_host->energyM;
   return SDV_OK;
 }
 int sdv_ba_solve(sdv_ctx* c, int iteration, double lambda, double* x_out) {
-  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  launch_ba_accumulate(b->hdr, b->P, b->R, b->nF, b->nP, c->st);
-  launch_ba_solve(b->hdr, b->P, b->R, b->nP, iteration, lambda, c->st); c->launches += 5;
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
+  launch_ba_accumulate(wins, 1, maxP, GATE_ALWAYS, c->st);
+  launch_ba_solve(wins, 1, maxP, iteration, lambda, 0, GATE_ALWAYS, c->st); c->launches += 5;
   if (x_out) { CK(cudaMemcpyAsync(x_out, b->hdr->lastX, (size_t)(kCP+6*b->nF)*sizeof(double), cudaMemcpyDeviceToHost, c->st)); }
   CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
   return SDV_OK;
 }
-int sdv_ba_backup(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); launch_ba_backup(c->ba->hdr, c->ba->P, c->ba->nP, c->st); c->launches++; return SDV_OK; }
+int sdv_ba_backup(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_backup(wins, 1, maxP, GATE_ALWAYS, c->st); c->launches++; return SDV_OK; }
 int sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak) {
-  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  launch_ba_step(b->hdr, b->P, b->nP, stepfac, load_backup, c->st); c->launches += 2;
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
+  launch_ba_step(wins, 1, stepfac, load_backup, GATE_ALWAYS, c->st); c->launches += 2;
   int rc = ba_pull_scalars(c, b); if (rc) return rc;
   if (canbreak) *canbreak = b->hdr_host->canbreak;
   return SDV_OK;
 }
 
-/* float FullSystem::optimize(int mnumOptIts)   FullSystemOptimize.cpp:344-502 */
-int sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) {
-  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; cudaStream_t st = c->st; int rc;
-  const int nF = b->nF;
-  if (nF < 2) { if (rmse_out) *rmse_out = 0; return SDV_OK; }
-  if (nF < 3) mnumOptIts = 100;
-  if (nF < 4) mnumOptIts = 75;
-  CK(cudaEventRecord(c->ev0, st));
-  b->opt_iterations = b->opt_accepts = 0;
-  launch_ba_reset_oob(b->R, b->nR, st);
-  launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 0, b->partials, b->thbuf, b->thcount, st);
-  launch_ba_energies(b->hdr, b->P, b->nP, st); c->launches += 4;
-  if ((rc = ba_pull_scalars(c, b))) return rc;
-  double lastEnergy = b->hdr_host->energyP, lastEnergyL = b->hdr_host->energyL, lastEnergyM = b->hdr_host->energyM;
-  launch_ba_apply(b->R, b->nR, st); c->launches++;
-  double lambda = 1e-1;
-  for (int iteration = 0; iteration < mnumOptIts; iteration++) {
-    b->opt_iterations++;
-    launch_ba_backup(b->hdr, b->P, b->nP, st);
-    launch_ba_accumulate(b->hdr, b->P, b->R, nF, b->nP, st);
-    launch_ba_solve(b->hdr, b->P, b->R, b->nP, iteration, lambda, st);
-    launch_ba_step(b->hdr, b->P, b->nP, 1.0f, 0, st);
-    launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 0, b->partials, b->thbuf, b->thcount, st);
-    launch_ba_energies(b->hdr, b->P, b->nP, st); c->launches += 11;
-    if ((rc = ba_pull_scalars(c, b))) return rc;
-    const bool canbreak = b->hdr_host->canbreak != 0;
-    const double newEnergy = b->hdr_host->energyP, newEnergyL = b->hdr_host->energyL, newEnergyM = b->hdr_host->energyM;
-    if (newEnergy + 0 + newEnergyL + newEnergyM < lastEnergy + 0 + lastEnergyL + lastEnergyM) {
-      b->opt_accepts++;
-      launch_ba_apply(b->R, b->nR, st); c->launches++;
-      lastEnergy = newEnergy; lastEnergyL = newEnergyL; lastEnergyM = newEnergyM; lambda *= 0.25;
-    } else {
-      launch_ba_step(b->hdr, b->P, b->nP, 1.0f, 1, st);                      // loadSateBackup
-      launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 0, b->partials, b->thbuf, b->thcount, st);
-      launch_ba_energies(b->hdr, b->P, b->nP, st); c->launches += 5;
-      if ((rc = ba_pull_scalars(c, b))) return rc;
-      lastEnergy = b->hdr_host->energyP; lastEnergyL = b->hdr_host->energyL; lastEnergyM = b->hdr_host->energyM;
-      lambda *= 1e2;
-    }
-    if (canbreak && iteration >= 1) break;                                   // setting_minOptIterations = 1
+/* float FullSystem::optimize(int mnumOptIts)   FullSystemOptimize.cpp:344-502, for n windows at once.
+ * The Gauss-Newton loop is DEVICE-RESIDENT: every kernel is launched for all windows (grid.y = window) on a fixed schedule and
+ * gated by per-window flags that ba_decide_kernel sets (accept -> APPLY, reject -> RELOAD, converged -> not ACTIVE); the host
+ * never reads a decision back.  One D2H of the per-window tail at the end. */
+int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) {
+  if (!c || n < 1 || !windows) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device)); cudaStream_t st = c->st;
+  std::vector<BAState*> bs(n); int maxIts = 0;
+  for (int i=0;i<n;i++) {
+    if (windows[i] < 0 || windows[i] >= (int)c->ba_windows.size() || !c->ba_windows[windows[i]]) return ctx_fail(c, SDV_ERR_ARG, "BA window %d not set", windows[i]);
+    bs[i] = c->ba_windows[windows[i]];
+    int m = mnumOptIts; if (bs[i]->nF < 3) m = 100; if (bs[i]->nF < 4) m = 75; if (bs[i]->nF < 2) m = 0; if (m > maxIts) maxIts = m;
+    bs[i]->hdr_host->mnumOptIts = mnumOptIts;
+    CK(cudaMemcpyAsync(&bs[i]->hdr->mnumOptIts, &bs[i]->hdr_host->mnumOptIts, sizeof(int), cudaMemcpyHostToDevice, st));
   }
-  launch_ba_reanchor(b->hdr, b->P, b->nP, st);
-  launch_ba_linearize(b->hdr, b->P, b->R, b->nR, 1, b->partials, b->thbuf, b->thcount, st); c->launches += 4;
+  const BAWinDev* wins; int maxP, maxR; { int rcw = ba_wins(c, n, bs.data(), &wins, &maxP, &maxR); if (rcw) return rcw; }
+  if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
+  CK(cudaEventRecord(c->ev0, st));
+  launch_ba_reset_oob(wins, n, maxR, st);
+  launch_ba_linearize(wins, n, maxR, 0, GATE_ALWAYS, st);
+  launch_ba_energies(wins, n, GATE_ALWAYS, st);
+  launch_ba_decide(wins, n, 0, st);
+  launch_ba_apply(wins, n, maxR, GATE_ALWAYS, st); c->launches += 6;
+  for (int iteration = 0; iteration < maxIts; iteration++) {
+    launch_ba_backup(wins, n, maxP, GATE_ACTIVE, st);
+    launch_ba_accumulate(wins, n, maxP, GATE_ACTIVE, st);
+    launch_ba_solve(wins, n, maxP, 0, 0.0, 1, GATE_ACTIVE, st);
+    launch_ba_step(wins, n, 1.0f, 0, GATE_ACTIVE, st);
+    launch_ba_linearize(wins, n, maxR, 0, GATE_ACTIVE, st);
+    launch_ba_energies(wins, n, GATE_ACTIVE, st);
+    launch_ba_decide(wins, n, 1, st);
+    launch_ba_apply(wins, n, maxR, GATE_ACTIVE | GATE_APPLY, st);
+    launch_ba_step(wins, n, 1.0f, 1, GATE_ACTIVE | GATE_RELOAD, st);          // loadSateBackup
+    launch_ba_linearize(wins, n, maxR, 0, GATE_ACTIVE | GATE_RELOAD, st);
+    launch_ba_energies(wins, n, GATE_ACTIVE | GATE_RELOAD, st);
+    launch_ba_decide(wins, n, 2, st); c->launches += 19;
+    if (maxIts > 8 && iteration >= 5 && (iteration % 4) == 1) {              // long schedules (tiny windows at start-up): poll for early exit
+      bool any = false;
+      for (int i=0;i<n;i++) { CK(cudaMemcpyAsync(&bs[i]->hdr_host->flags, &bs[i]->hdr->flags, sizeof(int), cudaMemcpyDeviceToHost, st)); }
+      CK(cudaStreamSynchronize(st));
+      for (int i=0;i<n;i++) any = any || (bs[i]->hdr_host->flags & BA_ACTIVE);
+      if (!any) break;
+    }
+  }
+  launch_ba_reanchor(wins, n, maxP, st);
+  launch_ba_linearize(wins, n, maxR, 1, GATE_ALWAYS, st);
+  launch_ba_decide(wins, n, 3, st); c->launches += 5;
   CK(cudaEventRecord(c->ev1, st));
-  if ((rc = ba_pull_scalars(c, b))) return rc;
+  for (int i=0;i<n;i++) { const size_t off = offsetof(BAHeader, energyP), len = sizeof(BAHeader) - off;
+    CK(cudaMemcpyAsync((char*)bs[i]->hdr_host + off, (char*)bs[i]->hdr + off, len, cudaMemcpyDeviceToHost, st)); }
+  CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-  if (rmse_out) *rmse_out = sqrtf((float)(b->hdr_host->energyP / b->hdr_host->resInA));
-  if (iterations_out) *iterations_out = b->opt_iterations;
-  if (accepts_out) *accepts_out = b->opt_accepts;
+  for (int i=0;i<n;i++) { const BAHeader* H = bs[i]->hdr_host;
+    if (rmse_out) rmse_out[i] = (bs[i]->nF < 2) ? 0.f : H->rmse;
+    if (iterations_out) iterations_out[i] = H->opt_iterations;
+    if (accepts_out) accepts_out[i] = H->opt_accepts; }
   return SDV_OK;
+}
+int sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) {
+  if (!c || !c->ba) return SDV_ERR_ARG;
+  int32_t w = -1; for (size_t i=0;i<c->ba_windows.size();i++) if (c->ba_windows[i] == c->ba) w = (int32_t)i;
+  return sdv_ba_optimize_batch(c, 1, &w, mnumOptIts, rmse_out, iterations_out, accepts_out);
 }
 
 // ---- read-back (what the reference leaves in FrameHessian / PointHessian / PointFrameResidual / EnergyFunctional)

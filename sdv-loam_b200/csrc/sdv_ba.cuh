@@ -51,7 +51,14 @@ struct BAHeader {                        // one per window, lives in device memo
   // scalars
   double energyP, energyL, energyM; int resInA; int canbreak; float sums[8];
   unsigned int ticket;
+  // device-resident Gauss-Newton control (FullSystem::optimize, FullSystemOptimize.cpp:391-458): set by ba_decide_kernel
+  int flags;                             // BA_ACTIVE | BA_APPLY | BA_RELOAD
+  int mnumOptIts, iteration, opt_iterations, opt_accepts;
+  double lambda, lastEnergy, lastEnergyL, lastEnergyM;
+  float rmse;
 };
+enum { BA_ACTIVE = 1, BA_APPLY = 2, BA_RELOAD = 4 };
+enum { GATE_ALWAYS = 0, GATE_ACTIVE = 1, GATE_APPLY = 2, GATE_RELOAD = 4 };
 
 struct BAPointsDev {                     // SoA over points
   float2* uv; float* idepth; float* idepth_zero; float* idepth_backup; float* step;
@@ -72,6 +79,10 @@ struct BAResDev {                        // SoA over residuals
   int* host_begin;                       // point range per host frame [nF+1]
 };
 
+struct BAWinDev {                        // one window as the batched kernels see it (blockIdx.y selects the window)
+  BAHeader* hdr; BAPointsDev P; BAResDev R; double* partials; float* thbuf; int* thcount;
+};
+
 struct BAState {
   BAHeader* hdr; BAHeader* hdr_host;     // device / pinned host mirror
   BAPointsDev P; BAResDev R; int capP, capR; int nF, nP, nR;
@@ -81,17 +92,17 @@ struct BAState {
   float last_ms;
 };
 
-// launchers (sdv_ba_kernels.cu)
-void launch_ba_setup(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st);                 // setState/Zero, takeData, adjoints, precalc, deltas
-void launch_ba_adjoints_precalc(BAHeader* hdr, BAPointsDev P, int nP, bool adjoints, cudaStream_t st);
-void launch_ba_reset_oob(BAResDev R, int nR, cudaStream_t st);
-void launch_ba_linearize(BAHeader* hdr, BAPointsDev P, BAResDev R, int nR, int fix, double* partials, float* thbuf, int* thcount, cudaStream_t st);
-void launch_ba_apply(BAResDev R, int nR, cudaStream_t st);
-void launch_ba_energies(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st);
-void launch_ba_accumulate(BAHeader* hdr, BAPointsDev P, BAResDev R, int nF, int nP, cudaStream_t st);
-void launch_ba_solve(BAHeader* hdr, BAPointsDev P, BAResDev R, int nP, int iteration, double lambda, cudaStream_t st);
-void launch_ba_backup(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st);
-void launch_ba_step(BAHeader* hdr, BAPointsDev P, int nP, float stepfac, int load_backup, cudaStream_t st);
-void launch_ba_reanchor(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st);
+// launchers (sdv_ba_kernels.cu): every kernel is batched over windows (grid.y = window); `gate` = flags the window must have set
+void launch_ba_setup(const BAWinDev* wins, int W, int maxP, cudaStream_t st);                 // setState/Zero, takeData, adjoints, precalc, deltas
+void launch_ba_reset_oob(const BAWinDev* wins, int W, int maxR, cudaStream_t st);
+void launch_ba_linearize(const BAWinDev* wins, int W, int maxR, int fix, int gate, cudaStream_t st);
+void launch_ba_apply(const BAWinDev* wins, int W, int maxR, int gate, cudaStream_t st);
+void launch_ba_energies(const BAWinDev* wins, int W, int gate, cudaStream_t st);
+void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st);
+void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, double lambda, int use_hdr_ctl, int gate, cudaStream_t st);
+void launch_ba_backup(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st);
+void launch_ba_step(const BAWinDev* wins, int W, float stepfac, int load_backup, int gate, cudaStream_t st);
+void launch_ba_reanchor(const BAWinDev* wins, int W, int maxP, cudaStream_t st);
+void launch_ba_decide(const BAWinDev* wins, int W, int stage, cudaStream_t st);              // 0 init, 1 after step+linearize, 2 after reload, 3 final rmse
 
 } // namespace sdv

@@ -18,6 +18,9 @@
 
 namespace sdv {
 
+#define BA_WIN(gate) const BAWinDev& Wn = wins[blockIdx.y]; BAHeader* __restrict__ H = Wn.hdr; \
+  if (((gate) != 0) && ((H->flags & (gate)) != (gate))) return; BAPointsDev P = Wn.P; BAResDev R = Wn.R; const int nP = H->nP, nR = H->nR; (void)P; (void)R; (void)nP; (void)nR;
+
 __constant__ int c_pattern[8][2] = {{0,-2},{-1,-1},{1,-1},{-2,0},{0,0},{2,0},{-1,1},{0,2}};   // settings.cpp:250
 
 // ================================================================================================ frames / pairs
@@ -44,7 +47,8 @@ __device__ void frame_set_state_zero(BAFrameDev& f) {                     // Hes
 
 // flags: 1 setState, 2 setStateZero, 4 takeData(prior), 8 adjoints, 16 precalc+deltas, 32 re-anchor newest frame first,
 //        64 = this is doStepFromBackup/loadSateBackup: first apply calib/frame steps (stepfac) or restore the backups
-__global__ void __launch_bounds__(64) ba_frames_kernel(BAHeader* __restrict__ H, int flags, float stepfac, int load_backup) {
+__global__ void __launch_bounds__(64) ba_frames_kernel(const BAWinDev* __restrict__ wins, int flags, float stepfac, int load_backup, int gate) {
+  BA_WIN(gate)
   const int tid = threadIdx.x; const int nF = H->nF;
   if (flags & 64) {
     if (tid == 0) {
@@ -124,13 +128,15 @@ __global__ void __launch_bounds__(64) ba_frames_kernel(BAHeader* __restrict__ H,
   }
 }
 
-__global__ void ba_points_setup_kernel(const BAHeader* __restrict__ H, BAPointsDev P, int nP, int take_data) {
+__global__ void ba_points_setup_kernel(const BAWinDev* __restrict__ wins, int take_data) {
+  BA_WIN(0)
   int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= nP) return;
   if (take_data) P.priorF[i] = P.hasDepthPrior[i] ? H->set.idepthFixPrior*1.0f*1.0f : 0.0f;       // EFPoint::takeData (EnergyFunctionalStructs.cpp:40-46)
   P.deltaF[i] = P.idepth[i] - P.idepth_zero[i];
 }
 
-__global__ void ba_reset_oob_kernel(BAResDev R, int nR) {                  // PointFrameResidual::resetOOB (Residuals.h:66-73)
+__global__ void ba_reset_oob_kernel(const BAWinDev* __restrict__ wins) {      // PointFrameResidual::resetOOB (Residuals.h:66-73)
+  BA_WIN(0)
   int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= nR) return;
   R.state_NewEnergy[i] = 0; R.state_energy[i] = 0; R.state_NewState[i] = RS_OUTLIER; R.state_state[i] = RS_IN;
 }
@@ -151,8 +157,11 @@ __device__ __forceinline__ void apply_res(BAResDev& R, int r) {            // Re
 }
 
 constexpr int kLinThreads = 128;
-__global__ void __launch_bounds__(kLinThreads) ba_linearize_kernel(BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nR, int fix,
-                                                                 double* __restrict__ partials, float* __restrict__ thbuf, int* __restrict__ thcount) {
+__global__ void __launch_bounds__(kLinThreads) ba_linearize_kernel(const BAWinDev* __restrict__ wins, int fix, int gate) {
+  BA_WIN(gate)
+  const int nblocks = (nR + kLinThreads - 1)/kLinThreads < 1 ? 1 : (nR + kLinThreads - 1)/kLinThreads;
+  if ((int)blockIdx.x >= nblocks) return;                                   // grid.x is sized for the largest window of the batch
+  double* __restrict__ partials = Wn.partials; float* __restrict__ thbuf = Wn.thbuf; int* __restrict__ thcount = Wn.thcount;
   const int r = blockIdx.x*kLinThreads + threadIdx.x;
   double energy = 0;
   if (r < nR) {
@@ -264,13 +273,15 @@ __global__ void __launch_bounds__(kLinThreads) ba_linearize_kernel(BAHeader* __r
   if (threadIdx.x == 0) {
     double s = 0; for (int k=0;k<kLinThreads/32;k++) s += wsum[k];
     partials[blockIdx.x] = s; __threadfence();
-    unsigned int t = atomicAdd(&H->ticket, 1u); is_last = (t == gridDim.x-1);
-    if (is_last) { __threadfence(); double tot = 0; for (unsigned int b=0;b<gridDim.x;b++) tot += __ldcg(partials+b); H->energyP = tot; H->ticket = 0; }
+    unsigned int t = atomicAdd(&H->ticket, 1u); is_last = (t == (unsigned int)nblocks-1);
+    if (is_last) { __threadfence(); double tot = 0; for (int b=0;b<nblocks;b++) tot += __ldcg(partials+b); H->energyP = tot; H->ticket = 0; }
   }
 }
 
 // exact k-th smallest (std::nth_element value) of n non-negative floats by 4x8-bit radix select, then the threshold formula
-__global__ void __launch_bounds__(1024) ba_energy_th_kernel(BAHeader* __restrict__ H, const float* __restrict__ buf, int* __restrict__ count) {
+__global__ void __launch_bounds__(1024) ba_energy_th_kernel(const BAWinDev* __restrict__ wins, int gate) {
+  BA_WIN(gate)
+  const float* __restrict__ buf = Wn.thbuf; int* __restrict__ count = Wn.thcount;
   __shared__ unsigned int hist[256]; __shared__ unsigned int prefix, kk, sel_mask;
   const int n = *count; BAFrameDev& nf = H->frames[H->nF-1];
   if (n == 0) { if (threadIdx.x == 0) { nf.frameEnergyTH = 12*12*8; *count = 0; } return; }
@@ -295,10 +306,11 @@ __global__ void __launch_bounds__(1024) ba_energy_th_kernel(BAHeader* __restrict
   }
 }
 
-__global__ void ba_apply_kernel(BAResDev R, int nR) { int r = blockIdx.x*blockDim.x + threadIdx.x; if (r < nR) apply_res(R, r); }
+__global__ void ba_apply_kernel(const BAWinDev* __restrict__ wins, int gate) { BA_WIN(gate) int r = blockIdx.x*blockDim.x + threadIdx.x; if (r < nR) apply_res(R, r); }
 
 // ================================================================================================ energies
-__global__ void __launch_bounds__(256) ba_energies_kernel(BAHeader* __restrict__ H, BAPointsDev P, int nP) {
+__global__ void __launch_bounds__(256) ba_energies_kernel(const BAWinDev* __restrict__ wins, int gate) {
+  BA_WIN(gate)
   __shared__ double sh[256];
   const int tid = threadIdx.x; const int nF = H->nF, N = H->dim;
   // calcLEnergyPt: chunks of 50 points, float Accumulator11 per chunk (EnergyFunctional.cpp:295-331)
@@ -326,7 +338,8 @@ __global__ void __launch_bounds__(256) ba_energies_kernel(BAHeader* __restrict__
 
 // ================================================================================================ accumulation
 // per point: Hdd/bd/Hcd sums over its active residuals in order (addPoint<0>), then HdiF / bdSumF (SC addPoint head)
-__global__ void ba_point_acc_kernel(const BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nP) {
+__global__ void ba_point_acc_kernel(const BAWinDev* __restrict__ wins, int gate) {
+  BA_WIN(gate)
   int p = blockIdx.x*blockDim.x + threadIdx.x; if (p >= nP) return;
   float bd = 0, Hdd = 0, Hcd[4] = {0,0,0,0}; int ngood = 0;
   for (int r = P.res_begin[p]; r < P.res_begin[p+1]; r++) {
@@ -353,7 +366,9 @@ __device__ __forceinline__ float tier_finish(Tier& t) { t.d1k = t.d + t.d1k; t.d
 
 // one CTA per (host,target) bucket; thread e < 66 owns one cell of AccumulatorApprox and walks the pair's residuals in order
 constexpr int kTopChunk = 32;
-__global__ void __launch_bounds__(96) ba_acc_top_kernel(BAHeader* __restrict__ H, BAResDev R) {
+__global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restrict__ wins, int gate) {
+  BA_WIN(gate)
+  if ((int)blockIdx.x >= H->nF*H->nF) return;
   const int pair = blockIdx.x; const int e = threadIdx.x;
   __shared__ float sJ[kTopChunk][24]; __shared__ int sAct[kTopChunk];
   int ei = 0, ej = 0;                                                        // cell (j row, i col) of the 10x10 upper triangle, Data[] order
@@ -390,7 +405,9 @@ __global__ void __launch_bounds__(96) ba_acc_top_kernel(BAHeader* __restrict__ H
 }
 
 // one CTA per host frame: accD (t1,t2,6x6), accE (t1,6x4), accEB (t1,6); CTA 0 also owns accHcc/accbc over all points
-__global__ void __launch_bounds__(256) ba_acc_sc_kernel(BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nP) {
+__global__ void __launch_bounds__(256) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
+  BA_WIN(gate)
+  if ((int)blockIdx.x >= H->nF) return;
   const int h = blockIdx.x; const int nF = H->nF; const int nF2 = nF*nF;
   const int p0 = R.host_begin[h], p1 = R.host_begin[h+1];
   const int nD = nF2*36, nE = nF*24, nEB = nF*6;
@@ -433,7 +450,9 @@ __device__ __forceinline__ void mm66_elem(const double* A, const double* B, doub
 __device__ __forceinline__ void mm66T_elem(const double* A, const double* B, double* C, int e) { int i = e/6, j = e%6; double s = 0; for (int k=0;k<6;k++) s += A[i*6+k]*B[j*6+k]; C[e] = s; }
 
 constexpr int kSolveThreads = 256;
-__global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(BAHeader* __restrict__ H, int iteration, double lambda) {
+__global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev* __restrict__ wins, int iteration_arg, double lambda_arg, int use_hdr_ctl, int gate) {
+  BA_WIN(gate)
+  const int iteration = use_hdr_ctl ? H->iteration : iteration_arg; const double lambda = use_hdr_ctl ? H->lambda : lambda_arg;
   const int tid = threadIdx.x; const int nF = H->nF, N = H->dim, nF2 = nF*nF;
   __shared__ double sA[kMaxDim*kMaxDim];                                    // working matrix (HFinal scaled -> LDLT in place)
   __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim];
@@ -603,7 +622,8 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(BAHeader* __res
   (void)sred;
 }
 
-__global__ void ba_resub_kernel(const BAHeader* __restrict__ H, BAPointsDev P, BAResDev R, int nP) {     // resubstituteFPt (:250-282)
+__global__ void ba_resub_kernel(const BAWinDev* __restrict__ wins, int gate) {     // resubstituteFPt (:250-282)
+  BA_WIN(gate)
   int p = blockIdx.x*blockDim.x + threadIdx.x; if (p >= nP) return;
   if (P.ngood[p] == 0) { P.step[p] = 0; return; }
   const int nF = H->nF;
@@ -615,14 +635,16 @@ __global__ void ba_resub_kernel(const BAHeader* __restrict__ H, BAPointsDev P, B
 }
 
 // ================================================================================================ backup / step
-__global__ void ba_backup_kernel(BAHeader* __restrict__ H, BAPointsDev P, int nP) {
+__global__ void ba_backup_kernel(const BAWinDev* __restrict__ wins, int gate) {
+  BA_WIN(gate)
   int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i < nP) P.idepth_backup[i] = P.idepth[i];
   if (i < H->nF) for (int k=0;k<10;k++) H->frames[i].state_backup[k] = H->frames[i].state[k];
   if (i == 0) for (int k=0;k<4;k++) H->calib.value_backup[k] = H->calib.value[k];
 }
 // points part of doStepFromBackup / loadSateBackup + the float sums the break test needs (single CTA keeps the reduction fixed-order)
-__global__ void __launch_bounds__(1024) ba_step_points_kernel(BAHeader* __restrict__ H, BAPointsDev P, int nP, float stepfac, int load_backup) {
+__global__ void __launch_bounds__(1024) ba_step_points_kernel(const BAWinDev* __restrict__ wins, float stepfac, int load_backup, int gate) {
+  BA_WIN(gate)
   __shared__ float s1[1024], s2[1024];
   float sumID = 0, sumNID = 0;
   for (int i = threadIdx.x; i < nP; i += 1024) {
@@ -635,36 +657,68 @@ __global__ void __launch_bounds__(1024) ba_step_points_kernel(BAHeader* __restri
   if (threadIdx.x == 0) { H->sums[0] = s1[0]; H->sums[1] = s2[0]; H->sums[2] = (float)nP; }
 }
 
+// ================================================================================================ device-resident GN control
+// stage 0: after the initial linearizeAll + energies (optimize :373-381)         -> lastEnergy*, lambda, APPLY
+// stage 1: after backup/solve/step/linearize/energies of one iteration (:395-454) -> accept (APPLY, lambda/4) or reject (RELOAD, lambda*100)
+// stage 2: after the reload path of a rejected step                               -> lastEnergy* from the re-linearisation; break test (:457)
+// stage 3: after the final linearizeAll(true)                                     -> rmse (:501)
+__global__ void ba_decide_kernel(const BAWinDev* __restrict__ wins, int W, int stage) {
+  const int wi = blockIdx.x*blockDim.x + threadIdx.x; if (wi >= W) return;
+  BAHeader* H = wins[wi].hdr;
+  if (stage == 0) {
+    int m = H->mnumOptIts; if (H->nF < 3) m = 100; if (H->nF < 4) m = 75;                // FullSystemOptimize.cpp:347-349 (sequential ifs)
+    H->mnumOptIts = m; H->iteration = 0; H->opt_iterations = 0; H->opt_accepts = 0; H->lambda = 1e-1;
+    H->lastEnergy = H->energyP; H->lastEnergyL = H->energyL; H->lastEnergyM = H->energyM;
+    H->flags = (H->nF >= 2) ? BA_ACTIVE : 0;
+  } else if (stage == 1) {
+    if (!(H->flags & BA_ACTIVE)) return;
+    H->opt_iterations++;
+    const double newE = H->energyP, newL = H->energyL, newM = H->energyM;
+    if (newE + 0 + newL + newM < H->lastEnergy + 0 + H->lastEnergyL + H->lastEnergyM) {
+      H->opt_accepts++; H->lastEnergy = newE; H->lastEnergyL = newL; H->lastEnergyM = newM; H->lambda *= 0.25; H->flags |= BA_APPLY;
+    } else { H->lambda *= 1e2; H->flags |= BA_RELOAD; }
+  } else if (stage == 2) {
+    if (!(H->flags & BA_ACTIVE)) return;
+    if (H->flags & BA_RELOAD) { H->lastEnergy = H->energyP; H->lastEnergyL = H->energyL; H->lastEnergyM = H->energyM; }
+    H->flags &= ~(BA_APPLY | BA_RELOAD);
+    const int it = H->iteration; H->iteration = it + 1;
+    if ((H->canbreak && it >= H->set.minOptIterations) || it + 1 >= H->mnumOptIts) H->flags &= ~BA_ACTIVE;
+  } else {
+    H->rmse = sqrtf((float)(H->energyP / H->resInA));
+  }
+}
+
 // ================================================================================================ launchers
-void launch_ba_setup(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) {
-  ba_frames_kernel<<<1, 64, 0, st>>>(hdr, 1|2|4|8|16, 0.f, 0);
-  if (nP > 0) ba_points_setup_kernel<<<(nP+255)/256, 256, 0, st>>>(hdr, P, nP, 1);
+static inline dim3 g2(int n, int per, int W) { int gx = (n + per - 1)/per; if (gx < 1) gx = 1; return dim3(gx, W); }
+void launch_ba_setup(const BAWinDev* wins, int W, int maxP, cudaStream_t st) {
+  ba_frames_kernel<<<dim3(1, W), 64, 0, st>>>(wins, 1|2|4|8|16, 0.f, 0, GATE_ALWAYS);
+  ba_points_setup_kernel<<<g2(maxP, 256, W), 256, 0, st>>>(wins, 1);
 }
-void launch_ba_reset_oob(BAResDev R, int nR, cudaStream_t st) { if (nR > 0) ba_reset_oob_kernel<<<(nR+255)/256, 256, 0, st>>>(R, nR); }
-void launch_ba_linearize(BAHeader* hdr, BAPointsDev P, BAResDev R, int nR, int fix, double* partials, float* thbuf, int* thcount, cudaStream_t st) {
-  int grid = (nR + kLinThreads - 1)/kLinThreads; if (grid < 1) grid = 1;
-  ba_linearize_kernel<<<grid, kLinThreads, 0, st>>>(hdr, P, R, nR, fix, partials, thbuf, thcount);
-  ba_energy_th_kernel<<<1, 1024, 0, st>>>(hdr, thbuf, thcount);
+void launch_ba_reset_oob(const BAWinDev* wins, int W, int maxR, cudaStream_t st) { ba_reset_oob_kernel<<<g2(maxR, 256, W), 256, 0, st>>>(wins); }
+void launch_ba_linearize(const BAWinDev* wins, int W, int maxR, int fix, int gate, cudaStream_t st) {
+  ba_linearize_kernel<<<g2(maxR, kLinThreads, W), kLinThreads, 0, st>>>(wins, fix, gate);
+  ba_energy_th_kernel<<<dim3(1, W), 1024, 0, st>>>(wins, gate);
 }
-void launch_ba_apply(BAResDev R, int nR, cudaStream_t st) { if (nR > 0) ba_apply_kernel<<<(nR+255)/256, 256, 0, st>>>(R, nR); }
-void launch_ba_energies(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) { ba_energies_kernel<<<1, 256, 0, st>>>(hdr, P, nP); }
-void launch_ba_accumulate(BAHeader* hdr, BAPointsDev P, BAResDev R, int nF, int nP, cudaStream_t st) {
-  if (nP > 0) ba_point_acc_kernel<<<(nP+127)/128, 128, 0, st>>>(hdr, P, R, nP);
-  ba_acc_top_kernel<<<nF*nF, 96, 0, st>>>(hdr, R);
-  ba_acc_sc_kernel<<<nF, 256, 0, st>>>(hdr, P, R, nP);
+void launch_ba_apply(const BAWinDev* wins, int W, int maxR, int gate, cudaStream_t st) { ba_apply_kernel<<<g2(maxR, 256, W), 256, 0, st>>>(wins, gate); }
+void launch_ba_energies(const BAWinDev* wins, int W, int gate, cudaStream_t st) { ba_energies_kernel<<<dim3(1, W), 256, 0, st>>>(wins, gate); }
+void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) {
+  ba_point_acc_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate);
+  ba_acc_top_kernel<<<dim3(kMaxF*kMaxF, W), 96, 0, st>>>(wins, gate);
+  ba_acc_sc_kernel<<<dim3(kMaxF, W), 256, 0, st>>>(wins, gate);
 }
-void launch_ba_solve(BAHeader* hdr, BAPointsDev P, BAResDev R, int nP, int iteration, double lambda, cudaStream_t st) {
-  ba_solve_kernel<<<1, kSolveThreads, 0, st>>>(hdr, iteration, lambda);
-  if (nP > 0) ba_resub_kernel<<<(nP+127)/128, 128, 0, st>>>(hdr, P, R, nP);
+void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, double lambda, int use_hdr_ctl, int gate, cudaStream_t st) {
+  ba_solve_kernel<<<dim3(1, W), kSolveThreads, 0, st>>>(wins, iteration, lambda, use_hdr_ctl, gate);
+  ba_resub_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate);
 }
-void launch_ba_backup(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) { int n = nP > kMaxF ? nP : kMaxF; ba_backup_kernel<<<(n+255)/256, 256, 0, st>>>(hdr, P, nP); }
-void launch_ba_step(BAHeader* hdr, BAPointsDev P, int nP, float stepfac, int load_backup, cudaStream_t st) {
-  ba_step_points_kernel<<<1, 1024, 0, st>>>(hdr, P, nP, stepfac, load_backup);
-  ba_frames_kernel<<<1, 64, 0, st>>>(hdr, 64|1|16, stepfac, load_backup);
+void launch_ba_backup(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) { ba_backup_kernel<<<g2(maxP > kMaxF ? maxP : kMaxF, 256, W), 256, 0, st>>>(wins, gate); }
+void launch_ba_step(const BAWinDev* wins, int W, float stepfac, int load_backup, int gate, cudaStream_t st) {
+  ba_step_points_kernel<<<dim3(1, W), 1024, 0, st>>>(wins, stepfac, load_backup, gate);
+  ba_frames_kernel<<<dim3(1, W), 64, 0, st>>>(wins, 64|1|16, stepfac, load_backup, gate);
 }
-void launch_ba_reanchor(BAHeader* hdr, BAPointsDev P, int nP, cudaStream_t st) {
-  ba_frames_kernel<<<1, 64, 0, st>>>(hdr, 32|8|16, 0.f, 0);
-  if (nP > 0) ba_points_setup_kernel<<<(nP+255)/256, 256, 0, st>>>(hdr, P, nP, 0);
+void launch_ba_reanchor(const BAWinDev* wins, int W, int maxP, cudaStream_t st) {
+  ba_frames_kernel<<<dim3(1, W), 64, 0, st>>>(wins, 32|8|16, 0.f, 0, GATE_ALWAYS);
+  ba_points_setup_kernel<<<g2(maxP, 256, W), 256, 0, st>>>(wins, 0);
 }
+void launch_ba_decide(const BAWinDev* wins, int W, int stage, cudaStream_t st) { ba_decide_kernel<<<(W + 127)/128, 128, 0, st>>>(wins, W, stage); }
 
 } // namespace sdv

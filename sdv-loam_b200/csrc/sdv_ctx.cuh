@@ -39,7 +39,8 @@ struct sdv_ctx {
   int cd_cap; float* cd_pts4; int* cd_round; float4* cd_splats; int* cd_done;
   int jobs_cap; sdv::TrackJob* jobs_dev; sdv::TrackJob* jobs_host;
   float last_ms;
-  sdv::BAState* ba = nullptr;
+  sdv::BAState* ba = nullptr;                   // selected back-end window
+  std::vector<sdv::BAState*> ba_windows; void* ba_wins_dev = nullptr; void* ba_wins_host = nullptr; int ba_wins_cap = 0;
   char err[512];
 };
 

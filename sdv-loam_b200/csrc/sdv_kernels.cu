@@ -218,9 +218,8 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
     for (int i = 0; i < 5; i++) ctl.lastRes[i] = nan("");
     for (int i = 0; i < 3; i++) ctl.flow[i] = 1000.0;
   }
-  long long evals[kLevels]; int iters[kLevels], accs[kLevels];
-#pragma unroll
-  for (int i = 0; i < kLevels; i++) { evals[i] = 0; iters[i] = 0; accs[i] = 0; }
+  __shared__ long long evals[kLevels]; __shared__ int iters[kLevels], accs[kLevels];   // statistics: shared, touched by thread 0 only (keeps them out of registers)
+  if (tid == 0) { for (int i = 0; i < kLevels; i++) { evals[i] = 0; iters[i] = 0; accs[i] = 0; } }
   __syncthreads();
 
   int evalCount = 0;
@@ -259,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       if (tid < kNAcc) tot[tid] = bsum[tid];
     }
     __syncthreads();
-    evalCount++; evals[lvl] += n;
+    evalCount++; if (tid == 0) evals[lvl] += n;
   };
 
   const int maxIterations[5] = {10,20,50,50,50};           // CoarseTracker.cpp:679
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
     if (tid == 0) { finalize_gs(tot, ctl.H, ctl.b); ctl.lambda = 0.01f; }
 
     for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
-      iters[lvl]++;
+      if (tid == 0) iters[lvl]++;
       double incn = 0;
       if (tid < 32) {                                        // warp 0: propose the LM step (CoarseTracker.cpp:722-765)
         const int r = tid & 7;
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       __syncthreads();
       const int f = ctl.flag;
       __syncthreads();
-      if (f & 1) accs[lvl]++;
+      if ((f & 1) && tid == 0) accs[lvl]++;
       if (f & 2) break;
     }
     if (tid == 0) {
@@ -417,10 +416,13 @@ static cudaError_t launch_track_t(TrackJob* jobs_dev, int njobs, const TrackCons
   return cudaLaunchKernelEx(&cfg, kern, jobs_dev, tc_dev);
 }
 // threads: 128 (throughput, 4 jobs resident per SM) or 256 (latency)
+#ifndef SDV_TRACK_MINB
+#define SDV_TRACK_MINB 4                    // measured: 3 (163 regs) -18 %, 5 (96 regs, spills) -16 %, 6 (80 regs) -45 % vs 4 (128 regs, no spills)
+#endif
 cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, int threads, cudaStream_t st) {
   if (threads == 256) return launch_track_t<256, 1>(jobs_dev, njobs, tc_dev, cluster_size, st);
   if (threads == 64)  return launch_track_t<64, 8>(jobs_dev, njobs, tc_dev, cluster_size, st);
-  return launch_track_t<128, 4>(jobs_dev, njobs, tc_dev, cluster_size, st);
+  return launch_track_t<128, SDV_TRACK_MINB>(jobs_dev, njobs, tc_dev, cluster_size, st);
 }
 
 // ================================================================================================ makeCoarseDepthL0

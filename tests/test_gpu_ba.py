@@ -131,3 +131,34 @@ def test_window_validation_errors():
     with pytest.raises(api.SdvError):
         api.EnergyFunctional(ctx, win, [0, 1, 99])
     ctx.close()
+
+
+def test_optimize_batch_device_resident_schedule():
+    """Batched mode: windows of different shapes (7, 5, 3 and 2 keyframes; with/without prior) optimised in ONE device-resident schedule
+    give exactly the per-window oracle results (each window takes its own accept/reject path and stops on its own break test)."""
+    api, synth = _mods()
+    seq = cached_sequence(8, 2000, synth.KITTI_K, synth.KITTI_WH)
+    w, h = synth.KITTI_WH; L = api.pyr_levels(w, h)
+    ctx = api.Context(synth.KITTI_K, w, h, max_frames=9)
+    for k in range(8):
+        ctx.makeImages(k, seq.images[k])
+    frames = [orc.Frame(seq.images[k], L) for k in range(8)]
+    cfgs = [dict(kfs=[0, 1, 2, 3, 4, 5, 6], noise=(0.005, 0.0003), prior=1e-3), dict(kfs=[1, 2, 4, 5, 7], noise=(0.02, 0.002), prior=0.0),
+            dict(kfs=[0, 3, 6], noise=(0.01, 0.0005), prior=1e-2), dict(kfs=[2, 3], noise=(0.003, 0.0002), prior=0.0),
+            dict(kfs=[0, 1, 2, 3, 4, 5, 6, 7], noise=(0.0, 0.0), prior=1e-3)]
+    gbs, obs = [], []
+    for i, cf in enumerate(cfgs):
+        win = synth.make_ba_window(seq, cf["kfs"], n_per_frame=150 + 20 * i, seed=20 + i, pose_noise=cf["noise"], match_noise=0.2, prior_scale=cf["prior"])
+        gbs.append(api.EnergyFunctional(ctx, win, cf["kfs"], window=i))
+        obs.append(orc.BAWindow(win, [frames[k] for k in cf["kfs"]]))
+    r = api.optimize_batch(ctx, list(range(len(cfgs))), 6)
+    for i, (gb, ob) in enumerate(zip(gbs, obs)):
+        ro = ob.optimize(6)
+        assert (ro["iterations"], ro["accepts"]) == (int(r["iterations"][i]), int(r["accepts"][i])), (i, ro, r)
+        assert np.float32(ro["rmse"]) == r["rmse"][i]
+        fo, fg = ob.frames(), gb.frames()
+        assert _same(fo["T_eval"], fg["T_eval"]) and _same(fo["state"], fg["state"]) and _same(fo["frameEnergyTH"], fg["frameEnergyTH"])
+        assert _same(ob.points()["idepth"], gb.points()["idepth"])
+        so, sg = ob.residuals(), gb.residuals()
+        assert _same(so["state"], sg["state"]) and _same(so["toRemove"], sg["toRemove"])
+    ctx.close()
