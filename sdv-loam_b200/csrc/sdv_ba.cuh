@@ -56,6 +56,8 @@ struct BAHeader {                        // one per window, lives in device memo
   int mnumOptIts, iteration, opt_iterations, opt_accepts;
   double lambda, lastEnergy, lastEnergyL, lastEnergyM;
   float rmse;
+  // cached orthonormal basis of the pose+scale nullspaces (valid while the evaluation points do not change)
+  int ortho_valid; double orthoU[7*kMaxDim]; double orthoS[7];
 };
 enum { BA_ACTIVE = 1, BA_APPLY = 2, BA_RELOAD = 4 };
 enum { GATE_ALWAYS = 0, GATE_ACTIVE = 1, GATE_APPLY = 2, GATE_RELOAD = 4 };

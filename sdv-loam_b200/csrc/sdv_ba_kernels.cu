@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(64) ba_frames_kernel(const BAWinDev* __restric
     }
     for (int i=0;i<6;i++) { f.delta[i] = f.state[i] - f.state_zero[i]; f.delta_prior[i] = f.state[i]; }
   }
-  if (tid == 0) { for (int i=0;i<4;i++) { H->calib.cDeltaF[i] = (float)H->calib.vmvz[i]; H->calib.cPrior[i] = H->set.initialCalibHessian; } }
+  if (tid == 0) { for (int i=0;i<4;i++) { H->calib.cDeltaF[i] = (float)H->calib.vmvz[i]; H->calib.cPrior[i] = H->set.initialCalibHessian; }
+    if (flags & (2|32)) H->ortho_valid = 0; }
   __syncthreads();
   if (tid < nF*nF) {
     const int h = tid % nF, t = tid / nF; const int idx = h + t*nF;
@@ -404,144 +405,176 @@ __global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restri
   if (e == 0) H->accTopNum[pair] = num;
 }
 
-// one CTA per host frame: accD (t1,t2,6x6), accE (t1,6x4), accEB (t1,6); CTA 0 also owns accHcc/accbc over all points
-__global__ void __launch_bounds__(256) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
+// one CTA per (host, t1): cells accD[(h,t1,t2)][6x6] for all t2, accE[(h,t1)][6x4], accEB[(h,t1)][6]; the rows of the host's points
+// (activity, JpJdF per target, HdiF, bdSumF, Hcd) are staged through shared memory 32 points at a time.  CTA (0,0) also owns
+// accHcc/accbc, which run over all points.
+constexpr int kScChunk = 32;
+__global__ void __launch_bounds__(320) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
   BA_WIN(gate)
-  if ((int)blockIdx.x >= H->nF) return;
-  const int h = blockIdx.x; const int nF = H->nF; const int nF2 = nF*nF;
+  const int nF = H->nF; const int nF2 = nF*nF;
+  const int h = blockIdx.x % kMaxF, t1 = blockIdx.x / kMaxF;
+  if (h >= nF || t1 >= nF) return;
   const int p0 = R.host_begin[h], p1 = R.host_begin[h+1];
-  const int nD = nF2*36, nE = nF*24, nEB = nF*6;
-  for (int e = threadIdx.x; e < nD + nE + nEB; e += 256) {
-    Tier t = {0,0,0,0,0}; int num = 0;
-    int kind, t1, t2 = 0, i, j = 0;
-    if (e < nD) { kind = 0; int q = e/36; t1 = q % nF; t2 = q / nF; i = (e%36)/6; j = e%6; }
-    else if (e < nD + nE) { kind = 1; int q = e - nD; t1 = q/24; i = (q%24)/4; j = q%4; }
-    else { kind = 2; int q = e - nD - nE; t1 = q/6; i = q%6; }
-    for (int p = p0; p < p1; p++) {
-      if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
-      const int r1 = P.res_of_target[(size_t)p*kMaxF + t1]; if (r1 < 0 || !R.isActive[r1]) continue;
-      const float Hdi = P.HdiF[p]; const float wl = Hdi*R.JpJdF[(size_t)r1*8+i];
-      if (kind == 0) { const int r2 = P.res_of_target[(size_t)p*kMaxF + t2]; if (r2 < 0 || !R.isActive[r2]) continue;
-        t.d += wl*R.JpJdF[(size_t)r2*8+j]; }                                // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
-      else if (kind == 1) t.d += wl*(P.Hcd_accAF[(size_t)p*4+j] + 0.0f);
-      else t.d += (Hdi*P.bdSumF[p])*R.JpJdF[(size_t)r1*8+i];                // accEB.update(r1->JpJdF, HdiF*bdSumF): A += w*L
+  __shared__ float sJ[kScChunk][kMaxF][6]; __shared__ int sAct[kScChunk][kMaxF]; __shared__ float sHdi[kScChunk], sBd[kScChunk], sHcd[kScChunk][4]; __shared__ int sUse[kScChunk];
+  const int nD = nF*36, nE = 24, nEB = 6; const int e = threadIdx.x; const bool mine = e < nD + nE + nEB;
+  int kind = 0, t2 = 0, i = 0, j = 0;
+  if (e < nD) { kind = 0; t2 = e/36; i = (e%36)/6; j = e%6; }
+  else if (e < nD + nE) { kind = 1; int q = e - nD; i = q/4; j = q%4; }
+  else { kind = 2; i = e - nD - nE; }
+  Tier t = {0,0,0,0,0}; int num = 0;
+  if (h != t1) for (int base = p0; base < p1; base += kScChunk) {
+    const int cnt = min(kScChunk, p1 - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < cnt*nF; k += blockDim.x) { int q = k / nF, tt = k - q*nF; int p = base + q;
+      int r = P.res_of_target[(size_t)p*kMaxF + tt]; int act = (r >= 0) ? R.isActive[r] : 0; sAct[q][tt] = act;
+      if (act) { for (int c=0;c<6;c++) sJ[q][tt][c] = R.JpJdF[(size_t)r*8+c]; } }
+    if (threadIdx.x < cnt) { int p = base + threadIdx.x; sUse[threadIdx.x] = (P.ngood[p] != 0 && !P.isFromSensor[p]) ? 1 : 0; sHdi[threadIdx.x] = P.HdiF[p]; sBd[threadIdx.x] = P.bdSumF[p];
+      for (int c=0;c<4;c++) sHcd[threadIdx.x][c] = P.Hcd_accAF[(size_t)p*4+c] + 0.0f; }
+    __syncthreads();
+    if (mine) for (int q = 0; q < cnt; q++) {
+      if (!sUse[q] || !sAct[q][t1]) continue;
+      const float Hdi = sHdi[q]; const float wl = Hdi*sJ[q][t1][i];
+      if (kind == 0) { if (!sAct[q][t2]) continue; t.d += wl*sJ[q][t2][j]; }       // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
+      else if (kind == 1) t.d += wl*sHcd[q][j];                                     // accE.update(r1->JpJdF, Hcd, HdiF)
+      else t.d += (Hdi*sBd[q])*sJ[q][t1][i];                                        // accEB.update(r1->JpJdF, HdiF*bdSumF)
       num++; t.n1 += 1; tier_shift(t);
     }
-    float v = tier_finish(t);
+  }
+  if (mine) { float v = tier_finish(t);
     if (kind == 0) { int b = h + nF*t1 + nF2*t2; H->accD[b*36 + i*6 + j] = v; if (i == 0 && j == 0) H->accDNum[b] = num; }
     else if (kind == 1) H->accE[(h + nF*t1)*24 + i*4 + j] = v;
-    else H->accEB[(h + nF*t1)*6 + i] = v;
-  }
-  if (h == 0 && threadIdx.x < 20) {
-    const int e = threadIdx.x; Tier t = {0,0,0,0,0};
+    else H->accEB[(h + nF*t1)*6 + i] = v; }
+  if (blockIdx.x == 0 && threadIdx.x < 20) {
+    const int e2 = threadIdx.x; Tier tt = {0,0,0,0,0};
     for (int p = 0; p < nP; p++) {
       if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
       const float Hdi = P.HdiF[p];
-      if (e < 16) t.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e%4] + 0.0f);
-      else t.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e-16] + 0.0f);
-      t.n1 += 1; tier_shift(t);
+      if (e2 < 16) tt.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e2/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e2%4] + 0.0f);
+      else tt.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e2-16] + 0.0f);
+      tt.n1 += 1; tier_shift(tt);
     }
-    float v = tier_finish(t); if (e < 16) H->accHcc[e] = v; else H->accbc[e-16] = v;
+    float v = tier_finish(tt); if (e2 < 16) H->accHcc[e2] = v; else H->accbc[e2-16] = v;
   }
 }
 
-// ================================================================================================ stitch + solve (single CTA)
-__device__ __forceinline__ void mm66_elem(const double* A, const double* B, double* C, int e) { int i = e/6, j = e%6; double s = 0; for (int k=0;k<6;k++) s += A[i*6+k]*B[k*6+j]; C[e] = s; }
-__device__ __forceinline__ void mm66T_elem(const double* A, const double* B, double* C, int e) { int i = e/6, j = e%6; double s = 0; for (int k=0;k<6;k++) s += A[i*6+k]*B[j*6+k]; C[e] = s; }
+// ================================================================================================ stitch + solve (single CTA per window)
+// Stitching is GATHER-style: one thread owns one element of the output system and walks the contributing (host,target) buckets in
+// the reference's order (AccumulatedTopHessian.cpp:181-242, AccumulatedSCHessian.cpp:64-135), so every fp64 sum has the reference's
+// order without a barrier per bucket.  The two system matrices live in shared memory.
+__device__ __forceinline__ double tri10(const float* a, int r, int c) { int lo = min(r,c), hi = max(r,c); return (double)a[lo*10 - lo*(lo-1)/2 + (hi-lo)]; }
+// element (i,j) of A1 * M * A2^T with M(p,q) supplied by a functor; evaluated as (A1*M) then * A2^T, inner indices ascending
+template <typename MF> __device__ __forceinline__ double triple66(const double* A1, const double* A2, int i, int j, MF M) {
+  double s = 0;
+#pragma unroll
+  for (int q = 0; q < 6; q++) { double t = 0;
+#pragma unroll
+    for (int p = 0; p < 6; p++) t += A1[i*6+p]*M(p, q);
+    s += t*A2[j*6+q]; }
+  return s;
+}
 
 constexpr int kSolveThreads = 256;
 __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev* __restrict__ wins, int iteration_arg, double lambda_arg, int use_hdr_ctl, int gate) {
   BA_WIN(gate)
   const int iteration = use_hdr_ctl ? H->iteration : iteration_arg; const double lambda = use_hdr_ctl ? H->lambda : lambda_arg;
   const int tid = threadIdx.x; const int nF = H->nF, N = H->dim, nF2 = nF*nF;
-  __shared__ double sA[kMaxDim*kMaxDim];                                    // working matrix (HFinal scaled -> LDLT in place)
-  __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim];
-  __shared__ double T1[36], T2[36], T3[36], accH66[36], accH64[24], accb[10], acc44[16];
-  __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double sred[kSolveThreads];
-  double* HA = H->HA; double* Hsc = H->Hsc;
-  for (int i = tid; i < N*N; i += kSolveThreads) { HA[i] = 0; Hsc[i] = 0; }
-  for (int i = tid; i < N; i += kSolveThreads) { H->bA[i] = 0; H->bsc[i] = 0; }
-  __syncthreads();
-  // ---- top stitch (AccumulatedTopHessian.cpp:181-242): pairs in order k = h + nF*t, each block update parallel over its elements
-  int resInA = 0;
-  for (int k = 0; k < nF2; k++) {
-    const int h = k % nF, t = k / nF, hIdx = kCP + h*6, tIdx = kCP + t*6;
-    const float* a = H->accTop + k*kNTop; const bool empty = (H->accTopNum[k] == 0); resInA += H->accTopNum[k];
-    if (tid < 36) { int r = 4 + tid/6, c = 4 + tid%6; int lo = min(r,c), hi = max(r,c); int off = lo*10 - lo*(lo-1)/2 + (hi-lo); accH66[tid] = empty ? 0.0 : (double)a[off]; }
-    else if (tid < 60) { int q = tid-36; int r = 4 + q/4, c = q%4; int off = c*10 - c*(c-1)/2 + (r-c); accH64[q] = empty ? 0.0 : (double)a[off]; }
-    else if (tid < 76) { int q = tid-60; int r = q/4, c = q%4; int lo = min(r,c), hi = max(r,c); int off = lo*10 - lo*(lo-1)/2 + (hi-lo); acc44[q] = empty ? 0.0 : (double)a[off]; }
-    else if (tid < 86) { accb[tid-76] = empty ? 0.0 : (double)a[55 + tid-76]; }
-    __syncthreads();
-    const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36;
-    if (tid < 36) mm66_elem(AH, accH66, T1, tid); else if (tid >= 64 && tid < 100) mm66_elem(AT, accH66, T3, tid-64);
-    __syncthreads();
-    if (tid < 36) { mm66T_elem(T1, AH, T2, tid); HA[(hIdx+tid/6)*N + hIdx+tid%6] += T2[tid]; }
-    __syncthreads();
-    if (tid < 36) { mm66T_elem(T1, AT, T2, tid); HA[(hIdx+tid/6)*N + tIdx+tid%6] += T2[tid]; }
-    __syncthreads();
-    if (tid < 36) { mm66T_elem(T3, AT, T2, tid); HA[(tIdx+tid/6)*N + tIdx+tid%6] += T2[tid]; }
-    __syncthreads();
-    if (tid < 24) { int r = tid/4, c = tid%4; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*accH64[q*4+c]; HA[(hIdx+r)*N + c] += s1; }
-    __syncthreads();
-    if (tid < 24) { int r = tid/4, c = tid%4; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*accH64[q*4+c]; HA[(tIdx+r)*N + c] += s2; }
-    if (tid >= 32 && tid < 48) { int q = tid-32; HA[(q/4)*N + q%4] += acc44[q]; }
-    if (tid >= 64 && tid < 70) { int r = tid-64; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*accb[4+q]; H->bA[hIdx+r] += s1; }
-    __syncthreads();
-    if (tid >= 64 && tid < 70) { int r = tid-64; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*accb[4+q]; H->bA[tIdx+r] += s2; }
-    if (tid >= 96 && tid < 100) H->bA[tid-96] += accb[tid-96];
-    __syncthreads();
-  }
-  if (tid < 4) { HA[tid*N+tid] += H->calib.cPrior[tid]; H->bA[tid] += H->calib.cPrior[tid]*(double)H->calib.cDeltaF[tid]; }
-  if (tid >= 32 && tid < 32 + 6*nF) { int q = tid-32, f = q/6, i = q%6, d = kCP + f*6 + i; HA[d*N+d] += H->frames[f].prior[i]; H->bA[d] += H->frames[f].prior[i]*H->frames[f].delta_prior[i]; }
-  __syncthreads();
-  for (int h = 0; h < nF; h++) {                                            // AccumulatedTopHessian.h:100-113
-    const int hIdx = kCP + h*6;
-    if (tid < 24) { int r = tid/6, c = tid%6; HA[r*N + hIdx+c] = HA[(hIdx+c)*N + r]; }
-    for (int t = h+1; t < nF; t++) { const int tIdx = kCP + t*6;
-      if (tid < 36) { int r = tid/6, c = tid%6; HA[(hIdx+r)*N + tIdx+c] += HA[(tIdx+c)*N + hIdx+r]; }
-      __syncthreads();
-      if (tid < 36) { int r = tid/6, c = tid%6; HA[(tIdx+r)*N + hIdx+c] = HA[(hIdx+c)*N + tIdx+r]; } }
-    __syncthreads();
-  }
-  // ---- SC stitch (AccumulatedSCHessian.cpp:64-135)
-  for (int k = 0; k < nF2; k++) {
-    const int i = k % nF, j = k / nF, iIdx = kCP + i*6, jIdx = kCP + j*6, ij = i + nF*j;
-    const double* AHij = H->adHost + ij*36; const double* ATij = H->adTarget + ij*36;
-    if (tid < 24) { int r = tid/4, c = tid%4; double s1 = 0; for (int q=0;q<6;q++) s1 += AHij[r*6+q]*(double)H->accE[ij*24+q*4+c]; Hsc[(iIdx+r)*N + c] += s1; }
-    if (tid >= 32 && tid < 38) { int r = tid-32; double s1 = 0; for (int q=0;q<6;q++) s1 += AHij[r*6+q]*(double)H->accEB[ij*6+q]; H->bsc[iIdx+r] += s1; }
-    __syncthreads();
-    if (tid < 24) { int r = tid/4, c = tid%4; double s2 = 0; for (int q=0;q<6;q++) s2 += ATij[r*6+q]*(double)H->accE[ij*24+q*4+c]; Hsc[(jIdx+r)*N + c] += s2; }
-    if (tid >= 32 && tid < 38) { int r = tid-32; double s2 = 0; for (int q=0;q<6;q++) s2 += ATij[r*6+q]*(double)H->accEB[ij*6+q]; H->bsc[jIdx+r] += s2; }
-    __syncthreads();
-    for (int k2 = 0; k2 < nF; k2++) {
-      const int kIdx = kCP + k2*6, ik = i + nF*k2, b = ij + k2*nF2;
-      if (H->accDNum[b] == 0) continue;                                    // uniform branch
-      const double* AHik = H->adHost + ik*36; const double* ATik = H->adTarget + ik*36;
-      if (tid < 36) accH66[tid] = (double)H->accD[b*36+tid];
-      __syncthreads();
-      if (tid < 36) mm66_elem(AHij, accH66, T1, tid); else if (tid >= 64 && tid < 100) mm66_elem(ATij, accH66, T3, tid-64);
-      __syncthreads();
-      if (tid < 36) { mm66T_elem(T1, AHik, T2, tid); Hsc[(iIdx+tid/6)*N + iIdx+tid%6] += T2[tid]; }
-      __syncthreads();
-      if (tid < 36) { mm66T_elem(T3, ATik, T2, tid); Hsc[(jIdx+tid/6)*N + kIdx+tid%6] += T2[tid]; }
-      __syncthreads();
-      if (tid < 36) { mm66T_elem(T3, AHik, T2, tid); Hsc[(jIdx+tid/6)*N + iIdx+tid%6] += T2[tid]; }
-      __syncthreads();
-      if (tid < 36) { mm66T_elem(T1, ATik, T2, tid); Hsc[(iIdx+tid/6)*N + kIdx+tid%6] += T2[tid]; }
-      __syncthreads();
+  __shared__ double sA[kMaxDim*kMaxDim];                                    // HA -> HFinal (scaled) -> LDLT in place
+  __shared__ double sS[kMaxDim*kMaxDim];                                    // Hsc -> nullspace basis
+  __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim], sbA[kMaxDim], sbS[kMaxDim];
+  __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double srot[4];
+  // ---- top: frame-frame blocks (raw), frame-calib blocks, calib block, gradient
+  for (int task = tid; task < nF2*36; task += kSolveThreads) {
+    const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
+    for (int k = 0; k < nF2; k++) {
+      const int h = k % nF, t = k / nF; if (!((a == h || a == t) && (b == h || b == t))) continue;
+      if (H->accTopNum[k] == 0) continue;                                  // empty bucket contributes exact zeros
+      const float* m = H->accTop + k*kNTop; const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36;
+      auto M = [&](int p, int q) { return tri10(m, 4+p, 4+q); };
+      if (a == h && b == h) acc += triple66(AH, AH, i, j, M);
+      if (a == t && b == t) acc += triple66(AT, AT, i, j, M);
+      if (a == h && b == t) acc += triple66(AH, AT, i, j, M);
     }
+    if (a == b && i == j) acc += H->frames[a].prior[i];
+    sA[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
   }
-  if (tid < 16) Hsc[(tid/4)*N + tid%4] += (double)H->accHcc[tid];
-  if (tid >= 32 && tid < 36) H->bsc[tid-32] += (double)H->accbc[tid-32];
+  for (int task = tid; task < nF*24; task += kSolveThreads) {              // H[frame a, calib] (6x4)
+    const int a = task/24, r = (task%24)/4, c = task%4; double acc = 0;
+    for (int k = 0; k < nF2; k++) { const int h = k % nF, t = k / nF; if (a != h && a != t) continue; if (H->accTopNum[k] == 0) continue;
+      const float* m = H->accTop + k*kNTop;
+      if (a == h) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*tri10(m, 4+q, c); acc += s1; }
+      if (a == t) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*tri10(m, 4+q, c); acc += s2; } }
+    sA[(kCP+a*6+r)*N + c] = acc;
+  }
+  if (tid < 16) { const int r = tid/4, c = tid%4; double acc = 0; int resInA = 0;
+    for (int k = 0; k < nF2; k++) { resInA += H->accTopNum[k]; if (H->accTopNum[k] == 0) continue; acc += tri10(H->accTop + k*kNTop, r, c); }
+    if (r == c) acc += H->calib.cPrior[r];
+    sA[r*N + c] = acc; if (tid == 0) H->resInA = resInA; }
+  for (int task = tid; task < N; task += kSolveThreads) {                  // bA
+    double acc = 0;
+    if (task < kCP) { for (int k = 0; k < nF2; k++) { if (H->accTopNum[k] == 0) continue; acc += (double)H->accTop[k*kNTop + 55 + task]; }
+      acc += H->calib.cPrior[task]*(double)H->calib.cDeltaF[task]; }
+    else { const int a = (task-kCP)/6, r = (task-kCP)%6;
+      for (int k = 0; k < nF2; k++) { const int h = k % nF, t = k / nF; if (a != h && a != t) continue; if (H->accTopNum[k] == 0) continue;
+        const float* m = H->accTop + k*kNTop;
+        if (a == h) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*(double)m[55+4+q]; acc += s1; }
+        if (a == t) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*(double)m[55+4+q]; acc += s2; } }
+      acc += H->frames[a].prior[r]*H->frames[a].delta_prior[r]; }
+    sbA[task] = acc;
+  }
   __syncthreads();
-  for (int h = 0; h < nF; h++) { const int hIdx = kCP + h*6; if (tid < 24) { int r = tid/6, c = tid%6; Hsc[r*N + hIdx+c] = Hsc[(hIdx+c)*N + r]; } }
+  // symmetrise (AccumulatedTopHessian.h:100-113): calib row-blocks = transposed column-blocks; (h,t) += (t,h)^T for t>h, then mirror
+  for (int task = tid; task < nF*24; task += kSolveThreads) { const int a = task/24, r = (task%24)/6, c = task%6; sA[r*N + kCP+a*6+c] = sA[(kCP+a*6+c)*N + r]; }
+  for (int task = tid; task < nF2*36; task += kSolveThreads) { const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, r = e/6, c = e%6;
+    if (b > a) sA[(kCP+a*6+r)*N + kCP+b*6+c] += sA[(kCP+b*6+c)*N + kCP+a*6+r]; }
   __syncthreads();
-  // ---- HFinal / bFinal, damping, diagonal pre-scaling (EnergyFunctional.cpp:668-744)
+  for (int task = tid; task < nF2*36; task += kSolveThreads) { const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, r = e/6, c = e%6;
+    if (b > a) sA[(kCP+b*6+r)*N + kCP+a*6+c] = sA[(kCP+a*6+c)*N + kCP+b*6+r]; }
+  // ---- Schur complement: frame-frame blocks
+  for (int task = tid; task < nF2*36; task += kSolveThreads) {
+    const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
+    for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+      const double* AHij = H->adHost + k*36; const double* ATij = H->adTarget + k*36;
+      for (int k2 = 0; k2 < nF; k2++) {
+        const bool c1 = (a == fi && b == fi), c2 = (a == fj && b == k2), c3 = (a == fj && b == fi), c4 = (a == fi && b == k2);
+        if (!(c1 || c2 || c3 || c4)) continue;
+        const int bk = k + k2*nF2; if (H->accDNum[bk] == 0) continue;
+        const float* d = H->accD + bk*36; const int ik = fi + nF*k2;
+        const double* AHik = H->adHost + ik*36; const double* ATik = H->adTarget + ik*36;
+        auto M = [&](int p, int q) { return (double)d[p*6+q]; };
+        if (c1) acc += triple66(AHij, AHik, i, j, M);
+        if (c2) acc += triple66(ATij, ATik, i, j, M);
+        if (c3) acc += triple66(ATij, AHik, i, j, M);
+        if (c4) acc += triple66(AHij, ATik, i, j, M);
+      } }
+    sS[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
+  }
+  for (int task = tid; task < nF*24; task += kSolveThreads) {              // Hsc[frame a, calib]
+    const int a = task/24, r = (task%24)/4, c = task%4; double acc = 0;
+    for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+      if (a == fi) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*(double)H->accE[k*24+q*4+c]; acc += s1; }
+      if (a == fj) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*(double)H->accE[k*24+q*4+c]; acc += s2; } }
+    sS[(kCP+a*6+r)*N + c] = acc;
+  }
+  if (tid < 16) sS[(tid/4)*N + tid%4] = (double)H->accHcc[tid];
+  for (int task = tid; task < N; task += kSolveThreads) {                  // bsc
+    double acc = 0;
+    if (task < kCP) acc = (double)H->accbc[task];
+    else { const int a = (task-kCP)/6, r = (task-kCP)%6;
+      for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+        if (a == fi) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*(double)H->accEB[k*6+q]; acc += s1; }
+        if (a == fj) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*(double)H->accEB[k*6+q]; acc += s2; } } }
+    sbS[task] = acc;
+  }
+  __syncthreads();
+  for (int task = tid; task < nF*24; task += kSolveThreads) { const int a = task/24, r = (task%24)/6, c = task%6; sS[r*N + kCP+a*6+c] = sS[(kCP+a*6+c)*N + r]; }
+  __syncthreads();
+  // ---- publish HA/bA/Hsc/bsc (read-back for tests), HFinal / bFinal, damping, diagonal pre-scaling (EnergyFunctional.cpp:668-744)
+  for (int i = tid; i < N*N; i += kSolveThreads) { H->HA[i] = sA[i]; H->Hsc[i] = sS[i]; double v = sA[i] + H->HM[i] - sS[i]; H->lastHS[i] = v; sA[i] = v; }
   if (tid < N) {
+    H->bA[tid] = sbA[tid]; H->bsc[tid] = sbS[tid];
     double s = 0; for (int j=0;j<N;j++) { double dj = (j < 4) ? (double)H->calib.cDeltaF[j] : H->frames[(j-4)/6].delta[(j-4)%6]; s += H->HM[tid*N+j]*dj; }
-    double bf = H->bA[tid] + (H->bM[tid] + s) - H->bsc[tid]; H->lastbS[tid] = bf; sb[tid] = bf;
+    double bf = sbA[tid] + (H->bM[tid] + s) - sbS[tid]; H->lastbS[tid] = bf; sb[tid] = bf;
   }
-  for (int i = tid; i < N*N; i += kSolveThreads) { double v = HA[i] + H->HM[i] - Hsc[i]; H->lastHS[i] = v; sA[i] = v; }
   __syncthreads();
   if (tid < N) { sA[tid*N+tid] *= (1+lambda); }
   __syncthreads();
@@ -583,29 +616,51 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
     for (int i=0;i<N;i++) sx[i] = sv[i]*sx[i];
   }
   __syncthreads();
-  // ---- orthogonalize x against the pose+scale nullspaces for iteration >= 2 (EnergyFunctional.cpp:615-648, 746-750)
+  // ---- orthogonalize x against the pose+scale nullspaces for iteration >= 2 (EnergyFunctional.cpp:615-648, 746-750).  The basis only
+  // depends on the evaluation points, so it is computed once per linearisation point (one-sided Jacobi, same operation order as the
+  // oracle: each dot product by one thread, row updates in parallel) and cached in the header.
   if (iteration >= 2) {
-    const int m = 7; double* A = sA;                                        // reuse: N x 7 column-major-by-column in sA
-    for (int e = tid; e < N*m; e += kSolveThreads) { int r = e % N, i = e / N; double v = 0;
-      if (r >= kCP) { int f = (r-kCP)/6, q = (r-kCP)%6; v = (i < 6) ? H->frames[f].nullspaces_pose[q*6+i] : H->frames[f].nullspaces_scale[q]; v *= (q < 3) ? (double)(1.0f/0.5f) : (double)(1.0f/1.0f); }
-      A[i*N + r] = v; }
-    __syncthreads();
-    if (tid < m) { double nr = 0; for (int r=0;r<N;r++) nr += A[tid*N+r]*A[tid*N+r]; nr = sqrt(nr); for (int r=0;r<N;r++) A[tid*N+r] /= nr; }
-    __syncthreads();
-    if (tid == 0) {                                                         // one-sided Jacobi (Hestenes); 7 columns, tiny
-      for (int sweep = 0; sweep < 60; sweep++) { double off = 0;
+    const int m = 7; double* A = sS;                                        // N x 7, column i at A[i*N ..]
+    if (!H->ortho_valid) {
+      for (int e = tid; e < N*m; e += kSolveThreads) { int r = e % N, i = e / N; double v = 0;
+        if (r >= kCP) { int f = (r-kCP)/6, q = (r-kCP)%6; v = (i < 6) ? H->frames[f].nullspaces_pose[q*6+i] : H->frames[f].nullspaces_scale[q]; v *= (q < 3) ? (double)(1.0f/0.5f) : (double)(1.0f/1.0f); }
+        A[i*N + r] = v; }
+      __syncthreads();
+      if (tid < m) { double nr = 0; for (int r=0;r<N;r++) nr += A[tid*N+r]*A[tid*N+r]; nr = sqrt(nr); for (int r=0;r<N;r++) A[tid*N+r] /= nr; }
+      __syncthreads();
+      for (int sweep = 0; sweep < 60; sweep++) {
+        if (tid == 0) srot[3] = 0;
         for (int p=0;p<m;p++) for (int q=p+1;q<m;q++) {
-          double al = 0, be = 0, ga = 0; for (int r=0;r<N;r++) { double ap = A[p*N+r], aq = A[q*N+r]; al += ap*ap; be += aq*aq; ga += ap*aq; }
+          __syncthreads();
+          if (tid == 0) { double al = 0; for (int r=0;r<N;r++) al += A[p*N+r]*A[p*N+r]; srot[0] = al; }
+          else if (tid == 32) { double be = 0; for (int r=0;r<N;r++) be += A[q*N+r]*A[q*N+r]; srot[1] = be; }
+          else if (tid == 64) { double ga = 0; for (int r=0;r<N;r++) ga += A[p*N+r]*A[q*N+r]; srot[2] = ga; }
+          __syncthreads();
+          const double al = srot[0], be = srot[1], ga = srot[2];
           if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17*sqrt(al*be)) continue;
-          off = fmax(off, fabs(ga)/sqrt(al*be + 1e-300));
-          double zeta = (be-al)/(2*ga), tt = ((zeta >= 0) ? 1.0 : -1.0)/(fabs(zeta) + sqrt(1+zeta*zeta)), c = 1/sqrt(1+tt*tt), s = c*tt;
-          for (int r=0;r<N;r++) { double ap = A[p*N+r], aq = A[q*N+r]; A[p*N+r] = c*ap - s*aq; A[q*N+r] = s*ap + c*aq; } }
-        if (off < 1e-15) break; }
-      double svals[7], maxSv = 0; for (int i=0;i<m;i++) { double nr = 0; for (int r=0;r<N;r++) nr += A[i*N+r]*A[i*N+r]; svals[i] = sqrt(nr); maxSv = fmax(maxSv, svals[i]); }
+          if (tid == 0) srot[3] = fmax(srot[3], fabs(ga)/sqrt(al*be + 1e-300));
+          const double zeta = (be-al)/(2*ga), tt = ((zeta >= 0) ? 1.0 : -1.0)/(fabs(zeta) + sqrt(1+zeta*zeta)), c = 1/sqrt(1+tt*tt), sn = c*tt;
+          if (tid < N) { double ap = A[p*N+tid], aq = A[q*N+tid]; A[p*N+tid] = c*ap - sn*aq; A[q*N+tid] = sn*ap + c*aq; }
+        }
+        __syncthreads();
+        if (srot[3] < 1e-15) break;
+        __syncthreads();
+      }
+      __syncthreads();
+      if (tid < m) { double nr = 0; for (int r=0;r<N;r++) nr += A[tid*N+r]*A[tid*N+r]; H->orthoS[tid] = sqrt(nr); }
+      for (int e = tid; e < N*m; e += kSolveThreads) H->orthoU[e] = A[e];
+      __syncthreads();
+      if (tid == 0) H->ortho_valid = 1;
+    } else {
+      for (int e = tid; e < N*m; e += kSolveThreads) A[e] = H->orthoU[e];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      double maxSv = 0; for (int i=0;i<m;i++) maxSv = fmax(maxSv, H->orthoS[i]);
       for (int r=0;r<N;r++) stmp[r] = 0;
-      for (int i=0;i<m;i++) { if (!(svals[i] > H->set.solverModeDelta*maxSv)) continue;
-        double dot = 0; for (int r=0;r<N;r++) dot += (A[i*N+r]/svals[i])*sx[r];
-        for (int r=0;r<N;r++) stmp[r] += (A[i*N+r]/svals[i])*dot; }
+      for (int i=0;i<m;i++) { const double svi = H->orthoS[i]; if (!(svi > H->set.solverModeDelta*maxSv)) continue;
+        double dot = 0; for (int r=0;r<N;r++) dot += (A[i*N+r]/svi)*sx[r];
+        for (int r=0;r<N;r++) stmp[r] += (A[i*N+r]/svi)*dot; }
       for (int r=0;r<N;r++) sx[r] -= stmp[r];
     }
     __syncthreads();
@@ -614,12 +669,10 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   if (tid < N) { H->lastX[tid] = sx[tid]; H->xF[tid] = (float)sx[tid]; }
   if (tid < 4) H->calib.step[tid] = -sx[tid];
   if (tid >= 32 && tid < 32 + nF) { BAFrameDev& f = H->frames[tid-32]; for (int i=0;i<6;i++) f.step[i] = -sx[kCP + 6*(tid-32) + i]; for (int i=6;i<10;i++) f.step[i] = 0; }
-  if (tid == 0) H->resInA = resInA;
   __syncthreads();
   for (int e = tid; e < nF2*6; e += kSolveThreads) { int pr = e/6, j = e%6, h = pr / nF, t = pr % nF;       // xAd[nF*h + t]
-    float s1 = 0, s2 = 0; for (int i=0;i<6;i++) { s1 += H->xF[kCP+6*h+i]*H->adHostF[(h+nF*t)*36+i*6+j]; s2 += H->xF[kCP+6*t+i]*H->adTargetF[(h+nF*t)*36+i*6+j]; }
+    float s1 = 0, s2 = 0; for (int i=0;i<6;i++) { s1 += (float)sx[kCP+6*h+i]*H->adHostF[(h+nF*t)*36+i*6+j]; s2 += (float)sx[kCP+6*t+i]*H->adTargetF[(h+nF*t)*36+i*6+j]; }
     H->xAd[(nF*h+t)*6+j] = s1 + s2; }
-  (void)sred;
 }
 
 __global__ void ba_resub_kernel(const BAWinDev* __restrict__ wins, int gate) {     // resubstituteFPt (:250-282)
@@ -704,7 +757,7 @@ void launch_ba_energies(const BAWinDev* wins, int W, int gate, cudaStream_t st) 
 void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) {
   ba_point_acc_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate);
   ba_acc_top_kernel<<<dim3(kMaxF*kMaxF, W), 96, 0, st>>>(wins, gate);
-  ba_acc_sc_kernel<<<dim3(kMaxF, W), 256, 0, st>>>(wins, gate);
+  ba_acc_sc_kernel<<<dim3(kMaxF*kMaxF, W), 320, 0, st>>>(wins, gate);
 }
 void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, double lambda, int use_hdr_ctl, int gate, cudaStream_t st) {
   ba_solve_kernel<<<dim3(1, W), kSolveThreads, 0, st>>>(wins, iteration, lambda, use_hdr_ctl, gate);
