@@ -58,6 +58,8 @@ struct BAHeader {                        // one per window, lives in device memo
   float rmse;
   // cached orthonormal basis of the pose+scale nullspaces (valid while the evaluation points do not change)
   int ortho_valid; double orthoU[7*kMaxDim]; double orthoS[7];
+  // stitch scratch: AH*M and AT*M per top bucket, AH_ij*D and AT_ij*D per Schur bucket (fp64, reference operation order)
+  double topT1[kMaxF*kMaxF*36], topT3[kMaxF*kMaxF*36], scT1[kMaxF*kMaxF*kMaxF*36], scT3[kMaxF*kMaxF*kMaxF*36];
 };
 enum { BA_ACTIVE = 1, BA_APPLY = 2, BA_RELOAD = 4 };
 enum { GATE_ALWAYS = 0, GATE_ACTIVE = 1, GATE_APPLY = 2, GATE_RELOAD = 4 };

@@ -405,55 +405,84 @@ __global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restri
   if (e == 0) H->accTopNum[pair] = num;
 }
 
-// one CTA per (host, t1): cells accD[(h,t1,t2)][6x6] for all t2, accE[(h,t1)][6x4], accEB[(h,t1)][6]; the rows of the host's points
-// (activity, JpJdF per target, HdiF, bdSumF, Hcd) are staged through shared memory 32 points at a time.  CTA (0,0) also owns
-// accHcc/accbc, which run over all points.
+// one CTA per host frame, 96 threads: threads 0..35 own cell (i,j) of EVERY accD[(h,t1,t2)] bucket of this host, threads 36..59 cell
+// (i,c) of every accE[(h,t1)], threads 60..65 cell i of every accEB[(h,t1)] — the accumulators live in shared memory.  The CTA walks
+// the host's points in order and, per point, only its ACTIVE residual pairs (r1,r2), exactly the loops of AccumulatedSCHessian.cpp:46-61,
+// so no bucket is ever visited for a point that does not touch it.  Float sums, their order and the 1k/1M tiers match the CPU path.
 constexpr int kScChunk = 32;
-__global__ void __launch_bounds__(320) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
+__global__ void __launch_bounds__(96) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
   BA_WIN(gate)
-  const int nF = H->nF; const int nF2 = nF*nF;
-  const int h = blockIdx.x % kMaxF, t1 = blockIdx.x / kMaxF;
-  if (h >= nF || t1 >= nF) return;
+  const int nF = H->nF; const int nF2 = nF*nF; const int h = blockIdx.x;
+  if (h >= nF) return;
   const int p0 = R.host_begin[h], p1 = R.host_begin[h+1];
-  __shared__ float sJ[kScChunk][kMaxF][6]; __shared__ int sAct[kScChunk][kMaxF]; __shared__ float sHdi[kScChunk], sBd[kScChunk], sHcd[kScChunk][4]; __shared__ int sUse[kScChunk];
-  const int nD = nF*36, nE = 24, nEB = 6; const int e = threadIdx.x; const bool mine = e < nD + nE + nEB;
-  int kind = 0, t2 = 0, i = 0, j = 0;
-  if (e < nD) { kind = 0; t2 = e/36; i = (e%36)/6; j = e%6; }
-  else if (e < nD + nE) { kind = 1; int q = e - nD; i = q/4; j = q%4; }
-  else { kind = 2; i = e - nD - nE; }
-  Tier t = {0,0,0,0,0}; int num = 0;
-  if (h != t1) for (int base = p0; base < p1; base += kScChunk) {
+  const int e = threadIdx.x;
+  __shared__ float sD[kMaxF*kMaxF*36], sD1k[kMaxF*kMaxF*36], sD1m[kMaxF*kMaxF*36];      // [t1*nF+t2][i*6+j]
+  __shared__ float sE[kMaxF*24], sE1k[kMaxF*24], sE1m[kMaxF*24], sEB[kMaxF*6], sEB1k[kMaxF*6], sEB1m[kMaxF*6];
+  // per-CELL update counters (each cell thread keeps its own, identical, count: no cross-thread dependency for the tier shifts)
+  __shared__ unsigned short cD[kMaxF*kMaxF*36], cD1k[kMaxF*kMaxF*36], cE[kMaxF*30], cE1k[kMaxF*30]; __shared__ int sNum[kMaxF*kMaxF];
+  __shared__ float sJ[kScChunk][kMaxF][6]; __shared__ int sMask[kScChunk]; __shared__ float sHdi[kScChunk], sBd[kScChunk], sHcd[kScChunk][4];
+  for (int k = e; k < nF2*36; k += 96) { sD[k] = 0; sD1k[k] = 0; sD1m[k] = 0; cD[k] = 0; cD1k[k] = 0; }
+  for (int k = e; k < nF*24; k += 96) { sE[k] = 0; sE1k[k] = 0; sE1m[k] = 0; }
+  for (int k = e; k < nF*6; k += 96) { sEB[k] = 0; sEB1k[k] = 0; sEB1m[k] = 0; }
+  for (int k = e; k < nF2; k += 96) sNum[k] = 0;
+  for (int k = e; k < nF*30; k += 96) { cE[k] = 0; cE1k[k] = 0; }
+  const int ci = (e < 36) ? e/6 : ((e < 60) ? (e-36)/4 : e-60), cj = (e < 36) ? e%6 : ((e < 60) ? (e-36)%4 : 0);
+  for (int base = p0; base < p1; base += kScChunk) {
     const int cnt = min(kScChunk, p1 - base);
     __syncthreads();
-    for (int k = threadIdx.x; k < cnt*nF; k += blockDim.x) { int q = k / nF, tt = k - q*nF; int p = base + q;
-      int r = P.res_of_target[(size_t)p*kMaxF + tt]; int act = (r >= 0) ? R.isActive[r] : 0; sAct[q][tt] = act;
-      if (act) { for (int c=0;c<6;c++) sJ[q][tt][c] = R.JpJdF[(size_t)r*8+c]; } }
-    if (threadIdx.x < cnt) { int p = base + threadIdx.x; sUse[threadIdx.x] = (P.ngood[p] != 0 && !P.isFromSensor[p]) ? 1 : 0; sHdi[threadIdx.x] = P.HdiF[p]; sBd[threadIdx.x] = P.bdSumF[p];
-      for (int c=0;c<4;c++) sHcd[threadIdx.x][c] = P.Hcd_accAF[(size_t)p*4+c] + 0.0f; }
+    if (e < cnt) { sMask[e] = 0; }
     __syncthreads();
-    if (mine) for (int q = 0; q < cnt; q++) {
-      if (!sUse[q] || !sAct[q][t1]) continue;
-      const float Hdi = sHdi[q]; const float wl = Hdi*sJ[q][t1][i];
-      if (kind == 0) { if (!sAct[q][t2]) continue; t.d += wl*sJ[q][t2][j]; }       // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
-      else if (kind == 1) t.d += wl*sHcd[q][j];                                     // accE.update(r1->JpJdF, Hcd, HdiF)
-      else t.d += (Hdi*sBd[q])*sJ[q][t1][i];                                        // accEB.update(r1->JpJdF, HdiF*bdSumF)
-      num++; t.n1 += 1; tier_shift(t);
+    for (int k = e; k < cnt*nF; k += 96) { int q = k / nF, tt = k - q*nF; int p = base + q;
+      int r = P.res_of_target[(size_t)p*kMaxF + tt]; int act = (r >= 0) ? R.isActive[r] : 0;
+      if (act) { atomicOr(&sMask[q], 1 << tt); for (int c=0;c<6;c++) sJ[q][tt][c] = R.JpJdF[(size_t)r*8+c]; } }
+    if (e < cnt) { int p = base + e; sHdi[e] = P.HdiF[p]; sBd[e] = P.bdSumF[p];
+      for (int c=0;c<4;c++) sHcd[e][c] = P.Hcd_accAF[(size_t)p*4+c] + 0.0f; }
+    __syncthreads();
+    if (e < cnt) { int p = base + e; if (P.ngood[p] == 0 || P.isFromSensor[p]) sMask[e] = 0; }   // such points never reach the accumulators
+    __syncthreads();
+    for (int q = 0; q < cnt; q++) {
+      const int mask = sMask[q]; if (mask == 0) continue;
+      const float Hdi = sHdi[q];
+      for (int t1 = 0; t1 < nF; t1++) { if (!((mask >> t1) & 1)) continue;      // residualsAll order == target order is NOT required: every (r1,r2) hits its own bucket once
+        if (e < 36) {
+          const float wl = Hdi*sJ[q][t1][ci];
+          for (int t2 = 0; t2 < nF; t2++) { if (!((mask >> t2) & 1)) continue;
+            const int bk = t1*nF + t2;
+            sD[bk*36 + e] += wl*sJ[q][t2][cj];                                   // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
+            if (e == 0) sNum[bk]++;
+            if (++cD[bk*36 + e] > 1000) {                                        // tier shift (MatrixAccumulators.h:49-65)
+              sD1k[bk*36 + e] += sD[bk*36 + e]; sD[bk*36 + e] = 0; cD1k[bk*36 + e] += cD[bk*36 + e]; cD[bk*36 + e] = 0;
+              if (cD1k[bk*36 + e] > 1000) { sD1m[bk*36 + e] += sD1k[bk*36 + e]; sD1k[bk*36 + e] = 0; cD1k[bk*36 + e] = 0; } }
+          }
+        } else if (e < 66) {
+          const int ce = t1*30 + (e-36);
+          if (e < 60) sE[t1*24 + (e-36)] += (Hdi*sJ[q][t1][ci])*sHcd[q][cj];     // accE.update(r1->JpJdF, Hcd, HdiF)
+          else sEB[t1*6 + (e-60)] += (Hdi*sBd[q])*sJ[q][t1][ci];                 // accEB.update(r1->JpJdF, HdiF*bdSumF)
+          if (++cE[ce] > 1000) {
+            if (e < 60) { sE1k[t1*24 + (e-36)] += sE[t1*24 + (e-36)]; sE[t1*24 + (e-36)] = 0; } else { sEB1k[t1*6 + (e-60)] += sEB[t1*6 + (e-60)]; sEB[t1*6 + (e-60)] = 0; }
+            cE1k[ce] += cE[ce]; cE[ce] = 0;
+            if (cE1k[ce] > 1000) { if (e < 60) { sE1m[t1*24 + (e-36)] += sE1k[t1*24 + (e-36)]; sE1k[t1*24 + (e-36)] = 0; } else { sEB1m[t1*6 + (e-60)] += sEB1k[t1*6 + (e-60)]; sEB1k[t1*6 + (e-60)] = 0; } cE1k[ce] = 0; } }
+        }
+        __syncwarp();
+      }
     }
   }
-  if (mine) { float v = tier_finish(t);
-    if (kind == 0) { int b = h + nF*t1 + nF2*t2; H->accD[b*36 + i*6 + j] = v; if (i == 0 && j == 0) H->accDNum[b] = num; }
-    else if (kind == 1) H->accE[(h + nF*t1)*24 + i*4 + j] = v;
-    else H->accEB[(h + nF*t1)*6 + i] = v; }
-  if (blockIdx.x == 0 && threadIdx.x < 20) {
-    const int e2 = threadIdx.x; Tier tt = {0,0,0,0,0};
+  __syncthreads();
+  // finish(): shiftUp(true)  ->  A1k += A ; A1m += A1k
+  for (int k = e; k < nF2*36; k += 96) { const int bk = k/36, t1 = bk / nF, t2 = bk % nF; float v1k = sD1k[k] + sD[k]; float v = sD1m[k] + v1k;
+    const int b = h + nF*t1 + nF2*t2; H->accD[b*36 + k%36] = v; if (k%36 == 0) H->accDNum[b] = sNum[bk]; }
+  for (int k = e; k < nF*24; k += 96) { const int t1 = k/24; float v1k = sE1k[k] + sE[k]; H->accE[(h + nF*t1)*24 + k%24] = sE1m[k] + v1k; }
+  for (int k = e; k < nF*6; k += 96) { const int t1 = k/6; float v1k = sEB1k[k] + sEB[k]; H->accEB[(h + nF*t1)*6 + k%6] = sEB1m[k] + v1k; }
+  if (h == 0 && e < 20) {
+    Tier tt = {0,0,0,0,0};
     for (int p = 0; p < nP; p++) {
       if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
       const float Hdi = P.HdiF[p];
-      if (e2 < 16) tt.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e2/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e2%4] + 0.0f);
-      else tt.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e2-16] + 0.0f);
+      if (e < 16) tt.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e%4] + 0.0f);
+      else tt.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e-16] + 0.0f);
       tt.n1 += 1; tier_shift(tt);
     }
-    float v = tier_finish(tt); if (e2 < 16) H->accHcc[e2] = v; else H->accbc[e2-16] = v;
+    float v = tier_finish(tt); if (e < 16) H->accHcc[e] = v; else H->accbc[e-16] = v;
   }
 }
 
@@ -473,7 +502,7 @@ template <typename MF> __device__ __forceinline__ double triple66(const double* 
   return s;
 }
 
-constexpr int kSolveThreads = 256;
+constexpr int kSolveThreads = 512;
 __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev* __restrict__ wins, int iteration_arg, double lambda_arg, int use_hdr_ctl, int gate) {
   BA_WIN(gate)
   const int iteration = use_hdr_ctl ? H->iteration : iteration_arg; const double lambda = use_hdr_ctl ? H->lambda : lambda_arg;
@@ -482,17 +511,30 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   __shared__ double sS[kMaxDim*kMaxDim];                                    // Hsc -> nullspace basis
   __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim], sbA[kMaxDim], sbS[kMaxDim];
   __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double srot[4];
+  // ---- products shared by many output elements, in the reference's operation order: T1 = AH*M, T3 = AT*M (top buckets), AH_ij*D, AT_ij*D (Schur buckets)
+  for (int task = tid; task < nF2*72; task += kSolveThreads) {
+    const int k = task/72, e = task%72, which = e/36, i = (e%36)/6, q = e%6; if (H->accTopNum[k] == 0) continue;
+    const float* m = H->accTop + k*kNTop; const double* A1 = (which ? H->adTarget : H->adHost) + k*36;
+    double t = 0; for (int p = 0; p < 6; p++) t += A1[i*6+p]*tri10(m, 4+p, 4+q);
+    (which ? H->topT3 : H->topT1)[k*36 + i*6 + q] = t;
+  }
+  for (int task = tid; task < nF2*nF*72; task += kSolveThreads) {
+    const int bk = task/72, e = task%72, which = e/36, i = (e%36)/6, q = e%6; if (H->accDNum[bk] == 0) continue;
+    const int k = bk % nF2; const float* d = H->accD + bk*36; const double* A1 = (which ? H->adTarget : H->adHost) + k*36;
+    double t = 0; for (int p = 0; p < 6; p++) t += A1[i*6+p]*(double)d[p*6+q];
+    (which ? H->scT3 : H->scT1)[bk*36 + i*6 + q] = t;
+  }
+  __syncthreads();
   // ---- top: frame-frame blocks (raw), frame-calib blocks, calib block, gradient
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
     for (int k = 0; k < nF2; k++) {
       const int h = k % nF, t = k / nF; if (!((a == h || a == t) && (b == h || b == t))) continue;
       if (H->accTopNum[k] == 0) continue;                                  // empty bucket contributes exact zeros
-      const float* m = H->accTop + k*kNTop; const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36;
-      auto M = [&](int p, int q) { return tri10(m, 4+p, 4+q); };
-      if (a == h && b == h) acc += triple66(AH, AH, i, j, M);
-      if (a == t && b == t) acc += triple66(AT, AT, i, j, M);
-      if (a == h && b == t) acc += triple66(AH, AT, i, j, M);
+      const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36; const double* T1 = H->topT1 + k*36 + i*6; const double* T3 = H->topT3 + k*36 + i*6;
+      if (a == h && b == h) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AH[j*6+q]; acc += s2; }
+      if (a == t && b == t) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*AT[j*6+q]; acc += s2; }
+      if (a == h && b == t) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AT[j*6+q]; acc += s2; }
     }
     if (a == b && i == j) acc += H->frames[a].prior[i];
     sA[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
@@ -533,18 +575,17 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
     for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
-      const double* AHij = H->adHost + k*36; const double* ATij = H->adTarget + k*36;
       for (int k2 = 0; k2 < nF; k2++) {
         const bool c1 = (a == fi && b == fi), c2 = (a == fj && b == k2), c3 = (a == fj && b == fi), c4 = (a == fi && b == k2);
         if (!(c1 || c2 || c3 || c4)) continue;
         const int bk = k + k2*nF2; if (H->accDNum[bk] == 0) continue;
-        const float* d = H->accD + bk*36; const int ik = fi + nF*k2;
-        const double* AHik = H->adHost + ik*36; const double* ATik = H->adTarget + ik*36;
-        auto M = [&](int p, int q) { return (double)d[p*6+q]; };
-        if (c1) acc += triple66(AHij, AHik, i, j, M);
-        if (c2) acc += triple66(ATij, ATik, i, j, M);
-        if (c3) acc += triple66(ATij, AHik, i, j, M);
-        if (c4) acc += triple66(AHij, ATik, i, j, M);
+        const int ik = fi + nF*k2;
+        const double* AHik = H->adHost + ik*36 + j*6; const double* ATik = H->adTarget + ik*36 + j*6;
+        const double* T1 = H->scT1 + bk*36 + i*6; const double* T3 = H->scT3 + bk*36 + i*6;
+        if (c1) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AHik[q]; acc += s2; }
+        if (c2) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*ATik[q]; acc += s2; }
+        if (c3) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*AHik[q]; acc += s2; }
+        if (c4) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*ATik[q]; acc += s2; }
       } }
     sS[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
   }
@@ -757,7 +798,7 @@ void launch_ba_energies(const BAWinDev* wins, int W, int gate, cudaStream_t st) 
 void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) {
   ba_point_acc_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate);
   ba_acc_top_kernel<<<dim3(kMaxF*kMaxF, W), 96, 0, st>>>(wins, gate);
-  ba_acc_sc_kernel<<<dim3(kMaxF*kMaxF, W), 320, 0, st>>>(wins, gate);
+  ba_acc_sc_kernel<<<dim3(kMaxF, W), 96, 0, st>>>(wins, gate);
 }
 void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, double lambda, int use_hdr_ctl, int gate, cudaStream_t st) {
   ba_solve_kernel<<<dim3(1, W), kSolveThreads, 0, st>>>(wins, iteration, lambda, use_hdr_ctl, gate);
