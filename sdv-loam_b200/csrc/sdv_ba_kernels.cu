@@ -405,10 +405,10 @@ __global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restri
   if (e == 0) H->accTopNum[pair] = num;
 }
 
-// one CTA per host frame, 96 threads: threads 0..35 own cell (i,j) of EVERY accD[(h,t1,t2)] bucket of this host, threads 36..59 cell
-// (i,c) of every accE[(h,t1)], threads 60..65 cell i of every accEB[(h,t1)] — the accumulators live in shared memory.  The CTA walks
-// the host's points in order and, per point, only its ACTIVE residual pairs (r1,r2), exactly the loops of AccumulatedSCHessian.cpp:46-61,
-// so no bucket is ever visited for a point that does not touch it.  Float sums, their order and the 1k/1M tiers match the CPU path.
+// one CTA per host frame: thread (t1,t2) owns the whole 6x6 accD[(h,t1,t2)] bucket in registers, thread nF^2+t1 owns accE[(h,t1)] (6x4)
+// and accEB[(h,t1)] (6).  The host's points are staged through shared memory 32 at a time (activity mask over targets, JpJdF per
+// target, HdiF, bdSumF, Hcd) and walked in order; a bucket is touched only by the points whose residuals towards t1 and t2 are active,
+// i.e. exactly the (r1,r2) loops of AccumulatedSCHessian.cpp:46-61.  Float sums, their order and the 1k/1M tiers match the CPU path.
 constexpr int kScChunk = 32;
 __global__ void __launch_bounds__(96) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
   BA_WIN(gate)
@@ -416,21 +416,16 @@ __global__ void __launch_bounds__(96) ba_acc_sc_kernel(const BAWinDev* __restric
   if (h >= nF) return;
   const int p0 = R.host_begin[h], p1 = R.host_begin[h+1];
   const int e = threadIdx.x;
-  __shared__ float sD[kMaxF*kMaxF*36], sD1k[kMaxF*kMaxF*36], sD1m[kMaxF*kMaxF*36];      // [t1*nF+t2][i*6+j]
-  __shared__ float sE[kMaxF*24], sE1k[kMaxF*24], sE1m[kMaxF*24], sEB[kMaxF*6], sEB1k[kMaxF*6], sEB1m[kMaxF*6];
-  // per-CELL update counters (each cell thread keeps its own, identical, count: no cross-thread dependency for the tier shifts)
-  __shared__ unsigned short cD[kMaxF*kMaxF*36], cD1k[kMaxF*kMaxF*36], cE[kMaxF*30], cE1k[kMaxF*30]; __shared__ int sNum[kMaxF*kMaxF];
+  const int role = (e < nF2) ? 0 : ((e < nF2 + nF) ? 1 : 2);
+  const int t1 = (role == 0) ? e / nF : ((role == 1) ? e - nF2 : 0), t2 = (role == 0) ? e % nF : 0;
   __shared__ float sJ[kScChunk][kMaxF][6]; __shared__ int sMask[kScChunk]; __shared__ float sHdi[kScChunk], sBd[kScChunk], sHcd[kScChunk][4];
-  for (int k = e; k < nF2*36; k += 96) { sD[k] = 0; sD1k[k] = 0; sD1m[k] = 0; cD[k] = 0; cD1k[k] = 0; }
-  for (int k = e; k < nF*24; k += 96) { sE[k] = 0; sE1k[k] = 0; sE1m[k] = 0; }
-  for (int k = e; k < nF*6; k += 96) { sEB[k] = 0; sEB1k[k] = 0; sEB1m[k] = 0; }
-  for (int k = e; k < nF2; k += 96) sNum[k] = 0;
-  for (int k = e; k < nF*30; k += 96) { cE[k] = 0; cE1k[k] = 0; }
-  const int ci = (e < 36) ? e/6 : ((e < 60) ? (e-36)/4 : e-60), cj = (e < 36) ? e%6 : ((e < 60) ? (e-36)%4 : 0);
+  float d[36], d1k[36], d1m[36]; float n1 = 0, n1k = 0; int num = 0;
+#pragma unroll
+  for (int k = 0; k < 36; k++) { d[k] = 0; d1k[k] = 0; d1m[k] = 0; }
   for (int base = p0; base < p1; base += kScChunk) {
     const int cnt = min(kScChunk, p1 - base);
     __syncthreads();
-    if (e < cnt) { sMask[e] = 0; }
+    if (e < cnt) sMask[e] = 0;
     __syncthreads();
     for (int k = e; k < cnt*nF; k += 96) { int q = k / nF, tt = k - q*nF; int p = base + q;
       int r = P.res_of_target[(size_t)p*kMaxF + tt]; int act = (r >= 0) ? R.isActive[r] : 0;
@@ -442,47 +437,56 @@ __global__ void __launch_bounds__(96) ba_acc_sc_kernel(const BAWinDev* __restric
     __syncthreads();
     for (int q = 0; q < cnt; q++) {
       const int mask = sMask[q]; if (mask == 0) continue;
-      const float Hdi = sHdi[q];
-      for (int t1 = 0; t1 < nF; t1++) { if (!((mask >> t1) & 1)) continue;      // residualsAll order == target order is NOT required: every (r1,r2) hits its own bucket once
-        if (e < 36) {
-          const float wl = Hdi*sJ[q][t1][ci];
-          for (int t2 = 0; t2 < nF; t2++) { if (!((mask >> t2) & 1)) continue;
-            const int bk = t1*nF + t2;
-            sD[bk*36 + e] += wl*sJ[q][t2][cj];                                   // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
-            if (e == 0) sNum[bk]++;
-            if (++cD[bk*36 + e] > 1000) {                                        // tier shift (MatrixAccumulators.h:49-65)
-              sD1k[bk*36 + e] += sD[bk*36 + e]; sD[bk*36 + e] = 0; cD1k[bk*36 + e] += cD[bk*36 + e]; cD[bk*36 + e] = 0;
-              if (cD1k[bk*36 + e] > 1000) { sD1m[bk*36 + e] += sD1k[bk*36 + e]; sD1k[bk*36 + e] = 0; cD1k[bk*36 + e] = 0; } }
-          }
-        } else if (e < 66) {
-          const int ce = t1*30 + (e-36);
-          if (e < 60) sE[t1*24 + (e-36)] += (Hdi*sJ[q][t1][ci])*sHcd[q][cj];     // accE.update(r1->JpJdF, Hcd, HdiF)
-          else sEB[t1*6 + (e-60)] += (Hdi*sBd[q])*sJ[q][t1][ci];                 // accEB.update(r1->JpJdF, HdiF*bdSumF)
-          if (++cE[ce] > 1000) {
-            if (e < 60) { sE1k[t1*24 + (e-36)] += sE[t1*24 + (e-36)]; sE[t1*24 + (e-36)] = 0; } else { sEB1k[t1*6 + (e-60)] += sEB[t1*6 + (e-60)]; sEB[t1*6 + (e-60)] = 0; }
-            cE1k[ce] += cE[ce]; cE[ce] = 0;
-            if (cE1k[ce] > 1000) { if (e < 60) { sE1m[t1*24 + (e-36)] += sE1k[t1*24 + (e-36)]; sE1k[t1*24 + (e-36)] = 0; } else { sEB1m[t1*6 + (e-60)] += sEB1k[t1*6 + (e-60)]; sEB1k[t1*6 + (e-60)] = 0; } cE1k[ce] = 0; } }
+      bool upd = false;
+      if (role == 0) {
+        if (((mask >> t1) & 1) && ((mask >> t2) & 1)) { upd = true;
+          const float Hdi = sHdi[q];
+#pragma unroll
+          for (int i = 0; i < 6; i++) { const float wl = Hdi*sJ[q][t1][i];
+#pragma unroll
+            for (int j = 0; j < 6; j++) d[i*6+j] += wl*sJ[q][t2][j]; }            // accD.update(r1->JpJdF, r2->JpJdF, HdiF): A += (w*L)*R^T
         }
-        __syncwarp();
+      } else if (role == 1) {
+        if ((mask >> t1) & 1) { upd = true;
+          const float Hdi = sHdi[q]; const float w2 = Hdi*sBd[q];
+#pragma unroll
+          for (int i = 0; i < 6; i++) { const float wl = Hdi*sJ[q][t1][i];
+#pragma unroll
+            for (int c = 0; c < 4; c++) d[i*4+c] += wl*sHcd[q][c];                // accE.update(r1->JpJdF, Hcd, HdiF)
+            d[24+i] += w2*sJ[q][t1][i]; }                                         // accEB.update(r1->JpJdF, HdiF*bdSumF)
+        }
       }
+      if (upd) { num++; n1 += 1;
+        if (n1 > 1000) {                                                          // tier shift (MatrixAccumulators.h:49-65)
+#pragma unroll
+          for (int k = 0; k < 36; k++) { d1k[k] += d[k]; d[k] = 0; }
+          n1k += n1; n1 = 0;
+          if (n1k > 1000) {
+#pragma unroll
+            for (int k = 0; k < 36; k++) { d1m[k] += d1k[k]; d1k[k] = 0; }
+            n1k = 0; } } }
     }
   }
-  __syncthreads();
   // finish(): shiftUp(true)  ->  A1k += A ; A1m += A1k
-  for (int k = e; k < nF2*36; k += 96) { const int bk = k/36, t1 = bk / nF, t2 = bk % nF; float v1k = sD1k[k] + sD[k]; float v = sD1m[k] + v1k;
-    const int b = h + nF*t1 + nF2*t2; H->accD[b*36 + k%36] = v; if (k%36 == 0) H->accDNum[b] = sNum[bk]; }
-  for (int k = e; k < nF*24; k += 96) { const int t1 = k/24; float v1k = sE1k[k] + sE[k]; H->accE[(h + nF*t1)*24 + k%24] = sE1m[k] + v1k; }
-  for (int k = e; k < nF*6; k += 96) { const int t1 = k/6; float v1k = sEB1k[k] + sEB[k]; H->accEB[(h + nF*t1)*6 + k%6] = sEB1m[k] + v1k; }
-  if (h == 0 && e < 20) {
-    Tier tt = {0,0,0,0,0};
+  if (role == 0) { const int b = h + nF*t1 + nF2*t2;
+#pragma unroll
+    for (int k = 0; k < 36; k++) { float v1k = d1k[k] + d[k]; H->accD[b*36 + k] = d1m[k] + v1k; }
+    H->accDNum[b] = num; }
+  else if (role == 1) {
+#pragma unroll
+    for (int k = 0; k < 24; k++) { float v1k = d1k[k] + d[k]; H->accE[(h + nF*t1)*24 + k] = d1m[k] + v1k; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { float v1k = d1k[24+k] + d[24+k]; H->accEB[(h + nF*t1)*6 + k] = d1m[24+k] + v1k; } }
+  if (h == 0 && e >= 32 && e < 52) {
+    const int e2 = e - 32; Tier tt = {0,0,0,0,0};
     for (int p = 0; p < nP; p++) {
       if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
       const float Hdi = P.HdiF[p];
-      if (e < 16) tt.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e%4] + 0.0f);
-      else tt.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e-16] + 0.0f);
+      if (e2 < 16) tt.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e2/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e2%4] + 0.0f);
+      else tt.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e2-16] + 0.0f);
       tt.n1 += 1; tier_shift(tt);
     }
-    float v = tier_finish(tt); if (e < 16) H->accHcc[e] = v; else H->accbc[e-16] = v;
+    float v = tier_finish(tt); if (e2 < 16) H->accHcc[e2] = v; else H->accbc[e2-16] = v;
   }
 }
 
