@@ -218,8 +218,11 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
     for (int i = 0; i < 5; i++) ctl.lastRes[i] = nan("");
     for (int i = 0; i < 3; i++) ctl.flow[i] = 1000.0;
   }
-  __shared__ long long evals[kLevels]; __shared__ int iters[kLevels], accs[kLevels];   // statistics: shared, touched by thread 0 only (keeps them out of registers)
-  if (tid == 0) { for (int i = 0; i < kLevels; i++) { evals[i] = 0; iters[i] = 0; accs[i] = 0; } }
+  // NOTE: keep these statistics as per-thread local arrays.  Moving them to shared memory changed ptxas' allocation under the
+  // 128-register cap (1 spill in the sweep) and cost 45 % of the kernel's throughput (measured, round 1).
+  long long evals[kLevels]; int iters[kLevels], accs[kLevels];
+#pragma unroll
+  for (int i = 0; i < kLevels; i++) { evals[i] = 0; iters[i] = 0; accs[i] = 0; }
   __syncthreads();
 
   int evalCount = 0;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       if (tid < kNAcc) tot[tid] = bsum[tid];
     }
     __syncthreads();
-    evalCount++; if (tid == 0) evals[lvl] += n;
+    evalCount++; evals[lvl] += n;
   };
 
   const int maxIterations[5] = {10,20,50,50,50};           // CoarseTracker.cpp:679
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
     if (tid == 0) { finalize_gs(tot, ctl.H, ctl.b); ctl.lambda = 0.01f; }
 
     for (int iteration = 0; iteration < maxIterations[lvl]; iteration++) {
-      if (tid == 0) iters[lvl]++;
+      iters[lvl]++;
       double incn = 0;
       if (tid < 32) {                                        // warp 0: propose the LM step (CoarseTracker.cpp:722-765)
         const int r = tid & 7;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       __syncthreads();
       const int f = ctl.flag;
       __syncthreads();
-      if ((f & 1) && tid == 0) accs[lvl]++;
+      if (f & 1) accs[lvl]++;
       if (f & 2) break;
     }
     if (tid == 0) {
