@@ -159,6 +159,7 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
   CK(cudaStreamSynchronize(c->st_in));            // previous ingest (descriptor + staging buffers are reused) must have drained
   int rc = ensure_stage(c, n); if (rc) return rc;
   const bool u8 = (kind & 1), dev = (kind & 2), adopt = (kind & 4) && dev && !u8;
+  c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
   const size_t px = (size_t)c->w*c->h;
   if (c->levels > 1 && ((c->w | c->h) & 1)) return ctx_fail(c, SDV_ERR_ARG, "pyramid needs even image sizes");
   for (int k=0;k<n;k++) {
@@ -173,8 +174,19 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
     PyrBatchHost& b = c->pyr_batch_host[k];
     b.scratch = c->stage[k] + px; b.out = f.base; b.I0 = f.I0;
     if (dev) b.src = imgs[k];
-    else if (u8) { b.src = c->stage[k]; CK(cudaMemcpyAsync(c->stage[k], imgs[k], px, cudaMemcpyHostToDevice, c->st_in)); }
-    else { b.src = f.I0; CK(cudaMemcpyAsync(f.I0, imgs[k], px*sizeof(float), cudaMemcpyHostToDevice, c->st_in)); }
+    else if (u8) { b.src = c->stage[k]; c->cp_dst.push_back(c->stage[k]); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px); }
+    else { b.src = f.I0; c->cp_dst.push_back(f.I0); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px*sizeof(float)); }
+  }
+  if (!c->cp_dst.empty()) {                                               // all H2D copies of the batch in ONE runtime call (per-copy launch cost dominates otherwise)
+    bool done = false;
+    if (c->cp_dst.size() > 1 && !c->no_batch_copy) {
+      cudaMemcpyAttributes at; memset(&at, 0, sizeof(at)); at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+      size_t aidx = 0, fail = 0;
+      cudaError_t e = cudaMemcpyBatchAsync(c->cp_dst.data(), c->cp_src.data(), c->cp_sz.data(), c->cp_dst.size(), &at, &aidx, 1, &fail, c->st_in);
+      if (e == cudaSuccess) done = true; else { cudaGetLastError(); c->no_batch_copy = true; }
+    }
+    if (!done) for (size_t i=0;i<c->cp_dst.size();i++) CK(cudaMemcpyAsync(c->cp_dst[i], c->cp_src[i], c->cp_sz[i], cudaMemcpyHostToDevice, c->st_in));
+    c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
   }
   CK(cudaMemcpyAsync(c->pyr_batch_dev, c->pyr_batch_host, (size_t)n*sizeof(PyrBatchHost), cudaMemcpyHostToDevice, c->st_in));
   if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev, n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in); c->launches += 2*(c->levels - 1); }

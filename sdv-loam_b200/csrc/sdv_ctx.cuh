@@ -32,6 +32,7 @@ struct sdv_ctx {
   std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
   std::vector<float*> stage; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev; sdv::PyrBatchHost* pyr_batch_host;
   std::vector<float4*> lvl0_pool; std::vector<int> lvl0_free;
+  std::vector<void*> cp_dst, cp_src; std::vector<size_t> cp_sz; bool no_batch_copy = false;
   std::vector<sdv::TrackerSlot> slots;
   double* partials; unsigned int* ticket; double* totals_dev; double* totals_host;
   float *cd_id[sdv::kLevels], *cd_ws[sdv::kLevels], *cd_id2[sdv::kLevels], *cd_ws2[sdv::kLevels];
