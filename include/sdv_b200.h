@@ -115,6 +115,19 @@ int  sdv_tracker_track(sdv_ctx* c, int slot, uint64_t new_frame, double T_io[7],
 int  sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* new_frames, double* T_io, double* ab_io,
                              int coarsest, const double* minResForAbort, double* lastRes, double* flow, int32_t* good,
                              sdv_track_stats* stats);
+/* ---- semi-direct pose refinement on matched map points
+ * bool CoarseTracker::structPoseEstimation(SE3& curToWorld, std::vector<std::pair<PointHessian*, Eigen::Vector2d>>& overlap_pts)
+ *                                                                                              CoarseTracker.cpp:949-1007
+ *   with calculateRes :840-871, calculateWeight :873-887, calcHandb :889-947 (called from FullSystem::trackNewCoarse, FullSystem.cpp:483-488).
+ * One overlap point = the PointHessian fields the function reads (u, v, idepth, host) + the matched pixel (it->second cast to float).
+ * `host` indexes the job's host_T7 rows = host->shell->camToWorld of the distinct host keyframes.  curToWorld_io is in-out like the
+ * reference argument (written only by accepted steps).  res = final mean squared reprojection error (resOld), iterations/accepts = loop
+ * statistics.  Batched: job k owns pts[pt_begin[k] .. pt_begin[k+1]) and host_T7 rows [host_begin[k] .. host_begin[k+1]) (<= 16 hosts). */
+typedef struct { float u, v, idepth; int32_t host; float obs_x, obs_y; } sdv_overlap_pt;
+int  sdv_tracker_struct_pose(sdv_ctx* c, int n, const sdv_overlap_pt* pts, int nH, const double* host_T7, double curToWorld_io[7],
+                             float* res, int* iterations, int* accepts);
+int  sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_begin, const sdv_overlap_pt* pts, const int32_t* host_begin,
+                                   const double* host_T7, double* curToWorld_io, float* res, int32_t* iterations, int32_t* accepts);
 /* device time of the last track / track_batch / calc_res launch in milliseconds (CUDA events on the context stream) */
 float sdv_last_kernel_ms(sdv_ctx* c);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

@@ -162,6 +162,20 @@ class CoarseTracker:
 
 
 # ------------------------------------------------------------------------------------------------ back-end window
+def struct_pose(w, h, K4, host_T7, pts6, curToWorld7):
+    """CoarseTracker::structPoseEstimation restated (orc_refine.cpp).  pts6: (n,6) float32 {u,v,idepth,host,obs_x,obs_y}."""
+    L = lib()
+    L.orc_struct_pose.argtypes = [C.c_int, C.c_int, _f32p, C.c_int, _f64p, C.c_int, _f32p, _f64p, _i32p]; L.orc_struct_pose.restype = C.c_float
+    hT = np.ascontiguousarray(host_T7, np.float64).reshape(-1, 7); p = np.ascontiguousarray(pts6, np.float32).reshape(-1, 6)
+    T = np.array(curToWorld7, np.float64).copy(); st = np.zeros(2, np.int32)
+    if len(p) == 0:
+        p = np.zeros((1, 6), np.float32); n = 0
+    else:
+        n = len(p)
+    res = L.orc_struct_pose(w, h, np.ascontiguousarray(K4, np.float32), len(hT), hT, n, p, T, st)
+    return dict(T=T, res=float(res), iterations=int(st[0]), accepts=int(st[1]))
+
+
 def _ba_protos():
     L = lib()
     if getattr(L, "_ba_done", False):

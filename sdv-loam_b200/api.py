@@ -31,6 +31,7 @@ class sdv_track_stats(C.Structure):
     _fields_ = [("point_evals", C.c_int64 * PYR_LEVELS), ("iterations", C.c_int32 * PYR_LEVELS), ("accepts", C.c_int32 * PYR_LEVELS)]
 
 
+OVERLAP_PT_DTYPE = np.dtype([("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("obs_x", np.float32), ("obs_y", np.float32)])
 TRACK_STATS_DTYPE = np.dtype([("point_evals", np.int64, PYR_LEVELS), ("iterations", np.int32, PYR_LEVELS), ("accepts", np.int32, PYR_LEVELS)])
 assert TRACK_STATS_DTYPE.itemsize == C.sizeof(sdv_track_stats)
 
@@ -65,6 +66,7 @@ def _load():
     L.sdv_tracker_get_cloud.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), _vp, _vp, _vp, _vp]
     L.sdv_tracker_calc_res.argtypes = [_vp, C.c_int, C.c_uint64, C.c_int, _f64p, C.c_double, C.c_double, C.c_float, _f64p]
     L.sdv_tracker_calc_gs.argtypes = [_vp, C.c_int, C.c_int, _f64p, _f64p]
+    L.sdv_tracker_struct_pose_batch.argtypes = [_vp, C.c_int, _i32p, _vp, _i32p, _f64p, _f64p, _f32p, _i32p, _i32p]
     L.sdv_tracker_track.argtypes = [_vp, C.c_int, C.c_uint64, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(sdv_track_stats)]
     L.sdv_tracker_track_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, C.c_int, _vp, _f64p, _f64p, _i32p, C.POINTER(sdv_track_stats)]
     L.sdv_last_kernel_ms.argtypes = [_vp]; L.sdv_last_kernel_ms.restype = C.c_float
@@ -219,6 +221,25 @@ class CoarseTracker:
         r = self.ctx.trackBatch([self.slot], [new_frame_id], T, abv, coarsest, mr)
         return dict(good=bool(r["good"][0]), T=T[0], ab=abv[0], lastResiduals=r["lastResiduals"][0], flow=r["flow"][0],
                     evals=r["evals"][0], iterations=r["iterations"][0], accepts=r["accepts"][0])
+
+    def structPoseEstimation(self, curToWorld7, overlap_pts, host_T7):
+        """CoarseTracker::structPoseEstimation (CoarseTracker.cpp:949-1007).  overlap_pts: OVERLAP_PT_DTYPE array, host_T7: (nH,7) camToWorld of
+        the host keyframes the points index.  Returns dict(T=refined curToWorld, res, iterations, accepts)."""
+        r = structPoseEstimationBatch(self.ctx, np.array(curToWorld7, np.float64).reshape(1, 7), [overlap_pts], [host_T7])
+        return dict(T=r["T"][0], res=float(r["res"][0]), iterations=int(r["iterations"][0]), accepts=int(r["accepts"][0]))
+
+
+def structPoseEstimationBatch(ctx, curToWorld7, overlap_pts_list, host_T7_list):
+    """n independent structPoseEstimation calls in one launch (one CTA each): curToWorld7 (n,7) is refined in place."""
+    n = len(overlap_pts_list)
+    T = np.ascontiguousarray(curToWorld7, np.float64).reshape(n, 7)
+    pb = np.zeros(n + 1, np.int32); hb = np.zeros(n + 1, np.int32)
+    pb[1:] = np.cumsum([len(p) for p in overlap_pts_list]); hb[1:] = np.cumsum([len(np.asarray(h).reshape(-1, 7)) for h in host_T7_list])
+    pts = np.concatenate([np.ascontiguousarray(p, OVERLAP_PT_DTYPE) for p in overlap_pts_list]) if pb[-1] else np.zeros(1, OVERLAP_PT_DTYPE)
+    hT = np.ascontiguousarray(np.concatenate([np.asarray(h, np.float64).reshape(-1, 7) for h in host_T7_list]))
+    res = np.zeros(n, np.float32); its = np.zeros(n, np.int32); acc = np.zeros(n, np.int32)
+    ctx._ck(LIB.sdv_tracker_struct_pose_batch(ctx.p, n, pb, pts.ctypes.data, hb, hT, T, res, its, acc))
+    return dict(T=T, res=res, iterations=its, accepts=acc)
 
 
 # ------------------------------------------------------------------------------------------------ back-end

@@ -123,6 +123,7 @@ void sdv_destroy(sdv_ctx* c) {
   cudaFree(c->pyr_batch_dev); cudaFreeHost(c->pyr_batch_host); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
   for (auto p : c->stage) cudaFree(p);
+  cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   ba_destroy(c);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_in); cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_in);
   delete c;

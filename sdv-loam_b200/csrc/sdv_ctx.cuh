@@ -40,6 +40,7 @@ struct sdv_ctx {
   int cd_cap; float* cd_pts4; int* cd_round; float4* cd_splats; int* cd_done;
   int jobs_cap; sdv::TrackJob* jobs_dev; sdv::TrackJob* jobs_host;
   float last_ms;
+  void* refine_dev = nullptr; void* refine_host = nullptr; size_t refine_cap = 0;      // staging of sdv_tracker_struct_pose_batch
   sdv::BAState* ba = nullptr;                   // selected back-end window
   std::vector<sdv::BAState*> ba_windows; void* ba_wins_dev = nullptr; void* ba_wins_host = nullptr; int ba_wins_cap = 0;
   char err[512];

@@ -268,3 +268,36 @@ def make_ba_window(seq: "Sequence", kf_idx, n_per_frame: int = 250, seed: int = 
                 r_point=np.array(r_point, np.int32), r_host=np.array(r_host, np.int32), r_target=np.array(r_target, np.int32),
                 r_hasMatcher=np.array(r_hasM, np.int32), r_matcher=np.array(r_match, np.float32), r_isNew=np.array(r_new, np.int32),
                 HM=HM, bM=bM, T_gt=np.array([np.concatenate([_quat_from_R(Rw2c[i]), tw2c[i]]) for i in range(nF)]))
+
+
+# ------------------------------------------------------------------------------------------------ overlap points (structPoseEstimation input)
+def make_overlap_points(n: int, nH: int = 5, seed: int = 0, K=KITTI_K, wh=KITTI_WH, match_noise: float = 0.4, outlier_frac: float = 0.05,
+                        pose_noise=(0.05, 0.004), step: float = 1.0):
+    """Stand-in for Reprojector::reprojectMap output (FullSystem.cpp:483-485): n map points hosted in nH keyframes, each with the pixel
+    it was matched to in the current frame (ground-truth projection + match_noise px, outlier_frac gross mismatches), plus the
+    photometric tracker's pose estimate of the current frame (ground truth perturbed by pose_noise (m, rad)).  Geometry only."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = K; w, h = wh
+    R, t = trajectory(nH + 1, seed + 7, step)
+    host_T7 = np.array([np.concatenate([_quat_from_R(R[i]), t[i]]) for i in range(nH)])
+    Rc, tc = R[nH], t[nH]
+    pts = np.zeros(n, np.dtype([("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("obs_x", np.float32), ("obs_y", np.float32)]))
+    k = 0
+    while k < n:
+        hi = int(rng.integers(0, nH)); u = float(rng.integers(4, w - 5)); v = float(rng.integers(4, h - 5)); d = rng.uniform(4.0, 60.0)
+        Xw = R[hi] @ (np.array([(u - cx) / fx, (v - cy) / fy, 1.0]) * d) + t[hi]
+        Xc = Rc.T @ (Xw - tc)
+        if Xc[2] < 1.0:
+            continue
+        Ku, Kv = fx * Xc[0] / Xc[2] + cx, fy * Xc[1] / Xc[2] + cy
+        if not (Ku > 8 and Kv > 8 and Ku < w - 9 and Kv < h - 9):
+            continue
+        if rng.uniform() < outlier_frac:
+            ox, oy = Ku + rng.normal(0, 25.0), Kv + rng.normal(0, 25.0)
+        else:
+            ox, oy = Ku + rng.normal(0, match_noise), Kv + rng.normal(0, match_noise)
+        pts[k] = (u, v, 1.0 / d, hi, ox, oy); k += 1
+    dR = _rot(*rng.normal(0, pose_noise[1], 3))
+    T_gt = np.concatenate([_quat_from_R(Rc), tc])
+    T_init = np.concatenate([_quat_from_R(dR @ Rc), tc + rng.normal(0, pose_noise[0], 3)])
+    return dict(pts=pts, host_T7=host_T7, T_init=T_init, T_gt=T_gt, K=np.array(K, np.float64), wh=(w, h))

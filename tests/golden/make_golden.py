@@ -67,3 +67,23 @@ def main_ba():
 
 if __name__ == "__main__" and "--ba" in sys.argv or __name__ == "__main__":
     main_ba()
+
+
+def pts6_of(p):
+    return np.stack([p["u"], p["v"], p["idepth"], p["host"].astype(np.float32), p["obs_x"], p["obs_y"]], 1).astype(np.float32)
+
+
+def main_refine():
+    """structPoseEstimation fixture (§8 a11): three seeded overlap sets, frozen oracle outputs."""
+    out = {}
+    for k, (n, nH, seed) in enumerate([(300, 5, 2), (900, 7, 11), (40, 2, 5)]):
+        d = synth.make_overlap_points(n, nH, seed, K=K, wh=WH)
+        r = orc.struct_pose(WH[0], WH[1], np.array(K, np.float32), d["host_T7"], pts6_of(d["pts"]), d["T_init"])
+        out.update({f"pts{k}": pts6_of(d["pts"]), f"host{k}": d["host_T7"], f"Tin{k}": d["T_init"], f"Tout{k}": r["T"],
+                    f"stat{k}": np.array([r["res"], r["iterations"], r["accepts"]])})
+        print("refine:", k, r["res"], r["iterations"], r["accepts"])
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "refine_small.npz"), **out)
+
+
+if __name__ == "__main__":
+    main_refine()
