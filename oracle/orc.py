@@ -202,6 +202,12 @@ def _ba_protos():
     L.orc_ba_get_precalc.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p]
     L.orc_ba_optimize.argtypes = [C.c_void_p, C.c_int, _i32p]; L.orc_ba_optimize.restype = C.c_float
     L.orc_ba_linearize_calls.argtypes = [C.c_void_p]; L.orc_ba_linearize_calls.restype = C.c_longlong
+    L.orc_ba_flag_points.argtypes = [C.c_void_p, _i32p, _i32p]
+    L.orc_ba_marginalize_points.argtypes = [C.c_void_p, _i32p, _f64p, _f64p, _f64p, _f64p]
+    L.orc_ba_marginalize_frame.argtypes = [C.c_void_p, C.c_int]
+    L.orc_ba_dim.argtypes = [C.c_void_p]
+    L.orc_ba_get_prior.argtypes = [C.c_void_p, _f64p, _f64p]
+    L.orc_ba_get_res_to_zero.argtypes = [C.c_void_p, _f32p, _i32p]
     L._ba_done = True
     return L
 
@@ -272,6 +278,23 @@ class BAWindow:
     def optimize(self, its=6):
         st = np.zeros(2, np.int32); rmse = self.L.orc_ba_optimize(self.p, its, st)
         return dict(rmse=float(rmse), iterations=int(st[0]), accepts=int(st[1]), linearize_calls=int(self.L.orc_ba_linearize_calls(self.p)))
+
+    # ---- keyframe hand-over
+    def flagPointsForRemoval(self, selected):
+        st = np.zeros(self.nP, np.int32); self.L.orc_ba_flag_points(self.p, np.ascontiguousarray(selected, np.int32), st); return st
+
+    def marginalizePointsF(self, status):
+        n = self.L.orc_ba_dim(self.p); M = np.zeros((n, n)); Mb = np.zeros(n); S = np.zeros((n, n)); Sb = np.zeros(n)
+        self.L.orc_ba_marginalize_points(self.p, np.ascontiguousarray(status, np.int32), M, Mb, S, Sb)
+        return dict(M=M, Mb=Mb, Msc=S, Mbsc=Sb)
+
+    def marginalizeFrame(self, idx): self.L.orc_ba_marginalize_frame(self.p, int(idx))
+
+    def prior(self):
+        n = self.L.orc_ba_dim(self.p); HM = np.zeros((n, n)); bM = np.zeros(n); self.L.orc_ba_get_prior(self.p, HM, bM); return HM, bM
+
+    def res_to_zero(self):
+        r = np.zeros((self.nR, 2), np.float32); l = np.zeros(self.nR, np.int32); self.L.orc_ba_get_res_to_zero(self.p, r, l); return r, l
 
     def __del__(self):
         if getattr(self, "p", None):

@@ -528,4 +528,172 @@ float BAWindow::optimize(int mnumOptIts) {
   return sqrtf((float)(lastEnergy / resInA));
 }
 
+
+// ================================================================================================ keyframe hand-over: marginalisation
+// FullSystem::flagPointsForRemoval, numeric part (FullSystem.cpp:764-797).  `selected[p]` = the host-side predicate
+// (ph->isOOB(...) || host->flaggedForMarginalization) && ph->isInlierNew()  — graph bookkeeping, evaluated by the caller.
+void BAWindow::flagPointsForRemoval(const int* selected, int* status) {
+  const int n = nF();
+  for (size_t pi=0; pi<points.size(); pi++) {
+    BAPoint& p = points[pi]; status[pi] = 0; if (!selected[pi]) continue;
+    for (int ri=p.res_begin; ri<p.res_end; ri++) {
+      BARes& r = res[ri];
+      r.state_NewEnergy = r.state_energy = 0; r.state_NewState = RS_OUTLIER; r.state_state = RS_IN;       // resetOOB
+      linearizeOne(r);
+      r.isLinearized = 0;
+      applyRes(r);
+      if (r.isActive) {                                                                                      // fixLinearizationF (EnergyFunctionalStructs.cpp:46-55)
+        const float* dp = &adHTdeltaF[(size_t)(r.host + n*r.target)*6]; const RawJ& J = r.efJ;
+        float dx0=0, dx1=0, dc0=0, dc1=0;
+        for (int i=0;i<6;i++) { dx0 += J.Jpdxi[0][i]*dp[i]; dx1 += J.Jpdxi[1][i]*dp[i]; }
+        for (int i=0;i<4;i++) { dc0 += J.Jpdc[0][i]*cDeltaF[i]; dc1 += J.Jpdc[1][i]*cDeltaF[i]; }
+        float Jp_delta_x = dx0 + dc0 + J.Jpdd[0]*p.deltaF;
+        float Jp_delta_y = dx1 + dc1 + J.Jpdd[1]*p.deltaF;
+        r.res_toZeroF[0] = J.resF[0] - Jp_delta_x; r.res_toZeroF[1] = J.resF[1] - Jp_delta_y;
+        r.isLinearized = 1;
+      }
+    }
+    status[pi] = (p.idepth_hessian > 50.0f) ? 2 : 1;                                                         // setting_minIdepthH_marg, settings.cpp:42
+  }
+}
+
+// EnergyFunctional::marginalizePointsF (EnergyFunctional.cpp:514-576): single-threaded accumulation (tid 0), non-MT stitchDouble.
+void BAWindow::marginalizePointsF(const int* status) {
+  const int n=nF(), N=dim(), n2=n*n;
+  std::vector<AccApprox> acc((size_t)n2); for (auto& a : acc) a.init();
+  std::vector<AccXX<8,4>> accE(n2); std::vector<AccX<8>> accEB(n2); std::vector<AccXX<8,8>> accD((size_t)n2*n);
+  AccXX<4,4> accHcc; AccX<4> accbc; accHcc.init(); accbc.init();
+  for (auto& a : accE) a.init(); for (auto& a : accEB) a.init(); for (auto& a : accD) a.init();
+  for (size_t pi=0; pi<points.size(); pi++) if (status[pi] == 2) points[pi].priorF *= 600.0f*600.0f;         // setting_idepthFixPriorMargFac (:527)
+  for (size_t pi=0; pi<points.size(); pi++) { if (status[pi] != 2) continue; BAPoint& p = points[pi];
+    // ---- addPoint<2> (AccumulatedTopHessian.cpp:13-112): active residuals, resApprox = res_toZeroF
+    float bd_acc=0, Hdd_acc=0, Hcd_acc[4]={0,0,0,0};
+    for (int ri=p.res_begin; ri<p.res_end; ri++) { BARes& r = res[ri]; if (!r.isActive) continue;
+      const RawJ& rJ = r.efJ; int htIDX = r.host + r.target*n;
+      float r0=r.res_toZeroF[0], r1=r.res_toZeroF[1]; float rr = r0*r0 + r1*r1;
+      float x[10], y[10]; for (int i=0;i<4;i++) { x[i]=rJ.Jpdc[0][i]; y[i]=rJ.Jpdc[1][i]; } for (int i=0;i<6;i++) { x[4+i]=rJ.Jpdxi[0][i]; y[4+i]=rJ.Jpdxi[1][i]; }
+      AccApprox& A = acc[htIDX]; A.update(x, y, 1, 0, 1); A.BR += rr;
+      for (int i=0;i<10;i++) A.TR[i] += x[i]*r0 + y[i]*r1;
+      bd_acc += r0*rJ.Jpdd[0] + r1*rJ.Jpdd[1];
+      Hdd_acc += rJ.Jpdd[0]*rJ.Jpdd[0] + rJ.Jpdd[1]*rJ.Jpdd[1];
+      for (int i=0;i<4;i++) Hcd_acc[i] += rJ.Jpdc[0][i]*rJ.Jpdd[0] + rJ.Jpdc[1][i]*rJ.Jpdd[1];
+    }
+    p.Hdd_accLF=Hdd_acc; p.bd_accLF=bd_acc; for (int i=0;i<4;i++) p.Hcd_accLF[i]=Hcd_acc[i];
+    p.Hdd_accAF=0; p.bd_accAF=0; for (int i=0;i<4;i++) p.Hcd_accAF[i]=0;
+    // ---- accSSE_bot->addPoint(p, false)  (AccumulatedSCHessian.cpp:10-62)
+    int ngood=0; for (int ri=p.res_begin; ri<p.res_end; ri++) if (res[ri].isActive) ngood++;
+    if (ngood==0) { p.HdiF=0; p.bdSumF=0; p.idepth_hessian=0; p.maxRelBaseline=0; continue; }
+    float Hh = p.Hdd_accAF+p.Hdd_accLF+p.priorF; if (Hh < 1e-10) Hh = 1e-10;
+    p.idepth_hessian=Hh; p.HdiF = 1.0/Hh;
+    p.bdSumF = p.bd_accAF + p.bd_accLF;
+    float Hcd[4]; for (int i=0;i<4;i++) Hcd[i]=p.Hcd_accAF[i]+p.Hcd_accLF[i];
+    if (p.isFromSensor) continue;
+    accHcc.update(Hcd,Hcd,p.HdiF); accbc.update(Hcd, p.bdSumF*p.HdiF);
+    for (int r1=p.res_begin; r1<p.res_end; r1++) { if (!res[r1].isActive) continue;
+      int r1ht = res[r1].host + res[r1].target*n;
+      for (int r2=p.res_begin; r2<p.res_end; r2++) { if (!res[r2].isActive) continue;
+        accD[(size_t)r1ht + (size_t)res[r2].target*n2].update(res[r1].JpJdF, res[r2].JpJdF, p.HdiF); }
+      accE[r1ht].update(res[r1].JpJdF, Hcd, p.HdiF);
+      accEB[r1ht].update(res[r1].JpJdF, p.HdiF*p.bdSumF);
+    }
+  }
+  // ---- accSSE_top_A->stitchDouble(M, Mb, this, usePrior=false, useDelta=false)   AccumulatedTopHessian.cpp:118-179 (h outer, t inner)
+  std::vector<double>& M = margM; std::vector<double>& Mb = margMb; M.assign((size_t)N*N,0); Mb.assign(N,0);
+  for (int h=0;h<n;h++) for (int t=0;t<n;t++) {
+    int hIdx=CPARS+h*6, tIdx=CPARS+t*6, aidx=h+n*t;
+    acc[aidx].finish(); if (acc[aidx].num==0) continue;
+    double accH[10][10], bv[10];
+    { int kk=0; for (int r=0;r<10;r++) for (int c=r;c<10;c++) { accH[r][c]=accH[c][r]=(double)acc[aidx].D1m[kk]; kk++; } for (int r=0;r<10;r++) bv[r]=(double)acc[aidx].TR1m[r]; }
+    const double* AH=&adHost[(size_t)aidx*36]; const double* AT=&adTarget[(size_t)aidx*36];
+    double H66[36], H64[24]; for (int r=0;r<6;r++) { for (int c=0;c<6;c++) H66[r*6+c]=accH[4+r][4+c]; for (int c=0;c<4;c++) H64[r*4+c]=accH[4+r][c]; }
+    double T1[36], T2[36];
+    mm66(AH,H66,T1); mm66T(T1,AH,T2); for (int r=0;r<6;r++) for (int c=0;c<6;c++) M[(size_t)(hIdx+r)*N+hIdx+c] += T2[r*6+c];
+    mm66(AT,H66,T1); mm66T(T1,AT,T2); for (int r=0;r<6;r++) for (int c=0;c<6;c++) M[(size_t)(tIdx+r)*N+tIdx+c] += T2[r*6+c];
+    mm66(AH,H66,T1); mm66T(T1,AT,T2); for (int r=0;r<6;r++) for (int c=0;c<6;c++) M[(size_t)(hIdx+r)*N+tIdx+c] += T2[r*6+c];
+    for (int r=0;r<6;r++) for (int c=0;c<4;c++) { double s1=0,s2=0; for (int q=0;q<6;q++) { s1 += AH[r*6+q]*H64[q*4+c]; s2 += AT[r*6+q]*H64[q*4+c]; }
+      M[(size_t)(hIdx+r)*N+c] += s1; M[(size_t)(tIdx+r)*N+c] += s2; }
+    for (int r=0;r<4;r++) for (int c=0;c<4;c++) M[(size_t)r*N+c] += accH[r][c];
+    for (int r=0;r<6;r++) { double s1=0,s2=0; for (int q=0;q<6;q++) { s1 += AH[r*6+q]*bv[4+q]; s2 += AT[r*6+q]*bv[4+q]; } Mb[hIdx+r]+=s1; Mb[tIdx+r]+=s2; }
+    for (int r=0;r<4;r++) Mb[r] += bv[r];
+  }
+  for (int h=0;h<n;h++) { int hIdx=CPARS+h*6;
+    for (int r=0;r<4;r++) for (int c=0;c<6;c++) M[(size_t)r*N+hIdx+c] = M[(size_t)(hIdx+c)*N+r];
+    for (int t=h+1;t<n;t++) { int tIdx=CPARS+t*6;
+      for (int r=0;r<6;r++) for (int c=0;c<6;c++) M[(size_t)(hIdx+r)*N+tIdx+c] += M[(size_t)(tIdx+c)*N+hIdx+r];
+      for (int r=0;r<6;r++) for (int c=0;c<6;c++) M[(size_t)(tIdx+r)*N+hIdx+c] = M[(size_t)(hIdx+c)*N+tIdx+r]; } }
+  // ---- accSSE_bot->stitchDouble(Msc, Mbsc, this)   AccumulatedSCHessian.cpp:136-195 (i outer, j inner)
+  std::vector<double>& S = margMsc; std::vector<double>& Sb = margMbsc; S.assign((size_t)N*N,0); Sb.assign(N,0);
+  for (int i=0;i<n;i++) for (int j=0;j<n;j++) {
+    int iIdx=CPARS+i*6, jIdx=CPARS+j*6, ij=i+n*j;
+    accE[ij].finish(); accEB[ij].finish();
+    const double* AHij=&adHost[(size_t)ij*36]; const double* ATij=&adTarget[(size_t)ij*36];
+    for (int r=0;r<6;r++) for (int c=0;c<4;c++) { double s1=0,s2=0; for (int q=0;q<6;q++) { double e=(double)accE[ij].A1m[q][c]; s1 += AHij[r*6+q]*e; s2 += ATij[r*6+q]*e; }
+      S[(size_t)(iIdx+r)*N+c] += s1; S[(size_t)(jIdx+r)*N+c] += s2; }
+    for (int r=0;r<6;r++) { double s1=0,s2=0; for (int q=0;q<6;q++) { double e=(double)accEB[ij].A1m[q]; s1 += AHij[r*6+q]*e; s2 += ATij[r*6+q]*e; } Sb[iIdx+r]+=s1; Sb[jIdx+r]+=s2; }
+    for (int k2=0;k2<n;k2++) {
+      int kIdx=CPARS+k2*6, ik=i+n*k2; AccXX<8,8>& D = accD[(size_t)ij + (size_t)k2*n2];
+      D.finish(); if (D.num==0) continue;
+      double D66[36]; for (int r=0;r<6;r++) for (int c=0;c<6;c++) D66[r*6+c]=(double)D.A1m[r][c];
+      const double* AHik=&adHost[(size_t)ik*36]; const double* ATik=&adTarget[(size_t)ik*36];
+      double T1[36], T2[36];
+      mm66(AHij,D66,T1); mm66T(T1,AHik,T2); for (int r=0;r<6;r++) for (int c=0;c<6;c++) S[(size_t)(iIdx+r)*N+iIdx+c] += T2[r*6+c];
+      mm66(ATij,D66,T1); mm66T(T1,ATik,T2); for (int r=0;r<6;r++) for (int c=0;c<6;c++) S[(size_t)(jIdx+r)*N+kIdx+c] += T2[r*6+c];
+      mm66T(T1,AHik,T2);                    for (int r=0;r<6;r++) for (int c=0;c<6;c++) S[(size_t)(jIdx+r)*N+iIdx+c] += T2[r*6+c];
+      mm66(AHij,D66,T1); mm66T(T1,ATik,T2); for (int r=0;r<6;r++) for (int c=0;c<6;c++) S[(size_t)(iIdx+r)*N+kIdx+c] += T2[r*6+c];
+    }
+  }
+  accHcc.finish(); accbc.finish();
+  for (int r=0;r<4;r++) { for (int c=0;c<4;c++) S[(size_t)r*N+c] = (double)accHcc.A1m[r][c]; Sb[r] = (double)accbc.A1m[r]; }
+  for (int h=0;h<n;h++) { int hIdx=CPARS+h*6; for (int r=0;r<4;r++) for (int c=0;c<6;c++) S[(size_t)r*N+hIdx+c] = S[(size_t)(hIdx+c)*N+r]; }
+  // ---- HM += setting_margWeightFac * (M - Msc)   (:552-567 ; SOLVER_ORTHOGONALIZE_POINTMARG / _FULL not set, settings.cpp:34)
+  const double fac = (double)(0.5f*0.5f);
+  for (size_t i=0;i<(size_t)N*N;i++) { double Hh = M[i]-S[i]; HM[i] += fac*Hh; }
+  for (int i=0;i<N;i++) { double bb = Mb[i]-Sb[i]; bM[i] += fac*bb; }
+}
+
+// 6x6 inverse through partial-pivot LU (Eigen's fixed-size path for n > 4): right-looking elimination, column-wise substitution.
+static void inverse6_lu(const double* A, double* inv) {
+  double L[36]; int perm[6]; for (int i=0;i<36;i++) L[i]=A[i]; for (int i=0;i<6;i++) perm[i]=i;
+  for (int k=0;k<6;k++) {
+    int piv=k; double big=std::fabs(L[k*6+k]); for (int i=k+1;i<6;i++) { double a=std::fabs(L[i*6+k]); if (a>big) { big=a; piv=i; } }
+    if (piv!=k) { for (int j=0;j<6;j++) std::swap(L[k*6+j], L[piv*6+j]); std::swap(perm[k], perm[piv]); }
+    for (int i=k+1;i<6;i++) L[i*6+k] /= L[k*6+k];
+    for (int i=k+1;i<6;i++) for (int j=k+1;j<6;j++) L[i*6+j] -= L[i*6+k]*L[k*6+j];
+  }
+  for (int c=0;c<6;c++) { double y[6]; for (int i=0;i<6;i++) y[i] = (perm[i]==c) ? 1.0 : 0.0;
+    for (int k=0;k<6;k++) for (int i=k+1;i<6;i++) y[i] -= L[i*6+k]*y[k];
+    for (int k=5;k>=0;k--) { y[k] /= L[k*6+k]; for (int i=0;i<k;i++) y[i] -= L[i*6+k]*y[k]; }
+    for (int i=0;i<6;i++) inv[i*6+c] = y[i]; }
+}
+
+// EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:434-512): move the frame's block to the end, add its prior, Schur-eliminate it
+// in the diagonally pre-scaled system, symmetrise.  The residuals that target the frame and its points are host bookkeeping
+// (FullSystemMarginalize.cpp:104-130) and must already be gone from the window.
+void BAWindow::marginalizeFrame(int idx) {
+  const int n=nF(), odim=dim(), ndim=odim-6;
+  std::vector<int> order; for (int i=0;i<odim;i++) { int f=(i-CPARS)/6; if (i<CPARS || f!=idx) order.push_back(i); } for (int i=0;i<6;i++) order.push_back(CPARS+6*idx+i);
+  std::vector<double> Hp((size_t)odim*odim), bp(odim);
+  for (int i=0;i<odim;i++) { bp[i]=bM[order[i]]; for (int j=0;j<odim;j++) Hp[(size_t)i*odim+j]=HM[(size_t)order[i]*odim+order[j]]; }
+  const BAFrame& fh = frames[idx];
+  for (int i=0;i<6;i++) { Hp[(size_t)(ndim+i)*odim+ndim+i] += fh.prior[i]; bp[ndim+i] += fh.prior[i]*fh.delta_prior[i]; }
+  std::vector<double> SV(odim), SVI(odim);
+  for (int i=0;i<odim;i++) { SV[i] = std::sqrt(std::fabs(Hp[(size_t)i*odim+i]) + 10.0); SVI[i] = 1.0/SV[i]; }
+  std::vector<double> Hs((size_t)odim*odim), bs(odim);
+  for (int i=0;i<odim;i++) { for (int j=0;j<odim;j++) Hs[(size_t)i*odim+j] = (SVI[i]*Hp[(size_t)i*odim+j])*SVI[j]; bs[i] = SVI[i]*bp[i]; }
+  double hp[36], hpi[36]; for (int i=0;i<6;i++) for (int j=0;j<6;j++) hp[i*6+j] = Hs[(size_t)(ndim+i)*odim+ndim+j];
+  for (int i=0;i<36;i++) hp[i] = 0.5*(hp[i]+hp[i]);                                  // (sic) hpi+hpi, not hpi+hpi^T  (:478,480)
+  inverse6_lu(hp, hpi);
+  for (int i=0;i<36;i++) hpi[i] = 0.5*(hpi[i]+hpi[i]);
+  std::vector<double> bli((size_t)ndim*6);                                            // bottomLeft^T * hpi
+  for (int i=0;i<ndim;i++) for (int j=0;j<6;j++) { double s=0; for (int k=0;k<6;k++) s += Hs[(size_t)(ndim+k)*odim+i]*hpi[k*6+j]; bli[(size_t)i*6+j]=s; }
+  for (int i=0;i<ndim;i++) { for (int j=0;j<ndim;j++) { double s=0; for (int k=0;k<6;k++) s += bli[(size_t)i*6+k]*Hs[(size_t)(ndim+k)*odim+j]; Hs[(size_t)i*odim+j] -= s; }
+    double s=0; for (int k=0;k<6;k++) s += bli[(size_t)i*6+k]*bs[ndim+k]; bs[i] -= s; }
+  for (int i=0;i<odim;i++) { for (int j=0;j<odim;j++) Hs[(size_t)i*odim+j] = (SV[i]*Hs[(size_t)i*odim+j])*SV[j]; bs[i] = SV[i]*bs[i]; }
+  std::vector<double> Hn((size_t)ndim*ndim), bn(ndim);
+  for (int i=0;i<ndim;i++) { bn[i]=bs[i]; for (int j=0;j<ndim;j++) Hn[(size_t)i*ndim+j] = 0.5*(Hs[(size_t)i*odim+j] + Hs[(size_t)j*odim+i]); }
+  HM = Hn; bM = bn;
+  frames.erase(frames.begin()+idx);
+  (void)n;
+}
+
 } // namespace orc

@@ -18,8 +18,12 @@
 //                                                    OptimizationBackend/EnergyFunctional.cpp:650-759, 221-282, 615-648, 295-350, 284-293
 //   FullSystem::optimize / doStepFromBackup / backupState / loadSateBackup / getNullspaces
 //                                                    FullSystem/FullSystemOptimize.cpp:344-502, 165-250, 255-321, 548-588
-// Scope notes: isLinearized is never set in this fork (its only writer, FullSystem.cpp:776-781, sits in a loop that never
-// executes), so the "L" accumulation is identically zero and is restated as such.  setting_solverMode =
+//   FullSystem::flagPointsForRemoval (numeric part) FullSystem/FullSystem.cpp:764-797 ; EFResidual::fixLinearizationF EnergyFunctionalStructs.cpp:46-55
+//   EnergyFunctional::marginalizePointsF / marginalizeFrame     OptimizationBackend/EnergyFunctional.cpp:514-576, 434-512
+//   AccumulatedTopHessianSSE::addPoint<2>, stitchDouble          OptimizationBackend/AccumulatedTopHessian.cpp:13-112, 118-179
+//   AccumulatedSCHessianSSE::addPoint(false), stitchDouble       OptimizationBackend/AccumulatedSCHessian.cpp:10-62, 136-195
+// Scope notes: isLinearized is set only by flagPointsForRemoval (FullSystem.cpp:781) on points that marginalizePointsF removes in the
+// same makeKeyFrame call, so inside optimize() the "L" accumulation is identically zero and is restated as such.  setting_solverMode =
 // SOLVER_ORTHOGONALIZE_X_LATER (settings.cpp:34): LDLT path, x orthogonalised against pose+scale nullspaces for iteration>=2.
 #pragma once
 #include <vector>
@@ -63,6 +67,7 @@ struct BARes {
   int state_state = RS_IN, state_NewState = RS_OUTLIER; double state_energy = 0, state_NewEnergy = 0, state_NewEnergyWithOutlier = -1;
   int isNew = 1, isActive = 0, toRemove = 0;
   RawJ J, efJ; float JpJdF[8]; float centerProjectedTo[3]; float projectedTo[8][2];
+  float res_toZeroF[2] = {0,0}; int isLinearized = 0;
 };
 struct Precalc { Mat33f PRE_RTll, PRE_KRKiTll, PRE_RTll_0; float PRE_aff_mode[2], PRE_b0_mode; Vec3f PRE_tTll, PRE_KtTll, PRE_tTll_0; };
 
@@ -101,6 +106,11 @@ struct BAWindow {
   bool doStepFromBackup(float stepfac);
   void backupState(); void loadStateBackup();
   float optimize(int mnumOptIts);
+  // ---- keyframe hand-over (FullSystem::makeKeyFrame, FullSystem.cpp:1152-1171)
+  void flagPointsForRemoval(const int* selected, int* status);   // numeric part: re-linearise + fixLinearizationF; status 0 keep / 1 PS_DROP / 2 PS_MARGINALIZE
+  void marginalizePointsF(const int* status);                    // HM,bM += 0.25 * (M - Msc) over the PS_MARGINALIZE points
+  void marginalizeFrame(int idx);                                // Schur-eliminate frame idx from HM,bM and drop it from `frames`
+  std::vector<double> margM, margMb, margMsc, margMbsc;          // last marginalizePointsF intermediates (tests)
 };
 
 } // namespace orc

@@ -160,3 +160,16 @@ void orc_ba_get_precalc(void* p, int host, int target, float* out /*9 KRKi, 3 Kt
 float orc_ba_optimize(void* p, int its, int* stats2) { BAWindow* b=(BAWindow*)p; float r=b->optimize(its); if (stats2) { stats2[0]=b->opt_iterations; stats2[1]=b->opt_accepts; } return r; }
 long long orc_ba_linearize_calls(void* p) { return ((BAWindow*)p)->linearize_calls; }
 }
+
+// ---- keyframe hand-over (marginalisation)
+extern "C" {
+void orc_ba_flag_points(void* p, const int* selected, int* status) { ((BAWindow*)p)->flagPointsForRemoval(selected, status); }
+void orc_ba_marginalize_points(void* p, const int* status, double* M, double* Mb, double* Msc, double* Mbsc) {
+  BAWindow* b=(BAWindow*)p; b->marginalizePointsF(status); size_t n=b->dim();
+  if (M) std::copy(b->margM.begin(), b->margM.end(), M); if (Mb) std::copy(b->margMb.begin(), b->margMb.end(), Mb);
+  if (Msc) std::copy(b->margMsc.begin(), b->margMsc.end(), Msc); if (Mbsc) std::copy(b->margMbsc.begin(), b->margMbsc.end(), Mbsc); (void)n; }
+void orc_ba_marginalize_frame(void* p, int idx) { ((BAWindow*)p)->marginalizeFrame(idx); }
+int  orc_ba_dim(void* p) { return ((BAWindow*)p)->dim(); }
+void orc_ba_get_prior(void* p, double* HM, double* bM) { BAWindow* b=(BAWindow*)p; std::copy(b->HM.begin(), b->HM.end(), HM); std::copy(b->bM.begin(), b->bM.end(), bM); }
+void orc_ba_get_res_to_zero(void* p, float* r2, int* isLin) { BAWindow* b=(BAWindow*)p; for (size_t i=0;i<b->res.size();i++) { r2[2*i]=b->res[i].res_toZeroF[0]; r2[2*i+1]=b->res[i].res_toZeroF[1]; isLin[i]=b->res[i].isLinearized; } }
+}
