@@ -182,6 +182,23 @@ int  sdv_ba_get_points(sdv_ctx* c, float* idepth, float* step, float* HdiF, floa
  * energies3 = {state_energy, state_NewEnergy, state_NewEnergyWithOutlier}; states: 0 IN, 1 OOB, 2 OUTLIER (Residuals.h:21) */
 int  sdv_ba_get_residuals(sdv_ctx* c, int32_t* state_state, int32_t* state_NewState, float* energies3, int32_t* isActive, float* J24, float* efJ24,
                           float* JpJdF8, float* center3, int32_t* toRemove);
+/* ---- keyframe hand-over: the numeric part of FullSystem::makeKeyFrame after optimize()      FullSystem.cpp:1152-1171
+ * sdv_ba_flag_points       FullSystem::flagPointsForRemoval :764-797 for the points the host selected
+ *                          (selected[p] = (ph->isOOB(..) || host->flaggedForMarginalization) && ph->isInlierNew(), graph bookkeeping):
+ *                          resetOOB + linearize + applyRes(true) + EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:46-55) per residual;
+ *                          status[p] = 0 untouched / 1 PS_DROP / 2 PS_MARGINALIZE (idepth_hessian > setting_minIdepthH_marg).
+ * sdv_ba_marginalize_points EnergyFunctional::marginalizePointsF, EnergyFunctional.cpp:514-576 (addPoint<2>, addPoint(p,false), stitchDouble,
+ *                          HM += margWeightFac*(M-Msc)); status==NULL uses the device-resident result of sdv_ba_flag_points.  The accumulation
+ *                          order is the order of the status==2 points in the flattened list (= allPointsToMarg when flattened after dropPointsF).
+ *                          M, Mb, Msc, Mbsc can be read through sdv_ba_get_system (HA, bA, Hsc, bsc slots).
+ * sdv_ba_marginalize_frame EnergyFunctional::marginalizeFrame, EnergyFunctional.cpp:434-512: Schur-eliminates frame idx from (HM,bM) and drops it
+ *                          from the window; points/residuals must be re-set (sdv_ba_set_points) before the window is used again.
+ * sdv_ba_get_prior         reads (HM,bM) of the current window, dim = 4 + 6*nF (row-major). */
+int  sdv_ba_flag_points(sdv_ctx* c, const int32_t* selected, int32_t* status_out);
+int  sdv_ba_marginalize_points(sdv_ctx* c, const int32_t* status);
+int  sdv_ba_marginalize_frame(sdv_ctx* c, int idx);
+int  sdv_ba_get_prior(sdv_ctx* c, int* dim, double* HM, double* bM);
+int  sdv_ba_get_linearized(sdv_ctx* c, float* res_toZero2, int32_t* isLinearized);
 int  sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
 int  sdv_ba_get_precalc(sdv_ctx* c, int host, int target, float out27[27], double adHost36[36], double adTarget36[36], float adHTdelta6[6]);
 

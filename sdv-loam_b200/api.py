@@ -262,6 +262,11 @@ def _ba_protos():
     L.sdv_ba_get_residuals.argtypes = [_vp, _i32p, _i32p, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p]
     L.sdv_ba_get_system.argtypes = [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, _f64p]
     L.sdv_ba_get_precalc.argtypes = [_vp, C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p]
+    L.sdv_ba_flag_points.argtypes = [_vp, _i32p, _i32p]
+    L.sdv_ba_marginalize_points.argtypes = [_vp, _vp]
+    L.sdv_ba_marginalize_frame.argtypes = [_vp, C.c_int]
+    L.sdv_ba_get_prior.argtypes = [_vp, C.POINTER(C.c_int), _vp, _vp]
+    L.sdv_ba_get_linearized.argtypes = [_vp, _f32p, _i32p]
     L._ba_done = True
 
 
@@ -327,6 +332,32 @@ class EnergyFunctional:
         o = dict(T_eval=np.zeros((n, 7)), state=np.zeros((n, 10)), step=np.zeros((n, 10)), frameEnergyTH=np.zeros(n, np.float32), PRE_worldToCam=np.zeros((n, 7)),
                  calib_value=np.zeros(4), calib_step=np.zeros(4))
         self.ctx._ck(LIB.sdv_ba_get_frames(self.ctx.p, o["T_eval"], o["state"], o["step"], o["frameEnergyTH"], o["PRE_worldToCam"], o["calib_value"], o["calib_step"])); return o
+
+    # ---- keyframe hand-over (FullSystem::makeKeyFrame after optimize, FullSystem.cpp:1152-1171)
+    def flagPointsForRemoval(self, selected):
+        self._sel(); st = np.zeros(self.nP, np.int32)
+        self.ctx._ck(LIB.sdv_ba_flag_points(self.ctx.p, np.ascontiguousarray(selected, np.int32), st)); return st
+
+    def marginalizePointsF(self, status=None):
+        self._sel(); st = None if status is None else np.ascontiguousarray(status, np.int32)
+        self.ctx._ck(LIB.sdv_ba_marginalize_points(self.ctx.p, None if st is None else st.ctypes.data))
+        n = self.n; M = np.zeros((n, n)); Mb = np.zeros(n); S = np.zeros((n, n)); Sb = np.zeros(n)
+        d1 = np.zeros((n, n)); d2 = np.zeros(n)
+        self.ctx._ck(LIB.sdv_ba_get_system(self.ctx.p, M, Mb, S, Sb, d1, d2))
+        return dict(M=M, Mb=Mb, Msc=S, Mbsc=Sb)
+
+    def marginalizeFrame(self, idx: int):
+        self._sel(); self.ctx._ck(LIB.sdv_ba_marginalize_frame(self.ctx.p, int(idx)))
+        self.nF -= 1; self.n -= 6; self.nP = 0; self.nR = 0
+
+    def prior(self):
+        self._sel(); d = C.c_int(0); self.ctx._ck(LIB.sdv_ba_get_prior(self.ctx.p, C.byref(d), None, None))
+        n = d.value; HM = np.zeros((n, n)); bM = np.zeros(n)
+        self.ctx._ck(LIB.sdv_ba_get_prior(self.ctx.p, C.byref(d), HM.ctypes.data, bM.ctypes.data)); return HM, bM
+
+    def linearized(self):
+        self._sel(); r = np.zeros((self.nR, 2), np.float32); l = np.zeros(self.nR, np.int32)
+        self.ctx._ck(LIB.sdv_ba_get_linearized(self.ctx.p, r, l)); return r, l
 
     def precalc(self, host, target):
         self._sel(); o = np.zeros(27, np.float32); aH = np.zeros(36); aT = np.zeros(36); d = np.zeros(6, np.float32)

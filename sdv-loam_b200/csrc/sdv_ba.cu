@@ -49,11 +49,12 @@ static size_t ba_layout(BAState* b, char* base, int cp, int cr) {
   P.priorF = bump<float>(p, cp); P.deltaF = bump<float>(p, cp); P.HdiF = bump<float>(p, cp); P.bdSumF = bump<float>(p, cp);
   P.Hdd_accAF = bump<float>(p, cp); P.bd_accAF = bump<float>(p, cp); P.Hcd_accAF = bump<float>(p, (size_t)cp*4);
   P.idepth_hessian = bump<float>(p, cp); P.maxRelBaseline = bump<float>(p, cp); P.numGoodResiduals = bump<int>(p, cp); P.ngood = bump<int>(p, cp);
-  P.res_of_target = bump<int>(p, (size_t)cp*kMaxF);
+  P.res_of_target = bump<int>(p, (size_t)cp*kMaxF); P.marg_status = bump<int>(p, cp);
   R.point = bump<int>(p, cr); R.host = bump<int>(p, cr); R.target = bump<int>(p, cr); R.hasMatcher = bump<int>(p, cr); R.matcher = bump<float2>(p, cr); R.isNew = bump<int>(p, cr);
   R.state_state = bump<int>(p, cr); R.state_NewState = bump<int>(p, cr); R.state_energy = bump<float>(p, cr); R.state_NewEnergy = bump<float>(p, cr); R.state_NewEnergyWithOutlier = bump<float>(p, cr);
   R.isActive = bump<int>(p, cr); R.toRemove = bump<int>(p, cr);
   R.J = bump<float>(p, (size_t)cr*24); R.efJ = bump<float>(p, (size_t)cr*24); R.JpJdF = bump<float>(p, (size_t)cr*8); R.center = bump<float>(p, (size_t)cr*3);
+  R.res_toZero = bump<float2>(p, cr); R.isLinearized = bump<int>(p, cr);
   R.pair_begin = bump<int>(p, kMaxF*kMaxF+1); R.pair_res = bump<int>(p, cr); R.host_begin = bump<int>(p, kMaxF+1);
   return (size_t)(p - base);
 }
@@ -310,6 +311,48 @@ int sdv_ba_get_residuals(sdv_ctx* c, int32_t* state_state, int32_t* state_NewSta
   CK(cudaStreamSynchronize(c->st));
   if (energies3) for (int i=0;i<n;i++) { energies3[3*i] = e0[i]; energies3[3*i+1] = e1[i]; energies3[3*i+2] = e2[i]; }
   return SDV_OK;
+}
+// ------------------------------------------------------------------------------------------------ keyframe hand-over (FullSystem::makeKeyFrame, FullSystem.cpp:1152-1171)
+int sdv_ba_flag_points(sdv_ctx* c, const int32_t* selected, int32_t* status_out) {
+  if (!c || !c->ba || !selected) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  if (b->nP <= 0) return ctx_fail(c, SDV_ERR_STATE, "flag_points: window has no points (call sdv_ba_set_points)");
+  WIN1();
+  CK(cudaMemcpyAsync(b->P.marg_status, selected, (size_t)b->nP*sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+  launch_ba_marg_flag(wins, 1, maxP, c->st); c->launches += 1;
+  if (status_out) CK(cudaMemcpyAsync(status_out, b->P.marg_status, (size_t)b->nP*sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  return SDV_OK;
+}
+int sdv_ba_marginalize_points(sdv_ctx* c, const int32_t* status) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  if (b->nP <= 0) return ctx_fail(c, SDV_ERR_STATE, "marginalize_points: window has no points");
+  WIN1();
+  if (status) CK(cudaMemcpyAsync(b->P.marg_status, status, (size_t)b->nP*sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
+  launch_ba_marg_points(wins, 1, maxP, c->st); c->launches += 4;
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  return SDV_OK;
+}
+int sdv_ba_marginalize_frame(sdv_ctx* c, int idx) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  if (idx < 0 || idx >= b->nF || b->nF < 2) return ctx_fail(c, SDV_ERR_ARG, "marginalize_frame: frame %d of %d", idx, b->nF);
+  WIN1();
+  launch_ba_marg_frame(wins, 1, idx, c->st); c->launches += 1;
+  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  b->nF -= 1; b->nP = 0; b->nR = 0;                                          // points/residuals are stale: the caller re-flattens the window (sdv_ba_set_points)
+  return SDV_OK;
+}
+int sdv_ba_get_prior(sdv_ctx* c, int* dim, double* HM, double* bM) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int N = kCP + 6*b->nF;
+  if (dim) *dim = N;
+  if (HM) CK(cudaMemcpyAsync(HM, b->hdr->HM, (size_t)N*N*sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  if (bM) CK(cudaMemcpyAsync(bM, b->hdr->bM, (size_t)N*sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+}
+int sdv_ba_get_linearized(sdv_ctx* c, float* res_toZero2, int32_t* isLinearized) {
+  if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  if (res_toZero2) CK(cudaMemcpyAsync(res_toZero2, b->R.res_toZero, (size_t)b->nR*2*sizeof(float), cudaMemcpyDeviceToHost, c->st));
+  if (isLinearized) CK(cudaMemcpyAsync(isLinearized, b->R.isLinearized, (size_t)b->nR*sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
 }
 int sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS) {
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int N = kCP + 6*b->nF;

@@ -71,6 +71,7 @@ struct BAPointsDev {                     // SoA over points
   float* priorF; float* deltaF; float* HdiF; float* bdSumF; float* Hdd_accAF; float* bd_accAF; float* Hcd_accAF;   // Hcd [nP*4]
   float* idepth_hessian; float* maxRelBaseline; int* numGoodResiduals; int* ngood;
   int* res_of_target;                    // [nP*kMaxF] residual index towards target t or -1
+  int* marg_status;                      // keyframe hand-over: 0 keep / 1 PS_DROP / 2 PS_MARGINALIZE (flagPointsForRemoval)
 };
 struct BAResDev {                        // SoA over residuals
   int* point; int* host; int* target; int* hasMatcher; float2* matcher; int* isNew;
@@ -79,6 +80,7 @@ struct BAResDev {                        // SoA over residuals
   float* J; float* efJ;                  // [nR*24] {resF[2], Jpdxi[0][6], Jpdxi[1][6], Jpdc[0][4], Jpdc[1][4], Jpdd[2]}
   float* JpJdF;                          // [nR*8]
   float* center;                         // [nR*3] centerProjectedTo
+  float2* res_toZero; int* isLinearized; // EFResidual::res_toZeroF / isLinearized (fixLinearizationF)
   int* pair_begin; int* pair_res;        // residual indices grouped by (host + nF*target), in residual order
   int* host_begin;                       // point range per host frame [nF+1]
 };
@@ -107,6 +109,10 @@ void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, doubl
 void launch_ba_backup(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st);
 void launch_ba_step(const BAWinDev* wins, int W, float stepfac, int load_backup, int gate, cudaStream_t st);
 void launch_ba_reanchor(const BAWinDev* wins, int W, int maxP, cudaStream_t st);
+// keyframe hand-over (FullSystem::makeKeyFrame, FullSystem.cpp:1152-1171)
+void launch_ba_marg_flag(const BAWinDev* wins, int W, int maxP, cudaStream_t st);           // flagPointsForRemoval numeric part; P.marg_status in: selected, out: status
+void launch_ba_marg_points(const BAWinDev* wins, int W, int maxP, cudaStream_t st);         // marginalizePointsF
+void launch_ba_marg_frame(const BAWinDev* wins, int W, int idx, cudaStream_t st);           // marginalizeFrame (frame idx of every window)
 void launch_ba_decide(const BAWinDev* wins, int W, int stage, cudaStream_t st);              // 0 init, 1 after step+linearize, 2 after reload, 3 final rmse
 
 } // namespace sdv

@@ -157,6 +157,98 @@ __device__ __forceinline__ void apply_res(BAResDev& R, int r) {            // Re
   R.state_state[r] = R.state_NewState[r]; R.state_energy[r] = R.state_NewEnergy[r];
 }
 
+// PointFrameResidual::linearize (Residuals.cpp:60-224) for residual r; returns the energy the caller sums (state_energy for OOB residuals).
+// thbuf != nullptr: also collect the setNewFrameEnergyTH candidates (linearizeAll_Reductor, FullSystemOptimize.cpp:23-29).
+__device__ __forceinline__ double lin_residual(BAHeader* __restrict__ H, BAPointsDev& P, BAResDev& R, int r, float* __restrict__ thbuf, int* __restrict__ thcount) {
+  double energy = 0;
+  R.state_NewEnergyWithOutlier[r] = -1;
+  bool done = false;
+  if (R.state_state[r] == RS_OOB) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+  const int nF = H->nF; const int hI = R.host[r], tI = R.target[r], pI = R.point[r];
+  const PrecalcDev& pc = H->precalc[hI*nF + tI];
+  const float wM3G = (float)(H->w - 3), hM3G = (float)(H->h - 3);
+  const float fxl = H->calib.sf[0], fyl = H->calib.sf[1], cxl = H->calib.sf[2], cyl = H->calib.sf[3], fxli = H->calib.si[0], fyli = H->calib.si[1];
+  float J[24]; float Ku = 0, Kv = 0;
+  if (!done && !R.hasMatcher[r]) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+  const float2 uv = P.uv[pI];
+  if (!done) {
+    const float idz = P.idepth_zero[pI]*1.0f;                                     // idepth_zero_scaled
+    float KliP0 = (uv.x+0-cxl)*fxli, KliP1 = (uv.y+0-cyl)*fyli, KliP2 = 1;
+    float p0 = ((pc.R0[0]*KliP0 + pc.R0[1]*KliP1) + pc.R0[2]*KliP2) + pc.t0[0]*idz;
+    float p1 = ((pc.R0[3]*KliP0 + pc.R0[4]*KliP1) + pc.R0[5]*KliP2) + pc.t0[1]*idz;
+    float p2 = ((pc.R0[6]*KliP0 + pc.R0[7]*KliP1) + pc.R0[8]*KliP2) + pc.t0[2]*idz;
+    float drescale = 1.0f/p2; float new_idepth = idz*drescale;
+    float u = p0*drescale, v = p1*drescale;
+    Ku = u*fxl + cxl; Kv = v*fyl + cyl;
+    if (!(drescale > 0) || !(Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G)) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+    else {
+      R.center[(size_t)r*3] = Ku; R.center[(size_t)r*3+1] = Kv; R.center[(size_t)r*3+2] = new_idepth;
+      float d_d_x = drescale * (pc.t0[0]-pc.t0[2]*u)*1.0f*fxl;
+      float d_d_y = drescale * (pc.t0[1]-pc.t0[2]*v)*1.0f*fyl;
+      float cx2 = drescale*(pc.R0[6]*u-pc.R0[0]);
+      float cx3 = fxl * drescale*(pc.R0[7]*u-pc.R0[1]) * fyli;
+      float cx0 = KliP0*cx2, cx1 = KliP1*cx3;
+      float cy2 = fyl * drescale*(pc.R0[6]*v-pc.R0[3]) * fxli;
+      float cy3 = drescale*(pc.R0[7]*v-pc.R0[4]);
+      float cy0 = KliP0*cy2, cy1 = KliP1*cy3;
+      cx0 = (cx0+u)*50.0f; cx1 *= 50.0f; cx2 = (cx2+1)*50.0f; cx3 *= 50.0f;
+      cy0 *= 50.0f; cy1 = (cy1+v)*50.0f; cy2 *= 50.0f; cy3 = (cy3+1)*50.0f;
+      J[2] = new_idepth*fxl; J[3] = 0; J[4] = -new_idepth*u*fxl; J[5] = -u*v*fxl; J[6] = (1+u*u)*fxl; J[7] = -v*fxl;
+      J[8] = 0; J[9] = new_idepth*fyl; J[10] = -new_idepth*v*fyl; J[11] = -(1+v*v)*fyl; J[12] = u*v*fyl; J[13] = u*fyl;
+      J[14] = cx0; J[15] = cx1; J[16] = cx2; J[17] = cx3; J[18] = cy0; J[19] = cy1; J[20] = cy2; J[21] = cy3;
+      J[22] = d_d_x; J[23] = d_d_y;
+    }
+  }
+  if (!done) {
+    // photometric 8-pattern outlier gate at the CURRENT pose (Residuals.cpp:157-194)
+    const float4* __restrict__ img = H->frames[tI].img0; const int wI = H->w;
+    const float ids = P.idepth[pI]*1.0f; const float a0 = pc.aff[0], a1 = pc.aff[1];
+    float wJI2_sum = 0, energyLeft2 = 0.0f;
+    for (int idx = 0; idx < 8; idx++) {
+      float x = uv.x + c_pattern[idx][0], y = uv.y + c_pattern[idx][1];
+      float q0 = ((pc.KRKi[0]*x + pc.KRKi[1]*y) + pc.KRKi[2]*1.0f) + pc.Kt[0]*ids;
+      float q1 = ((pc.KRKi[3]*x + pc.KRKi[4]*y) + pc.KRKi[5]*1.0f) + pc.Kt[1]*ids;
+      float q2 = ((pc.KRKi[6]*x + pc.KRKi[7]*y) + pc.KRKi[8]*1.0f) + pc.Kt[2]*ids;
+      float Ku2 = q0/q2, Kv2 = q1/q2;
+      if (!(Ku2 > 1.1f && Kv2 > 1.1f && Ku2 < wM3G && Kv2 < hM3G)) break;
+      int ix = (int)Ku2, iy = (int)Kv2; float dx = Ku2-ix, dy = Kv2-iy, dxdy = dx*dy;
+      const float4* bp = img + ix + iy*wI;
+      float4 p00 = __ldg(bp), p10 = __ldg(bp+1), p01 = __ldg(bp+wI), p11 = __ldg(bp+1+wI);
+      float w11 = dxdy, w01 = dy-dxdy, w10 = dx-dxdy, w00 = 1-dx-dy+dxdy;
+      float h0 = ((w11*p11.x + w01*p01.x) + w10*p10.x) + w00*p00.x;
+      float h1 = ((w11*p11.y + w01*p01.y) + w10*p10.y) + w00*p00.y;
+      float h2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
+      float residual = h0 - (a0*P.color[(size_t)pI*8+idx] + a1);
+      if (!isfinite(h0)) break;
+      float wgt = sqrtf(H->set.outlierTHSumComponent / (H->set.outlierTHSumComponent + (h1*h1 + h2*h2)));
+      wgt = 0.5f*(wgt + P.weights[(size_t)pI*8+idx]);
+      float hw = fabsf(residual) < H->set.huberTH ? 1 : H->set.huberTH / fabsf(residual);
+      energyLeft2 += wgt*wgt*hw*residual*residual*(2-hw);
+      if (hw < 1) hw = sqrtf(hw);
+      hw = hw*wgt; h1 *= hw; h2 *= hw;
+      wJI2_sum += hw*hw*(h1*h1 + h2*h2);
+    }
+    const float2 m = R.matcher[r];
+    float res0 = Ku - m.x, res1 = Kv - m.y;
+    float nrm = sqrtf(res0*res0 + res1*res1);
+    float hw = fabsf(nrm) < H->set.huberTH ? 1 : H->set.huberTH / fabsf(nrm);
+    float energyLeft = hw * (res0*res0 + res1*res1)*(2-hw);
+    if (hw < 1) hw = sqrtf(hw);
+    J[0] = res0*hw; J[1] = res1*hw;
+#pragma unroll
+    for (int k=2;k<24;k++) J[k] = J[k]*hw;
+#pragma unroll
+    for (int k=0;k<24;k++) R.J[(size_t)r*24+k] = J[k];
+    R.state_NewEnergyWithOutlier[r] = energyLeft2;
+    float th = fmaxf(H->frames[hI].frameEnergyTH, H->frames[tI].frameEnergyTH);
+    if (energyLeft2 > th || wJI2_sum < 2) { R.state_NewEnergy[r] = th; R.state_NewState[r] = RS_OUTLIER; }
+    else { R.state_NewEnergy[r] = energyLeft2; R.state_NewState[r] = RS_IN; }
+    energy = energyLeft;
+    if (thbuf && tI == nF-1) { int slot = atomicAdd(thcount, 1); thbuf[slot] = energyLeft2; }       // setNewFrameEnergyTH candidates (order-free)
+  }
+  return energy;
+}
+
 constexpr int kLinThreads = 128;
 __global__ void __launch_bounds__(kLinThreads) ba_linearize_kernel(const BAWinDev* __restrict__ wins, int fix, int gate) {
   BA_WIN(gate)
@@ -166,91 +258,9 @@ __global__ void __launch_bounds__(kLinThreads) ba_linearize_kernel(const BAWinDe
   const int r = blockIdx.x*kLinThreads + threadIdx.x;
   double energy = 0;
   if (r < nR) {
-    R.state_NewEnergyWithOutlier[r] = -1;
-    bool done = false;
-    if (R.state_state[r] == RS_OOB) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
+    energy = lin_residual(H, P, R, r, thbuf, thcount);
     const int nF = H->nF; const int hI = R.host[r], tI = R.target[r], pI = R.point[r];
-    const PrecalcDev& pc = H->precalc[hI*nF + tI];
-    const float wM3G = (float)(H->w - 3), hM3G = (float)(H->h - 3);
-    const float fxl = H->calib.sf[0], fyl = H->calib.sf[1], cxl = H->calib.sf[2], cyl = H->calib.sf[3], fxli = H->calib.si[0], fyli = H->calib.si[1];
-    float J[24]; float Ku = 0, Kv = 0;
-    if (!done && !R.hasMatcher[r]) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
-    const float2 uv = P.uv[pI];
-    if (!done) {
-      const float idz = P.idepth_zero[pI]*1.0f;                                     // idepth_zero_scaled
-      float KliP0 = (uv.x+0-cxl)*fxli, KliP1 = (uv.y+0-cyl)*fyli, KliP2 = 1;
-      float p0 = ((pc.R0[0]*KliP0 + pc.R0[1]*KliP1) + pc.R0[2]*KliP2) + pc.t0[0]*idz;
-      float p1 = ((pc.R0[3]*KliP0 + pc.R0[4]*KliP1) + pc.R0[5]*KliP2) + pc.t0[1]*idz;
-      float p2 = ((pc.R0[6]*KliP0 + pc.R0[7]*KliP1) + pc.R0[8]*KliP2) + pc.t0[2]*idz;
-      float drescale = 1.0f/p2; float new_idepth = idz*drescale;
-      float u = p0*drescale, v = p1*drescale;
-      Ku = u*fxl + cxl; Kv = v*fyl + cyl;
-      if (!(drescale > 0) || !(Ku > 1.1f && Kv > 1.1f && Ku < wM3G && Kv < hM3G)) { R.state_NewState[r] = RS_OOB; energy = R.state_energy[r]; done = true; }
-      else {
-        R.center[(size_t)r*3] = Ku; R.center[(size_t)r*3+1] = Kv; R.center[(size_t)r*3+2] = new_idepth;
-        float d_d_x = drescale * (pc.t0[0]-pc.t0[2]*u)*1.0f*fxl;
-        float d_d_y = drescale * (pc.t0[1]-pc.t0[2]*v)*1.0f*fyl;
-        float cx2 = drescale*(pc.R0[6]*u-pc.R0[0]);
-        float cx3 = fxl * drescale*(pc.R0[7]*u-pc.R0[1]) * fyli;
-        float cx0 = KliP0*cx2, cx1 = KliP1*cx3;
-        float cy2 = fyl * drescale*(pc.R0[6]*v-pc.R0[3]) * fxli;
-        float cy3 = drescale*(pc.R0[7]*v-pc.R0[4]);
-        float cy0 = KliP0*cy2, cy1 = KliP1*cy3;
-        cx0 = (cx0+u)*50.0f; cx1 *= 50.0f; cx2 = (cx2+1)*50.0f; cx3 *= 50.0f;
-        cy0 *= 50.0f; cy1 = (cy1+v)*50.0f; cy2 *= 50.0f; cy3 = (cy3+1)*50.0f;
-        J[2] = new_idepth*fxl; J[3] = 0; J[4] = -new_idepth*u*fxl; J[5] = -u*v*fxl; J[6] = (1+u*u)*fxl; J[7] = -v*fxl;
-        J[8] = 0; J[9] = new_idepth*fyl; J[10] = -new_idepth*v*fyl; J[11] = -(1+v*v)*fyl; J[12] = u*v*fyl; J[13] = u*fyl;
-        J[14] = cx0; J[15] = cx1; J[16] = cx2; J[17] = cx3; J[18] = cy0; J[19] = cy1; J[20] = cy2; J[21] = cy3;
-        J[22] = d_d_x; J[23] = d_d_y;
-      }
-    }
-    if (!done) {
-      // photometric 8-pattern outlier gate at the CURRENT pose (Residuals.cpp:157-194)
-      const float4* __restrict__ img = H->frames[tI].img0; const int wI = H->w;
-      const float ids = P.idepth[pI]*1.0f; const float a0 = pc.aff[0], a1 = pc.aff[1];
-      float wJI2_sum = 0, energyLeft2 = 0.0f;
-      for (int idx = 0; idx < 8; idx++) {
-        float x = uv.x + c_pattern[idx][0], y = uv.y + c_pattern[idx][1];
-        float q0 = ((pc.KRKi[0]*x + pc.KRKi[1]*y) + pc.KRKi[2]*1.0f) + pc.Kt[0]*ids;
-        float q1 = ((pc.KRKi[3]*x + pc.KRKi[4]*y) + pc.KRKi[5]*1.0f) + pc.Kt[1]*ids;
-        float q2 = ((pc.KRKi[6]*x + pc.KRKi[7]*y) + pc.KRKi[8]*1.0f) + pc.Kt[2]*ids;
-        float Ku2 = q0/q2, Kv2 = q1/q2;
-        if (!(Ku2 > 1.1f && Kv2 > 1.1f && Ku2 < wM3G && Kv2 < hM3G)) break;
-        int ix = (int)Ku2, iy = (int)Kv2; float dx = Ku2-ix, dy = Kv2-iy, dxdy = dx*dy;
-        const float4* bp = img + ix + iy*wI;
-        float4 p00 = __ldg(bp), p10 = __ldg(bp+1), p01 = __ldg(bp+wI), p11 = __ldg(bp+1+wI);
-        float w11 = dxdy, w01 = dy-dxdy, w10 = dx-dxdy, w00 = 1-dx-dy+dxdy;
-        float h0 = ((w11*p11.x + w01*p01.x) + w10*p10.x) + w00*p00.x;
-        float h1 = ((w11*p11.y + w01*p01.y) + w10*p10.y) + w00*p00.y;
-        float h2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
-        float residual = h0 - (a0*P.color[(size_t)pI*8+idx] + a1);
-        if (!isfinite(h0)) break;
-        float wgt = sqrtf(H->set.outlierTHSumComponent / (H->set.outlierTHSumComponent + (h1*h1 + h2*h2)));
-        wgt = 0.5f*(wgt + P.weights[(size_t)pI*8+idx]);
-        float hw = fabsf(residual) < H->set.huberTH ? 1 : H->set.huberTH / fabsf(residual);
-        energyLeft2 += wgt*wgt*hw*residual*residual*(2-hw);
-        if (hw < 1) hw = sqrtf(hw);
-        hw = hw*wgt; h1 *= hw; h2 *= hw;
-        wJI2_sum += hw*hw*(h1*h1 + h2*h2);
-      }
-      const float2 m = R.matcher[r];
-      float res0 = Ku - m.x, res1 = Kv - m.y;
-      float nrm = sqrtf(res0*res0 + res1*res1);
-      float hw = fabsf(nrm) < H->set.huberTH ? 1 : H->set.huberTH / fabsf(nrm);
-      float energyLeft = hw * (res0*res0 + res1*res1)*(2-hw);
-      if (hw < 1) hw = sqrtf(hw);
-      J[0] = res0*hw; J[1] = res1*hw;
-#pragma unroll
-      for (int k=2;k<24;k++) J[k] = J[k]*hw;
-#pragma unroll
-      for (int k=0;k<24;k++) R.J[(size_t)r*24+k] = J[k];
-      R.state_NewEnergyWithOutlier[r] = energyLeft2;
-      float th = fmaxf(H->frames[hI].frameEnergyTH, H->frames[tI].frameEnergyTH);
-      if (energyLeft2 > th || wJI2_sum < 2) { R.state_NewEnergy[r] = th; R.state_NewState[r] = RS_OUTLIER; }
-      else { R.state_NewEnergy[r] = energyLeft2; R.state_NewState[r] = RS_IN; }
-      energy = energyLeft;
-      if (tI == nF-1) { int slot = atomicAdd(thcount, 1); thbuf[slot] = energyLeft2; }       // setNewFrameEnergyTH candidates (order-free)
-    }
+    const PrecalcDev& pc = H->precalc[hI*nF + tI]; const float2 uv = P.uv[pI]; (void)tI;
     if (fix) {                                                              // linearizeAll_Reductor, fixLinearization branch (FullSystemOptimize.cpp:30-53)
       apply_res(R, r);
       if (R.isActive[r]) {
@@ -339,14 +349,19 @@ __global__ void __launch_bounds__(256) ba_energies_kernel(const BAWinDev* __rest
 
 // ================================================================================================ accumulation
 // per point: Hdd/bd/Hcd sums over its active residuals in order (addPoint<0>), then HdiF / bdSumF (SC addPoint head)
-__global__ void ba_point_acc_kernel(const BAWinDev* __restrict__ wins, int gate) {
+// mode 0: addPoint<0> + addPoint(p, shiftPriorToZero=true) over all points (solveSystemF).
+// mode 2: addPoint<2> + addPoint(p, false) over the PS_MARGINALIZE points (marginalizePointsF, EnergyFunctional.cpp:527,543-547): resApprox =
+//         res_toZeroF, priorF *= setting_idepthFixPriorMargFac, no prior shift; the "L" sums are stored in the A slots (only A+L is ever read).
+__global__ void ba_point_acc_kernel(const BAWinDev* __restrict__ wins, int gate, int mode) {
   BA_WIN(gate)
   int p = blockIdx.x*blockDim.x + threadIdx.x; if (p >= nP) return;
+  if (mode == 2) { if (P.marg_status[p] != 2) { P.ngood[p] = 0; return; } P.priorF[p] *= 600.0f*600.0f; }
   float bd = 0, Hdd = 0, Hcd[4] = {0,0,0,0}; int ngood = 0;
   for (int r = P.res_begin[p]; r < P.res_begin[p+1]; r++) {
     if (!R.isActive[r]) continue;
     const float* J = R.efJ + (size_t)r*24; ngood++;
-    bd += J[0]*J[22] + J[1]*J[23];
+    const float2 rz = (mode == 2) ? R.res_toZero[r] : make_float2(J[0], J[1]);
+    bd += rz.x*J[22] + rz.y*J[23];
     Hdd += J[22]*J[22] + J[23]*J[23];
     for (int i=0;i<4;i++) Hcd[i] += J[14+i]*J[22] + J[18+i]*J[23];
   }
@@ -355,7 +370,7 @@ __global__ void ba_point_acc_kernel(const BAWinDev* __restrict__ wins, int gate)
   if (ngood == 0) { P.HdiF[p] = 0; P.bdSumF[p] = 0; P.idepth_hessian[p] = 0; P.maxRelBaseline[p] = 0; return; }   // AccumulatedSCHessian.cpp:12-21
   float Hh = Hdd + 0.0f + P.priorF[p]; if (Hh < 1e-10) Hh = 1e-10;
   P.idepth_hessian[p] = Hh; P.HdiF[p] = (float)(1.0 / (double)Hh);
-  float bs = bd + 0.0f; bs += P.priorF[p]*P.deltaF[p]; P.bdSumF[p] = bs;
+  float bs = bd + 0.0f; if (mode != 2) bs += P.priorF[p]*P.deltaF[p]; P.bdSumF[p] = bs;
 }
 
 struct Tier { float d, d1k, d1m, n1, n1k; };
@@ -367,7 +382,7 @@ __device__ __forceinline__ float tier_finish(Tier& t) { t.d1k = t.d + t.d1k; t.d
 
 // one CTA per (host,target) bucket; thread e < 66 owns one cell of AccumulatorApprox and walks the pair's residuals in order
 constexpr int kTopChunk = 32;
-__global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restrict__ wins, int gate) {
+__global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restrict__ wins, int gate, int mode) {
   BA_WIN(gate)
   if ((int)blockIdx.x >= H->nF*H->nF) return;
   const int pair = blockIdx.x; const int e = threadIdx.x;
@@ -380,8 +395,9 @@ __global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restri
   for (int base = b0; base < b1; base += kTopChunk) {
     const int cnt = min(kTopChunk, b1 - base);
     __syncthreads();
-    for (int k = threadIdx.x; k < cnt*24; k += 96) { int q = k/24, c = k - q*24; int r = R.pair_res[base+q]; sJ[q][c] = R.efJ[(size_t)r*24+c]; }
-    if (threadIdx.x < cnt) sAct[threadIdx.x] = R.isActive[R.pair_res[base+threadIdx.x]];
+    for (int k = threadIdx.x; k < cnt*24; k += 96) { int q = k/24, c = k - q*24; int r = R.pair_res[base+q];
+      float v = R.efJ[(size_t)r*24+c]; if (mode == 2 && c < 2) { const float2 rz = R.res_toZero[r]; v = c ? rz.y : rz.x; } sJ[q][c] = v; }
+    if (threadIdx.x < cnt) { int r = R.pair_res[base+threadIdx.x]; int a = R.isActive[r]; if (mode == 2 && P.marg_status[R.point[r]] != 2) a = 0; sAct[threadIdx.x] = a; }
     __syncthreads();
     if (e < kNTop) {
       for (int q = 0; q < cnt; q++) {
@@ -507,14 +523,15 @@ template <typename MF> __device__ __forceinline__ double triple66(const double* 
 }
 
 constexpr int kSolveThreads = 512;
-__global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev* __restrict__ wins, int iteration_arg, double lambda_arg, int use_hdr_ctl, int gate) {
-  BA_WIN(gate)
-  const int iteration = use_hdr_ctl ? H->iteration : iteration_arg; const double lambda = use_hdr_ctl ? H->lambda : lambda_arg;
-  const int tid = threadIdx.x; const int nF = H->nF, N = H->dim, nF2 = nF*nF;
-  __shared__ double sA[kMaxDim*kMaxDim];                                    // HA -> HFinal (scaled) -> LDLT in place
-  __shared__ double sS[kMaxDim*kMaxDim];                                    // Hsc -> nullspace basis
-  __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim], sbA[kMaxDim], sbS[kMaxDim];
-  __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double srot[4];
+// Stitch the accumulated top (sA, sbA) and Schur (sS, sbS) systems from the per-bucket float accumulators.
+//   MARG = false: stitchDoubleMT as solveSystemF calls it (buckets walked k = h + nF*t ascending, priors and deltas added)
+//                 AccumulatedTopHessian.cpp:181-242 + .h:63-114, AccumulatedSCHessian.cpp:64-135 + .h:68-111
+//   MARG = true : the single-threaded stitchDouble of marginalizePointsF (h outer / t inner, no priors)
+//                 AccumulatedTopHessian.cpp:118-179, AccumulatedSCHessian.cpp:136-195
+template <bool MARG>
+__device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int tid, const int nF, const int N, const int nF2,
+                                          double* __restrict__ sA, double* __restrict__ sS, double* __restrict__ sbA, double* __restrict__ sbS) {
+#define BK(kk) (MARG ? ((kk)/nF + nF*((kk)%nF)) : (kk))
   // ---- products shared by many output elements, in the reference's operation order: T1 = AH*M, T3 = AT*M (top buckets), AH_ij*D, AT_ij*D (Schur buckets)
   for (int task = tid; task < nF2*72; task += kSolveThreads) {
     const int k = task/72, e = task%72, which = e/36, i = (e%36)/6, q = e%6; if (H->accTopNum[k] == 0) continue;
@@ -532,7 +549,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   // ---- top: frame-frame blocks (raw), frame-calib blocks, calib block, gradient
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
-    for (int k = 0; k < nF2; k++) {
+    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk);
       const int h = k % nF, t = k / nF; if (!((a == h || a == t) && (b == h || b == t))) continue;
       if (H->accTopNum[k] == 0) continue;                                  // empty bucket contributes exact zeros
       const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36; const double* T1 = H->topT1 + k*36 + i*6; const double* T3 = H->topT3 + k*36 + i*6;
@@ -540,31 +557,31 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
       if (a == t && b == t) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*AT[j*6+q]; acc += s2; }
       if (a == h && b == t) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AT[j*6+q]; acc += s2; }
     }
-    if (a == b && i == j) acc += H->frames[a].prior[i];
+    if (!MARG && a == b && i == j) acc += H->frames[a].prior[i];
     sA[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
   }
   for (int task = tid; task < nF*24; task += kSolveThreads) {              // H[frame a, calib] (6x4)
     const int a = task/24, r = (task%24)/4, c = task%4; double acc = 0;
-    for (int k = 0; k < nF2; k++) { const int h = k % nF, t = k / nF; if (a != h && a != t) continue; if (H->accTopNum[k] == 0) continue;
+    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int h = k % nF, t = k / nF; if (a != h && a != t) continue; if (H->accTopNum[k] == 0) continue;
       const float* m = H->accTop + k*kNTop;
       if (a == h) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*tri10(m, 4+q, c); acc += s1; }
       if (a == t) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*tri10(m, 4+q, c); acc += s2; } }
     sA[(kCP+a*6+r)*N + c] = acc;
   }
   if (tid < 16) { const int r = tid/4, c = tid%4; double acc = 0; int resInA = 0;
-    for (int k = 0; k < nF2; k++) { resInA += H->accTopNum[k]; if (H->accTopNum[k] == 0) continue; acc += tri10(H->accTop + k*kNTop, r, c); }
-    if (r == c) acc += H->calib.cPrior[r];
-    sA[r*N + c] = acc; if (tid == 0) H->resInA = resInA; }
+    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); resInA += H->accTopNum[k]; if (H->accTopNum[k] == 0) continue; acc += tri10(H->accTop + k*kNTop, r, c); }
+    if (!MARG && r == c) acc += H->calib.cPrior[r];
+    sA[r*N + c] = acc; if (!MARG && tid == 0) H->resInA = resInA; }
   for (int task = tid; task < N; task += kSolveThreads) {                  // bA
     double acc = 0;
-    if (task < kCP) { for (int k = 0; k < nF2; k++) { if (H->accTopNum[k] == 0) continue; acc += (double)H->accTop[k*kNTop + 55 + task]; }
-      acc += H->calib.cPrior[task]*(double)H->calib.cDeltaF[task]; }
+    if (task < kCP) { for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); if (H->accTopNum[k] == 0) continue; acc += (double)H->accTop[k*kNTop + 55 + task]; }
+      if (!MARG) acc += H->calib.cPrior[task]*(double)H->calib.cDeltaF[task]; }
     else { const int a = (task-kCP)/6, r = (task-kCP)%6;
-      for (int k = 0; k < nF2; k++) { const int h = k % nF, t = k / nF; if (a != h && a != t) continue; if (H->accTopNum[k] == 0) continue;
+      for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int h = k % nF, t = k / nF; if (a != h && a != t) continue; if (H->accTopNum[k] == 0) continue;
         const float* m = H->accTop + k*kNTop;
         if (a == h) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*(double)m[55+4+q]; acc += s1; }
         if (a == t) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*(double)m[55+4+q]; acc += s2; } }
-      acc += H->frames[a].prior[r]*H->frames[a].delta_prior[r]; }
+      if (!MARG) acc += H->frames[a].prior[r]*H->frames[a].delta_prior[r]; }
     sbA[task] = acc;
   }
   __syncthreads();
@@ -578,7 +595,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   // ---- Schur complement: frame-frame blocks
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
-    for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
       for (int k2 = 0; k2 < nF; k2++) {
         const bool c1 = (a == fi && b == fi), c2 = (a == fj && b == k2), c3 = (a == fj && b == fi), c4 = (a == fi && b == k2);
         if (!(c1 || c2 || c3 || c4)) continue;
@@ -595,7 +612,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   }
   for (int task = tid; task < nF*24; task += kSolveThreads) {              // Hsc[frame a, calib]
     const int a = task/24, r = (task%24)/4, c = task%4; double acc = 0;
-    for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
       if (a == fi) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*(double)H->accE[k*24+q*4+c]; acc += s1; }
       if (a == fj) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*(double)H->accE[k*24+q*4+c]; acc += s2; } }
     sS[(kCP+a*6+r)*N + c] = acc;
@@ -605,7 +622,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
     double acc = 0;
     if (task < kCP) acc = (double)H->accbc[task];
     else { const int a = (task-kCP)/6, r = (task-kCP)%6;
-      for (int k = 0; k < nF2; k++) { const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+      for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
         if (a == fi) { const double* AH = H->adHost + k*36; double s1 = 0; for (int q=0;q<6;q++) s1 += AH[r*6+q]*(double)H->accEB[k*6+q]; acc += s1; }
         if (a == fj) { const double* AT = H->adTarget + k*36; double s2 = 0; for (int q=0;q<6;q++) s2 += AT[r*6+q]*(double)H->accEB[k*6+q]; acc += s2; } } }
     sbS[task] = acc;
@@ -613,6 +630,18 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   __syncthreads();
   for (int task = tid; task < nF*24; task += kSolveThreads) { const int a = task/24, r = (task%24)/6, c = task%6; sS[r*N + kCP+a*6+c] = sS[(kCP+a*6+c)*N + r]; }
   __syncthreads();
+#undef BK
+}
+
+__global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev* __restrict__ wins, int iteration_arg, double lambda_arg, int use_hdr_ctl, int gate) {
+  BA_WIN(gate)
+  const int iteration = use_hdr_ctl ? H->iteration : iteration_arg; const double lambda = use_hdr_ctl ? H->lambda : lambda_arg;
+  const int tid = threadIdx.x; const int nF = H->nF, N = H->dim, nF2 = nF*nF;
+  __shared__ double sA[kMaxDim*kMaxDim];                                    // HA -> HFinal (scaled) -> LDLT in place
+  __shared__ double sS[kMaxDim*kMaxDim];                                    // Hsc -> nullspace basis
+  __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim], sbA[kMaxDim], sbS[kMaxDim];
+  __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double srot[4];
+  ba_stitch<false>(H, tid, nF, N, nF2, sA, sS, sbA, sbS);
   // ---- publish HA/bA/Hsc/bsc (read-back for tests), HFinal / bFinal, damping, diagonal pre-scaling (EnergyFunctional.cpp:668-744)
   for (int i = tid; i < N*N; i += kSolveThreads) { H->HA[i] = sA[i]; H->Hsc[i] = sS[i]; double v = sA[i] + H->HM[i] - sS[i]; H->lastHS[i] = v; sA[i] = v; }
   if (tid < N) {
@@ -786,6 +815,96 @@ __global__ void ba_decide_kernel(const BAWinDev* __restrict__ wins, int W, int s
   }
 }
 
+// ================================================================================================ keyframe hand-over: marginalisation
+// FullSystem::flagPointsForRemoval, numeric part (FullSystem.cpp:764-797).  P.marg_status[p] holds the host-side predicate on entry
+// ((isOOB || host flagged) && isInlierNew — graph bookkeeping) and the resulting EFPointStatus on exit.  One thread per point: its
+// residuals are re-linearised at the current state (resetOOB, linearize, applyRes(true)) and frozen by fixLinearizationF.
+__global__ void __launch_bounds__(128) ba_marg_flag_kernel(const BAWinDev* __restrict__ wins) {
+  BA_WIN(0)
+  const int p = blockIdx.x*blockDim.x + threadIdx.x; if (p >= nP) return;
+  if (!P.marg_status[p]) return;
+  const int nF = H->nF; const float deltaF = P.deltaF[p];
+  for (int r = P.res_begin[p]; r < P.res_begin[p+1]; r++) {
+    R.state_NewEnergy[r] = 0; R.state_energy[r] = 0; R.state_NewState[r] = RS_OUTLIER; R.state_state[r] = RS_IN;
+    lin_residual(H, P, R, r, nullptr, nullptr);
+    R.isLinearized[r] = 0;
+    apply_res(R, r);
+    if (R.isActive[r]) {                                                     // EFResidual::fixLinearizationF (EnergyFunctionalStructs.cpp:46-55)
+      const float* J = R.efJ + (size_t)r*24; const float* dp = H->adHTdeltaF + (R.host[r] + nF*R.target[r])*6;
+      float dx0 = 0, dx1 = 0, dc0 = 0, dc1 = 0;
+      for (int i=0;i<6;i++) { dx0 += J[2+i]*dp[i]; dx1 += J[8+i]*dp[i]; }
+      for (int i=0;i<4;i++) { dc0 += J[14+i]*H->calib.cDeltaF[i]; dc1 += J[18+i]*H->calib.cDeltaF[i]; }
+      const float Jp_delta_x = dx0 + dc0 + J[22]*deltaF, Jp_delta_y = dx1 + dc1 + J[23]*deltaF;
+      R.res_toZero[r] = make_float2(J[0] - Jp_delta_x, J[1] - Jp_delta_y);
+      R.isLinearized[r] = 1;
+    }
+  }
+  P.marg_status[p] = (P.idepth_hessian[p] > 50.0f) ? 2 : 1;                  // setting_minIdepthH_marg (settings.cpp:42)
+}
+
+// EnergyFunctional::marginalizePointsF, tail (EnergyFunctional.cpp:549-567): stitch M, Msc, then HM += margWeightFac*(M - Msc).
+// M/Mb/Msc/Mbsc are published in the HA/bA/Hsc/bsc slots of the header for read-back.
+__global__ void __launch_bounds__(kSolveThreads) ba_marg_stitch_kernel(const BAWinDev* __restrict__ wins) {
+  BA_WIN(0)
+  const int tid = threadIdx.x; const int nF = H->nF, N = H->dim, nF2 = nF*nF;
+  __shared__ double sA[kMaxDim*kMaxDim]; __shared__ double sS[kMaxDim*kMaxDim]; __shared__ double sbA[kMaxDim], sbS[kMaxDim];
+  ba_stitch<true>(H, tid, nF, N, nF2, sA, sS, sbA, sbS);
+  const double fac = (double)(0.5f*0.5f);                                    // setting_margWeightFac (settings.cpp:71)
+  for (int i = tid; i < N*N; i += kSolveThreads) { H->HA[i] = sA[i]; H->Hsc[i] = sS[i]; const double d = sA[i] - sS[i]; H->HM[i] += fac*d; }
+  if (tid < N) { H->bA[tid] = sbA[tid]; H->bsc[tid] = sbS[tid]; const double d = sbA[tid] - sbS[tid]; H->bM[tid] += fac*d; }
+  if (tid == 0) H->ortho_valid = 0;
+}
+
+// EnergyFunctional::marginalizeFrame (EnergyFunctional.cpp:434-512): fp64, one CTA.  The frame's 6 unknowns are moved to the end, its
+// prior added, the system is diagonally pre-scaled, the 6x6 block inverted (partial-pivot LU) and eliminated, the result un-scaled and
+// symmetrised.  Frame idx is then dropped from the header (frames[], nF, dim); points/residuals of the window are stale afterwards.
+__global__ void __launch_bounds__(kSolveThreads) ba_marg_frame_kernel(const BAWinDev* __restrict__ wins, int idx) {
+  BA_WIN(0)
+  const int tid = threadIdx.x; const int nF = H->nF, odim = H->dim, ndim = odim - 6;
+  if (idx < 0 || idx >= nF) return;
+  __shared__ double sH[kMaxDim*kMaxDim]; __shared__ double sb[kMaxDim], SV[kMaxDim], SVI[kMaxDim]; __shared__ double hpi[36], bli[kMaxDim*6]; __shared__ int ord[kMaxDim];
+  if (tid < odim) { int o; if (tid < ndim) o = (tid < kCP + 6*idx) ? tid : tid + 6; else o = kCP + 6*idx + (tid - ndim); ord[tid] = o; }
+  __syncthreads();
+  for (int i = tid; i < odim*odim; i += kSolveThreads) { const int r = i/odim, c = i%odim; double v = H->HM[ord[r]*odim + ord[c]];
+    if (r == c && r >= ndim) v += H->frames[idx].prior[r-ndim];
+    sH[i] = v; }
+  if (tid < odim) { double v = H->bM[ord[tid]]; if (tid >= ndim) v += H->frames[idx].prior[tid-ndim]*H->frames[idx].delta_prior[tid-ndim]; sb[tid] = v; }
+  __syncthreads();
+  if (tid < odim) { SV[tid] = sqrt(fabs(sH[tid*odim+tid]) + 10.0); SVI[tid] = 1.0/SV[tid]; }
+  __syncthreads();
+  for (int i = tid; i < odim*odim; i += kSolveThreads) { const int r = i/odim, c = i%odim; sH[i] = (SVI[r]*sH[i])*SVI[c]; }
+  if (tid < odim) sb[tid] = SVI[tid]*sb[tid];
+  __syncthreads();
+  if (tid == 0) {                                                            // hpi = bottomRightCorner<6,6>().inverse()
+    double L[36]; int perm[6];
+    for (int i=0;i<6;i++) { perm[i] = i; for (int j=0;j<6;j++) { double v = sH[(ndim+i)*odim + ndim+j]; L[i*6+j] = 0.5*(v+v); } }
+    for (int k=0;k<6;k++) {
+      int piv = k; double big = fabs(L[k*6+k]); for (int i=k+1;i<6;i++) { double a = fabs(L[i*6+k]); if (a > big) { big = a; piv = i; } }
+      if (piv != k) { for (int j=0;j<6;j++) { double t = L[k*6+j]; L[k*6+j] = L[piv*6+j]; L[piv*6+j] = t; } int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t; }
+      for (int i=k+1;i<6;i++) L[i*6+k] /= L[k*6+k];
+      for (int i=k+1;i<6;i++) for (int j=k+1;j<6;j++) L[i*6+j] -= L[i*6+k]*L[k*6+j];
+    }
+    for (int c=0;c<6;c++) { double y[6]; for (int i=0;i<6;i++) y[i] = (perm[i] == c) ? 1.0 : 0.0;
+      for (int k=0;k<6;k++) for (int i=k+1;i<6;i++) y[i] -= L[i*6+k]*y[k];
+      for (int k=5;k>=0;k--) { y[k] /= L[k*6+k]; for (int i=0;i<k;i++) y[i] -= L[i*6+k]*y[k]; }
+      for (int i=0;i<6;i++) hpi[i*6+c] = 0.5*(y[i]+y[i]); }
+  }
+  __syncthreads();
+  for (int t = tid; t < ndim*6; t += kSolveThreads) { const int i = t/6, j = t%6; double s = 0; for (int k=0;k<6;k++) s += sH[(ndim+k)*odim + i]*hpi[k*6+j]; bli[t] = s; }
+  __syncthreads();
+  for (int t = tid; t < ndim*ndim; t += kSolveThreads) { const int i = t/ndim, j = t%ndim; double s = 0; for (int k=0;k<6;k++) s += bli[i*6+k]*sH[(ndim+k)*odim + j]; sH[i*odim+j] -= s; }
+  __syncthreads();                                                           // (the bottom rows read above are not written by the update)
+  if (tid < ndim) { double s = 0; for (int k=0;k<6;k++) s += bli[tid*6+k]*sb[ndim+k]; sb[tid] -= s; }
+  __syncthreads();
+  for (int t = tid; t < ndim*ndim; t += kSolveThreads) { const int i = t/ndim, j = t%ndim; sH[i*odim+j] = (SV[i]*sH[i*odim+j])*SV[j]; }
+  if (tid < ndim) sb[tid] = SV[tid]*sb[tid];
+  __syncthreads();
+  for (int t = tid; t < ndim*ndim; t += kSolveThreads) { const int i = t/ndim, j = t%ndim; H->HM[i*ndim+j] = 0.5*(sH[i*odim+j] + sH[j*odim+i]); }
+  if (tid < ndim) H->bM[tid] = sb[tid];
+  __syncthreads();
+  if (tid == 0) { for (int f = idx; f+1 < nF; f++) H->frames[f] = H->frames[f+1]; H->nF = nF-1; H->dim = ndim; H->nP = 0; H->nR = 0; H->ortho_valid = 0; }
+}
+
 // ================================================================================================ launchers
 static inline dim3 g2(int n, int per, int W) { int gx = (n + per - 1)/per; if (gx < 1) gx = 1; return dim3(gx, W); }
 void launch_ba_setup(const BAWinDev* wins, int W, int maxP, cudaStream_t st) {
@@ -799,11 +918,12 @@ void launch_ba_linearize(const BAWinDev* wins, int W, int maxR, int fix, int gat
 }
 void launch_ba_apply(const BAWinDev* wins, int W, int maxR, int gate, cudaStream_t st) { ba_apply_kernel<<<g2(maxR, 256, W), 256, 0, st>>>(wins, gate); }
 void launch_ba_energies(const BAWinDev* wins, int W, int gate, cudaStream_t st) { ba_energies_kernel<<<dim3(1, W), 256, 0, st>>>(wins, gate); }
-void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) {
-  ba_point_acc_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate);
-  ba_acc_top_kernel<<<dim3(kMaxF*kMaxF, W), 96, 0, st>>>(wins, gate);
+static void accumulate_mode(const BAWinDev* wins, int W, int maxP, int gate, int mode, cudaStream_t st) {
+  ba_point_acc_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate, mode);
+  ba_acc_top_kernel<<<dim3(kMaxF*kMaxF, W), 96, 0, st>>>(wins, gate, mode);
   ba_acc_sc_kernel<<<dim3(kMaxF, W), 96, 0, st>>>(wins, gate);
 }
+void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) { accumulate_mode(wins, W, maxP, gate, 0, st); }
 void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, double lambda, int use_hdr_ctl, int gate, cudaStream_t st) {
   ba_solve_kernel<<<dim3(1, W), kSolveThreads, 0, st>>>(wins, iteration, lambda, use_hdr_ctl, gate);
   ba_resub_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate);
@@ -817,6 +937,12 @@ void launch_ba_reanchor(const BAWinDev* wins, int W, int maxP, cudaStream_t st) 
   ba_frames_kernel<<<dim3(1, W), 64, 0, st>>>(wins, 32|8|16, 0.f, 0, GATE_ALWAYS);
   ba_points_setup_kernel<<<g2(maxP, 256, W), 256, 0, st>>>(wins, 0);
 }
+void launch_ba_marg_flag(const BAWinDev* wins, int W, int maxP, cudaStream_t st) { ba_marg_flag_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins); }
+void launch_ba_marg_points(const BAWinDev* wins, int W, int maxP, cudaStream_t st) {
+  accumulate_mode(wins, W, maxP, GATE_ALWAYS, 2, st);
+  ba_marg_stitch_kernel<<<dim3(1, W), kSolveThreads, 0, st>>>(wins);
+}
+void launch_ba_marg_frame(const BAWinDev* wins, int W, int idx, cudaStream_t st) { ba_marg_frame_kernel<<<dim3(1, W), kSolveThreads, 0, st>>>(wins, idx); }
 void launch_ba_decide(const BAWinDev* wins, int W, int stage, cudaStream_t st) { ba_decide_kernel<<<(W + 127)/128, 128, 0, st>>>(wins, W, stage); }
 
 } // namespace sdv

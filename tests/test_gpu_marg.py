@@ -1,0 +1,87 @@
+"""GPU parity (-m gpu) of the keyframe hand-over: sdv_ba_flag_points / sdv_ba_marginalize_points / sdv_ba_marginalize_frame
+against the oracle.  Float accumulators (reference tiers and order) and every fp64 sum are evaluated in the oracle's order -> BIT-EXACT."""
+import numpy as np
+import pytest
+import orc
+from conftest import cached_sequence
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import sdv_loam_b200  # noqa
+    from sdv_loam_b200 import api, synth
+    return api, synth
+
+
+def _pair(api, synth, seq, kfs, **kw):
+    win = synth.make_ba_window(seq, kfs, **kw)
+    L = api.pyr_levels(*synth.KITTI_WH)
+    frames = [orc.Frame(seq.images[k], L) for k in kfs]
+    ctx = api.Context(synth.KITTI_K, *synth.KITTI_WH, max_frames=len(kfs) + 1)
+    for i, k in enumerate(kfs):
+        ctx.makeImages(500 + i, seq.images[k])
+    return win, ctx, orc.BAWindow(win, frames), api.EnergyFunctional(ctx, win, [500 + i for i in range(len(kfs))])
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def _select(win, marg_host, every):
+    sel = (win["host"] == marg_host).astype(np.int32); sel[::every] = 1
+    sel[win["host"] == win["nF"] - 1] = 0
+    return sel
+
+
+@pytest.mark.parametrize("cfg", [dict(kfs=[0, 1, 2, 3, 4, 5, 6], n_per_frame=250, prior_scale=1e-3, marg=0, every=5),
+                                 dict(kfs=[0, 1, 2, 3, 4, 5, 6, 7], n_per_frame=400, prior_scale=1e-2, sensor_frac=0.3, marg=3, every=3),
+                                 dict(kfs=[1, 3, 5], n_per_frame=150, prior_scale=0.0, sensor_frac=0.0, marg=1, every=2),
+                                 dict(kfs=[0, 2, 4, 6], n_per_frame=200, prior_scale=1e-3, sensor_frac=1.0, marg=3, every=4)])
+def test_keyframe_handover_bit_exact(cfg):
+    api, synth = _mods()
+    seq = cached_sequence(8, 2000, synth.KITTI_K, synth.KITTI_WH)
+    kfs, marg, every = cfg.pop("kfs"), cfg.pop("marg"), cfg.pop("every")
+    win, ctx, ob, gb = _pair(api, synth, seq, kfs, seed=3, pose_noise=(0.005, 0.0003), match_noise=0.1, **cfg)
+    ro, rg = ob.optimize(4), gb.optimize(4)
+    assert (ro["iterations"], ro["accepts"]) == (rg["iterations"], rg["accepts"])
+    sel = _select(win, marg, every)
+    so, sg = ob.flagPointsForRemoval(sel), gb.flagPointsForRemoval(sel)
+    assert _same(so, sg) and (so == 2).sum() > 0
+    (zo, lo), (zg, lg) = ob.res_to_zero(), gb.linearized()
+    assert _same(lo, lg) and _same(zo[lo == 1], zg[lg == 1])
+    a, b = ob.residuals(), gb.residuals()
+    assert _same(a["active"], b["active"]) and _same(a["efJ"], b["efJ"]) and _same(a["state"], b["state"])
+    mo = ob.marginalizePointsF(so); mg = gb.marginalizePointsF()                 # device-resident status of flag_points
+    for k in ("M", "Mb", "Msc", "Mbsc"):
+        assert _same(mo[k], mg[k]), k
+    (Ho, bo), (Hg, bg) = ob.prior(), gb.prior()
+    assert _same(Ho, Hg) and _same(bo, bg)
+    po, pg = ob.points(), gb.points()
+    assert _same(po["idepth_hessian"][so == 2], pg["idepth_hessian"][so == 2]) and _same(po["HdiF"][so == 2], pg["HdiF"][so == 2])
+    ob.marginalizeFrame(marg); gb.marginalizeFrame(marg)
+    (Ho, bo), (Hg, bg) = ob.prior(), gb.prior()
+    assert Ho.shape == Hg.shape == (4 + 6 * (len(kfs) - 1),) * 2
+    assert _same(Ho, Hg) and _same(bo, bg)
+    if len(kfs) > 3:                                                             # a second frame, now at a shifted index
+        ob.marginalizeFrame(0); gb.marginalizeFrame(0)
+        (Ho, bo), (Hg, bg) = ob.prior(), gb.prior()
+        assert _same(Ho, Hg) and _same(bo, bg)
+    ctx.close()
+
+
+def test_marginalize_points_host_status_and_errors():
+    api, synth = _mods()
+    seq = cached_sequence(8, 2000, synth.KITTI_K, synth.KITTI_WH)
+    win, ctx, ob, gb = _pair(api, synth, seq, [0, 1, 2, 3, 4], seed=9, n_per_frame=150, pose_noise=(0.004, 0.0003), match_noise=0.1, prior_scale=1e-3)
+    ob.optimize(3); gb.optimize(3)
+    sel = _select(win, 0, 6); so = ob.flagPointsForRemoval(sel); sg = gb.flagPointsForRemoval(sel)
+    st = so.copy(); st[np.where(st == 2)[0][::3]] = 1                            # the host may still demote points (PS_DROP) before marginalising
+    mo = ob.marginalizePointsF(st); mg = gb.marginalizePointsF(st)
+    assert _same(mo["M"], mg["M"]) and _same(mo["Msc"], mg["Msc"]) and _same(ob.prior()[0], gb.prior()[0])
+    with pytest.raises(api.SdvError):
+        gb.marginalizeFrame(9)
+    gb.marginalizeFrame(0)
+    with pytest.raises(api.SdvError):
+        gb.flagPointsForRemoval(sel[:1])                                         # window has no points until sdv_ba_set_points is called again
+    ctx.close()
