@@ -162,6 +162,24 @@ class CoarseTracker:
 
 
 # ------------------------------------------------------------------------------------------------ back-end window
+def reproject_map(w, h, levels, K4, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, cur_ab, pts, cur_kf_index=-1, only_host=-1, backup=False,
+                  cell_order=None, max_matches=1200):
+    """Reprojector::reprojectMap / backprojectMap restated (orc_reproject.cpp).  pts: structured array with u, v, idepth, host, type.
+    Returns (pt_index[n], px[n,2]) in cell visiting order."""
+    L = lib()
+    L.orc_reproject_map.argtypes = [C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.POINTER(C.c_void_p), _f64p, _f64p, C.c_void_p, _f64p, _f64p, C.c_int,
+                                    C.c_int, _f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, _i32p, _f64p]
+    nH = len(kf_frames); fr = (C.c_void_p * nH)(*[f.p for f in kf_frames])
+    p5 = np.ascontiguousarray(np.stack([pts["u"], pts["v"], pts["idepth"], pts["host"].astype(np.float32), pts["type"].astype(np.float32)], 1), np.float32)
+    ncells = int(np.ceil(w / 25.0)) * int(np.ceil(h / 25.0))
+    out_pt = np.zeros(ncells, np.int32); out_px = np.zeros((ncells, 2))
+    co = None if cell_order is None else np.ascontiguousarray(cell_order, np.int32)
+    n = L.orc_reproject_map(w, h, levels, np.ascontiguousarray(K4, np.float32), nH, fr, np.ascontiguousarray(kf_T7, np.float64), np.ascontiguousarray(kf_ab, np.float64),
+                            cur_frame.p, np.ascontiguousarray(cur_T7, np.float64), np.ascontiguousarray(cur_ab, np.float64), cur_kf_index, len(p5), p5,
+                            only_host, 1 if backup else 0, None if co is None else co.ctypes.data, max_matches, out_pt, out_px)
+    return out_pt[:n].copy(), out_px[:n].copy()
+
+
 def struct_pose(w, h, K4, host_T7, pts6, curToWorld7):
     """CoarseTracker::structPoseEstimation restated (orc_refine.cpp).  pts6: (n,6) float32 {u,v,idepth,host,obs_x,obs_y}."""
     L = lib()

@@ -301,3 +301,25 @@ def make_overlap_points(n: int, nH: int = 5, seed: int = 0, K=KITTI_K, wh=KITTI_
     T_gt = np.concatenate([_quat_from_R(Rc), tc])
     T_init = np.concatenate([_quat_from_R(dR @ Rc), tc + rng.normal(0, pose_noise[0], 3)])
     return dict(pts=pts, host_T7=host_T7, T_init=T_init, T_gt=T_gt, K=np.array(K, np.float64), wh=(w, h))
+
+
+# ------------------------------------------------------------------------------------------------ map points (Reprojector input)
+MAP_PT_DTYPE = np.dtype([("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("type", np.int32)])
+
+
+def make_map(seq: "Sequence", kf_idx, n_per_frame: int = 300, seed: int = 0, edgelet_frac: float = 0.3, idepth_noise: float = 0.0):
+    """Active map points of the keyframes kf_idx of `seq` (grouped by host, window order): integer pixels on LiDAR hits with their
+    measured inverse depth (ImmaturePoint truncation, ImmaturePoint.cpp:8), point type drawn at random (the Shi-Tomasi classification of
+    FullSystem.cpp:1326-1332 is point selection = out of scope).  Returns (pts[MAP_PT_DTYPE], host_T7 (camToWorld), host_ab)."""
+    rng = np.random.default_rng(seed); w, h = seq.wh
+    out = []
+    for hi, k in enumerate(kf_idx):
+        sel = select_points(seq.images[k], seq.clouds[k], n_per_frame, seed=seed + 17 * hi)
+        for (pu, pv, pid) in sel:
+            u, v = int(pu), int(pv)
+            if u < 10 or v < 10 or u >= w - 11 or v >= h - 11:
+                continue
+            out.append((u, v, pid * (1.0 + rng.normal(0, idepth_noise)) if idepth_noise > 0 else pid, hi, 1 if rng.uniform() < edgelet_frac else 0))
+    pts = np.array(out, MAP_PT_DTYPE)
+    host_T7 = np.array([np.concatenate([_quat_from_R(seq.R[k]), seq.t[k]]) for k in kf_idx])
+    return pts, host_T7, np.zeros((len(kf_idx), 2))
