@@ -115,6 +115,28 @@ int  sdv_tracker_track(sdv_ctx* c, int slot, uint64_t new_frame, double T_io[7],
 int  sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* new_frames, double* T_io, double* ab_io,
                              int coarsest, const double* minResForAbort, double* lastRes, double* flow, int32_t* good,
                              sdv_track_stats* stats);
+/* ---- map reprojection + direct feature alignment: the Reprojector of FullSystem::trackNewCoarse / makeKeyFrame
+ *   void Reprojector::reprojectMap(FrameHessian* frame, std::vector<std::pair<PointHessian*, Eigen::Vector2d>>& overlap_pts)     Reprojector.cpp:117-156
+ *   void Reprojector::backprojectMap(FrameHessian* ref_frame, FrameHessian* frame, overlap_pts&)                                   :158-185
+ *   with reprojectPoint :600-616, reprojectCell :198-233, findMatchDirect :235-292, getWarpMatrixAffine :14-37, getBestSearchLevel :39-51,
+ *   warpAffine :53-86, align1D :346-455, align2D :457-560 (options_: find_match_direct = true, align_max_iter = 10; grid cell 25 px).
+ * sdv_map_set     makes the active map of one sequence resident (per keyframe): the window's keyframes (frameHessians_ order: device frame
+ *                 handle, shell->camToWorld, shell->aff_g2l {a,b}) and their ACTIVE PointHessians grouped by host in that order
+ *                 (u, v, idepth, host index, type 0 CORNER / 1 EDGELET).  `slot` shares the index space of the tracker slots.
+ * sdv_reproject_map_batch   n independent reprojectMap calls in one launch sequence.  Per job: map slot, target frame handle + camToWorld +
+ *                 aff_g2l, cur_kf_index (index of the target in the map's keyframes or -1), only_host (-1: reprojectMap over all keyframes in
+ *                 close_kfs order; h: backprojectMap of keyframe h's points), backup (Reprojector::backup, selects the reference keyframe when
+ *                 there are <= 2 keyframes, :242-250).  cell_order[n_cols*n_rows] is the grid visiting order (the reference shuffles it with
+ *                 rand(), :111; NULL = identity); max_matches = (int)(0.8*setting_desiredImmatureDensity).
+ *                 Outputs per job k, in visiting order: n_out[k] matches, out_pt[k*cells + i] = index into the slot's points,
+ *                 out_px[(k*cells + i)*2] = aligned pixel (it->px). */
+typedef struct { float u, v, idepth; int32_t host; int32_t type; } sdv_map_pt;
+int  sdv_reproject_grid(sdv_ctx* c, int* n_cols, int* n_rows);
+int  sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const double* host_T7, const double* host_ab, int nP, const sdv_map_pt* pts);
+int  sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, const double* cur_T7, const double* cur_ab,
+                             const int32_t* cur_kf_index, const int32_t* only_host, const int32_t* backup, const int32_t* cell_order, int max_matches,
+                             int32_t* n_out, int32_t* out_pt, double* out_px);
+
 /* ---- semi-direct pose refinement on matched map points
  * bool CoarseTracker::structPoseEstimation(SE3& curToWorld, std::vector<std::pair<PointHessian*, Eigen::Vector2d>>& overlap_pts)
  *                                                                                              CoarseTracker.cpp:949-1007

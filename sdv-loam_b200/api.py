@@ -31,6 +31,7 @@ class sdv_track_stats(C.Structure):
     _fields_ = [("point_evals", C.c_int64 * PYR_LEVELS), ("iterations", C.c_int32 * PYR_LEVELS), ("accepts", C.c_int32 * PYR_LEVELS)]
 
 
+MAP_PT_DTYPE = np.dtype([("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("type", np.int32)])
 OVERLAP_PT_DTYPE = np.dtype([("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("obs_x", np.float32), ("obs_y", np.float32)])
 TRACK_STATS_DTYPE = np.dtype([("point_evals", np.int64, PYR_LEVELS), ("iterations", np.int32, PYR_LEVELS), ("accepts", np.int32, PYR_LEVELS)])
 assert TRACK_STATS_DTYPE.itemsize == C.sizeof(sdv_track_stats)
@@ -66,6 +67,9 @@ def _load():
     L.sdv_tracker_get_cloud.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_int), _vp, _vp, _vp, _vp]
     L.sdv_tracker_calc_res.argtypes = [_vp, C.c_int, C.c_uint64, C.c_int, _f64p, C.c_double, C.c_double, C.c_float, _f64p]
     L.sdv_tracker_calc_gs.argtypes = [_vp, C.c_int, C.c_int, _f64p, _f64p]
+    L.sdv_reproject_grid.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.sdv_map_set.argtypes = [_vp, C.c_int, C.c_int, _u64p, _f64p, _f64p, C.c_int, _vp]
+    L.sdv_reproject_map_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, _i32p, _i32p, _i32p, _vp, C.c_int, _i32p, _i32p, _f64p]
     L.sdv_tracker_struct_pose_batch.argtypes = [_vp, C.c_int, _i32p, _vp, _i32p, _f64p, _f64p, _f32p, _i32p, _i32p]
     L.sdv_tracker_track.argtypes = [_vp, C.c_int, C.c_uint64, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(sdv_track_stats)]
     L.sdv_tracker_track_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, C.c_int, _vp, _f64p, _f64p, _i32p, C.POINTER(sdv_track_stats)]
@@ -227,6 +231,32 @@ class CoarseTracker:
         the host keyframes the points index.  Returns dict(T=refined curToWorld, res, iterations, accepts)."""
         r = structPoseEstimationBatch(self.ctx, np.array(curToWorld7, np.float64).reshape(1, 7), [overlap_pts], [host_T7])
         return dict(T=r["T"][0], res=float(r["res"][0]), iterations=int(r["iterations"][0]), accepts=int(r["accepts"][0]))
+
+
+class Reprojector:
+    """Mirror of sdv_loam::Reprojector (FullSystem/Reprojector.h:17-111) over device-resident maps: one map slot per sequence."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx; a = C.c_int(0); b = C.c_int(0); ctx._ck(LIB.sdv_reproject_grid(ctx.p, C.byref(a), C.byref(b)))
+        self.grid_n_cols, self.grid_n_rows = a.value, b.value; self.n_cells = a.value * b.value
+
+    def setMap(self, slot: int, host_frame_ids, host_T7, host_ab, pts):
+        pts = np.ascontiguousarray(pts, MAP_PT_DTYPE); hT = np.ascontiguousarray(host_T7, np.float64).reshape(-1, 7)
+        hab = np.zeros((len(hT), 2)) if host_ab is None else np.ascontiguousarray(host_ab, np.float64).reshape(-1, 2)
+        self.ctx._ck(LIB.sdv_map_set(self.ctx.p, slot, len(hT), np.ascontiguousarray(host_frame_ids, np.uint64), hT, hab, len(pts), pts.ctypes.data if len(pts) else None))
+
+    def reprojectMapBatch(self, slots, cur_frame_ids, cur_T7, cur_ab=None, cur_kf_index=None, only_host=None, backup=None, cell_order=None, max_matches=1200):
+        n = len(slots); i32 = lambda a, d: np.full(n, d, np.int32) if a is None else np.ascontiguousarray(a, np.int32)
+        T = np.ascontiguousarray(cur_T7, np.float64).reshape(n, 7); ab = np.zeros((n, 2)) if cur_ab is None else np.ascontiguousarray(cur_ab, np.float64).reshape(n, 2)
+        n_out = np.zeros(n, np.int32); out_pt = np.zeros((n, self.n_cells), np.int32); out_px = np.zeros((n, self.n_cells, 2))
+        co = None if cell_order is None else np.ascontiguousarray(cell_order, np.int32)
+        self.ctx._ck(LIB.sdv_reproject_map_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(cur_frame_ids, np.uint64), T, ab,
+                                                 i32(cur_kf_index, -1), i32(only_host, -1), i32(backup, 0), None if co is None else co.ctypes.data, max_matches, n_out, out_pt, out_px))
+        return [(out_pt[k, :n_out[k]].copy(), out_px[k, :n_out[k]].copy()) for k in range(n)]
+
+    def reprojectMap(self, slot, cur_frame_id, cur_T7, cur_ab=None, **kw):
+        kw = {k: (None if v is None else ([v] if k != "cell_order" and k != "max_matches" else v)) for k, v in kw.items()}
+        return self.reprojectMapBatch([slot], [cur_frame_id], np.asarray(cur_T7, np.float64).reshape(1, 7), None if cur_ab is None else np.asarray(cur_ab, np.float64).reshape(1, 2), **kw)[0]
 
 
 def structPoseEstimationBatch(ctx, curToWorld7, overlap_pts_list, host_T7_list):

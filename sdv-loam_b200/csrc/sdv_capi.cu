@@ -124,6 +124,7 @@ void sdv_destroy(sdv_ctx* c) {
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
   for (auto p : c->stage) cudaFree(p);
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
+  rp_destroy(c);
   ba_destroy(c);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_in); cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_in);
   delete c;

@@ -21,6 +21,7 @@ struct TrackerSlot {                      // one CoarseTracker instance (referen
 };
 
 struct BAState;                           // sdv_ba.cuh
+struct RpState;                           // sdv_reproject.cu
 
 } // namespace sdv
 
@@ -41,12 +42,14 @@ struct sdv_ctx {
   int jobs_cap; sdv::TrackJob* jobs_dev; sdv::TrackJob* jobs_host;
   float last_ms;
   void* refine_dev = nullptr; void* refine_host = nullptr; size_t refine_cap = 0;      // staging of sdv_tracker_struct_pose_batch
+  sdv::RpState* rp = nullptr;                   // map slots + scratch of the Reprojector path (sdv_reproject.cu)
   sdv::BAState* ba = nullptr;                   // selected back-end window
   std::vector<sdv::BAState*> ba_windows; void* ba_wins_dev = nullptr; void* ba_wins_host = nullptr; int ba_wins_cap = 0;
   char err[512];
 };
 
 namespace sdv {
+void rp_destroy(sdv_ctx* c);
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
 void ba_destroy(sdv_ctx* c);
 int  ensure_lvl0(sdv_ctx* c, FrameDev& f);     // build the packed level-0 texels of a frame on demand (keyframes / read-back)
