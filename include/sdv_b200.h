@@ -150,6 +150,11 @@ int  sdv_tracker_struct_pose(sdv_ctx* c, int n, const sdv_overlap_pt* pts, int n
                              float* res, int* iterations, int* accepts);
 int  sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_begin, const sdv_overlap_pt* pts, const int32_t* host_begin,
                                    const double* host_T7, double* curToWorld_io, float* res, int32_t* iterations, int32_t* accepts);
+/* ---- fused per-frame refinement (the tail of FullSystem::trackNewCoarse, FullSystem.cpp:482-488): reprojectMap(fh) -> structPoseEstimation
+ * without leaving the device.  curToWorld_io: fh->shell->camToWorld from the photometric tracker in, refined pose out; cur_ab = the tracked
+ * aff_g2l.  n_matches = overlap_pts.size(), res/iterations/accepts as in sdv_tracker_struct_pose_batch. */
+int  sdv_tracker_refine_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, double* curToWorld_io, const double* cur_ab,
+                              const int32_t* cell_order, int max_matches, int32_t* n_matches, float* res, int32_t* iterations, int32_t* accepts);
 /* device time of the last track / track_batch / calc_res launch in milliseconds (CUDA events on the context stream) */
 float sdv_last_kernel_ms(sdv_ctx* c);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

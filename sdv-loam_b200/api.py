@@ -70,6 +70,7 @@ def _load():
     L.sdv_reproject_grid.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.sdv_map_set.argtypes = [_vp, C.c_int, C.c_int, _u64p, _f64p, _f64p, C.c_int, _vp]
     L.sdv_reproject_map_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, _i32p, _i32p, _i32p, _vp, C.c_int, _i32p, _i32p, _f64p]
+    L.sdv_tracker_refine_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, _vp, C.c_int, _i32p, _f32p, _i32p, _i32p]
     L.sdv_tracker_struct_pose_batch.argtypes = [_vp, C.c_int, _i32p, _vp, _i32p, _f64p, _f64p, _f32p, _i32p, _i32p]
     L.sdv_tracker_track.argtypes = [_vp, C.c_int, C.c_uint64, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(sdv_track_stats)]
     L.sdv_tracker_track_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, C.c_int, _vp, _f64p, _f64p, _i32p, C.POINTER(sdv_track_stats)]
@@ -253,6 +254,16 @@ class Reprojector:
         self.ctx._ck(LIB.sdv_reproject_map_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(cur_frame_ids, np.uint64), T, ab,
                                                  i32(cur_kf_index, -1), i32(only_host, -1), i32(backup, 0), None if co is None else co.ctypes.data, max_matches, n_out, out_pt, out_px))
         return [(out_pt[k, :n_out[k]].copy(), out_px[k, :n_out[k]].copy()) for k in range(n)]
+
+    def refineBatch(self, slots, cur_frame_ids, curToWorld7, cur_ab=None, cell_order=None, max_matches=1200):
+        """Tail of FullSystem::trackNewCoarse (FullSystem.cpp:482-488) for n frames: reprojectMap -> structPoseEstimation, device resident."""
+        n = len(slots); T = np.ascontiguousarray(curToWorld7, np.float64).reshape(n, 7).copy()
+        ab = np.zeros((n, 2)) if cur_ab is None else np.ascontiguousarray(cur_ab, np.float64).reshape(n, 2)
+        co = None if cell_order is None else np.ascontiguousarray(cell_order, np.int32)
+        nm = np.zeros(n, np.int32); res = np.zeros(n, np.float32); its = np.zeros(n, np.int32); acc = np.zeros(n, np.int32)
+        self.ctx._ck(LIB.sdv_tracker_refine_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(cur_frame_ids, np.uint64), T, ab,
+                                                  None if co is None else co.ctypes.data, max_matches, nm, res, its, acc))
+        return dict(T=T, n_matches=nm, res=res, iterations=its, accepts=acc, ms=self.ctx.last_kernel_ms())
 
     def reprojectMap(self, slot, cur_frame_id, cur_T7, cur_ab=None, **kw):
         kw = {k: (None if v is None else ([v] if k != "cell_order" and k != "max_matches" else v)) for k, v in kw.items()}

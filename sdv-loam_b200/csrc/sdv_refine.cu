@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "sdv_ctx.cuh"
+#include "sdv_refine.cuh"
 
 namespace sdv {
 
@@ -23,11 +24,6 @@ constexpr int kRefThreads = 128;
 constexpr int kRefChunk = 256;           // points staged per pass
 constexpr int kRefMaxHosts = 16;
 
-struct RefineJob {
-  double T[7];                           // curToWorld in/out
-  int pt_begin, pt_end, host_begin, nH;
-  float res; int iterations, accepts, num;
-};
 
 struct RefShared {
   float hostR[kRefMaxHosts][9], hostT[kRefMaxHosts][3];
@@ -126,7 +122,7 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
   const LevelGeom g = tc->geom[0];
   const float fxi = g.Ki[0], fyi = g.Ki[4];
   for (int k = threadIdx.x; k < jb.nH; k += blockDim.x) {
-    SE3d h = se3_from7(hostT7 + 7*(size_t)(jb.host_begin + k)); double R[9]; qmat(h.q, R);
+    SE3d h = se3_from7(jb.hostT ? jb.hostT + 7*k : hostT7 + 7*(size_t)(jb.host_begin + k)); double R[9]; qmat(h.q, R);
     for (int i=0;i<9;i++) S.hostR[k][i] = (float)R[i];
     for (int i=0;i<3;i++) S.hostT[k][i] = (float)h.t[i];
   }
@@ -175,6 +171,12 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
   if (threadIdx.x == 0) { jb.res = s_resOld; jb.num = S.num; }
 }
 
+void launch_struct_pose(RefineJob* jobs, int n_jobs, const sdv_overlap_pt* pts, const double* hostT7, const TrackConst* tc, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(struct_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefShared)); attr_set = true; }
+  struct_pose_kernel<<<n_jobs, kRefThreads, sizeof(RefShared), st>>>(jobs, pts, hostT7, tc);
+}
+
 } // namespace sdv
 
 using namespace sdv;
@@ -210,12 +212,10 @@ int sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_begi
     J[k].pt_begin = pt_begin[k]; J[k].pt_end = pt_begin[k+1]; J[k].host_begin = host_begin[k]; J[k].nH = host_begin[k+1]-host_begin[k]; }
   if (nP) memcpy(hb + o_pts, pts, (size_t)nP*sizeof(sdv_overlap_pt));
   memcpy(hb + o_host, host_T7, (size_t)nH*7*sizeof(double));
-  static bool attr_set = false;
-  if (!attr_set) { CK(cudaFuncSetAttribute(struct_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefShared))); attr_set = true; }
   c->launches += 1;
   CK(cudaMemcpyAsync(db, hb, total, cudaMemcpyHostToDevice, c->st));
   CK(cudaEventRecord(c->ev0, c->st));
-  struct_pose_kernel<<<n_jobs, kRefThreads, sizeof(RefShared), c->st>>>((RefineJob*)(db + o_jobs), (const sdv_overlap_pt*)(db + o_pts), (const double*)(db + o_host), c->tc_dev);
+  launch_struct_pose((RefineJob*)(db + o_jobs), n_jobs, (const sdv_overlap_pt*)(db + o_pts), (const double*)(db + o_host), c->tc_dev, c->st);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->st));
   CK(cudaMemcpyAsync(hb + o_jobs, db + o_jobs, (size_t)n_jobs*sizeof(RefineJob), cudaMemcpyDeviceToHost, c->st));

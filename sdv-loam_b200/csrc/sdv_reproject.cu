@@ -17,6 +17,7 @@
 #include <vector>
 #include <algorithm>
 #include "sdv_ctx.cuh"
+#include "sdv_refine.cuh"
 
 namespace sdv {
 
@@ -245,6 +246,27 @@ __global__ void __launch_bounds__(32*kRpWarps) rp_match_kernel(const RpJob* __re
   if (lane == 0) { S.out_pt[cb] = found; S.out_px[cb] = fpx; }
 }
 
+// Ordered emission of the per-cell results (reprojectMap :147-155): cells are visited in cell_order, every cell with a match contributes one
+// overlap point, the walk stops once more than max_matches were produced.  One CTA per frame; also fills the structPoseEstimation job.
+__global__ void __launch_bounds__(1024) rp_emit_kernel(const RpJob* __restrict__ jobs, RpConst C, RpScratch S, const int* __restrict__ cell_order, int max_matches,
+                                                       sdv_overlap_pt* __restrict__ ov, RefineJob* __restrict__ rj, int* __restrict__ n_out) {
+  const RpJob& jb = jobs[blockIdx.x]; const MapDev* __restrict__ m = jb.map;
+  const long long base = (long long)blockIdx.x*C.ncells; const int per = (C.ncells + 1023)/1024;
+  __shared__ int part[1024];
+  int s = 0; for (int k = 0; k < per; k++) { const int i = threadIdx.x*per + k; if (i < C.ncells) { const int cell = cell_order ? cell_order[i] : i; s += (S.out_pt[base+cell] >= 0) ? 1 : 0; } }
+  part[threadIdx.x] = s; __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) { int v = (threadIdx.x >= o) ? part[threadIdx.x-o] : 0; __syncthreads(); part[threadIdx.x] += v; __syncthreads(); }
+  int run = part[threadIdx.x] - s;
+  const int total = min(part[1023], max_matches + 1);
+  for (int k = 0; k < per; k++) { const int i = threadIdx.x*per + k; if (i >= C.ncells) break; const int cell = cell_order ? cell_order[i] : i;
+    const int pi = S.out_pt[base+cell]; if (pi < 0) continue;
+    if (run < total) { const sdv_map_pt p = m->pts[pi]; const double2 px = S.out_px[base+cell];
+      sdv_overlap_pt o; o.u = p.u; o.v = p.v; o.idepth = p.idepth; o.host = p.host; o.obs_x = (float)px.x; o.obs_y = (float)px.y; ov[base + run] = o; }
+    run++; }
+  if (threadIdx.x == 0) { RefineJob& r = rj[blockIdx.x]; for (int i=0;i<7;i++) r.T[i] = jb.curT[i]; r.hostT = &m->hostT[0][0]; r.pt_begin = (int)base; r.pt_end = (int)base + total;
+    r.host_begin = 0; r.nH = jb.nH; r.res = 0; r.iterations = 0; r.accepts = 0; r.num = 0; n_out[blockIdx.x] = total; }
+}
+
 } // namespace sdv
 
 using namespace sdv;
@@ -252,7 +274,7 @@ using namespace sdv;
 
 namespace sdv {
 struct MapSlot { MapDev host_copy; MapDev* dev = nullptr; sdv_map_pt* pts = nullptr; int cap = 0; int nH = 0, nP = 0; uint64_t host_ids[kRpMaxHosts]; double host_ab[kRpMaxHosts][2]; float host_exposure[kRpMaxHosts]; bool set = false; };
-struct RpState { std::vector<MapSlot> maps; void* dev = nullptr; void* host = nullptr; size_t cap = 0; RpConst C; bool c_ready = false; };
+struct RpState { std::vector<MapSlot> maps; void* dev = nullptr; void* host = nullptr; size_t cap = 0, host_cap = 0; RpConst C; bool c_ready = false; };
 static RpState* rp_state(sdv_ctx* c) { if (!c->rp) { c->rp = new RpState(); c->rp->maps.resize(c->slots.size()); } return c->rp; }
 void rp_destroy(sdv_ctx* c) { if (!c->rp) return; for (auto& m : c->rp->maps) { cudaFree(m.dev); cudaFree(m.pts); } cudaFree(c->rp->dev); cudaFreeHost(c->rp->host); delete c->rp; c->rp = nullptr; }
 static void rp_const(sdv_ctx* c, RpState* st) {
@@ -295,23 +317,27 @@ int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const
   return SDV_OK;
 }
 
-int sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, const double* cur_T7, const double* cur_ab,
-                            const int32_t* cur_kf_index, const int32_t* only_host, const int32_t* backup, const int32_t* cell_order, int max_matches,
-                            int32_t* n_out, int32_t* out_pt, double* out_px) {
-  if (!c || n_jobs <= 0 || !slots || !cur_frames || !cur_T7 || !n_out || !out_pt || !out_px) return SDV_ERR_ARG;
-  CK(cudaSetDevice(c->device)); RpState* st = rp_state(c); rp_const(c, st); const RpConst& C = st->C;
+// shared front half: builds the jobs, sizes the scratch and launches project / scan / scatter / match.  Results stay on the device.
+struct RpRun { RpScratch S; RpJob* jobs_dev; RpJob* jobs_host; int32_t* h_opt; double2* h_opx; sdv_overlap_pt* ov; RefineJob* rj; RefineJob* rj_host; int* n_out_dev; int* n_out_host; int* cell_order_dev; long long nc; };
+static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, const double* cur_T7, const double* cur_ab,
+                     const int32_t* cur_kf_index, const int32_t* only_host, const int32_t* backup, RpRun& R) {
+  RpState* st = rp_state(c); rp_const(c, st); const RpConst& C = st->C;
   long long totalP = 0; int maxP = 1;
   for (int k=0;k<n_jobs;k++) { if (slots[k] < 0 || slots[k] >= (int)st->maps.size() || !st->maps[slots[k]].set) return ctx_fail(c, SDV_ERR_STATE, "reproject job %d: map slot %d not set", k, slots[k]);
     totalP += st->maps[slots[k]].nP; maxP = std::max(maxP, st->maps[slots[k]].nP); }
-  const long long nc = (long long)n_jobs*C.ncells;
+  const long long nc = (long long)n_jobs*C.ncells; R.nc = nc;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_jobs = 0, o_px = al(o_jobs + (size_t)n_jobs*sizeof(RpJob)), o_key = al(o_px + (size_t)totalP*sizeof(double2)), o_cell = al(o_key + (size_t)totalP*4), o_list = al(o_cell + (size_t)totalP*4),
-         o_count = al(o_list + (size_t)totalP*4), o_begin = al(o_count + (size_t)nc*4), o_cur = al(o_begin + (size_t)nc*4), o_opt = al(o_cur + (size_t)nc*4), o_opx = al(o_opt + (size_t)nc*4), total = al(o_opx + (size_t)nc*sizeof(double2));
-  const size_t host_bytes = al((size_t)n_jobs*sizeof(RpJob)) + al((size_t)nc*4) + al((size_t)nc*sizeof(double2));
-  if (total > st->cap) { cudaFree(st->dev); cudaFreeHost(st->host); st->dev = st->host = nullptr; st->cap = 0; size_t cap = total + total/4;
-    CK(cudaMalloc(&st->dev, cap)); CK(cudaMallocHost(&st->host, std::max(cap/8, host_bytes) + host_bytes)); st->cap = cap; }
+         o_count = al(o_list + (size_t)totalP*4), o_begin = al(o_count + (size_t)nc*4), o_cur = al(o_begin + (size_t)nc*4), o_opt = al(o_cur + (size_t)nc*4), o_opx = al(o_opt + (size_t)nc*4),
+         o_ov = al(o_opx + (size_t)nc*sizeof(double2)), o_rj = al(o_ov + (size_t)nc*sizeof(sdv_overlap_pt)), o_no = al(o_rj + (size_t)n_jobs*sizeof(RefineJob)), o_co = al(o_no + (size_t)n_jobs*4),
+         total = al(o_co + (size_t)C.ncells*4);
+  size_t h_jobs = 0, h_opt = al(h_jobs + (size_t)n_jobs*sizeof(RpJob)), h_opx = al(h_opt + (size_t)nc*4), h_rj = al(h_opx + (size_t)nc*sizeof(double2)), h_no = al(h_rj + (size_t)n_jobs*sizeof(RefineJob)),
+         h_co = al(h_no + (size_t)n_jobs*4), host_total = al(h_co + (size_t)C.ncells*4);
+  if (total > st->cap || host_total > st->host_cap) { cudaFree(st->dev); cudaFreeHost(st->host); st->dev = st->host = nullptr; st->cap = st->host_cap = 0;
+    const size_t cap = total + total/4, hcap = host_total + host_total/4;
+    CK(cudaMalloc(&st->dev, cap)); CK(cudaMallocHost(&st->host, hcap)); st->cap = cap; st->host_cap = hcap; }
   unsigned char* db = (unsigned char*)st->dev; unsigned char* hb = (unsigned char*)st->host;
-  RpJob* J = (RpJob*)hb; int32_t* h_opt = (int32_t*)(hb + al((size_t)n_jobs*sizeof(RpJob))); double2* h_opx = (double2*)((unsigned char*)h_opt + al((size_t)nc*4));
+  RpJob* J = (RpJob*)(hb + h_jobs); R.jobs_host = J; R.h_opt = (int32_t*)(hb + h_opt); R.h_opx = (double2*)(hb + h_opx); R.rj_host = (RefineJob*)(hb + h_rj); R.n_out_host = (int*)(hb + h_no);
   { int rcj = join_ingest(c); if (rcj) return rcj; }
   long long off = 0;
   for (int k=0;k<n_jobs;k++) {
@@ -324,40 +350,73 @@ int sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const 
     j.cur_kf_index = cur_kf_index ? cur_kf_index[k] : -1; j.backup = backup ? backup[k] : 0; j.nH = m.nH; j.nP = m.nP; j.pt_off = off; off += m.nP;
     const int oh = only_host ? only_host[k] : -1;
     // close_kfs (:123-131): keyframes in reverse index order, stable sort by distance to the target frame; the target itself is skipped (:138-139)
-    std::vector<std::pair<int,double>> ck;
-    for (int i = m.nH-1; i >= 0; i--) { const double d0 = cur.t[0]-m.host_copy.hostT[i][4], d1 = cur.t[1]-m.host_copy.hostT[i][5], d2 = cur.t[2]-m.host_copy.hostT[i][6]; ck.push_back({i, sqrt(d0*d0 + d1*d1 + d2*d2)}); }
-    std::stable_sort(ck.begin(), ck.end(), [](const std::pair<int,double>& a, const std::pair<int,double>& b) { return a.second < b.second; });
+    std::pair<int,double> ck[kRpMaxHosts]; int nk = 0;
+    for (int i = m.nH-1; i >= 0; i--) { const double d0 = cur.t[0]-m.host_copy.hostT[i][4], d1 = cur.t[1]-m.host_copy.hostT[i][5], d2 = cur.t[2]-m.host_copy.hostT[i][6]; ck[nk++] = {i, sqrt(d0*d0 + d1*d1 + d2*d2)}; }
+    std::stable_sort(ck, ck + nk, [](const std::pair<int,double>& a, const std::pair<int,double>& b) { return a.second < b.second; });
     for (int i=0;i<kRpMaxHosts;i++) j.frame_rank[i] = -1;
     if (oh >= 0) { if (oh >= m.nH) return ctx_fail(c, SDV_ERR_ARG, "reproject job %d: only_host %d of %d", k, oh, m.nH); j.frame_rank[oh] = 0; }
-    else { int r = 0; for (auto& e : ck) if (e.first != j.cur_kf_index) j.frame_rank[e.first] = r++; }
+    else { int r = 0; for (int e = 0; e < nk; e++) if (ck[e].first != j.cur_kf_index) j.frame_rank[ck[e].first] = r++; }
     const double ca = cur_ab ? cur_ab[2*k] : 0.0, cbb = cur_ab ? cur_ab[2*k+1] : 0.0;
     for (int i=0;i<m.nH;i++) { double o2[2]; aff_from_to(m.host_exposure[i], f.exposure, m.host_ab[i][0], m.host_ab[i][1], ca, cbb, o2); j.affLL[i][0] = (float)o2[0]; j.affLL[i][1] = (float)o2[1]; }
   }
-  RpScratch S; S.cand_px = (double2*)(db + o_px); S.cand_key = (float*)(db + o_key); S.cand_cell = (int*)(db + o_cell); S.list = (int*)(db + o_list);
+  RpScratch& S = R.S; S.cand_px = (double2*)(db + o_px); S.cand_key = (float*)(db + o_key); S.cand_cell = (int*)(db + o_cell); S.list = (int*)(db + o_list);
   S.count = (int*)(db + o_count); S.begin = (int*)(db + o_begin); S.cursor = (int*)(db + o_cur); S.out_pt = (int*)(db + o_opt); S.out_px = (double2*)(db + o_opx);
+  R.ov = (sdv_overlap_pt*)(db + o_ov); R.rj = (RefineJob*)(db + o_rj); R.n_out_dev = (int*)(db + o_no); R.cell_order_dev = (int*)(db + o_co);
   cudaStream_t s = c->st;
   CK(cudaMemcpyAsync(db + o_jobs, J, (size_t)n_jobs*sizeof(RpJob), cudaMemcpyHostToDevice, s));
   CK(cudaMemsetAsync(S.count, 0, (size_t)nc*4, s));
   CK(cudaEventRecord(c->ev0, s));
-  RpJob* jd = (RpJob*)(db + o_jobs);
+  RpJob* jd = (RpJob*)(db + o_jobs); R.jobs_dev = jd;
   rp_project_kernel<<<dim3((maxP + 255)/256, n_jobs), 256, 0, s>>>(jd, C, S);
   rp_scan_kernel<<<n_jobs, 1024, 0, s>>>(C, S);
   rp_scatter_kernel<<<dim3((maxP + 255)/256, n_jobs), 256, 0, s>>>(jd, C, S);
   rp_match_kernel<<<dim3((C.ncells + kRpWarps - 1)/kRpWarps, n_jobs), 32*kRpWarps, 0, s>>>(jd, C, S);
   CK(cudaGetLastError()); c->launches += 4;
+  return SDV_OK;
+}
+
+int sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, const double* cur_T7, const double* cur_ab,
+                            const int32_t* cur_kf_index, const int32_t* only_host, const int32_t* backup, const int32_t* cell_order, int max_matches,
+                            int32_t* n_out, int32_t* out_pt, double* out_px) {
+  if (!c || n_jobs <= 0 || !slots || !cur_frames || !cur_T7 || !n_out || !out_pt || !out_px) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device)); RpRun R; { int rc = rp_launch(c, n_jobs, slots, cur_frames, cur_T7, cur_ab, cur_kf_index, only_host, backup, R); if (rc) return rc; }
+  const RpConst& C = c->rp->C; cudaStream_t s = c->st; const long long nc = R.nc;
   CK(cudaEventRecord(c->ev1, s));
-  CK(cudaMemcpyAsync(h_opt, S.out_pt, (size_t)nc*4, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h_opx, S.out_px, (size_t)nc*sizeof(double2), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(J, jd, (size_t)n_jobs*sizeof(RpJob), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(R.h_opt, R.S.out_pt, (size_t)nc*4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(R.h_opx, R.S.out_px, (size_t)nc*sizeof(double2), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(R.jobs_host, R.jobs_dev, (size_t)n_jobs*sizeof(RpJob), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s)); CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
   for (int k=0;k<n_jobs;k++) {
-    if (J[k].error) return ctx_fail(c, SDV_ERR_ARG, "reproject job %d: a map point names a host outside [0,%d)", k, J[k].nH);
+    if (R.jobs_host[k].error) return ctx_fail(c, SDV_ERR_ARG, "reproject job %d: a map point names a host outside [0,%d)", k, R.jobs_host[k].nH);
     int n = 0, matches = 0; int32_t* op = out_pt + (size_t)k*C.ncells; double* ox = out_px + (size_t)k*C.ncells*2;
     for (int i=0;i<C.ncells;i++) { const int cell = cell_order ? cell_order[i] : i; if (cell < 0 || cell >= C.ncells) return ctx_fail(c, SDV_ERR_ARG, "cell_order[%d] = %d", i, cell);
       const long long cb = (long long)k*C.ncells + cell;
-      if (h_opt[cb] >= 0) { op[n] = h_opt[cb]; ox[2*n] = h_opx[cb].x; ox[2*n+1] = h_opx[cb].y; n++; matches++; }
+      if (R.h_opt[cb] >= 0) { op[n] = R.h_opt[cb]; ox[2*n] = R.h_opx[cb].x; ox[2*n+1] = R.h_opx[cb].y; n++; matches++; }
       if (matches > max_matches) break; }                                      // Reprojector.cpp:151-153
     n_out[k] = n;
+  }
+  return SDV_OK;
+}
+
+int sdv_tracker_refine_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, double* curToWorld_io, const double* cur_ab,
+                             const int32_t* cell_order, int max_matches, int32_t* n_matches, float* res, int32_t* iterations, int32_t* accepts) {
+  if (!c || n_jobs <= 0 || !slots || !cur_frames || !curToWorld_io) return SDV_ERR_ARG;
+  CK(cudaSetDevice(c->device)); RpRun R; { int rc = rp_launch(c, n_jobs, slots, cur_frames, curToWorld_io, cur_ab, nullptr, nullptr, nullptr, R); if (rc) return rc; }
+  const RpConst& C = c->rp->C; cudaStream_t s = c->st;
+  if (cell_order) { for (int i=0;i<C.ncells;i++) if (cell_order[i] < 0 || cell_order[i] >= C.ncells) return ctx_fail(c, SDV_ERR_ARG, "cell_order[%d] = %d", i, cell_order[i]);
+    CK(cudaMemcpyAsync(R.cell_order_dev, cell_order, (size_t)C.ncells*4, cudaMemcpyHostToDevice, s)); }
+  rp_emit_kernel<<<n_jobs, 1024, 0, s>>>(R.jobs_dev, C, R.S, cell_order ? R.cell_order_dev : nullptr, max_matches, R.ov, R.rj, R.n_out_dev);
+  launch_struct_pose(R.rj, n_jobs, R.ov, nullptr, c->tc_dev, s);
+  CK(cudaGetLastError()); c->launches += 2;
+  CK(cudaEventRecord(c->ev1, s));
+  CK(cudaMemcpyAsync(R.rj_host, R.rj, (size_t)n_jobs*sizeof(RefineJob), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(R.n_out_host, R.n_out_dev, (size_t)n_jobs*4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(R.jobs_host, R.jobs_dev, (size_t)n_jobs*sizeof(RpJob), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s)); CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  for (int k=0;k<n_jobs;k++) {
+    if (R.jobs_host[k].error) return ctx_fail(c, SDV_ERR_ARG, "refine job %d: a map point names a host outside [0,%d)", k, R.jobs_host[k].nH);
+    for (int i=0;i<7;i++) curToWorld_io[7*k+i] = R.rj_host[k].T[i];
+    if (n_matches) n_matches[k] = R.n_out_host[k]; if (res) res[k] = R.rj_host[k].res; if (iterations) iterations[k] = R.rj_host[k].iterations; if (accepts) accepts[k] = R.rj_host[k].accepts;
   }
   return SDV_OK;
 }

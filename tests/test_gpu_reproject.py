@@ -84,6 +84,31 @@ def test_reproject_then_struct_pose_recovers_pose():
     ctx.close()
 
 
+def test_fused_refine_equals_separate_calls_and_oracle():
+    api, synth = _mods(); K, wh = synth.KITTI_K, synth.KITTI_WH; w, h = wh; kfs = [0, 1, 2, 3, 4, 5, 6]
+    seq, L, pts, hT, hab, ctx, frames, poses = _scene(api, synth, K, wh, 8, 2000, kfs, 400, idepth_noise=0.01)
+    rp = api.Reprojector(ctx); rp.setMap(0, [100 + k for k in kfs], hT, hab, pts); rp.setMap(1, [100 + k for k in kfs[:4]], hT[:4], hab[:4], pts[pts["host"] < 4])
+    rng = np.random.default_rng(3); order = rng.permutation(rp.n_cells).astype(np.int32)
+    T0 = np.stack([poses[7] + np.concatenate([np.zeros(4), rng.normal(0, 0.04, 3)]) for _ in range(4)])
+    slots = [0, 1, 0, 1]
+    f = rp.refineBatch(slots, [107] * 4, T0, cell_order=order, max_matches=300)
+    tr = api.CoarseTracker(ctx, 0); kf_frames = [frames[k] for k in kfs]
+    for k in range(4):
+        P = pts if slots[k] == 0 else pts[pts["host"] < 4]; nH = 7 if slots[k] == 0 else 4
+        idx, px = rp.reprojectMap(slots[k], 107, T0[k], cell_order=order, max_matches=300)
+        ov = np.zeros(len(idx), api.OVERLAP_PT_DTYPE)
+        for key in ("u", "v", "idepth", "host"):
+            ov[key] = P[key][idx]
+        ov["obs_x"], ov["obs_y"] = px[:, 0], px[:, 1]
+        r = tr.structPoseEstimation(T0[k], ov, hT[:nH])
+        assert f["n_matches"][k] == len(idx) == 301 and np.array_equal(f["T"][k], r["T"]) and (f["iterations"][k], f["accepts"][k]) == (r["iterations"], r["accepts"])
+        oi, opx = orc.reproject_map(w, h, L, K, kf_frames[:nH], hT[:nH], hab[:nH], frames[7], T0[k], [0.0, 0.0], P, cell_order=order, max_matches=300)
+        p6 = np.stack([P["u"][oi], P["v"][oi], P["idepth"][oi], P["host"][oi].astype(np.float32), opx[:, 0].astype(np.float32), opx[:, 1].astype(np.float32)], 1).astype(np.float32)
+        o = orc.struct_pose(w, h, np.array(K, np.float32), hT[:nH], p6, T0[k])
+        assert (o["iterations"], o["accepts"]) == (int(f["iterations"][k]), int(f["accepts"][k])) and np.abs(o["T"] - f["T"][k]).max() < 1e-9
+    ctx.close()
+
+
 def test_reproject_errors():
     api, synth = _mods(); kfs = [0, 1, 2]
     seq, L, pts, hT, hab, ctx, frames, poses = _scene(api, synth, SMALL_K, SMALL_WH, 5, 3000, kfs, 50)
