@@ -91,18 +91,18 @@ def test_fused_refine_equals_separate_calls_and_oracle():
     rng = np.random.default_rng(3); order = rng.permutation(rp.n_cells).astype(np.int32)
     T0 = np.stack([poses[7] + np.concatenate([np.zeros(4), rng.normal(0, 0.04, 3)]) for _ in range(4)])
     slots = [0, 1, 0, 1]
-    f = rp.refineBatch(slots, [107] * 4, T0, cell_order=order, max_matches=300)
+    f = rp.refineBatch(slots, [107] * 4, T0, cell_order=order, max_matches=150)
     tr = api.CoarseTracker(ctx, 0); kf_frames = [frames[k] for k in kfs]
     for k in range(4):
         P = pts if slots[k] == 0 else pts[pts["host"] < 4]; nH = 7 if slots[k] == 0 else 4
-        idx, px = rp.reprojectMap(slots[k], 107, T0[k], cell_order=order, max_matches=300)
+        idx, px = rp.reprojectMap(slots[k], 107, T0[k], cell_order=order, max_matches=150)
         ov = np.zeros(len(idx), api.OVERLAP_PT_DTYPE)
         for key in ("u", "v", "idepth", "host"):
             ov[key] = P[key][idx]
         ov["obs_x"], ov["obs_y"] = px[:, 0], px[:, 1]
         r = tr.structPoseEstimation(T0[k], ov, hT[:nH])
-        assert f["n_matches"][k] == len(idx) == 301 and np.array_equal(f["T"][k], r["T"]) and (f["iterations"][k], f["accepts"][k]) == (r["iterations"], r["accepts"])
-        oi, opx = orc.reproject_map(w, h, L, K, kf_frames[:nH], hT[:nH], hab[:nH], frames[7], T0[k], [0.0, 0.0], P, cell_order=order, max_matches=300)
+        assert f["n_matches"][k] == len(idx) == 151 and np.array_equal(f["T"][k], r["T"]) and (f["iterations"][k], f["accepts"][k]) == (r["iterations"], r["accepts"])
+        oi, opx = orc.reproject_map(w, h, L, K, kf_frames[:nH], hT[:nH], hab[:nH], frames[7], T0[k], [0.0, 0.0], P, cell_order=order, max_matches=150)
         p6 = np.stack([P["u"][oi], P["v"][oi], P["idepth"][oi], P["host"][oi].astype(np.float32), opx[:, 0].astype(np.float32), opx[:, 1].astype(np.float32)], 1).astype(np.float32)
         o = orc.struct_pose(w, h, np.array(K, np.float32), hT[:nH], p6, T0[k])
         assert (o["iterations"], o["accepts"]) == (int(f["iterations"][k]), int(f["accepts"][k])) and np.abs(o["T"] - f["T"][k]).max() < 1e-9
