@@ -155,6 +155,30 @@ int  sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_beg
  * aff_g2l.  n_matches = overlap_pts.size(), res/iterations/accepts as in sdv_tracker_struct_pose_batch. */
 int  sdv_tracker_refine_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, double* curToWorld_io, const double* cur_ab,
                               const int32_t* cell_order, int max_matches, int32_t* n_matches, float* res, int32_t* iterations, int32_t* accepts);
+/* ---- Vec4 FullSystem::trackNewCoarse(FrameHessian* fh)                                                   FullSystem.cpp:283-500 (§8 a4)
+ * The per-frame policy for a running system (allFrameHistory.size() > 2): 31 motion hypotheses (:334-395), the re-track loop over
+ * trackNewestCoarse with the achievedRes abort vector (:410-462), fallback (:464-470), pose composition (:474-479), reprojectMap +
+ * structPoseEstimation (:481-488).  Batched over n sequences: try i is one track_batch launch over the sequences still searching.
+ * The caller keeps FullSystem's per-sequence state (allFrameHistory shells, lastCoarseRMSE, firstCoarseRMSE) and passes what the function reads. */
+typedef struct {
+  /* in */
+  int32_t  slot;                 /* tracker slot == map slot of the sequence (coarseTracker / the active window) */
+  int32_t  poses_valid;          /* slast->poseValid && sprelast->poseValid && lastF->shell->poseValid  (:390) */
+  uint64_t frame;                /* device handle of fh */
+  double   sprelast_c2w[7], slast_c2w[7], lastF_c2w[7];   /* camToWorld of allFrameHistory[size-3], [size-2], coarseTracker->lastRef->shell */
+  double   aff_last[2];          /* slast->aff_g2l {a,b} */
+  /* in-out */
+  double   lastCoarseRMSE[5];    /* FullSystem::lastCoarseRMSE in, achievedRes out (:472) */
+  /* out */
+  double   camToWorld[7];        /* fh->shell->camToWorld after structPoseEstimation */
+  double   camToTrackingRef[7];  /* fh->shell->camToTrackingRef (:490-491) */
+  double   aff_g2l[2];           /* fh->shell->aff_g2l */
+  double   flow[3];              /* flowVecs (the Vec4 result is {lastCoarseRMSE[0], flow[0..2]}) */
+  float    refine_res;
+  int32_t  have_one_good, tries, n_matches, refine_iterations, refine_accepts;
+} sdv_track_new_coarse_io;
+int  sdv_track_new_coarse_batch(sdv_ctx* c, int n, sdv_track_new_coarse_io* io, const int32_t* cell_order, int max_matches);
+
 /* device time of the last track / track_batch / calc_res launch in milliseconds (CUDA events on the context stream) */
 float sdv_last_kernel_ms(sdv_ctx* c);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

@@ -180,6 +180,47 @@ def reproject_map(w, h, levels, K4, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, 
     return out_pt[:n].copy(), out_px[:n].copy()
 
 
+def track_new_coarse(tracker, new_frame, K4, kf_frames, kf_T7, kf_ab, map_pts, sprelast_c2w, slast_c2w, lastF_c2w, aff_last, poses_valid, lastCoarseRMSE,
+                     cell_order=None, max_matches=1200):
+    """FullSystem::trackNewCoarse restated for a running system (FullSystem.cpp:283-500, branch :334-395) over the oracle pieces:
+    hypotheses :346-388, re-track loop :410-462, fallback :464-470, pose composition :474-479, reprojectMap + structPoseEstimation :481-491.
+    `tracker` is an orc.CoarseTracker whose reference is lastF.  Pure-Python control flow (<= 31 tries), all numerics in liborc."""
+    w, h, L = tracker.w, tracker.h, tracker.levels
+    if not poses_valid:
+        tries = [np.array([1, 0, 0, 0, 0, 0, 0.0])]
+    else:
+        slast_2_sprelast = se3_mul(se3_inv(sprelast_c2w), slast_c2w); lastF_2_slast = se3_mul(se3_inv(slast_c2w), lastF_c2w)
+        fh_2_slast = slast_2_sprelast; inv = se3_inv(fh_2_slast); cm = se3_mul(inv, lastF_2_slast)
+        tries = [cm, se3_mul(se3_mul(inv, inv), lastF_2_slast), se3_mul(se3_inv(se3_exp(se3_log(fh_2_slast) * 0.5)), lastF_2_slast), lastF_2_slast,
+                 np.array([1, 0, 0, 0, 0, 0, 0.0])]
+        r = float(np.float32(0.02))
+        for q in [(r, 0, 0), (0, r, 0), (0, 0, r), (-r, 0, 0), (0, -r, 0), (0, 0, -r), (r, r, 0), (0, r, r), (r, 0, r), (-r, r, 0), (0, -r, r), (-r, 0, r), (r, -r, 0),
+                  (0, r, -r), (r, 0, -r), (-r, -r, 0), (0, -r, -r), (-r, 0, -r), (-r, -r, -r), (-r, -r, r), (-r, r, -r), (-r, r, r), (r, -r, -r), (r, -r, r), (r, r, -r), (r, r, r)]:
+            qq = np.array([1.0, q[0], q[1], q[2]]); qq = qq / np.sqrt(qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3] + qq[0] * qq[0])
+            tries.append(se3_mul(cm, np.concatenate([qq, np.zeros(3)])))
+    achieved = np.full(5, np.nan); have = False; flow = np.array([100.0, 100.0, 100.0]); lastF_2_fh = np.array([1, 0, 0, 0, 0, 0, 0.0]); aff = np.zeros(2); n_tries = 0
+    for T in tries:
+        r = tracker.trackNewestCoarse(new_frame, T, aff_last, L - 1, achieved.copy()); n_tries += 1
+        lr = r["lastResiduals"]
+        if r["good"] and np.isfinite(np.float32(lr[0])) and not (lr[0] >= achieved[0]):
+            flow = r["flow"].copy(); aff = r["ab"].copy(); lastF_2_fh = r["T"].copy(); have = True
+        if have:
+            for i in range(5):
+                if (not np.isfinite(np.float32(achieved[i]))) or achieved[i] > lr[i]:
+                    achieved[i] = lr[i]
+        if have and achieved[0] < lastCoarseRMSE[0] * float(np.float32(1.5)):
+            break
+    if not have:
+        flow = np.zeros(3); aff = np.array(aff_last, np.float64); lastF_2_fh = tries[0]
+    camToWorld = se3_mul(lastF_c2w, se3_inv(lastF_2_fh))
+    idx, px = reproject_map(w, h, L, K4, kf_frames, kf_T7, kf_ab, new_frame, camToWorld, aff, map_pts, cell_order=cell_order, max_matches=max_matches)
+    p6 = np.stack([map_pts["u"][idx], map_pts["v"][idx], map_pts["idepth"][idx], map_pts["host"][idx].astype(np.float32), px[:, 0].astype(np.float32), px[:, 1].astype(np.float32)], 1).astype(np.float32) \
+        if len(idx) else np.zeros((0, 6), np.float32)
+    sp = struct_pose(w, h, np.asarray(K4, np.float32), kf_T7, p6, camToWorld)
+    return dict(camToWorld=sp["T"], camToTrackingRef=se3_mul(se3_inv(lastF_c2w), sp["T"]), aff_g2l=aff, flow=flow, lastCoarseRMSE=achieved, have_one_good=have, tries=n_tries,
+                n_matches=len(idx), refine_iterations=sp["iterations"], refine_accepts=sp["accepts"], camToWorld_tracked=camToWorld)
+
+
 def struct_pose(w, h, K4, host_T7, pts6, curToWorld7):
     """CoarseTracker::structPoseEstimation restated (orc_refine.cpp).  pts6: (n,6) float32 {u,v,idepth,host,obs_x,obs_y}."""
     L = lib()

@@ -234,6 +234,33 @@ class CoarseTracker:
         return dict(T=r["T"][0], res=float(r["res"][0]), iterations=int(r["iterations"][0]), accepts=int(r["accepts"][0]))
 
 
+class sdv_track_new_coarse_io(C.Structure):
+    _fields_ = [("slot", C.c_int32), ("poses_valid", C.c_int32), ("frame", C.c_uint64), ("sprelast_c2w", C.c_double * 7), ("slast_c2w", C.c_double * 7), ("lastF_c2w", C.c_double * 7),
+                ("aff_last", C.c_double * 2), ("lastCoarseRMSE", C.c_double * 5), ("camToWorld", C.c_double * 7), ("camToTrackingRef", C.c_double * 7), ("aff_g2l", C.c_double * 2),
+                ("flow", C.c_double * 3), ("refine_res", C.c_float), ("have_one_good", C.c_int32), ("tries", C.c_int32), ("n_matches", C.c_int32), ("refine_iterations", C.c_int32),
+                ("refine_accepts", C.c_int32)]
+
+
+def trackNewCoarseBatch(ctx, jobs, cell_order=None, max_matches=1200):
+    """FullSystem::trackNewCoarse (FullSystem.cpp:283-500) for n sequences.  jobs: dicts with slot, frame, sprelast_c2w, slast_c2w, lastF_c2w, aff_last,
+    poses_valid, lastCoarseRMSE.  Returns one dict per job with the fields of sdv_track_new_coarse_io."""
+    LIB.sdv_track_new_coarse_batch.argtypes = [_vp, C.c_int, C.POINTER(sdv_track_new_coarse_io), _vp, C.c_int]
+    n = len(jobs); io = (sdv_track_new_coarse_io * n)()
+    for k, j in enumerate(jobs):
+        io[k].slot = j["slot"]; io[k].poses_valid = int(j.get("poses_valid", 1)); io[k].frame = j["frame"]
+        for name in ("sprelast_c2w", "slast_c2w", "lastF_c2w", "aff_last", "lastCoarseRMSE"):
+            v = np.asarray(j[name], np.float64); getattr(io[k], name)[:] = v.tolist()
+    co = None if cell_order is None else np.ascontiguousarray(cell_order, np.int32)
+    ctx._ck(LIB.sdv_track_new_coarse_batch(ctx.p, n, io, None if co is None else co.ctypes.data, max_matches))
+    out = []
+    for k in range(n):
+        o = io[k]
+        out.append(dict(camToWorld=np.array(o.camToWorld[:]), camToTrackingRef=np.array(o.camToTrackingRef[:]), aff_g2l=np.array(o.aff_g2l[:]), flow=np.array(o.flow[:]),
+                        lastCoarseRMSE=np.array(o.lastCoarseRMSE[:]), have_one_good=bool(o.have_one_good), tries=int(o.tries), n_matches=int(o.n_matches),
+                        refine_iterations=int(o.refine_iterations), refine_accepts=int(o.refine_accepts), refine_res=float(o.refine_res)))
+    return out
+
+
 class Reprojector:
     """Mirror of sdv_loam::Reprojector (FullSystem/Reprojector.h:17-111) over device-resident maps: one map slot per sequence."""
 

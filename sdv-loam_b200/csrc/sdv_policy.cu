@@ -1,0 +1,82 @@
+// sdv_policy.cu — FullSystem::trackNewCoarse as a batched host policy over the device kernels.
+//
+// Restates /root/reference/src/FullSystem/FullSystem.cpp:283-500 (the branch for a running system, :334-395: allFrameHistory.size() > 2;
+// the two-frame bootstrap through CoarseInitializer is out of scope):
+//   motion hypotheses lastF_2_fh_tries (constant / double / half / zero motion, zero from KF, 26 small rotations — the rotDelta loop of :357
+//   increments by 1.0, so it runs once), the re-track loop with the per-level "at least as good as the best try" abort vector (:410-462),
+//   the fallback when every try fails (:464-470), pose composition (:474-479), reprojectMap + structPoseEstimation (:481-488).
+// Batched form: try i is ONE sdv_tracker_track_batch launch over the sequences that have not met the immediate-accept rule (:460) yet —
+// with healthy tracking every sequence stops after try 0, stragglers continue in smaller launches.  The refinement of all sequences is one
+// sdv_tracker_refine_batch call.  Host code only; all numerics happen in the kernels the two entries launch.
+#include <vector>
+#include <math.h>
+#include <string.h>
+#include "sdv_ctx.cuh"
+
+using namespace sdv;
+
+static SE3d quatT(double w, double x, double y, double z) { SE3d s; s.q = qnormalize(Quat{w, x, y, z}); s.t[0] = s.t[1] = s.t[2] = 0; return s; }   // SE3(Quaterniond, Vec3) normalises
+
+static void make_tries(const sdv_track_new_coarse_io& io, std::vector<SE3d>& tries) {
+  tries.clear();
+  if (!io.poses_valid) { tries.push_back(se3_identity()); return; }                     // :390-394
+  const SE3d sprelast = se3_from7(io.sprelast_c2w), slast = se3_from7(io.slast_c2w), lastF = se3_from7(io.lastF_c2w);
+  const SE3d slast_2_sprelast = se3_mul(se3_inv(sprelast), slast);                       // :343
+  const SE3d lastF_2_slast = se3_mul(se3_inv(slast), lastF);                             // :344
+  const SE3d fh_2_slast = slast_2_sprelast, inv = se3_inv(fh_2_slast);
+  const SE3d cm = se3_mul(inv, lastF_2_slast);
+  tries.push_back(cm);                                                                   // constant motion
+  tries.push_back(se3_mul(se3_mul(inv, inv), lastF_2_slast));                            // double motion (left-associated like the expression :351)
+  { double lg[6]; se3_log(fh_2_slast, lg); for (int i=0;i<6;i++) lg[i] = lg[i]*0.5; tries.push_back(se3_mul(se3_inv(se3_exp(lg)), lastF_2_slast)); }   // half motion
+  tries.push_back(lastF_2_slast);                                                        // zero motion
+  tries.push_back(se3_identity());                                                       // zero motion from KF
+  const double r = (double)0.02f;                                                        // float rotDelta promoted to double in the Quaterniond ctor
+  const double q[26][3] = {{r,0,0},{0,r,0},{0,0,r},{-r,0,0},{0,-r,0},{0,0,-r},{r,r,0},{0,r,r},{r,0,r},{-r,r,0},{0,-r,r},{-r,0,r},{r,-r,0},{0,r,-r},{r,0,-r},
+                           {-r,-r,0},{0,-r,-r},{-r,0,-r},{-r,-r,-r},{-r,-r,r},{-r,r,-r},{-r,r,r},{r,-r,-r},{r,-r,r},{r,r,-r},{r,r,r}};
+  for (int k=0;k<26;k++) tries.push_back(se3_mul(cm, quatT(1, q[k][0], q[k][1], q[k][2])));   // (fh_2_slast^-1 * lastF_2_slast) * dR, left-associated
+}
+
+extern "C" int sdv_track_new_coarse_batch(sdv_ctx* c, int n, sdv_track_new_coarse_io* io, const int32_t* cell_order, int max_matches) {
+  if (!c || n <= 0 || !io) return SDV_ERR_ARG;
+  const float setting_reTrackThreshold = 1.5f;                                           // settings.cpp:130
+  const int coarsest = c->levels - 1;
+  struct St { std::vector<SE3d> tries; double achieved[5]; bool haveOneGood, done; SE3d lastF_2_fh; double aff[2]; double flow[3]; int tryIterations; };
+  std::vector<St> st(n);
+  size_t maxTries = 0;
+  for (int k=0;k<n;k++) { St& s = st[k]; make_tries(io[k], s.tries); maxTries = std::max(maxTries, s.tries.size());
+    for (int i=0;i<5;i++) s.achieved[i] = nan(""); s.haveOneGood = false; s.done = false; s.lastF_2_fh = se3_identity(); s.aff[0] = s.aff[1] = 0; s.flow[0] = s.flow[1] = s.flow[2] = 100; s.tryIterations = 0; }
+  std::vector<int> act; std::vector<int32_t> slots, good; std::vector<uint64_t> frames; std::vector<double> T, ab, minRes, lastRes, flow;
+  for (size_t i = 0; i < maxTries; i++) {
+    act.clear(); for (int k=0;k<n;k++) if (!st[k].done && i < st[k].tries.size()) act.push_back(k);
+    if (act.empty()) break;
+    const int m = (int)act.size();
+    slots.resize(m); frames.resize(m); good.resize(m); T.resize(7*m); ab.resize(2*m); minRes.resize(5*m); lastRes.resize(5*m); flow.resize(3*m);
+    for (int a=0;a<m;a++) { const int k = act[a]; slots[a] = io[k].slot; frames[a] = io[k].frame; se3_to7(st[k].tries[i], &T[7*a]);
+      ab[2*a] = io[k].aff_last[0]; ab[2*a+1] = io[k].aff_last[1]; for (int l=0;l<5;l++) minRes[5*a+l] = st[k].achieved[l]; }
+    int rc = sdv_tracker_track_batch(c, m, slots.data(), frames.data(), T.data(), ab.data(), coarsest, minRes.data(), lastRes.data(), flow.data(), good.data(), nullptr);
+    if (rc) return rc;
+    for (int a=0;a<m;a++) { const int k = act[a]; St& s = st[k]; s.tryIterations++;
+      const double* lr = &lastRes[5*a];
+      if (good[a] && isfinite((float)lr[0]) && !(lr[0] >= s.achieved[0])) {             // :444-450 "do we have a new winner?"
+        for (int l=0;l<3;l++) s.flow[l] = flow[3*a+l]; s.aff[0] = ab[2*a]; s.aff[1] = ab[2*a+1]; s.lastF_2_fh = se3_from7(&T[7*a]); s.haveOneGood = true; }
+      if (s.haveOneGood) for (int l=0;l<5;l++) if (!isfinite((float)s.achieved[l]) || s.achieved[l] > lr[l]) s.achieved[l] = lr[l];   // :453-459
+      if (s.haveOneGood && s.achieved[0] < io[k].lastCoarseRMSE[0]*setting_reTrackThreshold) s.done = true;                           // :461-462
+    }
+  }
+  std::vector<double> c2w(7*n), cab(2*n);
+  slots.resize(n); frames.resize(n);
+  for (int k=0;k<n;k++) { St& s = st[k]; sdv_track_new_coarse_io& o = io[k];
+    if (!s.haveOneGood) { s.flow[0] = s.flow[1] = s.flow[2] = 0; s.aff[0] = o.aff_last[0]; s.aff[1] = o.aff_last[1]; s.lastF_2_fh = s.tries[0]; }   // :464-470
+    for (int l=0;l<5;l++) o.lastCoarseRMSE[l] = s.achieved[l];                           // :472
+    const SE3d camToTrackingRef = se3_inv(s.lastF_2_fh); const SE3d camToWorld = se3_mul(se3_from7(o.lastF_c2w), camToTrackingRef);   // :475-479
+    se3_to7(camToWorld, &c2w[7*k]); cab[2*k] = s.aff[0]; cab[2*k+1] = s.aff[1]; slots[k] = o.slot; frames[k] = o.frame;
+    o.aff_g2l[0] = s.aff[0]; o.aff_g2l[1] = s.aff[1]; for (int l=0;l<3;l++) o.flow[l] = s.flow[l]; o.have_one_good = s.haveOneGood ? 1 : 0; o.tries = s.tryIterations; }
+  std::vector<int32_t> nm(n), its(n), acc(n); std::vector<float> res(n);
+  int rc = sdv_tracker_refine_batch(c, n, slots.data(), frames.data(), c2w.data(), cab.data(), cell_order, max_matches, nm.data(), res.data(), its.data(), acc.data());   // :481-488
+  if (rc) return rc;
+  for (int k=0;k<n;k++) { sdv_track_new_coarse_io& o = io[k];
+    for (int i=0;i<7;i++) o.camToWorld[i] = c2w[7*k+i];
+    const SE3d rel = se3_mul(se3_inv(se3_from7(o.lastF_c2w)), se3_from7(o.camToWorld)); se3_to7(rel, o.camToTrackingRef);              // :490-491
+    o.n_matches = nm[k]; o.refine_res = res[k]; o.refine_iterations = its[k]; o.refine_accepts = acc[k]; }
+  return SDV_OK;
+}
