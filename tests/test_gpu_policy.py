@@ -39,7 +39,7 @@ def test_track_new_coarse_batch_matches_oracle():
         o = orc.track_new_coarse(otr, frames[j["frame"] - 100], K, kf_frames, hT, hab, pts, j["sprelast_c2w"], j["slast_c2w"], j["lastF_c2w"], j["aff_last"], j["poses_valid"],
                                  j["lastCoarseRMSE"], cell_order=order)
         assert g["tries"] == o["tries"] and g["have_one_good"] == o["have_one_good"], (g["tries"], o["tries"])
-        assert np.allclose(g["lastCoarseRMSE"], o["lastCoarseRMSE"], rtol=1e-4, equal_nan=True) and np.allclose(g["aff_g2l"], o["aff_g2l"], atol=1e-6)
+        assert np.allclose(g["lastCoarseRMSE"], o["lastCoarseRMSE"], rtol=1e-4, equal_nan=True) and np.allclose(g["aff_g2l"], o["aff_g2l"], atol=2e-4)       # same bound as the LM parity tests (b is in grey levels)
         assert g["n_matches"] == o["n_matches"] and (g["refine_iterations"], g["refine_accepts"]) == (o["refine_iterations"], o["refine_accepts"])
         assert np.abs(g["camToWorld"] - o["camToWorld"]).max() < 1e-6 and np.abs(g["camToTrackingRef"] - o["camToTrackingRef"]).max() < 1e-6
     assert res[0]["tries"] == 1 and res[1]["tries"] == 31 and res[2]["tries"] == 1
