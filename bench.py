@@ -190,6 +190,54 @@ def ba_leg(ctx, api, synth, local_rank, W, reps=4, warm=2):
             "note": "device time of sdv_ba_optimize_batch (FullSystem::optimize, device-resident GN schedule); bit-exact vs the CPU oracle (tests/test_gpu_ba.py)"}
 
 
+def refine_leg(ctx, api, synth, B, reps=6, warm=2, seed=11):
+    """Semi-direct refinement leg = the tail of FullSystem::trackNewCoarse (FullSystem.cpp:481-488): Reprojector::reprojectMap of the active map
+    (7 keyframes, ~2000 active points) into the new frame + CoarseTracker::structPoseEstimation, fused on the device (sdv_tracker_refine_batch).
+    One map slot and one private target frame per sequence; the 7 keyframe images are shared by the sequences (read footprint per frame is
+    ~400 10x10 patches).  Reports device time (CUDA events in the library) and wall time of the C-ABI call (job H2D + result D2H inside)."""
+    from conftest import cached_sequence
+    orc = se3_helpers()
+    seq8 = cached_sequence(8, 2000, synth.KITTI_K, synth.KITTI_WH)
+    pts, hT, hab = synth.make_map(seq8, list(range(7)), n_per_frame=300, seed=2)
+    base = 1 << 42; kf_ids = [base + k for k in range(7)]
+    for k in range(7):
+        ctx.makeImages(kf_ids[k], seq8.images[k])
+    rp = api.Reprojector(ctx); slots = np.arange(B, dtype=np.int32); ids = np.arange(B, dtype=np.uint64) + np.uint64(base + 100)
+    for b in range(B):
+        rp.setMap(b, kf_ids, hT, hab, pts); ctx.makeImages(int(ids[b]), seq8.images[7])
+    gt = np.concatenate([synth._quat_from_R(seq8.R[7]), seq8.t[7]]); rng = np.random.default_rng(seed)
+    order = rng.permutation(rp.n_cells).astype(np.int32)
+    def inits():
+        T = np.tile(gt, (B, 1))
+        for b in range(B):
+            T[b] = orc.se3_mul(orc.se3_exp(np.concatenate([rng.normal(0, 0.02, 3), rng.normal(0, 0.001, 3)])), gt)
+        return T
+    ms = []; wall = []; last = None
+    for rep in range(warm + reps):
+        T0 = inits(); ctx.sync(); t0 = time.perf_counter()
+        r = rp.refineBatch(slots, ids, T0, cell_order=order, max_matches=400)
+        t1 = time.perf_counter()
+        if rep >= warm:
+            ms.append(r["ms"]); wall.append(t1 - t0); last = (r, T0)
+    r, T0 = last
+    e0 = float(np.median(np.linalg.norm(T0[:, 4:] - gt[4:], axis=1))); e1 = float(np.median(np.linalg.norm(r["T"][:, 4:] - gt[4:], axis=1)))
+    # CPU port of the same stage on one core (bounded sample)
+    L = 4; kf_frames = [orc.Frame(seq8.images[k], L) for k in range(7)]; cur = orc.Frame(seq8.images[7], L); w, h = synth.KITTI_WH
+    ts = []
+    for i in range(3):
+        t0 = time.perf_counter()
+        idx, px = orc.reproject_map(w, h, L, synth.KITTI_K, kf_frames, hT, hab, cur, T0[i], [0.0, 0.0], pts, cell_order=order, max_matches=400)
+        p6 = np.stack([pts["u"][idx], pts["v"][idx], pts["idepth"][idx], pts["host"][idx].astype(np.float32), px[:, 0].astype(np.float32), px[:, 1].astype(np.float32)], 1).astype(np.float32)
+        orc.struct_pose(w, h, np.array(synth.KITTI_K, np.float32), hT, p6, T0[i]); ts.append(time.perf_counter() - t0)
+    for b in range(B):
+        ctx.releaseFrame(int(ids[b]))
+    return {"frames": B, "map_points": int(len(pts)), "keyframes": 7, "ms_per_batch_device": float(np.mean(ms)), "ms_per_batch_wall": 1e3 * float(np.mean(wall)),
+            "frames_per_s_device": B / (float(np.mean(ms)) * 1e-3), "frames_per_s_wall": B / float(np.mean(wall)),
+            "matches_mean": float(r["n_matches"].mean()), "gn_iterations_mean": float(r["iterations"].mean()), "accepts_mean": float(r["accepts"].mean()),
+            "median_translation_err_in_out_m": [e0, e1], "cpu_ms_per_frame_1core": 1e3 * float(np.median(ts)),
+            "note": "sdv_tracker_refine_batch: reprojectMap (grid 25 px, warp-per-cell direct alignment) + structPoseEstimation, device resident; exact parity vs the CPU oracle (tests/test_gpu_reproject.py)"}
+
+
 def ba_cpu_ms(synth):
     """oracle optimize() on one host core, ms per window"""
     orc = se3_helpers()
@@ -220,6 +268,7 @@ def main():
     ap.add_argument("--points", type=int, default=2000, help="LiDAR-depth splats of the keyframe (reference default ~1500-2000 active points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ba-windows", type=int, default=296, help="BA leg: resident 7-keyframe windows optimised per batch (0 = skip the BA leg)")
+    ap.add_argument("--no-refine", action="store_true", help="skip the reprojectMap + structPoseEstimation leg")
     ap.add_argument("--kf-every", type=int, default=5, help="keyframe cadence assumed when combining the tracker and BA legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -261,7 +310,7 @@ def main():
     p4 = np.concatenate([pts, np.full((len(pts), 1), 1e-3, np.float32)], 1).astype(np.float32); rh = np.zeros(len(p4), np.int32)
 
     WBA = max(0, args.ba_windows)
-    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=B, max_frames=2 * B + 1 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
+    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=B, max_frames=3 * B + 16 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
     KF = 1 << 40
     for b in range(B):                                                   # per sequence: keyframe -> reference cloud (makeCoarseDepthL0 on device)
         ctx.makeImages(KF, seq.images[0]); api.CoarseTracker(ctx, b).setCoarseTrackingRef(KF, p4, rh); ctx.releaseFrame(KF)
@@ -359,6 +408,7 @@ def main():
     clocks = sampler.stop()
 
     ba = ba_leg(ctx, api, synth, local_rank, WBA) if WBA > 0 else None
+    refine = refine_leg(ctx, api, synth, B) if not args.no_refine else None
     tv = torch.tensor([t_value, t_e2e, kern_ms, t_e2e_u8], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
@@ -400,12 +450,20 @@ def main():
         fps_track = line["value"]; wps = ba["windows_per_s"]
         line["combined"] = {"kf_every": args.kf_every, "frames_per_s_track_plus_ba": 1.0 / (1.0 / fps_track + 1.0 / (args.kf_every * wps)),
                             "note": "tracking every frame + one FullSystem::optimize per kf_every frames, both legs measured separately on resident data"}
+        if refine is not None:
+            fr = refine["frames_per_s_device"] * world
+            line["combined"]["frames_per_s_track_refine_ba"] = 1.0 / (1.0 / fps_track + 1.0 / fr + 1.0 / (args.kf_every * wps))
+    if refine is not None:
+        refine["frames_per_s_device"] *= world; refine["frames_per_s_wall"] *= world
+        line["refine"] = refine
     if not args.no_cpu_baseline:
         arm = CpuArm(seq, synth, p4, 1); arm.run(3)
         nf, tw = arm.run(10 ** 9, budget_s=12.0)
         if ba is not None:
             cms = ba_cpu_ms(synth); line["ba"]["cpu_ms_per_window_1core"] = cms
             line["combined"]["cpu_frames_per_s_track_plus_ba_1core"] = 1.0 / (tw / nf + cms * 1e-3 / args.kf_every)
+            if refine is not None:
+                line["combined"]["cpu_frames_per_s_track_refine_ba_1core"] = 1.0 / (tw / nf + refine["cpu_ms_per_frame_1core"] * 1e-3 + cms * 1e-3 / args.kf_every)
         line["cpu_baseline"] = {"value": nf / tw, "unit": "frames/s", "cores": 1, "kind": "port",
                                 "sample": "%d frames (makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; oracle/ CPU restatement, g++ -O3 no FMA — reference binary unbuildable here" % (nf, tw)}
     print(json.dumps(line))

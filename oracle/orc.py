@@ -163,7 +163,7 @@ class CoarseTracker:
 
 # ------------------------------------------------------------------------------------------------ back-end window
 def reproject_map(w, h, levels, K4, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, cur_ab, pts, cur_kf_index=-1, only_host=-1, backup=False,
-                  cell_order=None, max_matches=1200):
+                  cell_order=None, max_matches=400):
     """Reprojector::reprojectMap / backprojectMap restated (orc_reproject.cpp).  pts: structured array with u, v, idepth, host, type.
     Returns (pt_index[n], px[n,2]) in cell visiting order."""
     L = lib()
@@ -181,7 +181,7 @@ def reproject_map(w, h, levels, K4, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, 
 
 
 def track_new_coarse(tracker, new_frame, K4, kf_frames, kf_T7, kf_ab, map_pts, sprelast_c2w, slast_c2w, lastF_c2w, aff_last, poses_valid, lastCoarseRMSE,
-                     cell_order=None, max_matches=1200):
+                     cell_order=None, max_matches=400):
     """FullSystem::trackNewCoarse restated for a running system (FullSystem.cpp:283-500, branch :334-395) over the oracle pieces:
     hypotheses :346-388, re-track loop :410-462, fallback :464-470, pose composition :474-479, reprojectMap + structPoseEstimation :481-491.
     `tracker` is an orc.CoarseTracker whose reference is lastF.  Pure-Python control flow (<= 31 tries), all numerics in liborc."""

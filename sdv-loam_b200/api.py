@@ -241,7 +241,7 @@ class sdv_track_new_coarse_io(C.Structure):
                 ("refine_accepts", C.c_int32)]
 
 
-def trackNewCoarseBatch(ctx, jobs, cell_order=None, max_matches=1200):
+def trackNewCoarseBatch(ctx, jobs, cell_order=None, max_matches=400):
     """FullSystem::trackNewCoarse (FullSystem.cpp:283-500) for n sequences.  jobs: dicts with slot, frame, sprelast_c2w, slast_c2w, lastF_c2w, aff_last,
     poses_valid, lastCoarseRMSE.  Returns one dict per job with the fields of sdv_track_new_coarse_io."""
     LIB.sdv_track_new_coarse_batch.argtypes = [_vp, C.c_int, C.POINTER(sdv_track_new_coarse_io), _vp, C.c_int]
@@ -273,7 +273,7 @@ class Reprojector:
         hab = np.zeros((len(hT), 2)) if host_ab is None else np.ascontiguousarray(host_ab, np.float64).reshape(-1, 2)
         self.ctx._ck(LIB.sdv_map_set(self.ctx.p, slot, len(hT), np.ascontiguousarray(host_frame_ids, np.uint64), hT, hab, len(pts), pts.ctypes.data if len(pts) else None))
 
-    def reprojectMapBatch(self, slots, cur_frame_ids, cur_T7, cur_ab=None, cur_kf_index=None, only_host=None, backup=None, cell_order=None, max_matches=1200):
+    def reprojectMapBatch(self, slots, cur_frame_ids, cur_T7, cur_ab=None, cur_kf_index=None, only_host=None, backup=None, cell_order=None, max_matches=400):
         n = len(slots); i32 = lambda a, d: np.full(n, d, np.int32) if a is None else np.ascontiguousarray(a, np.int32)
         T = np.ascontiguousarray(cur_T7, np.float64).reshape(n, 7); ab = np.zeros((n, 2)) if cur_ab is None else np.ascontiguousarray(cur_ab, np.float64).reshape(n, 2)
         n_out = np.zeros(n, np.int32); out_pt = np.zeros((n, self.n_cells), np.int32); out_px = np.zeros((n, self.n_cells, 2))
@@ -282,7 +282,7 @@ class Reprojector:
                                                  i32(cur_kf_index, -1), i32(only_host, -1), i32(backup, 0), None if co is None else co.ctypes.data, max_matches, n_out, out_pt, out_px))
         return [(out_pt[k, :n_out[k]].copy(), out_px[k, :n_out[k]].copy()) for k in range(n)]
 
-    def refineBatch(self, slots, cur_frame_ids, curToWorld7, cur_ab=None, cell_order=None, max_matches=1200):
+    def refineBatch(self, slots, cur_frame_ids, curToWorld7, cur_ab=None, cell_order=None, max_matches=400):
         """Tail of FullSystem::trackNewCoarse (FullSystem.cpp:482-488) for n frames: reprojectMap -> structPoseEstimation, device resident."""
         n = len(slots); T = np.ascontiguousarray(curToWorld7, np.float64).reshape(n, 7).copy()
         ab = np.zeros((n, 2)) if cur_ab is None else np.ascontiguousarray(cur_ab, np.float64).reshape(n, 2)
