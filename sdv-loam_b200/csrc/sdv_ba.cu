@@ -171,7 +171,7 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
   b->nP = nP; b->nR = nR;
   b->hdr_host->nP = nP; b->hdr_host->nR = nR;
   CK(cudaMemcpyAsync(&b->hdr->nP, &b->hdr_host->nP, 2*sizeof(int), cudaMemcpyHostToDevice, st));
-  if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
   { WIN1(); launch_ba_setup(wins, 1, maxP, st); launch_ba_reset_oob(wins, 1, maxR, st); }
   CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   c->launches += 3;
@@ -230,7 +230,7 @@ int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOpt
     CK(cudaMemcpyAsync(&bs[i]->hdr->mnumOptIts, &bs[i]->hdr_host->mnumOptIts, sizeof(int), cudaMemcpyHostToDevice, st));
   }
   const BAWinDev* wins; int maxP, maxR; { int rcw = ba_wins(c, n, bs.data(), &wins, &maxP, &maxR); if (rcw) return rcw; }
-  if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
+  { int rcj = join_ingest(c); if (rcj) return rcj; }
   CK(cudaEventRecord(c->ev0, st));
   launch_ba_reset_oob(wins, n, maxR, st);
   launch_ba_linearize(wins, n, maxR, 0, GATE_ALWAYS, st);

@@ -59,9 +59,10 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   c->set = s; c->device = device; c->w = w; c->h = h; c->levels = levels;
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_cp, cudaStreamNonBlocking));
+  for (int i=0;i<sdv_ctx::kIngRing;i++) CK(cudaEventCreateWithFlags(&c->ev_ing[i], cudaEventDisableTiming)); for (int i=0;i<2;i++) CK(cudaEventCreateWithFlags(&c->ev_cp[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming)); c->ingest_pending = false; c->launches = 0;
-  c->pyr_batch_dev = nullptr; c->pyr_batch_host = nullptr;
+  for (int i=0;i<2;i++) { c->pyr_batch_dev[i] = nullptr; c->pyr_batch_host[i] = nullptr; }
   CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
   memset(&c->tc, 0, sizeof(c->tc));
   c->tc.levels = levels; c->tc.huberTH = s.huberTH; c->tc.coarseCutoffTH = s.coarseCutoffTH;
@@ -74,7 +75,7 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   c->frame_texels = texels;
   c->frames.resize(s.max_frames);
   for (auto& f : c->frames) {
-    f.used = false; f.adopted = false; f.lvl0_slot = -1; f.base = nullptr;
+    f.used = false; f.adopted = false; f.lvl0_slot = -1; f.base = nullptr; f.ingest_seq = 0;
     CK(cudaMalloc(&f.I0_own, (size_t)w*h*sizeof(float))); f.I0 = f.I0_own;
     if (texels) CK(cudaMalloc(&f.base, texels*sizeof(float4)));
     f.lvl[0] = nullptr; for (int l=1;l<levels;l++) f.lvl[l] = f.base + c->lvl_off[l];
@@ -113,16 +114,17 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
 
 void sdv_destroy(sdv_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device); cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st);
+  cudaSetDevice(c->device); cudaStreamSynchronize(c->st_cp); cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st);
   for (auto& f : c->frames) { cudaFree(f.base); cudaFree(f.I0_own); }
   for (auto p : c->lvl0_pool) cudaFree(p);
   for (auto& t : c->slots) for (int l=0;l<c->levels;l++) cudaFree(t.pts[l]);
   for (int l=0;l<c->levels;l++) { cudaFree(c->cd_id[l]); cudaFree(c->cd_ws[l]); cudaFree(c->cd_id2[l]); cudaFree(c->cd_ws2[l]); }
   cudaFree(c->cd_owner); cudaFree(c->cd_counts); cudaFree(c->cd_scalars); cudaFreeHost(c->cd_scalars_host);
   cudaFree(c->cd_pts4); cudaFree(c->cd_round); cudaFree(c->cd_splats); cudaFree(c->cd_done);
-  cudaFree(c->pyr_batch_dev); cudaFreeHost(c->pyr_batch_host); cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
+  for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]); } cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
-  for (auto p : c->stage) cudaFree(p);
+  for (int i=0;i<2;i++) for (auto p : c->stage[i]) cudaFree(p);
+  for (int i=0;i<sdv_ctx::kIngRing;i++) cudaEventDestroy(c->ev_ing[i]); for (int i=0;i<2;i++) cudaEventDestroy(c->ev_cp[i]); cudaStreamDestroy(c->st_cp);
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);
   ba_destroy(c);
@@ -130,7 +132,7 @@ void sdv_destroy(sdv_ctx* c) {
   delete c;
 }
 
-int sdv_sync(sdv_ctx* c) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st_in)); CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
+int sdv_sync(sdv_ctx* c) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st_cp)); CK(cudaStreamSynchronize(c->st_in)); CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
 long long sdv_launch_count(sdv_ctx* c) { return c ? c->launches : 0; }
 int sdv_track_job_bytes(void) { return (int)sizeof(TrackJob); }
 float sdv_last_kernel_ms(sdv_ctx* c) { return c ? c->last_ms : 0.f; }
@@ -138,12 +140,14 @@ float sdv_last_kernel_ms(sdv_ctx* c) { return c ? c->last_ms : 0.f; }
 // ------------------------------------------------------------------------------------------------ frames
 static FrameDev* find_frame(sdv_ctx* c, uint64_t id) { auto it = c->frame_index.find(id); return it == c->frame_index.end() ? nullptr : &c->frames[it->second]; }
 
-static int ensure_stage(sdv_ctx* c, int n) {
+static int ensure_stage(sdv_ctx* c, int n, int par) {
   size_t fl = (size_t)c->w*c->h + pyramid_scratch_floats(c->w, c->h, c->levels);
-  while ((int)c->stage.size() < n) { float* p = nullptr; CK(cudaMalloc(&p, fl*sizeof(float))); c->stage.push_back(p); }
+  while ((int)c->stage[par].size() < n) { float* p = nullptr; CK(cudaMalloc(&p, fl*sizeof(float))); c->stage[par].push_back(p); }
   if (n > c->stage_cap) {
-    cudaFree(c->pyr_batch_dev); cudaFreeHost(c->pyr_batch_host); c->stage_cap = n;
-    CK(cudaMalloc(&c->pyr_batch_dev, (size_t)n*sizeof(PyrBatchHost))); CK(cudaMallocHost(&c->pyr_batch_host, (size_t)n*sizeof(PyrBatchHost)));
+    CK(cudaStreamSynchronize(c->st_in));
+    for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]);
+      CK(cudaMalloc(&c->pyr_batch_dev[i], (size_t)n*sizeof(PyrBatchHost))); CK(cudaMallocHost(&c->pyr_batch_host[i], (size_t)n*sizeof(PyrBatchHost))); }
+    c->stage_cap = n;
   }
   return SDV_OK;
 }
@@ -158,12 +162,16 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
   if (!c || n < 0 || !frames || !imgs) return SDV_ERR_ARG;
   if (n == 0) return SDV_OK;
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->st_in));            // previous ingest (descriptor + staging buffers are reused) must have drained
-  int rc = ensure_stage(c, n); if (rc) return rc;
+  const long long seq = c->ingest_seq + 1; const int par = (int)(seq & 1);
+  // staging buffers + descriptors of this parity were last used by ingest seq-2: it must have drained before the host rewrites the pinned
+  // descriptors (the device-side order copy(seq) after pyramid(seq-2) is enforced on the copy stream below)
+  if (seq > 2) CK(cudaEventSynchronize(c->ev_ing[(seq-2) % sdv_ctx::kIngRing]));
+  int rc = ensure_stage(c, n, par); if (rc) return rc;
   const bool u8 = (kind & 1), dev = (kind & 2), adopt = (kind & 4) && dev && !u8;
   c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
   const size_t px = (size_t)c->w*c->h;
   if (c->levels > 1 && ((c->w | c->h) & 1)) return ctx_fail(c, SDV_ERR_ARG, "pyramid needs even image sizes");
+  PyrBatchHost* desc = c->pyr_batch_host[par];
   for (int k=0;k<n;k++) {
     int idx = -1;
     auto it = c->frame_index.find(frames[k]);
@@ -171,38 +179,44 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
     else { for (size_t i=0;i<c->frames.size();i++) if (!c->frames[i].used) { idx = (int)i; break; } }
     if (idx < 0) return ctx_fail(c, SDV_ERR_CAPACITY, "frame pool exhausted (max_frames=%d)", (int)c->frames.size());
     FrameDev& f = c->frames[idx]; f.used = true; f.id = frames[k]; f.exposure = exposures ? exposures[k] : 1.0f; c->frame_index[frames[k]] = idx;
-    frame_drop_lvl0(c, f);
+    frame_drop_lvl0(c, f); f.ingest_seq = seq;
     f.adopted = adopt; f.I0 = adopt ? const_cast<float*>(reinterpret_cast<const float*>(imgs[k])) : f.I0_own;
-    PyrBatchHost& b = c->pyr_batch_host[k];
-    b.scratch = c->stage[k] + px; b.out = f.base; b.I0 = f.I0;
+    PyrBatchHost& b = desc[k];
+    b.scratch = c->stage[par][k] + px; b.out = f.base; b.I0 = f.I0;
     if (dev) b.src = imgs[k];
-    else if (u8) { b.src = c->stage[k]; c->cp_dst.push_back(c->stage[k]); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px); }
+    else if (u8) { b.src = c->stage[par][k]; c->cp_dst.push_back(c->stage[par][k]); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px); }
     else { b.src = f.I0; c->cp_dst.push_back(f.I0); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px*sizeof(float)); }
   }
-  if (!c->cp_dst.empty()) {                                               // all H2D copies of the batch in ONE runtime call (per-copy launch cost dominates otherwise)
+  if (!c->cp_dst.empty()) {                                               // all H2D copies of the batch in ONE runtime call, on the copy stream: PCIe stays busy while the
+    if (seq > 2) CK(cudaStreamWaitEvent(c->st_cp, c->ev_ing[(seq-2) % sdv_ctx::kIngRing], 0));   // previous batch's pyramid runs on st_in
     bool done = false;
     if (c->cp_dst.size() > 1 && !c->no_batch_copy) {
       cudaMemcpyAttributes at; memset(&at, 0, sizeof(at)); at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
       size_t aidx = 0, fail = 0;
-      cudaError_t e = cudaMemcpyBatchAsync(c->cp_dst.data(), c->cp_src.data(), c->cp_sz.data(), c->cp_dst.size(), &at, &aidx, 1, &fail, c->st_in);
+      cudaError_t e = cudaMemcpyBatchAsync(c->cp_dst.data(), c->cp_src.data(), c->cp_sz.data(), c->cp_dst.size(), &at, &aidx, 1, &fail, c->st_cp);
       if (e == cudaSuccess) done = true; else { cudaGetLastError(); c->no_batch_copy = true; }
     }
-    if (!done) for (size_t i=0;i<c->cp_dst.size();i++) CK(cudaMemcpyAsync(c->cp_dst[i], c->cp_src[i], c->cp_sz[i], cudaMemcpyHostToDevice, c->st_in));
+    if (!done) for (size_t i=0;i<c->cp_dst.size();i++) CK(cudaMemcpyAsync(c->cp_dst[i], c->cp_src[i], c->cp_sz[i], cudaMemcpyHostToDevice, c->st_cp));
     c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
+    CK(cudaEventRecord(c->ev_cp[par], c->st_cp)); CK(cudaStreamWaitEvent(c->st_in, c->ev_cp[par], 0));
   }
-  CK(cudaMemcpyAsync(c->pyr_batch_dev, c->pyr_batch_host, (size_t)n*sizeof(PyrBatchHost), cudaMemcpyHostToDevice, c->st_in));
-  if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev, n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in); c->launches += 2*(c->levels - 1); }
-  else if (u8 || (dev && !adopt)) { launch_pyramid_copy0(c->pyr_batch_dev, n, u8, c->w, c->h, c->st_in); c->launches += 1; }
+  CK(cudaMemcpyAsync(c->pyr_batch_dev[par], desc, (size_t)n*sizeof(PyrBatchHost), cudaMemcpyHostToDevice, c->st_in));
+  if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev[par], n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in); c->launches += 2*(c->levels - 1); }
+  else if (u8 || (dev && !adopt)) { launch_pyramid_copy0(c->pyr_batch_dev[par], n, u8, c->w, c->h, c->st_in); c->launches += 1; }
   CK(cudaGetLastError());
-  CK(cudaEventRecord(c->ev_in, c->st_in)); c->ingest_pending = true;
+  CK(cudaEventRecord(c->ev_ing[seq % sdv_ctx::kIngRing], c->st_in)); c->ingest_seq = seq; c->ingest_pending = true;
   return SDV_OK;
 }
 }  // extern "C"
 namespace sdv {
-int join_ingest(sdv_ctx* c) {                     // make the compute stream see every upload enqueued so far
-  if (c->ingest_pending) { CK(cudaStreamWaitEvent(c->st, c->ev_in, 0)); c->ingest_pending = false; }
+int join_ingest_upto(sdv_ctx* c, long long seq) {  // the compute stream waits for ingest calls <= seq (st_in is in order, so one event covers all earlier ones)
+  if (seq > c->ingest_seq) seq = c->ingest_seq;
+  if (seq <= c->seq_waited) return SDV_OK;
+  if (seq > c->ingest_seq - sdv_ctx::kIngRing) CK(cudaStreamWaitEvent(c->st, c->ev_ing[seq % sdv_ctx::kIngRing], 0));   // older ones have drained (frame_ingest syncs on seq-2)
+  c->seq_waited = seq;
   return SDV_OK;
 }
+int join_ingest(sdv_ctx* c) { c->ingest_pending = false; return join_ingest_upto(c, c->ingest_seq); }
 int ensure_lvl0(sdv_ctx* c, FrameDev& f) {        // FrameHessian::dI of a keyframe: packed level-0 texels, built once on demand
   if (f.lvl[0]) return SDV_OK;
   if (c->lvl0_free.empty()) return ctx_fail(c, SDV_ERR_CAPACITY, "keyframe level-0 image pool exhausted (max_kf_images=%d)", (int)c->lvl0_pool.size());
@@ -364,10 +378,12 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
     cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host); c->jobs_cap = n;
     CK(cudaMalloc(&c->jobs_dev, (size_t)n*sizeof(TrackJob))); CK(cudaMallocHost(&c->jobs_host, (size_t)n*sizeof(TrackJob)));
   }
+  long long need_seq = 0;
   for (int k=0;k<n;k++) {
     if (slots[k] < 0 || slots[k] >= (int)c->slots.size()) return SDV_ERR_ARG;
     TrackerSlot& t = c->slots[slots[k]];
     FrameDev* f = find_frame(c, new_frames[k]); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown new frame (job %d)", k);
+    if (f->ingest_seq > need_seq) need_seq = f->ingest_seq;
     if (t.ref_frame == ~0ull) return ctx_fail(c, SDV_ERR_STATE, "tracker slot %d has no reference", slots[k]);
     TrackJob& J = c->jobs_host[k]; memset(&J, 0, sizeof(J));
     J.img0 = f->I0;
@@ -378,7 +394,7 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
     for (int i=0;i<5;i++) J.minRes[i] = minRes ? minRes[5*k+i] : nan("");
     J.coarsest = coarsest;
   }
-  { int rcj = join_ingest(c); if (rcj) return rcj; }
+  { int rcj = join_ingest_upto(c, need_seq); if (rcj) return rcj; }     // only the uploads that built THESE frames: batch k+1's upload keeps streaming
   c->launches += 1;
   CK(cudaMemcpyAsync(c->jobs_dev, c->jobs_host, (size_t)n*sizeof(TrackJob), cudaMemcpyHostToDevice, c->st));
   CK(cudaEventRecord(c->ev0, c->st));

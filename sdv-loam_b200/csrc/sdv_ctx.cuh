@@ -12,6 +12,7 @@ struct FrameDev {                         // one FrameHessian's images on the de
   float* I0; float* I0_own; bool adopted;  // level-0 intensity plane (own storage, or an adopted caller buffer)
   float4* base; float4* lvl[kLevels];     // packed {I,dx,dy,|grad|^2} texels of levels >= 1 (lvl[0] = lazily built level-0 texels or nullptr)
   int lvl0_slot;                          // index into the keyframe level-0 texel pool, -1 if not built
+  long long ingest_seq;                   // ingest call that (re)built this frame's pyramid
 };
 
 struct TrackerSlot {                      // one CoarseTracker instance (reference keeps two: FullSystem.h coarseTracker / coarseTracker_forNewKF)
@@ -26,12 +27,14 @@ struct RpState;                           // sdv_reproject.cu
 } // namespace sdv
 
 struct sdv_ctx {
-  int device; cudaStream_t st, st_in; cudaEvent_t ev0, ev1, ev_in; bool ingest_pending; long long launches;
+  int device; cudaStream_t st, st_in, st_cp; cudaEvent_t ev0, ev1, ev_in; bool ingest_pending; long long launches;
+  // ingest pipeline: H2D copies on st_cp, pyramids on st_in, one completion event per ingest call (ring); a frame remembers the ingest that built it
+  static constexpr int kIngRing = 8; cudaEvent_t ev_ing[kIngRing], ev_cp[2]; long long ingest_seq = 0, seq_waited = 0;
   int w, h, levels; sdv_settings set;
   sdv::TrackConst tc; sdv::TrackConst* tc_dev;
   size_t lvl_off[sdv::kLevels]; size_t frame_texels;
   std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
-  std::vector<float*> stage; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev; sdv::PyrBatchHost* pyr_batch_host;
+  std::vector<float*> stage[2]; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev[2]; sdv::PyrBatchHost* pyr_batch_host[2];     // double-buffered by ingest parity
   std::vector<float4*> lvl0_pool; std::vector<int> lvl0_free;
   std::vector<void*> cp_dst, cp_src; std::vector<size_t> cp_sz; bool no_batch_copy = false;
   std::vector<sdv::TrackerSlot> slots;
@@ -53,5 +56,6 @@ void rp_destroy(sdv_ctx* c);
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
 void ba_destroy(sdv_ctx* c);
 int  ensure_lvl0(sdv_ctx* c, FrameDev& f);     // build the packed level-0 texels of a frame on demand (keyframes / read-back)
-int  join_ingest(sdv_ctx* c);
+int  join_ingest(sdv_ctx* c);                  // compute stream waits for every ingest enqueued so far
+int  join_ingest_upto(sdv_ctx* c, long long seq);   // ... for ingest calls <= seq only (frames carry their ingest_seq)
 }

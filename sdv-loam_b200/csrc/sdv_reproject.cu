@@ -273,7 +273,7 @@ using namespace sdv;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return ctx_fail(c, SDV_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 
 namespace sdv {
-struct MapSlot { MapDev host_copy; MapDev* dev = nullptr; sdv_map_pt* pts = nullptr; int cap = 0; int nH = 0, nP = 0; uint64_t host_ids[kRpMaxHosts]; double host_ab[kRpMaxHosts][2]; float host_exposure[kRpMaxHosts]; bool set = false; };
+struct MapSlot { long long ingest_seq = 0; MapDev host_copy; MapDev* dev = nullptr; sdv_map_pt* pts = nullptr; int cap = 0; int nH = 0, nP = 0; uint64_t host_ids[kRpMaxHosts]; double host_ab[kRpMaxHosts][2]; float host_exposure[kRpMaxHosts]; bool set = false; };
 struct RpState { std::vector<MapSlot> maps; void* dev = nullptr; void* host = nullptr; size_t cap = 0, host_cap = 0; RpConst C; bool c_ready = false; };
 static RpState* rp_state(sdv_ctx* c) { if (!c->rp) { c->rp = new RpState(); c->rp->maps.resize(c->slots.size()); } return c->rp; }
 void rp_destroy(sdv_ctx* c) { if (!c->rp) return; for (auto& m : c->rp->maps) { cudaFree(m.dev); cudaFree(m.pts); } cudaFree(c->rp->dev); cudaFreeHost(c->rp->host); delete c->rp; c->rp = nullptr; }
@@ -305,9 +305,9 @@ int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const
   if (!m.dev) CK(cudaMalloc(&m.dev, sizeof(MapDev)));
   if (nP > m.cap) { cudaFree(m.pts); m.pts = nullptr; m.cap = nP + nP/4 + 256; CK(cudaMalloc(&m.pts, (size_t)m.cap*sizeof(sdv_map_pt))); }
   { int rcj = join_ingest(c); if (rcj) return rcj; }
-  MapDev& h = m.host_copy; memset(&h, 0, sizeof(h)); h.nH = nH; h.nP = nP; h.pts = m.pts;
+  MapDev& h = m.host_copy; memset(&h, 0, sizeof(h)); h.nH = nH; h.nP = nP; h.pts = m.pts; m.ingest_seq = 0;
   for (int k=0;k<nH;k++) { auto it = c->frame_index.find(host_frames[k]); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "map_set: unknown keyframe handle (host %d)", k);
-    const FrameDev& f = c->frames[it->second]; h.hostI0[k] = f.I0; m.host_exposure[k] = f.exposure; m.host_ids[k] = host_frames[k];
+    const FrameDev& f = c->frames[it->second]; h.hostI0[k] = f.I0; m.host_exposure[k] = f.exposure; m.host_ids[k] = host_frames[k]; if (f.ingest_seq > m.ingest_seq) m.ingest_seq = f.ingest_seq;
     for (int i=0;i<7;i++) h.hostT[k][i] = host_T7[7*k+i]; m.host_ab[k][0] = host_ab ? host_ab[2*k] : 0.0; m.host_ab[k][1] = host_ab ? host_ab[2*k+1] : 0.0; }
   m.nH = nH; m.nP = nP; m.set = true;
   CK(cudaStreamSynchronize(c->st));                                            // a previous launch may still read the slot
@@ -338,7 +338,10 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
     CK(cudaMalloc(&st->dev, cap)); CK(cudaMallocHost(&st->host, hcap)); st->cap = cap; st->host_cap = hcap; }
   unsigned char* db = (unsigned char*)st->dev; unsigned char* hb = (unsigned char*)st->host;
   RpJob* J = (RpJob*)(hb + h_jobs); R.jobs_host = J; R.h_opt = (int32_t*)(hb + h_opt); R.h_opx = (double2*)(hb + h_opx); R.rj_host = (RefineJob*)(hb + h_rj); R.n_out_host = (int*)(hb + h_no);
-  { int rcj = join_ingest(c); if (rcj) return rcj; }
+  long long need_seq = 0;
+  for (int k=0;k<n_jobs;k++) { auto it = c->frame_index.find(cur_frames[k]); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "reproject job %d: unknown target frame", k);
+    need_seq = std::max(need_seq, std::max(c->frames[it->second].ingest_seq, st->maps[slots[k]].ingest_seq)); }
+  { int rcj = join_ingest_upto(c, need_seq); if (rcj) return rcj; }     // only the uploads these frames came from (a later batch may still be streaming in)
   long long off = 0;
   for (int k=0;k<n_jobs;k++) {
     const MapSlot& m = st->maps[slots[k]]; RpJob& j = J[k]; memset(&j, 0, sizeof(j));
