@@ -123,7 +123,7 @@ void sdv_destroy(sdv_ctx* c) {
   cudaFree(c->cd_pts4); cudaFree(c->cd_round); cudaFree(c->cd_splats); cudaFree(c->cd_done);
   for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]); } cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
-  for (int i=0;i<2;i++) for (auto p : c->stage[i]) cudaFree(p);
+  for (int i=0;i<2;i++) { for (auto p : c->stage[i]) cudaFree(p); cudaFree(c->stage_u8[i]); }
   for (int i=0;i<sdv_ctx::kIngRing;i++) cudaEventDestroy(c->ev_ing[i]); for (int i=0;i<2;i++) cudaEventDestroy(c->ev_cp[i]); cudaStreamDestroy(c->st_cp);
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);
@@ -168,6 +168,8 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
   if (seq > 2) CK(cudaEventSynchronize(c->ev_ing[(seq-2) % sdv_ctx::kIngRing]));
   int rc = ensure_stage(c, n, par); if (rc) return rc;
   const bool u8 = (kind & 1), dev = (kind & 2), adopt = (kind & 4) && dev && !u8;
+  if (u8 && !dev && (size_t)n*c->w*c->h > c->stage_u8_cap[par]) { CK(cudaStreamSynchronize(c->st_in)); cudaFree(c->stage_u8[par]); c->stage_u8[par] = nullptr;
+    c->stage_u8_cap[par] = (size_t)n*c->w*c->h; CK(cudaMalloc(&c->stage_u8[par], c->stage_u8_cap[par])); }
   c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
   const size_t px = (size_t)c->w*c->h;
   if (c->levels > 1 && ((c->w | c->h) & 1)) return ctx_fail(c, SDV_ERR_ARG, "pyramid needs even image sizes");
@@ -184,7 +186,9 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
     PyrBatchHost& b = desc[k];
     b.scratch = c->stage[par][k] + px; b.out = f.base; b.I0 = f.I0;
     if (dev) b.src = imgs[k];
-    else if (u8) { b.src = c->stage[par][k]; c->cp_dst.push_back(c->stage[par][k]); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px); }
+    else if (u8) { unsigned char* d8 = c->stage_u8[par] + (size_t)k*px; b.src = d8;
+      if (!c->cp_dst.empty() && (unsigned char*)c->cp_src.back() + c->cp_sz.back() == (const unsigned char*)imgs[k] && (unsigned char*)c->cp_dst.back() + c->cp_sz.back() == d8) c->cp_sz.back() += px;   // adjacent in host memory: one copy
+      else { c->cp_dst.push_back(d8); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px); } }
     else { b.src = f.I0; c->cp_dst.push_back(f.I0); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px*sizeof(float)); }
   }
   if (!c->cp_dst.empty()) {                                               // all H2D copies of the batch in ONE runtime call, on the copy stream: PCIe stays busy while the

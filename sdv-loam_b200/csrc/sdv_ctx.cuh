@@ -34,6 +34,7 @@ struct sdv_ctx {
   sdv::TrackConst tc; sdv::TrackConst* tc_dev;
   size_t lvl_off[sdv::kLevels]; size_t frame_texels;
   std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
+  unsigned char* stage_u8[2] = {nullptr, nullptr}; size_t stage_u8_cap[2] = {0, 0};   // contiguous mono8 staging per parity (adjacent host images coalesce into one copy)
   std::vector<float*> stage[2]; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev[2]; sdv::PyrBatchHost* pyr_batch_host[2];     // double-buffered by ingest parity
   std::vector<float4*> lvl0_pool; std::vector<int> lvl0_free;
   std::vector<void*> cp_dst, cp_src; std::vector<size_t> cp_sz; bool no_batch_copy = false;
