@@ -380,7 +380,7 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
   CK(cudaSetDevice(c->device));
   if (n > c->jobs_cap) {
     cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host); c->jobs_cap = n;
-    CK(cudaMalloc(&c->jobs_dev, (size_t)n*sizeof(TrackJob))); CK(cudaMallocHost(&c->jobs_host, (size_t)n*sizeof(TrackJob)));
+    CK(cudaMalloc(&c->jobs_dev, (size_t)n*sizeof(TrackJob) + 16)); CK(cudaMallocHost(&c->jobs_host, (size_t)n*sizeof(TrackJob) + 16));
   }
   long long need_seq = 0;
   for (int k=0;k<n;k++) {
@@ -399,8 +399,8 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
     J.coarsest = coarsest;
   }
   { int rcj = join_ingest_upto(c, need_seq); if (rcj) return rcj; }     // only the uploads that built THESE frames: batch k+1's upload keeps streaming
-  c->launches += 1;
-  CK(cudaMemcpyAsync(c->jobs_dev, c->jobs_host, (size_t)n*sizeof(TrackJob), cudaMemcpyHostToDevice, c->st));
+  c->launches += 2;                                                    // descriptor copy kernel + track_cluster_kernel
+  launch_h2d_words(c->jobs_dev, c->jobs_host, (size_t)n*sizeof(TrackJob), c->st);      // kernel copy: not queued behind the next batch's image upload
   CK(cudaEventRecord(c->ev0, c->st));
   CK(launch_track_cluster(c->jobs_dev, n, c->tc_dev, c->set.cluster_size, c->set.track_threads, c->st));
   CK(cudaEventRecord(c->ev1, c->st));

@@ -428,6 +428,15 @@ cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst
   return launch_track_t<128, SDV_TRACK_MINB>(jobs_dev, njobs, tc_dev, cluster_size, st);
 }
 
+__global__ void h2d_words_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x*blockDim.x) dst[i] = src[i];
+}
+void launch_h2d_words(void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st) {      // bytes is rounded up to 16: both buffers are allocated with slack
+  const size_t n16 = (bytes + 15)/16; if (!n16) return;
+  int blocks = (int)((n16 + 255)/256); if (blocks > 296) blocks = 296;
+  h2d_words_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(dst_dev), reinterpret_cast<const uint4*>(src_pinned), n16);
+}
+
 // ================================================================================================ makeCoarseDepthL0
 // (a) splat in POINT ORDER per pixel: round r adds, for every pixel, the not-yet-added point of lowest index, which
 //     reproduces the reference's sequential float `+=` order bit-for-bit even for colliding points (CoarseTracker.cpp:264-294).

@@ -18,6 +18,9 @@ void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const flo
                           double* partials, unsigned int* ticket, double* totals, cudaStream_t st);
 
 // device-resident trackNewestCoarse (CoarseTracker.cpp:662-838): njobs clusters of cluster_size CTAs
+// small host->device transfer done by a kernel reading pinned (UVA-mapped) host memory: it does not queue behind bulk cudaMemcpyAsync traffic on the
+// H2D copy engine, so a job-descriptor upload cannot be delayed by the next batch's image upload (measured: 9.8 -> see DESIGN.md §6)
+void launch_h2d_words(void* dst_dev, const void* src_pinned, size_t bytes, cudaStream_t st);
 cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, int threads, cudaStream_t st);
 
 // makeCoarseDepthL0 (CoarseTracker.cpp:258-425)

@@ -366,7 +366,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
   S.count = (int*)(db + o_count); S.begin = (int*)(db + o_begin); S.cursor = (int*)(db + o_cur); S.out_pt = (int*)(db + o_opt); S.out_px = (double2*)(db + o_opx);
   R.ov = (sdv_overlap_pt*)(db + o_ov); R.rj = (RefineJob*)(db + o_rj); R.n_out_dev = (int*)(db + o_no); R.cell_order_dev = (int*)(db + o_co);
   cudaStream_t s = c->st;
-  CK(cudaMemcpyAsync(db + o_jobs, J, (size_t)n_jobs*sizeof(RpJob), cudaMemcpyHostToDevice, s));
+  launch_h2d_words(db + o_jobs, J, (size_t)n_jobs*sizeof(RpJob), s);               // kernel copy (see launch_h2d_words)
   CK(cudaMemsetAsync(S.count, 0, (size_t)nc*4, s));
   CK(cudaEventRecord(c->ev0, s));
   RpJob* jd = (RpJob*)(db + o_jobs); R.jobs_dev = jd;
@@ -374,7 +374,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
   rp_scan_kernel<<<n_jobs, 1024, 0, s>>>(C, S);
   rp_scatter_kernel<<<dim3((maxP + 255)/256, n_jobs), 256, 0, s>>>(jd, C, S);
   rp_match_kernel<<<dim3((C.ncells + kRpWarps - 1)/kRpWarps, n_jobs), 32*kRpWarps, 0, s>>>(jd, C, S);
-  CK(cudaGetLastError()); c->launches += 4;
+  CK(cudaGetLastError()); c->launches += 5;
   return SDV_OK;
 }
 
