@@ -146,7 +146,7 @@ static int ensure_stage(sdv_ctx* c, int n, int par) {
   if (n > c->stage_cap) {
     CK(cudaStreamSynchronize(c->st_in));
     for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]);
-      CK(cudaMalloc(&c->pyr_batch_dev[i], (size_t)n*sizeof(PyrBatchHost))); CK(cudaMallocHost(&c->pyr_batch_host[i], (size_t)n*sizeof(PyrBatchHost))); }
+      CK(cudaMalloc(&c->pyr_batch_dev[i], (size_t)n*sizeof(PyrBatchHost) + 16)); CK(cudaMallocHost(&c->pyr_batch_host[i], (size_t)n*sizeof(PyrBatchHost) + 16)); }
     c->stage_cap = n;
   }
   return SDV_OK;
@@ -204,7 +204,8 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
     c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
     CK(cudaEventRecord(c->ev_cp[par], c->st_cp)); CK(cudaStreamWaitEvent(c->st_in, c->ev_cp[par], 0));
   }
-  CK(cudaMemcpyAsync(c->pyr_batch_dev[par], desc, (size_t)n*sizeof(PyrBatchHost), cudaMemcpyHostToDevice, c->st_in));
+  launch_h2d_words(c->pyr_batch_dev[par], desc, (size_t)n*sizeof(PyrBatchHost), c->st_in);   // kernel copy: a cudaMemcpyAsync here becomes ready only after this batch's bulk copy and
+  c->launches += 1;                                                                              // would queue behind the NEXT batch's bulk copy on the H2D engine
   if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev[par], n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in); c->launches += 2*(c->levels - 1); }
   else if (u8 || (dev && !adopt)) { launch_pyramid_copy0(c->pyr_batch_dev[par], n, u8, c->w, c->h, c->st_in); c->launches += 1; }
   CK(cudaGetLastError());
