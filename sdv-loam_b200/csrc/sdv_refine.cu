@@ -17,6 +17,7 @@
 #include <string.h>
 #include "sdv_ctx.cuh"
 #include "sdv_refine.cuh"
+#include "sdv_warp_solve.cuh"
 
 namespace sdv {
 
@@ -29,7 +30,8 @@ struct RefShared {
   float hostR[kRefMaxHosts][9], hostT[kRefMaxHosts][3];
   float R[9], t[3];
   float J[12][kRefChunk]; float r0[kRefChunk], r1[kRefChunk]; float wgt[kRefChunk]; int ok[kRefChunk];
-  double H[36], b[6];
+  double H[36], b[6]; double H0[36], b0[6];   // H0,b0: undamped system of the last calcHandb evaluation (restored instead of re-evaluating the same pose)
+  double inc[6];
   float energy; int num; int done;
 };
 
@@ -133,39 +135,59 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
   if (threadIdx.x == 0) s_resOld = S.energy / S.num;
   ref_hb(S, jb, pts, g, fxi, fyi);
   const float lambdaExtrapolationLimit = 0.001f;
+  // undamped copy of the system at the current pose: structPoseEstimation re-linearises at the pose BEFORE an accepted step (:989), i.e. for the
+  // first accepted step at the very pose the loop started from — identical values, so they are restored rather than recomputed
+  __shared__ int cur_id, hb_id;
+  if (threadIdx.x < 36) S.H0[threadIdx.x] = S.H[threadIdx.x]; if (threadIdx.x < 6) S.b0[threadIdx.x] = S.b[threadIdx.x];
+  if (threadIdx.x == 0) { cur_id = 0; hb_id = 0; }
+  __syncthreads();
   for (int iteration = 0; iteration < 10; iteration++) {
     __shared__ double s_incn;
-    if (threadIdx.x == 0) {
-      jb.iterations++;
-      float lambda = s_lambda;
-      for (int i=0;i<6;i++) S.H[i*6+i] *= (1 + lambda);
-      double nb[6], inc[6]; for (int i=0;i<6;i++) nb[i] = -S.b[i];
-      ldlt_solve<6>(6, S.H, 6, nb, inc);
+    if (threadIdx.x < 32) {                                              // warp 0: damp, solve (6x6 padded to the 8x8 warp LDLT), propose
+      const int r = threadIdx.x & 7; const float lambda = s_lambda;
+      if (threadIdx.x < 6) S.H[threadIdx.x*6+threadIdx.x] *= (1 + lambda);
+      __syncwarp();
+      double a[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] = (r < 6 && j < 6) ? S.H[r*6+j] : ((r == j) ? 1.0 : 0.0);
+      const double rhs = (r < 6) ? -S.b[r] : 0.0;
+      const double x = warp_ldlt_solve8(a, rhs);
       float extrapFac = 1;
       if (lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / lambda));
-      for (int i=0;i<6;i++) inc[i] *= extrapFac;
-      cand = se3_mul(se3_exp(inc), cur);
-      ref_set_pose(S, cand);
-      double n2 = 0; for (int i=0;i<6;i++) n2 += inc[i]*inc[i]; s_incn = sqrt(n2);
+      if (threadIdx.x < 6) S.inc[threadIdx.x] = x*extrapFac;
+      __syncwarp();
+      if (threadIdx.x == 0) {
+        jb.iterations++;
+        double inc[6]; for (int i=0;i<6;i++) inc[i] = S.inc[i];
+        cand = se3_mul(se3_exp(inc), cur);
+        ref_set_pose(S, cand);
+        double n2 = 0; for (int i=0;i<6;i++) n2 += inc[i]*inc[i]; s_incn = sqrt(n2);
+      }
     }
     __syncthreads();
     ref_energy(S, jb, pts, g, fxi, fyi);
-    __shared__ int s_accept;
+    __shared__ int s_accept, s_recompute;
     if (threadIdx.x == 0) {
       float resNew = (S.num == 0) ? 1000000.0f : S.energy / S.num;
-      s_accept = (resNew < s_resOld);
-      if (s_accept) { s_resOld = resNew; jb.accepts++; ref_set_pose(S, cur); }
+      s_accept = (resNew < s_resOld); s_recompute = 0;
+      if (s_accept) { s_resOld = resNew; jb.accepts++; s_recompute = (hb_id != cur_id); if (s_recompute) ref_set_pose(S, cur); }
     }
     __syncthreads();
     if (s_accept) {
-      if (threadIdx.x < 36) S.H[threadIdx.x] = 0.0; if (threadIdx.x < 6) S.b[threadIdx.x] = 0.0;
-      __syncthreads();
-      ref_hb(S, jb, pts, g, fxi, fyi);                                   // (sic) at the pose before the accepted step
-      if (threadIdx.x == 0) { cur = cand; SE3d c2w = se3_inv(cand); se3_to7(c2w, jb.T); s_lambda *= 0.5f; }
+      if (s_recompute) {
+        if (threadIdx.x < 36) S.H[threadIdx.x] = 0.0; if (threadIdx.x < 6) S.b[threadIdx.x] = 0.0;
+        __syncthreads();
+        ref_hb(S, jb, pts, g, fxi, fyi);                                 // (sic) at the pose before the accepted step
+        if (threadIdx.x < 36) S.H0[threadIdx.x] = S.H[threadIdx.x]; if (threadIdx.x < 6) S.b0[threadIdx.x] = S.b[threadIdx.x];
+        if (threadIdx.x == 0) hb_id = cur_id;
+      } else {
+        if (threadIdx.x < 36) S.H[threadIdx.x] = S.H0[threadIdx.x]; if (threadIdx.x < 6) S.b[threadIdx.x] = S.b0[threadIdx.x];
+      }
+      if (threadIdx.x == 0) { cur = cand; cur_id++; SE3d c2w = se3_inv(cand); se3_to7(c2w, jb.T); s_lambda *= 0.5f; }
     } else if (threadIdx.x == 0) { float l = s_lambda*4; if (l < lambdaExtrapolationLimit) l = lambdaExtrapolationLimit; s_lambda = l; }
     __syncthreads();
     const bool small = !(s_incn > 1e-5);
-    __syncthreads();                                                     // s_incn is rewritten by thread 0 at the top of the next iteration
+    __syncthreads();                                                     // s_incn is rewritten by warp 0 at the top of the next iteration
     if (small) break;
   }
   if (threadIdx.x == 0) { jb.res = s_resOld; jb.num = S.num; }

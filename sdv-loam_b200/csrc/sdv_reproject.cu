@@ -33,7 +33,8 @@ struct RpJob {
   int cur_kf_index, backup, nH, nP; long long pt_off; int error;
 };
 struct RpConst { double K[9], Ki[9]; int w[kLevels], h[kLevels]; int levels, ncols, ncells; };
-struct RpScratch { double2* cand_px; float* cand_key; int* cand_cell; int* list; int* count; int* begin; int* cursor; int* out_pt; double2* out_px; };
+struct RpScratch { double2* cand_px; float* cand_key; int* cand_cell; int* list; int* count; int* begin; int* cursor; int* out_pt; double2* out_px;
+                   double* xf; };   // xf[job][host][14]: camToWorld_host^-1 and T_cur_ref = camToWorld_cur^-1 * camToWorld_host (7 doubles each), built by rp_project_kernel
 
 __device__ __forceinline__ void mv3(const double* M, double x, double y, double z, double* o) {
   o[0] = (M[0]*x + M[1]*y) + M[2]*z; o[1] = (M[3]*x + M[4]*y) + M[5]*z; o[2] = (M[6]*x + M[7]*y) + M[8]*z;
@@ -63,6 +64,10 @@ __device__ __forceinline__ float grad_g(float d) { return isfinite(d) ? d : 0.0f
 
 __global__ void __launch_bounds__(256) rp_project_kernel(RpJob* __restrict__ jobs, RpConst C, RpScratch S) {
   RpJob& jb = jobs[blockIdx.y]; const MapDev* __restrict__ m = jb.map;
+  if (blockIdx.x == 0 && threadIdx.x < jb.nH) {                              // per (frame, keyframe) transforms used by every findMatchDirect attempt (:262)
+    const SE3d refPose = se3_from7(m->hostT[threadIdx.x]); double* o = S.xf + ((size_t)blockIdx.y*kRpMaxHosts + threadIdx.x)*14;
+    se3_to7(se3_inv(refPose), o); se3_to7(se3_mul(se3_from7(jb.curTinv), refPose), o + 7);
+  }
   const int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= jb.nP) return;
   const long long gi = jb.pt_off + i; S.cand_cell[gi] = -1;
   const sdv_map_pt p = m->pts[i];
@@ -98,19 +103,29 @@ __global__ void __launch_bounds__(256) rp_scatter_kernel(const RpJob* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------------- findMatchDirect (one warp)
-struct RpWarpSmem { float pwb[100]; float a0[64], a1[64], a2[64]; float jx[64], jy[64]; };
+struct __align__(16) RpWarpSmem { float a0[64], a1[64], a2[64]; float jx[64], jy[64]; float pwb[100]; };
+// J = ((0 - a[0]) - a[1]) - ... - a[63]: the host loop's order, 16 vector loads feeding one dependent FADD chain
+__device__ __forceinline__ float chain_sub64(const float* a) {
+  const float4* a4 = reinterpret_cast<const float4*>(a); float J = 0;
+#pragma unroll
+  for (int q = 0; q < 16; q++) { const float4 t = a4[q]; J -= t.x; J -= t.y; J -= t.z; J -= t.w; }
+  return J;
+}
 constexpr int kRpWarps = 4;
+#ifndef RP_MATCH_MINB
+#define RP_MATCH_MINB 6
+#endif
 
 __device__ __forceinline__ float cur_pixel(const RpJob& jb, int level, int idx) { return level == 0 ? __ldg(jb.curI0 + idx) : __ldg(&jb.curLvl[level][idx]).x; }
 
-__device__ bool find_match_direct(const RpJob& jb, const RpConst& C, const sdv_map_pt& pt, double2& px_io, RpWarpSmem& sm, const int lane) {
+__device__ bool find_match_direct(const RpJob& jb, const RpConst& C, const sdv_map_pt& pt, double2& px_io, RpWarpSmem& sm, const int lane, const double* __restrict__ xf) {
   const MapDev* __restrict__ m = jb.map;
   int ref;
   if (jb.nH <= 2) { if (!jb.backup) ref = 0; else if (jb.cur_kf_index == 0) ref = 1; else if (jb.cur_kf_index == 1) ref = 0; else return false; }
   else ref = pt.host;
   const float aLL0 = jb.affLL[ref][0], aLL1 = jb.affLL[ref][1];
   double pw[3]; point_world(C, m, pt, pw);
-  const SE3d refPose = se3_from7(m->hostT[ref]); const SE3d refInv = se3_inv(refPose);
+  const SE3d refInv = se3_from7(xf + ref*14);
   double ptRef[3]; xform(refInv, pw, ptRef);
   double cR[3] = {ptRef[0], ptRef[1], ptRef[2]}, px[2]; pixel_from_cam(C, cR, px);
   if (!in_frame(C, px[0], px[1], 4+2)) return false;
@@ -119,7 +134,7 @@ __device__ bool find_match_direct(const RpJob& jb, const RpConst& C, const sdv_m
   { const int hp = 5; double du[3], dv[3]; mv3(C.Ki, px[0]+hp, px[1]+0, 1.0, du); mv3(C.Ki, px[0]+0, px[1]+hp, 1.0, dv);
     const double su = ptRef[2]/du[2], sv = ptRef[2]/dv[2];
     for (int i=0;i<3;i++) { du[i] *= su; dv[i] *= sv; }
-    const SE3d Tcr = se3_mul(se3_from7(jb.curTinv), refPose);
+    const SE3d Tcr = se3_from7(xf + ref*14 + 7);
     double c0[3], c1[3], c2[3], pc[2], pu[2], pv[2];
     xform(Tcr, ptRef, c0); pixel_from_cam(C, c0, pc); xform(Tcr, du, c1); pixel_from_cam(C, c1, pu); xform(Tcr, dv, c2); pixel_from_cam(C, c2, pv);
     A[0] = (pu[0]-pc[0])/hp; A[2] = (pu[1]-pc[1])/hp; A[1] = (pv[0]-pc[0])/hp; A[3] = (pv[1]-pc[1])/hp; }
@@ -178,8 +193,7 @@ __device__ bool find_match_direct(const RpJob& jb, const RpConst& C, const sdv_m
         sm.a0[q0] = r0*jv0; sm.a0[q1] = r1*jv1; sm.a2[q0] = r0; sm.a2[q1] = r1; }
       __syncwarp();
       float J = 0;
-      if (lane == 0) { for (int q = 0; q < 64; q++) J -= sm.a0[q]; }
-      if (lane == 1) { for (int q = 0; q < 64; q++) J -= sm.a2[q]; }
+      if (lane < 2) J = chain_sub64(lane == 0 ? sm.a0 : sm.a2);
       const float Jres0 = __shfl_sync(0xffffffffu, J, 0), Jres1 = __shfl_sync(0xffffffffu, J, 1);
       const float up0 = Hi00*Jres0 + Hi01*Jres1, up1 = Hi10*Jres0 + Hi11*Jres1;
       u += up0*dir0; v += up0*dir1; mean_diff += up1;
@@ -207,7 +221,7 @@ __device__ bool find_match_direct(const RpJob& jb, const RpConst& C, const sdv_m
         sm.a0[q0] = r0*dx0; sm.a0[q1] = r1*dx1; sm.a1[q0] = r0*dy0; sm.a1[q1] = r1*dy1; sm.a2[q0] = r0; sm.a2[q1] = r1; }
       __syncwarp();
       float J = 0;
-      if (lane < 3) { const float* a = lane == 0 ? sm.a0 : (lane == 1 ? sm.a1 : sm.a2); for (int q = 0; q < 64; q++) J -= a[q]; }
+      if (lane < 3) J = chain_sub64(lane == 0 ? sm.a0 : (lane == 1 ? sm.a1 : sm.a2));
       const float J0 = __shfl_sync(0xffffffffu, J, 0), J1 = __shfl_sync(0xffffffffu, J, 1), J2 = __shfl_sync(0xffffffffu, J, 2);
       const float up0 = (Hi[0]*J0 + Hi[1]*J1) + Hi[2]*J2, up1 = (Hi[3]*J0 + Hi[4]*J1) + Hi[5]*J2, up2 = (Hi[6]*J0 + Hi[7]*J1) + Hi[8]*J2;
       u += up0; v += up1; mean_diff += up2;
@@ -219,7 +233,7 @@ __device__ bool find_match_direct(const RpJob& jb, const RpConst& C, const sdv_m
   return converged && !early_false;
 }
 
-__global__ void __launch_bounds__(32*kRpWarps) rp_match_kernel(const RpJob* __restrict__ jobs, RpConst C, RpScratch S) {
+__global__ void __launch_bounds__(32*kRpWarps, RP_MATCH_MINB) rp_match_kernel(const RpJob* __restrict__ jobs, RpConst C, RpScratch S) {
   __shared__ RpWarpSmem smem[kRpWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x*kRpWarps + warp; if (cell >= C.ncells) return;
@@ -241,7 +255,7 @@ __global__ void __launch_bounds__(32*kRpWarps) rp_match_kernel(const RpJob* __re
     if (bi < 0) break;
     last_key = bk; last_rank = br;
     double2 px = S.cand_px[jb.pt_off + bi];
-    if (find_match_direct(jb, C, m->pts[bi], px, smem[warp], lane)) { found = bi; fpx = px; break; }
+    if (find_match_direct(jb, C, m->pts[bi], px, smem[warp], lane, S.xf + (size_t)blockIdx.y*kRpMaxHosts*14)) { found = bi; fpx = px; break; }
   }
   if (lane == 0) { S.out_pt[cb] = found; S.out_px[cb] = fpx; }
 }
@@ -329,7 +343,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_jobs = 0, o_px = al(o_jobs + (size_t)n_jobs*sizeof(RpJob)), o_key = al(o_px + (size_t)totalP*sizeof(double2)), o_cell = al(o_key + (size_t)totalP*4), o_list = al(o_cell + (size_t)totalP*4),
          o_count = al(o_list + (size_t)totalP*4), o_begin = al(o_count + (size_t)nc*4), o_cur = al(o_begin + (size_t)nc*4), o_opt = al(o_cur + (size_t)nc*4), o_opx = al(o_opt + (size_t)nc*4),
-         o_ov = al(o_opx + (size_t)nc*sizeof(double2)), o_rj = al(o_ov + (size_t)nc*sizeof(sdv_overlap_pt)), o_no = al(o_rj + (size_t)n_jobs*sizeof(RefineJob)), o_co = al(o_no + (size_t)n_jobs*4),
+         o_xf = al(o_opx + (size_t)nc*sizeof(double2)), o_ov = al(o_xf + (size_t)n_jobs*kRpMaxHosts*14*sizeof(double)), o_rj = al(o_ov + (size_t)nc*sizeof(sdv_overlap_pt)), o_no = al(o_rj + (size_t)n_jobs*sizeof(RefineJob)), o_co = al(o_no + (size_t)n_jobs*4),
          total = al(o_co + (size_t)C.ncells*4);
   size_t h_jobs = 0, h_opt = al(h_jobs + (size_t)n_jobs*sizeof(RpJob)), h_opx = al(h_opt + (size_t)nc*4), h_rj = al(h_opx + (size_t)nc*sizeof(double2)), h_no = al(h_rj + (size_t)n_jobs*sizeof(RefineJob)),
          h_co = al(h_no + (size_t)n_jobs*4), host_total = al(h_co + (size_t)C.ncells*4);
@@ -363,7 +377,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
     for (int i=0;i<m.nH;i++) { double o2[2]; aff_from_to(m.host_exposure[i], f.exposure, m.host_ab[i][0], m.host_ab[i][1], ca, cbb, o2); j.affLL[i][0] = (float)o2[0]; j.affLL[i][1] = (float)o2[1]; }
   }
   RpScratch& S = R.S; S.cand_px = (double2*)(db + o_px); S.cand_key = (float*)(db + o_key); S.cand_cell = (int*)(db + o_cell); S.list = (int*)(db + o_list);
-  S.count = (int*)(db + o_count); S.begin = (int*)(db + o_begin); S.cursor = (int*)(db + o_cur); S.out_pt = (int*)(db + o_opt); S.out_px = (double2*)(db + o_opx);
+  S.count = (int*)(db + o_count); S.begin = (int*)(db + o_begin); S.cursor = (int*)(db + o_cur); S.out_pt = (int*)(db + o_opt); S.out_px = (double2*)(db + o_opx); S.xf = (double*)(db + o_xf);
   R.ov = (sdv_overlap_pt*)(db + o_ov); R.rj = (RefineJob*)(db + o_rj); R.n_out_dev = (int*)(db + o_no); R.cell_order_dev = (int*)(db + o_co);
   cudaStream_t s = c->st;
   launch_h2d_words(db + o_jobs, J, (size_t)n_jobs*sizeof(RpJob), s);               // kernel copy (see launch_h2d_words)
