@@ -57,33 +57,34 @@ __device__ void ref_set_pose(RefShared& S, const SE3d& w2c) {      // thread 0
 }
 
 // float energy of the pose staged in S.R/S.t ; result in S.energy / S.num (all threads call)
-__device__ void ref_energy(RefShared& S, const RefineJob& jb, const sdv_overlap_pt* pts, const LevelGeom& g, float fxi, float fyi) {
+__device__ void ref_energy(RefShared& S, const int pt_begin, const int pt_end, const sdv_overlap_pt* __restrict__ pts, const LevelGeom& g, float fxi, float fyi) {
   if (threadIdx.x == 0) { S.energy = 0.f; S.num = 0; }
-  for (int base = jb.pt_begin; base < jb.pt_end; base += kRefChunk) {
-    int cnt = min(kRefChunk, jb.pt_end - base);
+  for (int base = pt_begin; base < pt_end; base += kRefChunk) {
+    int cnt = min(kRefChunk, pt_end - base);
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       sdv_overlap_pt p = pts[base+i]; float pf[3], Ku, Kv;
       bool ok = ref_project(p, S, g, fxi, fyi, pf, Ku, Kv);
       float a = Ku - p.obs_x, b = Kv - p.obs_y;
-      S.r0[i] = a*a; S.r1[i] = b*b; S.ok[i] = ok;
+      S.r0[i] = ok ? a*a : 0.f; S.r1[i] = ok ? b*b : 0.f; S.ok[i] = ok;        // skipped points add exact zeros: the chain below is branch-free
     }
     __syncthreads();
     if (threadIdx.x == 0) { float e = S.energy; int n = S.num;
-      for (int i=0;i<cnt;i++) if (S.ok[i]) { e = e + S.r0[i] + S.r1[i]; n++; }
+#pragma unroll 8
+      for (int i=0;i<cnt;i++) { e = e + S.r0[i] + S.r1[i]; n += S.ok[i]; }
       S.energy = e; S.num = n; }
   }
   __syncthreads();
 }
 
 // H,b at the pose staged in S.R/S.t, accumulated onto S.H/S.b (all threads call)
-__device__ void ref_hb(RefShared& S, const RefineJob& jb, const sdv_overlap_pt* pts, const LevelGeom& g, float fxi, float fyi) {
+__device__ void ref_hb(RefShared& S, const int pt_begin, const int pt_end, const sdv_overlap_pt* __restrict__ pts, const LevelGeom& g, float fxi, float fyi) {
   int role = threadIdx.x, ri = 0, rj = 0;            // 0..20 upper H entries (row-major over i<=j), 21..26 b
   if (role < 21) { int r = role; for (ri = 0; r >= 6-ri; ri++) r -= 6-ri; rj = ri + r; }
   double acc = 0.0;
   if (role < 21) acc = S.H[ri*6+rj]; else if (role < 27) acc = S.b[role-21];
-  for (int base = jb.pt_begin; base < jb.pt_end; base += kRefChunk) {
-    int cnt = min(kRefChunk, jb.pt_end - base);
+  for (int base = pt_begin; base < pt_end; base += kRefChunk) {
+    int cnt = min(kRefChunk, pt_end - base);
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       sdv_overlap_pt p = pts[base+i]; float pf[3], Ku, Kv;
@@ -96,18 +97,17 @@ __device__ void ref_hb(RefShared& S, const RefineJob& jb, const sdv_overlap_pt* 
       float x = sqrtf(r0*r0 + r1*r1);
       const float tb = 4.6851f; float b2 = tb*tb, x2 = x*x, wv = 0.f;                                                   // Tukey :873-887
       if (x2 <= b2) { float tmp = 1.0f - x2/b2; wv = tmp*tmp; }
-      for (int k=0;k<6;k++) { S.J[k][i] = dx[k]; S.J[6+k][i] = dy[k]; }
-      S.r0[i] = r0; S.r1[i] = r1; S.wgt[i] = wv; S.ok[i] = ok;
+      for (int k=0;k<6;k++) { S.J[k][i] = ok ? dx[k] : 0.f; S.J[6+k][i] = ok ? dy[k] : 0.f; }   // skipped points contribute exact zeros (no NaN*0)
+      S.r0[i] = ok ? r0 : 0.f; S.r1[i] = ok ? r1 : 0.f; S.wgt[i] = ok ? wv : 0.f; S.ok[i] = ok;
     }
     __syncthreads();
     if (role < 21) {
-      for (int i=0;i<cnt;i++) if (S.ok[i]) {
-        double w = (double)S.wgt[i];
-        acc += ((double)S.J[ri][i]*(double)S.J[rj][i] + (double)S.J[6+ri][i]*(double)S.J[6+rj][i])*w; }
-    } else if (role < 27) { int k = role-21;
-      for (int i=0;i<cnt;i++) if (S.ok[i]) {
-        double w = (double)S.wgt[i];
-        acc += ((double)S.J[k][i]*(double)S.r0[i] + (double)S.J[6+k][i]*(double)S.r1[i])*w; }
+      const float* __restrict__ a0 = S.J[ri]; const float* __restrict__ a1 = S.J[rj]; const float* __restrict__ c0 = S.J[6+ri]; const float* __restrict__ c1 = S.J[6+rj];
+#pragma unroll 4
+      for (int i=0;i<cnt;i++) acc += ((double)a0[i]*(double)a1[i] + (double)c0[i]*(double)c1[i])*(double)S.wgt[i];
+    } else if (role < 27) { const int k = role-21; const float* __restrict__ a0 = S.J[k]; const float* __restrict__ c0 = S.J[6+k];
+#pragma unroll 4
+      for (int i=0;i<cnt;i++) acc += ((double)a0[i]*(double)S.r0[i] + (double)c0[i]*(double)S.r1[i])*(double)S.wgt[i];
     }
   }
   __syncthreads();
@@ -121,19 +121,21 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
   __shared__ SE3d cur, cand;             // worldToCur_current / worldToCur_new
   __shared__ float s_lambda, s_resOld;
   RefineJob& jb = jobs[blockIdx.x];
+  const int pt_begin = jb.pt_begin, pt_end = jb.pt_end, nH = jb.nH, host_begin = jb.host_begin; const double* __restrict__ hostT = jb.hostT;   // read once: jb is written below, so the
+                                                                        // compiler would otherwise re-load these from global memory inside every loop
   const LevelGeom g = tc->geom[0];
   const float fxi = g.Ki[0], fyi = g.Ki[4];
-  for (int k = threadIdx.x; k < jb.nH; k += blockDim.x) {
-    SE3d h = se3_from7(jb.hostT ? jb.hostT + 7*k : hostT7 + 7*(size_t)(jb.host_begin + k)); double R[9]; qmat(h.q, R);
+  for (int k = threadIdx.x; k < nH; k += blockDim.x) {
+    SE3d h = se3_from7(hostT ? hostT + 7*k : hostT7 + 7*(size_t)(host_begin + k)); double R[9]; qmat(h.q, R);
     for (int i=0;i<9;i++) S.hostR[k][i] = (float)R[i];
     for (int i=0;i<3;i++) S.hostT[k][i] = (float)h.t[i];
   }
   if (threadIdx.x < 36) S.H[threadIdx.x] = 0.0; if (threadIdx.x < 6) S.b[threadIdx.x] = 0.0;
   if (threadIdx.x == 0) { cur = se3_inv(se3_from7(jb.T)); ref_set_pose(S, cur); s_lambda = 0.01f; S.done = 0; jb.iterations = 0; jb.accepts = 0; }
   __syncthreads();
-  ref_energy(S, jb, pts, g, fxi, fyi);
+  ref_energy(S, pt_begin, pt_end, pts, g, fxi, fyi);
   if (threadIdx.x == 0) s_resOld = S.energy / S.num;
-  ref_hb(S, jb, pts, g, fxi, fyi);
+  ref_hb(S, pt_begin, pt_end, pts, g, fxi, fyi);
   const float lambdaExtrapolationLimit = 0.001f;
   // undamped copy of the system at the current pose: structPoseEstimation re-linearises at the pose BEFORE an accepted step (:989), i.e. for the
   // first accepted step at the very pose the loop started from — identical values, so they are restored rather than recomputed
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
       }
     }
     __syncthreads();
-    ref_energy(S, jb, pts, g, fxi, fyi);
+    ref_energy(S, pt_begin, pt_end, pts, g, fxi, fyi);
     __shared__ int s_accept, s_recompute;
     if (threadIdx.x == 0) {
       float resNew = (S.num == 0) ? 1000000.0f : S.energy / S.num;
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
       if (s_recompute) {
         if (threadIdx.x < 36) S.H[threadIdx.x] = 0.0; if (threadIdx.x < 6) S.b[threadIdx.x] = 0.0;
         __syncthreads();
-        ref_hb(S, jb, pts, g, fxi, fyi);                                 // (sic) at the pose before the accepted step
+        ref_hb(S, pt_begin, pt_end, pts, g, fxi, fyi);                                 // (sic) at the pose before the accepted step
         if (threadIdx.x < 36) S.H0[threadIdx.x] = S.H[threadIdx.x]; if (threadIdx.x < 6) S.b0[threadIdx.x] = S.b[threadIdx.x];
         if (threadIdx.x == 0) hb_id = cur_id;
       } else {
