@@ -381,7 +381,7 @@ __device__ __forceinline__ void tier_shift(Tier& t) {                       // s
 __device__ __forceinline__ float tier_finish(Tier& t) { t.d1k = t.d + t.d1k; t.d1m = t.d1k + t.d1m; return t.d1m; }
 
 // one CTA per (host,target) bucket; thread e < 66 owns one cell of AccumulatorApprox and walks the pair's residuals in order
-constexpr int kTopChunk = 32;
+constexpr int kTopChunk = 96;                 // residuals staged per pass (one per thread for the activity flags); fewer latency-bound gather stages per bucket
 __global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restrict__ wins, int gate, int mode) {
   BA_WIN(gate)
   if ((int)blockIdx.x >= H->nF*H->nF) return;
@@ -425,10 +425,31 @@ __global__ void __launch_bounds__(96) ba_acc_top_kernel(const BAWinDev* __restri
 // and accEB[(h,t1)] (6).  The host's points are staged through shared memory 32 at a time (activity mask over targets, JpJdF per
 // target, HdiF, bdSumF, Hcd) and walked in order; a bucket is touched only by the points whose residuals towards t1 and t2 are active,
 // i.e. exactly the (r1,r2) loops of AccumulatedSCHessian.cpp:46-61.  Float sums, their order and the 1k/1M tiers match the CPU path.
-constexpr int kScChunk = 32;
+constexpr int kScChunk = 64;
 __global__ void __launch_bounds__(96) ba_acc_sc_kernel(const BAWinDev* __restrict__ wins, int gate) {
   BA_WIN(gate)
   const int nF = H->nF; const int nF2 = nF*nF; const int h = blockIdx.x;
+  if (blockIdx.x == kMaxF) {                                                  // extra CTA: accHcc (4x4) and accbc (4) over ALL points of the window, in point order.
+    // Points are staged through shared memory 256 at a time; threads 0..19 own one cell each and walk the staged chunk (a walk over global memory was the
+    // critical path of the whole kernel: 1687 dependent L2 round trips per cell).
+    constexpr int kHcChunk = 256;
+    __shared__ float hHdi[kHcChunk], hBd[kHcChunk], hHcd[kHcChunk][4]; __shared__ int hOk[kHcChunk];
+    const int e2 = threadIdx.x; Tier tt = {0,0,0,0,0};
+    for (int base = 0; base < nP; base += kHcChunk) {
+      const int cnt = min(kHcChunk, nP - base);
+      __syncthreads();
+      for (int q = threadIdx.x; q < cnt; q += 96) { const int p = base + q; const int ok = !(P.ngood[p] == 0 || P.isFromSensor[p]); hOk[q] = ok;
+        hHdi[q] = P.HdiF[p]; hBd[q] = P.bdSumF[p]; for (int c = 0; c < 4; c++) hHcd[q][c] = P.Hcd_accAF[(size_t)p*4 + c] + 0.0f; }
+      __syncthreads();
+      if (e2 < 20) for (int q = 0; q < cnt; q++) { if (!hOk[q]) continue;
+        const float Hdi = hHdi[q];
+        if (e2 < 16) tt.d += (Hdi*hHcd[q][e2/4])*hHcd[q][e2%4];
+        else tt.d += (hBd[q]*Hdi)*hHcd[q][e2-16];
+        tt.n1 += 1; tier_shift(tt); }
+    }
+    if (e2 < 20) { const float v = tier_finish(tt); if (e2 < 16) H->accHcc[e2] = v; else H->accbc[e2-16] = v; }
+    return;
+  }
   if (h >= nF) return;
   const int p0 = R.host_begin[h], p1 = R.host_begin[h+1];
   const int e = threadIdx.x;
@@ -493,17 +514,6 @@ __global__ void __launch_bounds__(96) ba_acc_sc_kernel(const BAWinDev* __restric
     for (int k = 0; k < 24; k++) { float v1k = d1k[k] + d[k]; H->accE[(h + nF*t1)*24 + k] = d1m[k] + v1k; }
 #pragma unroll
     for (int k = 0; k < 6; k++) { float v1k = d1k[24+k] + d[24+k]; H->accEB[(h + nF*t1)*6 + k] = d1m[24+k] + v1k; } }
-  if (h == 0 && e >= 32 && e < 52) {
-    const int e2 = e - 32; Tier tt = {0,0,0,0,0};
-    for (int p = 0; p < nP; p++) {
-      if (P.ngood[p] == 0 || P.isFromSensor[p]) continue;
-      const float Hdi = P.HdiF[p];
-      if (e2 < 16) tt.d += (Hdi*(P.Hcd_accAF[(size_t)p*4 + e2/4] + 0.0f))*(P.Hcd_accAF[(size_t)p*4 + e2%4] + 0.0f);
-      else tt.d += (P.bdSumF[p]*Hdi)*(P.Hcd_accAF[(size_t)p*4 + e2-16] + 0.0f);
-      tt.n1 += 1; tier_shift(tt);
-    }
-    float v = tier_finish(tt); if (e2 < 16) H->accHcc[e2] = v; else H->accbc[e2-16] = v;
-  }
 }
 
 // ================================================================================================ stitch + solve (single CTA per window)
@@ -921,7 +931,7 @@ void launch_ba_energies(const BAWinDev* wins, int W, int gate, cudaStream_t st) 
 static void accumulate_mode(const BAWinDev* wins, int W, int maxP, int gate, int mode, cudaStream_t st) {
   ba_point_acc_kernel<<<g2(maxP, 128, W), 128, 0, st>>>(wins, gate, mode);
   ba_acc_top_kernel<<<dim3(kMaxF*kMaxF, W), 96, 0, st>>>(wins, gate, mode);
-  ba_acc_sc_kernel<<<dim3(kMaxF, W), 96, 0, st>>>(wins, gate);
+  ba_acc_sc_kernel<<<dim3(kMaxF + 1, W), 96, 0, st>>>(wins, gate);          // kMaxF host CTAs + one CTA for the calibration block
 }
 void launch_ba_accumulate(const BAWinDev* wins, int W, int maxP, int gate, cudaStream_t st) { accumulate_mode(wins, W, maxP, gate, 0, st); }
 void launch_ba_solve(const BAWinDev* wins, int W, int maxP, int iteration, double lambda, int use_hdr_ctl, int gate, cudaStream_t st) {
