@@ -7,8 +7,9 @@ independent sequences / Monte-Carlo re-runs sharded over GPUs, no cross-GPU depe
 photometric SE(3)+affine LM against the keyframe's LiDAR-depth reference cloud, device-resident) -> pose/residuals back.
 
   value   : frames/s with the raw frames already resident in HBM (sdv_frame_build_batch_dev + sdv_tracker_track_batch)
-  e2e     : frames/s through the reference-facing C-ABI with HOST buffers: pinned float images H2D every step
-            (sdv_frame_upload_batch = makeImages(float*) signature) and pose/residual D2H every step, inside the timed region
+  e2e     : frames/s through the reference-facing C-ABI with HOST buffers: pinned mono8 images (the sensor_msgs/Image wire format the reference
+            ingests; the synthetic frames are mono8-exact) H2D every step and pose/residual D2H every step, inside the timed region;
+            e2e_float32 = the same with float images (FrameHessian::makeImages(float*) signature, 4x the PCIe bytes)
   roofline: the device-resident LM kernel (track_cluster_kernel): algorithmic bytes = 64 B x point evaluations
   cpu_baseline / --impl reference: the CPU restatement (oracle/, "port": the reference cannot be built here) on host cores.
 """
@@ -432,10 +433,11 @@ def main():
                    "l2_policy": "inputs larger than L2: %.1f GB of per-sequence pyramids+clouds per step vs 126 MB L2" % (B * 9.3e-3),
                    "init": "ground truth perturbed N(4cm, 0.002rad) (constant-motion prediction error)",
                    "tracked_ok_fraction": float(ev[1].item()) / (world * B * K), "pose_err_vs_gt_m_rad": [pose_err_t, pose_err_r]},
-        "e2e": {"value": world * B * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * h * w * 4 + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
-                "api": "sdv_frame_upload_batch(float*, pinned) + sdv_tracker_track_batch, upload of batch k+1 overlapped with tracking of batch k"},
-        "e2e_mono8": {"value": world * B * K / t_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": B * h * w + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
-                      "api": "sdv_frame_upload_batch_u8 (sensor wire format, u8->float fused into the pyramid kernel) + sdv_tracker_track_batch"},
+        "e2e": {"value": world * B * K / t_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": B * h * w + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
+                "api": "sdv_frame_upload_batch_u8 (pinned host mono8 = the sensor_msgs/Image wire format the reference ingests; u8->float fused into the pyramid kernel) + sdv_tracker_track_batch; "
+                       "upload of batch k+1 overlapped with tracking of batch k; synthetic frames are mono8-exact, results identical to the float path"},
+        "e2e_float32": {"value": world * B * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * h * w * 4 + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
+                        "api": "sdv_frame_upload_batch(float*, pinned) = FrameHessian::makeImages(float*) signature + sdv_tracker_track_batch; PCIe-bound (4x the bytes of the wire format)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "track_cluster_kernel<128,4> (device-resident trackNewestCoarse: calcRes+calcGSSSE+LM)", "bound": "hbm",

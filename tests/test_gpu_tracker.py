@@ -194,3 +194,41 @@ def test_properties_full_size(kitti_seq):
     err = orc.se3_log(orc.se3_mul(r1["T"], orc.se3_inv(Tgt)))
     assert np.linalg.norm(err[:3]) < 5e-3 and np.linalg.norm(err[3:]) < 5e-4
     ctx.close()
+
+
+def test_ingest_variants_identical_pyramids_and_pipelined_order(kitti_seq):
+    """The batched ingest entries (float host, mono8 host, device buffers; adjacent mono8 images coalesced into one copy, uploads of consecutive
+    batches overlapping on the copy stream) build bit-identical pyramids to the single-frame float upload, and tracking a batch while the next
+    one streams in gives the same poses as the serial order."""
+    api, synth = _api(); w, h = synth.KITTI_WH; L = api.pyr_levels(w, h); B = 6
+    imgs = [np.ascontiguousarray(kitti_seq.images[k]) for k in (1, 2)]                    # mono8-exact floats
+    ctx = api.Context(synth.KITTI_K, w, h, max_frames=4 * B + 2, n_tracker_slots=B)
+    p4 = _pts(synth, kitti_seq, 1500); rh = np.zeros(len(p4), np.int32)
+    ctx.makeImages(999, kitti_seq.images[0])
+    for b in range(B):
+        api.CoarseTracker(ctx, b).setCoarseTrackingRef(999, p4, rh)
+    ctx.makeImages(900, imgs[0])
+    ref = [ctx.frameLevel(900, l)[0].copy() for l in range(L)]
+    f32 = np.ascontiguousarray(np.stack([imgs[0]] * B)); u8 = np.ascontiguousarray(np.stack([imgs[0]] * B).astype(np.uint8))
+    u8_gap = [np.ascontiguousarray(imgs[0].astype(np.uint8)) for _ in range(B)]          # separate allocations: no coalescing
+    ids = np.arange(B, dtype=np.uint64)
+    ctx.makeImagesBatch(ids + 100, np.array([f32[b].ctypes.data for b in range(B)], np.uint64))
+    ctx.makeImagesBatch(ids + 200, np.array([u8[b].ctypes.data for b in range(B)], np.uint64), u8=True)
+    ctx.makeImagesBatch(ids + 300, np.array([a.ctypes.data for a in u8_gap], np.uint64), u8=True)
+    for base in (100, 200, 300):
+        for b in (0, B - 1):
+            for l in range(L):
+                assert np.array_equal(ctx.frameLevel(int(base + b), l)[0], ref[l], equal_nan=True), (base, b, l)
+    # pipelined: upload batch B while batch A is tracked, vs strictly serial
+    slots = np.arange(B, dtype=np.int32); T0 = np.tile(ID7, (B, 1)); T0[:, 6] = -0.9
+    u8b = np.ascontiguousarray(np.stack([imgs[1]] * B).astype(np.uint8))
+    pa = np.array([u8[b].ctypes.data for b in range(B)], np.uint64); pb = np.array([u8b[b].ctypes.data for b in range(B)], np.uint64)
+    ctx.makeImagesBatch(ids + 100, pa, u8=True); ctx.sync(); ctx.makeImagesBatch(ids + 200, pb, u8=True); ctx.sync()
+    Ta = T0.copy(); ctx.trackBatch(slots, ids + 100, Ta, np.zeros((B, 2))); Tb = T0.copy(); ctx.trackBatch(slots, ids + 200, Tb, np.zeros((B, 2)))
+    ctx.makeImagesBatch(ids + 100, pa, u8=True)                                            # no sync: the next upload is enqueued before tracking starts
+    ctx.makeImagesBatch(ids + 200, pb, u8=True)
+    Ta2 = T0.copy(); ctx.trackBatch(slots, ids + 100, Ta2, np.zeros((B, 2)))
+    ctx.makeImagesBatch(ids + 300, pa, u8=True)
+    Tb2 = T0.copy(); ctx.trackBatch(slots, ids + 200, Tb2, np.zeros((B, 2)))
+    assert np.array_equal(Ta, Ta2) and np.array_equal(Tb, Tb2)
+    ctx.close()
