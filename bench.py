@@ -273,6 +273,7 @@ def main():
     ap.add_argument("--kf-every", type=int, default=5, help="keyframe cadence assumed when combining the tracker and BA legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # NCCL's version banner / debug lines must not land on stdout next to the JSON line
     W = max(args.warmup, 3)
 
     if args.impl == "reference":
