@@ -47,7 +47,10 @@ def se3_helpers():
 
 def gt_and_inits(seq, synth, B, steps_total, seed=7):
     """Initial guesses = ground-truth relative pose perturbed like a constant-motion prediction error (few cm / ~0.1 deg)."""
-    orc = se3_helpers()
+    class orc:                                                            # data generation uses the package's own numpy SE(3) helpers, not the oracle
+        se3_mul = staticmethod(synth.se3_mul7); se3_exp = staticmethod(synth.se3_exp7)
+        @staticmethod
+        def se3_from_rt(R, t): return np.concatenate([synth._quat_from_R(R), t])
     gts = [orc.se3_from_rt(*synth.rel_pose(seq.R[0], seq.t[0], seq.R[k], seq.t[k])) for k in range(N_FRAMES)]
     rng = np.random.default_rng(seed)
     inits = np.zeros((steps_total, B, 7))
@@ -191,13 +194,12 @@ def ba_leg(ctx, api, synth, local_rank, W, reps=4, warm=2):
             "note": "device time of sdv_ba_optimize_batch (FullSystem::optimize, device-resident GN schedule); bit-exact vs the CPU oracle (tests/test_gpu_ba.py)"}
 
 
-def refine_leg(ctx, api, synth, B, reps=6, warm=2, seed=11):
+def refine_leg(ctx, api, synth, B, reps=6, warm=2, seed=11, cpu=True):
     """Semi-direct refinement leg = the tail of FullSystem::trackNewCoarse (FullSystem.cpp:481-488): Reprojector::reprojectMap of the active map
     (7 keyframes, ~2000 active points) into the new frame + CoarseTracker::structPoseEstimation, fused on the device (sdv_tracker_refine_batch).
     One map slot and one private target frame per sequence; the 7 keyframe images are shared by the sequences (read footprint per frame is
     ~400 10x10 patches).  Reports device time (CUDA events in the library) and wall time of the C-ABI call (job H2D + result D2H inside)."""
     from conftest import cached_sequence
-    orc = se3_helpers()
     seq8 = cached_sequence(8, 2000, synth.KITTI_K, synth.KITTI_WH)
     pts, hT, hab = synth.make_map(seq8, list(range(7)), n_per_frame=300, seed=2)
     base = 1 << 42; kf_ids = [base + k for k in range(7)]
@@ -211,7 +213,7 @@ def refine_leg(ctx, api, synth, B, reps=6, warm=2, seed=11):
     def inits():
         T = np.tile(gt, (B, 1))
         for b in range(B):
-            T[b] = orc.se3_mul(orc.se3_exp(np.concatenate([rng.normal(0, 0.02, 3), rng.normal(0, 0.001, 3)])), gt)
+            T[b] = synth.se3_mul7(synth.se3_exp7(np.concatenate([rng.normal(0, 0.02, 3), rng.normal(0, 0.001, 3)])), gt)
         return T
     ms = []; wall = []; last = None
     for rep in range(warm + reps):
@@ -222,20 +224,22 @@ def refine_leg(ctx, api, synth, B, reps=6, warm=2, seed=11):
             ms.append(r["ms"]); wall.append(t1 - t0); last = (r, T0)
     r, T0 = last
     e0 = float(np.median(np.linalg.norm(T0[:, 4:] - gt[4:], axis=1))); e1 = float(np.median(np.linalg.norm(r["T"][:, 4:] - gt[4:], axis=1)))
-    # CPU port of the same stage on one core (bounded sample)
-    L = 4; kf_frames = [orc.Frame(seq8.images[k], L) for k in range(7)]; cur = orc.Frame(seq8.images[7], L); w, h = synth.KITTI_WH
-    ts = []
-    for i in range(3):
-        t0 = time.perf_counter()
-        idx, px = orc.reproject_map(w, h, L, synth.KITTI_K, kf_frames, hT, hab, cur, T0[i], [0.0, 0.0], pts, cell_order=order, max_matches=400)
-        p6 = np.stack([pts["u"][idx], pts["v"][idx], pts["idepth"][idx], pts["host"][idx].astype(np.float32), px[:, 0].astype(np.float32), px[:, 1].astype(np.float32)], 1).astype(np.float32)
-        orc.struct_pose(w, h, np.array(synth.KITTI_K, np.float32), hT, p6, T0[i]); ts.append(time.perf_counter() - t0)
+    ts = [float('nan')]
+    if cpu:
+        # CPU port of the same stage on one core (bounded sample) — the cpu_baseline side of this leg, the only place it touches oracle/
+        orc = se3_helpers(); L = 4; kf_frames = [orc.Frame(seq8.images[k], L) for k in range(7)]; cur = orc.Frame(seq8.images[7], L); w, h = synth.KITTI_WH
+        ts = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            idx, px = orc.reproject_map(w, h, L, synth.KITTI_K, kf_frames, hT, hab, cur, T0[i], [0.0, 0.0], pts, cell_order=order, max_matches=400)
+            p6 = np.stack([pts["u"][idx], pts["v"][idx], pts["idepth"][idx], pts["host"][idx].astype(np.float32), px[:, 0].astype(np.float32), px[:, 1].astype(np.float32)], 1).astype(np.float32)
+            orc.struct_pose(w, h, np.array(synth.KITTI_K, np.float32), hT, p6, T0[i]); ts.append(time.perf_counter() - t0)
     for b in range(B):
         ctx.releaseFrame(int(ids[b]))
     return {"frames": B, "map_points": int(len(pts)), "keyframes": 7, "ms_per_batch_device": float(np.mean(ms)), "ms_per_batch_wall": 1e3 * float(np.mean(wall)),
             "frames_per_s_device": B / (float(np.mean(ms)) * 1e-3), "frames_per_s_wall": B / float(np.mean(wall)),
             "matches_mean": float(r["n_matches"].mean()), "gn_iterations_mean": float(r["iterations"].mean()), "accepts_mean": float(r["accepts"].mean()),
-            "median_translation_err_in_out_m": [e0, e1], "cpu_ms_per_frame_1core": 1e3 * float(np.median(ts)),
+            "median_translation_err_in_out_m": [e0, e1], "cpu_ms_per_frame_1core": (1e3 * float(np.median(ts)) if cpu else None),
             "note": "sdv_tracker_refine_batch: reprojectMap (grid 25 px, warp-per-cell direct alignment) + structPoseEstimation, device resident; exact parity vs the CPU oracle (tests/test_gpu_reproject.py)"}
 
 
@@ -359,14 +363,13 @@ def main():
         step_dev(s)
     barrier(); l0 = ctx.launch_count()
     t0 = time.perf_counter(); kern_ms = 0.0; evals = 0; good = 0; pose_err = 0.0
-    orc = se3_helpers()
     for s in range(W, W + K):
         r, T = step_dev(s)
         kern_ms += ctx.last_kernel_ms(); evals += int(r["evals"].sum()); good += int(r["good"].sum())
     barrier(); t_value = time.perf_counter() - t0
     launches = ctx.launch_count() - l0
     k_last = 1 + (W + K - 1) % (N_FRAMES - 1)
-    errs = [np.abs(orc.se3_log(orc.se3_mul(T[b], orc.se3_inv(gts[k_last])))) for b in range(min(B, 16))]
+    errs = [np.abs(synth.se3_log7(synth.se3_mul7(T[b], synth.se3_inv7(gts[k_last])))) for b in range(min(B, 16))]
     pose_err_t = float(max(e[:3].max() for e in errs)); pose_err_r = float(max(e[3:].max() for e in errs))
 
     # ---------------------------------------------------------------- leg 2: end to end through host buffers (H2D + D2H every step)
@@ -410,7 +413,7 @@ def main():
     clocks = sampler.stop()
 
     ba = ba_leg(ctx, api, synth, local_rank, WBA) if WBA > 0 else None
-    refine = refine_leg(ctx, api, synth, B) if not args.no_refine else None
+    refine = refine_leg(ctx, api, synth, B, cpu=not args.no_cpu_baseline) if not args.no_refine else None
     tv = torch.tensor([t_value, t_e2e, kern_ms, t_e2e_u8], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)

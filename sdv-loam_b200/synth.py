@@ -323,3 +323,42 @@ def make_map(seq: "Sequence", kf_idx, n_per_frame: int = 300, seed: int = 0, edg
     pts = np.array(out, MAP_PT_DTYPE)
     host_T7 = np.array([np.concatenate([_quat_from_R(seq.R[k]), seq.t[k]]) for k in kf_idx])
     return pts, host_T7, np.zeros((len(kf_idx), 2))
+
+
+# ------------------------------------------------------------------------------------------------ small SE(3) helpers on T7 = {qw,qx,qy,qz,tx,ty,tz} (numpy, for data generation)
+def _qmul(a, b):
+    return np.array([a[0]*b[0] - a[1]*b[1] - a[2]*b[2] - a[3]*b[3], a[0]*b[1] + a[1]*b[0] + a[2]*b[3] - a[3]*b[2],
+                     a[0]*b[2] + a[2]*b[0] + a[3]*b[1] - a[1]*b[3], a[0]*b[3] + a[3]*b[0] + a[1]*b[2] - a[2]*b[1]])
+
+
+def _qrot(q, v):
+    qv = q[1:]; uv = 2.0 * np.cross(qv, v); return v + q[0] * uv + np.cross(qv, uv)
+
+
+def se3_mul7(a, b):
+    q = _qmul(a[:4], b[:4]); q = q / np.linalg.norm(q); return np.concatenate([q, a[4:] + _qrot(a[:4], b[4:])])
+
+
+def se3_inv7(a):
+    q = np.array([a[0], -a[1], -a[2], -a[3]]); return np.concatenate([q, _qrot(q, -a[4:])])
+
+
+def se3_exp7(xi):
+    """xi = [upsilon(3); omega(3)] (Sophus order)."""
+    ups, om = np.asarray(xi[:3], np.float64), np.asarray(xi[3:], np.float64); th = np.linalg.norm(om)
+    Om = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0.0]])
+    if th < 1e-10:
+        q = np.array([1.0, 0.5 * om[0], 0.5 * om[1], 0.5 * om[2]]); V = np.eye(3) + 0.5 * Om
+    else:
+        q = np.concatenate([[np.cos(th / 2)], np.sin(th / 2) / th * om]); V = np.eye(3) + (1 - np.cos(th)) / th**2 * Om + (th - np.sin(th)) / th**3 * (Om @ Om)
+    return np.concatenate([q / np.linalg.norm(q), V @ ups])
+
+
+def se3_log7(T):
+    q, t = T[:4], T[4:]; n = np.linalg.norm(q[1:])
+    om = np.zeros(3) if n < 1e-12 else 2.0 * np.arctan2(n, q[0]) / n * q[1:]
+    if q[0] < 0 and n >= 1e-12:
+        om = 2.0 * np.arctan2(-n, -q[0]) / (-n) * (-q[1:])
+    th = np.linalg.norm(om); Om = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0.0]])
+    Vi = np.eye(3) - 0.5 * Om + ((1.0 / 12.0) if th < 1e-8 else (1 - th / (2 * np.tan(th / 2))) / th**2) * (Om @ Om)
+    return np.concatenate([Vi @ t, om])
