@@ -272,6 +272,7 @@ def main():
     ap.add_argument("--seqs", type=int, default=592, help="resident sequences per GPU (148 SMs x 4 jobs)")
     ap.add_argument("--points", type=int, default=2000, help="LiDAR-depth splats of the keyframe (reference default ~1500-2000 active points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--track-threads", type=int, default=128, help="threads per trackNewestCoarse job (128: 4 jobs/SM; 64: 8 jobs/SM; 256: latency mode)")
     ap.add_argument("--ba-windows", type=int, default=296, help="BA leg: resident 7-keyframe windows optimised per batch (0 = skip the BA leg)")
     ap.add_argument("--no-refine", action="store_true", help="skip the reprojectMap + structPoseEstimation leg")
     ap.add_argument("--kf-every", type=int, default=5, help="keyframe cadence assumed when combining the tracker and BA legs")
@@ -316,7 +317,7 @@ def main():
     p4 = np.concatenate([pts, np.full((len(pts), 1), 1e-3, np.float32)], 1).astype(np.float32); rh = np.zeros(len(p4), np.int32)
 
     WBA = max(0, args.ba_windows)
-    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=B, max_frames=3 * B + 16 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
+    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=B, track_threads=args.track_threads, max_frames=3 * B + 16 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
     KF = 1 << 40
     for b in range(B):                                                   # per sequence: keyframe -> reference cloud (makeCoarseDepthL0 on device)
         ctx.makeImages(KF, seq.images[0]); api.CoarseTracker(ctx, b).setCoarseTrackingRef(KF, p4, rh); ctx.releaseFrame(KF)
