@@ -85,3 +85,22 @@ def test_marginalize_points_host_status_and_errors():
     with pytest.raises(api.SdvError):
         gb.flagPointsForRemoval(sel[:1])                                         # window has no points until sdv_ba_set_points is called again
     ctx.close()
+
+
+def test_marginalize_nothing_and_two_frame_window():
+    """No point reaches PS_MARGINALIZE -> HM,bM unchanged (M = Msc = 0); frame elimination down to a single keyframe."""
+    api, synth = _mods()
+    seq = cached_sequence(8, 2000, synth.KITTI_K, synth.KITTI_WH)
+    win, ctx, ob, gb = _pair(api, synth, seq, [0, 3], seed=4, n_per_frame=120, pose_noise=(0.004, 0.0003), match_noise=0.1, prior_scale=1e-3)
+    ob.optimize(3); gb.optimize(3)
+    H0, b0 = gb.prior()
+    st = np.zeros(len(win["uv"]), np.int32); st[::4] = 1                          # only PS_DROP
+    mo = ob.marginalizePointsF(st); mg = gb.marginalizePointsF(st)
+    assert not mg["M"].any() and not mg["Msc"].any() and _same(mo["M"], mg["M"])
+    H1, b1 = gb.prior(); assert _same(H0, H1) and _same(b0, b1)
+    ob.marginalizeFrame(0); gb.marginalizeFrame(0)
+    (Ho, bo), (Hg, bg) = ob.prior(), gb.prior()
+    assert Hg.shape == (10, 10) and _same(Ho, Hg) and _same(bo, bg)
+    with pytest.raises(api.SdvError):
+        gb.marginalizeFrame(0)                                                    # a window keeps at least one keyframe
+    ctx.close()

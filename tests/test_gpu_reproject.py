@@ -121,3 +121,20 @@ def test_reproject_errors():
     with pytest.raises(api.SdvError):
         rp.setMap(0, [100, 555, 102], hT, hab, pts)                         # unknown keyframe handle
     ctx.close()
+
+
+def test_reproject_edge_cases_empty_map_and_no_candidates():
+    """Empty map, a map whose points all project outside the target frame, and a target equal to a keyframe (cur_kf_index skips its own points)."""
+    api, synth = _mods(); kfs = [0, 1, 2]; w, h = SMALL_WH
+    seq, L, pts, hT, hab, ctx, frames, poses = _scene(api, synth, SMALL_K, SMALL_WH, 5, 3000, kfs, 120)
+    rp = api.Reprojector(ctx)
+    rp.setMap(0, [100, 101, 102], hT, hab, pts[:0])
+    idx, px = rp.reprojectMap(0, 104, poses[4]); assert len(idx) == 0
+    r = rp.refineBatch([0], [104], poses[4:5]); assert r["n_matches"][0] == 0 and np.array_equal(r["T"][0], poses[4]) and r["accepts"][0] == 0
+    far = poses[4].copy(); far[4:] += [500.0, 0, 0]                                   # camera 500 m to the side: nothing lands in the image
+    rp.setMap(0, [100, 101, 102], hT, hab, pts)
+    o = orc.reproject_map(w, h, L, SMALL_K, [frames[k] for k in kfs], hT, hab, frames[4], far, [0.0, 0.0], pts)
+    g = rp.reprojectMap(0, 104, far); assert _eq(o, g)
+    o = orc.reproject_map(w, h, L, SMALL_K, [frames[k] for k in kfs], hT, hab, frames[1], poses[1], [0.0, 0.0], pts, cur_kf_index=1)
+    g = rp.reprojectMap(0, 101, poses[1], cur_kf_index=1); assert _eq(o, g) and len(g[0]) > 5 and np.all(pts["host"][g[0]] != 1)
+    ctx.close()
