@@ -411,14 +411,50 @@ def main():
         T = inits[s % steps_total].copy(); ab = np.zeros((B, 2)); ctx.trackBatch(slots, frame_ids(s), T, ab)
     barrier(); t_e2e_u8 = time.perf_counter() - t0
     tu = time.perf_counter(); upload_u8(s3 + K); ctx.sync(); t_e2e_u8 += time.perf_counter() - tu
+    # ---------------------------------------------------------------- leg 2c: the WHOLE FullSystem::trackNewCoarse per frame through host buffers: mono8 upload ->
+    # motion hypotheses + trackNewestCoarse re-track loop -> reprojectMap -> structPoseEstimation (sdv_track_new_coarse_batch), pose D2H
+    t_e2e_full = None; full_stats = None
+    if not args.no_refine:
+        KFM = (1 << 40) + 1; ctx.makeImages(KFM, seq.images[0])
+        kf_c2w = np.concatenate([synth._quat_from_R(seq.R[0]), seq.t[0]])
+        mp = np.zeros(len(pts), api.MAP_PT_DTYPE); mp["u"] = np.floor(pts[:, 0]); mp["v"] = np.floor(pts[:, 1]); mp["idepth"] = pts[:, 2]; mp["host"] = 0; mp["type"] = (np.arange(len(pts)) % 3 == 0)
+        rp = api.Reprojector(ctx)
+        for b in range(B):
+            rp.setMap(b, [KFM], kf_c2w[None], None, mp)
+        order = np.random.default_rng(3).permutation(rp.n_cells).astype(np.int32)
+        nfull = W + K + 2
+        io_all = np.zeros((nfull, B), api.TRACK_NEW_COARSE_DTYPE)
+        for i in range(nfull):                                           # history chosen so that the constant-motion hypothesis equals the perturbed initial guess of the other legs:
+            io = io_all[i]; io["slot"] = slots; io["poses_valid"] = 1    # slast = lastF (keyframe pose), sprelast = lastF * init  =>  try 0 = init
+            io["lastF_c2w"] = kf_c2w; io["slast_c2w"] = kf_c2w; io["lastCoarseRMSE"] = 100.0
+            for b in range(B):
+                io["sprelast_c2w"][b] = synth.se3_mul7(kf_c2w, inits[(s3 + i) % steps_total, b])
+        upload_u8(s3)
+        def full_step(i):
+            io = io_all[i]; io["frame"] = frame_ids(s3 + i)
+            api.trackNewCoarseBatchArray(ctx, io, cell_order=order, max_matches=400)
+            return io
+        for i in range(W):
+            upload_u8(s3 + i + 1); full_step(i)
+        barrier(); t0 = time.perf_counter()
+        for i in range(W, W + K):
+            if i + 1 < W + K:
+                upload_u8(s3 + i + 1)
+            io = full_step(i)
+        barrier(); t_e2e_full = time.perf_counter() - t0
+        tu = time.perf_counter(); upload_u8(s3 + W + K); ctx.sync(); t_e2e_full += time.perf_counter() - tu
+        k_last = 1 + (s3 + W + K - 1) % (N_FRAMES - 1)
+        gt_c2w = np.concatenate([synth._quat_from_R(seq.R[k_last]), seq.t[k_last]])
+        full_stats = {"tries_mean": float(io["tries"].mean()), "matches_mean": float(io["n_matches"].mean()), "refine_accepts_mean": float(io["refine_accepts"].mean()),
+                      "median_translation_err_m": float(np.median(np.linalg.norm(io["camToWorld"][:, 4:] - gt_c2w[4:], axis=1)))}
     clocks = sampler.stop()
 
     ba = ba_leg(ctx, api, synth, local_rank, WBA) if WBA > 0 else None
     refine = refine_leg(ctx, api, synth, B, cpu=not args.no_cpu_baseline) if not args.no_refine else None
-    tv = torch.tensor([t_value, t_e2e, kern_ms, t_e2e_u8], dtype=torch.float64, device="cuda")
+    tv = torch.tensor([t_value, t_e2e, kern_ms, t_e2e_u8, t_e2e_full or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
-    t_value, t_e2e, kern_ms_max, t_e2e_u8 = [float(x) for x in tv.cpu()]
+    t_value, t_e2e, kern_ms_max, t_e2e_u8, t_e2e_full_max = [float(x) for x in tv.cpu()]
     ev = torch.tensor([float(evals), float(good)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ev, op=dist.ReduceOp.SUM)
@@ -443,6 +479,10 @@ def main():
                        "upload of batch k+1 overlapped with tracking of batch k; synthetic frames are mono8-exact, results identical to the float path"},
         "e2e_float32": {"value": world * B * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * h * w * 4 + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
                         "api": "sdv_frame_upload_batch(float*, pinned) = FrameHessian::makeImages(float*) signature + sdv_tracker_track_batch; PCIe-bound (4x the bytes of the wire format)"},
+        "e2e_trackNewCoarse": (None if not full_stats else dict({"value": world * B * K / t_e2e_full_max, "unit": "frames/s", "h2d_bytes_per_step": B * h * w + B * (job_bytes + 416),
+                               "d2h_bytes_per_step": B * (job_bytes + 416),
+                               "api": "sdv_frame_upload_batch_u8 + sdv_track_new_coarse_batch (the whole FullSystem::trackNewCoarse: hypotheses, trackNewestCoarse re-track loop, reprojectMap, "
+                                      "structPoseEstimation) on host buffers; single-keyframe map of the bench sequence"}, **full_stats)),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "track_cluster_kernel<128,4> (device-resident trackNewestCoarse: calcRes+calcGSSSE+LM)", "bound": "hbm",

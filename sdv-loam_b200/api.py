@@ -241,17 +241,33 @@ class sdv_track_new_coarse_io(C.Structure):
                 ("refine_accepts", C.c_int32)]
 
 
+TRACK_NEW_COARSE_DTYPE = np.dtype([("slot", np.int32), ("poses_valid", np.int32), ("frame", np.uint64), ("sprelast_c2w", np.float64, 7), ("slast_c2w", np.float64, 7),
+                                   ("lastF_c2w", np.float64, 7), ("aff_last", np.float64, 2), ("lastCoarseRMSE", np.float64, 5), ("camToWorld", np.float64, 7),
+                                   ("camToTrackingRef", np.float64, 7), ("aff_g2l", np.float64, 2), ("flow", np.float64, 3), ("refine_res", np.float32),
+                                   ("have_one_good", np.int32), ("tries", np.int32), ("n_matches", np.int32), ("refine_iterations", np.int32), ("refine_accepts", np.int32)], align=True)
+assert TRACK_NEW_COARSE_DTYPE.itemsize == C.sizeof(sdv_track_new_coarse_io)
+
+
+def trackNewCoarseBatchArray(ctx, io, cell_order=None, max_matches=400):
+    """Same as trackNewCoarseBatch on a numpy structured array (TRACK_NEW_COARSE_DTYPE), updated in place — no per-job Python work."""
+    LIB.sdv_track_new_coarse_batch.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int]
+    assert io.dtype == TRACK_NEW_COARSE_DTYPE and io.flags.c_contiguous
+    co = None if cell_order is None else np.ascontiguousarray(cell_order, np.int32)
+    ctx._ck(LIB.sdv_track_new_coarse_batch(ctx.p, len(io), io.ctypes.data, None if co is None else co.ctypes.data, max_matches))
+    return io
+
+
 def trackNewCoarseBatch(ctx, jobs, cell_order=None, max_matches=400):
     """FullSystem::trackNewCoarse (FullSystem.cpp:283-500) for n sequences.  jobs: dicts with slot, frame, sprelast_c2w, slast_c2w, lastF_c2w, aff_last,
     poses_valid, lastCoarseRMSE.  Returns one dict per job with the fields of sdv_track_new_coarse_io."""
-    LIB.sdv_track_new_coarse_batch.argtypes = [_vp, C.c_int, C.POINTER(sdv_track_new_coarse_io), _vp, C.c_int]
+    LIB.sdv_track_new_coarse_batch.argtypes = [_vp, C.c_int, _vp, _vp, C.c_int]
     n = len(jobs); io = (sdv_track_new_coarse_io * n)()
     for k, j in enumerate(jobs):
         io[k].slot = j["slot"]; io[k].poses_valid = int(j.get("poses_valid", 1)); io[k].frame = j["frame"]
         for name in ("sprelast_c2w", "slast_c2w", "lastF_c2w", "aff_last", "lastCoarseRMSE"):
             v = np.asarray(j[name], np.float64); getattr(io[k], name)[:] = v.tolist()
     co = None if cell_order is None else np.ascontiguousarray(cell_order, np.int32)
-    ctx._ck(LIB.sdv_track_new_coarse_batch(ctx.p, n, io, None if co is None else co.ctypes.data, max_matches))
+    ctx._ck(LIB.sdv_track_new_coarse_batch(ctx.p, n, C.addressof(io), None if co is None else co.ctypes.data, max_matches))
     out = []
     for k in range(n):
         o = io[k]

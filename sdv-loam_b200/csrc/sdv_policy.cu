@@ -17,41 +17,51 @@ using namespace sdv;
 
 static SE3d quatT(double w, double x, double y, double z) { SE3d s; s.q = qnormalize(Quat{w, x, y, z}); s.t[0] = s.t[1] = s.t[2] = 0; return s; }   // SE3(Quaterniond, Vec3) normalises
 
-static void make_tries(const sdv_track_new_coarse_io& io, std::vector<SE3d>& tries) {
-  tries.clear();
-  if (!io.poses_valid) { tries.push_back(se3_identity()); return; }                     // :390-394
+// Hypothesis i of FullSystem.cpp:346-388, generated on demand (healthy tracking only ever needs i = 0; building all 31 for every sequence of a batch
+// would cost more host time than the launch they feed).
+struct TryGen { bool valid; SE3d inv, lastF_2_slast, cm, fh_2_slast; };
+static TryGen try_gen(const sdv_track_new_coarse_io& io) {
+  TryGen g; g.valid = io.poses_valid != 0; if (!g.valid) return g;                       // :390-394 -> {SE3()}
   const SE3d sprelast = se3_from7(io.sprelast_c2w), slast = se3_from7(io.slast_c2w), lastF = se3_from7(io.lastF_c2w);
-  const SE3d slast_2_sprelast = se3_mul(se3_inv(sprelast), slast);                       // :343
-  const SE3d lastF_2_slast = se3_mul(se3_inv(slast), lastF);                             // :344
-  const SE3d fh_2_slast = slast_2_sprelast, inv = se3_inv(fh_2_slast);
-  const SE3d cm = se3_mul(inv, lastF_2_slast);
-  tries.push_back(cm);                                                                   // constant motion
-  tries.push_back(se3_mul(se3_mul(inv, inv), lastF_2_slast));                            // double motion (left-associated like the expression :351)
-  { double lg[6]; se3_log(fh_2_slast, lg); for (int i=0;i<6;i++) lg[i] = lg[i]*0.5; tries.push_back(se3_mul(se3_inv(se3_exp(lg)), lastF_2_slast)); }   // half motion
-  tries.push_back(lastF_2_slast);                                                        // zero motion
-  tries.push_back(se3_identity());                                                       // zero motion from KF
-  const double r = (double)0.02f;                                                        // float rotDelta promoted to double in the Quaterniond ctor
-  const double q[26][3] = {{r,0,0},{0,r,0},{0,0,r},{-r,0,0},{0,-r,0},{0,0,-r},{r,r,0},{0,r,r},{r,0,r},{-r,r,0},{0,-r,r},{-r,0,r},{r,-r,0},{0,r,-r},{r,0,-r},
-                           {-r,-r,0},{0,-r,-r},{-r,0,-r},{-r,-r,-r},{-r,-r,r},{-r,r,-r},{-r,r,r},{r,-r,-r},{r,-r,r},{r,r,-r},{r,r,r}};
-  for (int k=0;k<26;k++) tries.push_back(se3_mul(cm, quatT(1, q[k][0], q[k][1], q[k][2])));   // (fh_2_slast^-1 * lastF_2_slast) * dR, left-associated
+  g.fh_2_slast = se3_mul(se3_inv(sprelast), slast);                                      // slast_2_sprelast, assumed equal to fh_2_slast (:343,347)
+  g.lastF_2_slast = se3_mul(se3_inv(slast), lastF);                                      // :344
+  g.inv = se3_inv(g.fh_2_slast); g.cm = se3_mul(g.inv, g.lastF_2_slast);
+  return g;
+}
+static int n_tries(const TryGen& g) { return g.valid ? 31 : 1; }
+static SE3d make_try(const TryGen& g, int i) {
+  if (!g.valid) return se3_identity();
+  switch (i) {
+    case 0: return g.cm;                                                                 // constant motion
+    case 1: return se3_mul(se3_mul(g.inv, g.inv), g.lastF_2_slast);                      // double motion (left-associated like the expression :351)
+    case 2: { double lg[6]; se3_log(g.fh_2_slast, lg); for (int k=0;k<6;k++) lg[k] = lg[k]*0.5; return se3_mul(se3_inv(se3_exp(lg)), g.lastF_2_slast); }   // half motion
+    case 3: return g.lastF_2_slast;                                                      // zero motion
+    case 4: return se3_identity();                                                       // zero motion from KF
+    default: break;
+  }
+  const double r = (double)0.02f;                                                        // float rotDelta promoted to double in the Quaterniond ctor; the loop of :357 runs once
+  static const int q[26][3] = {{1,0,0},{0,1,0},{0,0,1},{-1,0,0},{0,-1,0},{0,0,-1},{1,1,0},{0,1,1},{1,0,1},{-1,1,0},{0,-1,1},{-1,0,1},{1,-1,0},{0,1,-1},{1,0,-1},
+                               {-1,-1,0},{0,-1,-1},{-1,0,-1},{-1,-1,-1},{-1,-1,1},{-1,1,-1},{-1,1,1},{1,-1,-1},{1,-1,1},{1,1,-1},{1,1,1}};
+  const int k = i - 5;
+  return se3_mul(g.cm, quatT(1, q[k][0]*r, q[k][1]*r, q[k][2]*r));                       // (fh_2_slast^-1 * lastF_2_slast) * dR, left-associated
 }
 
 extern "C" int sdv_track_new_coarse_batch(sdv_ctx* c, int n, sdv_track_new_coarse_io* io, const int32_t* cell_order, int max_matches) {
   if (!c || n <= 0 || !io) return SDV_ERR_ARG;
   const float setting_reTrackThreshold = 1.5f;                                           // settings.cpp:130
   const int coarsest = c->levels - 1;
-  struct St { std::vector<SE3d> tries; double achieved[5]; bool haveOneGood, done; SE3d lastF_2_fh; double aff[2]; double flow[3]; int tryIterations; };
+  struct St { TryGen gen; int ntries; SE3d try0; double achieved[5]; bool haveOneGood, done; SE3d lastF_2_fh; double aff[2]; double flow[3]; int tryIterations; };
   std::vector<St> st(n);
   size_t maxTries = 0;
-  for (int k=0;k<n;k++) { St& s = st[k]; make_tries(io[k], s.tries); maxTries = std::max(maxTries, s.tries.size());
+  for (int k=0;k<n;k++) { St& s = st[k]; s.gen = try_gen(io[k]); s.ntries = n_tries(s.gen); s.try0 = make_try(s.gen, 0); maxTries = std::max(maxTries, (size_t)s.ntries);
     for (int i=0;i<5;i++) s.achieved[i] = nan(""); s.haveOneGood = false; s.done = false; s.lastF_2_fh = se3_identity(); s.aff[0] = s.aff[1] = 0; s.flow[0] = s.flow[1] = s.flow[2] = 100; s.tryIterations = 0; }
   std::vector<int> act; std::vector<int32_t> slots, good; std::vector<uint64_t> frames; std::vector<double> T, ab, minRes, lastRes, flow;
   for (size_t i = 0; i < maxTries; i++) {
-    act.clear(); for (int k=0;k<n;k++) if (!st[k].done && i < st[k].tries.size()) act.push_back(k);
+    act.clear(); for (int k=0;k<n;k++) if (!st[k].done && (int)i < st[k].ntries) act.push_back(k);
     if (act.empty()) break;
     const int m = (int)act.size();
     slots.resize(m); frames.resize(m); good.resize(m); T.resize(7*m); ab.resize(2*m); minRes.resize(5*m); lastRes.resize(5*m); flow.resize(3*m);
-    for (int a=0;a<m;a++) { const int k = act[a]; slots[a] = io[k].slot; frames[a] = io[k].frame; se3_to7(st[k].tries[i], &T[7*a]);
+    for (int a=0;a<m;a++) { const int k = act[a]; slots[a] = io[k].slot; frames[a] = io[k].frame; se3_to7(i == 0 ? st[k].try0 : make_try(st[k].gen, (int)i), &T[7*a]);
       ab[2*a] = io[k].aff_last[0]; ab[2*a+1] = io[k].aff_last[1]; for (int l=0;l<5;l++) minRes[5*a+l] = st[k].achieved[l]; }
     int rc = sdv_tracker_track_batch(c, m, slots.data(), frames.data(), T.data(), ab.data(), coarsest, minRes.data(), lastRes.data(), flow.data(), good.data(), nullptr);
     if (rc) return rc;
@@ -66,7 +76,7 @@ extern "C" int sdv_track_new_coarse_batch(sdv_ctx* c, int n, sdv_track_new_coars
   std::vector<double> c2w(7*n), cab(2*n);
   slots.resize(n); frames.resize(n);
   for (int k=0;k<n;k++) { St& s = st[k]; sdv_track_new_coarse_io& o = io[k];
-    if (!s.haveOneGood) { s.flow[0] = s.flow[1] = s.flow[2] = 0; s.aff[0] = o.aff_last[0]; s.aff[1] = o.aff_last[1]; s.lastF_2_fh = s.tries[0]; }   // :464-470
+    if (!s.haveOneGood) { s.flow[0] = s.flow[1] = s.flow[2] = 0; s.aff[0] = o.aff_last[0]; s.aff[1] = o.aff_last[1]; s.lastF_2_fh = s.try0; }   // :464-470
     for (int l=0;l<5;l++) o.lastCoarseRMSE[l] = s.achieved[l];                           // :472
     const SE3d camToTrackingRef = se3_inv(s.lastF_2_fh); const SE3d camToWorld = se3_mul(se3_from7(o.lastF_c2w), camToTrackingRef);   // :475-479
     se3_to7(camToWorld, &c2w[7*k]); cab[2*k] = s.aff[0]; cab[2*k+1] = s.aff[1]; slots[k] = o.slot; frames[k] = o.frame;
