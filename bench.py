@@ -9,7 +9,8 @@ photometric SE(3)+affine LM against the keyframe's LiDAR-depth reference cloud, 
   value   : frames/s with the raw frames already resident in HBM (sdv_frame_build_batch_dev + sdv_tracker_track_batch)
   e2e     : frames/s through the reference-facing C-ABI with HOST buffers: pinned mono8 images (the sensor_msgs/Image wire format the reference
             ingests; the synthetic frames are mono8-exact) H2D every step and pose/residual D2H every step, inside the timed region;
-            e2e_float32 = the same with float images (FrameHessian::makeImages(float*) signature, 4x the PCIe bytes)
+            e2e_float32 = the same with float images (FrameHessian::makeImages(float*) signature, 4x the PCIe bytes);
+            e2e_trackNewCoarse = mono8 upload + the whole FullSystem::trackNewCoarse (sdv_track_new_coarse_batch) per frame
   roofline: the device-resident LM kernel (track_cluster_kernel): algorithmic bytes = 64 B x point evaluations
   cpu_baseline / --impl reference: the CPU restatement (oracle/, "port": the reference cannot be built here) on host cores.
 """
