@@ -52,7 +52,9 @@ def cached_sequence(n, seed, K, wh, **kw):
     clouds = np.empty(n, dtype=object)
     for i in range(n):
         clouds[i] = seq.clouds[i]
-    np.savez_compressed(path, R=seq.R, t=seq.t, images=np.stack(seq.images), clouds=clouds)
+    tmp = path + ".%d.tmp.npz" % os.getpid()                                # atomic publish: several ranks of a multi-GPU bench may render the same sequence at once
+    np.savez_compressed(tmp, R=seq.R, t=seq.t, images=np.stack(seq.images), clouds=clouds)
+    os.replace(tmp, path)
     return seq
 
 
