@@ -33,7 +33,8 @@ struct RpJob {
   int cur_kf_index, backup, nH, nP; long long pt_off; int error;
 };
 struct RpConst { double K[9], Ki[9]; int w[kLevels], h[kLevels]; int levels, ncols, ncells; };
-struct RpScratch { double2* cand_px; float* cand_key; int* cand_cell; int* list; int* count; int* begin; int* cursor; int* out_pt; double2* out_px;
+struct RpScratch { double2* cand_px; float* cand_key; int* cand_cell; unsigned long long* list;   // list: per cell, (key bits << 32) | (frame rank << 27) | point index
+                   int* count; int* begin; int* cursor; int* out_pt; double2* out_px;
                    double* xf; };   // xf[job][host][14]: camToWorld_host^-1 and T_cur_ref = camToWorld_cur^-1 * camToWorld_host (7 doubles each), built by rp_project_kernel
 
 __device__ __forceinline__ void mv3(const double* M, double x, double y, double z, double* o) {
@@ -99,7 +100,10 @@ __global__ void __launch_bounds__(256) rp_scatter_kernel(const RpJob* __restrict
   const int k = S.cand_cell[jb.pt_off + i]; if (k < 0) return;
   const long long cb = (long long)blockIdx.y*C.ncells + k;
   const int pos = atomicAdd(&S.cursor[cb], 1);
-  S.list[jb.pt_off + S.begin[cb] + pos] = i;
+  // sort key of reprojectCell's stable list sort: gradient magnitude (non-negative float: its bit pattern orders like the value), then insertion order
+  // = (close_kfs rank of the host keyframe, index within the map)
+  const unsigned long long key = ((unsigned long long)__float_as_uint(S.cand_key[jb.pt_off + i]) << 32) | ((unsigned long long)jb.frame_rank[jb.map->pts[i].host] << 27) | (unsigned int)i;
+  S.list[jb.pt_off + S.begin[cb] + pos] = key;
 }
 
 // ---------------------------------------------------------------------------------------------------------------- findMatchDirect (one warp)
@@ -239,21 +243,17 @@ __global__ void __launch_bounds__(32*kRpWarps, RP_MATCH_MINB) rp_match_kernel(co
   const int cell = blockIdx.x*kRpWarps + warp; if (cell >= C.ncells) return;
   const RpJob& jb = jobs[blockIdx.y]; const MapDev* __restrict__ m = jb.map;
   const long long cb = (long long)blockIdx.y*C.ncells + cell;
-  const int n = S.count[cb]; const int* __restrict__ lst = S.list + jb.pt_off + S.begin[cb];
+  const int n = S.count[cb]; const unsigned long long* __restrict__ lst = S.list + jb.pt_off + S.begin[cb];
   int found = -1; double2 fpx = make_double2(0, 0);
-  float last_key = -1.f; long long last_rank = -1;                              // keys are >= 0
+  unsigned long long last = 0; bool first = true;
   for (int tries = 0; tries < n; tries++) {
-    // next candidate in (key, insertion rank) order = what the stable list sort of reprojectCell :200 visits
-    float bk = 0.f; long long br = -1; int bi = -1;
-    for (int j = lane; j < n; j += 32) { const int i = lst[j]; const float k = S.cand_key[jb.pt_off + i];
-      const long long r = ((long long)jb.frame_rank[m->pts[i].host] << 32) | (unsigned int)i;
-      const bool after = (k > last_key) || (k == last_key && r > last_rank) || !(k == k);
-      if (!after) continue;
-      if (bi < 0 || k < bk || (k == bk && r < br)) { bk = k; br = r; bi = i; } }
-    for (int o = 16; o > 0; o >>= 1) { const float ok = __shfl_xor_sync(0xffffffffu, bk, o); const long long orr = __shfl_xor_sync(0xffffffffu, br, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi >= 0 && (bi < 0 || ok < bk || (ok == bk && orr < br))) { bk = ok; br = orr; bi = oi; } }
-    if (bi < 0) break;
-    last_key = bk; last_rank = br;
+    // next candidate in (key, insertion rank) order = what the stable list sort of reprojectCell :200 visits: smallest packed key above the last one tried
+    unsigned long long best = ~0ull;
+    for (int j = lane; j < n; j += 32) { const unsigned long long k = lst[j]; if ((first || k > last) && k < best) best = k; }
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o); best = ob < best ? ob : best; }
+    if (best == ~0ull) break;
+    last = best; first = false;
+    const int bi = (int)(best & 0x7ffffffull);
     double2 px = S.cand_px[jb.pt_off + bi];
     if (find_match_direct(jb, C, m->pts[bi], px, smem[warp], lane, S.xf + (size_t)blockIdx.y*kRpMaxHosts*14)) { found = bi; fpx = px; break; }
   }
@@ -312,7 +312,7 @@ int sdv_reproject_grid(sdv_ctx* c, int* n_cols, int* n_rows) {
 }
 
 int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const double* host_T7, const double* host_ab, int nP, const sdv_map_pt* pts) {
-  if (!c || nH < 1 || nH > kRpMaxHosts || !host_frames || !host_T7 || nP < 0 || (nP > 0 && !pts)) return SDV_ERR_ARG;
+  if (!c || nH < 1 || nH > kRpMaxHosts || !host_frames || !host_T7 || nP < 0 || nP >= (1 << 27) || (nP > 0 && !pts)) return SDV_ERR_ARG;   // point index packs into 27 bits of the sort key
   CK(cudaSetDevice(c->device)); RpState* st = rp_state(c);
   if (slot < 0 || slot >= (int)st->maps.size()) return SDV_ERR_ARG;
   MapSlot& m = st->maps[slot];
@@ -342,7 +342,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
   const long long nc = (long long)n_jobs*C.ncells; R.nc = nc;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t o_jobs = 0, o_px = al(o_jobs + (size_t)n_jobs*sizeof(RpJob)), o_key = al(o_px + (size_t)totalP*sizeof(double2)), o_cell = al(o_key + (size_t)totalP*4), o_list = al(o_cell + (size_t)totalP*4),
-         o_count = al(o_list + (size_t)totalP*4), o_begin = al(o_count + (size_t)nc*4), o_cur = al(o_begin + (size_t)nc*4), o_opt = al(o_cur + (size_t)nc*4), o_opx = al(o_opt + (size_t)nc*4),
+         o_count = al(o_list + (size_t)totalP*8), o_begin = al(o_count + (size_t)nc*4), o_cur = al(o_begin + (size_t)nc*4), o_opt = al(o_cur + (size_t)nc*4), o_opx = al(o_opt + (size_t)nc*4),
          o_xf = al(o_opx + (size_t)nc*sizeof(double2)), o_ov = al(o_xf + (size_t)n_jobs*kRpMaxHosts*14*sizeof(double)), o_rj = al(o_ov + (size_t)nc*sizeof(sdv_overlap_pt)), o_no = al(o_rj + (size_t)n_jobs*sizeof(RefineJob)), o_co = al(o_no + (size_t)n_jobs*4),
          total = al(o_co + (size_t)C.ncells*4);
   size_t h_jobs = 0, h_opt = al(h_jobs + (size_t)n_jobs*sizeof(RpJob)), h_opx = al(h_opt + (size_t)nc*4), h_rj = al(h_opx + (size_t)nc*sizeof(double2)), h_no = al(h_rj + (size_t)n_jobs*sizeof(RefineJob)),
@@ -376,7 +376,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
     const double ca = cur_ab ? cur_ab[2*k] : 0.0, cbb = cur_ab ? cur_ab[2*k+1] : 0.0;
     for (int i=0;i<m.nH;i++) { double o2[2]; aff_from_to(m.host_exposure[i], f.exposure, m.host_ab[i][0], m.host_ab[i][1], ca, cbb, o2); j.affLL[i][0] = (float)o2[0]; j.affLL[i][1] = (float)o2[1]; }
   }
-  RpScratch& S = R.S; S.cand_px = (double2*)(db + o_px); S.cand_key = (float*)(db + o_key); S.cand_cell = (int*)(db + o_cell); S.list = (int*)(db + o_list);
+  RpScratch& S = R.S; S.cand_px = (double2*)(db + o_px); S.cand_key = (float*)(db + o_key); S.cand_cell = (int*)(db + o_cell); S.list = (unsigned long long*)(db + o_list);
   S.count = (int*)(db + o_count); S.begin = (int*)(db + o_begin); S.cursor = (int*)(db + o_cur); S.out_pt = (int*)(db + o_opt); S.out_px = (double2*)(db + o_opx); S.xf = (double*)(db + o_xf);
   R.ov = (sdv_overlap_pt*)(db + o_ov); R.rj = (RefineJob*)(db + o_rj); R.n_out_dev = (int*)(db + o_no); R.cell_order_dev = (int*)(db + o_co);
   cudaStream_t s = c->st;
