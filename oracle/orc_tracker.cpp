@@ -132,8 +132,9 @@ void CoarseTracker::setCoarseTrackingRef(const Frame* ref, const RefPoint* pts, 
     std::memcpy(bak, weightSumsl, sizeof(float)*w[lvl]*h[lvl]);
     for (int i=w[lvl]; i<wh; i++) if (bak[i] <= 0) {
       float sum=0, num=0, numn=0;
-      if (bak[i+1+wl] > 0) { sum += idepthl[i+1+wl]; num += bak[i+1+wl]; numn++; }
-      if (bak[i-1-wl] > 0) { sum += idepthl[i-1-wl]; num += bak[i-1-wl]; numn++; }
+      const int nAll = w[lvl]*h[lvl];            // the reference indexes -1 (i = w) and w*h (i = wh-1) here: undefined; treated as empty neighbours
+      if (i+1+wl < nAll && bak[i+1+wl] > 0) { sum += idepthl[i+1+wl]; num += bak[i+1+wl]; numn++; }
+      if (i-1-wl >= 0 && bak[i-1-wl] > 0) { sum += idepthl[i-1-wl]; num += bak[i-1-wl]; numn++; }
       if (bak[i+wl-1] > 0) { sum += idepthl[i+wl-1]; num += bak[i+wl-1]; numn++; }
       if (bak[i-wl+1] > 0) { sum += idepthl[i-wl+1]; num += bak[i-wl+1]; numn++; }
       if (numn>0) { idepthl[i] = sum/numn; weightSumsl[i] = num/numn; }

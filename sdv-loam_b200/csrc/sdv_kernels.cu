@@ -480,10 +480,11 @@ __global__ void cd_dilate_kernel(const float* __restrict__ id_in, const float* _
     int o0, o1, o2, o3;
     if (diag) { o0 = 1+w; o1 = -1-w; o2 = w-1; o3 = -w+1; } else { o0 = 1; o1 = -1; o2 = w; o3 = -w; }
     float sum = 0, num = 0, numn = 0;
-    if (bak[i+o0] > 0) { sum += id_in[i+o0]; num += bak[i+o0]; numn++; }
-    if (bak[i+o1] > 0) { sum += id_in[i+o1]; num += bak[i+o1]; numn++; }
-    if (bak[i+o2] > 0) { sum += id_in[i+o2]; num += bak[i+o2]; numn++; }
-    if (bak[i+o3] > 0) { sum += id_in[i+o3]; num += bak[i+o3]; numn++; }
+    // The reference reads one element past either end of the array for the first / last pixel of the loop (i = w: i-1-w = -1; i = n-w-1: i+1+w = n) —
+    // undefined there; here such a neighbour counts as empty.  Both pixels lie in the 2 px border that the cloud emission drops, so no output depends on it.
+#define CD_NB(o) { const int j = i + (o); if (j >= 0 && j < n && bak[j] > 0) { sum += id_in[j]; num += bak[j]; numn++; } }
+    CD_NB(o0) CD_NB(o1) CD_NB(o2) CD_NB(o3)
+#undef CD_NB
     if (numn > 0) { idv = sum/numn; wsv = num/numn; }
   }
   id_out[i] = idv; ws_out[i] = wsv;
