@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       iters[lvl]++;
       double incn = 0;
       if (tid < 32) {                                        // warp 0: propose the LM step (CoarseTracker.cpp:722-765)
+        __syncwarp();                                        // ctl.H / ctl.b / ctl.lambda were written by lane 0 (finalize_gs) — order them before the other lanes' reads (racecheck)
         const int r = tid & 7;
         const float lambda = ctl.lambda;
         const bool fixA = tc.affineOptModeA < 0, fixB = tc.affineOptModeB < 0;
