@@ -224,6 +224,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
 #pragma unroll
   for (int i = 0; i < kLevels; i++) { evals[i] = 0; iters[i] = 0; accs[i] = 0; }
   __syncthreads();
+  if (C > 1) cluster.sync();                                // every CTA of the cluster must be running before the first distributed-shared-memory write (racecheck)
 
   int evalCount = 0;
   // all threads: evaluate the residual + GN system at ctl.ep for level `lvl`; totals (identical in every CTA) land in tot[]
