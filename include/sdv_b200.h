@@ -178,6 +178,8 @@ typedef struct {
   int32_t  have_one_good, tries, n_matches, refine_iterations, refine_accepts;
 } sdv_track_new_coarse_io;
 int  sdv_track_new_coarse_batch(sdv_ctx* c, int n, sdv_track_new_coarse_io* io, const int32_t* cell_order, int max_matches);
+/* lastF_2_fh_tries[i] of FullSystem.cpp:346-394 for one job (host arithmetic only, no device needed); n_tries = 31, or 1 when the pose history is invalid */
+int  sdv_track_hypothesis(const sdv_track_new_coarse_io* io, int i, double T7_out[7], int* n_tries);
 
 /* device time of the last track / track_batch / calc_res launch in milliseconds (CUDA events on the context stream) */
 float sdv_last_kernel_ms(sdv_ctx* c);

@@ -180,24 +180,29 @@ def reproject_map(w, h, levels, K4, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, 
     return out_pt[:n].copy(), out_px[:n].copy()
 
 
+def track_hypotheses(sprelast_c2w, slast_c2w, lastF_c2w, poses_valid):
+    """lastF_2_fh_tries of FullSystem::trackNewCoarse for a running system (FullSystem.cpp:334-394)."""
+    if not poses_valid:
+        return [np.array([1, 0, 0, 0, 0, 0, 0.0])]
+    slast_2_sprelast = se3_mul(se3_inv(sprelast_c2w), slast_c2w); lastF_2_slast = se3_mul(se3_inv(slast_c2w), lastF_c2w)
+    fh_2_slast = slast_2_sprelast; inv = se3_inv(fh_2_slast); cm = se3_mul(inv, lastF_2_slast)
+    tries = [cm, se3_mul(se3_mul(inv, inv), lastF_2_slast), se3_mul(se3_inv(se3_exp(se3_log(fh_2_slast) * 0.5)), lastF_2_slast), lastF_2_slast,
+             np.array([1, 0, 0, 0, 0, 0, 0.0])]
+    r = float(np.float32(0.02))
+    for q in [(r, 0, 0), (0, r, 0), (0, 0, r), (-r, 0, 0), (0, -r, 0), (0, 0, -r), (r, r, 0), (0, r, r), (r, 0, r), (-r, r, 0), (0, -r, r), (-r, 0, r), (r, -r, 0),
+              (0, r, -r), (r, 0, -r), (-r, -r, 0), (0, -r, -r), (-r, 0, -r), (-r, -r, -r), (-r, -r, r), (-r, r, -r), (-r, r, r), (r, -r, -r), (r, -r, r), (r, r, -r), (r, r, r)]:
+        qq = np.array([1.0, q[0], q[1], q[2]]); qq = qq / np.sqrt(qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3] + qq[0] * qq[0])
+        tries.append(se3_mul(cm, np.concatenate([qq, np.zeros(3)])))
+    return tries
+
+
 def track_new_coarse(tracker, new_frame, K4, kf_frames, kf_T7, kf_ab, map_pts, sprelast_c2w, slast_c2w, lastF_c2w, aff_last, poses_valid, lastCoarseRMSE,
                      cell_order=None, max_matches=400):
     """FullSystem::trackNewCoarse restated for a running system (FullSystem.cpp:283-500, branch :334-395) over the oracle pieces:
     hypotheses :346-388, re-track loop :410-462, fallback :464-470, pose composition :474-479, reprojectMap + structPoseEstimation :481-491.
     `tracker` is an orc.CoarseTracker whose reference is lastF.  Pure-Python control flow (<= 31 tries), all numerics in liborc."""
     w, h, L = tracker.w, tracker.h, tracker.levels
-    if not poses_valid:
-        tries = [np.array([1, 0, 0, 0, 0, 0, 0.0])]
-    else:
-        slast_2_sprelast = se3_mul(se3_inv(sprelast_c2w), slast_c2w); lastF_2_slast = se3_mul(se3_inv(slast_c2w), lastF_c2w)
-        fh_2_slast = slast_2_sprelast; inv = se3_inv(fh_2_slast); cm = se3_mul(inv, lastF_2_slast)
-        tries = [cm, se3_mul(se3_mul(inv, inv), lastF_2_slast), se3_mul(se3_inv(se3_exp(se3_log(fh_2_slast) * 0.5)), lastF_2_slast), lastF_2_slast,
-                 np.array([1, 0, 0, 0, 0, 0, 0.0])]
-        r = float(np.float32(0.02))
-        for q in [(r, 0, 0), (0, r, 0), (0, 0, r), (-r, 0, 0), (0, -r, 0), (0, 0, -r), (r, r, 0), (0, r, r), (r, 0, r), (-r, r, 0), (0, -r, r), (-r, 0, r), (r, -r, 0),
-                  (0, r, -r), (r, 0, -r), (-r, -r, 0), (0, -r, -r), (-r, 0, -r), (-r, -r, -r), (-r, -r, r), (-r, r, -r), (-r, r, r), (r, -r, -r), (r, -r, r), (r, r, -r), (r, r, r)]:
-            qq = np.array([1.0, q[0], q[1], q[2]]); qq = qq / np.sqrt(qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3] + qq[0] * qq[0])
-            tries.append(se3_mul(cm, np.concatenate([qq, np.zeros(3)])))
+    tries = track_hypotheses(sprelast_c2w, slast_c2w, lastF_c2w, poses_valid)
     achieved = np.full(5, np.nan); have = False; flow = np.array([100.0, 100.0, 100.0]); lastF_2_fh = np.array([1, 0, 0, 0, 0, 0, 0.0]); aff = np.zeros(2); n_tries = 0
     for T in tries:
         r = tracker.trackNewestCoarse(new_frame, T, aff_last, L - 1, achieved.copy()); n_tries += 1

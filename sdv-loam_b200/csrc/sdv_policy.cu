@@ -46,6 +46,15 @@ static SE3d make_try(const TryGen& g, int i) {
   return se3_mul(g.cm, quatT(1, q[k][0]*r, q[k][1]*r, q[k][2]*r));                       // (fh_2_slast^-1 * lastF_2_slast) * dR, left-associated
 }
 
+// Host-only helper (no device work): hypothesis i of the re-track loop for one job, so the generation can be checked without a GPU.
+extern "C" int sdv_track_hypothesis(const sdv_track_new_coarse_io* io, int i, double T7_out[7], int* n_tries_out) {
+  if (!io || !T7_out) return SDV_ERR_ARG;
+  const TryGen g = try_gen(*io); const int n = n_tries(g);
+  if (n_tries_out) *n_tries_out = n;
+  if (i < 0 || i >= n) return SDV_ERR_ARG;
+  se3_to7(make_try(g, i), T7_out); return SDV_OK;
+}
+
 extern "C" int sdv_track_new_coarse_batch(sdv_ctx* c, int n, sdv_track_new_coarse_io* io, const int32_t* cell_order, int max_matches) {
   if (!c || n <= 0 || !io) return SDV_ERR_ARG;
   const float setting_reTrackThreshold = 1.5f;                                           // settings.cpp:130
