@@ -226,6 +226,16 @@ def track_new_coarse(tracker, new_frame, K4, kf_frames, kf_T7, kf_ab, map_pts, s
                 n_matches=len(idx), refine_iterations=sp["iterations"], refine_accepts=sp["accepts"], camToWorld_tracked=camToWorld)
 
 
+def struct_pose_hb(w, h, K4, host_T7, pts6, curToWorld7):
+    """calcHandb + calculateRes at one pose: returns (H 6x6, b 6, mean squared pixel error, number of in-frame points)."""
+    L = lib()
+    L.orc_struct_pose_hb.argtypes = [C.c_int, C.c_int, _f32p, C.c_int, _f64p, C.c_int, _f32p, _f64p, _f64p, _f64p, _i32p]; L.orc_struct_pose_hb.restype = C.c_float
+    hT = np.ascontiguousarray(host_T7, np.float64).reshape(-1, 7); p = np.ascontiguousarray(pts6, np.float32).reshape(-1, 6)
+    H = np.zeros(36); b = np.zeros(6); num = np.zeros(1, np.int32)
+    e = L.orc_struct_pose_hb(w, h, np.ascontiguousarray(K4, np.float32), len(hT), hT, len(p), p, np.ascontiguousarray(curToWorld7, np.float64), H, b, num)
+    return H.reshape(6, 6), b, float(e), int(num[0])
+
+
 def struct_pose(w, h, K4, host_T7, pts6, curToWorld7):
     """CoarseTracker::structPoseEstimation restated (orc_refine.cpp).  pts6: (n,6) float32 {u,v,idepth,host,obs_x,obs_y}."""
     L = lib()

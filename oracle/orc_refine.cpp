@@ -6,7 +6,8 @@
 //   CoarseTracker::calcHandb             FullSystem/CoarseTracker.cpp:889-947
 //   CoarseTracker::structPoseEstimation  FullSystem/CoarseTracker.cpp:949-1007
 //   point2world / world2frame / pixel2unit   FullSystem/ResidualProjections.h:61-102
-// Load-bearing quirks kept on purpose: after an accepted step H,b are re-linearised at the OLD pose (:989 before :990), the damping
+// Load-bearing quirks kept on purpose: d_xi_x[4] = 1 + X*d_xi_x[2] and d_xi_y[3] = -(1 + Y*d_xi_y[2]) (:916,:922) evaluate to 1 - (X/Z)^2 and -(1 - (Y/Z)^2), not the
+// derivatives 1 + (X/Z)^2 / -(1 + (Y/Z)^2) (tests/test_oracle_refine.py::test_normal_equations_by_finite_differences); after an accepted step H,b are re-linearised at the OLD pose (:989 before :990), the damping
 // factor is applied to H in place every iteration (so it compounds across rejected steps, :966), the function has no return value.
 #include "orc_tracker.hpp"
 #include <vector>
@@ -117,5 +118,21 @@ float orc_struct_pose(int w, int h, const float K4[4], int nH, const double* hos
   curToWorld7[0]=c2w.q.w; curToWorld7[1]=c2w.q.x; curToWorld7[2]=c2w.q.y; curToWorld7[3]=c2w.q.z; curToWorld7[4]=c2w.t.v[0]; curToWorld7[5]=c2w.t.v[1]; curToWorld7[6]=c2w.t.v[2];
   if (stats2) { stats2[0]=P.iterations; stats2[1]=P.accepts; }
   return P.lastRes;
+}
+// normal equations + mean squared pixel error at one pose (calcHandb :889-947, calculateRes :840-871) — exposed for the finite-difference test
+float orc_struct_pose_hb(int w, int h, const float K4[4], int nH, const double* hostT7, int n, const float* pts6, const double curToWorld7[7], double* H36, double* b6, int* num_out) {
+  PoseRefiner P; P.w = w; P.h = h; P.fx = K4[0]; P.fy = K4[1]; P.cx = K4[2]; P.cy = K4[3];
+  Mat33f Km; std::memset(&Km,0,sizeof(Km)); Km.m[0][0]=K4[0]; Km.m[1][1]=K4[1]; Km.m[0][2]=K4[2]; Km.m[1][2]=K4[3]; Km.m[2][2]=1;
+  Mat33f Ki = inverse3<float,Mat33f>(Km); P.fxi = Ki.m[0][0]; P.fyi = Ki.m[1][1]; P.cxi = Ki.m[0][2]; P.cyi = Ki.m[1][2];
+  for (int k=0;k<nH;k++) { SE3 s; s.q = Quat{hostT7[7*k],hostT7[7*k+1],hostT7[7*k+2],hostT7[7*k+3]}; s.t = Vec3d{{hostT7[7*k+4],hostT7[7*k+5],hostT7[7*k+6]}};
+    P.hostR.push_back(castf(s.rotationMatrix())); P.hostT.push_back(castf(s.t)); }
+  std::vector<OverlapPoint> v(n);
+  for (int i=0;i<n;i++) { v[i].u=pts6[6*i]; v[i].v=pts6[6*i+1]; v[i].idepth=pts6[6*i+2]; v[i].host=(int)pts6[6*i+3]; v[i].obs[0]=pts6[6*i+4]; v[i].obs[1]=pts6[6*i+5]; }
+  SE3 c2w; c2w.q = Quat{curToWorld7[0],curToWorld7[1],curToWorld7[2],curToWorld7[3]}; c2w.t = Vec3d{{curToWorld7[4],curToWorld7[5],curToWorld7[6]}};
+  SE3 w2c = c2w.inverse();
+  for (int i=0;i<36;i++) H36[i]=0; for (int i=0;i<6;i++) b6[i]=0;
+  P.calcHandb(H36, b6, w2c, v);
+  int num; float e = P.calculateRes(w2c, v, num); if (num_out) *num_out = num;
+  return num ? e/num : 0.f;
 }
 }

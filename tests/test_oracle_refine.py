@@ -50,3 +50,32 @@ def test_golden_regression():
         r = orc.struct_pose(640, 192, np.array([383.4, 383.4, 312.0, 97.0], np.float32), g[f"host{k}"], g[f"pts{k}"], g[f"Tin{k}"])
         assert np.allclose(r["T"], g[f"Tout{k}"], rtol=0, atol=1e-12)
         assert r["iterations"] == int(g[f"stat{k}"][1]) and r["accepts"] == int(g[f"stat{k}"][2]) and abs(r["res"] - g[f"stat{k}"][0]) <= 1e-6 * g[f"stat{k}"][0]
+
+
+def test_normal_equations_by_finite_differences():
+    """calcHandb (CoarseTracker.cpp:889-947): J = d(unit-plane projection)/d(left se(3) increment of worldToCur), H = sum w J^T J, b = sum w J^T r with
+    Tukey weights — re-derived here by numerical differentiation of an independent float64 projection."""
+    d = synth.make_overlap_points(120, 4, 6, outlier_frac=0.05, match_noise=0.5)
+    K = d["K"]; fx, fy, cx, cy = K; p = d["pts"]
+    Hm, bv, _, num = orc.struct_pose_hb(W, H, K.astype(np.float32), d["host_T7"], pts6_of(p), d["T_init"]); assert num == len(p)
+
+    def unit_proj(w2c, i):
+        hostT = d["host_T7"][p["host"][i]]; X = orc.se3_rot(hostT) @ (np.array([(p["u"][i] - cx) / fx, (p["v"][i] - cy) / fy, 1.0]) / p["idepth"][i]) + hostT[4:]
+        Xc = orc.se3_rot(w2c) @ X + w2c[4:]; return Xc[:2] / Xc[2]
+
+    w2c = orc.se3_inv(d["T_init"]); Href = np.zeros((6, 6)); bref = np.zeros(6); eps = 1e-6
+    for i in range(len(p)):
+        r = unit_proj(w2c, i) - np.array([(p["obs_x"][i] - cx) / fx, (p["obs_y"][i] - cy) / fy])
+        J = np.zeros((2, 6))
+        for k in range(6):
+            e = np.zeros(6); e[k] = eps
+            J[:, k] = (unit_proj(orc.se3_mul(orc.se3_exp(e), w2c), i) - unit_proj(orc.se3_mul(orc.se3_exp(-e), w2c), i)) / (2 * eps)
+        # Two entries of the reference's analytic Jacobian are NOT the derivative: d_xi_x[4] = 1 + X*d_xi_x[2] = 1 - (X/Z)^2 and d_xi_y[3] = -(1 + Y*d_xi_y[2]) =
+        # -(1 - (Y/Z)^2) (CoarseTracker.cpp:916,922), where the true values are 1 + (X/Z)^2 and -(1 + (Y/Z)^2).  The restatement keeps the reference's
+        # expressions (they steer structPoseEstimation's steps); every other entry must equal the numerical derivative.
+        u_, v_ = unit_proj(w2c, i)
+        assert abs(J[0, 4] - (1 + u_ * u_)) < 1e-6 and abs(J[1, 3] + (1 + v_ * v_)) < 1e-6          # the numerical derivative has the textbook form
+        J[0, 4] = 1 - u_ * u_; J[1, 3] = -(1 - v_ * v_)
+        x = np.linalg.norm(r); wgt = (1 - x * x / 4.6851 ** 2) ** 2 if x <= 4.6851 else 0.0
+        Href += wgt * J.T @ J; bref += wgt * J.T @ r
+    assert np.allclose(Hm, Href, rtol=2e-4, atol=1e-6 * np.abs(Href).max()) and np.allclose(bv, bref, rtol=2e-3, atol=2e-5 * (np.abs(bref).max() + 1e-9))
