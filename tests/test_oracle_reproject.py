@@ -66,3 +66,28 @@ def test_backproject_single_host_and_two_keyframe_rule(scene):
     two = pts[pts["host"] < 2]
     idx2, px2 = orc.reproject_map(w, h, 4, SMALL_K, frames[:2], host_T7[:2], host_ab[:2], cur, cur_T7, [0.0, 0.0], two)
     assert len(idx2) > 20
+
+
+def test_alignment_recovers_known_subpixel_shift():
+    """findMatchDirect on analytic images: cur(x, y) = ref(x - dx, y - dy), identical camera poses (affine warp = identity, search level 0).
+    align2D must move the projected pixel by (dx, dy); align1D (EDGELET) along the reference gradient direction."""
+    import sdv_loam_b200  # noqa
+    w, h = 320, 192; L = 3; K = (300.0, 300.0, 159.5, 95.5)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    tex = lambda x, y: 120 + 50 * np.sin(x / 5.3) * np.cos(y / 6.1) + 30 * np.sin((x + 2 * y) / 9.7)
+    T = np.array([1, 0, 0, 0, 0, 0, 0.0])
+    for (dx, dy) in ((0.37, -0.22), (-0.6, 0.45)):
+        ref = orc.Frame(tex(xx, yy).astype(np.float32), L); cur = orc.Frame(tex(xx - dx, yy - dy).astype(np.float32), L)
+        pts = np.zeros(40, [("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("type", np.int32)])
+        rng = np.random.default_rng(3)
+        pts["u"] = rng.integers(2, 10, 40) + 30 * (np.arange(40) % 10); pts["v"] = rng.integers(2, 10, 40) + 40 * (np.arange(40) // 10) + 20
+        pts["idepth"] = 0.1; pts["type"] = 0
+        idx, px = orc.reproject_map(w, h, L, K, [ref, ref, ref], np.stack([T] * 3), np.zeros((3, 2)), cur, T, [0.0, 0.0], pts)   # 3 keyframes: reference patch = host
+        assert len(idx) >= 30
+        err = px - np.stack([pts["u"][idx] + dx, pts["v"][idx] + dy], 1)
+        assert np.abs(err).max() < 0.1 and np.median(np.abs(err)) < 0.03, np.abs(err).max()   # uint8 patch truncation + 0.03 px convergence threshold
+    # edgelets on an image that varies along x only: 1-D alignment recovers dx and leaves y untouched
+    dx = 0.41; ref = orc.Frame(tex(xx, 0 * yy + 7).astype(np.float32), L); cur = orc.Frame(tex(xx - dx, 0 * yy + 7).astype(np.float32), L)
+    pts["type"] = 1
+    idx, px = orc.reproject_map(w, h, L, K, [ref, ref, ref], np.stack([T] * 3), np.zeros((3, 2)), cur, T, [0.0, 0.0], pts)
+    assert len(idx) >= 25 and np.abs(px[:, 0] - (pts["u"][idx] + dx)).max() < 0.1 and np.abs(px[:, 1] - pts["v"][idx]).max() < 1e-6
