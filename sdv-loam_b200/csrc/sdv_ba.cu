@@ -4,6 +4,7 @@
 #include "../../include/sdv_b200.h"
 #include "sdv_ctx.cuh"
 #include "sdv_ba.cuh"
+#include <stdlib.h>
 #include <cstring>
 #include <cstddef>
 #include <vector>
@@ -19,6 +20,7 @@ void ba_destroy(sdv_ctx* c) {
     cudaFree(b->hdr); cudaFreeHost(b->hdr_host); cudaFree(b->pool); cudaFree(b->partials); cudaFree(b->thbuf); cudaFree(b->thcount); delete b; }
   c->ba_windows.clear(); c->ba = nullptr;
   cudaFree(c->ba_wins_dev); cudaFreeHost(c->ba_wins_host); c->ba_wins_dev = c->ba_wins_host = nullptr;
+  if (c->ba_graph) { cudaGraphExecDestroy(c->ba_graph); c->ba_graph = nullptr; }
 }
 }
 
@@ -231,36 +233,57 @@ int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOpt
   }
   const BAWinDev* wins; int maxP, maxR; { int rcw = ba_wins(c, n, bs.data(), &wins, &maxP, &maxR); if (rcw) return rcw; }
   { int rcj = join_ingest(c); if (rcj) return rcj; }
-  CK(cudaEventRecord(c->ev0, st));
-  launch_ba_reset_oob(wins, n, maxR, st);
-  launch_ba_linearize(wins, n, maxR, 0, GATE_ALWAYS, st);
-  launch_ba_energies(wins, n, GATE_ALWAYS, st);
-  launch_ba_decide(wins, n, 0, st);
-  launch_ba_apply(wins, n, maxR, GATE_ALWAYS, st); c->launches += 6;
-  for (int iteration = 0; iteration < maxIts; iteration++) {
-    launch_ba_backup(wins, n, maxP, GATE_ACTIVE, st);
-    launch_ba_accumulate(wins, n, maxP, GATE_ACTIVE, st);
-    launch_ba_solve(wins, n, maxP, 0, 0.0, 1, GATE_ACTIVE, st);
-    launch_ba_step(wins, n, 1.0f, 0, GATE_ACTIVE, st);
-    launch_ba_linearize(wins, n, maxR, 0, GATE_ACTIVE, st);
-    launch_ba_energies(wins, n, GATE_ACTIVE, st);
-    launch_ba_decide(wins, n, 1, st);
-    launch_ba_apply(wins, n, maxR, GATE_ACTIVE | GATE_APPLY, st);
-    launch_ba_step(wins, n, 1.0f, 1, GATE_ACTIVE | GATE_RELOAD, st);          // loadSateBackup
-    launch_ba_linearize(wins, n, maxR, 0, GATE_ACTIVE | GATE_RELOAD, st);
-    launch_ba_energies(wins, n, GATE_ACTIVE | GATE_RELOAD, st);
-    launch_ba_decide(wins, n, 2, st); c->launches += 19;
-    if (maxIts > 8 && iteration >= 5 && (iteration % 4) == 1) {              // long schedules (tiny windows at start-up): poll for early exit
-      bool any = false;
-      for (int i=0;i<n;i++) { CK(cudaMemcpyAsync(&bs[i]->hdr_host->flags, &bs[i]->hdr->flags, sizeof(int), cudaMemcpyDeviceToHost, st)); }
-      CK(cudaStreamSynchronize(st));
-      for (int i=0;i<n;i++) any = any || (bs[i]->hdr_host->flags & BA_ACTIVE);
-      if (!any) break;
+  // The schedule is fixed (decisions are taken on the device and gate the launches), so for the usual short schedules it is captured once into a CUDA graph and
+  // replayed: one graph launch instead of 6 + 19 per iteration + 5 kernel launches — what a single window (launch-latency bound) pays for.
+  auto schedule = [&](cudaStream_t st, bool poll) -> int {
+    launch_ba_reset_oob(wins, n, maxR, st);
+    launch_ba_linearize(wins, n, maxR, 0, GATE_ALWAYS, st);
+    launch_ba_energies(wins, n, GATE_ALWAYS, st);
+    launch_ba_decide(wins, n, 0, st);
+    launch_ba_apply(wins, n, maxR, GATE_ALWAYS, st);
+    for (int iteration = 0; iteration < maxIts; iteration++) {
+      launch_ba_backup(wins, n, maxP, GATE_ACTIVE, st);
+      launch_ba_accumulate(wins, n, maxP, GATE_ACTIVE, st);
+      launch_ba_solve(wins, n, maxP, 0, 0.0, 1, GATE_ACTIVE, st);
+      launch_ba_step(wins, n, 1.0f, 0, GATE_ACTIVE, st);
+      launch_ba_linearize(wins, n, maxR, 0, GATE_ACTIVE, st);
+      launch_ba_energies(wins, n, GATE_ACTIVE, st);
+      launch_ba_decide(wins, n, 1, st);
+      launch_ba_apply(wins, n, maxR, GATE_ACTIVE | GATE_APPLY, st);
+      launch_ba_step(wins, n, 1.0f, 1, GATE_ACTIVE | GATE_RELOAD, st);          // loadSateBackup
+      launch_ba_linearize(wins, n, maxR, 0, GATE_ACTIVE | GATE_RELOAD, st);
+      launch_ba_energies(wins, n, GATE_ACTIVE | GATE_RELOAD, st);
+      launch_ba_decide(wins, n, 2, st);
+      if (poll && maxIts > 8 && iteration >= 5 && (iteration % 4) == 1) {        // long schedules (tiny windows at start-up): poll for early exit
+        bool any = false;
+        for (int i=0;i<n;i++) { CK(cudaMemcpyAsync(&bs[i]->hdr_host->flags, &bs[i]->hdr->flags, sizeof(int), cudaMemcpyDeviceToHost, st)); }
+        CK(cudaStreamSynchronize(st));
+        for (int i=0;i<n;i++) any = any || (bs[i]->hdr_host->flags & BA_ACTIVE);
+        if (!any) break;
+      }
     }
+    launch_ba_reanchor(wins, n, maxP, st);
+    launch_ba_linearize(wins, n, maxR, 1, GATE_ALWAYS, st);
+    launch_ba_decide(wins, n, 3, st);
+    return SDV_OK;
+  };
+  c->launches += 6 + 19*(long long)maxIts + 5;
+  if (maxIts <= 8 && !getenv("SDV_BA_NO_GRAPH")) {
+    if (!c->ba_graph || c->bag_wins != (const void*)wins || c->bag_n != n || c->bag_maxP != maxP || c->bag_maxR != maxR || c->bag_its != maxIts) {
+      if (c->ba_graph) { cudaGraphExecDestroy(c->ba_graph); c->ba_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      schedule(st, false);
+      CK(cudaStreamEndCapture(st, &g));
+      CK(cudaGraphInstantiate(&c->ba_graph, g, 0)); cudaGraphDestroy(g);
+      c->bag_wins = wins; c->bag_n = n; c->bag_maxP = maxP; c->bag_maxR = maxR; c->bag_its = maxIts;
+    }
+    CK(cudaEventRecord(c->ev0, st));
+    CK(cudaGraphLaunch(c->ba_graph, st));
+  } else {
+    CK(cudaEventRecord(c->ev0, st));
+    { int rcs = schedule(st, true); if (rcs) return rcs; }
   }
-  launch_ba_reanchor(wins, n, maxP, st);
-  launch_ba_linearize(wins, n, maxR, 1, GATE_ALWAYS, st);
-  launch_ba_decide(wins, n, 3, st); c->launches += 5;
   CK(cudaEventRecord(c->ev1, st));
   for (int i=0;i<n;i++) { const size_t off = offsetof(BAHeader, energyP), len = sizeof(BAHeader) - off;
     CK(cudaMemcpyAsync((char*)bs[i]->hdr_host + off, (char*)bs[i]->hdr + off, len, cudaMemcpyDeviceToHost, st)); }

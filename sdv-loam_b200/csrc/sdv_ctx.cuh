@@ -49,6 +49,8 @@ struct sdv_ctx {
   sdv::RpState* rp = nullptr;                   // map slots + scratch of the Reprojector path (sdv_reproject.cu)
   sdv::BAState* ba = nullptr;                   // selected back-end window
   std::vector<sdv::BAState*> ba_windows; void* ba_wins_dev = nullptr; void* ba_wins_host = nullptr; int ba_wins_cap = 0;
+  // the fixed Gauss-Newton launch schedule of sdv_ba_optimize_batch as a CUDA graph, keyed by what the launches depend on
+  cudaGraphExec_t ba_graph = nullptr; const void* bag_wins = nullptr; int bag_n = 0, bag_maxP = 0, bag_maxR = 0, bag_its = 0;
   char err[512];
 };
 
