@@ -87,3 +87,30 @@ def main_refine():
 
 if __name__ == "__main__":
     main_refine()
+
+
+def main_handover():
+    """Keyframe hand-over + reprojection fixtures (§8 b9, a10): frozen oracle outputs on the small window / sequence."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import cached_sequence
+    seq = cached_sequence(5, 3000, K, WH)
+    win = synth.make_ba_window(seq, [0, 1, 2, 3, 4], n_per_frame=120, seed=5, pose_noise=(0.004, 0.0003), match_noise=0.15, prior_scale=1e-2)
+    frames = [orc.Frame(seq.images[k], 4) for k in win["kf_idx"]]
+    ba = orc.BAWindow(win, frames); ba.optimize(4)
+    sel = (win["host"] == 0).astype(np.int32); sel[::7] = 1; sel[win["host"] == win["nF"] - 1] = 0
+    st = ba.flagPointsForRemoval(sel); m = ba.marginalizePointsF(st); HM1, bM1 = ba.prior()
+    ba.marginalizeFrame(0); HM2, bM2 = ba.prior()
+    pts, hT, hab = synth.make_map(seq, [0, 1, 2, 3], n_per_frame=250, seed=2)
+    cur_T7 = np.concatenate([synth._quat_from_R(seq.R[4]), seq.t[4]]); cur_T7[4:] += [0.02, -0.01, 0.03]
+    order = np.random.default_rng(9).permutation(int(np.ceil(WH[0] / 25)) * int(np.ceil(WH[1] / 25))).astype(np.int32)
+    idx, px = orc.reproject_map(WH[0], WH[1], 4, K, frames[:4], hT, hab, frames[4], cur_T7, [0.0, 0.0], pts, cell_order=order, max_matches=60)
+    p6 = np.stack([pts["u"][idx], pts["v"][idx], pts["idepth"][idx], pts["host"][idx].astype(np.float32), px[:, 0].astype(np.float32), px[:, 1].astype(np.float32)], 1).astype(np.float32)
+    sp = orc.struct_pose(WH[0], WH[1], np.array(K, np.float32), hT, p6, cur_T7)
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "handover_small.npz"), sel=sel, status=st, M=m["M"], Msc=m["Msc"], HM1=HM1, bM1=bM1, HM2=HM2, bM2=bM2,
+                        map_pts=np.stack([pts["u"], pts["v"], pts["idepth"], pts["host"].astype(np.float32), pts["type"].astype(np.float32)], 1), map_T7=hT, cur_T7=cur_T7, order=order,
+                        match_idx=idx, match_px=px, refined_T7=sp["T"], refine_stats=np.array([sp["iterations"], sp["accepts"]]))
+    print("handover:", np.bincount(st, minlength=3), len(idx), sp["iterations"], sp["accepts"])
+
+
+if __name__ == "__main__":
+    main_handover()

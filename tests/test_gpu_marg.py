@@ -104,3 +104,30 @@ def test_marginalize_nothing_and_two_frame_window():
     with pytest.raises(api.SdvError):
         gb.marginalizeFrame(0)                                                    # a window keeps at least one keyframe
     ctx.close()
+
+
+def test_golden_handover_on_gpu():
+    """CUDA path against the committed fixture (tests/golden/handover_small.npz): marginalisation prior before/after frame elimination, reprojection matches,
+    refined pose — without running the oracle."""
+    import os
+    api, synth = _mods()
+    from conftest import SMALL_K, SMALL_WH
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "handover_small.npz")); b = np.load(os.path.join(here, "golden", "ba_small.npz"))
+    win = {k[4:]: b[k] for k in b.files if k.startswith("win_")}; win["nF"] = int(win["nF"]); win["wh"] = SMALL_WH; win["kf_idx"] = list(range(win["nF"]))
+    w, h = SMALL_WH; ctx = api.Context(SMALL_K, w, h, max_frames=8)
+    for k in range(5):
+        ctx.makeImages(500 + k, b["images"][k].astype(np.float32))
+    gb = api.EnergyFunctional(ctx, win, [500 + k for k in range(5)]); gb.optimize(4)
+    st = gb.flagPointsForRemoval(g["sel"]); assert np.array_equal(st, g["status"])
+    m = gb.marginalizePointsF(); assert _same(m["M"], g["M"]) and _same(m["Msc"], g["Msc"])
+    H1, b1 = gb.prior(); assert _same(H1, g["HM1"]) and _same(b1, g["bM1"])
+    gb.marginalizeFrame(0); H2, b2 = gb.prior(); assert _same(H2, g["HM2"]) and _same(b2, g["bM2"])
+    mp = g["map_pts"]; pts = np.zeros(len(mp), api.MAP_PT_DTYPE)
+    pts["u"], pts["v"], pts["idepth"], pts["host"], pts["type"] = mp[:, 0], mp[:, 1], mp[:, 2], mp[:, 3].astype(np.int32), mp[:, 4].astype(np.int32)
+    rp = api.Reprojector(ctx); rp.setMap(0, [500, 501, 502, 503], g["map_T7"], None, pts)
+    idx, px = rp.reprojectMap(0, 504, g["cur_T7"], cell_order=g["order"], max_matches=60)
+    assert np.array_equal(idx, g["match_idx"]) and np.array_equal(px, g["match_px"])
+    r = rp.refineBatch([0], [504], g["cur_T7"][None], cell_order=g["order"], max_matches=60)
+    assert (int(r["iterations"][0]), int(r["accepts"][0])) == tuple(int(x) for x in g["refine_stats"]) and np.abs(r["T"][0] - g["refined_T7"]).max() < 1e-9
+    ctx.close()

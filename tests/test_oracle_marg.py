@@ -111,3 +111,28 @@ def test_marginalize_frame_is_a_schur_complement(window, idx):
     assert H2.shape == (N - 6, N - 6) and np.array_equal(H2, H2.T)
     sc = np.abs(ref).max()
     assert np.allclose(H2, 0.5 * (ref + ref.T), rtol=1e-7, atol=1e-9 * sc) and np.allclose(b2, refb, rtol=1e-5, atol=1e-7 * (1 + np.abs(refb).max()))   # cancellation: cond(D) ~ 1e5
+
+
+def _golden_setup():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "handover_small.npz"))
+    b = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ba_small.npz"))
+    win = {k[4:]: b[k] for k in b.files if k.startswith("win_")}; win["nF"] = int(win["nF"]); win["wh"] = SMALL_WH; win["kf_idx"] = list(range(win["nF"]))
+    imgs = [b["images"][k].astype(np.float32) for k in range(5)]
+    return g, win, imgs
+
+
+def test_golden_handover_regression():
+    """tests/golden/handover_small.npz pins the oracle's keyframe hand-over and reprojection outputs (make_golden.py::main_handover) against drift."""
+    g, win, imgs = _golden_setup()
+    frames = [orc.Frame(im, 4) for im in imgs]
+    ba = orc.BAWindow(win, frames); ba.optimize(4)
+    st = ba.flagPointsForRemoval(g["sel"]); assert np.array_equal(st, g["status"])
+    m = ba.marginalizePointsF(st); assert np.array_equal(m["M"], g["M"]) and np.array_equal(m["Msc"], g["Msc"])
+    H1, b1 = ba.prior(); assert np.array_equal(H1, g["HM1"]) and np.array_equal(b1, g["bM1"])
+    ba.marginalizeFrame(0); H2, b2 = ba.prior(); assert np.array_equal(H2, g["HM2"]) and np.array_equal(b2, g["bM2"])
+    mp = g["map_pts"]; pts = np.zeros(len(mp), [("u", np.float32), ("v", np.float32), ("idepth", np.float32), ("host", np.int32), ("type", np.int32)])
+    pts["u"], pts["v"], pts["idepth"], pts["host"], pts["type"] = mp[:, 0], mp[:, 1], mp[:, 2], mp[:, 3].astype(np.int32), mp[:, 4].astype(np.int32)
+    idx, px = orc.reproject_map(SMALL_WH[0], SMALL_WH[1], 4, SMALL_K, frames[:4], g["map_T7"], np.zeros((4, 2)), frames[4], g["cur_T7"], [0.0, 0.0], pts,
+                                cell_order=g["order"], max_matches=60)
+    assert np.array_equal(idx, g["match_idx"]) and np.array_equal(px, g["match_px"])
