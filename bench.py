@@ -12,6 +12,8 @@ photometric SE(3)+affine LM against the keyframe's LiDAR-depth reference cloud, 
             e2e_float32 = the same with float images (FrameHessian::makeImages(float*) signature, 4x the PCIe bytes);
             e2e_trackNewCoarse = mono8 upload + the whole FullSystem::trackNewCoarse (sdv_track_new_coarse_batch) per frame
   roofline: the device-resident LM kernel (track_cluster_kernel): algorithmic bytes = 64 B x point evaluations
+  refine  : reprojectMap + structPoseEstimation (sdv_tracker_refine_batch) on resident data; ba: FullSystem::optimize on resident 7-keyframe windows
+            (sdv_ba_optimize_batch); combined: the three legs folded into one frames/s figure (tracking + refinement every frame, BA every kf_every-th)
   cpu_baseline / --impl reference: the CPU restatement (oracle/, "port": the reference cannot be built here) on host cores.
 """
 from __future__ import annotations
