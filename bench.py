@@ -146,22 +146,31 @@ class CpuArm:
         self.rngs = [np.random.default_rng(100 + i) for i in range(threads)]
         self.count = [0] * threads
 
-    def _work(self, i, n_frames, budget_s):
-        orc = self.orc; tr = self.trackers[i][1]; rng = self.rngs[i]
-        t0 = time.perf_counter(); done = 0
-        while done < n_frames:
-            k = 1 + self.count[i] % (N_FRAMES - 1); self.count[i] += 1
-            fk = orc.Frame(self.imgs[k], self.L)                              # FrameHessian::makeImages
-            d = np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.002, 3)])
-            tr.trackNewestCoarse(fk, orc.se3_mul(orc.se3_exp(d), self.gts[k]), [0.0, 0.0], self.L - 1)
-            done += 1
-            if budget_s is not None and time.perf_counter() - t0 > budget_s:
-                break
+    def _inits(self, i, n):
+        """initial guesses for the next n frames of thread i (same distribution as the GPU arm's), drawn before the clock starts"""
+        orc = self.orc; rng = self.rngs[i]; out = np.zeros((n, 7))
+        for f in range(n):
+            k = 1 + (self.count[i] + f) % (N_FRAMES - 1)
+            out[f] = orc.se3_mul(orc.se3_exp(np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.002, 3)])), self.gts[k])
+        return out
+
+    def _work(self, i, n_frames, budget_s, inits):
+        """n_frames x (FrameHessian::makeImages + trackNewestCoarse) inside ONE C call (orc_bench_track_loop): the thread spends its time in the CPU path,
+        not in the interpreter, and the GIL is released throughout — a per-frame Python loop throttled 128 threads to a few frames/s each."""
+        L = self.orc.lib(); tr = self.trackers[i][1]
+        L.orc_bench_track_loop.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+        w, h = self.synth.KITTI_WH
+        ptrs = (ctypes.c_void_p * (N_FRAMES - 1))(*[self.imgs[k].ctypes.data for k in range(1, N_FRAMES)])
+        done = L.orc_bench_track_loop(tr.p, w, h, self.L, ptrs, N_FRAMES - 1, self.count[i] % (N_FRAMES - 1), len(inits), inits, float(budget_s or 0.0), None, None)
+        self.count[i] += done
         return done
 
     def run(self, frames_per_thread, budget_s=None):
         res = [0] * self.threads
-        def job(i): res[i] = self._work(i, frames_per_thread, budget_s)
+        n = min(frames_per_thread, 4096)
+        inits = [self._inits(i, n) for i in range(self.threads)]
+        def job(i): res[i] = self._work(i, n, budget_s, inits[i])
         th = [threading.Thread(target=job, args=(i,)) for i in range(self.threads)]
         t0 = time.perf_counter()
         for t in th: t.start()

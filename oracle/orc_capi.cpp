@@ -173,3 +173,24 @@ int  orc_ba_dim(void* p) { return ((BAWindow*)p)->dim(); }
 void orc_ba_get_prior(void* p, double* HM, double* bM) { BAWindow* b=(BAWindow*)p; std::copy(b->HM.begin(), b->HM.end(), HM); std::copy(b->bM.begin(), b->bM.end(), bM); }
 void orc_ba_get_res_to_zero(void* p, float* r2, int* isLin) { BAWindow* b=(BAWindow*)p; for (size_t i=0;i<b->res.size();i++) { r2[2*i]=b->res[i].res_toZeroF[0]; r2[2*i+1]=b->res[i].res_toZeroF[1]; isLin[i]=b->res[i].isLinearized; } }
 }
+
+// ---- timing loop of the CPU arm (bench.py cpu_baseline / --impl reference): n_frames x { FrameHessian::makeImages ; CoarseTracker::trackNewestCoarse } in ONE call, so
+// that a host thread spends its time in this code and not in the Python interpreter (the GIL is released for the whole call).  imgs: n_imgs level-0 images that are
+// tracked in turn starting at `start`; inits7: one initial guess per frame.  Stops early after budget_s seconds (<= 0: no budget).  Returns the frames done.
+#include <time.h>
+extern "C" int orc_bench_track_loop(void* t, int w, int h, int levels, const float* const* imgs, int n_imgs, int start, int n_frames, const double* inits7, double budget_s,
+                                    double* last_T7, int* good_count) {
+  CoarseTracker* T = (CoarseTracker*)t; timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+  const double nanv = std::nan(""); const double minRes[5] = {nanv, nanv, nanv, nanv, nanv};
+  int done = 0, good = 0;
+  for (int f = 0; f < n_frames; f++) {
+    Frame fk; fk.makeImages(imgs[(start + f) % n_imgs], w, h, levels);
+    SE3 s = se3_from(inits7 + 7*(size_t)f); AffLight aff; aff.a = 0; aff.b = 0;
+    if (T->trackNewestCoarse(&fk, s, aff, levels-1, minRes)) good++;
+    if (last_T7) se3_to(s, last_T7);
+    done++;
+    if (budget_s > 0) { timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); if ((t1.tv_sec - t0.tv_sec) + 1e-9*(t1.tv_nsec - t0.tv_nsec) > budget_s) break; }
+  }
+  if (good_count) *good_count = good;
+  return done;
+}
