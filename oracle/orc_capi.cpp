@@ -183,8 +183,10 @@ extern "C" int orc_bench_track_loop(void* t, int w, int h, int levels, const flo
   CoarseTracker* T = (CoarseTracker*)t; timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
   const double nanv = std::nan(""); const double minRes[5] = {nanv, nanv, nanv, nanv, nanv};
   int done = 0, good = 0;
+  Frame fk;                                       // one frame object per thread, buffers reused (the reference allocates a FrameHessian per frame; with one process and
+                                                  // many threads the page faults of fresh 10 MB pyramids serialise on the kernel's mmap lock, which is not the path under test)
   for (int f = 0; f < n_frames; f++) {
-    Frame fk; fk.makeImages(imgs[(start + f) % n_imgs], w, h, levels);
+    fk.makeImages(imgs[(start + f) % n_imgs], w, h, levels);
     SE3 s = se3_from(inits7 + 7*(size_t)f); AffLight aff; aff.a = 0; aff.b = 0;
     if (T->trackNewestCoarse(&fk, s, aff, levels-1, minRes)) good++;
     if (last_T7) se3_to(s, last_T7);
