@@ -45,3 +45,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import orc" not in txt and "liborc" not in txt and "oracle/" not in txt.replace("independent of oracle/", ""), f
+
+
+def test_null_context_is_an_argument_error_everywhere():
+    """Error behaviour of the boundary: every entry that takes a context returns SDV_ERR_ARG (-1) for a NULL context instead of crashing (the reference's asserts
+    become error codes).  Runs in a child process so that a regression cannot take the test session down."""
+    import re, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "sdv_b200.h")).read()
+    protos = re.findall(r'^\s*int\s+(sdv_\w+)\s*\(\s*sdv_ctx\*\s*c?\s*([^;]*)\)\s*;', hdr, re.M | re.S)
+    assert len(protos) >= 40
+    calls = [(n, 1 + (rest.count(",") if rest.strip() else 0)) for n, rest in protos]
+    code = textwrap.dedent('''
+        import ctypes as C, sys
+        L = C.CDLL(sys.argv[1]); bad = []
+        for item in sys.argv[2:]:
+            name, nargs = item.split(":"); f = getattr(L, name); f.restype = C.c_int
+            rc = f(*[C.c_void_p(0) for _ in range(int(nargs))])
+            if rc != -1: bad.append((name, rc))
+        print("BAD", bad) if bad else print("OK")
+    ''')
+    lib = os.path.join(root, "sdv-loam_b200", "libsdv_b200.so")
+    out = subprocess.run([sys.executable, "-c", code, lib] + [f"{n}:{k}" for n, k in calls], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "OK", (out.stdout[-500:], out.stderr[-500:])
