@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
+WORKLOAD = "S-KITTI tracker step: %d resident sequences/GPU x 1 frame (1200x360 crop of 1241x376, 4 pyramid levels, %d LiDAR-depth splats -> ~10k reference points at level 0), batched mode"
 ALG_BYTES_PER_EVAL = 64          # 16 B point + 4 texels x 12 B  
 N_FRAMES = 4                     # frame 0 = keyframe, frames 1..3 tracked against it in turn
 
@@ -326,7 +327,8 @@ def main():
         line = {"impl": "reference", "metric": "frames/sec (KITTI 1241x376 + 64-beam): makeImages + trackNewestCoarse per frame", "value": fps, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": min(W, 3), "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "S-KITTI tracker step (1200x360, 4 pyramid levels, %d LiDAR-depth splats)" % args.points, "frames_per_step": cores * per},
+                "config": {"workload": WORKLOAD % (args.seqs, args.points), "frames_per_step": cores * per,
+                           "note": "same workload definition as the B200 arm; each CPU step is a bounded sample of it: %d threads x %d frames, one sequence per thread" % (cores, per)},
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d steps x %d threads x %d frames, one sequence per thread; oracle/ CPU restatement (g++ -O3, no FMA) — the reference binary cannot be built here (no Eigen3/Boost/ROS)" % (steps, cores, per)},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -498,7 +500,7 @@ def main():
         "value": world * B * K / t_value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "S-KITTI tracker step: %d resident sequences/GPU x 1 frame (1200x360 crop of 1241x376, 4 pyramid levels, %d LiDAR-depth splats -> ~10k reference points at level 0), batched mode" % (B, args.points),
+        "config": {"workload": WORKLOAD % (B, args.points),
                    "sequences_per_gpu": B, "global_batch_frames": world * B, "parallelism": "seq-shard x%d (no data-path collective)" % world,
                    "l2_policy": "inputs larger than L2: %.1f GB of per-sequence pyramids+clouds per step vs 126 MB L2" % (B * 9.3e-3),
                    "init": "ground truth perturbed N(4cm, 0.002rad) (constant-motion prediction error)",
