@@ -133,6 +133,10 @@ int  sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint
 typedef struct { float u, v, idepth; int32_t host; int32_t type; } sdv_map_pt;
 int  sdv_reproject_grid(sdv_ctx* c, int* n_cols, int* n_rows);
 int  sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const double* host_T7, const double* host_ab, int nP, const sdv_map_pt* pts);
+/* A resident map slot (and a resident BA window, below) REFERENCES the device images of its keyframes: while it does, sdv_frame_release /
+ * re-uploading one of those handles returns SDV_ERR_STATE instead of handing the storage to another frame under the reader.  sdv_map_set on
+ * the same slot replaces the references; sdv_map_clear drops them (the FrameHessian destructor path of a marginalised keyframe). */
+int  sdv_map_clear(sdv_ctx* c, int slot);
 int  sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, const double* cur_T7, const double* cur_ab,
                              const int32_t* cur_kf_index, const int32_t* only_host, const int32_t* backup, const int32_t* cell_order, int max_matches,
                              int32_t* n_out, int32_t* out_pt, double* out_px);
@@ -226,6 +230,7 @@ int  sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* itera
  * set_ / get_ / step-wise calls address (default 0); sdv_ba_optimize_batch runs FullSystem::optimize on n windows at once — every
  * kernel is launched once for all windows and the accept/reject/break decisions are taken on the device. */
 int  sdv_ba_select(sdv_ctx* c, int window);
+int  sdv_ba_clear(sdv_ctx* c);               /* empty the selected window and drop its references to keyframe images (see sdv_map_clear) */
 int  sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out);
 /* read-back of what the reference leaves in FrameHessian/CalibHessian, PointHessian/EFPoint, PointFrameResidual/EFResidual, EnergyFunctional */
 int  sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* step10, float* frameEnergyTH, double* PRE_worldToCam7,

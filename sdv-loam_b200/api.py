@@ -112,7 +112,8 @@ class Context:
         self.p = _vp()
         rc = LIB.sdv_create(C.byref(cal), w, h, self.levels, C.byref(s), device, C.byref(self.p))
         if rc != 0:
-            msg = LIB.sdv_last_error(self.p).decode() if self.p else "no CUDA device / library"
+            msg = LIB.sdv_last_error(None).decode()      # no context exists after a failed create: the library keeps the message per thread
+            self.p = None
             raise SdvError(f"sdv_create failed ({rc}): {msg}")
 
     def _ck(self, rc):

@@ -17,6 +17,7 @@ namespace sdv {
 void ba_destroy(sdv_ctx* c) {
   if (!c) return;
   for (BAState* b : c->ba_windows) { if (!b) continue;
+    for (int i=0;i<b->n_pinned;i++) frame_unpin(c, b->pinned[i]);
     cudaFree(b->hdr); cudaFreeHost(b->hdr_host); cudaFree(b->pool); cudaFree(b->partials); cudaFree(b->thbuf); cudaFree(b->thcount); delete b; }
   c->ba_windows.clear(); c->ba = nullptr;
   cudaFree(c->ba_wins_dev); cudaFreeHost(c->ba_wins_host); c->ba_wins_dev = c->ba_wins_host = nullptr;
@@ -102,6 +103,9 @@ int sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const doubl
   if (!c || nF < 1 || nF > SDV_MAX_FRAMES_WINDOW || !frame_ids || !T_evalPT7 || !state10 || !state_zero10 || !calib_value_scaled) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   BAState* b; int rc = ba_get(c, &b); if (rc) return rc;
+  for (int f=0; f<nF; f++) if (c->frame_index.find(frame_ids[f]) == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "BA frame %d: unknown frame handle", f);
+  for (int i=0;i<b->n_pinned;i++) frame_unpin(c, b->pinned[i]);          // the window is being replaced: drop its references, take the new ones
+  b->n_pinned = nF; for (int f=0; f<nF; f++) { b->pinned[f] = frame_ids[f]; frame_pin(c, frame_ids[f]); }
   BAHeader* H = b->hdr_host; memset(H, 0, sizeof(BAHeader));
   H->nF = nF; H->w = c->w; H->h = c->h; H->dim = kCP + 6*nF; b->nF = nF;
   BASettingsDev& s = H->set;
@@ -141,9 +145,14 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
   int rc = ba_alloc(c, b, nP, nR, nF); if (rc) return rc;
   // ---- makeIDX mirror (EnergyFunctional.cpp:761-782): validate the flattening and build the index lists the kernels walk
   std::vector<int> rot((size_t)nP*kMaxF, -1), pair_begin(kMaxF*kMaxF+1, 0), pair_res(nR), host_begin(kMaxF+1, 0);
+  if (nP > 0 && (!uv || !idepth || !idepth_zero || !color8 || !weights8 || !host || !hasDepthPrior || !isFromSensor || !res_begin)) return SDV_ERR_ARG;
+  if (nR > 0 && (!r_point || !r_host || !r_target || !r_hasMatcher || !r_matcher || !r_isNew)) return SDV_ERR_ARG;
+  // the CSR must be sane BEFORE any residual is indexed through it: [0 .. nR], monotone
+  if (nP > 0 && (res_begin[0] != 0 || res_begin[nP] != nR)) return ctx_fail(c, SDV_ERR_ARG, "res_begin must span all residuals (res_begin[0]=%d, res_begin[nP]=%d, nR=%d)", res_begin[0], res_begin[nP], nR);
+  if (nP == 0 && nR != 0) return ctx_fail(c, SDV_ERR_ARG, "residuals without points");
+  for (int p=0;p<nP;p++) if (res_begin[p] > res_begin[p+1]) return ctx_fail(c, SDV_ERR_ARG, "res_begin not monotone at point %d", p);
   for (int p=0;p<nP;p++) {
     if (host[p] < 0 || host[p] >= nF || (p > 0 && host[p] < host[p-1])) return ctx_fail(c, SDV_ERR_ARG, "points must be grouped by host frame in frame order (ef->allPoints order)");
-    if (res_begin[p] > res_begin[p+1]) return ctx_fail(c, SDV_ERR_ARG, "res_begin not monotone");
     for (int r=res_begin[p]; r<res_begin[p+1]; r++) {
       if (r_point[r] != p || r_host[r] != host[p] || r_target[r] < 0 || r_target[r] >= nF || r_target[r] == host[p]) return ctx_fail(c, SDV_ERR_ARG, "residual %d inconsistent with its point", r);
       if (rot[(size_t)p*kMaxF + r_target[r]] >= 0) return ctx_fail(c, SDV_ERR_ARG, "two residuals of point %d share a target", p);
@@ -151,7 +160,6 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
     }
     host_begin[host[p]+1] = p+1;
   }
-  if (nP > 0 && (res_begin[0] != 0 || res_begin[nP] != nR)) return ctx_fail(c, SDV_ERR_ARG, "res_begin must span all residuals");
   for (int f=1; f<=nF; f++) if (host_begin[f] < host_begin[f-1]) host_begin[f] = host_begin[f-1];
   for (int r=0;r<nR;r++) pair_begin[r_host[r] + nF*r_target[r] + 1]++;
   for (int k=0;k<nF*nF;k++) pair_begin[k+1] += pair_begin[k];
@@ -180,6 +188,11 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
   return SDV_OK;
 }
 
+int sdv_ba_clear(sdv_ctx* c) {               // empties the selected window and drops its references to frame images
+  if (!c) return SDV_ERR_ARG; if (!c->ba) return SDV_OK; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
+  CK(cudaStreamSynchronize(c->st));
+  for (int i=0;i<b->n_pinned;i++) frame_unpin(c, b->pinned[i]); b->n_pinned = 0; b->nF = 0; b->nP = 0; b->nR = 0; return SDV_OK;
+}
 int sdv_ba_select(sdv_ctx* c, int window) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); return ba_select(c, window); }
 
 int sdv_ba_reset_oob(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_reset_oob(wins, 1, maxR, c->st); c->launches++; return SDV_OK; }
@@ -361,6 +374,7 @@ int sdv_ba_marginalize_frame(sdv_ctx* c, int idx) {
   WIN1();
   launch_ba_marg_frame(wins, 1, idx, c->st); c->launches += 1;
   CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  if (idx < b->n_pinned) { frame_unpin(c, b->pinned[idx]); for (int i=idx; i+1<b->n_pinned; i++) b->pinned[i] = b->pinned[i+1]; b->n_pinned--; }
   b->nF -= 1; b->nP = 0; b->nR = 0;                                          // points/residuals are stale: the caller re-flattens the window (sdv_ba_set_points)
   return SDV_OK;
 }

@@ -96,6 +96,7 @@ struct BAState {
   double* partials; float* thbuf; int* thcount;
   int opt_iterations, opt_accepts;
   float last_ms;
+  unsigned long long pinned[kMaxF]; int n_pinned;   // frame handles whose level-0 texels this window's header points at (sdv_ctx::pins)
 };
 
 // launchers (sdv_ba_kernels.cu): every kernel is batched over windows (grid.y = window); `gate` = flags the window must have set

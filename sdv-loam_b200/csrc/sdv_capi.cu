@@ -3,6 +3,7 @@
 // the device path is unavailable.
 #include "../../include/sdv_b200.h"
 #include "sdv_ctx.cuh"
+#include "sdv_refine.cuh"
 #include <cstdio>
 #include <cstring>
 #include <cstdarg>
@@ -31,7 +32,8 @@ int sdv_pyr_levels(int w, int h) {               // util/globalCalib.cpp:22-30
   return used;
 }
 
-const char* sdv_last_error(sdv_ctx* c) { return c ? c->err : "null context"; }
+static thread_local char g_create_err[512] = "null context";   // message of the last failed sdv_create on this thread (there is no context to hold it)
+const char* sdv_last_error(sdv_ctx* c) { return c ? c->err : g_create_err; }
 
 static void make_geom(sdv_ctx* c, const sdv_calib* K) {   // CoarseTracker::makeK (CoarseTracker.cpp:77-106)
   float fx[SDV_PYR_LEVELS], fy[SDV_PYR_LEVELS], cx[SDV_PYR_LEVELS], cy[SDV_PYR_LEVELS];
@@ -46,10 +48,18 @@ static void make_geom(sdv_ctx* c, const sdv_calib* K) {   // CoarseTracker::make
   }
 }
 
+static int create_impl(sdv_ctx* c, const sdv_calib* K, int w, int h, int levels, const sdv_settings* s_in, int device);
 int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings* s_in, int device, sdv_ctx** out) {
-  if (!K || !out || w <= 0 || h <= 0 || levels < 1 || levels > SDV_PYR_LEVELS) return SDV_ERR_ARG;
-  int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) return SDV_ERR_CUDA;
-  sdv_ctx* c = new sdv_ctx(); *out = c; c->err[0] = 0;
+  if (out) *out = nullptr;
+  if (!K || !out || w <= 0 || h <= 0 || levels < 1 || levels > SDV_PYR_LEVELS || device < 0) { snprintf(g_create_err, sizeof g_create_err, "sdv_create: bad argument"); return SDV_ERR_ARG; }
+  int ndev = 0; if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= device) { snprintf(g_create_err, sizeof g_create_err, "sdv_create: no CUDA device %d (this library has no CPU fallback)", device); return SDV_ERR_CUDA; }
+  sdv_ctx* c = new sdv_ctx();                              // value-initialised: every pointer/handle member starts null, so sdv_destroy is safe on a partially built context
+  c->err[0] = 0;
+  int rc = create_impl(c, K, w, h, levels, s_in, device);
+  if (rc != SDV_OK) { snprintf(g_create_err, sizeof g_create_err, "%s", c->err[0] ? c->err : "sdv_create failed"); sdv_destroy(c); return rc; }
+  *out = c; return SDV_OK;
+}
+static int create_impl(sdv_ctx* c, const sdv_calib* K, int w, int h, int levels, const sdv_settings* s_in, int device) {
   sdv_settings s; if (s_in) s = *s_in; else sdv_default_settings(&s);
   if (s.n_tracker_slots < 1) s.n_tracker_slots = 2;
   if (s.max_frames < 2) s.max_frames = 2;
@@ -58,6 +68,7 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
   if (s.cluster_size > 16) s.cluster_size = 16;
   c->set = s; c->device = device; c->w = w; c->h = h; c->levels = levels;
   CK(cudaSetDevice(device));
+  CK(kernels_init_device()); CK(refine_init_device());      // per-device function attributes (opt-in shared memory, cluster sizes)
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_cp, cudaStreamNonBlocking));
   for (int i=0;i<sdv_ctx::kIngRing;i++) CK(cudaEventCreateWithFlags(&c->ev_ing[i], cudaEventDisableTiming)); for (int i=0;i<2;i++) CK(cudaEventCreateWithFlags(&c->ev_cp[i], cudaEventDisableTiming));
@@ -114,7 +125,8 @@ int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings*
 
 void sdv_destroy(sdv_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device); cudaStreamSynchronize(c->st_cp); cudaStreamSynchronize(c->st_in); cudaStreamSynchronize(c->st);
+  cudaSetDevice(c->device);
+  if (c->st_cp) cudaStreamSynchronize(c->st_cp); if (c->st_in) cudaStreamSynchronize(c->st_in); if (c->st) cudaStreamSynchronize(c->st);
   for (auto& f : c->frames) { cudaFree(f.base); cudaFree(f.I0_own); }
   for (auto p : c->lvl0_pool) cudaFree(p);
   for (auto& t : c->slots) for (int l=0;l<c->levels;l++) cudaFree(t.pts[l]);
@@ -124,11 +136,12 @@ void sdv_destroy(sdv_ctx* c) {
   for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]); } cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
   for (int i=0;i<2;i++) { for (auto p : c->stage[i]) cudaFree(p); cudaFree(c->stage_u8[i]); }
-  for (int i=0;i<sdv_ctx::kIngRing;i++) cudaEventDestroy(c->ev_ing[i]); for (int i=0;i<2;i++) cudaEventDestroy(c->ev_cp[i]); cudaStreamDestroy(c->st_cp);
+  for (int i=0;i<sdv_ctx::kIngRing;i++) if (c->ev_ing[i]) cudaEventDestroy(c->ev_ing[i]); for (int i=0;i<2;i++) if (c->ev_cp[i]) cudaEventDestroy(c->ev_cp[i]); if (c->st_cp) cudaStreamDestroy(c->st_cp);
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);
   ba_destroy(c);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev_in); cudaStreamDestroy(c->st); cudaStreamDestroy(c->st_in);
+  if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->ev_in) cudaEventDestroy(c->ev_in); if (c->st) cudaStreamDestroy(c->st); if (c->st_in) cudaStreamDestroy(c->st_in);
+  cudaGetLastError();                                      // a partially built context may have produced benign errors above: do not leave them sticky
   delete c;
 }
 
@@ -177,7 +190,8 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
   for (int k=0;k<n;k++) {
     int idx = -1;
     auto it = c->frame_index.find(frames[k]);
-    if (it != c->frame_index.end()) idx = it->second;
+    if (it != c->frame_index.end()) { idx = it->second;
+      if (frame_pinned(c, frames[k])) return ctx_fail(c, SDV_ERR_STATE, "frame %llu is referenced by a resident BA window / map slot and cannot be re-uploaded", (unsigned long long)frames[k]); }
     else { for (size_t i=0;i<c->frames.size();i++) if (!c->frames[i].used) { idx = (int)i; break; } }
     if (idx < 0) return ctx_fail(c, SDV_ERR_CAPACITY, "frame pool exhausted (max_frames=%d)", (int)c->frames.size());
     FrameDev& f = c->frames[idx]; f.used = true; f.id = frames[k]; f.exposure = exposures ? exposures[k] : 1.0f; c->frame_index[frames[k]] = idx;
@@ -250,6 +264,7 @@ int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposur
 int sdv_frame_release(sdv_ctx* c, uint64_t frame) {
   if (!c) return SDV_ERR_ARG;
   auto it = c->frame_index.find(frame); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
+  if (frame_pinned(c, frame)) return ctx_fail(c, SDV_ERR_STATE, "frame %llu is referenced by a resident BA window / map slot: replace or clear that window / map first", (unsigned long long)frame);
   FrameDev& f = c->frames[it->second]; f.used = false; frame_drop_lvl0(c, f); f.adopted = false; f.I0 = f.I0_own; c->frame_index.erase(it); return SDV_OK;
 }
 int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out) {
@@ -322,7 +337,7 @@ int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const f
     CK(cudaMemcpyAsync(c->cd_pts4, pts4, (size_t)4*n*sizeof(float), cudaMemcpyHostToDevice, c->st));
     CK(cudaMemcpyAsync(c->cd_round, round_half, (size_t)n*sizeof(int), cudaMemcpyHostToDevice, c->st));
     launch_cd_prep(c->cd_pts4, c->cd_round, n, w, c->cd_splats, c->cd_done, c->st);
-    for (int round = 0; round < 64; round++) {              // usually 1-3 rounds: one per multiplicity of colliding splats
+    for (int round = 0; round < n; round++) {               // usually 1-3 rounds: one per multiplicity of colliding splats; at most n (every splat on one pixel)
       CK(cudaMemsetAsync(c->cd_scalars, 0, sizeof(int), c->st));
       launch_cd_round(c->cd_splats, n, c->cd_done, c->cd_owner, c->cd_id[0], c->cd_ws[0], c->cd_scalars, c->st);
       CK(cudaMemcpyAsync(c->cd_scalars_host, c->cd_scalars, sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -333,15 +348,17 @@ int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const f
   for (int l=1;l<c->levels;l++) launch_cd_pool(c->cd_id[l-1], c->cd_ws[l-1], c->cd_id[l], c->cd_ws[l], w>>l, h>>l, w>>(l-1), c->st);
   for (int l=0;l<c->levels;l++) {
     launch_cd_dilate(c->cd_id[l], c->cd_ws[l], c->cd_id2[l], c->cd_ws2[l], w>>l, h>>l, l < 2 ? 1 : 0, c->st);
-    launch_cd_compact(c->cd_id2[l], c->cd_ws2[l], l == 0 ? nullptr : f->lvl[l], l == 0 ? f->I0 : nullptr, w>>l, h>>l, c->cd_counts, c->cd_scalars + 1 + l, t.pts[l], c->st);
+    launch_cd_compact(c->cd_id2[l], c->cd_ws2[l], l == 0 ? nullptr : f->lvl[l], l == 0 ? f->I0 : nullptr, w>>l, h>>l, c->cd_counts, c->cd_scalars + 1 + l, t.pts[l], t.cap[l], c->st);
   }
   CK(cudaMemcpyAsync(c->cd_scalars_host, c->cd_scalars, 8*sizeof(int), cudaMemcpyDeviceToHost, c->st));
   CK(cudaStreamSynchronize(c->st));
   CK(cudaGetLastError());
-  for (int l=0;l<c->levels;l++) {
-    t.npts[l] = c->cd_scalars_host[1+l];
-    if (t.npts[l] > t.cap[l]) return ctx_fail(c, SDV_ERR_CAPACITY, "level %d cloud (%d) exceeds capacity %d", l, t.npts[l], t.cap[l]);
+  for (int l=0;l<c->levels;l++) if (c->cd_scalars_host[1+l] > t.cap[l]) {
+    // the emit kernel never wrote past cap[l], but the slot's clouds are now a truncated mix: invalidate the slot instead of leaving it half-updated
+    t.ref_frame = ~0ull; t.has_totals = false; for (int k=0;k<c->levels;k++) t.npts[k] = 0;
+    return ctx_fail(c, SDV_ERR_CAPACITY, "level %d cloud (%d) exceeds capacity %d (max_ref_points); slot %d has no reference now", l, c->cd_scalars_host[1+l], t.cap[l], slot);
   }
+  for (int l=0;l<c->levels;l++) t.npts[l] = c->cd_scalars_host[1+l];
   t.ref_frame = ref_frame; t.ref_a = ref_a; t.ref_b = ref_b; t.refExposure = f->exposure; t.has_totals = false;
   return SDV_OK;
 }

@@ -34,6 +34,9 @@ struct sdv_ctx {
   sdv::TrackConst tc; sdv::TrackConst* tc_dev;
   size_t lvl_off[sdv::kLevels]; size_t frame_texels;
   std::vector<sdv::FrameDev> frames; std::unordered_map<uint64_t,int> frame_index;
+  // frames whose device images are referenced by a resident BA window (BAHeader::frames[].img0) or map slot (MapDev::hostI0): refcount per handle.
+  // A pinned frame can be neither released nor re-uploaded (SDV_ERR_STATE) — its pool storage would be handed to another frame under the reader.
+  std::unordered_map<uint64_t,int> pins;
   unsigned char* stage_u8[2] = {nullptr, nullptr}; size_t stage_u8_cap[2] = {0, 0};   // contiguous mono8 staging per parity (adjacent host images coalesce into one copy)
   std::vector<float*> stage[2]; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev[2]; sdv::PyrBatchHost* pyr_batch_host[2];     // double-buffered by ingest parity
   std::vector<float4*> lvl0_pool; std::vector<int> lvl0_free;
@@ -59,6 +62,9 @@ void rp_destroy(sdv_ctx* c);
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
 void ba_destroy(sdv_ctx* c);
 int  ensure_lvl0(sdv_ctx* c, FrameDev& f);     // build the packed level-0 texels of a frame on demand (keyframes / read-back)
+inline void frame_pin(sdv_ctx* c, uint64_t id) { c->pins[id]++; }
+inline void frame_unpin(sdv_ctx* c, uint64_t id) { auto it = c->pins.find(id); if (it != c->pins.end() && --it->second <= 0) c->pins.erase(it); }
+inline bool frame_pinned(const sdv_ctx* c, uint64_t id) { return c->pins.find(id) != c->pins.end(); }
 int  join_ingest(sdv_ctx* c);                  // compute stream waits for every ingest enqueued so far
 int  join_ingest_upto(sdv_ctx* c, long long seq);   // ... for ingest calls <= seq only (frames carry their ingest_seq)
 }

@@ -8,6 +8,7 @@
 #include "sdv_kernels.cuh"
 #include "sdv_warp_solve.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 namespace cg = cooperative_groups;
 
 namespace sdv {
@@ -173,9 +174,7 @@ constexpr int kStepThreads = 256;
 int step_kernel_max_grid() { return 148*4; }
 void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const float* I0, const LevelGeom& g, const EvalParams& ep,
                           double* partials, unsigned int* ticket, double* totals, cudaStream_t st) {
-  static bool attr_set = false;
-  size_t smem = (size_t)kNAcc*kStepThreads*sizeof(float);
-  if (!attr_set) { cudaFuncSetAttribute(coarse_res_gs_kernel<kStepThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  size_t smem = (size_t)kNAcc*kStepThreads*sizeof(float);                // opt-in size set per device by kernels_init_device()
   int grid = (n + kStepThreads - 1)/kStepThreads; if (grid < 1) grid = 1; if (grid > step_kernel_max_grid()) grid = step_kernel_max_grid();
   coarse_res_gs_kernel<kStepThreads><<<grid, kStepThreads, smem, st>>>(pts, n, img, I0, g, ep, partials, ticket, totals);
 }
@@ -198,7 +197,7 @@ constexpr int kMaxCluster = 16;
 // overlaps the point sweeps of the others.  <128,4> is the batched-throughput configuration (cluster size 1);
 // <256,1> with a cluster of 8-16 CTAs is the low-latency single-sequence configuration.
 template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
+__global__ void __launch_bounds__(THREADS, MINB) track_cluster_v1_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
@@ -400,25 +399,441 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
   if (C > 1) cluster.sync();                                // keep every CTA's shared memory alive until all remote writes/reads are done
 }
 
+
+// ================================================================================================ device-resident LM, asynchronous data path (round 2)
+// Same algorithm and the same point -> thread mapping and summation order as track_cluster_v1_kernel (results are bit-identical), but no
+// load ever stalls a warp on HBM:
+//   * the reference cloud streams through shared memory in chunks: one elected thread issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) per
+//     2 KB block of float4 points, completion is signalled on an mbarrier (expect_tx), two chunks in flight;
+//   * the bilinear footprint of point k+1 is gathered by per-thread cp.async (SASS LDGSTS) into a private shared-memory slot while point k
+//     is accumulated — the gather needs no registers and is complete one full iteration later;
+//   * the level-0 flow indicators (every 32nd point, CoarseTracker.cpp:538-566) are a dense pre-pass (all lanes busy) instead of a divergent branch
+//     that cost one lane's 6 divisions per warp iteration;
+//   * the LM control flow is a state machine around ONE instance of the sweep (a third of the code size of v1).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile("{\n\t.reg .pred p;\n\tSDV_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SDV_DONE_%=;\n\tbra SDV_WAIT_%=;\n\tSDV_DONE_%=:\n\t}"
+               :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t s, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(s), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t s, const void* g)  { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1()  { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0()  { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct PtState { float u, v, nid, dx, dy, col; bool ok; };     // what the accumulate stage needs of a projected point (its taps are in the thread's smem slot)
+
+// calcRes, first half (CoarseTracker.cpp:525-575): projection + bounds, then launch the gather of the 2x2 (level 0: 12-tap) footprint into `slot`.
+template <int THREADS, bool LVL0>
+__device__ __forceinline__ PtState stage_project(const float4 p, const LevelGeom& g, const EvalParams& ep, const float4* __restrict__ img, const float* __restrict__ I0, uint32_t slot) {
+  PtState s; const float x = p.x, y = p.y, id = p.z; s.col = p.w;
+  float pt0 = ((ep.RKi[0]*x + ep.RKi[1]*y) + ep.RKi[2]*1.0f) + ep.t[0]*id;
+  float pt1 = ((ep.RKi[3]*x + ep.RKi[4]*y) + ep.RKi[5]*1.0f) + ep.t[1]*id;
+  float pt2 = ((ep.RKi[6]*x + ep.RKi[7]*y) + ep.RKi[8]*1.0f) + ep.t[2]*id;
+  s.u = pt0 / pt2; s.v = pt1 / pt2;
+  const float Ku = g.fx*s.u + g.cx, Kv = g.fy*s.v + g.cy;
+  s.nid = id / pt2;
+  s.ok = (Ku > 2 && Kv > 2 && Ku < (float)(g.w-3) && Kv < (float)(g.h-3) && s.nid > 0);
+  s.dx = 0.f; s.dy = 0.f;
+  if (s.ok) {
+    const int ix = (int)Ku, iy = (int)Kv, w = g.w;
+    s.dx = Ku - ix; s.dy = Kv - iy;
+    if (LVL0) {                                             // planar intensity: rows -1..2 (gradients are formed in stage_accumulate exactly like makeImages does)
+      const float* b = I0 + ix + iy*w;
+      cp_async4(slot + 0*THREADS*4, b - w);       cp_async4(slot + 1*THREADS*4, b - w + 1);
+      cp_async4(slot + 2*THREADS*4, b - 1);       cp_async4(slot + 3*THREADS*4, b);         cp_async4(slot + 4*THREADS*4, b + 1);     cp_async4(slot + 5*THREADS*4, b + 2);
+      cp_async4(slot + 6*THREADS*4, b + w - 1);   cp_async4(slot + 7*THREADS*4, b + w);     cp_async4(slot + 8*THREADS*4, b + w + 1); cp_async4(slot + 9*THREADS*4, b + w + 2);
+      cp_async4(slot + 10*THREADS*4, b + 2*w);    cp_async4(slot + 11*THREADS*4, b + 2*w + 1);
+    } else {
+      const float4* bp = img + ix + iy*w;
+      cp_async16(slot + 0*THREADS*16, bp); cp_async16(slot + 1*THREADS*16, bp + 1); cp_async16(slot + 2*THREADS*16, bp + w); cp_async16(slot + 3*THREADS*16, bp + w + 1);
+    }
+  }
+  return s;
+}
+// calcRes second half + calcGSSSE for one point whose taps have landed (CoarseTracker.cpp:576-601, 442-466).  Expression trees identical to eval_point.
+template <int THREADS, bool LVL0>
+__device__ __forceinline__ void stage_accumulate(const PtState s, const LevelGeom& g, const EvalParams& ep, const unsigned char* slot, float (&acc)[kNAcc]) {
+  if (!s.ok) return;
+  float4 p00, p10, p01, p11;
+  if (LVL0) {
+    const float* t = reinterpret_cast<const float*>(slot);
+    float a_m1_0 = t[0*THREADS], a_m1_1 = t[1*THREADS];
+    float a_0_m1 = t[2*THREADS], a_0_0 = t[3*THREADS], a_0_1 = t[4*THREADS], a_0_2 = t[5*THREADS];
+    float a_1_m1 = t[6*THREADS], a_1_0 = t[7*THREADS], a_1_1 = t[8*THREADS], a_1_2 = t[9*THREADS];
+    float a_2_0 = t[10*THREADS], a_2_1 = t[11*THREADS];
+    p00.x = a_0_0; p00.y = grad_guard(0.5f*(a_0_1 - a_0_m1)); p00.z = grad_guard(0.5f*(a_1_0 - a_m1_0));
+    p10.x = a_0_1; p10.y = grad_guard(0.5f*(a_0_2 - a_0_0));  p10.z = grad_guard(0.5f*(a_1_1 - a_m1_1));
+    p01.x = a_1_0; p01.y = grad_guard(0.5f*(a_1_1 - a_1_m1)); p01.z = grad_guard(0.5f*(a_2_0 - a_0_0));
+    p11.x = a_1_1; p11.y = grad_guard(0.5f*(a_1_2 - a_1_0));  p11.z = grad_guard(0.5f*(a_2_1 - a_0_1));
+  } else {
+    const float4* t = reinterpret_cast<const float4*>(slot);
+    p00 = t[0*THREADS]; p10 = t[1*THREADS]; p01 = t[2*THREADS]; p11 = t[3*THREADS];
+  }
+  const float dx = s.dx, dy = s.dy, dxdy = dx*dy, u = s.u, v = s.v, new_idepth = s.nid, refColor = s.col;
+  float w11 = dxdy, w01 = dy-dxdy, w10 = dx-dxdy, w00 = 1-dx-dy+dxdy;
+  float hit0 = ((w11*p11.x + w01*p01.x) + w10*p10.x) + w00*p00.x;
+  float hit1 = ((w11*p11.y + w01*p01.y) + w10*p10.y) + w00*p00.y;
+  float hit2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
+  if (!isfinite(hit0)) return;
+  float residual = hit0 - (ep.aLL*refColor + ep.bLL);
+  float ar = fabsf(residual);
+  float hw = ar < ep.huber ? 1.0f : ep.huber / ar;
+  acc[kIdxNE] += 1.0f;
+  if (ar > ep.cutoff) { acc[kIdxE] += ep.maxEnergy; acc[kIdxNSat] += 1.0f; return; }
+  acc[kIdxE] += hw*residual*residual*(2-hw);
+  float dxf = hit1*g.fx, dyf = hit2*g.fy;
+  float J[9];
+  J[0] = new_idepth*dxf;
+  J[1] = new_idepth*dyf;
+  J[2] = 0.0f - new_idepth*(u*dxf + v*dyf);
+  J[3] = 0.0f - ((u*v)*dxf + dyf*(1.0f + v*v));
+  J[4] = (u*v)*dyf + dxf*(1.0f + u*u);
+  J[5] = u*dyf - v*dxf;
+  J[6] = ep.aLL*(ep.b0 - refColor);
+  J[7] = -1.0f;
+  J[8] = residual;
+  int k = 0;
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    float Jw = J[r]*hw;
+#pragma unroll
+    for (int c = r; c < 9; c++) { acc[k] = fmaf(Jw, J[c], acc[k]); k++; }
+  }
+}
+// flow indicators of one level-0 point with index % 32 == 0 (CoarseTracker.cpp:538-566); same expressions as eval_point
+__device__ __forceinline__ void flow_point(const float4 p, const LevelGeom& g, const EvalParams& ep, float (&acc)[kNAcc]) {
+  const float x = p.x, y = p.y, id = p.z;
+  float pt0 = ((ep.RKi[0]*x + ep.RKi[1]*y) + ep.RKi[2]*1.0f) + ep.t[0]*id;
+  float pt1 = ((ep.RKi[3]*x + ep.RKi[4]*y) + ep.RKi[5]*1.0f) + ep.t[1]*id;
+  float pt2 = ((ep.RKi[6]*x + ep.RKi[7]*y) + ep.RKi[8]*1.0f) + ep.t[2]*id;
+  float u = pt0 / pt2, v = pt1 / pt2;
+  float Ku = g.fx*u + g.cx, Kv = g.fy*v + g.cy;
+  float k0 = (g.Ki[0]*x + g.Ki[1]*y) + g.Ki[2]*1.0f, k1 = (g.Ki[3]*x + g.Ki[4]*y) + g.Ki[5]*1.0f, k2 = (g.Ki[6]*x + g.Ki[7]*y) + g.Ki[8]*1.0f;
+  float r0 = (ep.RKi[0]*x + ep.RKi[1]*y) + ep.RKi[2]*1.0f, r1 = (ep.RKi[3]*x + ep.RKi[4]*y) + ep.RKi[5]*1.0f, r2 = (ep.RKi[6]*x + ep.RKi[7]*y) + ep.RKi[8]*1.0f;
+  float a0 = k0 + ep.t[0]*id, a1 = k1 + ep.t[1]*id, a2 = k2 + ep.t[2]*id;
+  float KuT = g.fx*(a0/a2) + g.cx, KvT = g.fy*(a1/a2) + g.cy;
+  float b0_ = k0 - ep.t[0]*id, b1_ = k1 - ep.t[1]*id, b2_ = k2 - ep.t[2]*id;
+  float KuT2 = g.fx*(b0_/b2_) + g.cx, KvT2 = g.fy*(b1_/b2_) + g.cy;
+  float c0 = r0 - ep.t[0]*id, c1 = r1 - ep.t[1]*id, c2 = r2 - ep.t[2]*id;
+  float Ku3 = g.fx*(c0/c2) + g.cx, Kv3 = g.fy*(c1/c2) + g.cy;
+  acc[kIdxFlowT]  += (KuT-x)*(KuT-x) + (KvT-y)*(KvT-y);
+  acc[kIdxFlowT]  += (KuT2-x)*(KuT2-x) + (KvT2-y)*(KvT2-y);
+  acc[kIdxFlowRT] += (Ku-x)*(Ku-x) + (Kv-y)*(Kv-y);
+  acc[kIdxFlowRT] += (Ku3-x)*(Ku3-x) + (Kv3-y)*(Kv3-y);
+  acc[kIdxFlowN]  += 2.0f;
+}
+
+constexpr int kPtChunk = 4;                                 // sweep iterations (blocks of THREADS points) per TMA-staged chunk
+
+struct Ctl2 {                                               // per-CTA LM state (every CTA of a cluster computes it redundantly and identically)
+  SE3d cur; double a_cur, b_cur;
+  SE3d cand; double a_cand, b_cand;
+  double H[64], b[8];
+  double resOld[6], resNew[6];
+  double lastRes[5], flow[3];
+  double incn;
+  float lambda, lcr;                                        // LM damping, levelCutoffRepeat
+  int lvl, mode, iteration, haveRepeated, aborted, done;
+  long long evals[kLevels]; int iters[kLevels], accs[kLevels];
+  EvalParams ep;
+};
+__constant__ unsigned char kAccRow[45] = {0,0,0,0,0,0,0,0,0, 1,1,1,1,1,1,1,1, 2,2,2,2,2,2,2, 3,3,3,3,3,3, 4,4,4,4,4, 5,5,5,5, 6,6,6, 7,7, 8};
+__constant__ unsigned char kAccCol[45] = {0,1,2,3,4,5,6,7,8, 1,2,3,4,5,6,7,8, 2,3,4,5,6,7,8, 3,4,5,6,7,8, 4,5,6,7,8, 5,6,7,8, 6,7,8, 7,8, 8};
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x;
+  TrackJob& J = jobs[blockIdx.x / C];
+
+  // dynamic smem: [ tap ring 2 x 4 x THREADS x 16 B | point chunks 2 x kPtChunk x THREADS x 16 B ] aliased by the reduction scratch [kNAcc][THREADS] floats,
+  // then the DSMEM gather buffers and the reduced sums
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr size_t kRingBytes = (size_t)2*4*THREADS*16, kPtsBytes = (size_t)2*kPtChunk*THREADS*16, kRedBytes = (size_t)kNAcc*THREADS*sizeof(float);
+  constexpr size_t kStageBytes = (kRingBytes + kPtsBytes) > kRedBytes ? (kRingBytes + kPtsBytes) : kRedBytes;
+  unsigned char* ring = smem_raw;
+  float4* pbuf   = reinterpret_cast<float4*>(smem_raw + kRingBytes);
+  float*  red    = reinterpret_cast<float*>(smem_raw);
+  double* gather = reinterpret_cast<double*>(smem_raw + kStageBytes);                    // [2][kMaxCluster][kNAcc]
+  double* bsum   = gather + 2*kMaxCluster*kNAcc;                                         // [kNAcc]
+  double* tot    = bsum + kNAcc;                                                         // [kNAcc]
+  __shared__ Ctl2 ctl;
+  __shared__ TrackConst tc;
+  __shared__ __align__(8) uint64_t full_bar[2];
+  for (int i = tid; i < (int)(sizeof(TrackConst)/4); i += THREADS) reinterpret_cast<int*>(&tc)[i] = reinterpret_cast<const int*>(tc_g)[i];
+  if (tid == 0) {
+    ctl.cur = se3_from7(J.T); ctl.a_cur = J.ab[0]; ctl.b_cur = J.ab[1];
+    for (int i = 0; i < 5; i++) ctl.lastRes[i] = nan("");
+    for (int i = 0; i < 3; i++) ctl.flow[i] = 1000.0;
+    for (int i = 0; i < kLevels; i++) { ctl.evals[i] = 0; ctl.iters[i] = 0; ctl.accs[i] = 0; }
+    ctl.lvl = J.coarsest; ctl.mode = 0; ctl.iteration = 0; ctl.haveRepeated = 0; ctl.aborted = 0; ctl.done = 0; ctl.lcr = 1.0f; ctl.lambda = 0.01f; ctl.incn = 0;
+    mbar_init(&full_bar[0], 1); mbar_init(&full_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[ctl.lvl], ctl.lvl,
+                                 tc.coarseCutoffTH*ctl.lcr, tc.huberTH, ctl.ep);
+  __syncthreads();
+  if (C > 1) cluster.sync();                                // every CTA of the cluster must be running before the first distributed-shared-memory write
+
+  int evalCount = 0;
+  uint32_t bar_phase = 0;                                   // bit b = parity the next wait on full_bar[b] expects
+  const int stride = C*THREADS;
+  const uint32_t slot_base = smem_u32(ring) + tid*16;       // level >= 1: [slot][tap][tid] float4 ; level 0 reuses the bytes as [slot][tap 0..11][tid] float
+  const uint32_t slot_base0 = smem_u32(ring) + tid*4;
+  constexpr uint32_t kSlotStride = 4*THREADS*16;
+
+  while (true) {
+    const int lvl = ctl.lvl;
+    // ------------------------------------------------------------------ one calcRes + calcGSSSE sweep at ctl.ep
+    float acc[kNAcc];
+#pragma unroll
+    for (int k = 0; k < kNAcc; k++) acc[k] = 0.f;
+    {
+      const float4* __restrict__ pts = J.pts[lvl]; const int n = J.npts[lvl];
+      const float4* __restrict__ img = (lvl == 0) ? nullptr : J.img[lvl]; const float* __restrict__ I0 = J.img0;
+      const LevelGeom& g = tc.geom[lvl];
+      const int K = (n + stride - 1)/stride;                // sweep iterations (uniform over the CTA)
+      const int NC = (K + kPtChunk - 1)/kPtChunk;           // point chunks
+      auto issue_chunk = [&](int c) {                       // thread 0: TMA bulk copies of chunk c's (<= kPtChunk) blocks into buffer c&1
+        const int b = c & 1; uint32_t bytes = 0; int cnt[kPtChunk];
+#pragma unroll
+        for (int j = 0; j < kPtChunk; j++) {
+          const int base = (c*kPtChunk + j)*stride + rank*THREADS; int m = n - base; m = m < 0 ? 0 : (m > THREADS ? THREADS : m);
+          cnt[j] = m; bytes += (uint32_t)m*16u;
+        }
+        mbar_expect_tx(&full_bar[b], bytes);
+#pragma unroll
+        for (int j = 0; j < kPtChunk; j++) if (cnt[j] > 0)
+          bulk_g2s(pbuf + (b*kPtChunk + j)*THREADS, pts + (size_t)(c*kPtChunk + j)*stride + rank*THREADS, (uint32_t)cnt[j]*16u, &full_bar[b]);
+      };
+      if (tid == 0) { if (NC > 0) issue_chunk(0); if (NC > 1) issue_chunk(1); }
+      if (lvl == 0) {                                       // dense flow-indicator pre-pass: point indices 0, 32, 64, ...
+        for (int j = rank*THREADS + tid; 32*j < n; j += stride) flow_point(__ldg(pts + 32*j), g, ctl.ep, acc);
+      }
+      PtState sN; sN.ok = false; sN.u = sN.v = sN.nid = sN.dx = sN.dy = sN.col = 0.f;
+      auto project = [&](int m) {                           // stage A for sweep iteration m (its chunk has landed)
+        const int i = m*stride + rank*THREADS + tid;
+        PtState s; s.ok = false; s.u = s.v = s.nid = s.dx = s.dy = s.col = 0.f;
+        if (i < n) {
+          const float4 p = pbuf[(((m/kPtChunk) & 1)*kPtChunk + (m % kPtChunk))*THREADS + tid];
+          const uint32_t so = (uint32_t)(m & 1)*kSlotStride;
+          s = (lvl == 0) ? stage_project<THREADS, true>(p, g, ctl.ep, img, I0, slot_base0 + so) : stage_project<THREADS, false>(p, g, ctl.ep, img, I0, slot_base + so);
+        }
+        return s;
+      };
+      if (K > 0) { mbar_wait(&full_bar[0], bar_phase & 1u); bar_phase ^= 1u; sN = project(0); }
+      cp_async_commit();
+      for (int k = 0; k < K; k++) {
+        const PtState sC = sN;
+        const int m = k + 1;
+        if (m < K) {
+          if (m % kPtChunk == 0) {                          // entering chunk c: everyone is done reading chunk c-1, its buffer can take chunk c+1
+            const int c = m / kPtChunk;
+            __syncthreads();
+            if (tid == 0 && c + 1 < NC) issue_chunk(c + 1);
+            mbar_wait(&full_bar[c & 1], (bar_phase >> (c & 1)) & 1u); bar_phase ^= (1u << (c & 1));
+          }
+          sN = project(m);
+        }
+        cp_async_commit();
+        cp_async_wait1();                                   // the gather of iteration k (committed one iteration ago) has landed in this thread's slot
+        const unsigned char* slot = ring + (size_t)(k & 1)*kSlotStride;
+        if (lvl == 0) stage_accumulate<THREADS, true>(sC, g, ctl.ep, slot + tid*4, acc);
+        else          stage_accumulate<THREADS, false>(sC, g, ctl.ep, slot + tid*16, acc);
+      }
+      cp_async_wait0();
+      __syncthreads();                                      // the reduction scratch aliases the tap ring / point chunks
+      block_reduce_acc<THREADS>(acc, red, bsum);
+      if (C > 1) {
+        const int buf = evalCount & 1;
+        for (int k = tid; k < kNAcc*C; k += THREADS) {
+          int r = k / kNAcc, e = k - r*kNAcc;
+          double* dst = cluster.map_shared_rank(gather, r);
+          dst[(buf*kMaxCluster + rank)*kNAcc + e] = bsum[e];
+        }
+        cluster.sync();
+        if (tid < kNAcc) { double s = 0; for (int r = 0; r < C; r++) s += gather[(buf*kMaxCluster + r)*kNAcc + tid]; tot[tid] = s; }
+      } else {
+        if (tid < kNAcc) tot[tid] = bsum[tid];
+      }
+      __syncthreads();
+      evalCount++;
+      if (tid == 0) ctl.evals[lvl] += n;
+    }
+    // ------------------------------------------------------------------ LM control (warp 0), CoarseTracker.cpp:679-812 as a state machine
+    if (tid < 32) {
+      const int lane = tid;
+      const int maxIterations[5] = {10,20,50,50,50};        // :679
+      const float lambdaExtrapolationLimit = 0.001f;         // :680
+      bool propose = false, level_end = false;
+      if (ctl.mode == 0) {                                   // level entry: resOld at the current pose (:690-702)
+        if (lane == 0) finalize_res(tot, ctl.resOld);
+        __syncwarp();
+        if (ctl.resOld[5] > 0.6 && ctl.lcr < 50) {
+          if (lane == 0) {
+            ctl.lcr *= 2;
+            make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl, tc.coarseCutoffTH*ctl.lcr, tc.huberTH, ctl.ep);
+          }
+        } else {
+          if (lane == 0) { finalize_gs(tot, ctl.H, ctl.b); ctl.lambda = 0.01f; ctl.iteration = 0; }
+          propose = true;
+        }
+      } else {                                               // candidate evaluated: accept / reject (:770-806)
+        if (lane == 0) {
+          finalize_res(tot, ctl.resNew);
+          bool accept = (ctl.resNew[0]/ctl.resNew[1]) < (ctl.resOld[0]/ctl.resOld[1]);
+          if (accept) {
+            finalize_gs(tot, ctl.H, ctl.b);
+            for (int i = 0; i < 6; i++) ctl.resOld[i] = ctl.resNew[i];
+            ctl.cur = ctl.cand; ctl.a_cur = ctl.a_cand; ctl.b_cur = ctl.b_cand;
+            ctl.lambda *= 0.5f; ctl.accs[lvl]++;
+          } else {
+            ctl.lambda *= 4;
+            if (ctl.lambda < lambdaExtrapolationLimit) ctl.lambda = lambdaExtrapolationLimit;
+          }
+          ctl.iteration++;
+        }
+        __syncwarp();
+        if (!(ctl.incn > 1e-3) || ctl.iteration >= maxIterations[lvl]) level_end = true; else propose = true;
+      }
+      __syncwarp();
+      if (level_end) {                                       // :808-822
+        if (lane == 0) {
+          ctl.lastRes[lvl] = sqrtf((float)(ctl.resOld[0]/ctl.resOld[1]));
+          ctl.flow[0] = ctl.resOld[2]; ctl.flow[1] = ctl.resOld[3]; ctl.flow[2] = ctl.resOld[4];
+          int nl = lvl;
+          if (ctl.lastRes[lvl] > 1.5*J.minRes[lvl]) { ctl.aborted = 1; ctl.done = 1; }
+          else {
+            if (ctl.lcr > 1 && !ctl.haveRepeated) { nl++; ctl.haveRepeated = 1; }
+            nl--;
+            if (nl < 0) ctl.done = 1;
+            else {
+              ctl.lvl = nl; ctl.mode = 0; ctl.lcr = 1.0f;
+              make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[nl], nl, tc.coarseCutoffTH, tc.huberTH, ctl.ep);
+            }
+          }
+        }
+      } else if (propose) {                                  // propose the LM step (:722-765)
+        if (lane == 0) ctl.iters[lvl]++;
+        const int r = lane & 7;
+        const float lambda = ctl.lambda;
+        const bool fixA = tc.affineOptModeA < 0, fixB = tc.affineOptModeB < 0;
+        const int nv = (!fixA && !fixB) ? 8 : ((fixA && fixB) ? 6 : 7);
+        const bool stitch = fixA && !fixB;                   // fix a only: b takes slot 6 (:736-748)
+        const int rr = (stitch && r == 6) ? 7 : r;
+        double a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int cc = (stitch && j == 6) ? 7 : j;
+          double hv = ctl.H[rr*8 + cc];
+          if (rr == cc) hv *= (1 + lambda);
+          a[j] = (r < nv && j < nv) ? hv : ((r == j) ? 1.0 : 0.0);
+        }
+        double rhs = (r < nv) ? -ctl.b[rr] : 0.0;
+        const double x = warp_ldlt_solve8(a, rhs);
+        double inc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) inc[j] = __shfl_sync(0xffffffffu, x, j, 8);
+        if (fixA && fixB) { inc[6] = 0; inc[7] = 0; }
+        else if (!fixA && fixB) { inc[7] = 0; }
+        else if (stitch) { inc[7] = inc[6]; inc[6] = 0; }
+        float extrapFac = 1;
+        if (lambda < lambdaExtrapolationLimit) extrapFac = sqrtf(sqrtf(lambdaExtrapolationLimit / lambda));
+#pragma unroll
+        for (int i = 0; i < 8; i++) inc[i] *= extrapFac;
+        double incScaled[8];
+#pragma unroll
+        for (int i = 0; i < 3; i++) incScaled[i] = inc[i]*1.0f;        // SCALE_XI_ROT   (:755)
+#pragma unroll
+        for (int i = 3; i < 6; i++) incScaled[i] = inc[i]*0.5f;        // SCALE_XI_TRANS (:756)
+        incScaled[6] = inc[6]*10.0f; incScaled[7] = inc[7]*1000.0f;    // SCALE_A, SCALE_B
+        double s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += incScaled[i];
+        if (!isfinite(s)) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) incScaled[i] = 0;
+        }
+        double incn = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) incn += inc[i]*inc[i];
+        incn = sqrt(incn);
+        if (lane == 0) {
+          const SE3d cand = se3_mul(se3_exp(incScaled), ctl.cur);
+          const double a_cand = ctl.a_cur + incScaled[6], b_cand = ctl.b_cur + incScaled[7];
+          ctl.cand = cand; ctl.a_cand = a_cand; ctl.b_cand = b_cand; ctl.incn = incn; ctl.mode = 1;
+          make_eval_params(cand, a_cand, b_cand, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl, tc.coarseCutoffTH*ctl.lcr, tc.huberTH, ctl.ep);
+        }
+      }
+    }
+    __syncthreads();
+    if (ctl.done) break;
+  }
+
+  if (rank == 0 && tid == 0) {
+    int good = 0;
+    if (!ctl.aborted) {
+      se3_to7(ctl.cur, J.T);
+      double a_out = ctl.a_cur, b_out = ctl.b_cur;
+      good = 1;
+      if ((tc.affineOptModeA != 0 && (fabsf((float)a_out) > 1.2f)) || (tc.affineOptModeB != 0 && (fabsf((float)b_out) > 200))) good = 0;
+      if (good) {
+        double rel[2]; aff_from_to(J.refExposure, J.newExposure, J.ref_a, J.ref_b, a_out, b_out, rel);
+        float r0 = (float)rel[0], r1 = (float)rel[1];
+        if ((tc.affineOptModeA == 0 && (fabsf(logf(r0)) > 1.5f)) || (tc.affineOptModeB == 0 && (fabsf(r1) > 200))) good = 0;
+        if (good) { if (tc.affineOptModeA < 0) a_out = 0; if (tc.affineOptModeB < 0) b_out = 0; }
+      }
+      J.ab[0] = a_out; J.ab[1] = b_out;
+    }
+    J.good = good;
+    for (int i = 0; i < 5; i++) J.lastRes[i] = ctl.lastRes[i];
+    for (int i = 0; i < 3; i++) J.flow[i] = ctl.flow[i];
+    for (int i = 0; i < kLevels; i++) { J.point_evals[i] = ctl.evals[i]; J.iterations[i] = ctl.iters[i]; J.accepts[i] = ctl.accs[i]; }
+  }
+  if (C > 1) cluster.sync();                                // keep every CTA's shared memory alive until all remote writes/reads are done
+}
+
+template <int THREADS>
+static size_t track_kernel_smem_v2() {
+  size_t stage = (size_t)2*4*THREADS*16 + (size_t)2*kPtChunk*THREADS*16, red = (size_t)kNAcc*THREADS*sizeof(float);
+  return (stage > red ? stage : red) + (size_t)(2*kMaxCluster*kNAcc + 2*kNAcc)*sizeof(double);
+}
+
 template <int THREADS>
 static size_t track_kernel_smem() { return (size_t)kNAcc*THREADS*sizeof(float) + (size_t)(2*kMaxCluster*kNAcc + 2*kNAcc)*sizeof(double); }
 
-template <int THREADS, int MINB>
-static cudaError_t launch_track_t(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
-  static bool attr_set = false;
-  size_t smem = track_kernel_smem<THREADS>();
-  auto kern = track_cluster_kernel<THREADS, MINB>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1); if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+static bool track_use_v1() { static int v = -1; if (v < 0) { const char* e = getenv("SDV_TRACK_IMPL"); v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; } return v == 1; }
+
+template <typename Kern>
+static cudaError_t launch_track_kern(Kern kern, size_t smem, int threads, TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(njobs*cluster_size)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(njobs*cluster_size)); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, jobs_dev, tc_dev);
+}
+template <int THREADS, int MINB>
+static cudaError_t launch_track_t(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
+  if (track_use_v1()) return launch_track_kern(track_cluster_v1_kernel<THREADS, MINB>, track_kernel_smem<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st);
+  return launch_track_kern(track_cluster_kernel<THREADS, MINB>, track_kernel_smem_v2<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st);
+}
+template <typename Kern>
+static cudaError_t track_attrs(Kern kern, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 }
 // threads: 128 (throughput, 4 jobs resident per SM) or 256 (latency)
 #ifndef SDV_TRACK_MINB
@@ -428,6 +843,19 @@ cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst
   if (threads == 256) return launch_track_t<256, 1>(jobs_dev, njobs, tc_dev, cluster_size, st);
   if (threads == 64)  return launch_track_t<64, 8>(jobs_dev, njobs, tc_dev, cluster_size, st);
   return launch_track_t<128, SDV_TRACK_MINB>(jobs_dev, njobs, tc_dev, cluster_size, st);
+}
+
+// Function attributes (opt-in dynamic shared memory, non-portable cluster sizes) belong to the CURRENT DEVICE's copy of a kernel: sdv_create calls this
+// after cudaSetDevice, so a second context on another device of the same process gets them too (a process-wide "already set" flag did not).
+cudaError_t kernels_init_device() {
+  cudaError_t e = cudaFuncSetAttribute(coarse_res_gs_kernel<kStepThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kNAcc*kStepThreads*sizeof(float)));
+  if (e != cudaSuccess) return e;
+#define SDV_TRACK_ATTRS(T, M) \
+  if ((e = track_attrs(track_cluster_v1_kernel<T, M>, track_kernel_smem<T>())) != cudaSuccess) return e; \
+  if ((e = track_attrs(track_cluster_kernel<T, M>, track_kernel_smem_v2<T>())) != cudaSuccess) return e;
+  SDV_TRACK_ATTRS(256, 1) SDV_TRACK_ATTRS(64, 8) SDV_TRACK_ATTRS(128, SDV_TRACK_MINB)
+#undef SDV_TRACK_ATTRS
+  return cudaSuccess;
 }
 
 __global__ void h2d_words_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
@@ -527,7 +955,7 @@ __global__ void cd_scan_kernel(int* blockCounts, int nblocks, int* total) {   //
   if (threadIdx.x == 0) *total = carry;
 }
 __global__ void __launch_bounds__(kScanThreads) cd_emit_kernel(const float* __restrict__ id, const float* __restrict__ ws, const float4* __restrict__ ref, const float* __restrict__ ref0, int w, int h,
-                                                              const int* __restrict__ blockOffsets, float4* out) {
+                                                              const int* __restrict__ blockOffsets, float4* out, int cap) {
   __shared__ int s[kScanThreads/32];
   int base = (blockIdx.x*kScanThreads + threadIdx.x)*kScanItems; int n = w*h;
   float idn[kScanItems], col[kScanItems]; bool ok[kScanItems]; int c = 0;
@@ -538,7 +966,8 @@ __global__ void __launch_bounds__(kScanThreads) cd_emit_kernel(const float* __re
   __syncthreads();
   int woff = 0; for (int k = 0; k < warp; k++) woff += s[k];
   int pos = blockOffsets[blockIdx.x] + woff + incl - c;
-  for (int j = 0; j < kScanItems; j++) if (ok[j]) { int i = base + j; int y = i / w, x = i - y*w; out[pos++] = make_float4((float)x, (float)y, idn[j], col[j]); }
+  // cap = capacity of `out` (max_ref_points may make it smaller than the cloud): never write past it — the host compares the scanned total with cap afterwards
+  for (int j = 0; j < kScanItems; j++) if (ok[j]) { int i = base + j; int y = i / w, x = i - y*w; if (pos < cap) out[pos] = make_float4((float)x, (float)y, idn[j], col[j]); pos++; }
 }
 
 int cd_num_blocks(int w, int h) { return (w*h + kScanThreads*kScanItems - 1)/(kScanThreads*kScanItems); }
@@ -559,11 +988,11 @@ void launch_cd_pool(const float* id_lm, const float* ws_lm, float* id_l, float* 
 void launch_cd_dilate(const float* id_in, const float* bak, float* id_out, float* ws_out, int w, int h, int diag, cudaStream_t st) {
   cd_dilate_kernel<<<(w*h+255)/256, 256, 0, st>>>(id_in, bak, id_out, ws_out, w, h, diag);
 }
-void launch_cd_compact(const float* id, const float* ws, const float4* ref, const float* ref0, int w, int h, int* blockCounts, int* total, float4* out, cudaStream_t st) {
+void launch_cd_compact(const float* id, const float* ws, const float4* ref, const float* ref0, int w, int h, int* blockCounts, int* total, float4* out, int cap, cudaStream_t st) {
   int nb = cd_num_blocks(w, h);
   cd_count_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, ref0, w, h, blockCounts);
   cd_scan_kernel<<<1, 1024, 0, st>>>(blockCounts, nb, total);
-  cd_emit_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, ref0, w, h, blockCounts, out);
+  cd_emit_kernel<<<nb, kScanThreads, 0, st>>>(id, ws, ref, ref0, w, h, blockCounts, out, cap);
 }
 
 __global__ void pack_cloud_kernel(const float* u, const float* v, const float* id, const float* col, int n, float4* out) {

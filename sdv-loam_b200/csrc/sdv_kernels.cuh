@@ -12,6 +12,7 @@ void launch_pyramid_copy0(const void* batch_dev, int nframes, bool src_u8, int w
 void launch_pyramid_level0_texels(const float* I0, float4* out, int w, int h, cudaStream_t st);
 void launch_unpack_level(const float4* in, float* dI3, float* ab, int n, cudaStream_t st);
 
+cudaError_t kernels_init_device();        // per-device function attributes of the tracker kernels (called by sdv_create after cudaSetDevice)
 // fused calcRes + calcGSSSE, one launch (CoarseTracker.cpp:486-634, 427-484)
 int  step_kernel_max_grid();
 void launch_coarse_res_gs(const float4* pts, int n, const float4* img, const float* I0, const LevelGeom& g, const EvalParams& ep,
@@ -29,7 +30,7 @@ void launch_cd_prep(const float* pts4, const int* round_half, int n, int w, floa
 void launch_cd_round(const float4* splats, int n, int* done, int* owner, float* idepth, float* ws, int* remaining, cudaStream_t st);
 void launch_cd_pool(const float* id_lm, const float* ws_lm, float* id_l, float* ws_l, int wl, int hl, int wlm1, cudaStream_t st);
 void launch_cd_dilate(const float* id_in, const float* bak, float* id_out, float* ws_out, int w, int h, int diag, cudaStream_t st);
-void launch_cd_compact(const float* id, const float* ws, const float4* ref, const float* ref0, int w, int h, int* blockCounts, int* total, float4* out, cudaStream_t st);
+void launch_cd_compact(const float* id, const float* ws, const float4* ref, const float* ref0, int w, int h, int* blockCounts, int* total, float4* out, int cap, cudaStream_t st);
 void launch_pack_cloud(const float* u, const float* v, const float* id, const float* col, int n, float4* out, cudaStream_t st);
 
 } // namespace sdv

@@ -195,9 +195,10 @@ __global__ void __launch_bounds__(kRefThreads) struct_pose_kernel(RefineJob* job
   if (threadIdx.x == 0) { jb.res = s_resOld; jb.num = S.num; }
 }
 
+cudaError_t refine_init_device() {         // per-device opt-in shared memory size (called by sdv_create after cudaSetDevice)
+  return cudaFuncSetAttribute(struct_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefShared));
+}
 void launch_struct_pose(RefineJob* jobs, int n_jobs, const sdv_overlap_pt* pts, const double* hostT7, const TrackConst* tc, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(struct_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RefShared)); attr_set = true; }
   struct_pose_kernel<<<n_jobs, kRefThreads, sizeof(RefShared), st>>>(jobs, pts, hostT7, tc);
 }
 
@@ -220,7 +221,7 @@ int sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_begi
                                   double* curToWorld_io, float* res_out, int32_t* iterations, int32_t* accepts) {
   if (!c || n_jobs <= 0 || !pt_begin || !host_begin || !host_T7 || !curToWorld_io) return SDV_ERR_ARG;
   const int nP = pt_begin[n_jobs], nH = host_begin[n_jobs];
-  if (nP < 0 || nH <= 0 || (nP > 0 && !pts)) return SDV_ERR_ARG;
+  if (pt_begin[0] != 0 || host_begin[0] != 0 || nP < 0 || nH <= 0 || (nP > 0 && !pts)) return SDV_ERR_ARG;   // both CSRs start at 0: nothing is indexed below it
   for (int k=0;k<n_jobs;k++) {
     int hs = host_begin[k+1]-host_begin[k];
     if (pt_begin[k+1] < pt_begin[k] || hs < 0 || hs > kRefMaxHosts) return ctx_fail(c, SDV_ERR_ARG, "struct_pose job %d: bad ranges (hosts %d, max %d)", k, hs, kRefMaxHosts);

@@ -14,6 +14,7 @@ struct RefineJob {
   float res; int iterations, accepts, num;
 };
 
+cudaError_t refine_init_device();
 void launch_struct_pose(RefineJob* jobs, int n_jobs, const sdv_overlap_pt* pts, const double* hostT7, const TrackConst* tc, cudaStream_t st);
 
 } // namespace sdv

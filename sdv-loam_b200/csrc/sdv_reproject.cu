@@ -290,7 +290,7 @@ namespace sdv {
 struct MapSlot { long long ingest_seq = 0; MapDev host_copy; MapDev* dev = nullptr; sdv_map_pt* pts = nullptr; int cap = 0; int nH = 0, nP = 0; uint64_t host_ids[kRpMaxHosts]; double host_ab[kRpMaxHosts][2]; float host_exposure[kRpMaxHosts]; bool set = false; };
 struct RpState { std::vector<MapSlot> maps; void* dev = nullptr; void* host = nullptr; size_t cap = 0, host_cap = 0; RpConst C; bool c_ready = false; };
 static RpState* rp_state(sdv_ctx* c) { if (!c->rp) { c->rp = new RpState(); c->rp->maps.resize(c->slots.size()); } return c->rp; }
-void rp_destroy(sdv_ctx* c) { if (!c->rp) return; for (auto& m : c->rp->maps) { cudaFree(m.dev); cudaFree(m.pts); } cudaFree(c->rp->dev); cudaFreeHost(c->rp->host); delete c->rp; c->rp = nullptr; }
+void rp_destroy(sdv_ctx* c) { if (!c->rp) return; for (auto& m : c->rp->maps) { if (m.set) for (int k=0;k<m.nH;k++) frame_unpin(c, m.host_ids[k]); cudaFree(m.dev); cudaFree(m.pts); } cudaFree(c->rp->dev); cudaFreeHost(c->rp->host); delete c->rp; c->rp = nullptr; }
 static void rp_const(sdv_ctx* c, RpState* st) {
   if (st->c_ready) return; RpConst& C = st->C; const LevelGeom& g = c->tc.geom[0];
   for (int i=0;i<9;i++) C.K[i] = 0; C.K[0] = (double)g.fx; C.K[2] = (double)g.cx; C.K[4] = (double)g.fy; C.K[5] = (double)g.cy; C.K[8] = 1.0;
@@ -319,8 +319,11 @@ int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const
   if (!m.dev) CK(cudaMalloc(&m.dev, sizeof(MapDev)));
   if (nP > m.cap) { cudaFree(m.pts); m.pts = nullptr; m.cap = nP + nP/4 + 256; CK(cudaMalloc(&m.pts, (size_t)m.cap*sizeof(sdv_map_pt))); }
   { int rcj = join_ingest(c); if (rcj) return rcj; }
+  for (int k=0;k<nH;k++) if (c->frame_index.find(host_frames[k]) == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "map_set: unknown keyframe handle (host %d)", k);
+  if (m.set) for (int k=0;k<m.nH;k++) frame_unpin(c, m.host_ids[k]);       // the slot's previous keyframes are no longer referenced by it
+  for (int k=0;k<nH;k++) frame_pin(c, host_frames[k]);
   MapDev& h = m.host_copy; memset(&h, 0, sizeof(h)); h.nH = nH; h.nP = nP; h.pts = m.pts; m.ingest_seq = 0;
-  for (int k=0;k<nH;k++) { auto it = c->frame_index.find(host_frames[k]); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "map_set: unknown keyframe handle (host %d)", k);
+  for (int k=0;k<nH;k++) { auto it = c->frame_index.find(host_frames[k]);
     const FrameDev& f = c->frames[it->second]; h.hostI0[k] = f.I0; m.host_exposure[k] = f.exposure; m.host_ids[k] = host_frames[k]; if (f.ingest_seq > m.ingest_seq) m.ingest_seq = f.ingest_seq;
     for (int i=0;i<7;i++) h.hostT[k][i] = host_T7[7*k+i]; m.host_ab[k][0] = host_ab ? host_ab[2*k] : 0.0; m.host_ab[k][1] = host_ab ? host_ab[2*k+1] : 0.0; }
   m.nH = nH; m.nP = nP; m.set = true;
@@ -329,6 +332,14 @@ int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const
   if (nP) CK(cudaMemcpyAsync(m.pts, pts, (size_t)nP*sizeof(sdv_map_pt), cudaMemcpyHostToDevice, c->st));
   CK(cudaStreamSynchronize(c->st));
   return SDV_OK;
+}
+
+int sdv_map_clear(sdv_ctx* c, int slot) {
+  if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); RpState* st = rp_state(c);
+  if (slot < 0 || slot >= (int)st->maps.size()) return SDV_ERR_ARG;
+  MapSlot& m = st->maps[slot]; if (!m.set) return SDV_OK;
+  CK(cudaStreamSynchronize(c->st));                                            // a launch may still read the slot
+  for (int k=0;k<m.nH;k++) frame_unpin(c, m.host_ids[k]); m.set = false; m.nH = 0; m.nP = 0; return SDV_OK;
 }
 
 // shared front half: builds the jobs, sizes the scratch and launches project / scan / scatter / match.  Results stay on the device.
