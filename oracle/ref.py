@@ -1,0 +1,174 @@
+"""ctypes binding of oracle/_ref/libsdvref.so — the reference's OWN hot-path sources (unmodified, /root/reference/src) compiled against the
+stand-in headers of oracle/ref_stub/ (see oracle/Makefile, oracle/ref_shim.cpp).  TEST INFRASTRUCTURE ONLY.
+
+What it is for: pinning the oracle restatement (oracle/orc_*.cpp) on reference-compiled code (tests/test_ref_pin.py) and, where the library
+exists, serving as the "reference" CPU arm of bench.py.  It is built only where /root/reference exists; elsewhere the prebuilt .so is used.
+The reference keeps its calibration and settings in process globals (util/globalCalib.cpp, util/settings.cpp): one image size at a time.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libsdvref.so")
+REF_SRC = "/root/reference/src"
+_LIB = None
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
+
+
+def available() -> bool:
+    return os.path.exists(SO) or os.path.isdir(REF_SRC)
+
+
+def build(force: bool = False) -> str | None:
+    """Compile the reference translation units (only possible where /root/reference exists); returns the .so path or None."""
+    if os.path.isdir(REF_SRC):
+        deps = [os.path.join(_HERE, "ref_shim.cpp"), os.path.join(_HERE, "orc_math.hpp"), os.path.join(_HERE, "Makefile")]
+        for d, _, fs in os.walk(os.path.join(_HERE, "ref_stub")):
+            deps += [os.path.join(d, f) for f in fs]
+        stale = force or not os.path.exists(SO) or any(os.path.getmtime(p) > os.path.getmtime(SO) for p in deps)
+        if stale:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-j8", "ref"])
+    return SO if os.path.exists(SO) else None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = build()
+        if so is None:
+            raise RuntimeError("oracle/_ref/libsdvref.so is not built and /root/reference is absent")
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        L = C.CDLL(so, mode=os.RTLD_NOW)
+        os.close(devnull)
+        L.ref_set_calib.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+        L.ref_get_global_K.argtypes = [C.c_int, _f32p, _f32p]
+        L.ref_settings.argtypes = [C.c_float] * 4
+        L.ref_frame_create.restype = _vp; L.ref_frame_create.argtypes = [_f32p, C.c_float]
+        L.ref_frame_destroy.argtypes = [_vp]
+        L.ref_frame_dI.restype = C.POINTER(C.c_float); L.ref_frame_dI.argtypes = [_vp, C.c_int]
+        L.ref_frame_abs.restype = C.POINTER(C.c_float); L.ref_frame_abs.argtypes = [_vp, C.c_int]
+        L.ref_tracker_create.restype = _vp; L.ref_tracker_create.argtypes = []
+        L.ref_tracker_destroy.argtypes = [_vp]
+        L.ref_tracker_get_K.argtypes = [_vp, C.c_int, _f32p]; L.ref_tracker_get_Ki.argtypes = [_vp, C.c_int, _f32p]
+        L.ref_tracker_set_ref.argtypes = [_vp, _vp, _vp, _f32p, _i32p, C.c_int, C.c_double, C.c_double]
+        L.ref_tracker_cloud_n.argtypes = [_vp, C.c_int]
+        L.ref_tracker_get_cloud.argtypes = [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p]
+        L.ref_tracker_calc_res.argtypes = [_vp, _vp, C.c_int, _f64p, C.c_double, C.c_double, C.c_float, _f64p]
+        L.ref_tracker_warped_n.argtypes = [_vp]; L.ref_tracker_get_warped.argtypes = [_vp, _f32p]
+        L.ref_tracker_calc_gs.argtypes = [_vp, C.c_int, _f64p, C.c_double, C.c_double, _f64p, _f64p]
+        L.ref_tracker_track.argtypes = [_vp, _vp, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p]
+        L.ref_interp33.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
+        L.ref_interp33_bilin.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
+        L.ref_aff_from_to.argtypes = [C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, _f64p]
+        _LIB = L
+    return _LIB
+
+
+class _Quiet:
+    """setGlobalCalib printf()s: keep the reference's stdout chatter out of test output"""
+    def __enter__(self):
+        import sys
+        sys.stdout.flush(); self.fd = os.dup(1); dn = os.open(os.devnull, os.O_WRONLY); os.dup2(dn, 1); os.close(dn)
+    def __exit__(self, *a):
+        C.CDLL(None).fflush(None); os.dup2(self.fd, 1); os.close(self.fd)
+
+
+def set_calib(w, h, K) -> int:
+    """setGlobalCalib + CalibHessian: returns pyrLevelsUsed.  Process-global, like the reference."""
+    with _Quiet():
+        return lib().ref_set_calib(w, h, *[float(k) for k in K])
+
+
+def settings(huberTH=6.0, coarseCutoffTH=20.0, affA=0.0, affB=0.0):
+    lib().ref_settings(huberTH, coarseCutoffTH, affA, affB)
+
+
+def global_K(lvl):
+    a = np.zeros(4, np.float32); b = np.zeros(4, np.float32); lib().ref_get_global_K(lvl, a, b); return a, b
+
+
+class Frame:
+    """FrameHessian after makeImages (HessianBlocks.cpp:107-167)."""
+
+    def __init__(self, color, wh, levels, exposure: float = 1.0):
+        self.w, self.h = wh; self.levels = levels
+        color = np.ascontiguousarray(color, np.float32); assert color.shape == (self.h, self.w)
+        self.p = lib().ref_frame_create(color, exposure)
+
+    def dI(self, lvl):
+        w, h = self.w >> lvl, self.h >> lvl
+        return np.ctypeslib.as_array(lib().ref_frame_dI(self.p, lvl), shape=(h, w, 3)).copy()
+
+    def absSquaredGrad(self, lvl):
+        w, h = self.w >> lvl, self.h >> lvl
+        return np.ctypeslib.as_array(lib().ref_frame_abs(self.p, lvl), shape=(h, w)).copy()
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            _LIB.ref_frame_destroy(self.p); self.p = None
+
+
+class CoarseTracker:
+    """The reference's CoarseTracker (FullSystem/CoarseTracker.cpp) behind the flat signatures of orc.CoarseTracker."""
+
+    def __init__(self):
+        self.p = lib().ref_tracker_create(); self._keep = None
+
+    def K(self, lvl):
+        o = np.zeros(4, np.float32); lib().ref_tracker_get_K(self.p, lvl, o); return o
+
+    def Ki(self, lvl):
+        o = np.zeros(9, np.float32); lib().ref_tracker_get_Ki(self.p, lvl, o); return o.reshape(3, 3)
+
+    def setCoarseTrackingRef(self, ref: Frame, pts, round_half, ref_a=0.0, ref_b=0.0, old: Frame | None = None):
+        """pts (n,4) {u,v,idepth,HdiF}; rows with round_half != 0 (points of older keyframes, need `old`) must come first."""
+        self._keep = (ref, old)
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 4); rh = np.ascontiguousarray(round_half, np.int32)
+        rc = lib().ref_tracker_set_ref(self.p, ref.p, None if old is None else old.p, pts, rh, len(pts), ref_a, ref_b)
+        if rc != 0:
+            raise ValueError("round_half rows must precede the direct rows and need an `old` frame")
+
+    def cloud(self, lvl):
+        n = lib().ref_tracker_cloud_n(self.p, lvl); a = [np.zeros(max(n, 1), np.float32) for _ in range(4)]
+        lib().ref_tracker_get_cloud(self.p, lvl, *a); return [x[:n] for x in a]
+
+    def calcRes(self, new: Frame, lvl, T7, a, b, cutoff):
+        rs = np.zeros(6); lib().ref_tracker_calc_res(self.p, new.p, lvl, np.ascontiguousarray(T7, np.float64), a, b, cutoff, rs); return rs
+
+    def warped(self):
+        n = lib().ref_tracker_warped_n(self.p); o = np.zeros((8, max(n, 1)), np.float32)
+        if n:
+            o = np.zeros((8, n), np.float32); lib().ref_tracker_get_warped(self.p, o)
+            return o
+        return o[:, :0]
+
+    def calcGSSSE(self, lvl, T7, a, b):
+        H = np.zeros(64); bb = np.zeros(8); lib().ref_tracker_calc_gs(self.p, lvl, np.ascontiguousarray(T7, np.float64), a, b, H, bb); return H.reshape(8, 8), bb
+
+    def trackNewestCoarse(self, new: Frame, T7, ab, coarsest, minRes=None):
+        T = np.array(T7, np.float64); abv = np.array(ab, np.float64)
+        minRes = np.full(5, np.nan) if minRes is None else np.ascontiguousarray(minRes, np.float64)
+        lastRes = np.zeros(5); flow = np.zeros(3)
+        with _Quiet():
+            good = lib().ref_tracker_track(self.p, new.p, T, abv, coarsest, minRes, lastRes, flow)
+        return dict(good=bool(good), T=T, ab=abv, lastResiduals=lastRes, flow=flow)
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            _LIB.ref_tracker_destroy(self.p); self.p = None
+
+
+def interp33(dI3, x, y, bilin=False):
+    dI3 = np.ascontiguousarray(dI3, np.float32); o = np.zeros(3, np.float32)
+    (lib().ref_interp33_bilin if bilin else lib().ref_interp33)(dI3.reshape(-1), dI3.shape[1], x, y, o); return o
+
+
+def aff_from_to(eF, eT, aF, bF, aT, bT):
+    o = np.zeros(2); lib().ref_aff_from_to(eF, eT, aF, bF, aT, bT, o); return o

@@ -1,0 +1,4 @@
+#pragma once   // stand-in (absent; not used on the hot path)
+#include "opencv2/core/core.hpp"
+#include "sensor_msgs/Image.h"
+namespace cv_bridge { struct CvImage { cv::Mat image; }; typedef std::shared_ptr<CvImage> CvImagePtr; typedef std::shared_ptr<const CvImage> CvImageConstPtr; }

@@ -532,6 +532,17 @@ __device__ __forceinline__ void flow_point(const float4 p, const LevelGeom& g, c
   acc[kIdxFlowN]  += 2.0f;
 }
 
+#ifdef SDV_TRACK_PROFILE
+__device__ long long g_track_prof[16];
+#define SDV_PROF_T(var) long long var = clock64()
+#define SDV_PROF_ADD(slot, t0, t1) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_track_prof[slot] += (t1) - (t0); } while (0)
+#else
+#define SDV_PROF_T(var) do {} while (0)
+#define SDV_PROF_ADD(slot, t0, t1) do {} while (0)
+#endif
+#ifndef SDV_TRACK_STAGGER_DEFAULT_NS
+#define SDV_TRACK_STAGGER_DEFAULT_NS 0
+#endif
 constexpr int kPtChunk = 4;                                 // sweep iterations (blocks of THREADS points) per TMA-staged chunk
 
 struct Ctl2 {                                               // per-CTA LM state (every CTA of a cluster computes it redundantly and identically)
@@ -550,12 +561,16 @@ __constant__ unsigned char kAccRow[45] = {0,0,0,0,0,0,0,0,0, 1,1,1,1,1,1,1,1, 2,
 __constant__ unsigned char kAccCol[45] = {0,1,2,3,4,5,6,7,8, 1,2,3,4,5,6,7,8, 2,3,4,5,6,7,8, 3,4,5,6,7,8, 4,5,6,7,8, 5,6,7,8, 6,7,8, 7,8, 8};
 
 template <int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g) {
+__global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* __restrict__ jobs, const TrackConst* __restrict__ tc_g, unsigned stagger_ns) {
   cg::cluster_group cluster = cg::this_cluster();
   const int C = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x;
   TrackJob& J = jobs[blockIdx.x / C];
+  // Phase stagger: the MINB jobs co-resident on an SM run the same program on similar data and would reach their single-warp LM control steps
+  // together, leaving the SM idle; CTAs are dealt round-robin over the SMs, so wave j of the grid (blockIdx / #SMs-worth) starts j*stagger_ns late
+  // and one job's control step overlaps the other jobs' sweeps.
+  if (stagger_ns && C == 1) { const unsigned wave = (unsigned)(((unsigned long long)blockIdx.x*MINB)/gridDim.x); for (unsigned k = 0; k < wave; k++) __nanosleep(stagger_ns); }
 
   // dynamic smem: [ tap ring 2 x 4 x THREADS x 16 B | point chunks 2 x kPtChunk x THREADS x 16 B ] aliased by the reduction scratch [kNAcc][THREADS] floats,
   // then the DSMEM gather buffers and the reduced sums
@@ -618,7 +633,11 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         for (int j = 0; j < kPtChunk; j++) if (cnt[j] > 0)
           bulk_g2s(pbuf + (b*kPtChunk + j)*THREADS, pts + (size_t)(c*kPtChunk + j)*stride + rank*THREADS, (uint32_t)cnt[j]*16u, &full_bar[b]);
       };
+      SDV_PROF_T(tp0);
+#ifndef SDV_PTS_LDG
       if (tid == 0) { if (NC > 0) issue_chunk(0); if (NC > 1) issue_chunk(1); }
+#endif
+      SDV_PROF_T(tp1); SDV_PROF_ADD(0, tp0, tp1);
       if (lvl == 0) {                                       // dense flow-indicator pre-pass: point indices 0, 32, 64, ...
         for (int j = rank*THREADS + tid; 32*j < n; j += stride) flow_point(__ldg(pts + 32*j), g, ctl.ep, acc);
       }
@@ -627,24 +646,36 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         const int i = m*stride + rank*THREADS + tid;
         PtState s; s.ok = false; s.u = s.v = s.nid = s.dx = s.dy = s.col = 0.f;
         if (i < n) {
+#ifdef SDV_PTS_LDG
+          const float4 p = __ldg(pts + i);
+#else
           const float4 p = pbuf[(((m/kPtChunk) & 1)*kPtChunk + (m % kPtChunk))*THREADS + tid];
+#endif
           const uint32_t so = (uint32_t)(m & 1)*kSlotStride;
           s = (lvl == 0) ? stage_project<THREADS, true>(p, g, ctl.ep, img, I0, slot_base0 + so) : stage_project<THREADS, false>(p, g, ctl.ep, img, I0, slot_base + so);
         }
         return s;
       };
+      SDV_PROF_T(tp2); SDV_PROF_ADD(1, tp1, tp2);
+#ifdef SDV_PTS_LDG
+      if (K > 0) sN = project(0);
+#else
       if (K > 0) { mbar_wait(&full_bar[0], bar_phase & 1u); bar_phase ^= 1u; sN = project(0); }
+#endif
       cp_async_commit();
+      SDV_PROF_T(tp3); SDV_PROF_ADD(2, tp2, tp3);
       for (int k = 0; k < K; k++) {
         const PtState sC = sN;
         const int m = k + 1;
         if (m < K) {
+#ifndef SDV_PTS_LDG
           if (m % kPtChunk == 0) {                          // entering chunk c: everyone is done reading chunk c-1, its buffer can take chunk c+1
             const int c = m / kPtChunk;
             __syncthreads();
             if (tid == 0 && c + 1 < NC) issue_chunk(c + 1);
             mbar_wait(&full_bar[c & 1], (bar_phase >> (c & 1)) & 1u); bar_phase ^= (1u << (c & 1));
           }
+#endif
           sN = project(m);
         }
         cp_async_commit();
@@ -653,8 +684,10 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         if (lvl == 0) stage_accumulate<THREADS, true>(sC, g, ctl.ep, slot + tid*4, acc);
         else          stage_accumulate<THREADS, false>(sC, g, ctl.ep, slot + tid*16, acc);
       }
+      SDV_PROF_T(tp4); SDV_PROF_ADD(3, tp3, tp4);
       cp_async_wait0();
       __syncthreads();                                      // the reduction scratch aliases the tap ring / point chunks
+      SDV_PROF_T(tp5); SDV_PROF_ADD(4, tp4, tp5);
       block_reduce_acc<THREADS>(acc, red, bsum);
       if (C > 1) {
         const int buf = evalCount & 1;
@@ -671,7 +704,12 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       __syncthreads();
       evalCount++;
       if (tid == 0) ctl.evals[lvl] += n;
+      SDV_PROF_T(tp6); SDV_PROF_ADD(5, tp5, tp6);
+#ifdef SDV_TRACK_PROFILE
+      if (blockIdx.x == 0 && tid == 0) g_track_prof[8] += 1;
+#endif
     }
+    SDV_PROF_T(tc0);
     // ------------------------------------------------------------------ LM control (warp 0), CoarseTracker.cpp:679-812 as a state machine
     if (tid < 32) {
       const int lane = tid;
@@ -779,6 +817,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       }
     }
     __syncthreads();
+    SDV_PROF_T(tc1); SDV_PROF_ADD(6, tc0, tc1);
     if (ctl.done) break;
   }
 
@@ -816,19 +855,22 @@ static size_t track_kernel_smem() { return (size_t)kNAcc*THREADS*sizeof(float) +
 
 static bool track_use_v1() { static int v = -1; if (v < 0) { const char* e = getenv("SDV_TRACK_IMPL"); v = (e && e[0] == 'v' && e[1] == '1') ? 1 : 0; } return v == 1; }
 
-template <typename Kern>
-static cudaError_t launch_track_kern(Kern kern, size_t smem, int threads, TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
+static unsigned track_stagger_ns() { static long v = -1; if (v < 0) { const char* e = getenv("SDV_TRACK_STAGGER_NS"); v = e ? atol(e) : SDV_TRACK_STAGGER_DEFAULT_NS; if (v < 0) v = 0; } return (unsigned)v; }
+template <typename Kern, typename... Extra>
+static cudaError_t launch_track_kern(Kern kern, size_t smem, int threads, TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st, Extra... extra) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(njobs*cluster_size)); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cluster_size; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, jobs_dev, tc_dev);
+  return cudaLaunchKernelEx(&cfg, kern, jobs_dev, tc_dev, extra...);
 }
 template <int THREADS, int MINB>
 static cudaError_t launch_track_t(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, cudaStream_t st) {
   if (track_use_v1()) return launch_track_kern(track_cluster_v1_kernel<THREADS, MINB>, track_kernel_smem<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st);
-  return launch_track_kern(track_cluster_kernel<THREADS, MINB>, track_kernel_smem_v2<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st);
+  // stagger only when the grid fills the co-resident slots of the chip (otherwise there is nothing to desynchronise)
+  const unsigned stag = (cluster_size == 1 && njobs > 148) ? track_stagger_ns() : 0u;
+  return launch_track_kern(track_cluster_kernel<THREADS, MINB>, track_kernel_smem_v2<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st, stag);
 }
 template <typename Kern>
 static cudaError_t track_attrs(Kern kern, size_t smem) {
@@ -858,6 +900,14 @@ cudaError_t kernels_init_device() {
   return cudaSuccess;
 }
 
+#ifdef SDV_TRACK_PROFILE
+extern "C" int sdv_debug_track_profile(long long* out16, int reset) {
+  long long z[16] = {0};
+  if (out16 && cudaMemcpyFromSymbol(out16, g_track_prof, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(g_track_prof, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 __global__ void h2d_words_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
   for (size_t i = (size_t)blockIdx.x*blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x*blockDim.x) dst[i] = src[i];
 }
