@@ -538,6 +538,7 @@ void BAWindow::flagPointsForRemoval(const int* selected, int* status) {
     BAPoint& p = points[pi]; status[pi] = 0; if (!selected[pi]) continue;
     for (int ri=p.res_begin; ri<p.res_end; ri++) {
       BARes& r = res[ri];
+      if (r.toRemove) continue;                                                                              // deleted by linearizeAll(fix) in the reference (FullSystemOptimize.cpp:129-157) — found by the oracle/_ref pin
       r.state_NewEnergy = r.state_energy = 0; r.state_NewState = RS_OUTLIER; r.state_state = RS_IN;       // resetOOB
       linearizeOne(r);
       r.isLinearized = 0;

@@ -67,6 +67,32 @@ def lib():
         L.ref_interp33.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
         L.ref_interp33_bilin.argtypes = [_f32p, C.c_int, C.c_float, C.c_float, _f32p]
         L.ref_aff_from_to.argtypes = [C.c_float, C.c_float, C.c_double, C.c_double, C.c_double, C.c_double, _f64p]
+        L.ref_ba_create.restype = _vp; L.ref_ba_create.argtypes = []
+        L.ref_ba_destroy.argtypes = [_vp]
+        L.ref_ba_set_calib.argtypes = [_vp, _f64p]
+        L.ref_ba_add_frame.argtypes = [_vp, _vp, _f64p, _f64p, _f64p, C.c_float, C.c_int, C.c_float]
+        L.ref_ba_set_points.argtypes = [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _i32p, _i32p, _i32p]
+        L.ref_ba_set_residuals.argtypes = [_vp, C.c_int, _i32p, _i32p, _i32p, _i32p, _f32p, _i32p]
+        L.ref_ba_set_prior.argtypes = [_vp, _f64p, _f64p]
+        for nm in ("ref_ba_init", "ref_ba_reset_oob", "ref_ba_apply_res", "ref_ba_backup", "ref_ba_load_backup", "ref_ba_marginalize_points", "ref_ba_drop_points"):
+            getattr(L, nm).argtypes = [_vp]
+        L.ref_ba_linearize_all.argtypes = [_vp, C.c_int]; L.ref_ba_linearize_all.restype = C.c_double
+        L.ref_ba_energy_L.argtypes = [_vp]; L.ref_ba_energy_L.restype = C.c_double
+        L.ref_ba_energy_M.argtypes = [_vp]; L.ref_ba_energy_M.restype = C.c_double
+        L.ref_ba_get_residuals.argtypes = [_vp, _i32p, _i32p, _f64p, _i32p, _f32p, _f32p, _f32p, _f32p, _i32p]
+        L.ref_ba_accumulate.argtypes = [_vp, _f64p, _f64p, _f64p, _f64p]
+        L.ref_ba_solve.argtypes = [_vp, C.c_int, C.c_double, _f64p, _f64p, _f64p]
+        L.ref_ba_do_step.argtypes = [_vp, C.c_float]
+        L.ref_ba_optimize.argtypes = [_vp, C.c_int]; L.ref_ba_optimize.restype = C.c_float
+        L.ref_ba_get_points.argtypes = [_vp, _f32p, _f32p, _f32p, _f32p, _f32p, _i32p, _f32p]
+        L.ref_ba_get_frames.argtypes = [_vp, _f64p, _f64p, _f64p, _f32p, _f64p]
+        L.ref_ba_get_calib.argtypes = [_vp, _f64p, _f64p]
+        L.ref_ba_get_precalc.argtypes = [_vp, C.c_int, C.c_int, _f32p, _f64p, _f64p, _f32p]
+        L.ref_ba_flag_points.argtypes = [_vp, _i32p, _i32p]
+        L.ref_ba_marginalize_frame.argtypes = [_vp, C.c_int]
+        L.ref_ba_dim.argtypes = [_vp]
+        L.ref_ba_get_prior.argtypes = [_vp, _f64p, _f64p]
+        L.ref_ba_get_res_to_zero.argtypes = [_vp, _f32p, _i32p]
         _LIB = L
     return _LIB
 
@@ -172,3 +198,101 @@ def interp33(dI3, x, y, bilin=False):
 
 def aff_from_to(eF, eT, aF, bF, aT, bT):
     o = np.zeros(2); lib().ref_aff_from_to(eF, eT, aF, bF, aT, bT, o); return o
+
+
+class BAWindow:
+    """The flattened sliding window of synth.make_ba_window() loaded into the reference's own FullSystem / EnergyFunctional (ref_shim.cpp ref_ba_*).
+    Same methods as orc.BAWindow.  `frames`: ref.Frame objects of the window's keyframes (set_calib must match their size)."""
+
+    def __init__(self, win: dict, frames):
+        L = lib(); self.L = L; self.win = win; self._frames = frames
+        self.nF = win["nF"]; self.nP = len(win["uv"]); self.nR = len(win["r_point"]); self.n = 4 + 6 * self.nF
+        with _Quiet():
+            self.p = L.ref_ba_create()
+        L.ref_ba_set_calib(self.p, np.ascontiguousarray(win["K"], np.float64))
+        for i in range(self.nF):
+            L.ref_ba_add_frame(self.p, frames[i].p, np.ascontiguousarray(win["T_eval"][i]), np.ascontiguousarray(win["state"][i]), np.ascontiguousarray(win["state_zero"][i]),
+                               float(win["ab_exposure"][i]), int(win["frameID"][i]), float(win["frameEnergyTH"][i]))
+        c = lambda k, t: np.ascontiguousarray(win[k], t)
+        L.ref_ba_set_points(self.p, self.nP, c("uv", np.float32), c("idepth", np.float32), c("idepth_zero", np.float32), c("color", np.float32), c("weights", np.float32),
+                            c("host", np.int32), c("hasDepthPrior", np.int32), c("isFromSensor", np.int32), c("res_begin", np.int32))
+        L.ref_ba_set_residuals(self.p, self.nR, c("r_point", np.int32), c("r_host", np.int32), c("r_target", np.int32), c("r_hasMatcher", np.int32), c("r_matcher", np.float32), c("r_isNew", np.int32))
+        L.ref_ba_set_prior(self.p, c("HM", np.float64), c("bM", np.float64))
+        L.ref_ba_init(self.p)
+
+    def reset_oob(self): self.L.ref_ba_reset_oob(self.p)
+    def linearizeAll(self, fix=False):
+        with _Quiet():
+            return self.L.ref_ba_linearize_all(self.p, 1 if fix else 0)
+    def applyRes(self): self.L.ref_ba_apply_res(self.p)
+    def calcLEnergy(self): return self.L.ref_ba_energy_L(self.p)
+    def calcMEnergy(self): return self.L.ref_ba_energy_M(self.p)
+    def backupState(self): self.L.ref_ba_backup(self.p)
+    def doStepFromBackup(self, f=1.0): return bool(self.L.ref_ba_do_step(self.p, f))
+    def loadStateBackup(self): self.L.ref_ba_load_backup(self.p)
+
+    def residuals(self):
+        n = self.nR
+        o = dict(state=np.zeros(n, np.int32), new_state=np.zeros(n, np.int32), energies=np.zeros((n, 3)), active=np.zeros(n, np.int32), J=np.zeros((n, 24), np.float32),
+                 efJ=np.zeros((n, 24), np.float32), JpJdF=np.zeros((n, 8), np.float32), center=np.zeros((n, 3), np.float32), isLinearized=np.zeros(n, np.int32))
+        self.L.ref_ba_get_residuals(self.p, o["state"], o["new_state"], o["energies"], o["active"], o["J"], o["efJ"], o["JpJdF"], o["center"], o["isLinearized"]); return o
+
+    def accumulate(self):
+        n = self.L.ref_ba_dim(self.p); HA = np.zeros((n, n)); bA = np.zeros(n); Hsc = np.zeros((n, n)); bsc = np.zeros(n)
+        self.L.ref_ba_accumulate(self.p, HA, bA, Hsc, bsc); return HA, bA, Hsc, bsc
+
+    def solveSystem(self, iteration, lam):
+        n = self.L.ref_ba_dim(self.p); x = np.zeros(n); HS = np.zeros((n, n)); bS = np.zeros(n)
+        with _Quiet():
+            self.L.ref_ba_solve(self.p, iteration, lam, x, HS, bS)
+        return x, HS, bS
+
+    def points(self):
+        n = self.nP
+        o = dict(idepth=np.zeros(n, np.float32), step=np.zeros(n, np.float32), HdiF=np.zeros(n, np.float32), bdSumF=np.zeros(n, np.float32), maxRelBaseline=np.zeros(n, np.float32),
+                 numGood=np.zeros(n, np.int32), idepth_hessian=np.zeros(n, np.float32))
+        self.L.ref_ba_get_points(self.p, o["idepth"], o["step"], o["HdiF"], o["bdSumF"], o["maxRelBaseline"], o["numGood"], o["idepth_hessian"]); return o
+
+    def frames(self):
+        n = (self.L.ref_ba_dim(self.p) - 4) // 6
+        o = dict(T_eval=np.zeros((n, 7)), state=np.zeros((n, 10)), step=np.zeros((n, 10)), frameEnergyTH=np.zeros(n, np.float32), PRE_worldToCam=np.zeros((n, 7)))
+        self.L.ref_ba_get_frames(self.p, o["T_eval"], o["state"], o["step"], o["frameEnergyTH"], o["PRE_worldToCam"]); return o
+
+    def calib(self):
+        v = np.zeros(4); s = np.zeros(4); self.L.ref_ba_get_calib(self.p, v, s); return v, s
+
+    def precalc(self, host, target):
+        o = np.zeros(27, np.float32); aH = np.zeros(36); aT = np.zeros(36); d = np.zeros(6, np.float32)
+        self.L.ref_ba_get_precalc(self.p, host, target, o, aH, aT, d)
+        return dict(KRKi=o[:9].reshape(3, 3), Kt=o[9:12], R0=o[12:21].reshape(3, 3), t0=o[21:24], aff=o[24:26], b0=o[26], adHost=aH.reshape(6, 6), adTarget=aT.reshape(6, 6), adHTdelta=d)
+
+    def optimize(self, its=6):
+        with _Quiet():
+            rmse = self.L.ref_ba_optimize(self.p, its)
+        return dict(rmse=float(rmse))
+
+    def flagPointsForRemoval(self, selected):
+        st = np.zeros(self.nP, np.int32)
+        with _Quiet():
+            self.L.ref_ba_flag_points(self.p, np.ascontiguousarray(selected, np.int32), st)
+        return st
+
+    def marginalizePointsF(self):
+        with _Quiet():
+            self.L.ref_ba_marginalize_points(self.p)
+
+    def marginalizeFrame(self, idx):
+        with _Quiet():
+            self.L.ref_ba_marginalize_frame(self.p, int(idx))
+
+    def prior(self):
+        n = self.L.ref_ba_dim(self.p); HM = np.zeros((n, n)); bM = np.zeros(n); self.L.ref_ba_get_prior(self.p, HM, bM); return HM, bM
+
+    def res_to_zero(self):
+        r = np.zeros((self.nR, 2), np.float32); l = np.zeros(self.nR, np.int32); self.L.ref_ba_get_res_to_zero(self.p, r, l); return r, l
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            with _Quiet():
+                _LIB.ref_ba_destroy(self.p)
+            self.p = None

@@ -56,7 +56,7 @@ using namespace sdv_loam;
 namespace {
 CalibHessian* g_calib = nullptr;
 SE3 se3_from(const double T[7]) { orc::SE3 s; s.q = orc::Quat{T[0], T[1], T[2], T[3]}; s.t = orc::Vec3d{{T[4], T[5], T[6]}}; return SE3(s); }
-void se3_to(const SE3& S, double T[7]) { T[0] = S.s.q.w; T[1] = S.s.q.x; T[2] = S.s.q.y; T[3] = S.s.q.z; T[4] = S.s.t[0]; T[5] = S.s.t[1]; T[6] = S.s.t[2]; }
+void se3_to(const SE3& S, double T[7]) { T[0] = S.q.w; T[1] = S.q.x; T[2] = S.q.y; T[3] = S.q.z; T[4] = S.t_[0]; T[5] = S.t_[1]; T[6] = S.t_[2]; }
 
 struct RefFrame {                          // a FrameHessian with its FrameShell and the objects the shim hung on it
   FrameHessian* fh; FrameShell* shell;
@@ -172,5 +172,137 @@ void ref_interp33_bilin(const float* dI3, int w, float x, float y, float out3[3]
 void ref_aff_from_to(float eF, float eT, double aF, double bF, double aT, double bT, double out[2]) {   // AffLight::fromToVecExposure (util/NumType.h:149-158)
   Vec2 r = AffLight::fromToVecExposure(eF, eT, AffLight(aF, bF), AffLight(aT, bT)); out[0] = r[0]; out[1] = r[1];
 }
+
+// ---------------------------------------------------------------------------------------------- back-end: a FullSystem whose window is filled from flat arrays
+// The reference's own FullSystem (FullSystem.cpp ctor: trackers, selector, EnergyFunctional, mapping thread idle) with frameHessians / PointHessians /
+// PointFrameResiduals inserted through EnergyFunctional::insertFrame / insertPoint / insertResidual, i.e. what makeKeyFrame + activatePointsMT leave behind.
+// Same flat window layout as orc_ba_* (synth.make_ba_window): points grouped by host in frame order, residuals grouped per point.
+struct RefBA { FullSystem* fs; std::vector<RefFrame*> frames; std::vector<PointHessian*> pts; std::vector<ImmaturePoint*> ips; std::vector<PointFrameResidual*> res; std::vector<PointHessian*> res_pt; std::vector<char> dead; };
+// linearizeAll(fix) / flagPointsForRemoval DELETE residuals that went out of bounds (FullSystemOptimize.cpp:129-157): find out which of ours are gone (pointer compare only)
+static void refresh_dead(RefBA* b) {
+  b->dead.assign(b->res.size(), 1);
+  for (size_t i = 0; i < b->res.size(); i++) for (PointFrameResidual* r : b->res_pt[i]->residuals) if (r == b->res[i]) { b->dead[i] = 0; break; }
+}
+
+void* ref_ba_create() {
+  setting_logStuff = false; multiThreading = false; setting_debugout_runquiet = true;
+  RefBA* b = new RefBA(); b->fs = new FullSystem(); b->fs->linearizeOperation = true; return b;
+}
+void ref_ba_destroy(void* p) {       // the window's frames belong to the caller (RefFrame); points/residuals are ours: detach everything before ~FullSystem walks its lists
+  RefBA* b = (RefBA*)p; if (!b) return; FullSystem* fs = b->fs;
+  for (RefFrame* f : b->frames) { f->fh->pointHessians.clear(); f->fh->pointHessiansMarginalized.clear(); f->fh->pointHessiansOut.clear(); f->fh->efFrame = 0; }
+  fs->frameHessians.clear(); fs->activeResiduals.clear();
+  fs->blockUntilMappingIsFinished();
+  // leak the (small) reference-side graph rather than run destructors over a graph we assembled by hand
+  delete b;
+}
+void ref_ba_set_calib(void* p, const double vs[4]) { RefBA* b = (RefBA*)p; VecC v; for (int i = 0; i < 4; i++) v[i] = vs[i]; b->fs->Hcalib.setValueScaled(v); b->fs->Hcalib.value_zero = b->fs->Hcalib.value; b->fs->Hcalib.value_minus_value_zero.setZero(); }
+void ref_ba_add_frame(void* p, void* frame, const double T_eval[7], const double state[10], const double state_zero[10], float ab_exposure, int frameID, float frameEnergyTH) {
+  RefBA* b = (RefBA*)p; RefFrame* F = (RefFrame*)frame; FrameHessian* fh = F->fh; drop_points(F);
+  Vec10 st, sz; for (int i = 0; i < 10; i++) { st[i] = state[i]; sz[i] = state_zero[i]; }
+  fh->ab_exposure = ab_exposure; fh->frameID = frameID; fh->frameEnergyTH = frameEnergyTH; fh->flaggedForMarginalization = false;
+  fh->worldToCam_evalPT = se3_from(T_eval); fh->setState(st); fh->setStateZero(sz);
+  fh->idx = (int)b->fs->frameHessians.size(); b->fs->frameHessians.push_back(fh); b->frames.push_back(F);
+  b->fs->ef->insertFrame(fh, &b->fs->Hcalib);
+  fh->step.setZero(); fh->state_backup = fh->state; fh->step_backup.setZero();
+}
+void ref_ba_set_points(void* p, int nP, const float* uv, const float* idepth, const float* idepth_zero, const float* color, const float* weights,
+                       const int* host, const int* hasDepthPrior, const int* isFromSensor, const int* /*res_begin*/) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs;
+  for (int i = 0; i < nP; i++) {
+    FrameHessian* fh = fs->frameHessians[host[i]];
+    ImmaturePoint* ip = new ImmaturePoint((int)uv[2*i], (int)uv[2*i+1], fh, 0, &fs->Hcalib); ip->idepth_min = ip->idepth_max = idepth[i]; b->ips.push_back(ip);
+    PointHessian* ph = new PointHessian(ip, &fs->Hcalib);
+    ph->u = uv[2*i]; ph->v = uv[2*i+1]; for (int k = 0; k < 8; k++) { ph->color[k] = color[8*i+k]; ph->weights[k] = weights[8*i+k]; }
+    ph->setIdepth(idepth[i]); ph->setIdepthZero(idepth_zero[i]); ph->hasDepthPrior = hasDepthPrior[i] != 0; ph->isFromSensor = isFromSensor[i] != 0;
+    ph->setPointStatus(PointHessian::ACTIVE); ph->step = 0; ph->step_backup = 0; ph->idepth_backup = ph->idepth;
+    ph->lastResiduals[0] = std::pair<PointFrameResidual*, ResState>(0, ResState::OOB); ph->lastResiduals[1] = ph->lastResiduals[0];
+    fh->pointHessians.push_back(ph); fs->ef->insertPoint(ph); b->pts.push_back(ph);
+  }
+}
+void ref_ba_set_residuals(void* p, int nR, const int* point, const int* host, const int* target, const int* hasMatcher, const float* matcher, const int* isNew) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs;
+  for (int i = 0; i < nR; i++) {
+    PointHessian* ph = b->pts[point[i]];
+    PointFrameResidual* r = new PointFrameResidual(ph, fs->frameHessians[host[i]], fs->frameHessians[target[i]]);
+    r->hasMatcher = hasMatcher[i] != 0; r->matcher = Eigen::Vector2d(matcher[2*i], matcher[2*i+1]); r->isNew = isNew[i] != 0; r->setState(ResState::IN);
+    ph->residuals.push_back(r); fs->ef->insertResidual(r); fs->activeResiduals.push_back(r); b->res.push_back(r); b->res_pt.push_back(ph); b->dead.push_back(0);
+    ph->lastResiduals[1] = ph->lastResiduals[0]; ph->lastResiduals[0] = std::pair<PointFrameResidual*, ResState>(r, ResState::IN);
+  }
+}
+void ref_ba_set_prior(void* p, const double* HM, const double* bM) { RefBA* b = (RefBA*)p; EnergyFunctional* ef = b->fs->ef; int n = (int)ef->HM.rows();
+  for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) ef->HM(i, j) = HM[(size_t)i*n+j]; ef->bM[i] = bM[i]; } }
+void ref_ba_init(void* p) { RefBA* b = (RefBA*)p; b->fs->ef->makeIDX(); b->fs->ef->setAdjointsF(&b->fs->Hcalib); b->fs->setPrecalcValues(); }
+void ref_ba_reset_oob(void* p) { RefBA* b = (RefBA*)p; for (size_t i = 0; i < b->res.size(); i++) if (!b->dead[i]) b->res[i]->resetOOB(); }
+double ref_ba_linearize_all(void* p, int fix) { RefBA* b = (RefBA*)p; Vec3 v = b->fs->linearizeAll(fix != 0); refresh_dead(b); return v[0]; }
+void ref_ba_apply_res(void* p) { RefBA* b = (RefBA*)p; for (size_t i = 0; i < b->res.size(); i++) if (!b->dead[i]) b->res[i]->applyRes(true); }
+double ref_ba_energy_L(void* p) { return ((RefBA*)p)->fs->calcLEnergy(); }
+double ref_ba_energy_M(void* p) { return ((RefBA*)p)->fs->calcMEnergy(); }
+static void packJ(const RawResidualJacobian* J, float* o) { o[0] = J->resF[0]; o[1] = J->resF[1]; for (int i = 0; i < 6; i++) { o[2+i] = J->Jpdxi[0][i]; o[8+i] = J->Jpdxi[1][i]; }
+  for (int i = 0; i < 4; i++) { o[14+i] = J->Jpdc[0][i]; o[18+i] = J->Jpdc[1][i]; } o[22] = J->Jpdd[0]; o[23] = J->Jpdd[1]; }
+void ref_ba_get_residuals(void* p, int* state_state, int* state_NewState, double* energies3, int* isActive, float* J24, float* efJ24, float* JpJdF8, float* center3, int* isLinearized) {
+  RefBA* b = (RefBA*)p; int n = (int)b->res.size();
+  for (int i = 0; i < n; i++) { if (b->dead[i]) { state_state[i] = state_NewState[i] = -1; isActive[i] = 0; isLinearized[i] = 0; continue; }
+    const PointFrameResidual* r = b->res[i]; state_state[i] = (int)r->state_state; state_NewState[i] = (int)r->state_NewState;
+    energies3[3*i] = r->state_energy; energies3[3*i+1] = r->state_NewEnergy; energies3[3*i+2] = r->state_NewEnergyWithOutlier; isActive[i] = r->efResidual->isActive() ? 1 : 0;
+    packJ(r->J, J24+24*i); packJ(r->efResidual->J, efJ24+24*i); for (int k = 0; k < 8; k++) JpJdF8[8*i+k] = r->efResidual->JpJdF[k]; for (int k = 0; k < 3; k++) center3[3*i+k] = r->centerProjectedTo[k];
+    isLinearized[i] = r->efResidual->isLinearized ? 1 : 0; }
+}
+static void copy_mat(const MatXX& M, double* o) { int n = (int)M.rows(), m = (int)M.cols(); for (int i = 0; i < n; i++) for (int j = 0; j < m; j++) o[(size_t)i*m+j] = M(i, j); }
+void ref_ba_accumulate(void* p, double* HA, double* bA, double* Hsc, double* bsc) {       // EnergyFunctional::accumulateAF_MT / accumulateSCF_MT (single-threaded path)
+  RefBA* b = (RefBA*)p; EnergyFunctional* ef = b->fs->ef; MatXX H1, H2; VecX b1, b2;
+  MatXX HL; VecX bL;
+  ef->accumulateAF_MT(H1, b1, false); ef->accumulateLF_MT(HL, bL, false); ef->accumulateSCF_MT(H2, b2, false);     // same order as solveSystemF (:662-666): SC reads the *_accLF sums of the L pass
+  copy_mat(H1, HA); copy_mat(H2, Hsc); for (int i = 0; i < (int)b1.size(); i++) { bA[i] = b1[i]; bsc[i] = b2[i]; }
+}
+void ref_ba_solve(void* p, int iteration, double lambda, double* x, double* HS, double* bS) {
+  RefBA* b = (RefBA*)p; b->fs->solveSystem(iteration, lambda); EnergyFunctional* ef = b->fs->ef;
+  for (int i = 0; i < (int)ef->lastX.size(); i++) x[i] = ef->lastX[i];
+  if (HS) copy_mat(ef->lastHS, HS); if (bS) for (int i = 0; i < (int)ef->lastbS.size(); i++) bS[i] = ef->lastbS[i];
+}
+void ref_ba_backup(void* p) { ((RefBA*)p)->fs->backupState(false); }
+int  ref_ba_do_step(void* p, float f) { return ((RefBA*)p)->fs->doStepFromBackup(f, f, f, f, f) ? 1 : 0; }
+void ref_ba_load_backup(void* p) { ((RefBA*)p)->fs->loadSateBackup(); }
+float ref_ba_optimize(void* p, int its) { RefBA* b = (RefBA*)p; float r = b->fs->optimize(its); refresh_dead(b); return r; }
+void ref_ba_get_points(void* p, float* idepth, float* step, float* HdiF, float* bdSumF, float* maxRelBaseline, int* numGood, float* idepth_hessian) {
+  RefBA* b = (RefBA*)p; for (size_t i = 0; i < b->pts.size(); i++) { const PointHessian* q = b->pts[i]; idepth[i] = q->idepth; step[i] = q->step; HdiF[i] = q->efPoint->HdiF; bdSumF[i] = q->efPoint->bdSumF;
+    maxRelBaseline[i] = q->maxRelBaseline; numGood[i] = q->numGoodResiduals; idepth_hessian[i] = q->idepth_hessian; }
+}
+void ref_ba_get_frames(void* p, double* T_eval7, double* state10, double* step10, float* frameEnergyTH, double* PRE_w2c7) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs;
+  for (size_t i = 0; i < fs->frameHessians.size(); i++) { const FrameHessian* f = fs->frameHessians[i]; se3_to(f->worldToCam_evalPT, T_eval7+7*i); se3_to(f->PRE_worldToCam, PRE_w2c7+7*i);
+    for (int k = 0; k < 10; k++) { state10[10*i+k] = f->state[k]; step10[10*i+k] = f->step[k]; } frameEnergyTH[i] = f->frameEnergyTH; }
+}
+void ref_ba_get_calib(void* p, double value[4], double step[4]) { RefBA* b = (RefBA*)p; for (int i = 0; i < 4; i++) { value[i] = b->fs->Hcalib.value[i]; step[i] = b->fs->Hcalib.step[i]; } }
+void ref_ba_get_precalc(void* p, int host, int target, float* out, double* adH36, double* adT36, float* adHTdelta6) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs; int n = (int)fs->frameHessians.size(); const FrameFramePrecalc& c = fs->frameHessians[host]->targetPrecalc[target];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { out[i*3+j] = c.PRE_KRKiTll(i, j); out[12+i*3+j] = c.PRE_RTll_0(i, j); }
+  for (int i = 0; i < 3; i++) { out[9+i] = c.PRE_KtTll[i]; out[21+i] = c.PRE_tTll_0[i]; } out[24] = c.PRE_aff_mode[0]; out[25] = c.PRE_aff_mode[1]; out[26] = c.PRE_b0_mode;
+  int idx = host + target*n; for (int i = 0; i < 6; i++) { for (int j = 0; j < 6; j++) { adH36[6*i+j] = fs->ef->adHost[idx](i, j); adT36[6*i+j] = fs->ef->adTarget[idx](i, j); } adHTdelta6[i] = fs->ef->adHTdeltaF[idx][i]; }
+}
+// keyframe hand-over.  `selected[p]` stands for the pointer-graph predicate (isOOB || host flagged) && isInlierNew (FullSystem.cpp:763-767): the shim makes exactly the
+// selected points satisfy it (lastResiduals[0] = OOB, enough good residuals) and then runs the reference's own flagPointsForRemoval.
+void ref_ba_flag_points(void* p, const int* selected, int* status) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs;
+  for (size_t i = 0; i < b->pts.size(); i++) { PointHessian* ph = b->pts[i];
+    if (selected[i]) { ph->lastResiduals[0].second = ResState::OOB; if (ph->numGoodResiduals < setting_minGoodResForMarg) ph->numGoodResiduals = setting_minGoodResForMarg; }
+    else { ph->lastResiduals[0].second = ResState::IN; ph->lastResiduals[1].second = ResState::IN; } }
+  // flagPointsForRemoval skips the newest keyframe's points (:749): so does the flat interface's caller
+  fs->flagPointsForRemoval(); refresh_dead(b);
+  for (size_t i = 0; i < b->pts.size(); i++) status[i] = (b->pts[i]->efPoint->stateFlag == EFPointStatus::PS_MARGINALIZE) ? 2 : (b->pts[i]->efPoint->stateFlag == EFPointStatus::PS_DROP ? 1 : 0);
+}
+void ref_ba_marginalize_points(void* p) { ((RefBA*)p)->fs->ef->marginalizePointsF(); }
+void ref_ba_drop_points(void* p) { ((RefBA*)p)->fs->ef->dropPointsF(); }
+void ref_ba_marginalize_frame(void* p, int idx) { RefBA* b = (RefBA*)p; FullSystem* fs = b->fs; FrameHessian* fh = fs->frameHessians[idx];
+  fh->pointHessians.clear();                                                                                  // marginalizeFrame asserts the frame's points are gone (they were flagged + marginalised/dropped before)
+  // FullSystem::marginalizeFrame deletes the FrameHessian; ours belongs to the caller's RefFrame: run the numeric part (EnergyFunctional::marginalizeFrame) and the list surgery only
+  fs->ef->marginalizeFrame(fh->efFrame);
+  for (size_t i = idx; i + 1 < fs->frameHessians.size(); i++) fs->frameHessians[i] = fs->frameHessians[i+1]; fs->frameHessians.pop_back();
+  for (size_t i = 0; i < fs->frameHessians.size(); i++) fs->frameHessians[i]->idx = (int)i;
+  fh->efFrame = 0;
+}
+int  ref_ba_dim(void* p) { return (int)((RefBA*)p)->fs->ef->HM.rows(); }
+void ref_ba_get_prior(void* p, double* HM, double* bM) { RefBA* b = (RefBA*)p; copy_mat(b->fs->ef->HM, HM); for (int i = 0; i < (int)b->fs->ef->bM.size(); i++) bM[i] = b->fs->ef->bM[i]; }
+void ref_ba_get_res_to_zero(void* p, float* r2, int* isLin) { RefBA* b = (RefBA*)p; for (size_t i = 0; i < b->res.size(); i++) { if (b->dead[i]) { r2[2*i] = r2[2*i+1] = 0; isLin[i] = 0; continue; } r2[2*i] = b->res[i]->efResidual->res_toZeroF[0]; r2[2*i+1] = b->res[i]->efResidual->res_toZeroF[1]; isLin[i] = b->res[i]->efResidual->isLinearized ? 1 : 0; } }
 
 }  // extern "C"

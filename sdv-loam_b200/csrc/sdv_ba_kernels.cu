@@ -835,6 +835,7 @@ __global__ void __launch_bounds__(128) ba_marg_flag_kernel(const BAWinDev* __res
   if (!P.marg_status[p]) return;
   const int nF = H->nF; const float deltaF = P.deltaF[p];
   for (int r = P.res_begin[p]; r < P.res_begin[p+1]; r++) {
+    if (R.toRemove[r]) continue;                                             // dropped by linearizeAll(fix) (the reference deleted it, FullSystemOptimize.cpp:129-157): it is not in ph->residuals any more
     R.state_NewEnergy[r] = 0; R.state_energy[r] = 0; R.state_NewState[r] = RS_OUTLIER; R.state_state[r] = RS_IN;
     lin_residual(H, P, R, r, nullptr, nullptr);
     R.isLinearized[r] = 0;

@@ -416,8 +416,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if defined(SDV_MBAR_SPIN)          // non-blocking test_wait poll
+  uint32_t done = 0;
+  while (!done) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#elif defined(SDV_MBAR_HINT_NS)     // try_wait with an explicit suspend-time hint
+  asm volatile("{\n\t.reg .pred p;\n\tSDV_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra SDV_DONE_%=;\n\tbra SDV_WAIT_%=;\n\tSDV_DONE_%=:\n\t}"
+               :: "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SDV_MBAR_HINT_NS) : "memory");
+#else
   asm volatile("{\n\t.reg .pred p;\n\tSDV_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra SDV_DONE_%=;\n\tbra SDV_WAIT_%=;\n\tSDV_DONE_%=:\n\t}"
                :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -534,7 +542,10 @@ __device__ __forceinline__ void flow_point(const float4 p, const LevelGeom& g, c
 
 #ifdef SDV_TRACK_PROFILE
 __device__ long long g_track_prof[16];
-#define SDV_PROF_T(var) long long var = clock64()
+#ifndef SDV_PROF_MASK
+#define SDV_PROF_MASK 0xffff
+#endif
+#define SDV_PROF_T(var) long long var = ((SDV_PROF_MASK >> __COUNTER__) & 1) ? clock64() : 0
 #define SDV_PROF_ADD(slot, t0, t1) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_track_prof[slot] += (t1) - (t0); } while (0)
 #else
 #define SDV_PROF_T(var) do {} while (0)
