@@ -93,6 +93,20 @@ def lib():
         L.ref_ba_dim.argtypes = [_vp]
         L.ref_ba_get_prior.argtypes = [_vp, _f64p, _f64p]
         L.ref_ba_get_res_to_zero.argtypes = [_vp, _f32p, _i32p]
+        L.ref_sys_create.restype = _vp; L.ref_sys_create.argtypes = [C.c_int]
+        L.ref_sys_destroy.argtypes = [_vp]
+        L.ref_srand.argtypes = [C.c_uint]
+        L.ref_sys_add_frame.argtypes = [_vp, _f32p, C.c_float, C.c_double, _f64p, C.c_int]
+        L.ref_sys_num_frames.argtypes = [_vp]; L.ref_sys_num_keyframes.argtypes = [_vp]
+        L.ref_sys_get_frame.argtypes = [_vp, C.c_int, _f64p, _f64p, _i32p]
+        L.ref_sys_get_last_rmse.argtypes = [_vp, _f64p]
+        L.ref_sys_window.argtypes = [_vp, _i32p, _i32p]
+        L.ref_sys_tracker_info.argtypes = [_vp, C.POINTER(C.c_int), _f64p, C.POINTER(C.c_float), _i32p, C.POINTER(C.c_double)]
+        L.ref_sys_tracker_cloud.argtypes = [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p]
+        L.ref_sys_history.argtypes = [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, C.POINTER(C.c_int)]
+        L.ref_sys_map_size.argtypes = [_vp, C.POINTER(C.c_int)]
+        L.ref_sys_map.argtypes = [_vp, _i32p, _f64p, _f64p, _f32p, _f32p]
+        L.ref_sys_get_track_result.argtypes = [_vp, C.c_int, _f64p]
         _LIB = L
     return _LIB
 
@@ -296,3 +310,69 @@ class BAWindow:
             with _Quiet():
                 _LIB.ref_ba_destroy(self.p)
             self.p = None
+
+
+class System:
+    """The reference's whole vision pipeline: FullSystem::addActiveFrame per frame (FullSystem.cpp:822-900), fed like main.cpp:466-509 feeds it.
+    BASELINE.json config #1 (single sequence, CPU reference path, pose + energy dump) runs through this class.  set_calib() first."""
+
+    def __init__(self, levels: int, perfect_images: bool = True, seed: int = 3141592):
+        self.levels = levels
+        with _Quiet():
+            self.p = lib().ref_sys_create(1 if perfect_images else 0)
+        lib().ref_srand(seed)                                  # PixelSelector2.cpp:15 does srand(3141592); rand() is then consumed by the Reprojector shuffle and makeNewTraces
+
+    def srand(self, seed: int): lib().ref_srand(seed)
+
+    def addActiveFrame(self, image, cloud_px, timestamp: float, exposure: float = 1.0) -> int:
+        """image (h,w) float32 0..255; cloud_px (n,3) {Ku, Kv, depth} of the LiDAR sweep in the cropped image (main.cpp:810-855).  Returns 0, -1 lost, -2 init failed."""
+        img = np.ascontiguousarray(image, np.float32); cl = np.ascontiguousarray(cloud_px, np.float64).reshape(-1, 3)
+        with _Quiet():
+            return lib().ref_sys_add_frame(self.p, img, exposure, timestamp, cl, len(cl))
+
+    def num_frames(self): return lib().ref_sys_num_frames(self.p)
+    def num_keyframes(self): return lib().ref_sys_num_keyframes(self.p)
+
+    def frame(self, i):
+        T = np.zeros(7); ab = np.zeros(2); fl = np.zeros(3, np.int32); lib().ref_sys_get_frame(self.p, i, T, ab, fl)
+        c2r = np.zeros(7); lib().ref_sys_get_track_result(self.p, i, c2r)
+        return dict(camToWorld=T, aff_g2l=ab, poseValid=bool(fl[0]), isKeyframe=bool(fl[1]), trackingRef=int(fl[2]), camToTrackingRef=c2r)
+
+    def lastCoarseRMSE(self):
+        o = np.zeros(5); lib().ref_sys_get_last_rmse(self.p, o); return o
+
+    def window(self):
+        ids = np.zeros(16, np.int32); n = np.zeros(16, np.int32); k = lib().ref_sys_window(self.p, ids, n); return ids[:k].copy(), n[:k].copy()
+
+    def tracker_snapshot(self):
+        """State trackNewCoarse will see for the NEXT frame: reference clouds of the tracker that will be used, pose history, active map."""
+        rid = C.c_int(0); ab = np.zeros(2); ex = C.c_float(0); n = np.zeros(6, np.int32); fr = C.c_double(0)
+        if lib().ref_sys_tracker_info(self.p, C.byref(rid), ab, C.byref(ex), n, C.byref(fr)) != 0:
+            return None
+        clouds = []
+        for l in range(self.levels):
+            a = [np.zeros(max(int(n[l]), 1), np.float32) for _ in range(4)]; lib().ref_sys_tracker_cloud(self.p, l, *a); clouds.append([x[:n[l]].copy() for x in a])
+        sp = np.zeros(7); sl = np.zeros(7); lf = np.zeros(7); al = np.zeros(2); rm = np.zeros(5); nh = C.c_int(0)
+        lib().ref_sys_history(self.p, sp, sl, lf, al, rm, C.byref(nh))
+        nkf = C.c_int(0); npts = lib().ref_sys_map_size(self.p, C.byref(nkf)); k = nkf.value
+        ids = np.zeros(max(k, 1), np.int32); kT = np.zeros((max(k, 1), 7)); kab = np.zeros((max(k, 1), 2)); kex = np.zeros(max(k, 1), np.float32); p5 = np.zeros((max(npts, 1), 5), np.float32)
+        lib().ref_sys_map(self.p, ids, kT, kab, kex, p5)
+        return dict(ref_frame=rid.value, ref_ab=ab, ref_exposure=ex.value, clouds=clouds, firstCoarseRMSE=fr.value, sprelast=sp, slast=sl, lastF=lf, aff_last=al, lastCoarseRMSE=rm,
+                    n_history=nh.value, kf_ids=ids[:k], kf_T7=kT[:k], kf_ab=kab[:k], kf_exposure=kex[:k], map_pts=p5[:npts])
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            with _Quiet():
+                _LIB.ref_sys_destroy(self.p)
+            self.p = None
+
+
+def libc_rand_shuffle(n: int):
+    """std::random_shuffle(first, last) of libstdc++ on 0..n-1, driven by the C library's rand() in THIS process (the reference's Reprojector grid, Reprojector.cpp:107).
+    Call right after srand(seed) to learn the cell order a Reprojector constructed next will use; then srand(seed) again."""
+    libc = C.CDLL(None); a = list(range(n))
+    for i in range(1, n):
+        j = libc.rand() % (i + 1)
+        if i != j:
+            a[i], a[j] = a[j], a[i]
+    return np.array(a, np.int32)

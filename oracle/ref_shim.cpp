@@ -305,4 +305,75 @@ int  ref_ba_dim(void* p) { return (int)((RefBA*)p)->fs->ef->HM.rows(); }
 void ref_ba_get_prior(void* p, double* HM, double* bM) { RefBA* b = (RefBA*)p; copy_mat(b->fs->ef->HM, HM); for (int i = 0; i < (int)b->fs->ef->bM.size(); i++) bM[i] = b->fs->ef->bM[i]; }
 void ref_ba_get_res_to_zero(void* p, float* r2, int* isLin) { RefBA* b = (RefBA*)p; for (size_t i = 0; i < b->res.size(); i++) { if (b->dead[i]) { r2[2*i] = r2[2*i+1] = 0; isLin[i] = 0; continue; } r2[2*i] = b->res[i]->efResidual->res_toZeroF[0]; r2[2*i+1] = b->res[i]->efResidual->res_toZeroF[1]; isLin[i] = b->res[i]->efResidual->isLinearized ? 1 : 0; } }
 
+// ---------------------------------------------------------------------------------------------- the whole pipeline: FullSystem::addActiveFrame per frame (main.cpp:466-509)
+// BASELINE.json config #1 ("first 200 frames, single sequence, CPU reference path, pose + energy dump") runs HERE on the reference's own FullSystem: makeImages ->
+// trackNewCoarse (hypotheses, trackNewestCoarse, reprojectMap, structPoseEstimation) -> makeKeyFrame / makeNonKeyFrame (traceNewCoarse, activatePointsMT, optimize,
+// marginalisation, makeNewTraces, setCoarseTrackingRef).  The shim only feeds the queues main.cpp feeds (image, LiDAR pixels {Ku, Kv, depth}) and reads state back.
+struct RefSys { FullSystem* fs; int next_id; };
+void* ref_sys_create(int mode_perfect_images) {
+  setting_logStuff = false; multiThreading = false; setting_debugout_runquiet = true; disableAllDisplay = true; setting_render_display3D = false; setting_render_displayDepth = false;
+  setting_render_displayVideo = false; setting_render_displayResidual = false; setting_render_renderWindowFrames = false; setting_render_plotTrackingFull = false; setting_render_displayCoarseTrackingFull = false;
+  if (mode_perfect_images) { setting_photometricCalibration = 0; setting_affineOptModeA = -1; setting_affineOptModeB = -1; setting_minGradHistAdd = 3; }   // main.cpp:461-468 (mode 2)
+  else { setting_photometricCalibration = 0; setting_affineOptModeA = 0; setting_affineOptModeB = 0; }                                                    // mode 1
+  RefSys* s = new RefSys(); s->fs = new FullSystem(); s->fs->linearizeOperation = true; s->next_id = 0; return s;
+}
+void ref_sys_destroy(void* p) { RefSys* s = (RefSys*)p; if (!s) return; delete s->fs; delete s; }
+void ref_srand(unsigned seed) { srand(seed); }
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void ref_segv(int sig) { void* bt[64]; int n = backtrace(bt, 64); backtrace_symbols_fd(bt, n, 2); _exit(139); }
+void ref_debug_install_segv_handler() { signal(SIGSEGV, ref_segv); signal(SIGABRT, ref_segv); }
+// cloud_px: n rows {Ku, Kv, depth} in the (cropped) image — what main.cpp:785-855 pushes into qCloudPixel
+int ref_sys_add_frame(void* p, const float* image, float exposure, double timestamp, const double* cloud_px, int n) {
+  RefSys* s = (RefSys*)p; FullSystem* fs = s->fs;
+  std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d> > v(n); for (int i = 0; i < n; i++) v[i] = Eigen::Vector3d(cloud_px[3*i], cloud_px[3*i+1], cloud_px[3*i+2]);
+  fs->qCloudPixel.push(v); fs->qTimeLidarCloud.push(timestamp); fs->qTimeImg.push(timestamp);
+  ImageAndExposure* img = new ImageAndExposure(wG[0], hG[0], timestamp); img->exposure_time = exposure; memcpy(img->image, image, sizeof(float)*(size_t)wG[0]*hG[0]);
+  fs->addActiveFrame(img, s->next_id++);
+  delete img; fs->qCloudPixel.pop(); fs->qTimeLidarCloud.pop(); fs->qTimeImg.pop();
+  return fs->isLost ? -1 : (fs->initFailed ? -2 : 0);
+}
+int ref_sys_num_frames(void* p) { return (int)((RefSys*)p)->fs->allFrameHistory.size(); }
+int ref_sys_num_keyframes(void* p) { return (int)((RefSys*)p)->fs->allKeyFramesHistory.size(); }
+// per frame: camToWorld (7), aff_g2l (2), flags {poseValid, is keyframe (trackingRef == 0 or in allKeyFramesHistory), trackingRef id}
+void ref_sys_get_frame(void* p, int i, double T7[7], double ab[2], int flags[3]) {
+  FullSystem* fs = ((RefSys*)p)->fs; FrameShell* sh = fs->allFrameHistory[i];
+  se3_to(sh->camToWorld, T7); ab[0] = sh->aff_g2l.a; ab[1] = sh->aff_g2l.b; flags[0] = sh->poseValid ? 1 : 0; flags[1] = 0;
+  for (FrameShell* k : fs->allKeyFramesHistory) if (k == sh) flags[1] = 1;
+  flags[2] = sh->trackingRef ? sh->trackingRef->id : -1;
+}
+void ref_sys_get_last_rmse(void* p, double out5[5]) { FullSystem* fs = ((RefSys*)p)->fs; for (int i = 0; i < 5; i++) out5[i] = fs->lastCoarseRMSE[i]; }
+int ref_sys_window(void* p, int* kf_ids, int* n_points) { FullSystem* fs = ((RefSys*)p)->fs; int n = (int)fs->frameHessians.size();
+  for (int i = 0; i < n; i++) { if (kf_ids) kf_ids[i] = fs->frameHessians[i]->shell->id; if (n_points) n_points[i] = (int)fs->frameHessians[i]->pointHessians.size(); } return n; }
+
+// ---- state of the running system BEFORE the next addActiveFrame = the inputs of FullSystem::trackNewCoarse for that frame (teacher-forced replay of the tracker on other arms)
+static CoarseTracker* next_tracker(FullSystem* fs) {          // the swap of addActiveFrame (FullSystem.cpp:853-859) has not happened yet: predict it
+  return (fs->coarseTracker_forNewKF->refFrameID > fs->coarseTracker->refFrameID) ? fs->coarseTracker_forNewKF : fs->coarseTracker;
+}
+int ref_sys_tracker_info(void* p, int* ref_shell_id, double ref_ab[2], float* ref_exposure, int* pc_n /*PYR_LEVELS*/, double* firstCoarseRMSE) {
+  FullSystem* fs = ((RefSys*)p)->fs; CoarseTracker* t = next_tracker(fs); if (!t->lastRef) return -1;
+  *ref_shell_id = t->lastRef->shell->id; ref_ab[0] = t->lastRef_aff_g2l.a; ref_ab[1] = t->lastRef_aff_g2l.b; *ref_exposure = t->lastRef->ab_exposure;
+  for (int l = 0; l < pyrLevelsUsed; l++) pc_n[l] = t->pc_n[l]; *firstCoarseRMSE = t->firstCoarseRMSE; return 0;
+}
+void ref_sys_tracker_cloud(void* p, int lvl, float* u, float* v, float* id, float* color) {
+  CoarseTracker* t = next_tracker(((RefSys*)p)->fs); for (int i = 0; i < t->pc_n[lvl]; i++) { u[i] = t->pc_u[lvl][i]; v[i] = t->pc_v[lvl][i]; id[i] = t->pc_idepth[lvl][i]; color[i] = t->pc_color[lvl][i]; }
+}
+// history as trackNewCoarse will see it for the NEXT frame (allFrameHistory gets the new shell first, so "size()-2" there is back() here)
+void ref_sys_history(void* p, double sprelast7[7], double slast7[7], double lastF7[7], double aff_last[2], double lastCoarseRMSE[5], int* n_history) {
+  FullSystem* fs = ((RefSys*)p)->fs; int n = (int)fs->allFrameHistory.size(); *n_history = n;
+  FrameShell* slast = fs->allFrameHistory[n-1]; FrameShell* sprelast = fs->allFrameHistory[n >= 2 ? n-2 : n-1];
+  se3_to(sprelast->camToWorld, sprelast7); se3_to(slast->camToWorld, slast7); se3_to(next_tracker(fs)->lastRef->shell->camToWorld, lastF7);
+  aff_last[0] = slast->aff_g2l.a; aff_last[1] = slast->aff_g2l.b; for (int i = 0; i < 5; i++) lastCoarseRMSE[i] = fs->lastCoarseRMSE[i];
+}
+int ref_sys_map_size(void* p, int* nKF) { FullSystem* fs = ((RefSys*)p)->fs; *nKF = (int)fs->frameHessians.size(); int n = 0; for (FrameHessian* fh : fs->frameHessians) n += (int)fh->pointHessians.size(); return n; }
+// active map = what Reprojector(&Hcalib, fh, frameHessians) walks: keyframes in window order, their ACTIVE PointHessians {u, v, idepth_scaled, host index, type}
+void ref_sys_map(void* p, int* kf_shell_ids, double* kf_T7, double* kf_ab, float* kf_exposure, float* pts5 /*n x {u,v,idepth,host,type}*/) {
+  FullSystem* fs = ((RefSys*)p)->fs; int k = 0;
+  for (size_t h = 0; h < fs->frameHessians.size(); h++) { FrameHessian* fh = fs->frameHessians[h]; kf_shell_ids[h] = fh->shell->id; se3_to(fh->shell->camToWorld, kf_T7 + 7*h);
+    kf_ab[2*h] = fh->aff_g2l().a; kf_ab[2*h+1] = fh->aff_g2l().b; kf_exposure[h] = fh->ab_exposure;
+    for (PointHessian* ph : fh->pointHessians) { pts5[5*k] = ph->u; pts5[5*k+1] = ph->v; pts5[5*k+2] = ph->idepth_scaled; pts5[5*k+3] = (float)h; pts5[5*k+4] = (ph->type == PointHessian::EDGELET) ? 1.f : 0.f; k++; } }
+}
+void ref_sys_get_track_result(void* p, int i, double camToTrackingRef7[7]) { se3_to(((RefSys*)p)->fs->allFrameHistory[i]->camToTrackingRef, camToTrackingRef7); }
+
 }  // extern "C"

@@ -61,6 +61,28 @@ SDV_HD void finalize_gs(const double* tot, double* H /*64*/, double* b /*8*/) {
   }
 }
 
+// same, every caller lane computes but only `write` lanes store (keeps a warp's control flow uniform in the device-resident LM)
+SDV_HD void finalize_gs_guarded(const double* tot, double* H /*64*/, double* b /*8*/, bool write) {
+  int nW = (int)(tot[kIdxNE] - tot[kIdxNSat]);
+  int npad = (nW + 3) & ~3;
+  float invn = 1.0f/npad;
+  const float sc[8] = {1.0f,1.0f,1.0f,0.5f,0.5f,0.5f,10.0f,1000.0f};
+  int k = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r=0;r<9;r++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c=r;c<9;c++) {
+      float hv = (float)tot[k++];
+      if (r < 8 && c < 8) { double v = (double)hv * invn; v *= sc[c]; v *= sc[r]; if (write) { H[r*8+c] = v; H[c*8+r] = v; } }
+      else if (r < 8 && c == 8) { double v = (double)hv * invn; v *= sc[r]; if (write) b[r] = v; }
+    }
+  }
+}
+
 #if defined(__CUDACC__)
 #ifndef SDV_PREFETCH_MODE
 #define SDV_PREFETCH_MODE 0                // 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2

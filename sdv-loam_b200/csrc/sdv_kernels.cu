@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
   constexpr uint32_t kSlotStride = 4*THREADS*16;
 
   while (true) {
-    const int lvl = ctl.lvl;
+    const int lvl = ctl.lvl; int n_eval = 0;
     // ------------------------------------------------------------------ one calcRes + calcGSSSE sweep at ctl.ep
     float acc[kNAcc];
 #pragma unroll
@@ -714,7 +714,8 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       }
       __syncthreads();
       evalCount++;
-      if (tid == 0) ctl.evals[lvl] += n;
+      n_eval = n;                                             // ctl.evals is updated by lane 0 inside the control block: a lane-0-only store HERE left warp 0 split 1 + 31 with
+                                                            // nothing to reconverge it before the control step (ncu: every control instruction issued twice, 30 us per evaluation)
       SDV_PROF_T(tp6); SDV_PROF_ADD(5, tp5, tp6);
 #ifdef SDV_TRACK_PROFILE
       if (blockIdx.x == 0 && tid == 0) g_track_prof[8] += 1;
@@ -722,62 +723,61 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
     }
     SDV_PROF_T(tc0);
     // ------------------------------------------------------------------ LM control (warp 0), CoarseTracker.cpp:679-812 as a state machine
+    // All 32 lanes execute the SAME instruction stream on the same values (SIMT: no extra cost) and only lane 0's stores to `ctl` are predicated.  A lane-0-only
+    // branch in front of the warp-cooperative LDLT left the warp diverged at the shuffles (ncu: the solve executed twice per call, every __shfl_sync a rendezvous of
+    // two groups): 30 us per evaluation, 0.45 ms per launch.
     if (tid < 32) {
-      const int lane = tid;
-      const int maxIterations[5] = {10,20,50,50,50};        // :679
+      __syncwarp();                                          // converge warp 0 before anything warp-cooperative
+      const bool L0 = (tid == 0);
       const float lambdaExtrapolationLimit = 0.001f;         // :680
-      bool propose = false, level_end = false;
-      if (ctl.mode == 0) {                                   // level entry: resOld at the current pose (:690-702)
-        if (lane == 0) finalize_res(tot, ctl.resOld);
-        __syncwarp();
-        if (ctl.resOld[5] > 0.6 && ctl.lcr < 50) {
-          if (lane == 0) {
-            ctl.lcr *= 2;
-            make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl, tc.coarseCutoffTH*ctl.lcr, tc.huberTH, ctl.ep);
-          }
-        } else {
-          if (lane == 0) { finalize_gs(tot, ctl.H, ctl.b); ctl.lambda = 0.01f; ctl.iteration = 0; }
-          propose = true;
-        }
-      } else {                                               // candidate evaluated: accept / reject (:770-806)
-        if (lane == 0) {
-          finalize_res(tot, ctl.resNew);
-          bool accept = (ctl.resNew[0]/ctl.resNew[1]) < (ctl.resOld[0]/ctl.resOld[1]);
-          if (accept) {
-            finalize_gs(tot, ctl.H, ctl.b);
-            for (int i = 0; i < 6; i++) ctl.resOld[i] = ctl.resNew[i];
-            ctl.cur = ctl.cand; ctl.a_cur = ctl.a_cand; ctl.b_cur = ctl.b_cand;
-            ctl.lambda *= 0.5f; ctl.accs[lvl]++;
-          } else {
-            ctl.lambda *= 4;
-            if (ctl.lambda < lambdaExtrapolationLimit) ctl.lambda = lambdaExtrapolationLimit;
-          }
-          ctl.iteration++;
-        }
-        __syncwarp();
-        if (!(ctl.incn > 1e-3) || ctl.iteration >= maxIterations[lvl]) level_end = true; else propose = true;
-      }
+      const int maxIt = (lvl == 0) ? 10 : ((lvl == 1) ? 20 : 50);   // maxIterations[] = {10,20,50,50,50}  (:679)
+      const int mode = ctl.mode; float lcr = ctl.lcr; float lambda = ctl.lambda; int iteration = ctl.iteration;
+      SE3d cur = ctl.cur; double a_cur = ctl.a_cur, b_cur = ctl.b_cur;
+      double resOld[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) resOld[i] = ctl.resOld[i];
+      bool propose = false, level_end = false, repeat_entry = false;
       __syncwarp();
-      if (level_end) {                                       // :808-822
-        if (lane == 0) {
-          ctl.lastRes[lvl] = sqrtf((float)(ctl.resOld[0]/ctl.resOld[1]));
-          ctl.flow[0] = ctl.resOld[2]; ctl.flow[1] = ctl.resOld[3]; ctl.flow[2] = ctl.resOld[4];
-          int nl = lvl;
-          if (ctl.lastRes[lvl] > 1.5*J.minRes[lvl]) { ctl.aborted = 1; ctl.done = 1; }
-          else {
-            if (ctl.lcr > 1 && !ctl.haveRepeated) { nl++; ctl.haveRepeated = 1; }
-            nl--;
-            if (nl < 0) ctl.done = 1;
-            else {
-              ctl.lvl = nl; ctl.mode = 0; ctl.lcr = 1.0f;
-              make_eval_params(ctl.cur, ctl.a_cur, ctl.b_cur, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[nl], nl, tc.coarseCutoffTH, tc.huberTH, ctl.ep);
-            }
-          }
+      if (mode == 0) {                                       // level entry: resOld at the current pose (:690-702)
+        finalize_res(tot, resOld);
+        if (resOld[5] > 0.6 && lcr < 50) { lcr *= 2; repeat_entry = true; }
+        else { finalize_gs_guarded(tot, ctl.H, ctl.b, L0); lambda = 0.01f; iteration = 0; propose = true; }
+      } else {                                               // candidate evaluated: accept / reject (:770-806)
+        double resNew[6]; finalize_res(tot, resNew);
+        const bool accept = (resNew[0]/resNew[1]) < (resOld[0]/resOld[1]);
+        if (accept) {
+          finalize_gs_guarded(tot, ctl.H, ctl.b, L0);
+#pragma unroll
+          for (int i = 0; i < 6; i++) resOld[i] = resNew[i];
+          cur = ctl.cand; a_cur = ctl.a_cand; b_cur = ctl.b_cand;
+          lambda *= 0.5f;
+        } else {
+          lambda *= 4;
+          if (lambda < lambdaExtrapolationLimit) lambda = lambdaExtrapolationLimit;
         }
-      } else if (propose) {                                  // propose the LM step (:722-765)
-        if (lane == 0) ctl.iters[lvl]++;
-        const int r = lane & 7;
-        const float lambda = ctl.lambda;
+        if (L0 && accept) ctl.accs[lvl]++;
+        iteration++;
+        if (!(ctl.incn > 1e-3) || iteration >= maxIt) level_end = true; else propose = true;
+      }
+      __syncwarp();                                          // ctl.H / ctl.b (lane 0's stores) before every lane reads them
+      int next_lvl = lvl, next_mode = mode, done = 0, aborted = 0, haveRepeated = ctl.haveRepeated;
+      double incn_out = ctl.incn; SE3d cand = cur; double a_cand = a_cur, b_cand = b_cur;
+      bool new_ep = false; SE3d ep_pose = cur; double ep_a = a_cur, ep_b = b_cur; int ep_lvl = lvl; float ep_lcr = lcr;
+      double lastRes_l = 0;
+      if (repeat_entry) { new_ep = true; next_mode = 0; }
+      if (level_end) {                                       // :808-822
+        lastRes_l = sqrtf((float)(resOld[0]/resOld[1]));
+        if (lastRes_l > 1.5*J.minRes[lvl]) { aborted = 1; done = 1; }
+        else {
+          int nl = lvl;
+          if (lcr > 1 && !haveRepeated) { nl++; haveRepeated = 1; }
+          nl--;
+          if (nl < 0) done = 1;
+          else { next_lvl = nl; next_mode = 0; lcr = 1.0f; new_ep = true; ep_lvl = nl; ep_lcr = 1.0f; }
+        }
+      }
+      if (propose) {                                         // propose the LM step (:722-765) — warp-cooperative, every lane converged
+        const int r = tid & 7;
         const bool fixA = tc.affineOptModeA < 0, fixB = tc.affineOptModeB < 0;
         const int nv = (!fixA && !fixB) ? 8 : ((fixA && fixB) ? 6 : 7);
         const bool stitch = fixA && !fixB;                   // fix a only: b takes slot 6 (:736-748)
@@ -808,23 +808,32 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
 #pragma unroll
         for (int i = 3; i < 6; i++) incScaled[i] = inc[i]*0.5f;        // SCALE_XI_TRANS (:756)
         incScaled[6] = inc[6]*10.0f; incScaled[7] = inc[7]*1000.0f;    // SCALE_A, SCALE_B
-        double s = 0;
+        double ssum = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) s += incScaled[i];
-        if (!isfinite(s)) {
+        for (int i = 0; i < 8; i++) ssum += incScaled[i];
+        if (!isfinite(ssum)) {
 #pragma unroll
           for (int i = 0; i < 8; i++) incScaled[i] = 0;
         }
         double incn = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) incn += inc[i]*inc[i];
-        incn = sqrt(incn);
-        if (lane == 0) {
-          const SE3d cand = se3_mul(se3_exp(incScaled), ctl.cur);
-          const double a_cand = ctl.a_cur + incScaled[6], b_cand = ctl.b_cur + incScaled[7];
-          ctl.cand = cand; ctl.a_cand = a_cand; ctl.b_cand = b_cand; ctl.incn = incn; ctl.mode = 1;
-          make_eval_params(cand, a_cand, b_cand, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[lvl], lvl, tc.coarseCutoffTH*ctl.lcr, tc.huberTH, ctl.ep);
-        }
+        incn_out = sqrt(incn);
+        cand = se3_mul(se3_exp(incScaled), cur); a_cand = a_cur + incScaled[6]; b_cand = b_cur + incScaled[7];
+        next_mode = 1; new_ep = true; ep_pose = cand; ep_a = a_cand; ep_b = b_cand;
+      }
+      EvalParams ep;
+      if (new_ep) make_eval_params(ep_pose, ep_a, ep_b, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[ep_lvl], ep_lvl, tc.coarseCutoffTH*ep_lcr, tc.huberTH, ep);
+      if (L0) {                                              // publish (plain predicated stores; nothing collective follows inside this block)
+        ctl.cur = cur; ctl.a_cur = a_cur; ctl.b_cur = b_cur; ctl.cand = cand; ctl.a_cand = a_cand; ctl.b_cand = b_cand;
+#pragma unroll
+        for (int i = 0; i < 6; i++) ctl.resOld[i] = resOld[i];
+        ctl.lambda = lambda; ctl.lcr = lcr; ctl.iteration = iteration; ctl.incn = incn_out; ctl.mode = next_mode; ctl.lvl = next_lvl;
+        ctl.haveRepeated = haveRepeated; ctl.done = done; ctl.aborted = aborted;
+        if (propose) ctl.iters[lvl]++;
+        ctl.evals[lvl] += n_eval;
+        if (level_end) { ctl.lastRes[lvl] = lastRes_l; ctl.flow[0] = resOld[2]; ctl.flow[1] = resOld[3]; ctl.flow[2] = resOld[4]; }
+        if (new_ep) ctl.ep = ep;
       }
     }
     __syncthreads();
