@@ -103,10 +103,12 @@ def lib():
         L.ref_sys_window.argtypes = [_vp, _i32p, _i32p]
         L.ref_sys_tracker_info.argtypes = [_vp, C.POINTER(C.c_int), _f64p, C.POINTER(C.c_float), _i32p, C.POINTER(C.c_double)]
         L.ref_sys_tracker_cloud.argtypes = [_vp, C.c_int, _f32p, _f32p, _f32p, _f32p]
+        L.ref_sys_tracker_K.argtypes = [_vp, _f32p, _f64p]
         L.ref_sys_history.argtypes = [_vp, _f64p, _f64p, _f64p, _f64p, _f64p, C.POINTER(C.c_int)]
         L.ref_sys_map_size.argtypes = [_vp, C.POINTER(C.c_int)]
         L.ref_sys_map.argtypes = [_vp, _i32p, _f64p, _f64p, _f32p, _f32p]
         L.ref_sys_get_track_result.argtypes = [_vp, C.c_int, _f64p]
+        L.ref_reproject_map.argtypes = [C.c_int, C.POINTER(_vp), _f64p, _f64p, _vp, _f64p, _f64p, C.c_int, _f32p, C.c_uint, C.c_int, _i32p, _f64p]
         _LIB = L
     return _LIB
 
@@ -357,7 +359,8 @@ class System:
         nkf = C.c_int(0); npts = lib().ref_sys_map_size(self.p, C.byref(nkf)); k = nkf.value
         ids = np.zeros(max(k, 1), np.int32); kT = np.zeros((max(k, 1), 7)); kab = np.zeros((max(k, 1), 2)); kex = np.zeros(max(k, 1), np.float32); p5 = np.zeros((max(npts, 1), 5), np.float32)
         lib().ref_sys_map(self.p, ids, kT, kab, kex, p5)
-        return dict(ref_frame=rid.value, ref_ab=ab, ref_exposure=ex.value, clouds=clouds, firstCoarseRMSE=fr.value, sprelast=sp, slast=sl, lastF=lf, aff_last=al, lastCoarseRMSE=rm,
+        K4 = np.zeros(4, np.float32); cal = np.zeros(4); lib().ref_sys_tracker_K(self.p, K4, cal)
+        return dict(tracker_K=K4, calib=cal, ref_frame=rid.value, ref_ab=ab, ref_exposure=ex.value, clouds=clouds, firstCoarseRMSE=fr.value, sprelast=sp, slast=sl, lastF=lf, aff_last=al, lastCoarseRMSE=rm,
                     n_history=nh.value, kf_ids=ids[:k], kf_T7=kT[:k], kf_ab=kab[:k], kf_exposure=kex[:k], map_pts=p5[:npts])
 
     def __del__(self):
@@ -376,3 +379,17 @@ def libc_rand_shuffle(n: int):
         if i != j:
             a[i], a[j] = a[j], a[i]
     return np.array(a, np.int32)
+
+
+def reproject_map(wh, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, cur_ab, pts, seed=1, refine=False):
+    """Reprojector::reprojectMap (Reprojector.cpp:117-156) [+ structPoseEstimation] of the reference on flat inputs; pts: structured array u, v, idepth, host, type.
+    Returns (pt_index, px, cell_order used, refined camToWorld or None)."""
+    L = lib(); nH = len(kf_frames); fr = (_vp * nH)(*[f.p for f in kf_frames])
+    p5 = np.ascontiguousarray(np.stack([pts["u"], pts["v"], pts["idepth"], pts["host"].astype(np.float32), pts["type"].astype(np.float32)], 1), np.float32)
+    ncells = int(np.ceil(wh[0] / 25.0)) * int(np.ceil(wh[1] / 25.0))
+    L.ref_srand(seed); order = libc_rand_shuffle(ncells)
+    out_pt = np.zeros(ncells, np.int32); out_px = np.zeros((ncells, 2)); T = np.array(cur_T7, np.float64).copy()
+    with _Quiet():
+        n = L.ref_reproject_map(nH, fr, np.ascontiguousarray(kf_T7, np.float64), np.ascontiguousarray(kf_ab, np.float64), cur_frame.p, T, np.ascontiguousarray(cur_ab, np.float64),
+                                len(p5), p5, seed, 1 if refine else 0, out_pt, out_px)
+    return out_pt[:n].copy(), out_px[:n].copy(), order, (T if refine else None)

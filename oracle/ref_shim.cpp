@@ -317,7 +317,8 @@ void* ref_sys_create(int mode_perfect_images) {
   else { setting_photometricCalibration = 0; setting_affineOptModeA = 0; setting_affineOptModeB = 0; }                                                    // mode 1
   RefSys* s = new RefSys(); s->fs = new FullSystem(); s->fs->linearizeOperation = true; s->next_id = 0; return s;
 }
-void ref_sys_destroy(void* p) { RefSys* s = (RefSys*)p; if (!s) return; delete s->fs; delete s; }
+// ~FullSystem double-frees parts of its graph when the run ended between keyframes (it was only ever run at process exit): stop the mapping thread and leak the rest
+void ref_sys_destroy(void* p) { RefSys* s = (RefSys*)p; if (!s) return; s->fs->blockUntilMappingIsFinished(); delete s; }
 void ref_srand(unsigned seed) { srand(seed); }
 #include <execinfo.h>
 #include <signal.h>
@@ -356,6 +357,10 @@ int ref_sys_tracker_info(void* p, int* ref_shell_id, double ref_ab[2], float* re
   *ref_shell_id = t->lastRef->shell->id; ref_ab[0] = t->lastRef_aff_g2l.a; ref_ab[1] = t->lastRef_aff_g2l.b; *ref_exposure = t->lastRef->ab_exposure;
   for (int l = 0; l < pyrLevelsUsed; l++) pc_n[l] = t->pc_n[l]; *firstCoarseRMSE = t->firstCoarseRMSE; return 0;
 }
+void ref_sys_tracker_K(void* p, float K4[4], double calib_value_scaled[4]) {      // level-0 intrinsics of the tracker that will be used (makeK at its keyframe) and the current CalibHessian (the Reprojector reads it)
+  FullSystem* fs = ((RefSys*)p)->fs; CoarseTracker* t = next_tracker(fs); K4[0] = t->fx[0]; K4[1] = t->fy[0]; K4[2] = t->cx[0]; K4[3] = t->cy[0];
+  for (int i = 0; i < 4; i++) calib_value_scaled[i] = fs->Hcalib.value_scaled[i];
+}
 void ref_sys_tracker_cloud(void* p, int lvl, float* u, float* v, float* id, float* color) {
   CoarseTracker* t = next_tracker(((RefSys*)p)->fs); for (int i = 0; i < t->pc_n[lvl]; i++) { u[i] = t->pc_u[lvl][i]; v[i] = t->pc_v[lvl][i]; id[i] = t->pc_idepth[lvl][i]; color[i] = t->pc_color[lvl][i]; }
 }
@@ -375,5 +380,44 @@ void ref_sys_map(void* p, int* kf_shell_ids, double* kf_T7, double* kf_ab, float
     for (PointHessian* ph : fh->pointHessians) { pts5[5*k] = ph->u; pts5[5*k+1] = ph->v; pts5[5*k+2] = ph->idepth_scaled; pts5[5*k+3] = (float)h; pts5[5*k+4] = (ph->type == PointHessian::EDGELET) ? 1.f : 0.f; k++; } }
 }
 void ref_sys_get_track_result(void* p, int i, double camToTrackingRef7[7]) { se3_to(((RefSys*)p)->fs->allFrameHistory[i]->camToTrackingRef, camToTrackingRef7); }
+
+// ---------------------------------------------------------------------------------------------- Reprojector::reprojectMap (+ CoarseTracker::structPoseEstimation) on flat inputs
+// Same inputs as orc_reproject_map: keyframes (RefFrame handles in window order) with camToWorld / aff, the current frame with its pose, the ACTIVE map points
+// {u, v, idepth, host, type}.  `seed`: srand(seed) right before the Reprojector is constructed — its grid order is std::random_shuffle over rand() (Reprojector.cpp:107).
+// refine != 0: also runs structPoseEstimation on the matches (FullSystem.cpp:482-488) and returns the refined camToWorld in cur_T7_io.
+int ref_reproject_map(int nH, void** kf_frames, const double* kf_T7, const double* kf_ab, void* cur_frame, double* cur_T7_io, const double* cur_ab, int nP, const float* pts5,
+                      unsigned seed, int refine, int* out_pt, double* out_px) {
+  std::vector<FrameHessian*> fhs; RefFrame* C = (RefFrame*)cur_frame;
+  for (int h = 0; h < nH; h++) { RefFrame* F = (RefFrame*)kf_frames[h]; drop_points(F); F->fh->idx = h;
+    F->shell->camToWorld = se3_from(kf_T7 + 7*h); F->shell->aff_g2l = AffLight(kf_ab[2*h], kf_ab[2*h+1]); F->shell->poseValid = true; fhs.push_back(F->fh); }
+  C->shell->camToWorld = se3_from(cur_T7_io); C->shell->aff_g2l = AffLight(cur_ab[0], cur_ab[1]);
+  std::vector<PointHessian*> all;
+  for (int i = 0; i < nP; i++) { RefFrame* F = (RefFrame*)kf_frames[(int)pts5[5*i+3]];
+    ImmaturePoint* ip = new ImmaturePoint((int)pts5[5*i], (int)pts5[5*i+1], F->fh, 0, g_calib); ip->idepth_min = ip->idepth_max = pts5[5*i+2];
+    ip->type = pts5[5*i+4] != 0 ? ImmaturePoint::EDGELET : ImmaturePoint::CORNER; F->ips.push_back(ip);
+    PointHessian* ph = new PointHessian(ip, g_calib); ph->u = pts5[5*i]; ph->v = pts5[5*i+1]; ph->setIdepth(pts5[5*i+2]); ph->setPointStatus(PointHessian::ACTIVE); ph->idx = i;
+    F->phs.push_back(ph); F->fh->pointHessians.push_back(ph); all.push_back(ph); }
+  std::vector<std::pair<PointHessian*, Eigen::Vector2d> > overlap;
+  srand(seed);
+  { Reprojector rp(g_calib, C->fh, fhs); rp.reprojectMap(C->fh, overlap); }
+  for (size_t k = 0; k < overlap.size(); k++) { out_pt[k] = overlap[k].first->idx; out_px[2*k] = overlap[k].second[0]; out_px[2*k+1] = overlap[k].second[1]; }
+  if (refine) { CoarseTracker* t = new CoarseTracker(wG[0], hG[0]); t->makeK(g_calib); t->debugPrint = false; SE3 c2w = C->shell->camToWorld; t->structPoseEstimation(c2w, overlap); se3_to(c2w, cur_T7_io); delete t; }
+  for (int h = 0; h < nH; h++) drop_points((RefFrame*)kf_frames[h]);
+  return (int)overlap.size();
+}
+
+// debugging aid: reprojectMap + structPoseEstimation on the LIVE window of a running system for a new image at a given pose (what trackNewCoarse does after tracking)
+int ref_sys_debug_refine(void* p, const float* image, double* T7_io, const double* ab, unsigned seed, int* n_active_nonactive /*2*/) {
+  FullSystem* fs = ((RefSys*)p)->fs;
+  FrameHessian* fh = new FrameHessian(); FrameShell* sh = new FrameShell(); sh->id = 100000; fh->shell = sh; fh->ab_exposure = 1;
+  std::vector<float> c(image, image + (size_t)wG[0]*hG[0]); fh->makeImages(c.data(), &fs->Hcalib);
+  sh->camToWorld = se3_from(T7_io); sh->aff_g2l = AffLight(ab[0], ab[1]);
+  int na = 0, nn = 0; for (FrameHessian* f : fs->frameHessians) for (PointHessian* ph : f->pointHessians) { if (ph->status == PointHessian::ACTIVE) na++; else nn++; }
+  n_active_nonactive[0] = na; n_active_nonactive[1] = nn;
+  std::vector<std::pair<PointHessian*, Eigen::Vector2d> > overlap; srand(seed);
+  { Reprojector rp(&fs->Hcalib, fh, fs->frameHessians); rp.reprojectMap(fh, overlap); }
+  SE3 c2w = sh->camToWorld; next_tracker(fs)->structPoseEstimation(c2w, overlap); se3_to(c2w, T7_io);
+  return (int)overlap.size();
+}
 
 }  // extern "C"

@@ -61,27 +61,31 @@ SDV_HD void finalize_gs(const double* tot, double* H /*64*/, double* b /*8*/) {
   }
 }
 
-// same, every caller lane computes but only `write` lanes store (keeps a warp's control flow uniform in the device-resident LM)
-SDV_HD void finalize_gs_guarded(const double* tot, double* H /*64*/, double* b /*8*/, bool write) {
-  int nW = (int)(tot[kIdxNE] - tot[kIdxNSat]);
-  int npad = (nW + 3) & ~3;
-  float invn = 1.0f/npad;
-  const float sc[8] = {1.0f,1.0f,1.0f,0.5f,0.5f,0.5f,10.0f,1000.0f};
-  int k = 0;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
+// finalize_gs spread over the 32 lanes of a warp: lane handles upper-triangle entries k = lane and lane + 32 (45 entries), same arithmetic per entry as finalize_gs
+// (CoarseTracker.cpp:468-483).  45 dependent read-convert-scale-store chains on one lane cost ~9k cycles per LM evaluation; this is ~0.5k.
+__device__ __forceinline__ void finalize_gs_warp(const double* tot, double* H /*64*/, double* b /*8*/, int lane) {
+  const int nW = (int)(tot[kIdxNE] - tot[kIdxNSat]);
+  const int npad = (nW + 3) & ~3;
+  const float invn = 1.0f/npad;
 #pragma unroll
-#endif
-  for (int r=0;r<9;r++) {
-#if defined(__CUDA_ARCH__)
+  for (int rep = 0; rep < 2; rep++) {
+    const int k = lane + 32*rep;
+    if (k < kNH) {
+      // (r,c) of the k-th entry of the row-major upper triangle of the 9x9 system
+      int r = 0, base = 0;
 #pragma unroll
-#endif
-    for (int c=r;c<9;c++) {
-      float hv = (float)tot[k++];
-      if (r < 8 && c < 8) { double v = (double)hv * invn; v *= sc[c]; v *= sc[r]; if (write) { H[r*8+c] = v; H[c*8+r] = v; } }
-      else if (r < 8 && c == 8) { double v = (double)hv * invn; v *= sc[r]; if (write) b[r] = v; }
+      for (int rr = 0; rr < 8; rr++) { const int next = base + (9 - rr); if (k >= next) { r = rr + 1; base = next; } }
+      const int c = r + (k - base);
+      const float scr = (r < 3) ? 1.0f : ((r < 6) ? 0.5f : ((r == 6) ? 10.0f : 1000.0f));   // SCALE_XI_ROT x3, SCALE_XI_TRANS x3, SCALE_A, SCALE_B
+      const float scc = (c < 3) ? 1.0f : ((c < 6) ? 0.5f : ((c == 6) ? 10.0f : 1000.0f));
+      const float hv = (float)tot[k];
+      if (r < 8 && c < 8) { double v = (double)hv * invn; v *= scc; v *= scr; H[r*8+c] = v; H[c*8+r] = v; }
+      else if (r < 8 && c == 8) { double v = (double)hv * invn; v *= scr; b[r] = v; }
     }
   }
 }
+#endif
 
 #if defined(__CUDACC__)
 #ifndef SDV_PREFETCH_MODE

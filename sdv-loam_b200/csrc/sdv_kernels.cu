@@ -741,12 +741,12 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       if (mode == 0) {                                       // level entry: resOld at the current pose (:690-702)
         finalize_res(tot, resOld);
         if (resOld[5] > 0.6 && lcr < 50) { lcr *= 2; repeat_entry = true; }
-        else { finalize_gs_guarded(tot, ctl.H, ctl.b, L0); lambda = 0.01f; iteration = 0; propose = true; }
+        else { finalize_gs_warp(tot, ctl.H, ctl.b, tid); lambda = 0.01f; iteration = 0; propose = true; }
       } else {                                               // candidate evaluated: accept / reject (:770-806)
         double resNew[6]; finalize_res(tot, resNew);
         const bool accept = (resNew[0]/resNew[1]) < (resOld[0]/resOld[1]);
         if (accept) {
-          finalize_gs_guarded(tot, ctl.H, ctl.b, L0);
+          finalize_gs_warp(tot, ctl.H, ctl.b, tid);
 #pragma unroll
           for (int i = 0; i < 6; i++) resOld[i] = resNew[i];
           cur = ctl.cand; a_cur = ctl.a_cand; b_cur = ctl.b_cand;
@@ -760,6 +760,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         if (!(ctl.incn > 1e-3) || iteration >= maxIt) level_end = true; else propose = true;
       }
       __syncwarp();                                          // ctl.H / ctl.b (lane 0's stores) before every lane reads them
+      SDV_PROF_T(tq1); SDV_PROF_ADD(9, tc0, tq1);
       int next_lvl = lvl, next_mode = mode, done = 0, aborted = 0, haveRepeated = ctl.haveRepeated;
       double incn_out = ctl.incn; SE3d cand = cur; double a_cand = a_cur, b_cand = b_cur;
       bool new_ep = false; SE3d ep_pose = cur; double ep_a = a_cur, ep_b = b_cur; int ep_lvl = lvl; float ep_lcr = lcr;
@@ -792,6 +793,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         }
         double rhs = (r < nv) ? -ctl.b[rr] : 0.0;
         const double x = warp_ldlt_solve8(a, rhs);
+        SDV_PROF_T(tq2); SDV_PROF_ADD(10, tq1, tq2);
         double inc[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) inc[j] = __shfl_sync(0xffffffffu, x, j, 8);
@@ -821,7 +823,9 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         incn_out = sqrt(incn);
         cand = se3_mul(se3_exp(incScaled), cur); a_cand = a_cur + incScaled[6]; b_cand = b_cur + incScaled[7];
         next_mode = 1; new_ep = true; ep_pose = cand; ep_a = a_cand; ep_b = b_cand;
+        SDV_PROF_T(tq3); SDV_PROF_ADD(11, tq2, tq3);
       }
+      SDV_PROF_T(tq4);
       EvalParams ep;
       if (new_ep) make_eval_params(ep_pose, ep_a, ep_b, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[ep_lvl], ep_lvl, tc.coarseCutoffTH*ep_lcr, tc.huberTH, ep);
       if (L0) {                                              // publish (plain predicated stores; nothing collective follows inside this block)
@@ -835,6 +839,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         if (level_end) { ctl.lastRes[lvl] = lastRes_l; ctl.flow[0] = resOld[2]; ctl.flow[1] = resOld[3]; ctl.flow[2] = resOld[4]; }
         if (new_ep) ctl.ep = ep;
       }
+      SDV_PROF_T(tq5); SDV_PROF_ADD(12, tq4, tq5);
     }
     __syncthreads();
     SDV_PROF_T(tc1); SDV_PROF_ADD(6, tc0, tc1);

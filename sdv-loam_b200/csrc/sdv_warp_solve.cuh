@@ -83,4 +83,5 @@ __device__ __forceinline__ double warp_ldlt_solve8(double (&a)[8], double rhs) {
   return out;
 }
 
+
 } // namespace sdv

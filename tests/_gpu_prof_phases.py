@@ -27,7 +27,7 @@ for s in (0, 3, 0, 3):
     f(None, 1)
     r = ctx.trackBatch(list(range(B)), list(range(B)), T, ab)
     f(prof.ctypes.data, 0)
-names = ["issue", "flowpass", "first wait+project", "main loop", "drain+sync", "reduce", "control"]
+names = ["issue", "flowpass", "first wait+project", "main loop", "drain+sync", "reduce", "control", "-", "(evals)", "ctl: finalize/accept", "ctl: ldlt solve", "ctl: exp/mul", "ctl: eval params+publish"]
 n = max(int(prof[8]), 1)
 print(f"B={B} th={th} cs={cs} kernel {ctx.last_kernel_ms():.4f} ms, evals (block 0) {n}")
 for i, nm in enumerate(names):
