@@ -32,6 +32,14 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 WORKLOAD = "S-KITTI tracker step: %d resident sequences/GPU x 1 frame (1200x360 crop of 1241x376, 4 pyramid levels, %d LiDAR-depth splats -> ~10k reference points at level 0), batched mode"
+N_INIT_POOL = 24                 # distinct batches of initial guesses, cycled (drawing 500 x 592 guesses in Python would dominate the set-up)
+
+
+def common_config(args, world, B):
+    """config keys shared by the B200 arm and the reference arm (the driver compares them)"""
+    return {"workload": WORKLOAD % (B, args.points), "sequences_per_gpu": B, "global_batch_frames": world * B, "batches_per_step": args.batches,
+            "parallelism": "seq-shard x%d (no data-path collective)" % world,
+            "init": "ground truth perturbed N(4cm, 0.002rad) (constant-motion prediction error)"}
 ALG_BYTES_PER_EVAL = 64          # 16 B point + 4 texels x 12 B  (SURVEY.md §8d, BASELINE.md §3)
 N_FRAMES = 4                     # frame 0 = keyframe, frames 1..3 tracked against it in turn
 
@@ -125,9 +133,52 @@ def ncu_traffic():
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def ref_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref
+        return ref.available() and ref.build() is not None
+    except Exception:
+        return False
+
+
+class RefArm:
+    """The REFERENCE's own FrameHessian::makeImages + CoarseTracker::trackNewestCoarse (oracle/_ref/libsdvref.so = /root/reference/src compiled unmodified against stand-in
+    headers, see oracle/Makefile), one independent sequence per host thread, the frame loop inside one C call per thread (ref_bench_track_loop)."""
+    kind = "reference"
+
+    def __init__(self, seq, synth, p4, threads):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref
+        self.ref = ref; self.orc = se3_helpers(); self.seq, self.synth, self.threads = seq, synth, threads
+        try:                                                                  # the reference allocates a fresh FrameHessian pyramid (10 MB) per frame: keep those blocks on the heap, or glibc
+            libc = ctypes.CDLL("libc.so.6"); libc.mallopt(-3, 1 << 30); libc.mallopt(-1, 1 << 30)   # mmaps/unmaps each one and the threads serialise in the kernel (M_MMAP_THRESHOLD, M_TRIM_THRESHOLD)
+        except OSError:
+            pass
+        w, h = synth.KITTI_WH; self.L = ref.set_calib(w, h, synth.KITTI_K); ref.settings()
+        self.gts = [self.orc.se3_from_rt(*synth.rel_pose(seq.R[0], seq.t[0], seq.R[k], seq.t[k])) for k in range(N_FRAMES)]
+        self.imgs = [np.ascontiguousarray(im, np.float32) for im in seq.images]
+        self.trackers = []
+        for i in range(threads):
+            f0 = ref.Frame(self.imgs[0], (w, h), self.L); tr = ref.CoarseTracker(); tr.setCoarseTrackingRef(f0, p4, np.zeros(len(p4), np.int32)); self.trackers.append((f0, tr))
+        self.rngs = [np.random.default_rng(100 + i) for i in range(threads)]; self.count = [0] * threads
+        L = ref.lib(); L.ref_bench_track_loop.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                           np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+        self.ptrs = (ctypes.c_void_p * (N_FRAMES - 1))(*[self.imgs[k].ctypes.data for k in range(1, N_FRAMES)])
+
+    def run(self, frames_per_thread, budget_s=None):
+        return _arm_run(self, frames_per_thread, budget_s)
+
+    def _work(self, i, n_frames, budget_s, inits):
+        done = self.ref.lib().ref_bench_track_loop(self.trackers[i][1].p, self.ptrs, N_FRAMES - 1, self.count[i] % (N_FRAMES - 1), len(inits), inits, float(budget_s or 0.0), None, None)
+        self.count[i] += done
+        return done
+
+
 class CpuArm:
     """The oracle's makeImages + trackNewestCoarse, one independent sequence per host thread (ctypes releases the GIL).
     Keyframe pyramids / reference clouds are built once up front, like the GPU arm does before its timed region."""
+    kind = "port"
 
     def __init__(self, seq, synth, p4, threads):
         self.orc = orc = se3_helpers()
@@ -168,9 +219,22 @@ class CpuArm:
         return done
 
     def run(self, frames_per_thread, budget_s=None):
+        return _arm_run(self, frames_per_thread, budget_s)
+
+
+def _arm_inits(arm, i, n):
+    orc = arm.orc; rng = arm.rngs[i]; out = np.zeros((n, 7))
+    for f in range(n):
+        k = 1 + (arm.count[i] + f) % (N_FRAMES - 1)
+        out[f] = orc.se3_mul(orc.se3_exp(np.concatenate([rng.normal(0, 0.04, 3), rng.normal(0, 0.002, 3)])), arm.gts[k])
+    return out
+
+
+def _arm_run(self, frames_per_thread, budget_s=None):
+    if True:
         res = [0] * self.threads
         n = min(frames_per_thread, 4096)
-        inits = [self._inits(i, n) for i in range(self.threads)]
+        inits = [_arm_inits(self, i, n) for i in range(self.threads)]
         def job(i): res[i] = self._work(i, n, budget_s, inits[i])
         th = [threading.Thread(target=job, args=(i,)) for i in range(self.threads)]
         t0 = time.perf_counter()
@@ -293,46 +357,128 @@ def host_cores():
     return n
 
 
+def make_cpu_arm(seq, synth, p4, threads):
+    """the reference's own code when oracle/_ref can be had (it travels prebuilt to the GPU box), else the oracle port"""
+    return RefArm(seq, synth, p4, threads) if ref_available() else CpuArm(seq, synth, p4, threads)
+
+
+def cpu_note(arm):
+    if arm.kind == "reference":
+        return "the reference's own sources (/root/reference/src, unmodified) compiled against stand-in Eigen/Sophus headers (oracle/_ref, g++ -O3, SSE2, no FMA)"
+    return "oracle/ CPU restatement (g++ -O3, no FMA): oracle/_ref is not available on this box"
+
+
+def single_sequence_leg(api, synth, seq, p4, rh, local_rank, frames=240, warm=12):
+    """BASELINE.json configs[1]/[2] as written: ONE sequence on one GPU.  A sequence is a chain (frame n+1 needs frame n's pose; an LM iteration needs the previous one), so
+    this is a latency figure: makeImages + trackNewestCoarse per frame with the low-latency launch (256 threads, thread-block cluster of 16 CTAs, DSMEM all-gather of the
+    partial sums).  device = CUDA-event time of the kernels; e2e = wall clock per frame with the mono8 image uploaded from pinned host memory and the pose read back."""
+    import torch
+    w, h = synth.KITTI_WH
+    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=1, max_frames=8, cluster_size=16, track_threads=256)
+    KF = 1 << 40; ctx.makeImages(KF, seq.images[0]); tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(KF, p4, rh)
+    gts, inits = gt_and_inits(seq, synth, 1, N_INIT_POOL, seed=99)
+    host_u8 = torch.empty((N_FRAMES - 1, h, w), dtype=torch.uint8).pin_memory()
+    for k in range(N_FRAMES - 1):
+        host_u8[k].copy_(torch.from_numpy(seq.images[1 + k].astype(np.uint8)))
+    ptrs = [np.array([host_u8[k].data_ptr()], np.uint64) for k in range(N_FRAMES - 1)]
+    slots = np.zeros(1, np.int32); dev_ms = []; t0 = None
+    for f in range(warm + frames):
+        if f == warm:
+            ctx.sync(); t0 = time.perf_counter()
+        ids = np.array([f & 1], np.uint64)
+        ctx.makeImagesBatch(ids, ptrs[f % (N_FRAMES - 1)], u8=True)
+        T = inits[(3 * (f // 3) + f % (N_FRAMES - 1)) % len(inits)].copy(); ab = np.zeros((1, 2))
+        r = ctx.trackBatch(slots, ids, T, ab)
+        if f >= warm:
+            dev_ms.append(ctx.last_kernel_ms())
+    ctx.sync(); wall = time.perf_counter() - t0
+    ok = bool(r["good"][0]); ctx.close()
+    return {"frames": frames, "frames_per_s_e2e": frames / wall, "ms_per_frame_e2e": 1e3 * wall / frames, "track_kernel_ms": float(np.mean(dev_ms)), "tracked_ok": ok,
+            "launch": "track_cluster_kernel<256,1>, cluster of 16 CTAs per job (DSMEM), 1 job",
+            "note": "one sequence = a dependent chain: latency-bound by design (SURVEY 8e: replicas only within a sequence); the batched mode above is the throughput mode"}
+
+
+def stress_leg(api, local_rank):
+    """BASELINE.json configs[4] (S-STRESS): 1920x1200, 5 pyramid levels, ~160k reference points at level 0 (32k active points x ~5 from the dilation), 8-keyframe window with
+    32k points.  Step-wise residual/Jacobian kernel (coarse_res_gs_kernel = calcRes + calcGSSSE fused, solve on host) and the device-resident tracker on ONE job."""
+    w, h = 1920, 1200; K = (1100.0, 1100.0, 959.5, 599.5)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.rint(127 + 60 * np.sin(xx / 23.0) * np.cos(yy / 31.0) + 30 * np.sin((xx + yy) / 7.0)).astype(np.float32)
+    ctx = api.Context(K, w, h, device=local_rank, max_frames=3, n_tracker_slots=1, cluster_size=16, track_threads=256)
+    ctx.makeImages(0, img); ctx.makeImages(1, np.roll(img, 2, axis=1)); tr = api.CoarseTracker(ctx, 0)
+    rng = np.random.default_rng(0); T = np.array([1, 0, 0, 0, 0.01, 0, 0.0]); out = {"image": "1920x1200", "levels": ctx.levels}
+    n = 163840
+    for lvl in range(ctx.levels):
+        wl, hl = w >> lvl, h >> lvl; nl = min(n, (wl - 8) * (hl - 8) // 2)
+        u = rng.uniform(4, wl - 5, nl).astype(np.float32); v = rng.uniform(4, hl - 5, nl).astype(np.float32)
+        order = np.lexsort((u, v.astype(np.int32))); u, v = u[order], v[order]              # raster order like makeCoarseDepthL0
+        tr.setCloud(0, lvl, u, v, rng.uniform(0.02, 0.2, nl).astype(np.float32), rng.uniform(0, 255, nl).astype(np.float32))
+        if lvl == 0:
+            ms = []
+            for rep in range(14):
+                tr.calcRes(1, 0, T, 0.0, 0.0, 20.0); ms.append(ctx.last_kernel_ms())
+            m = float(np.median(ms[4:]))
+            out["coarse_res_gs_level0"] = {"points": int(nl), "us_per_pass": 1e3 * m, "GBps_algorithmic": ALG_BYTES_PER_EVAL * nl / (m * 1e-3) / 1e9}
+    ms = []; ev = 0
+    for rep in range(6):
+        r = tr.trackNewestCoarse(1, np.array([1, 0, 0, 0, 0, 0, 0.0]), [0.0, 0.0]); ms.append(ctx.last_kernel_ms()); ev = int(np.sum(r["evals"]))
+    m = float(np.median(ms[2:])); peak, _ = measured_peak()
+    out["track_one_job"] = {"ms": m, "point_evals": ev, "GBps_algorithmic": ALG_BYTES_PER_EVAL * ev / (m * 1e-3) / 1e9, "frac_of_peak": ALG_BYTES_PER_EVAL * ev / (m * 1e-3) / 1e9 / peak,
+                            "launch": "cluster of 16 CTAs x 256 threads (one job cannot fill 148 SMs: latency-bound, see DESIGN.md 4)"}
+    ctx.close()
+    return out
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores (oracle/_ref when available, else the oracle port), same workload / metric / config keys."""
+    if rank != 0:
+        return
+    seq, synth = load_sequence()
+    p4 = np.concatenate([synth.select_points(seq.images[0], seq.clouds[0], args.points), np.full((args.points, 1), 1e-3, np.float32)], 1).astype(np.float32)
+    cores = host_cores(); per = 16
+    arm = make_cpu_arm(seq, synth, p4, cores)
+    W = max(args.warmup, 0)
+    for _ in range(W):
+        arm.run(2)
+    steps = max(1, min(args.steps, 20)); tot_f = 0; tot_t = 0.0
+    for _ in range(steps):
+        f, t = arm.run(per); tot_f += f; tot_t += t
+    fps = tot_f / tot_t
+    cfg = common_config(args, max(1, args.gpus), args.seqs)
+    cfg["note"] = "same workload definition as the B200 arm; each CPU step is a bounded sample of it: %d threads x %d frames, one sequence per thread" % (cores, per)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": arm.kind, "threads": cores, "frames_per_s_per_thread": fps / cores,
+                             "sample": "%d steps x %d threads x %d frames, one sequence per thread; %s" % (steps, cores, per, cpu_note(arm))},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+METRIC = "frames/sec (KITTI 1241x376 + 64-beam): makeImages + trackNewestCoarse per frame"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--seqs", type=int, default=592, help="resident sequences per GPU (148 SMs x 4 jobs)")
+    ap.add_argument("--seqs", type=int, default=1184, help="resident sequences per GPU (148 SMs x 4 co-resident jobs x 2 waves)")
+    ap.add_argument("--batches", type=int, default=12, help="batches (one frame of every resident sequence) per step: makes the timed region >= 1 s at the default --steps")
     ap.add_argument("--points", type=int, default=2000, help="LiDAR-depth splats of the keyframe (reference default ~1500-2000 active points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--track-threads", type=int, default=128, help="threads per trackNewestCoarse job (128: 4 jobs/SM; 64: 8 jobs/SM; 256: latency mode)")
     ap.add_argument("--ba-windows", type=int, default=296, help="BA leg: resident 7-keyframe windows optimised per batch (0 = skip the BA leg)")
     ap.add_argument("--no-refine", action="store_true", help="skip the reprojectMap + structPoseEstimation leg")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the single-sequence and S-STRESS legs")
     ap.add_argument("--kf-every", type=int, default=5, help="keyframe cadence assumed when combining the tracker and BA legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")          # NCCL's version banner / debug lines must not land on stdout next to the JSON line
-    W = max(args.warmup, 3)
-
     if args.impl == "reference":
-        if rank != 0:
-            return
-        seq, synth = load_sequence()
-        p4 = np.concatenate([synth.select_points(seq.images[0], seq.clouds[0], args.points), np.full((args.points, 1), 1e-3, np.float32)], 1).astype(np.float32)
-        cores = host_cores(); per = 16
-        arm = CpuArm(seq, synth, p4, cores)
-        for _ in range(min(W, 3)):
-            arm.run(2)
-        steps = min(args.steps, 20); tot_f = 0; tot_t = 0.0
-        for _ in range(steps):
-            f, t = arm.run(per); tot_f += f; tot_t += t
-        fps = tot_f / tot_t
-        line = {"impl": "reference", "metric": "frames/sec (KITTI 1241x376 + 64-beam): makeImages + trackNewestCoarse per frame", "value": fps, "unit": "frames/s",
-                "n_gpus": args.gpus, "steps": steps, "warmup": min(W, 3), "ms_per_step": 1e3 * tot_t / steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD % (args.seqs, args.points), "frames_per_step": cores * per,
-                           "note": "same workload definition as the B200 arm; each CPU step is a bounded sample of it: %d threads x %d frames, one sequence per thread" % (cores, per)},
-                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                 "sample": "%d steps x %d threads x %d frames, one sequence per thread; oracle/ CPU restatement (g++ -O3, no FMA) — the reference binary cannot be built here (no Eigen3/Boost/ROS)" % (steps, cores, per)},
-                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line)); return
+        reference_arm(args, rank, world); return
+    W = max(args.warmup, 3); R = max(1, args.batches)
 
     import torch
     import torch.distributed as dist
@@ -352,36 +498,28 @@ def main():
     KF = 1 << 40
     for b in range(B):                                                   # per sequence: keyframe -> reference cloud (makeCoarseDepthL0 on device)
         ctx.makeImages(KF, seq.images[0]); api.CoarseTracker(ctx, b).setCoarseTrackingRef(KF, p4, rh); ctx.releaseFrame(KF)
-    steps_total = 3 * (W + K + 2)
-    gts, inits = gt_and_inits(seq, synth, B, steps_total, seed=7 + rank)
+    gts, inits = gt_and_inits(seq, synth, B, N_INIT_POOL, seed=7 + rank)          # pool index s is for frame 1 + s % 3
     frames_np = np.stack(seq.images[1:]).astype(np.float32)              # (3,h,w)
     # device-resident raw inputs (value leg): one private copy per sequence, so nothing is artificially shared in L2
     dev_in = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.float32, device="cuda")
     for k in range(N_FRAMES - 1):
         dev_in[k] = torch.from_numpy(frames_np[k]).cuda()
-    # pinned host inputs (e2e leg)
-    host_in = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.float32).pin_memory()
-    for k in range(N_FRAMES - 1):
-        host_in[k].copy_(torch.from_numpy(frames_np[k]).expand(B, h, w))
     slots = np.arange(B, dtype=np.int32)
     ids_par = [np.arange(B, dtype=np.uint64) * 2 + p for p in (0, 1)]       # frame handles alternate between two pool slots per sequence
     stride = h * w * 4
     dev_ptrs = [np.uint64(dev_in[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(stride) for k in range(N_FRAMES - 1)]
-    host_ptrs = None
 
     def frame_ids(step):
         return ids_par[step & 1]
 
+    def init_of(step):                                                   # batch `step` shows frame 1 + step % 3: take a pool entry drawn for that frame
+        return inits[(3 * (step // 3) + step % (N_FRAMES - 1)) % N_INIT_POOL]
+
     def step_dev(step):
         ctx.makeImagesBatch(frame_ids(step), dev_ptrs[step % (N_FRAMES - 1)], device=True, adopt=True)   # zero-copy: level-0 plane = the resident input
-        T = inits[step].copy(); ab = np.zeros((B, 2))
+        T = init_of(step).copy(); ab = np.zeros((B, 2))
         r = ctx.trackBatch(slots, frame_ids(step), T, ab)
         return r, T
-
-    host_ptrs = [np.uint64(host_in[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(stride) for k in range(N_FRAMES - 1)]
-
-    def upload_host(step):
-        ctx.makeImagesBatch(frame_ids(step), host_ptrs[step % (N_FRAMES - 1)])
 
     def barrier():
         torch.cuda.synchronize(); ctx.sync()
@@ -390,39 +528,44 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- leg 1: inputs resident in HBM
-    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.3)   # samples span both timed legs (each is only tens of ms)
-    for s in range(W):
+    sampler = ClockSampler(local_rank); sampler.start(); time.sleep(0.3)
+    for s in range(W * R):
         step_dev(s)
     barrier(); l0 = ctx.launch_count()
-    t0 = time.perf_counter(); kern_ms = 0.0; evals = 0; good = 0; pose_err = 0.0
-    for s in range(W, W + K):
+    t0 = time.perf_counter(); kern_ms = 0.0; evals = 0; good = 0
+    for s in range(W * R, (W + K) * R):
         r, T = step_dev(s)
         kern_ms += ctx.last_kernel_ms(); evals += int(r["evals"].sum()); good += int(r["good"].sum())
     barrier(); t_value = time.perf_counter() - t0
     launches = ctx.launch_count() - l0
-    k_last = 1 + (W + K - 1) % (N_FRAMES - 1)
+    k_last = 1 + ((W + K) * R - 1) % (N_FRAMES - 1)
     errs = [np.abs(synth.se3_log7(synth.se3_mul7(T[b], synth.se3_inv7(gts[k_last])))) for b in range(min(B, 16))]
     pose_err_t = float(max(e[:3].max() for e in errs)); pose_err_r = float(max(e[3:].max() for e in errs))
+    NB = K * R                                                            # timed batches per leg
 
-    # ---------------------------------------------------------------- leg 2: end to end through host buffers (H2D + D2H every step)
-    s0 = W + K
-    upload_host(s0)
-    for s in range(s0, s0 + W):                                          # warm-up, same software pipeline
-        upload_host(s + 1)
-        T = inits[s].copy(); ab = np.zeros((B, 2)); ctx.trackBatch(slots, frame_ids(s), T, ab)
-    barrier()
-    s1 = s0 + W
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(s1, s1 + K):
-        if s + 1 < s1 + K:
-            upload_host(s + 1)                                           # async H2D + pyramid of the next batch overlaps this batch's tracking
-        T = inits[s].copy(); ab = np.zeros((B, 2))
-        ctx.trackBatch(slots, frame_ids(s), T, ab)                       # D2H of poses/residuals inside
-    barrier(); t_e2e = time.perf_counter() - t0
-    # the first batch's upload happened before t0: charge it (one un-overlapped upload) so every step's H2D is inside the timed region
-    tu = time.perf_counter(); upload_host(s1 + K); ctx.sync(); t_e2e += time.perf_counter() - tu
-    # ---------------------------------------------------------------- leg 2b: same, raw mono8 wire format (sensor_msgs/Image), conversion fused on device
+    # ---------------------------------------------------------------- leg 2: end to end through host buffers (H2D + D2H every batch)
+    def e2e_leg(upload, first):
+        upload(first)
+        for s in range(first, first + W):                                # warm-up, same software pipeline
+            upload(s + 1); T = init_of(s).copy(); ab = np.zeros((B, 2)); ctx.trackBatch(slots, frame_ids(s), T, ab)
+        barrier(); s1 = first + W
+        t0 = time.perf_counter()
+        for s in range(s1, s1 + NB):
+            if s + 1 < s1 + NB:
+                upload(s + 1)                                            # async H2D + pyramid of the next batch overlaps this batch's tracking
+            T = init_of(s).copy(); ab = np.zeros((B, 2))
+            ctx.trackBatch(slots, frame_ids(s), T, ab)                   # D2H of poses/residuals inside
+        barrier(); t = time.perf_counter() - t0
+        # the first batch's upload happened before t0: charge it (one un-overlapped upload) so every batch's H2D is inside the timed region
+        tu = time.perf_counter(); upload(s1 + NB); ctx.sync(); t += time.perf_counter() - tu
+        return t, s1 + NB + 1
+
+    host_in = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.float32).pin_memory()
+    for k in range(N_FRAMES - 1):
+        host_in[k].copy_(torch.from_numpy(frames_np[k]).expand(B, h, w))
+    host_ptrs = [np.uint64(host_in[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(stride) for k in range(N_FRAMES - 1)]
+    t_e2e, nxt = e2e_leg(lambda step: ctx.makeImagesBatch(frame_ids(step), host_ptrs[step % (N_FRAMES - 1)]), (W + K) * R)
+    del host_in
     host_u8 = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.uint8).pin_memory()
     for k in range(N_FRAMES - 1):
         host_u8[k].copy_(torch.from_numpy(frames_np[k].astype(np.uint8)).expand(B, h, w))
@@ -430,18 +573,7 @@ def main():
 
     def upload_u8(step):
         ctx.makeImagesBatch(frame_ids(step), u8_ptrs[step % (N_FRAMES - 1)], u8=True)
-    s2 = s1 + K + 1
-    upload_u8(s2)
-    for s in range(s2, s2 + W):
-        upload_u8(s + 1); T = inits[s % steps_total].copy(); ab = np.zeros((B, 2)); ctx.trackBatch(slots, frame_ids(s), T, ab)
-    barrier(); s3 = s2 + W
-    t0 = time.perf_counter()
-    for s in range(s3, s3 + K):
-        if s + 1 < s3 + K:
-            upload_u8(s + 1)
-        T = inits[s % steps_total].copy(); ab = np.zeros((B, 2)); ctx.trackBatch(slots, frame_ids(s), T, ab)
-    barrier(); t_e2e_u8 = time.perf_counter() - t0
-    tu = time.perf_counter(); upload_u8(s3 + K); ctx.sync(); t_e2e_u8 += time.perf_counter() - tu
+    t_e2e_u8, s3 = e2e_leg(upload_u8, nxt)
     # ---------------------------------------------------------------- leg 2c: the WHOLE FullSystem::trackNewCoarse per frame through host buffers: mono8 upload ->
     # motion hypotheses + trackNewestCoarse re-track loop -> reprojectMap -> structPoseEstimation (sdv_track_new_coarse_batch), pose D2H
     t_e2e_full = None; full_stats = None
@@ -453,35 +585,37 @@ def main():
         for b in range(B):
             rp.setMap(b, [KFM], kf_c2w[None], None, mp)
         order = np.random.default_rng(3).permutation(rp.n_cells).astype(np.int32)
-        nfull = W + K + 2
-        io_all = np.zeros((nfull, B), api.TRACK_NEW_COARSE_DTYPE)
-        for i in range(nfull):                                           # history chosen so that the constant-motion hypothesis equals the perturbed initial guess of the other legs:
+        KF_full = min(K * R, 3 * K); nfull = W + KF_full + 2
+        io_all = np.zeros((N_INIT_POOL, B), api.TRACK_NEW_COARSE_DTYPE)
+        for i in range(N_INIT_POOL):                                     # history chosen so that the constant-motion hypothesis equals the perturbed initial guess of the other legs:
             io = io_all[i]; io["slot"] = slots; io["poses_valid"] = 1    # slast = lastF (keyframe pose), sprelast = lastF * init  =>  try 0 = init
             io["lastF_c2w"] = kf_c2w; io["slast_c2w"] = kf_c2w; io["lastCoarseRMSE"] = 100.0
             for b in range(B):
-                io["sprelast_c2w"][b] = synth.se3_mul7(kf_c2w, inits[(s3 + i) % steps_total, b])
+                io["sprelast_c2w"][b] = synth.se3_mul7(kf_c2w, inits[i, b])
         upload_u8(s3)
+
         def full_step(i):
-            io = io_all[i]; io["frame"] = frame_ids(s3 + i)
+            io = io_all[(3 * ((s3 + i) // 3) + (s3 + i) % (N_FRAMES - 1)) % N_INIT_POOL].copy(); io["frame"] = frame_ids(s3 + i)
             api.trackNewCoarseBatchArray(ctx, io, cell_order=order, max_matches=400)
             return io
         for i in range(W):
             upload_u8(s3 + i + 1); full_step(i)
         barrier(); t0 = time.perf_counter()
-        for i in range(W, W + K):
-            if i + 1 < W + K:
+        for i in range(W, W + KF_full):
+            if i + 1 < W + KF_full:
                 upload_u8(s3 + i + 1)
             io = full_step(i)
         barrier(); t_e2e_full = time.perf_counter() - t0
-        tu = time.perf_counter(); upload_u8(s3 + W + K); ctx.sync(); t_e2e_full += time.perf_counter() - tu
-        k_last = 1 + (s3 + W + K - 1) % (N_FRAMES - 1)
+        tu = time.perf_counter(); upload_u8(s3 + W + KF_full); ctx.sync(); t_e2e_full += time.perf_counter() - tu
+        k_last = 1 + (s3 + W + KF_full - 1) % (N_FRAMES - 1)
         gt_c2w = np.concatenate([synth._quat_from_R(seq.R[k_last]), seq.t[k_last]])
-        full_stats = {"tries_mean": float(io["tries"].mean()), "matches_mean": float(io["n_matches"].mean()), "refine_accepts_mean": float(io["refine_accepts"].mean()),
+        full_stats = {"batches": KF_full, "tries_mean": float(io["tries"].mean()), "matches_mean": float(io["n_matches"].mean()), "refine_accepts_mean": float(io["refine_accepts"].mean()),
                       "median_translation_err_m": float(np.median(np.linalg.norm(io["camToWorld"][:, 4:] - gt_c2w[4:], axis=1)))}
     clocks = sampler.stop()
+    del host_u8
 
     ba = ba_leg(ctx, api, synth, local_rank, WBA) if WBA > 0 else None
-    refine = refine_leg(ctx, api, synth, B, cpu=not args.no_cpu_baseline) if not args.no_refine else None
+    refine = refine_leg(ctx, api, synth, min(B, 592), cpu=not args.no_cpu_baseline) if not args.no_refine else None
     tv = torch.tensor([t_value, t_e2e, kern_ms, t_e2e_u8, t_e2e_full or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
@@ -489,39 +623,49 @@ def main():
     ev = torch.tensor([float(evals), float(good)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ev, op=dist.ReduceOp.SUM)
+    ctx.close()
+    # ---------------------------------------------------------------- one sequence per GPU (BASELINE configs as written): every rank runs its own chain
+    single = None
+    if not args.no_extra_legs:
+        single = single_sequence_leg(api, synth, seq, p4, rh, local_rank)
+        sv = torch.tensor([single["frames_per_s_e2e"], 1.0 / single["track_kernel_ms"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sv, op=dist.ReduceOp.SUM)
+        single["one_seq_per_gpu_frames_per_s_e2e"] = float(sv[0].item()); single["gpus"] = world
     if rank != 0:
-        ctx.close(); return
+        if world > 1:
+            dist.destroy_process_group()
+        return
     peak, peak_src = measured_peak()
     job_bytes = api.track_job_bytes()
     achieved = evals * ALG_BYTES_PER_EVAL / (kern_ms * 1e-3) / 1e9      # this rank's kernel: algorithmic GB/s
     traffic = ncu_traffic()
+    cfg = common_config(args, world, B)
+    cfg.update({"l2_policy": "inputs larger than L2: %.1f GB of per-sequence pyramids+clouds per batch vs 126 MB L2" % (B * 9.3e-3),
+                "timed_region_s": t_value, "tracked_ok_fraction": float(ev[1].item()) / (world * B * NB), "pose_err_vs_gt_m_rad": [pose_err_t, pose_err_r]})
     line = {
-        "metric": "frames/sec (KITTI 1241x376 + 64-beam): makeImages + trackNewestCoarse per frame",
-        "value": world * B * K / t_value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": 1e3 * t_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD % (B, args.points),
-                   "sequences_per_gpu": B, "global_batch_frames": world * B, "parallelism": "seq-shard x%d (no data-path collective)" % world,
-                   "l2_policy": "inputs larger than L2: %.1f GB of per-sequence pyramids+clouds per step vs 126 MB L2" % (B * 9.3e-3),
-                   "init": "ground truth perturbed N(4cm, 0.002rad) (constant-motion prediction error)",
-                   "tracked_ok_fraction": float(ev[1].item()) / (world * B * K), "pose_err_vs_gt_m_rad": [pose_err_t, pose_err_r]},
-        "e2e": {"value": world * B * K / t_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": B * h * w + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
+        "metric": METRIC, "value": world * B * NB / t_value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "e2e": {"value": world * B * NB / t_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": R * (B * h * w + B * job_bytes), "d2h_bytes_per_step": R * B * job_bytes,
                 "api": "sdv_frame_upload_batch_u8 (pinned host mono8 = the sensor_msgs/Image wire format the reference ingests; u8->float fused into the pyramid kernel) + sdv_tracker_track_batch; "
                        "upload of batch k+1 overlapped with tracking of batch k; synthetic frames are mono8-exact, results identical to the float path"},
-        "e2e_float32": {"value": world * B * K / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": B * h * w * 4 + B * job_bytes, "d2h_bytes_per_step": B * job_bytes,
+        "e2e_float32": {"value": world * B * NB / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": R * (B * h * w * 4 + B * job_bytes), "d2h_bytes_per_step": R * B * job_bytes,
                         "api": "sdv_frame_upload_batch(float*, pinned) = FrameHessian::makeImages(float*) signature + sdv_tracker_track_batch; PCIe-bound (4x the bytes of the wire format)"},
-        "e2e_trackNewCoarse": (None if not full_stats else dict({"value": world * B * K / t_e2e_full_max, "unit": "frames/s", "h2d_bytes_per_step": B * h * w + B * (job_bytes + 416),
-                               "d2h_bytes_per_step": B * (job_bytes + 416),
+        "e2e_trackNewCoarse": (None if not full_stats else dict({"value": world * B * full_stats["batches"] / t_e2e_full_max, "unit": "frames/s", "h2d_bytes_per_batch": B * h * w + B * (job_bytes + 416),
+                               "d2h_bytes_per_batch": B * (job_bytes + 416),
                                "api": "sdv_frame_upload_batch_u8 + sdv_track_new_coarse_batch (the whole FullSystem::trackNewCoarse: hypotheses, trackNewestCoarse re-track loop, reprojectMap, "
                                       "structPoseEstimation) on host buffers; single-keyframe map of the bench sequence"}, **full_stats)),
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"kernel": "track_cluster_kernel<128,4> (device-resident trackNewestCoarse: calcRes+calcGSSSE+LM)", "bound": "hbm",
+        "roofline": {"kernel": "track_cluster_kernel<128,4> (device-resident trackNewestCoarse: calcRes+calcGSSSE+LM; TMA bulk point staging + cp.async tap ring)", "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": evals * ALG_BYTES_PER_EVAL / K, "point_evals_per_launch": evals / K,
-                     "avg_launch_ms": kern_ms / K, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                     "algorithmic_bytes_per_launch": evals * ALG_BYTES_PER_EVAL / NB, "point_evals_per_launch": evals / NB,
+                     "avg_launch_ms": kern_ms / NB, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                      "kernel_share_of_step": kern_ms * 1e-3 / t_value},
     }
+    if single is not None:
+        line["single_sequence"] = single
+        line["s_stress"] = stress_leg(api, local_rank)
     if ba is not None:
         ba["windows_per_s"] *= world   # every rank optimises its own windows (weak scaling, no collective)
         line["ba"] = ba
@@ -535,17 +679,18 @@ def main():
         refine["frames_per_s_device"] *= world; refine["frames_per_s_wall"] *= world
         line["refine"] = refine
     if not args.no_cpu_baseline:
-        arm = CpuArm(seq, synth, p4, 1); arm.run(3)
+        arm = make_cpu_arm(seq, synth, p4, 1); arm.run(3)
         nf, tw = arm.run(10 ** 9, budget_s=12.0)
+        if single is not None:
+            single["cpu_1thread_frames_per_s"] = nf / tw
         if ba is not None:
             cms = ba_cpu_ms(synth); line["ba"]["cpu_ms_per_window_1core"] = cms
             line["combined"]["cpu_frames_per_s_track_plus_ba_1core"] = 1.0 / (tw / nf + cms * 1e-3 / args.kf_every)
             if refine is not None:
                 line["combined"]["cpu_frames_per_s_track_refine_ba_1core"] = 1.0 / (tw / nf + refine["cpu_ms_per_frame_1core"] * 1e-3 + cms * 1e-3 / args.kf_every)
-        line["cpu_baseline"] = {"value": nf / tw, "unit": "frames/s", "cores": 1, "kind": "port",
-                                "sample": "%d frames (makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; oracle/ CPU restatement, g++ -O3 no FMA — reference binary unbuildable here" % (nf, tw)}
+        line["cpu_baseline"] = {"value": nf / tw, "unit": "frames/s", "cores": 1, "kind": arm.kind,
+                                "sample": "%d frames (makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; %s" % (nf, tw, cpu_note(arm))}
     print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

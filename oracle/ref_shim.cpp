@@ -45,6 +45,7 @@
 #include "util/globalFuncs.h"
 #include "util/settings.h"
 #include "util/FrameShell.h"
+#include "util/Undistort.h"
 #undef private
 #undef protected
 #include <vector>
@@ -418,6 +419,51 @@ int ref_sys_debug_refine(void* p, const float* image, double* T7_io, const doubl
   { Reprojector rp(&fs->Hcalib, fh, fs->frameHessians); rp.reprojectMap(fh, overlap); }
   SE3 c2w = sh->camToWorld; next_tracker(fs)->structPoseEstimation(c2w, overlap); se3_to(c2w, T7_io);
   return (int)overlap.size();
+}
+
+// ---- timing loop of the REFERENCE CPU arm (bench.py cpu_baseline / --impl reference): n_frames x { FrameHessian::makeImages ; CoarseTracker::trackNewestCoarse } in one call
+// on one host thread, the reference's own code (a FrameHessian is allocated and freed per frame, as addActiveFrame does).  One tracker object per thread; the calibration
+// globals are only read.  Same contract as orc_bench_track_loop.
+#include <time.h>
+int ref_bench_track_loop(void* t, const float* const* imgs, int n_imgs, int start, int n_frames, const double* inits7, double budget_s, double* last_T7, int* good_count) {
+  CoarseTracker* T = (CoarseTracker*)t; timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+  Vec5 mr; for (int i = 0; i < 5; i++) mr[i] = NAN;
+  int done = 0, good = 0; FrameShell shell; std::vector<float> buf((size_t)wG[0]*hG[0]);
+  for (int f = 0; f < n_frames; f++) {
+    FrameHessian* fh = new FrameHessian(); fh->shell = &shell; fh->ab_exposure = 1;
+    memcpy(buf.data(), imgs[(start + f) % n_imgs], buf.size()*sizeof(float));
+    fh->makeImages(buf.data(), g_calib);
+    SE3 s = se3_from(inits7 + 7*(size_t)f); AffLight aff(0, 0);
+    if (T->trackNewestCoarse(fh, s, aff, pyrLevelsUsed-1, mr, 0)) good++;
+    if (last_T7) se3_to(s, last_T7);
+    fh->efFrame = 0; delete fh; done++;
+    if (budget_s > 0) { timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); if ((t1.tv_sec - t0.tv_sec) + 1e-9*(t1.tv_nsec - t0.tv_nsec) > budget_s) break; }
+  }
+  if (good_count) *good_count = good;
+  return done;
+}
+
+// ---------------------------------------------------------------------------------------------- ingest: Undistort (util/Undistort.cpp) — photometric processFrame + geometric crop-remap
+// config_text: the content of a calibration file (reference format, e.g. calib/KITTI/00.txt: "Pinhole fx fy cx cy 0 / wOrg hOrg / crop / w h").  It is written to a temporary
+// file because Undistort::getUndistorterForFile reads a path.  Returns a handle; out: sizes and the rectified K.
+void* ref_undistort_create(const char* config_text, int wh_org[2], int wh[2], double K4[4]) {
+  char path[] = "/tmp/sdv_ref_calib_XXXXXX"; int fd = mkstemp(path); if (fd < 0) return 0;
+  FILE* f = fdopen(fd, "w"); fputs(config_text, f); fclose(f);
+  fflush(stdout);
+  Undistort* u = Undistort::getUndistorterForFile(path, "", "");
+  remove(path); if (!u) return 0;
+  wh_org[0] = u->getOriginalSize()[0]; wh_org[1] = u->getOriginalSize()[1]; wh[0] = u->getSize()[0]; wh[1] = u->getSize()[1];
+  Mat33 K = u->getK(); K4[0] = K(0, 0); K4[1] = K(1, 1); K4[2] = K(0, 2); K4[3] = K(1, 2);
+  return u;
+}
+void ref_undistort_destroy(void* p) { delete (Undistort*)p; }
+void ref_undistort_maps(void* p, float* remapX, float* remapY) { Undistort* u = (Undistort*)p; size_t n = (size_t)u->w*u->h; memcpy(remapX, u->remapX, n*sizeof(float)); memcpy(remapY, u->remapY, n*sizeof(float)); }
+int  ref_undistort_passthrough(void* p) { return ((Undistort*)p)->passthrough ? 1 : 0; }
+// Undistort::undistort<unsigned char> (:341-435): mono8 wire image (sensor_msgs/Image, DatasetReader.h:152-155) -> float image the pipeline tracks
+void ref_undistort_apply_u8(void* p, const unsigned char* raw, float exposure, float* out) {
+  Undistort* u = (Undistort*)p; MinimalImageB img(u->wOrg, u->hOrg); memcpy(img.data, raw, (size_t)u->wOrg*u->hOrg);
+  ImageAndExposure* r = u->undistort<unsigned char>(&img, exposure, 0.0, 1.0f);
+  memcpy(out, r->image, sizeof(float)*(size_t)u->w*u->h); delete r;
 }
 
 }  // extern "C"
