@@ -6,15 +6,17 @@ independent sequences / Monte-Carlo re-runs sharded over GPUs, no cross-GPU depe
 1200x360 frame -> FrameHessian::makeImages (pyramid + gradients) -> CoarseTracker::trackNewestCoarse (coarse-to-fine
 photometric SE(3)+affine LM against the keyframe's LiDAR-depth reference cloud, device-resident) -> pose/residuals back.
 
-  value   : frames/s with the raw frames already resident in HBM (sdv_frame_build_batch_dev + sdv_tracker_track_batch)
-  e2e     : frames/s through the reference-facing C-ABI with HOST buffers: pinned mono8 images (the sensor_msgs/Image wire format the reference
-            ingests; the synthetic frames are mono8-exact) H2D every step and pose/residual D2H every step, inside the timed region;
-            e2e_float32 = the same with float images (FrameHessian::makeImages(float*) signature, 4x the PCIe bytes);
-            e2e_trackNewCoarse = mono8 upload + the whole FullSystem::trackNewCoarse (sdv_track_new_coarse_batch) per frame
+  value   : frames/s with the rectified frames already resident in HBM (sdv_frame_build_batch_dev + sdv_tracker_track_batch)
+  e2e     : frames/s through the reference-facing C-ABI with HOST buffers: pinned RAW 1241x376 mono8 images (the sensor_msgs/Image wire format the reference
+            ingests) H2D every step, rectified on the device with the reference's own Undistort tables for calib/KITTI/00.txt (crop -> 1200x360, fused into the
+            pyramid kernel: sdv_frame_upload_batch_raw_u8), pose/residual D2H every step, all inside the timed region;
+            e2e_float32 = host-rectified float images (FrameHessian::makeImages(float*) signature, 4x the PCIe bytes);
+            e2e_trackNewCoarse = raw mono8 upload + the whole FullSystem::trackNewCoarse (sdv_track_new_coarse_batch) per frame
   roofline: the device-resident LM kernel (track_cluster_kernel): algorithmic bytes = 64 B x point evaluations
   refine  : reprojectMap + structPoseEstimation (sdv_tracker_refine_batch) on resident data; ba: FullSystem::optimize on resident 7-keyframe windows
             (sdv_ba_optimize_batch); combined: the three legs folded into one frames/s figure (tracking + refinement every frame, BA every kf_every-th)
-  cpu_baseline / --impl reference: the CPU restatement (oracle/, "port": the reference cannot be built here) on host cores.
+  cpu_baseline / --impl reference: the reference's own compiled code (oracle/_ref: Undistort::undistort + makeImages + trackNewestCoarse per frame) on the host
+            cores; the oracle port only where oracle/_ref is missing.
 """
 from __future__ import annotations
 import argparse
@@ -31,7 +33,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
-WORKLOAD = "S-KITTI tracker step: %d resident sequences/GPU x 1 frame (1200x360 crop of 1241x376, 4 pyramid levels, %d LiDAR-depth splats -> ~10k reference points at level 0), batched mode"
+WORKLOAD = "S-KITTI tracker step: %d resident sequences/GPU x 1 frame (raw 1241x376 mono8 -> Undistort crop 1200x360 of calib/KITTI/00.txt, 4 pyramid levels, %d LiDAR-depth splats -> ~10k reference points at level 0), batched mode"
+KITTI00_CALIB = "Pinhole 718.856 718.856 607.1928 185.2157 0\n1241 376\ncrop\n1200 360\n"      # calib/KITTI/00.txt of the reference, verbatim (4-line data file)
+K_RAW, WH_RAW = (718.856, 718.856, 607.1928, 185.2157), (1241, 376)
 N_INIT_POOL = 24                 # distinct batches of initial guesses, cycled (drawing 500 x 592 guesses in Python would dominate the set-up)
 
 
@@ -45,10 +49,19 @@ N_FRAMES = 4                     # frame 0 = keyframe, frames 1..3 tracked again
 
 
 def load_sequence():
+    """The bench drive as the camera delivers it: raw 1241x376 mono8 frames rendered with the real KITTI pinhole, plus what the reference's ingest makes of them —
+    Undistort for calib/KITTI/00.txt (host mirror, bit-identical tables: tests/test_undistort.py): rectified K, 1200x360 float frames (undistort_host == the
+    reference's undistort<unsigned char>, bit for bit), and the LiDAR pixels of the keyframe in the rectified image."""
+    import types
     import sdv_loam_b200  # noqa: F401
-    from sdv_loam_b200 import synth
+    from sdv_loam_b200 import synth, undistort
     from conftest import cached_sequence
-    return cached_sequence(N_FRAMES, 1000, synth.KITTI_K, synth.KITTI_WH), synth
+    und = undistort.Undistort.from_text(KITTI00_CALIB)
+    rawseq = cached_sequence(N_FRAMES, 1000, K_RAW, WH_RAW)
+    raw = [np.ascontiguousarray(im.astype(np.uint8)) for im in rawseq.images]
+    seq = types.SimpleNamespace(K=und.K4, wh=(und.w, und.h), n=N_FRAMES, R=rawseq.R, t=rawseq.t, raw=raw, und=und, images=[und.undistort_host(r) for r in raw])
+    seq.clouds = [synth.lidar_pixels(synth.World(1000), seq.R[0], seq.t[0], seq.K, seq.wh)]            # only the keyframe's cloud is used
+    return seq, synth
 
 
 def se3_helpers():
@@ -143,7 +156,7 @@ def ref_available():
 
 
 class RefArm:
-    """The REFERENCE's own FrameHessian::makeImages + CoarseTracker::trackNewestCoarse (oracle/_ref/libsdvref.so = /root/reference/src compiled unmodified against stand-in
+    """The REFERENCE's own Undistort::undistort<unsigned char> + FrameHessian::makeImages + CoarseTracker::trackNewestCoarse on the raw mono8 frames (oracle/_ref/libsdvref.so = /root/reference/src compiled unmodified against stand-in
     headers, see oracle/Makefile), one independent sequence per host thread, the frame loop inside one C call per thread (ref_bench_track_loop)."""
     kind = "reference"
 
@@ -155,22 +168,23 @@ class RefArm:
             libc = ctypes.CDLL("libc.so.6"); libc.mallopt(-3, 1 << 30); libc.mallopt(-1, 1 << 30)   # mmaps/unmaps each one and the threads serialise in the kernel (M_MMAP_THRESHOLD, M_TRIM_THRESHOLD)
         except OSError:
             pass
-        w, h = synth.KITTI_WH; self.L = ref.set_calib(w, h, synth.KITTI_K); ref.settings()
+        w, h = seq.wh; self.L = ref.set_calib(w, h, seq.K); ref.settings()
         self.gts = [self.orc.se3_from_rt(*synth.rel_pose(seq.R[0], seq.t[0], seq.R[k], seq.t[k])) for k in range(N_FRAMES)]
-        self.imgs = [np.ascontiguousarray(im, np.float32) for im in seq.images]
-        self.trackers = []
+        self.trackers = []; self.unds = []
         for i in range(threads):
-            f0 = ref.Frame(self.imgs[0], (w, h), self.L); tr = ref.CoarseTracker(); tr.setCoarseTrackingRef(f0, p4, np.zeros(len(p4), np.int32)); self.trackers.append((f0, tr))
+            u = ref.Undistort(KITTI00_CALIB); self.unds.append(u)                                     # private: undistort<> writes into the undistorter's own buffer
+            f0 = ref.Frame(u.undistort(seq.raw[0]), (w, h), self.L); tr = ref.CoarseTracker(); tr.setCoarseTrackingRef(f0, p4, np.zeros(len(p4), np.int32)); self.trackers.append((f0, tr))
+        assert tuple(float(np.float32(x)) for x in self.unds[0].K4d) == tuple(seq.K)
         self.rngs = [np.random.default_rng(100 + i) for i in range(threads)]; self.count = [0] * threads
-        L = ref.lib(); L.ref_bench_track_loop.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                           np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
-        self.ptrs = (ctypes.c_void_p * (N_FRAMES - 1))(*[self.imgs[k].ctypes.data for k in range(1, N_FRAMES)])
+        L = ref.lib(); L.ref_bench_ingest_track_loop.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                                  np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+        self.ptrs = (ctypes.c_void_p * (N_FRAMES - 1))(*[seq.raw[k].ctypes.data for k in range(1, N_FRAMES)])
 
     def run(self, frames_per_thread, budget_s=None):
         return _arm_run(self, frames_per_thread, budget_s)
 
     def _work(self, i, n_frames, budget_s, inits):
-        done = self.ref.lib().ref_bench_track_loop(self.trackers[i][1].p, self.ptrs, N_FRAMES - 1, self.count[i] % (N_FRAMES - 1), len(inits), inits, float(budget_s or 0.0), None, None)
+        done = self.ref.lib().ref_bench_ingest_track_loop(self.trackers[i][1].p, self.unds[i].p, self.ptrs, N_FRAMES - 1, self.count[i] % (N_FRAMES - 1), len(inits), inits, float(budget_s or 0.0), None, None)
         self.count[i] += done
         return done
 
@@ -187,13 +201,13 @@ class CpuArm:
         except OSError:
             pass
         self.seq, self.synth, self.threads = seq, synth, threads
-        w, h = synth.KITTI_WH; self.L = 4
+        w, h = seq.wh; self.L = 4
         self.gts = [orc.se3_from_rt(*synth.rel_pose(seq.R[0], seq.t[0], seq.R[k], seq.t[k])) for k in range(N_FRAMES)]
         self.imgs = [np.ascontiguousarray(im, np.float32) for im in seq.images]
         self.trackers = []
         for i in range(threads):
             f0 = orc.Frame(self.imgs[0], self.L)
-            tr = orc.CoarseTracker(w, h, self.L, synth.KITTI_K); tr.setCoarseTrackingRef(f0, p4, np.zeros(len(p4), np.int32))
+            tr = orc.CoarseTracker(w, h, self.L, seq.K); tr.setCoarseTrackingRef(f0, p4, np.zeros(len(p4), np.int32))
             self.trackers.append((f0, tr))
         self.rngs = [np.random.default_rng(100 + i) for i in range(threads)]
         self.count = [0] * threads
@@ -212,7 +226,7 @@ class CpuArm:
         L = self.orc.lib(); tr = self.trackers[i][1]
         L.orc_bench_track_loop.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
-        w, h = self.synth.KITTI_WH
+        w, h = self.seq.wh
         ptrs = (ctypes.c_void_p * (N_FRAMES - 1))(*[self.imgs[k].ctypes.data for k in range(1, N_FRAMES)])
         done = L.orc_bench_track_loop(tr.p, w, h, self.L, ptrs, N_FRAMES - 1, self.count[i] % (N_FRAMES - 1), len(inits), inits, float(budget_s or 0.0), None, None)
         self.count[i] += done
@@ -364,29 +378,29 @@ def make_cpu_arm(seq, synth, p4, threads):
 
 def cpu_note(arm):
     if arm.kind == "reference":
-        return "the reference's own sources (/root/reference/src, unmodified) compiled against stand-in Eigen/Sophus headers (oracle/_ref, g++ -O3, SSE2, no FMA)"
-    return "oracle/ CPU restatement (g++ -O3, no FMA): oracle/_ref is not available on this box"
+        return "the reference's own sources (/root/reference/src, unmodified) compiled against stand-in Eigen/Sophus headers (oracle/_ref, g++ -O3, SSE2, no FMA); per frame: Undistort::undistort + makeImages + trackNewestCoarse"
+    return "oracle/ CPU restatement (g++ -O3, no FMA) on host-rectified frames (no undistort stage): oracle/_ref is not available on this box"
 
 
 def single_sequence_leg(api, synth, seq, p4, rh, local_rank, frames=240, warm=12):
     """BASELINE.json configs[1]/[2] as written: ONE sequence on one GPU.  A sequence is a chain (frame n+1 needs frame n's pose; an LM iteration needs the previous one), so
-    this is a latency figure: makeImages + trackNewestCoarse per frame with the low-latency launch (256 threads, thread-block cluster of 16 CTAs, DSMEM all-gather of the
-    partial sums).  device = CUDA-event time of the kernels; e2e = wall clock per frame with the mono8 image uploaded from pinned host memory and the pose read back."""
+    this is a latency figure: undistort + makeImages + trackNewestCoarse per frame with the low-latency launch (256 threads, thread-block cluster of 16 CTAs, DSMEM all-gather of the
+    partial sums).  device = CUDA-event time of the kernels; e2e = wall clock per frame with the raw mono8 image uploaded from pinned host memory and the pose read back."""
     import torch
-    w, h = synth.KITTI_WH
-    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=1, max_frames=8, cluster_size=16, track_threads=256)
-    KF = 1 << 40; ctx.makeImages(KF, seq.images[0]); tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(KF, p4, rh)
+    w, h = seq.wh; wo, ho = WH_RAW
+    ctx = api.Context(seq.K, w, h, device=local_rank, n_tracker_slots=1, max_frames=8, cluster_size=16, track_threads=256); ctx.setUndistort(seq.und)
+    KF = 1 << 40; ctx.makeImagesRaw(KF, seq.raw[0]); tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(KF, p4, rh)
     gts, inits = gt_and_inits(seq, synth, 1, N_INIT_POOL, seed=99)
-    host_u8 = torch.empty((N_FRAMES - 1, h, w), dtype=torch.uint8).pin_memory()
+    host_u8 = torch.empty((N_FRAMES - 1, ho, wo), dtype=torch.uint8).pin_memory()
     for k in range(N_FRAMES - 1):
-        host_u8[k].copy_(torch.from_numpy(seq.images[1 + k].astype(np.uint8)))
+        host_u8[k].copy_(torch.from_numpy(seq.raw[1 + k]))
     ptrs = [np.array([host_u8[k].data_ptr()], np.uint64) for k in range(N_FRAMES - 1)]
     slots = np.zeros(1, np.int32); dev_ms = []; t0 = None
     for f in range(warm + frames):
         if f == warm:
             ctx.sync(); t0 = time.perf_counter()
         ids = np.array([f & 1], np.uint64)
-        ctx.makeImagesBatch(ids, ptrs[f % (N_FRAMES - 1)], u8=True)
+        ctx.makeImagesBatch(ids, ptrs[f % (N_FRAMES - 1)], raw=True)
         T = inits[(3 * (f // 3) + f % (N_FRAMES - 1)) % len(inits)].copy(); ab = np.zeros((1, 2))
         r = ctx.trackBatch(slots, ids, T, ab)
         if f >= warm:
@@ -455,7 +469,7 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
-METRIC = "frames/sec (KITTI 1241x376 + 64-beam): makeImages + trackNewestCoarse per frame"
+METRIC = "frames/sec (KITTI 1241x376 + 64-beam): undistort + makeImages + trackNewestCoarse per frame"
 
 
 def main():
@@ -489,12 +503,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     seq, synth = load_sequence()
     from sdv_loam_b200 import api
-    w, h = synth.KITTI_WH; B = args.seqs; K = args.steps
+    w, h = seq.wh; wo, ho = WH_RAW; B = args.seqs; K = args.steps
     pts = synth.select_points(seq.images[0], seq.clouds[0], args.points)
     p4 = np.concatenate([pts, np.full((len(pts), 1), 1e-3, np.float32)], 1).astype(np.float32); rh = np.zeros(len(p4), np.int32)
 
     WBA = max(0, args.ba_windows)
-    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=B, track_threads=args.track_threads, max_frames=3 * B + 16 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
+    ctx = api.Context(seq.K, w, h, device=local_rank, n_tracker_slots=B, track_threads=args.track_threads, max_frames=3 * B + 16, max_kf_images=12)
+    ctx.setUndistort(seq.und)
     KF = 1 << 40
     for b in range(B):                                                   # per sequence: keyframe -> reference cloud (makeCoarseDepthL0 on device)
         ctx.makeImages(KF, seq.images[0]); api.CoarseTracker(ctx, b).setCoarseTrackingRef(KF, p4, rh); ctx.releaseFrame(KF)
@@ -560,19 +575,19 @@ def main():
         tu = time.perf_counter(); upload(s1 + NB); ctx.sync(); t += time.perf_counter() - tu
         return t, s1 + NB + 1
 
-    host_in = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.float32).pin_memory()
+    host_in = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.float32, pin_memory=True)
     for k in range(N_FRAMES - 1):
         host_in[k].copy_(torch.from_numpy(frames_np[k]).expand(B, h, w))
     host_ptrs = [np.uint64(host_in[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(stride) for k in range(N_FRAMES - 1)]
     t_e2e, nxt = e2e_leg(lambda step: ctx.makeImagesBatch(frame_ids(step), host_ptrs[step % (N_FRAMES - 1)]), (W + K) * R)
     del host_in
-    host_u8 = torch.empty((N_FRAMES - 1, B, h, w), dtype=torch.uint8).pin_memory()
+    host_u8 = torch.empty((N_FRAMES - 1, B, ho, wo), dtype=torch.uint8, pin_memory=True)     # the RAW camera frames, one private copy per sequence
     for k in range(N_FRAMES - 1):
-        host_u8[k].copy_(torch.from_numpy(frames_np[k].astype(np.uint8)).expand(B, h, w))
-    u8_ptrs = [np.uint64(host_u8[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(h * w) for k in range(N_FRAMES - 1)]
+        host_u8[k].copy_(torch.from_numpy(seq.raw[1 + k]).expand(B, ho, wo))
+    u8_ptrs = [np.uint64(host_u8[k].data_ptr()) + np.arange(B, dtype=np.uint64) * np.uint64(ho * wo) for k in range(N_FRAMES - 1)]
 
     def upload_u8(step):
-        ctx.makeImagesBatch(frame_ids(step), u8_ptrs[step % (N_FRAMES - 1)], u8=True)
+        ctx.makeImagesBatch(frame_ids(step), u8_ptrs[step % (N_FRAMES - 1)], raw=True)
     t_e2e_u8, s3 = e2e_leg(upload_u8, nxt)
     # ---------------------------------------------------------------- leg 2c: the WHOLE FullSystem::trackNewCoarse per frame through host buffers: mono8 upload ->
     # motion hypotheses + trackNewestCoarse re-track loop -> reprojectMap -> structPoseEstimation (sdv_track_new_coarse_batch), pose D2H
@@ -614,8 +629,12 @@ def main():
     clocks = sampler.stop()
     del host_u8
 
+    ctx.close()
+    # back-end and refinement legs: their own context (the 8-frame window sequence of tests/, rendered for synth.KITTI_K)
+    Bref = min(B, 592)
+    ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=Bref, track_threads=args.track_threads, max_frames=Bref + 32 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
     ba = ba_leg(ctx, api, synth, local_rank, WBA) if WBA > 0 else None
-    refine = refine_leg(ctx, api, synth, min(B, 592), cpu=not args.no_cpu_baseline) if not args.no_refine else None
+    refine = refine_leg(ctx, api, synth, Bref, cpu=not args.no_cpu_baseline) if not args.no_refine else None
     tv = torch.tensor([t_value, t_e2e, kern_ms, t_e2e_u8, t_e2e_full or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
@@ -646,14 +665,15 @@ def main():
     line = {
         "metric": METRIC, "value": world * B * NB / t_value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
-        "e2e": {"value": world * B * NB / t_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": R * (B * h * w + B * job_bytes), "d2h_bytes_per_step": R * B * job_bytes,
-                "api": "sdv_frame_upload_batch_u8 (pinned host mono8 = the sensor_msgs/Image wire format the reference ingests; u8->float fused into the pyramid kernel) + sdv_tracker_track_batch; "
-                       "upload of batch k+1 overlapped with tracking of batch k; synthetic frames are mono8-exact, results identical to the float path"},
+        "e2e": {"value": world * B * NB / t_e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": R * (B * ho * wo + B * job_bytes), "d2h_bytes_per_step": R * B * job_bytes,
+                "api": "sdv_frame_upload_batch_raw_u8 (pinned host RAW 1241x376 mono8 = the sensor_msgs/Image wire format the reference ingests; Undistort::undistort crop-remap + u8->float "
+                       "fused into the level-0/1 pyramid kernel, tables of calib/KITTI/00.txt via sdv_set_undistort) + sdv_tracker_track_batch; upload of batch k+1 overlapped with tracking of "
+                       "batch k; the rectified images are bit-identical to the reference's undistort<unsigned char> output (tests/test_undistort.py), i.e. to what the other legs track"},
         "e2e_float32": {"value": world * B * NB / t_e2e, "unit": "frames/s", "h2d_bytes_per_step": R * (B * h * w * 4 + B * job_bytes), "d2h_bytes_per_step": R * B * job_bytes,
-                        "api": "sdv_frame_upload_batch(float*, pinned) = FrameHessian::makeImages(float*) signature + sdv_tracker_track_batch; PCIe-bound (4x the bytes of the wire format)"},
-        "e2e_trackNewCoarse": (None if not full_stats else dict({"value": world * B * full_stats["batches"] / t_e2e_full_max, "unit": "frames/s", "h2d_bytes_per_batch": B * h * w + B * (job_bytes + 416),
+                        "api": "sdv_frame_upload_batch(float*, pinned, host-rectified frames) = FrameHessian::makeImages(float*) signature + sdv_tracker_track_batch; PCIe-bound (4x the bytes of the wire format)"},
+        "e2e_trackNewCoarse": (None if not full_stats else dict({"value": world * B * full_stats["batches"] / t_e2e_full_max, "unit": "frames/s", "h2d_bytes_per_batch": B * ho * wo + B * (job_bytes + 416),
                                "d2h_bytes_per_batch": B * (job_bytes + 416),
-                               "api": "sdv_frame_upload_batch_u8 + sdv_track_new_coarse_batch (the whole FullSystem::trackNewCoarse: hypotheses, trackNewestCoarse re-track loop, reprojectMap, "
+                               "api": "sdv_frame_upload_batch_raw_u8 + sdv_track_new_coarse_batch (the whole FullSystem::trackNewCoarse: hypotheses, trackNewestCoarse re-track loop, reprojectMap, "
                                       "structPoseEstimation) on host buffers; single-keyframe map of the bench sequence"}, **full_stats)),
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -689,7 +709,7 @@ def main():
             if refine is not None:
                 line["combined"]["cpu_frames_per_s_track_refine_ba_1core"] = 1.0 / (tw / nf + refine["cpu_ms_per_frame_1core"] * 1e-3 + cms * 1e-3 / args.kf_every)
         line["cpu_baseline"] = {"value": nf / tw, "unit": "frames/s", "cores": 1, "kind": arm.kind,
-                                "sample": "%d frames (makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; %s" % (nf, tw, cpu_note(arm))}
+                                "sample": "%d frames (undistort + makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; %s" % (nf, tw, cpu_note(arm))}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -59,6 +59,11 @@ const char* sdv_last_error(sdv_ctx* c);
 int  sdv_pyr_levels(int w, int h);                           /* pyrLevelsUsed rule, util/globalCalib.cpp:22-30 */
 int  sdv_sync(sdv_ctx* c);                                   /* drain the context's stream */
 
+/* CoarseTracker::makeK(CalibHessian*) (CoarseTracker.cpp:77-106) and the CalibHessian Reprojector::reprojectMap reads (Reprojector.cpp:117-124): the bundle
+ * adjustment optimises the intrinsics at every keyframe, and setCoarseTrackingRef re-derives the tracker's per-level K from them.  Replaces the calibration given
+ * to sdv_create for every later tracker / reprojection / structPoseEstimation call of this context (the BA windows carry their own: sdv_ba_set_window). */
+int  sdv_set_calib(sdv_ctx* c, const sdv_calib* K);
+
 /* ---- frames: FrameHessian::makeImages(float* color, CalibHessian*)  FullSystem/HessianBlocks.cpp:107-167 ------------
  * builds the pyramid on the device, keyed by a caller-chosen handle: level 0 is kept as the planar intensity image (its {dx,dy} are
  * formed on the fly, bit-identically, by the tracker; packed level-0 texels are built lazily when the frame enters a BA window),
@@ -71,6 +76,15 @@ int  sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const flo
  * u8->float conversion of the ingest (DatasetReader.h:152-155, Undistort crop without photometric calibration) is fused
  * into the level-0 kernel; 4x less PCIe traffic.   _dev: level-0 images already in device memory (kernel-only timing). */
 int  sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs_wh, const float* exposures);
+/* RAW ingest — Undistort::undistort<unsigned char> (util/Undistort.cpp:341-435) + PhotometricUndistorter::processFrame (:177-214), what
+ * src/main.cpp:537-560 runs on every sensor_msgs/Image before FullSystem::addActiveFrame.  sdv_set_undistort hands over, once per calibration,
+ * the tables the reference's Undistort object holds after readFromFile (:842-886): remapX/remapY (w*h floats of the RECTIFIED size given to
+ * sdv_create, source coordinates in the raw w_org x h_org image, -1 = outside), the scalar `factor` of the uncalibrated path, and optionally the
+ * inverse response G[256] and the inverse vignette (w_org*h_org) of the photometric calibration (both NULL for KITTI: no pcalib).  A response is
+ * applied to frames uploaded with exposure > 0 only (:185).  _raw_u8 then takes native-size mono8 images; rectification, photometric stage and the
+ * level-0/level-1 pyramid build are ONE kernel.  Entries that would read outside the raw image are refused (SDV_ERR_ARG). */
+int  sdv_set_undistort(sdv_ctx* c, int w_org, int h_org, const float* remapX, const float* remapY, float factor, const float* G256, const float* vignette_inv);
+int  sdv_frame_upload_batch_raw_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* raw_imgs_worg_horg, const float* exposures);
 int  sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int fmt, const float* exposures);
 /* fmt: 0 float (copied into frame storage), 1 mono8, 2 float ADOPTED as the frame's level-0 plane (zero copy: the buffer must stay
  * valid and unmodified until sdv_frame_release / the handle is re-uploaded — for producers that already write into device memory). */

@@ -1,6 +1,6 @@
 """ctypes binding of the CPU oracle (oracle/liborc.so).  TEST INFRASTRUCTURE ONLY: imported by tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs — never by the product package.
-PARITY UNPINNED: the reference has no golden vectors for this path and cannot be built here."""
+Parity: pinned on the reference's own compiled code (oracle/_ref, oracle/ref.py; see orc_math.hpp and DESIGN.md §0)."""
 from __future__ import annotations
 import ctypes as C
 import os

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.  See orc_ba.hpp for the file:line map.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned on oracle/_ref (tests/test_ref_pin_ba.py).  See orc_ba.hpp for the file:line map.
 #include "orc_ba.hpp"
 #include <cstdio>
 #include <cassert>

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  PARITY UNPINNED (no reference goldens).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Pinned on oracle/_ref: tests/test_ref_pin_ba.py.
 //
 // CPU restatement of the SDV-LOAM sliding-window back-end on a FLATTENED window (the reference's pointer graph
 // FrameHessian -> PointHessian -> PointFrameResidual is host bookkeeping; every array here is in the reference's

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Parity status: orc_math.hpp.
 // Flat C entry points over the oracle classes so tests/ and bench.py (cpu_baseline / --impl reference) can
 // drive them through ctypes.  Pose layout everywhere: double T[7] = {qw,qx,qy,qz, tx,ty,tz}.
 #include "orc_tracker.hpp"

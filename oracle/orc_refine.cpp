@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned on oracle/_ref at sequence level (tests/test_sequence_parity.py).
 // CPU restatement of the semi-direct pose refinement that follows the photometric tracker, file:line relative
 // to /root/reference/src:
 //   CoarseTracker::calculateRes          FullSystem/CoarseTracker.cpp:840-871

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned on oracle/_ref: tests/test_sequence_parity.py, tests/test_ref_pin.py.
 // CPU restatement of the map reprojection / direct feature alignment stage that feeds structPoseEstimation,
 // file:line relative to /root/reference/src/FullSystem/Reprojector.cpp:
 //   getWarpMatrixAffine :14-37   getBestSearchLevel :39-51   warpAffine :53-86   initializeGrid :100-112 (cell_size 25)

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.  See orc_tracker.hpp for the file:line map.
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Pinned bit for bit on oracle/_ref (tests/test_ref_pin.py).  See orc_tracker.hpp for the file:line map.
 #include "orc_tracker.hpp"
 #include <cstdio>
 #include <cassert>

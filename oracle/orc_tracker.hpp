@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  PARITY UNPINNED (no reference goldens).
+// ORACLE — TEST INFRASTRUCTURE ONLY (see orc_math.hpp header).  Pinned bit for bit on oracle/_ref: tests/test_ref_pin.py.
 //
 // CPU restatement of the SDV-LOAM front-end tracker path (all file:line relative to /root/reference/src):
 //   FrameHessian::makeImages            FullSystem/HessianBlocks.cpp:107-167

@@ -109,6 +109,11 @@ def lib():
         L.ref_sys_map.argtypes = [_vp, _i32p, _f64p, _f64p, _f32p, _f32p]
         L.ref_sys_get_track_result.argtypes = [_vp, C.c_int, _f64p]
         L.ref_reproject_map.argtypes = [C.c_int, C.POINTER(_vp), _f64p, _f64p, _vp, _f64p, _f64p, C.c_int, _f32p, C.c_uint, C.c_int, _i32p, _f64p]
+        L.ref_undistort_create.argtypes = [C.c_char_p, _i32p, _i32p, _f64p]; L.ref_undistort_create.restype = _vp
+        L.ref_undistort_destroy.argtypes = [_vp]; L.ref_undistort_destroy.restype = None
+        L.ref_undistort_maps.argtypes = [_vp, _f32p, _f32p]; L.ref_undistort_maps.restype = None
+        L.ref_undistort_passthrough.argtypes = [_vp]
+        L.ref_undistort_apply_u8.argtypes = [_vp, _vp, C.c_float, _f32p]; L.ref_undistort_apply_u8.restype = None
         _LIB = L
     return _LIB
 
@@ -364,10 +369,13 @@ class System:
                     n_history=nh.value, kf_ids=ids[:k], kf_T7=kT[:k], kf_ab=kab[:k], kf_exposure=kex[:k], map_pts=p5[:npts])
 
     def __del__(self):
-        if getattr(self, "p", None) and _LIB is not None:
-            with _Quiet():
-                _LIB.ref_sys_destroy(self.p)
-            self.p = None
+        try:
+            if getattr(self, "p", None) and _LIB is not None:
+                with _Quiet():
+                    _LIB.ref_sys_destroy(self.p)
+                self.p = None
+        except Exception:                                                     # interpreter shutdown: the mapping thread dies with the process
+            pass
 
 
 def libc_rand_shuffle(n: int):
@@ -393,3 +401,32 @@ def reproject_map(wh, kf_frames, kf_T7, kf_ab, cur_frame, cur_T7, cur_ab, pts, s
         n = L.ref_reproject_map(nH, fr, np.ascontiguousarray(kf_T7, np.float64), np.ascontiguousarray(kf_ab, np.float64), cur_frame.p, T, np.ascontiguousarray(cur_ab, np.float64),
                                 len(p5), p5, seed, 1 if refine else 0, out_pt, out_px)
     return out_pt[:n].copy(), out_px[:n].copy(), order, (T if refine else None)
+
+
+class Undistort:
+    """The reference's Undistort object for a calibration text (Undistort::getUndistorterForFile, util/Undistort.cpp:232-334): K, remap tables, undistort<unsigned char>."""
+
+    def __init__(self, config_text: str):
+        L = lib(); who = np.zeros(2, np.int32); wh = np.zeros(2, np.int32); K4 = np.zeros(4)
+        with _Quiet():
+            self.p = L.ref_undistort_create(config_text.encode(), who, wh, K4)
+        if not self.p:
+            raise RuntimeError("the reference rejected the calibration text")
+        self.wOrg, self.hOrg = int(who[0]), int(who[1]); self.w, self.h = int(wh[0]), int(wh[1]); self.K4d = K4
+        self.remapX = np.zeros((self.h, self.w), np.float32); self.remapY = np.zeros((self.h, self.w), np.float32)
+        L.ref_undistort_maps(self.p, self.remapX.reshape(-1), self.remapY.reshape(-1))
+        self.passthrough = bool(L.ref_undistort_passthrough(self.p))
+
+    def undistort(self, raw_u8, exposure: float = 1.0):
+        raw = np.ascontiguousarray(raw_u8, np.uint8); assert raw.shape == (self.hOrg, self.wOrg)
+        out = np.zeros((self.h, self.w), np.float32)
+        with _Quiet():
+            lib().ref_undistort_apply_u8(self.p, raw.ctypes.data, exposure, out.reshape(-1))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "p", None):
+                lib().ref_undistort_destroy(self.p); self.p = None
+        except Exception:
+            pass

@@ -466,4 +466,25 @@ void ref_undistort_apply_u8(void* p, const unsigned char* raw, float exposure, f
   memcpy(out, r->image, sizeof(float)*(size_t)u->w*u->h); delete r;
 }
 
+// bench arm with the ingest in front: per frame Undistort::undistort<unsigned char> (photometric stage + crop-remap, what src/main.cpp:537-560 runs on every image message)
+// -> FrameHessian::makeImages -> trackNewestCoarse.  `u` must be private to the calling thread (undistort<> writes into the undistorter's own output buffer).
+int ref_bench_ingest_track_loop(void* t, void* u, const unsigned char* const* raws, int n_imgs, int start, int n_frames, const double* inits7, double budget_s, double* last_T7, int* good_count) {
+  CoarseTracker* T = (CoarseTracker*)t; Undistort* U = (Undistort*)u; timespec t0; clock_gettime(CLOCK_MONOTONIC, &t0);
+  Vec5 mr; for (int i = 0; i < 5; i++) mr[i] = NAN;
+  int done = 0, good = 0; FrameShell shell;
+  for (int f = 0; f < n_frames; f++) {
+    MinimalImageB raw(U->wOrg, U->hOrg); memcpy(raw.data, raws[(start + f) % n_imgs], (size_t)U->wOrg*U->hOrg);     // the decoded sensor_msgs/Image (DatasetReader.h:152-155)
+    ImageAndExposure* img = U->undistort<unsigned char>(&raw, 1.0f, 0.0, 1.0f);
+    FrameHessian* fh = new FrameHessian(); fh->shell = &shell; fh->ab_exposure = img->exposure_time;
+    fh->makeImages(img->image, g_calib);
+    SE3 s = se3_from(inits7 + 7*(size_t)f); AffLight aff(0, 0);
+    if (T->trackNewestCoarse(fh, s, aff, pyrLevelsUsed-1, mr, 0)) good++;
+    if (last_T7) se3_to(s, last_T7);
+    fh->efFrame = 0; delete fh; delete img; done++;
+    if (budget_s > 0) { timespec t1; clock_gettime(CLOCK_MONOTONIC, &t1); if ((t1.tv_sec - t0.tv_sec) + 1e-9*(t1.tv_nsec - t0.tv_nsec) > budget_s) break; }
+  }
+  if (good_count) *good_count = good;
+  return done;
+}
+
 }  // extern "C"

@@ -48,6 +48,18 @@ static void make_geom(sdv_ctx* c, const sdv_calib* K) {   // CoarseTracker::make
   }
 }
 
+// CoarseTracker::makeK(HCalib) / the CalibHessian the Reprojector reads (FullSystem::optimize moves the intrinsics at every keyframe): new K for every later call.
+// Stream-ordered after the work already enqueued on the compute stream.
+int sdv_set_calib(sdv_ctx* c, const sdv_calib* K) {
+  if (!c || !K) return SDV_ERR_ARG;
+  if (!(K->fx > 0 && K->fy > 0)) return ctx_fail(c, SDV_ERR_ARG, "sdv_set_calib: focal lengths must be positive");
+  CK(cudaSetDevice(c->device));
+  make_geom(c, K);
+  CK(cudaMemcpyAsync(c->tc_dev, &c->tc, sizeof(TrackConst), cudaMemcpyHostToDevice, c->st));   // pageable source: staged before the call returns
+  rp_calib_changed(c);
+  return SDV_OK;
+}
+
 static int create_impl(sdv_ctx* c, const sdv_calib* K, int w, int h, int levels, const sdv_settings* s_in, int device);
 int sdv_create(const sdv_calib* K, int w, int h, int levels, const sdv_settings* s_in, int device, sdv_ctx** out) {
   if (out) *out = nullptr;
@@ -136,6 +148,7 @@ void sdv_destroy(sdv_ctx* c) {
   for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]); } cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
   for (int i=0;i<2;i++) { for (auto p : c->stage[i]) cudaFree(p); cudaFree(c->stage_u8[i]); }
+  cudaFree(c->und_buf);
   for (int i=0;i<sdv_ctx::kIngRing;i++) if (c->ev_ing[i]) cudaEventDestroy(c->ev_ing[i]); for (int i=0;i<2;i++) if (c->ev_cp[i]) cudaEventDestroy(c->ev_cp[i]); if (c->st_cp) cudaStreamDestroy(c->st_cp);
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);
@@ -167,7 +180,8 @@ static int ensure_stage(sdv_ctx* c, int n, int par) {
 
 static void frame_drop_lvl0(sdv_ctx* c, FrameDev& f) { if (f.lvl0_slot >= 0) { c->lvl0_free.push_back(f.lvl0_slot); f.lvl0_slot = -1; } f.lvl[0] = nullptr; }
 
-// kind bit0: mono8 input, bit1: input already in device memory, bit2: adopt the (device, float) buffer as the frame's level-0 plane.
+// kind bit0: mono8 input, bit1: input already in device memory, bit2: adopt the (device, float) buffer as the frame's level-0 plane,
+// bit3: RAW mono8 input of the camera's native size, rectified through the tables of sdv_set_undistort inside the level-0 kernel.
 // Everything is enqueued on the ingest stream; the compute stream picks it up through ev_in at the next tracker / BA call, so an
 // upload overlaps the tracking of the previous batch.  Level 0 stays a planar intensity image: a pinned-host float upload lands
 // directly in frame storage and only levels >= 1 are built (gradients of level 0 are formed on the fly by the consumers).
@@ -180,11 +194,12 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
   // descriptors (the device-side order copy(seq) after pyramid(seq-2) is enforced on the copy stream below)
   if (seq > 2) CK(cudaEventSynchronize(c->ev_ing[(seq-2) % sdv_ctx::kIngRing]));
   int rc = ensure_stage(c, n, par); if (rc) return rc;
-  const bool u8 = (kind & 1), dev = (kind & 2), adopt = (kind & 4) && dev && !u8;
-  if (u8 && !dev && (size_t)n*c->w*c->h > c->stage_u8_cap[par]) { CK(cudaStreamSynchronize(c->st_in)); cudaFree(c->stage_u8[par]); c->stage_u8[par] = nullptr;
-    c->stage_u8_cap[par] = (size_t)n*c->w*c->h; CK(cudaMalloc(&c->stage_u8[par], c->stage_u8_cap[par])); }
+  const bool raw = (kind & 8), u8 = (kind & 1) || raw, dev = (kind & 2), adopt = (kind & 4) && dev && !u8;
+  if (raw && !c->has_und) return ctx_fail(c, SDV_ERR_STATE, "raw upload before sdv_set_undistort");
+  const size_t px = (size_t)c->w*c->h, px_in = raw ? (size_t)c->und.wOrg*c->und.hOrg : px;     // bytes of one mono8 input image
+  if (u8 && !dev && (size_t)n*px_in > c->stage_u8_cap[par]) { CK(cudaStreamSynchronize(c->st_in)); cudaFree(c->stage_u8[par]); c->stage_u8[par] = nullptr;
+    c->stage_u8_cap[par] = (size_t)n*px_in; CK(cudaMalloc(&c->stage_u8[par], c->stage_u8_cap[par])); }
   c->cp_dst.clear(); c->cp_src.clear(); c->cp_sz.clear();
-  const size_t px = (size_t)c->w*c->h;
   if (c->levels > 1 && ((c->w | c->h) & 1)) return ctx_fail(c, SDV_ERR_ARG, "pyramid needs even image sizes");
   PyrBatchHost* desc = c->pyr_batch_host[par];
   for (int k=0;k<n;k++) {
@@ -198,11 +213,11 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
     frame_drop_lvl0(c, f); f.ingest_seq = seq;
     f.adopted = adopt; f.I0 = adopt ? const_cast<float*>(reinterpret_cast<const float*>(imgs[k])) : f.I0_own;
     PyrBatchHost& b = desc[k];
-    b.scratch = c->stage[par][k] + px; b.out = f.base; b.I0 = f.I0;
+    b.scratch = c->stage[par][k] + px; b.out = f.base; b.I0 = f.I0; b.flags = (f.exposure > 0.f) ? 1 : 0; b.pad = 0;
     if (dev) b.src = imgs[k];
-    else if (u8) { unsigned char* d8 = c->stage_u8[par] + (size_t)k*px; b.src = d8;
-      if (!c->cp_dst.empty() && (unsigned char*)c->cp_src.back() + c->cp_sz.back() == (const unsigned char*)imgs[k] && (unsigned char*)c->cp_dst.back() + c->cp_sz.back() == d8) c->cp_sz.back() += px;   // adjacent in host memory: one copy
-      else { c->cp_dst.push_back(d8); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px); } }
+    else if (u8) { unsigned char* d8 = c->stage_u8[par] + (size_t)k*px_in; b.src = d8;
+      if (!c->cp_dst.empty() && (unsigned char*)c->cp_src.back() + c->cp_sz.back() == (const unsigned char*)imgs[k] && (unsigned char*)c->cp_dst.back() + c->cp_sz.back() == d8) c->cp_sz.back() += px_in;   // adjacent in host memory: one copy
+      else { c->cp_dst.push_back(d8); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px_in); } }
     else { b.src = f.I0; c->cp_dst.push_back(f.I0); c->cp_src.push_back(const_cast<void*>(imgs[k])); c->cp_sz.push_back(px*sizeof(float)); }
   }
   if (!c->cp_dst.empty()) {                                               // all H2D copies of the batch in ONE runtime call, on the copy stream: PCIe stays busy while the
@@ -220,8 +235,9 @@ static int frame_ingest(sdv_ctx* c, int n, const uint64_t* frames, const void* c
   }
   launch_h2d_words(c->pyr_batch_dev[par], desc, (size_t)n*sizeof(PyrBatchHost), c->st_in);   // kernel copy: a cudaMemcpyAsync here becomes ready only after this batch's bulk copy and
   c->launches += 1;                                                                              // would queue behind the NEXT batch's bulk copy on the H2D engine
-  if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev[par], n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in); c->launches += 2*(c->levels - 1); }
-  else if (u8 || (dev && !adopt)) { launch_pyramid_copy0(c->pyr_batch_dev[par], n, u8, c->w, c->h, c->st_in); c->launches += 1; }
+  const UndistortDev* und = raw ? &c->und : nullptr;
+  if (c->levels > 1) { launch_pyramid_batch(c->pyr_batch_dev[par], n, u8, c->lvl_off, c->w, c->h, c->levels, c->st_in, und); c->launches += 2*(c->levels - 1); }
+  else if (u8 || (dev && !adopt)) { launch_pyramid_copy0(c->pyr_batch_dev[par], n, u8, c->w, c->h, c->st_in, und); c->launches += 1; }
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev_ing[seq % sdv_ctx::kIngRing], c->st_in)); c->ingest_seq = seq; c->ingest_pending = true;
   return SDV_OK;
@@ -253,6 +269,33 @@ int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const floa
 }
 int sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs, const float* exposures) {
   return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 1);
+}
+// Undistort (util/Undistort.cpp) as data: the tables the reference builds once per calibration file, kept on the device for the raw-image ingest
+int sdv_set_undistort(sdv_ctx* c, int w_org, int h_org, const float* remapX, const float* remapY, float factor, const float* G256, const float* vignette_inv) {
+  if (!c || w_org < 2 || h_org < 2 || !remapX || !remapY) return SDV_ERR_ARG;
+  if (vignette_inv && !G256) return ctx_fail(c, SDV_ERR_ARG, "a vignette map needs a response function (PhotometricUndistorter::processFrame applies it to G[v] only)");
+  CK(cudaSetDevice(c->device));
+  const size_t px = (size_t)c->w*c->h, po = (size_t)w_org*h_org;
+  for (size_t i=0;i<px;i++) {                                              // Undistort.cpp:871 tests iy against wOrg-1: a table built that way may read below the raw image
+    const float x = remapX[i], y = remapY[i];
+    if (x < 0) continue;
+    if (!(x > 0 && y > 0 && x < w_org-1 && y < h_org-1)) return ctx_fail(c, SDV_ERR_ARG, "remap table entry %zu (%g,%g) reads outside the %dx%d raw image", i, x, y, w_org, h_org);
+  }
+  CK(cudaStreamSynchronize(c->st_in));                                     // an ingest in flight may still read the previous tables
+  cudaFree(c->und_buf); c->und_buf = nullptr; c->has_und = false;
+  const size_t nfl = 2*px + (G256 ? 256 : 0) + (vignette_inv ? po : 0);
+  CK(cudaMalloc(&c->und_buf, nfl*sizeof(float)));
+  float* p = c->und_buf;
+  CK(cudaMemcpy(p, remapX, px*sizeof(float), cudaMemcpyHostToDevice)); c->und.remapX = p; p += px;
+  CK(cudaMemcpy(p, remapY, px*sizeof(float), cudaMemcpyHostToDevice)); c->und.remapY = p; p += px;
+  c->und.G = nullptr; c->und.vignette = nullptr;
+  if (G256) { CK(cudaMemcpy(p, G256, 256*sizeof(float), cudaMemcpyHostToDevice)); c->und.G = p; p += 256; }
+  if (vignette_inv) { CK(cudaMemcpy(p, vignette_inv, po*sizeof(float), cudaMemcpyHostToDevice)); c->und.vignette = p; p += po; }
+  c->und.wOrg = w_org; c->und.hOrg = h_org; c->und.factor = factor; c->has_und = true;
+  return SDV_OK;
+}
+int sdv_frame_upload_batch_raw_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* raw_imgs, const float* exposures) {
+  return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(raw_imgs), exposures, 8);
 }
 int sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int fmt, const float* exposures) {
   if (fmt < 0 || fmt > 2) return SDV_ERR_ARG;

@@ -39,6 +39,7 @@ struct sdv_ctx {
   std::unordered_map<uint64_t,int> pins;
   unsigned char* stage_u8[2] = {nullptr, nullptr}; size_t stage_u8_cap[2] = {0, 0};   // contiguous mono8 staging per parity (adjacent host images coalesce into one copy)
   std::vector<float*> stage[2]; int stage_cap; sdv::PyrBatchHost* pyr_batch_dev[2]; sdv::PyrBatchHost* pyr_batch_host[2];     // double-buffered by ingest parity
+  sdv::UndistortDev und = {}; bool has_und = false; float* und_buf = nullptr;       // sdv_set_undistort: remap tables (+ response / vignette) of the raw-image ingest
   std::vector<float4*> lvl0_pool; std::vector<int> lvl0_free;
   std::vector<void*> cp_dst, cp_src; std::vector<size_t> cp_sz; bool no_batch_copy = false;
   std::vector<sdv::TrackerSlot> slots;
@@ -59,6 +60,7 @@ struct sdv_ctx {
 
 namespace sdv {
 void rp_destroy(sdv_ctx* c);
+void rp_calib_changed(sdv_ctx* c);             // the Reprojector constants (K, K^-1) are rebuilt from the context calibration at the next call
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
 void ba_destroy(sdv_ctx* c);
 int  ensure_lvl0(sdv_ctx* c, FrameDev& f);     // build the packed level-0 texels of a frame on demand (keyframes / read-back)

@@ -73,9 +73,9 @@ __device__ __forceinline__ void finalize_gs_warp(const double* tot, double* H /*
     const int k = lane + 32*rep;
     if (k < kNH) {
       // (r,c) of the k-th entry of the row-major upper triangle of the 9x9 system
-      int r = 0, base = 0;
+      int r = 0, base = 0; bool walking = true;
 #pragma unroll
-      for (int rr = 0; rr < 8; rr++) { const int next = base + (9 - rr); if (k >= next) { r = rr + 1; base = next; } }
+      for (int rr = 0; rr < 8; rr++) { const int next = base + (9 - rr); if (walking && k >= next) { r = rr + 1; base = next; } else walking = false; }
       const int c = r + (k - base);
       const float scr = (r < 3) ? 1.0f : ((r < 6) ? 0.5f : ((r == 6) ? 10.0f : 1000.0f));   // SCALE_XI_ROT x3, SCALE_XI_TRANS x3, SCALE_A, SCALE_B
       const float scc = (c < 3) ? 1.0f : ((c < 6) ? 0.5f : ((c == 6) ? 10.0f : 1000.0f));

@@ -17,7 +17,8 @@ namespace sdv {
 // Batched over frames (blockIdx.y = frame of the batch): one launch per level for the whole batch.
 // gradient + pack of one level from a planar intensity image (HessianBlocks.cpp:147-165).  Flat-index neighbours on
 // purpose: at x=0 / x=w-1 the reference reads across the row boundary (idx±1), and so do we.
-struct PyrBatch { const void* src; float* I0; float* scratch; float4* out; };   // per frame: level-0 input (float/u8; may equal I0), level-0 plane, planar scratch, base of levels >= 1
+struct PyrBatch { const void* src; float* I0; float* scratch; float4* out; int flags; int pad; };   // per frame: level-0 input (float/u8; may equal I0), level-0 plane, planar scratch, base of levels >= 1; flags bit0: photometric response applies (exposure > 0)
+static_assert(sizeof(PyrBatch) == sizeof(PyrBatchHost), "PyrBatch mirrors PyrBatchHost");
 
 template <typename T> __device__ __forceinline__ float px_load(const T* p, int i);
 template <> __device__ __forceinline__ float px_load<float>(const float* p, int i) { return __ldg(p + i); }
@@ -63,11 +64,51 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const PyrBatch* __restric
   }
 }
 
+// Undistort::undistort<unsigned char> (util/Undistort.cpp:341-435) fused with PhotometricUndistorter::processFrame (:177-214): one rectified level-0 pixel from the
+// RAW mono8 wire image.  remapX/remapY are the tables of Undistort::readFromFile (:842-886; -1 = outside), the four taps go through the photometric stage
+// (factor*v, or G[v] (* vignetteMapInv) with a response calibration and exposure > 0) and are blended in the reference's order (fmad off):
+//   xxyy*src[1+wOrg] + (yy-xxyy)*src[wOrg] + (xx-xxyy)*src[1] + (1-xx-yy+xxyy)*src[0]
+__device__ __forceinline__ float undist_tap(const unsigned char* __restrict__ raw, int i, const UndistortDev& U, bool photo) {
+  const unsigned char v = __ldg(raw + i);
+  if (!photo) return U.factor * (float)v;
+  float r = __ldg(U.G + v);
+  if (U.vignette) r *= __ldg(U.vignette + i);
+  return r;
+}
+__device__ __forceinline__ float undist_px(const unsigned char* __restrict__ raw, int idx, const UndistortDev& U, bool photo) {
+  float xx = __ldg(U.remapX + idx), yy = __ldg(U.remapY + idx);
+  if (xx < 0) return 0.f;
+  const int xxi = (int)xx, yyi = (int)yy;
+  xx -= xxi; yy -= yyi;
+  const float xxyy = xx*yy;
+  const int o = xxi + yyi*U.wOrg;
+  const float s0 = undist_tap(raw, o, U, photo), s1 = undist_tap(raw, o+1, U, photo), sw = undist_tap(raw, o+U.wOrg, U, photo), sw1 = undist_tap(raw, o+1+U.wOrg, U, photo);
+  return xxyy*sw1 + (yy-xxyy)*sw + (xx-xxyy)*s1 + (1-xx-yy+xxyy)*s0;
+}
+// raw ingest, levels > 1: level-0 plane + level 1 in one pass (one thread = one level-1 pixel = a 2x2 quad of rectified pixels)
+__global__ void __launch_bounds__(256) pyr_down_remap_kernel(const PyrBatch* __restrict__ batch, UndistortDev U, size_t dst_off, int wl, int hl, int wlm1) {
+  const PyrBatch b = batch[blockIdx.y];
+  const unsigned char* raw = reinterpret_cast<const unsigned char*>(b.src); const bool photo = (b.flags & 1) && U.G;
+  float* I = b.scratch + dst_off; float* I0 = b.I0;
+  const int n = wl*hl;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) {
+    int y = idx / wl, x = idx - y*wl;
+    int bi = 2*x + 2*y*wlm1;
+    float a0 = undist_px(raw, bi, U, photo), a1 = undist_px(raw, bi+1, U, photo), a2 = undist_px(raw, bi+wlm1, U, photo), a3 = undist_px(raw, bi+wlm1+1, U, photo);
+    I[idx] = 0.25f * (((a0 + a1) + a2) + a3);
+    *reinterpret_cast<float2*>(I0 + bi) = make_float2(a0, a1); *reinterpret_cast<float2*>(I0 + bi + wlm1) = make_float2(a2, a3);
+  }
+}
+__global__ void __launch_bounds__(256) pyr_remap0_kernel(const PyrBatch* __restrict__ batch, UndistortDev U, int n) {
+  const PyrBatch b = batch[blockIdx.y]; const bool photo = (b.flags & 1) && U.G;
+  for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) b.I0[idx] = undist_px(reinterpret_cast<const unsigned char*>(b.src), idx, U, photo);
+}
+
 size_t pyramid_scratch_floats(int w, int h, int levels) { size_t n = 0; for (int l = 1; l < levels; l++) n += (size_t)(w>>l)*(h>>l); return n + 4; }
 
 // batch_dev: nframes PyrBatch descriptors in device memory.  src_u8: level-0 input is mono8 (sensor_msgs/Image wire format) instead of float.
 // Requires even w,h whenever levels > 1 (pyrLevelsUsed only halves even sizes, globalCalib.cpp:24).
-void launch_pyramid_batch(const void* batch_dev_v, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st) {
+void launch_pyramid_batch(const void* batch_dev_v, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st, const UndistortDev* und) {
   const PyrBatch* batch_dev = reinterpret_cast<const PyrBatch*>(batch_dev_v);
   if (nframes <= 0) return;
   size_t soff = 0, prev_soff = 0; int wl = w, hl = h;
@@ -75,7 +116,8 @@ void launch_pyramid_batch(const void* batch_dev_v, int nframes, bool src_u8, con
   for (int l = 0; l + 1 < levels; l++) {
     int wn = wl>>1, hn = hl>>1; int gn = (wn*hn + 255)/256; if (gn > cap) gn = cap;
     dim3 g2(gn, nframes);
-    if (l == 0 && src_u8) pyr_down_kernel<unsigned char><<<g2, 256, 0, st>>>(batch_dev, 1, 0, soff, wn, hn, wl);
+    if (l == 0 && und) pyr_down_remap_kernel<<<g2, 256, 0, st>>>(batch_dev, *und, soff, wn, hn, wl);
+    else if (l == 0 && src_u8) pyr_down_kernel<unsigned char><<<g2, 256, 0, st>>>(batch_dev, 1, 0, soff, wn, hn, wl);
     else pyr_down_kernel<float><<<g2, 256, 0, st>>>(batch_dev, l == 0, prev_soff, soff, wn, hn, wl);
     pyr_grad_kernel<<<g2, 256, 0, st>>>(batch_dev, soff, lvl_off[l+1], wn, hn);
     prev_soff = soff; soff += (size_t)wn*hn; wl = wn; hl = hn;
@@ -86,10 +128,11 @@ template <typename T> __global__ void pyr_copy0_kernel(const PyrBatch* __restric
   const PyrBatch b = batch[blockIdx.y]; if (reinterpret_cast<const void*>(b.I0) == b.src) return;
   for (int idx = blockIdx.x*blockDim.x + threadIdx.x; idx < n; idx += gridDim.x*blockDim.x) b.I0[idx] = px_load<T>(reinterpret_cast<const T*>(b.src), idx);
 }
-void launch_pyramid_copy0(const void* batch_dev_v, int nframes, bool src_u8, int w, int h, cudaStream_t st) {
+void launch_pyramid_copy0(const void* batch_dev_v, int nframes, bool src_u8, int w, int h, cudaStream_t st, const UndistortDev* und) {
   const PyrBatch* batch_dev = reinterpret_cast<const PyrBatch*>(batch_dev_v); if (nframes <= 0) return;
   dim3 g((w*h + 255)/256 > 1024 ? 1024 : (w*h + 255)/256, nframes);
-  if (src_u8) pyr_copy0_kernel<unsigned char><<<g, 256, 0, st>>>(batch_dev, w*h); else pyr_copy0_kernel<float><<<g, 256, 0, st>>>(batch_dev, w*h);
+  if (und) pyr_remap0_kernel<<<g, 256, 0, st>>>(batch_dev, *und, w*h);
+  else if (src_u8) pyr_copy0_kernel<unsigned char><<<g, 256, 0, st>>>(batch_dev, w*h); else pyr_copy0_kernel<float><<<g, 256, 0, st>>>(batch_dev, w*h);
 }
 void launch_pyramid_level0_texels(const float* I0, float4* out, int w, int h, cudaStream_t st) {
   int n = w*h; int grid = (n + 255)/256; if (grid > 148*16) grid = 148*16;

@@ -5,10 +5,12 @@
 namespace sdv {
 
 // pyramid (FrameHessian::makeImages, HessianBlocks.cpp:107-167)
-struct PyrBatchHost { const void* src; float* I0; float* scratch; float4* out; };   // mirrors PyrBatch in sdv_kernels.cu
+struct PyrBatchHost { const void* src; float* I0; float* scratch; float4* out; int flags; int pad; };   // mirrors PyrBatch in sdv_kernels.cu
+// geometric + photometric undistortion tables of the ingest (util/Undistort.cpp): device pointers; G / vignette may be null
+struct UndistortDev { const float* remapX; const float* remapY; const float* G; const float* vignette; int wOrg, hOrg; float factor; };
 size_t pyramid_scratch_floats(int w, int h, int levels);
-void launch_pyramid_batch(const void* batch_dev, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st);
-void launch_pyramid_copy0(const void* batch_dev, int nframes, bool src_u8, int w, int h, cudaStream_t st);
+void launch_pyramid_batch(const void* batch_dev, int nframes, bool src_u8, const size_t* lvl_off, int w, int h, int levels, cudaStream_t st, const UndistortDev* und = nullptr);
+void launch_pyramid_copy0(const void* batch_dev, int nframes, bool src_u8, int w, int h, cudaStream_t st, const UndistortDev* und = nullptr);
 void launch_pyramid_level0_texels(const float* I0, float4* out, int w, int h, cudaStream_t st);
 void launch_unpack_level(const float4* in, float* dI3, float* ab, int n, cudaStream_t st);
 

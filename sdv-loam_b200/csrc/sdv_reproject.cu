@@ -291,6 +291,7 @@ struct MapSlot { long long ingest_seq = 0; MapDev host_copy; MapDev* dev = nullp
 struct RpState { std::vector<MapSlot> maps; void* dev = nullptr; void* host = nullptr; size_t cap = 0, host_cap = 0; RpConst C; bool c_ready = false; };
 static RpState* rp_state(sdv_ctx* c) { if (!c->rp) { c->rp = new RpState(); c->rp->maps.resize(c->slots.size()); } return c->rp; }
 void rp_destroy(sdv_ctx* c) { if (!c->rp) return; for (auto& m : c->rp->maps) { if (m.set) for (int k=0;k<m.nH;k++) frame_unpin(c, m.host_ids[k]); cudaFree(m.dev); cudaFree(m.pts); } cudaFree(c->rp->dev); cudaFreeHost(c->rp->host); delete c->rp; c->rp = nullptr; }
+void rp_calib_changed(sdv_ctx* c) { if (c->rp) c->rp->c_ready = false; }
 static void rp_const(sdv_ctx* c, RpState* st) {
   if (st->c_ready) return; RpConst& C = st->C; const LevelGeom& g = c->tc.geom[0];
   for (int i=0;i<9;i++) C.K[i] = 0; C.K[0] = (double)g.fx; C.K[2] = (double)g.cx; C.K[4] = (double)g.fy; C.K[5] = (double)g.cy; C.K[8] = 1.0;

@@ -9,10 +9,10 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 th = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 cs = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 seq, _ = bench.load_sequence()
-w, h = synth.KITTI_WH
+w, h = seq.wh
 pts = synth.select_points(seq.images[0], seq.clouds[0], 2000)
 p4 = np.concatenate([pts, np.full((len(pts), 1), 1e-3, np.float32)], 1).astype(np.float32); rh = np.zeros(len(p4), np.int32)
-ctx = api.Context(synth.KITTI_K, w, h, n_tracker_slots=B, max_frames=B + 2, cluster_size=cs, track_threads=th)
+ctx = api.Context(seq.K, w, h, n_tracker_slots=B, max_frames=B + 2, cluster_size=cs, track_threads=th)
 KF = 1 << 40
 for b in range(B):
     ctx.makeImages(KF, seq.images[0]); api.CoarseTracker(ctx, b).setCoarseTrackingRef(KF, p4, rh); ctx.releaseFrame(KF)

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz.
 
 The reference ships no golden vectors and cannot be built or imported here, so these fixtures are
-REGRESSION PINS OF THE ORACLE (oracle/, parity unpinned), not reference outputs: they freeze the oracle's results on small
+REGRESSION PINS OF THE ORACLE (oracle/; the oracle itself is pinned on oracle/_ref by tests/test_ref_pin*.py), not reference outputs: they freeze the oracle's results on small
 seeded inputs so that (a) any drift of the oracle is caught on CPU and (b) the CUDA path is compared against a committed
 vector as well as against the live oracle.  Run from the repo root:  python tests/golden/make_golden.py
 """

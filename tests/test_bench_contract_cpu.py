@@ -1,5 +1,6 @@
-"""CPU checks of the bench.py contract: the reference arm runs here (it is the CPU oracle port) and prints one JSON line with the agreed keys;
-the committed default-run JSON of the B200 arm (profiles/r1b_bench_default.json) carries every key the driver reads."""
+"""CPU checks of the bench.py contract: the reference arm runs here (the reference's own compiled tracker from oracle/_ref when it was built, else the oracle port)
+and prints one JSON line with the agreed keys; the committed default-run JSON of the B200 arm (newest profiles/r*_bench_default.json) carries every key the driver reads."""
+import glob
 import json
 import os
 import subprocess
@@ -16,7 +17,9 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    import ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref.available() else "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["warmup"] == 1 and d["steps"] == 1 and {"sequences_per_gpu", "workload"} <= set(d["config"])
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
 
@@ -28,7 +31,8 @@ def test_reference_arm_other_ranks_stay_silent():
 
 
 def test_committed_b200_line_has_every_contract_key():
-    d = json.loads([l for l in open(os.path.join(ROOT, "profiles", "r1b_bench_default.json")) if l.startswith("{")][-1])
+    newest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_default.json")))[-1]
+    d = json.loads([l for l in open(newest) if l.startswith("{")][-1])
     assert BASE_KEYS | {"gpu_launches", "clocks", "roofline"} <= set(d)
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["roofline"]["bound"] == "hbm"
     assert abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9

@@ -232,3 +232,23 @@ def test_ingest_variants_identical_pyramids_and_pipelined_order(kitti_seq):
     Tb2 = T0.copy(); ctx.trackBatch(slots, ids + 200, Tb2, np.zeros((B, 2)))
     assert np.array_equal(Ta, Ta2) and np.array_equal(Tb, Tb2)
     ctx.close()
+
+
+def test_set_calib_equals_fresh_context(kitti_seq):
+    """sdv_set_calib = CoarseTracker::makeK with the intrinsics the bundle adjustment moved: same results as a context created with them (tracker, LM, refinement)."""
+    api, synth = _api()
+    K2 = tuple(np.float32(synth.KITTI_K) * np.float32([1.01, 0.99, 1.0, 1.0]) + np.float32([0, 0, 1.5, -0.75]))
+    ctx_a, tr_a, _, _, L = _pair(api, synth, kitti_seq, synth.KITTI_K, synth.KITTI_WH, 1500)
+    ctx_b, tr_b, _, _, _ = _pair(api, synth, kitti_seq, K2, synth.KITTI_WH, 1500)
+    ctx_a.setCalib(K2)
+    T = orc.se3_exp([0.02, 0.0, 0.45, 1e-3, -1e-3, 5e-4])
+    for l in range(L):
+        ra = tr_a.calcRes(1, l, T, 0.01, 0.5, 20.0); rb = tr_b.calcRes(1, l, T, 0.01, 0.5, 20.0)
+        assert np.array_equal(ra, rb, equal_nan=True), l
+        (Ha, ba), (Hb, bb) = tr_a.calcGSSSE(l), tr_b.calcGSSSE(l)
+        assert np.array_equal(Ha, Hb, equal_nan=True) and np.array_equal(ba, bb, equal_nan=True)
+    qa = tr_a.trackNewestCoarse(1, ID7, [0.0, 0.0]); qb = tr_b.trackNewestCoarse(1, ID7, [0.0, 0.0])
+    assert np.array_equal(qa["T"], qb["T"]) and np.array_equal(qa["iterations"], qb["iterations"])
+    with pytest.raises(api.SdvError):
+        ctx_a.setCalib((0.0, 500.0, 1.0, 1.0))
+    ctx_a.close(); ctx_b.close()
