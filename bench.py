@@ -479,7 +479,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seqs", type=int, default=1184, help="resident sequences per GPU (148 SMs x 4 co-resident jobs x 2 waves)")
-    ap.add_argument("--batches", type=int, default=12, help="batches (one frame of every resident sequence) per step: makes the timed region >= 1 s at the default --steps")
+    ap.add_argument("--batches", type=int, default=16, help="batches (one frame of every resident sequence) per step: makes the timed region >= 1 s at the default --steps")
     ap.add_argument("--points", type=int, default=2000, help="LiDAR-depth splats of the keyframe (reference default ~1500-2000 active points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--track-threads", type=int, default=128, help="threads per trackNewestCoarse job (128: 4 jobs/SM; 64: 8 jobs/SM; 256: latency mode)")

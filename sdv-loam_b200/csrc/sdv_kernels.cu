@@ -624,7 +624,11 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
   // Phase stagger: the MINB jobs co-resident on an SM run the same program on similar data and would reach their single-warp LM control steps
   // together, leaving the SM idle; CTAs are dealt round-robin over the SMs, so wave j of the grid (blockIdx / #SMs-worth) starts j*stagger_ns late
   // and one job's control step overlaps the other jobs' sweeps.
-  if (stagger_ns && C == 1) { const unsigned wave = (unsigned)(((unsigned long long)blockIdx.x*MINB)/gridDim.x); for (unsigned k = 0; k < wave; k++) __nanosleep(stagger_ns); }
+  if (stagger_ns && C == 1) {                               // only the first resident set is delayed; CTAs that start later are desynchronised by their predecessors
+    unsigned nsm; asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+    const unsigned wave = (blockIdx.x < nsm*MINB) ? (blockIdx.x / nsm) % MINB : 0u;
+    for (unsigned k = 0; k < wave; k++) __nanosleep(stagger_ns);
+  }
 
   // dynamic smem: [ tap ring 2 x 4 x THREADS x 16 B | point chunks 2 x kPtChunk x THREADS x 16 B ] aliased by the reduction scratch [kNAcc][THREADS] floats,
   // then the DSMEM gather buffers and the reduced sums

@@ -82,7 +82,7 @@ class GpuReplay:
         from sdv_loam_b200 import api
         self.api = api; self.seq = seq; w, h = seq.wh
         self.ctx = api.Context(K, w, h, levels=levels, n_tracker_slots=2, max_frames=24, affineOptModeA=-1.0, affineOptModeB=-1.0)
-        self.tr = api.CoarseTracker(self.ctx, 0); self.rp = api.Reprojector(self.ctx); self.resident = set()
+        self.tr = api.CoarseTracker(self.ctx, 0); self.rp = api.Reprojector(self.ctx); self.resident = set(); self.K = None
 
     def _need(self, ids):
         for k in ids:
@@ -91,6 +91,9 @@ class GpuReplay:
 
     def track(self, snap, order, i):
         api = self.api; kf = [int(k) for k in snap["kf_ids"]]; need = set(kf) | {int(snap["ref_frame"]), i}
+        Kt = tuple(float(x) for x in snap["tracker_K"])                                              # CoarseTracker::makeK of the tracker in use (== float(CalibHessian) on every frame)
+        if Kt != self.K:
+            self.ctx.setCalib(Kt); self.K = Kt
         for k in list(self.resident - need):
             try:
                 self.ctx.releaseFrame(k); self.resident.discard(k)

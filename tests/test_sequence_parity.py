@@ -83,7 +83,7 @@ def test_gpu_replays_reference_sequence():
         dump.append(sr.dump_line(res))
         if snap is None:
             continue
-        assert tuple(np.float32(snap["tracker_K"])) == tuple(np.float32(seq.K))         # the intrinsics prior keeps K where it is on this drive: one context calibration serves
+        assert np.array_equal(np.float32(snap["tracker_K"]), np.float32(snap["calib"]))  # tracker K (makeK) == current CalibHessian on every frame: one context calibration (sdv_set_calib) serves both
         g = gpu.track(snap, order, i)
         et, er = sr.pose_err(g["camToWorld"], res["tracked_camToWorld"])
         ee = abs(g["lastCoarseRMSE"][0] - res["lastCoarseRMSE"][0]) / res["lastCoarseRMSE"][0]
