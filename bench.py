@@ -277,10 +277,17 @@ def ba_leg(ctx, api, synth, local_rank, W, reps=4, warm=2):
         if rep >= warm:
             ms.append(r["ms"]); its = r
     ms = float(np.mean(ms))
+    one = []; one_wall = []                                              # latency of ONE window (BASELINE single-sequence view of the back-end): same schedule, grid of one window
+    for rep in range(warm + reps):
+        api.EnergyFunctional(ctx, wins[0], ids[0], window=0); ctx.sync(); t0 = time.perf_counter()
+        r1 = api.optimize_batch(ctx, [0], 6); t1 = time.perf_counter()
+        if rep >= warm:
+            one.append(r1["ms"]); one_wall.append(1e3 * (t1 - t0))
     nR = int(np.mean([len(w["r_point"]) for w in wins])); nP = int(np.mean([len(w["uv"]) for w in wins]))
     lin_calls = float(np.mean(1 + its["iterations"] + (its["iterations"] - its["accepts"]) + 1))   # initial + per iteration + reloads + final
     return {"windows": W, "keyframes": 7, "points_per_window": nP, "residuals_per_window": nR, "ms_per_batch": ms, "windows_per_s": W / (ms * 1e-3),
             "gn_iterations_mean": float(its["iterations"].mean()), "accepts_mean": float(its["accepts"].mean()),
+            "single_window_ms_device": float(np.mean(one)), "single_window_ms_wall": float(np.mean(one_wall)),
             "linearize_GBps_algorithmic": W * nR * 576 * lin_calls / (ms * 1e-3) / 1e9,
             "note": "device time of sdv_ba_optimize_batch (FullSystem::optimize, device-resident GN schedule); bit-exact vs the CPU oracle (tests/test_gpu_ba.py)"}
 
@@ -626,6 +633,19 @@ def main():
         gt_c2w = np.concatenate([synth._quat_from_R(seq.R[k_last]), seq.t[k_last]])
         full_stats = {"batches": KF_full, "tries_mean": float(io["tries"].mean()), "matches_mean": float(io["n_matches"].mean()), "refine_accepts_mean": float(io["refine_accepts"].mean()),
                       "median_translation_err_m": float(np.median(np.linalg.norm(io["camToWorld"][:, 4:] - gt_c2w[4:], axis=1)))}
+    # ---------------------------------------------------------------- leg 2d: the batched runner (sdv_loam_b200/runner.py): world x B Monte-Carlo re-runs of the drive dealt to the
+    # ranks by dist.shard_sequences, every re-run a CHAIN (frame k+1 starts from the constant-motion prediction of its own results), raw mono8 uploads, final reduction over ranks
+    from sdv_loam_b200 import runner
+    seeds = 100000 + np.arange(world * B)
+    be = runner.GpuBackend(ctx, B, u8_ptrs, raw=True)
+    runner.run_monte_carlo(be, seeds, N_FRAMES - 1, gts[1], rank, world, device="cuda")                  # warm-up pass
+    mc = runner.run_monte_carlo(be, seeds, N_FRAMES - 1, gts[1], rank, world, device="cuda")
+    mc_err = [np.abs(synth.se3_log7(synth.se3_mul7(mc["local_poses"][-1][b], synth.se3_inv7(gts[N_FRAMES - 1])))) for b in range(min(B, 64))]
+    mc_runner = {"sequences": mc["sequences"], "frames_per_sequence": N_FRAMES - 1, "frames": mc["frames"], "seconds_max_over_ranks": mc["seconds"], "frames_per_s": mc["frames_per_s"],
+                 "pose_digest": mc["pose_digest"], "tracked_ok_fraction_rank0": mc["local_ok_fraction"],
+                 "final_pose_err_vs_gt_m_rad": [float(max(e[:3].max() for e in mc_err)), float(max(e[3:].max() for e in mc_err))],
+                 "api": "runner.run_monte_carlo over runner.GpuBackend: sequence i -> rank i mod world (dist.shard_sequences), per frame sdv_frame_upload_batch_raw_u8 + "
+                        "sdv_tracker_track_batch, next guess = constant motion from the re-run's own last two poses; no overlap of upload and tracking inside a chain step"}
     clocks = sampler.stop()
     del host_u8
 
@@ -683,6 +703,7 @@ def main():
                      "avg_launch_ms": kern_ms / NB, "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                      "kernel_share_of_step": kern_ms * 1e-3 / t_value},
     }
+    line["mc_runner"] = mc_runner
     if single is not None:
         line["single_sequence"] = single
         line["s_stress"] = stress_leg(api, local_rank)

@@ -59,6 +59,9 @@ const char* sdv_last_error(sdv_ctx* c);
 int  sdv_pyr_levels(int w, int h);                           /* pyrLevelsUsed rule, util/globalCalib.cpp:22-30 */
 int  sdv_sync(sdv_ctx* c);                                   /* drain the context's stream */
 
+/* Threading: a context may be used by TWO host threads at once, split the way the reference splits its work — every sdv_ba_* entry (mapping
+ * thread, FullSystem::mapMutex) on one side, every other entry (tracking thread, trackMutex) on the other.  Each side is serialised internally and runs on its own
+ * stream; calls of the same side from several threads are serialised by the library. */
 /* CoarseTracker::makeK(CalibHessian*) (CoarseTracker.cpp:77-106) and the CalibHessian Reprojector::reprojectMap reads (Reprojector.cpp:117-124): the bundle
  * adjustment optimises the intrinsics at every keyframe, and setCoarseTrackingRef re-derives the tracker's per-level K from them.  Replaces the calibration given
  * to sdv_create for every later tracker / reprojection / structPoseEstimation call of this context (the BA windows carry their own: sdv_ba_set_window). */
@@ -240,6 +243,7 @@ int  sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak_out);
 /* float FullSystem::optimize(int mnumOptIts)  FullSystemOptimize.cpp:344-502 — the whole GN loop incl. the final re-anchoring and
  * linearizeAll(true).  Returns sqrt(lastEnergy / resInA) like the reference. */
 int  sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out);
+float sdv_ba_last_kernel_ms(sdv_ctx* c);                        /* device time of the last sdv_ba_optimize / sdv_ba_optimize_batch (back-end stream) */
 /* Batched mode: a context holds any number of independent windows (one per resident sequence).  sdv_ba_select picks the window the
  * set_ / get_ / step-wise calls address (default 0); sdv_ba_optimize_batch runs FullSystem::optimize on n windows at once — every
  * kernel is launched once for all windows and the accept/reject/break decisions are taken on the device. */

@@ -78,6 +78,7 @@ def _load():
     L.sdv_tracker_track.argtypes = [_vp, C.c_int, C.c_uint64, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(sdv_track_stats)]
     L.sdv_tracker_track_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, C.c_int, _vp, _f64p, _f64p, _i32p, C.POINTER(sdv_track_stats)]
     L.sdv_last_kernel_ms.argtypes = [_vp]; L.sdv_last_kernel_ms.restype = C.c_float
+    L.sdv_ba_last_kernel_ms.argtypes = [_vp]; L.sdv_ba_last_kernel_ms.restype = C.c_float
     return L
 
 
@@ -421,7 +422,7 @@ class EnergyFunctional:
     def optimize(self, its=6):
         self._sel(); r = C.c_float(0); i = C.c_int32(0); a = C.c_int32(0)
         self.ctx._ck(LIB.sdv_ba_optimize(self.ctx.p, its, C.byref(r), C.byref(i), C.byref(a)))
-        return dict(rmse=float(r.value), iterations=int(i.value), accepts=int(a.value), ms=self.ctx.last_kernel_ms())
+        return dict(rmse=float(r.value), iterations=int(i.value), accepts=int(a.value), ms=float(LIB.sdv_ba_last_kernel_ms(self.ctx.p)))
 
     def residuals(self):
         self._sel(); n = self.nR
@@ -480,4 +481,4 @@ def optimize_batch(ctx: Context, windows, its: int = 6):
     _ba_protos(); w = np.ascontiguousarray(windows, np.int32); n = len(w)
     rmse = np.zeros(n, np.float32); it = np.zeros(n, np.int32); acc = np.zeros(n, np.int32)
     ctx._ck(LIB.sdv_ba_optimize_batch(ctx.p, n, w, its, rmse, it, acc))
-    return dict(rmse=rmse, iterations=it, accepts=acc, ms=ctx.last_kernel_ms())
+    return dict(rmse=rmse, iterations=it, accepts=acc, ms=float(LIB.sdv_ba_last_kernel_ms(ctx.p)))

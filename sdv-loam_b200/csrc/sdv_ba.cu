@@ -80,9 +80,9 @@ static int ba_wins(sdv_ctx* c, int n, BAState* const* bs, const BAWinDev** out, 
   if (n > c->ba_wins_cap) { cudaFree(c->ba_wins_dev); cudaFreeHost(c->ba_wins_host); c->ba_wins_cap = n + 16;
     CK(cudaMalloc(&c->ba_wins_dev, (size_t)c->ba_wins_cap*sizeof(BAWinDev))); CK(cudaMallocHost(&c->ba_wins_host, (size_t)c->ba_wins_cap*sizeof(BAWinDev))); }
   BAWinDev* h = (BAWinDev*)c->ba_wins_host; int mp = 1, mr = 1;
-  CK(cudaStreamSynchronize(c->st));                                          // the pinned staging array may still feed a previous launch sequence
+  CK(cudaStreamSynchronize(c->st_ba));                                          // the pinned staging array may still feed a previous launch sequence
   for (int i=0;i<n;i++) { h[i] = win_of(bs[i]); if (bs[i]->nP > mp) mp = bs[i]->nP; if (bs[i]->nR > mr) mr = bs[i]->nR; }
-  CK(cudaMemcpyAsync(c->ba_wins_dev, h, (size_t)n*sizeof(BAWinDev), cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->ba_wins_dev, h, (size_t)n*sizeof(BAWinDev), cudaMemcpyHostToDevice, c->st_ba));
   *out = (const BAWinDev*)c->ba_wins_dev; if (maxP) *maxP = mp; if (maxR) *maxR = mr;
   return SDV_OK;
 }
@@ -90,8 +90,8 @@ static int ba_wins(sdv_ctx* c, int n, BAState* const* bs, const BAWinDev** out, 
 
 static int ba_pull_scalars(sdv_ctx* c, BAState* b) {                        // energyP .. end of header
   const size_t off = offsetof(BAHeader, energyP), len = sizeof(BAHeader) - off;
-  CK(cudaMemcpyAsync((char*)b->hdr_host + off, (char*)b->hdr + off, len, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  CK(cudaMemcpyAsync((char*)b->hdr_host + off, (char*)b->hdr + off, len, cudaMemcpyDeviceToHost, c->st_ba));
+  CK(cudaStreamSynchronize(c->st_ba)); CK(cudaGetLastError());
   return SDV_OK;
 }
 
@@ -99,8 +99,9 @@ extern "C" {
 
 int sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const double* T_evalPT7, const double* state10, const double* state_zero10,
                       const float* ab_exposure, const int32_t* frameID, const float* frameEnergyTH, const double calib_value_scaled[4],
-                      const double* HM, const double* bM) {
+                      const double* HM, const double* bM) { SDV_GUARD_BA(c);
   if (!c || nF < 1 || nF > SDV_MAX_FRAMES_WINDOW || !frame_ids || !T_evalPT7 || !state10 || !state_zero10 || !calib_value_scaled) return SDV_ERR_ARG;
+  SDV_GUARD_TRK(c);                                                           // frame table, pins, level-0 texel pool and the ingest join belong to the tracker domain
   CK(cudaSetDevice(c->device));
   BAState* b; int rc = ba_get(c, &b); if (rc) return rc;
   for (int f=0; f<nF; f++) if (c->frame_index.find(frame_ids[f]) == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "BA frame %d: unknown frame handle", f);
@@ -130,15 +131,17 @@ int sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const doubl
   const int N = H->dim;
   if (HM) memcpy(H->HM, HM, (size_t)N*N*sizeof(double));
   if (bM) memcpy(H->bM, bM, (size_t)N*sizeof(double));
-  CK(cudaMemcpyAsync(b->hdr, H, sizeof(BAHeader), cudaMemcpyHostToDevice, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  { int rcj = join_ingest(c); if (rcj) return rcj; }                          // the keyframes' pyramids (ingest stream) and level-0 texels (tracker stream) are complete
+  CK(cudaEventRecord(c->ev_xdom, c->st)); CK(cudaStreamWaitEvent(c->st_ba, c->ev_xdom, 0));   // before the back-end stream reads them; pinned frames cannot change afterwards
+  CK(cudaMemcpyAsync(b->hdr, H, sizeof(BAHeader), cudaMemcpyHostToDevice, c->st_ba));
+  CK(cudaStreamSynchronize(c->st_ba));
   return SDV_OK;
 }
 
 int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, const float* idepth_zero, const float* color8, const float* weights8,
                       const int32_t* host, const int32_t* hasDepthPrior, const int32_t* isFromSensor, const int32_t* res_begin,
                       int nR, const int32_t* r_point, const int32_t* r_host, const int32_t* r_target, const int32_t* r_hasMatcher,
-                      const float* r_matcher, const int32_t* r_isNew) {
+                      const float* r_matcher, const int32_t* r_isNew) { SDV_GUARD_BA(c);
   if (!c || !c->ba || nP < 0 || nR < 0) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   BAState* b = c->ba; const int nF = b->nF;
@@ -164,7 +167,7 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
   for (int r=0;r<nR;r++) pair_begin[r_host[r] + nF*r_target[r] + 1]++;
   for (int k=0;k<nF*nF;k++) pair_begin[k+1] += pair_begin[k];
   { std::vector<int> cur(pair_begin.begin(), pair_begin.end()-1); for (int r=0;r<nR;r++) pair_res[cur[r_host[r] + nF*r_target[r]]++] = r; }
-  BAPointsDev& P = b->P; BAResDev& R = b->R; cudaStream_t st = c->st;
+  BAPointsDev& P = b->P; BAResDev& R = b->R; cudaStream_t st = c->st_ba;
 #define UP(dst, src, n, T) do { if ((n) > 0) CK(cudaMemcpyAsync(dst, src, (size_t)(n)*sizeof(T), cudaMemcpyHostToDevice, st)); } while (0)
   UP(P.uv, uv, (size_t)nP*2, float); UP(P.idepth, idepth, nP, float); UP(P.idepth_zero, idepth_zero, nP, float); UP(P.idepth_backup, idepth, nP, float);
   UP(P.color, color8, (size_t)nP*8, float); UP(P.weights, weights8, (size_t)nP*8, float);
@@ -181,49 +184,49 @@ int sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, 
   b->nP = nP; b->nR = nR;
   b->hdr_host->nP = nP; b->hdr_host->nR = nR;
   CK(cudaMemcpyAsync(&b->hdr->nP, &b->hdr_host->nP, 2*sizeof(int), cudaMemcpyHostToDevice, st));
-  { int rcj = join_ingest(c); if (rcj) return rcj; }
   { WIN1(); launch_ba_setup(wins, 1, maxP, st); launch_ba_reset_oob(wins, 1, maxR, st); }
   CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
   c->launches += 3;
   return SDV_OK;
 }
 
-int sdv_ba_clear(sdv_ctx* c) {               // empties the selected window and drops its references to frame images
+int sdv_ba_clear(sdv_ctx* c) { SDV_GUARD_BA(c);               // empties the selected window and drops its references to frame images
   if (!c) return SDV_ERR_ARG; if (!c->ba) return SDV_OK; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  CK(cudaStreamSynchronize(c->st));
-  for (int i=0;i<b->n_pinned;i++) frame_unpin(c, b->pinned[i]); b->n_pinned = 0; b->nF = 0; b->nP = 0; b->nR = 0; return SDV_OK;
+  CK(cudaStreamSynchronize(c->st_ba));
+  { SDV_GUARD_TRK(c); for (int i=0;i<b->n_pinned;i++) frame_unpin(c, b->pinned[i]); }
+  b->n_pinned = 0; b->nF = 0; b->nP = 0; b->nR = 0; return SDV_OK;
 }
-int sdv_ba_select(sdv_ctx* c, int window) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); return ba_select(c, window); }
+int sdv_ba_select(sdv_ctx* c, int window) { SDV_GUARD_BA(c); if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); return ba_select(c, window); }
 
-int sdv_ba_reset_oob(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_reset_oob(wins, 1, maxR, c->st); c->launches++; return SDV_OK; }
+int sdv_ba_reset_oob(sdv_ctx* c) { SDV_GUARD_BA(c); if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_reset_oob(wins, 1, maxR, c->st_ba); c->launches++; return SDV_OK; }
 
-int sdv_ba_linearize(sdv_ctx* c, int fix, double* energy) {
+int sdv_ba_linearize(sdv_ctx* c, int fix, double* energy) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
-  launch_ba_linearize(wins, 1, maxR, fix, GATE_ALWAYS, c->st); c->launches += 2;
+  launch_ba_linearize(wins, 1, maxR, fix, GATE_ALWAYS, c->st_ba); c->launches += 2;
   int rc = ba_pull_scalars(c, b); if (rc) return rc;
   if (energy) *energy = b->hdr_host->energyP;
   return SDV_OK;
 }
-int sdv_ba_apply_res(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_apply(wins, 1, maxR, GATE_ALWAYS, c->st); c->launches++; CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
-int sdv_ba_energy(sdv_ctx* c, double* EL, double* EM) {
+int sdv_ba_apply_res(sdv_ctx* c) { SDV_GUARD_BA(c); if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_apply(wins, 1, maxR, GATE_ALWAYS, c->st_ba); c->launches++; CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK; }
+int sdv_ba_energy(sdv_ctx* c, double* EL, double* EM) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
-  launch_ba_energies(wins, 1, GATE_ALWAYS, c->st); c->launches++;
+  launch_ba_energies(wins, 1, GATE_ALWAYS, c->st_ba); c->launches++;
   int rc = ba_pull_scalars(c, b); if (rc) return rc;
   if (EL) *EL = b->hdr_host->energyL; if (EM) *EM = b->hdr_host->energyM;
   return SDV_OK;
 }
-int sdv_ba_solve(sdv_ctx* c, int iteration, double lambda, double* x_out) {
+int sdv_ba_solve(sdv_ctx* c, int iteration, double lambda, double* x_out) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
-  launch_ba_accumulate(wins, 1, maxP, GATE_ALWAYS, c->st);
-  launch_ba_solve(wins, 1, maxP, iteration, lambda, 0, GATE_ALWAYS, c->st); c->launches += 5;
-  if (x_out) { CK(cudaMemcpyAsync(x_out, b->hdr->lastX, (size_t)(kCP+6*b->nF)*sizeof(double), cudaMemcpyDeviceToHost, c->st)); }
-  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  launch_ba_accumulate(wins, 1, maxP, GATE_ALWAYS, c->st_ba);
+  launch_ba_solve(wins, 1, maxP, iteration, lambda, 0, GATE_ALWAYS, c->st_ba); c->launches += 5;
+  if (x_out) { CK(cudaMemcpyAsync(x_out, b->hdr->lastX, (size_t)(kCP+6*b->nF)*sizeof(double), cudaMemcpyDeviceToHost, c->st_ba)); }
+  CK(cudaStreamSynchronize(c->st_ba)); CK(cudaGetLastError());
   return SDV_OK;
 }
-int sdv_ba_backup(sdv_ctx* c) { if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_backup(wins, 1, maxP, GATE_ALWAYS, c->st); c->launches++; return SDV_OK; }
-int sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak) {
+int sdv_ba_backup(sdv_ctx* c) { SDV_GUARD_BA(c); if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_backup(wins, 1, maxP, GATE_ALWAYS, c->st_ba); c->launches++; return SDV_OK; }
+int sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1();
-  launch_ba_step(wins, 1, stepfac, load_backup, GATE_ALWAYS, c->st); c->launches += 2;
+  launch_ba_step(wins, 1, stepfac, load_backup, GATE_ALWAYS, c->st_ba); c->launches += 2;
   int rc = ba_pull_scalars(c, b); if (rc) return rc;
   if (canbreak) *canbreak = b->hdr_host->canbreak;
   return SDV_OK;
@@ -233,9 +236,9 @@ int sdv_ba_step(sdv_ctx* c, float stepfac, int load_backup, int* canbreak) {
  * The Gauss-Newton loop is DEVICE-RESIDENT: every kernel is launched for all windows (grid.y = window) on a fixed schedule and
  * gated by per-window flags that ba_decide_kernel sets (accept -> APPLY, reject -> RELOAD, converged -> not ACTIVE); the host
  * never reads a decision back.  One D2H of the per-window tail at the end. */
-int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) {
+int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) { SDV_GUARD_BA(c);
   if (!c || n < 1 || !windows) return SDV_ERR_ARG;
-  CK(cudaSetDevice(c->device)); cudaStream_t st = c->st;
+  CK(cudaSetDevice(c->device)); cudaStream_t st = c->st_ba;
   std::vector<BAState*> bs(n); int maxIts = 0;
   for (int i=0;i<n;i++) {
     if (windows[i] < 0 || windows[i] >= (int)c->ba_windows.size() || !c->ba_windows[windows[i]]) return ctx_fail(c, SDV_ERR_ARG, "BA window %d not set", windows[i]);
@@ -245,7 +248,6 @@ int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOpt
     CK(cudaMemcpyAsync(&bs[i]->hdr->mnumOptIts, &bs[i]->hdr_host->mnumOptIts, sizeof(int), cudaMemcpyHostToDevice, st));
   }
   const BAWinDev* wins; int maxP, maxR; { int rcw = ba_wins(c, n, bs.data(), &wins, &maxP, &maxR); if (rcw) return rcw; }
-  { int rcj = join_ingest(c); if (rcj) return rcj; }
   // The schedule is fixed (decisions are taken on the device and gate the launches), so for the usual short schedules it is captured once into a CUDA graph and
   // replayed: one graph launch instead of 6 + 19 per iteration + 5 kernel launches — what a single window (launch-latency bound) pays for.
   auto schedule = [&](cudaStream_t st, bool poll) -> int {
@@ -291,33 +293,34 @@ int sdv_ba_optimize_batch(sdv_ctx* c, int n, const int32_t* windows, int mnumOpt
       CK(cudaGraphInstantiate(&c->ba_graph, g, 0)); cudaGraphDestroy(g);
       c->bag_wins = wins; c->bag_n = n; c->bag_maxP = maxP; c->bag_maxR = maxR; c->bag_its = maxIts;
     }
-    CK(cudaEventRecord(c->ev0, st));
+    CK(cudaEventRecord(c->ba_ev0, st));
     CK(cudaGraphLaunch(c->ba_graph, st));
   } else {
-    CK(cudaEventRecord(c->ev0, st));
+    CK(cudaEventRecord(c->ba_ev0, st));
     { int rcs = schedule(st, true); if (rcs) return rcs; }
   }
-  CK(cudaEventRecord(c->ev1, st));
+  CK(cudaEventRecord(c->ba_ev1, st));
   for (int i=0;i<n;i++) { const size_t off = offsetof(BAHeader, energyP), len = sizeof(BAHeader) - off;
     CK(cudaMemcpyAsync((char*)bs[i]->hdr_host + off, (char*)bs[i]->hdr + off, len, cudaMemcpyDeviceToHost, st)); }
   CK(cudaStreamSynchronize(st)); CK(cudaGetLastError());
-  CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  CK(cudaEventElapsedTime(&c->ba_last_ms, c->ba_ev0, c->ba_ev1));
   for (int i=0;i<n;i++) { const BAHeader* H = bs[i]->hdr_host;
     if (rmse_out) rmse_out[i] = (bs[i]->nF < 2) ? 0.f : H->rmse;
     if (iterations_out) iterations_out[i] = H->opt_iterations;
     if (accepts_out) accepts_out[i] = H->opt_accepts; }
   return SDV_OK;
 }
-int sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) {
+float sdv_ba_last_kernel_ms(sdv_ctx* c) { return c ? c->ba_last_ms : 0.f; }
+int sdv_ba_optimize(sdv_ctx* c, int mnumOptIts, float* rmse_out, int32_t* iterations_out, int32_t* accepts_out) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG;
   int32_t w = -1; for (size_t i=0;i<c->ba_windows.size();i++) if (c->ba_windows[i] == c->ba) w = (int32_t)i;
   return sdv_ba_optimize_batch(c, 1, &w, mnumOptIts, rmse_out, iterations_out, accepts_out);
 }
 
 // ---- read-back (what the reference leaves in FrameHessian / PointHessian / PointFrameResidual / EnergyFunctional)
-int sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* step10, float* frameEnergyTH, double* PRE_worldToCam7, double calib_value[4], double calib_step[4]) {
+int sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* step10, float* frameEnergyTH, double* PRE_worldToCam7, double calib_value[4], double calib_step[4]) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  CK(cudaMemcpyAsync(b->hdr_host, b->hdr, offsetof(BAHeader, precalc), cudaMemcpyDeviceToHost, c->st)); CK(cudaStreamSynchronize(c->st));
+  CK(cudaMemcpyAsync(b->hdr_host, b->hdr, offsetof(BAHeader, precalc), cudaMemcpyDeviceToHost, c->st_ba)); CK(cudaStreamSynchronize(c->st_ba));
   const BAHeader* H = b->hdr_host;
   for (int f=0; f<b->nF; f++) { const BAFrameDev& F = H->frames[f];
     if (T_evalPT7) se3_to7(F.evalPT, T_evalPT7 + 7*f); if (PRE_worldToCam7) se3_to7(F.PRE_w2c, PRE_worldToCam7 + 7*f);
@@ -326,79 +329,79 @@ int sdv_ba_get_frames(sdv_ctx* c, double* T_evalPT7, double* state10, double* st
   for (int i=0;i<4;i++) { if (calib_value) calib_value[i] = H->calib.value[i]; if (calib_step) calib_step[i] = H->calib.step[i]; }
   return SDV_OK;
 }
-int sdv_ba_get_points(sdv_ctx* c, float* idepth, float* step, float* HdiF, float* bdSumF, float* maxRelBaseline, int32_t* numGoodResiduals, float* idepth_hessian) {
+int sdv_ba_get_points(sdv_ctx* c, float* idepth, float* step, float* HdiF, float* bdSumF, float* maxRelBaseline, int32_t* numGoodResiduals, float* idepth_hessian) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int n = b->nP; const BAPointsDev& P = b->P;
-#define DN(dst, src, T) do { if (dst && n > 0) CK(cudaMemcpyAsync(dst, src, (size_t)n*sizeof(T), cudaMemcpyDeviceToHost, c->st)); } while (0)
+#define DN(dst, src, T) do { if (dst && n > 0) CK(cudaMemcpyAsync(dst, src, (size_t)n*sizeof(T), cudaMemcpyDeviceToHost, c->st_ba)); } while (0)
   DN(idepth, P.idepth, float); DN(step, P.step, float); DN(HdiF, P.HdiF, float); DN(bdSumF, P.bdSumF, float); DN(maxRelBaseline, P.maxRelBaseline, float);
   DN(numGoodResiduals, P.numGoodResiduals, int); DN(idepth_hessian, P.idepth_hessian, float);
 #undef DN
-  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+  CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK;
 }
 int sdv_ba_get_residuals(sdv_ctx* c, int32_t* state_state, int32_t* state_NewState, float* energies3, int32_t* isActive, float* J24, float* efJ24,
-                         float* JpJdF8, float* center3, int32_t* toRemove) {
+                         float* JpJdF8, float* center3, int32_t* toRemove) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int n = b->nR; const BAResDev& R = b->R;
   if (n == 0) return SDV_OK;
   std::vector<float> e0(n), e1(n), e2(n);
-#define DN(dst, src, cnt, T) do { if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt)*sizeof(T), cudaMemcpyDeviceToHost, c->st)); } while (0)
+#define DN(dst, src, cnt, T) do { if (dst) CK(cudaMemcpyAsync(dst, src, (size_t)(cnt)*sizeof(T), cudaMemcpyDeviceToHost, c->st_ba)); } while (0)
   DN(state_state, R.state_state, n, int); DN(state_NewState, R.state_NewState, n, int); DN(isActive, R.isActive, n, int); DN(toRemove, R.toRemove, n, int);
   DN(J24, R.J, (size_t)n*24, float); DN(efJ24, R.efJ, (size_t)n*24, float); DN(JpJdF8, R.JpJdF, (size_t)n*8, float); DN(center3, R.center, (size_t)n*3, float);
   DN(e0.data(), R.state_energy, n, float); DN(e1.data(), R.state_NewEnergy, n, float); DN(e2.data(), R.state_NewEnergyWithOutlier, n, float);
 #undef DN
-  CK(cudaStreamSynchronize(c->st));
+  CK(cudaStreamSynchronize(c->st_ba));
   if (energies3) for (int i=0;i<n;i++) { energies3[3*i] = e0[i]; energies3[3*i+1] = e1[i]; energies3[3*i+2] = e2[i]; }
   return SDV_OK;
 }
 // ------------------------------------------------------------------------------------------------ keyframe hand-over (FullSystem::makeKeyFrame, FullSystem.cpp:1152-1171)
-int sdv_ba_flag_points(sdv_ctx* c, const int32_t* selected, int32_t* status_out) {
+int sdv_ba_flag_points(sdv_ctx* c, const int32_t* selected, int32_t* status_out) { SDV_GUARD_BA(c);
   if (!c || !c->ba || !selected) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
   if (b->nP <= 0) return ctx_fail(c, SDV_ERR_STATE, "flag_points: window has no points (call sdv_ba_set_points)");
   WIN1();
-  CK(cudaMemcpyAsync(b->P.marg_status, selected, (size_t)b->nP*sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
-  launch_ba_marg_flag(wins, 1, maxP, c->st); c->launches += 1;
-  if (status_out) CK(cudaMemcpyAsync(status_out, b->P.marg_status, (size_t)b->nP*sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(b->P.marg_status, selected, (size_t)b->nP*sizeof(int32_t), cudaMemcpyHostToDevice, c->st_ba));
+  launch_ba_marg_flag(wins, 1, maxP, c->st_ba); c->launches += 1;
+  if (status_out) CK(cudaMemcpyAsync(status_out, b->P.marg_status, (size_t)b->nP*sizeof(int32_t), cudaMemcpyDeviceToHost, c->st_ba));
+  CK(cudaStreamSynchronize(c->st_ba)); CK(cudaGetLastError());
   return SDV_OK;
 }
-int sdv_ba_marginalize_points(sdv_ctx* c, const int32_t* status) {
+int sdv_ba_marginalize_points(sdv_ctx* c, const int32_t* status) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
   if (b->nP <= 0) return ctx_fail(c, SDV_ERR_STATE, "marginalize_points: window has no points");
   WIN1();
-  if (status) CK(cudaMemcpyAsync(b->P.marg_status, status, (size_t)b->nP*sizeof(int32_t), cudaMemcpyHostToDevice, c->st));
-  launch_ba_marg_points(wins, 1, maxP, c->st); c->launches += 4;
-  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
+  if (status) CK(cudaMemcpyAsync(b->P.marg_status, status, (size_t)b->nP*sizeof(int32_t), cudaMemcpyHostToDevice, c->st_ba));
+  launch_ba_marg_points(wins, 1, maxP, c->st_ba); c->launches += 4;
+  CK(cudaStreamSynchronize(c->st_ba)); CK(cudaGetLastError());
   return SDV_OK;
 }
-int sdv_ba_marginalize_frame(sdv_ctx* c, int idx) {
+int sdv_ba_marginalize_frame(sdv_ctx* c, int idx) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
   if (idx < 0 || idx >= b->nF || b->nF < 2) return ctx_fail(c, SDV_ERR_ARG, "marginalize_frame: frame %d of %d", idx, b->nF);
   WIN1();
-  launch_ba_marg_frame(wins, 1, idx, c->st); c->launches += 1;
-  CK(cudaStreamSynchronize(c->st)); CK(cudaGetLastError());
-  if (idx < b->n_pinned) { frame_unpin(c, b->pinned[idx]); for (int i=idx; i+1<b->n_pinned; i++) b->pinned[i] = b->pinned[i+1]; b->n_pinned--; }
+  launch_ba_marg_frame(wins, 1, idx, c->st_ba); c->launches += 1;
+  CK(cudaStreamSynchronize(c->st_ba)); CK(cudaGetLastError());
+  if (idx < b->n_pinned) { { SDV_GUARD_TRK(c); frame_unpin(c, b->pinned[idx]); } for (int i=idx; i+1<b->n_pinned; i++) b->pinned[i] = b->pinned[i+1]; b->n_pinned--; }
   b->nF -= 1; b->nP = 0; b->nR = 0;                                          // points/residuals are stale: the caller re-flattens the window (sdv_ba_set_points)
   return SDV_OK;
 }
-int sdv_ba_get_prior(sdv_ctx* c, int* dim, double* HM, double* bM) {
+int sdv_ba_get_prior(sdv_ctx* c, int* dim, double* HM, double* bM) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int N = kCP + 6*b->nF;
   if (dim) *dim = N;
-  if (HM) CK(cudaMemcpyAsync(HM, b->hdr->HM, (size_t)N*N*sizeof(double), cudaMemcpyDeviceToHost, c->st));
-  if (bM) CK(cudaMemcpyAsync(bM, b->hdr->bM, (size_t)N*sizeof(double), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+  if (HM) CK(cudaMemcpyAsync(HM, b->hdr->HM, (size_t)N*N*sizeof(double), cudaMemcpyDeviceToHost, c->st_ba));
+  if (bM) CK(cudaMemcpyAsync(bM, b->hdr->bM, (size_t)N*sizeof(double), cudaMemcpyDeviceToHost, c->st_ba));
+  CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK;
 }
-int sdv_ba_get_linearized(sdv_ctx* c, float* res_toZero2, int32_t* isLinearized) {
+int sdv_ba_get_linearized(sdv_ctx* c, float* res_toZero2, int32_t* isLinearized) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba;
-  if (res_toZero2) CK(cudaMemcpyAsync(res_toZero2, b->R.res_toZero, (size_t)b->nR*2*sizeof(float), cudaMemcpyDeviceToHost, c->st));
-  if (isLinearized) CK(cudaMemcpyAsync(isLinearized, b->R.isLinearized, (size_t)b->nR*sizeof(int32_t), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+  if (res_toZero2) CK(cudaMemcpyAsync(res_toZero2, b->R.res_toZero, (size_t)b->nR*2*sizeof(float), cudaMemcpyDeviceToHost, c->st_ba));
+  if (isLinearized) CK(cudaMemcpyAsync(isLinearized, b->R.isLinearized, (size_t)b->nR*sizeof(int32_t), cudaMemcpyDeviceToHost, c->st_ba));
+  CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK;
 }
-int sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS) {
+int sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int N = kCP + 6*b->nF;
-#define DN(dst, src, cnt) do { if (dst) CK(cudaMemcpyAsync(dst, b->hdr->src, (size_t)(cnt)*sizeof(double), cudaMemcpyDeviceToHost, c->st)); } while (0)
+#define DN(dst, src, cnt) do { if (dst) CK(cudaMemcpyAsync(dst, b->hdr->src, (size_t)(cnt)*sizeof(double), cudaMemcpyDeviceToHost, c->st_ba)); } while (0)
   DN(HA, HA, N*N); DN(bA, bA, N); DN(Hsc, Hsc, N*N); DN(bsc, bsc, N); DN(lastHS, lastHS, N*N); DN(lastbS, lastbS, N);
 #undef DN
-  CK(cudaStreamSynchronize(c->st)); return SDV_OK;
+  CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK;
 }
-int sdv_ba_get_precalc(sdv_ctx* c, int host, int target, float out27[27], double adHost36[36], double adTarget36[36], float adHTdelta6[6]) {
+int sdv_ba_get_precalc(sdv_ctx* c, int host, int target, float out27[27], double adHost36[36], double adTarget36[36], float adHTdelta6[6]) { SDV_GUARD_BA(c);
   if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; const int nF = b->nF;
   if (host < 0 || target < 0 || host >= nF || target >= nF) return SDV_ERR_ARG;
   PrecalcDev p; CK(cudaMemcpy(&p, &b->hdr->precalc[host*nF+target], sizeof(p), cudaMemcpyDeviceToHost));

@@ -12,7 +12,7 @@ using namespace sdv;
 
 namespace sdv {
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...) {
-  if (c) { va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof(c->err), fmt, ap); va_end(ap); }
+  if (c) { std::lock_guard<std::mutex> lk(c->mu_err); va_list ap; va_start(ap, fmt); vsnprintf(c->err, sizeof(c->err), fmt, ap); va_end(ap); }
   return code;
 }
 }
@@ -50,7 +50,7 @@ static void make_geom(sdv_ctx* c, const sdv_calib* K) {   // CoarseTracker::make
 
 // CoarseTracker::makeK(HCalib) / the CalibHessian the Reprojector reads (FullSystem::optimize moves the intrinsics at every keyframe): new K for every later call.
 // Stream-ordered after the work already enqueued on the compute stream.
-int sdv_set_calib(sdv_ctx* c, const sdv_calib* K) {
+int sdv_set_calib(sdv_ctx* c, const sdv_calib* K) { SDV_GUARD_TRK(c);
   if (!c || !K) return SDV_ERR_ARG;
   if (!(K->fx > 0 && K->fy > 0)) return ctx_fail(c, SDV_ERR_ARG, "sdv_set_calib: focal lengths must be positive");
   CK(cudaSetDevice(c->device));
@@ -81,12 +81,12 @@ static int create_impl(sdv_ctx* c, const sdv_calib* K, int w, int h, int levels,
   c->set = s; c->device = device; c->w = w; c->h = h; c->levels = levels;
   CK(cudaSetDevice(device));
   CK(kernels_init_device()); CK(refine_init_device());      // per-device function attributes (opt-in shared memory, cluster sizes)
-  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_ba, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&c->st_cp, cudaStreamNonBlocking));
   for (int i=0;i<sdv_ctx::kIngRing;i++) CK(cudaEventCreateWithFlags(&c->ev_ing[i], cudaEventDisableTiming)); for (int i=0;i<2;i++) CK(cudaEventCreateWithFlags(&c->ev_cp[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming)); c->ingest_pending = false; c->launches = 0;
   for (int i=0;i<2;i++) { c->pyr_batch_dev[i] = nullptr; c->pyr_batch_host[i] = nullptr; }
-  CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1)); CK(cudaEventCreate(&c->ba_ev0)); CK(cudaEventCreate(&c->ba_ev1)); CK(cudaEventCreateWithFlags(&c->ev_xdom, cudaEventDisableTiming));
   memset(&c->tc, 0, sizeof(c->tc));
   c->tc.levels = levels; c->tc.huberTH = s.huberTH; c->tc.coarseCutoffTH = s.coarseCutoffTH;
   c->tc.affineOptModeA = s.affineOptModeA; c->tc.affineOptModeB = s.affineOptModeB;
@@ -153,13 +153,14 @@ void sdv_destroy(sdv_ctx* c) {
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);
   ba_destroy(c);
+  if (c->ba_ev0) cudaEventDestroy(c->ba_ev0); if (c->ba_ev1) cudaEventDestroy(c->ba_ev1); if (c->ev_xdom) cudaEventDestroy(c->ev_xdom); if (c->st_ba) cudaStreamDestroy(c->st_ba);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->ev_in) cudaEventDestroy(c->ev_in); if (c->st) cudaStreamDestroy(c->st); if (c->st_in) cudaStreamDestroy(c->st_in);
   cudaGetLastError();                                      // a partially built context may have produced benign errors above: do not leave them sticky
   delete c;
 }
 
-int sdv_sync(sdv_ctx* c) { if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st_cp)); CK(cudaStreamSynchronize(c->st_in)); CK(cudaStreamSynchronize(c->st)); return SDV_OK; }
-long long sdv_launch_count(sdv_ctx* c) { return c ? c->launches : 0; }
+int sdv_sync(sdv_ctx* c) { SDV_GUARD_TRK(c); if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st_cp)); CK(cudaStreamSynchronize(c->st_in)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK; }
+long long sdv_launch_count(sdv_ctx* c) { return c ? c->launches.load() : 0LL; }
 int sdv_track_job_bytes(void) { return (int)sizeof(TrackJob); }
 float sdv_last_kernel_ms(sdv_ctx* c) { return c ? c->last_ms : 0.f; }
 
@@ -264,14 +265,14 @@ int ensure_lvl0(sdv_ctx* c, FrameDev& f) {        // FrameHessian::dI of a keyfr
 }
 extern "C" {
 
-int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs, const float* exposures) {
+int sdv_frame_upload_batch(sdv_ctx* c, int n, const uint64_t* frames, const float* const* imgs, const float* exposures) { SDV_GUARD_TRK(c);
   return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 0);
 }
-int sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs, const float* exposures) {
+int sdv_frame_upload_batch_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* imgs, const float* exposures) { SDV_GUARD_TRK(c);
   return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(imgs), exposures, 1);
 }
 // Undistort (util/Undistort.cpp) as data: the tables the reference builds once per calibration file, kept on the device for the raw-image ingest
-int sdv_set_undistort(sdv_ctx* c, int w_org, int h_org, const float* remapX, const float* remapY, float factor, const float* G256, const float* vignette_inv) {
+int sdv_set_undistort(sdv_ctx* c, int w_org, int h_org, const float* remapX, const float* remapY, float factor, const float* G256, const float* vignette_inv) { SDV_GUARD_TRK(c);
   if (!c || w_org < 2 || h_org < 2 || !remapX || !remapY) return SDV_ERR_ARG;
   if (vignette_inv && !G256) return ctx_fail(c, SDV_ERR_ARG, "a vignette map needs a response function (PhotometricUndistorter::processFrame applies it to G[v] only)");
   CK(cudaSetDevice(c->device));
@@ -294,23 +295,23 @@ int sdv_set_undistort(sdv_ctx* c, int w_org, int h_org, const float* remapX, con
   c->und.wOrg = w_org; c->und.hOrg = h_org; c->und.factor = factor; c->has_und = true;
   return SDV_OK;
 }
-int sdv_frame_upload_batch_raw_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* raw_imgs, const float* exposures) {
+int sdv_frame_upload_batch_raw_u8(sdv_ctx* c, int n, const uint64_t* frames, const uint8_t* const* raw_imgs, const float* exposures) { SDV_GUARD_TRK(c);
   return frame_ingest(c, n, frames, reinterpret_cast<const void* const*>(raw_imgs), exposures, 8);
 }
-int sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int fmt, const float* exposures) {
+int sdv_frame_build_batch_dev(sdv_ctx* c, int n, const uint64_t* frames, const void* const* imgs_dev, int fmt, const float* exposures) { SDV_GUARD_TRK(c);
   if (fmt < 0 || fmt > 2) return SDV_ERR_ARG;
   return frame_ingest(c, n, frames, imgs_dev, exposures, 2 | (fmt == 1 ? 1 : 0) | (fmt == 2 ? 4 : 0));
 }
-int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposure) {
+int sdv_frame_upload(sdv_ctx* c, uint64_t frame, const float* img, float exposure) { SDV_GUARD_TRK(c);
   const float* imgs[1] = {img}; return sdv_frame_upload_batch(c, 1, &frame, imgs, &exposure);
 }
-int sdv_frame_release(sdv_ctx* c, uint64_t frame) {
+int sdv_frame_release(sdv_ctx* c, uint64_t frame) { SDV_GUARD_TRK(c);
   if (!c) return SDV_ERR_ARG;
   auto it = c->frame_index.find(frame); if (it == c->frame_index.end()) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
   if (frame_pinned(c, frame)) return ctx_fail(c, SDV_ERR_STATE, "frame %llu is referenced by a resident BA window / map slot: replace or clear that window / map first", (unsigned long long)frame);
   FrameDev& f = c->frames[it->second]; f.used = false; frame_drop_lvl0(c, f); f.adopted = false; f.I0 = f.I0_own; c->frame_index.erase(it); return SDV_OK;
 }
-int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out) {
+int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, float* abs_out) { SDV_GUARD_TRK(c);
   if (!c || lvl < 0 || lvl >= c->levels) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   FrameDev* f = find_frame(c, frame); if (!f) return ctx_fail(c, SDV_ERR_NOFRAME, "unknown frame %llu", (unsigned long long)frame);
@@ -329,7 +330,7 @@ int sdv_frame_download(sdv_ctx* c, uint64_t frame, int lvl, float* dI3_out, floa
 
 // ------------------------------------------------------------------------------------------------ tracker reference
 int sdv_tracker_set_cloud(sdv_ctx* c, int slot, uint64_t ref_frame, int lvl, int n, const float* u, const float* v,
-                          const float* idepth, const float* color, double ref_a, double ref_b) {
+                          const float* idepth, const float* color, double ref_a, double ref_b) { SDV_GUARD_TRK(c);
   if (!c || slot < 0 || slot >= (int)c->slots.size() || lvl < 0 || lvl >= c->levels || n < 0) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   TrackerSlot& t = c->slots[slot];
@@ -345,7 +346,7 @@ int sdv_tracker_set_cloud(sdv_ctx* c, int slot, uint64_t ref_frame, int lvl, int
   return SDV_OK;
 }
 
-int sdv_tracker_get_cloud(sdv_ctx* c, int slot, int lvl, int* n_out, float* u, float* v, float* idepth, float* color) {
+int sdv_tracker_get_cloud(sdv_ctx* c, int slot, int lvl, int* n_out, float* u, float* v, float* idepth, float* color) { SDV_GUARD_TRK(c);
   if (!c || slot < 0 || slot >= (int)c->slots.size() || lvl < 0 || lvl >= c->levels || !n_out) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   TrackerSlot& t = c->slots[slot]; int n = t.npts[lvl]; *n_out = n;
@@ -357,7 +358,7 @@ int sdv_tracker_get_cloud(sdv_ctx* c, int slot, int lvl, int* n_out, float* u, f
 }
 
 int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const float* pts4, const int32_t* round_half,
-                        float /*unused*/, double ref_a, double ref_b) {
+                        float /*unused*/, double ref_a, double ref_b) { SDV_GUARD_TRK(c);
   if (!c || slot < 0 || slot >= (int)c->slots.size() || n < 0 || (n > 0 && (!pts4 || !round_half))) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   TrackerSlot& t = c->slots[slot];
@@ -407,7 +408,7 @@ int sdv_tracker_set_ref(sdv_ctx* c, int slot, uint64_t ref_frame, int n, const f
 }
 
 // ------------------------------------------------------------------------------------------------ calcRes / calcGSSSE
-int sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, const double T[7], double a, double b, float cutoffTH, double rs_out[6]) {
+int sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, const double T[7], double a, double b, float cutoffTH, double rs_out[6]) { SDV_GUARD_TRK(c);
   if (!c || slot < 0 || slot >= (int)c->slots.size() || lvl < 0 || lvl >= c->levels || !T || !rs_out) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   TrackerSlot& t = c->slots[slot];
@@ -426,7 +427,7 @@ int sdv_tracker_calc_res(sdv_ctx* c, int slot, uint64_t new_frame, int lvl, cons
   finalize_res(t.totals, rs_out);
   return SDV_OK;
 }
-int sdv_tracker_calc_gs(sdv_ctx* c, int slot, int /*lvl*/, double H[64], double b[8]) {
+int sdv_tracker_calc_gs(sdv_ctx* c, int slot, int /*lvl*/, double H[64], double b[8]) { SDV_GUARD_TRK(c);
   if (!c || slot < 0 || slot >= (int)c->slots.size() || !H || !b) return SDV_ERR_ARG;
   TrackerSlot& t = c->slots[slot];
   if (!t.has_totals) return ctx_fail(c, SDV_ERR_STATE, "calc_gs before calc_res on slot %d", slot);
@@ -436,7 +437,7 @@ int sdv_tracker_calc_gs(sdv_ctx* c, int slot, int /*lvl*/, double H[64], double 
 
 // ------------------------------------------------------------------------------------------------ trackNewestCoarse
 int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* new_frames, double* T_io, double* ab_io, int coarsest,
-                            const double* minRes, double* lastRes, double* flow, int32_t* good, sdv_track_stats* stats) {
+                            const double* minRes, double* lastRes, double* flow, int32_t* good, sdv_track_stats* stats) { SDV_GUARD_TRK(c);
   if (!c || n <= 0 || !slots || !new_frames || !T_io || !ab_io || coarsest < 0 || coarsest >= c->levels || coarsest >= 5) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device));
   if (n > c->jobs_cap) {
@@ -480,7 +481,7 @@ int sdv_tracker_track_batch(sdv_ctx* c, int n, const int32_t* slots, const uint6
   return SDV_OK;
 }
 int sdv_tracker_track(sdv_ctx* c, int slot, uint64_t new_frame, double T_io[7], double ab_io[2], int coarsest, const double minRes[5],
-                      double lastRes[5], double flow[3], int* good, sdv_track_stats* stats) {
+                      double lastRes[5], double flow[3], int* good, sdv_track_stats* stats) { SDV_GUARD_TRK(c);
   int32_t s = slot, g = 0;
   int rc = sdv_tracker_track_batch(c, 1, &s, &new_frame, T_io, ab_io, coarsest, minRes, lastRes, flow, &g, stats);
   if (good) *good = g; return rc;

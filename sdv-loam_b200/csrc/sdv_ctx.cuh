@@ -2,6 +2,8 @@
 #pragma once
 #include <vector>
 #include <unordered_map>
+#include <mutex>
+#include <atomic>
 #include "sdv_kernels.cuh"
 #include "../../include/sdv_b200.h"
 
@@ -27,7 +29,12 @@ struct RpState;                           // sdv_reproject.cu
 } // namespace sdv
 
 struct sdv_ctx {
-  int device; cudaStream_t st, st_in, st_cp; cudaEvent_t ev0, ev1, ev_in; bool ingest_pending; long long launches;
+  // Two call domains, as in the reference (FullSystem::trackMutex / mapMutex): tracker-slot, frame, map and policy entries run under mu_trk on stream `st`;
+  // back-end (sdv_ba_*) entries run under mu_ba on stream `st_ba`.  A tracking thread and a mapping thread may therefore use ONE context concurrently.
+  // Back-end entries that touch the frame table (set_window, marginalize_frame, clear) take mu_trk as well, always after mu_ba (tracker entries never take mu_ba).
+  std::recursive_mutex mu_trk, mu_ba; std::mutex mu_err;
+  int device; cudaStream_t st, st_in, st_cp, st_ba; cudaEvent_t ev0, ev1, ev_in, ba_ev0, ba_ev1, ev_xdom; bool ingest_pending; std::atomic<long long> launches;
+  float ba_last_ms = 0.f;
   // ingest pipeline: H2D copies on st_cp, pyramids on st_in, one completion event per ingest call (ring); a frame remembers the ingest that built it
   static constexpr int kIngRing = 8; cudaEvent_t ev_ing[kIngRing], ev_cp[2]; long long ingest_seq = 0, seq_waited = 0;
   int w, h, levels; sdv_settings set;
@@ -70,3 +77,6 @@ inline bool frame_pinned(const sdv_ctx* c, uint64_t id) { return c->pins.find(id
 int  join_ingest(sdv_ctx* c);                  // compute stream waits for every ingest enqueued so far
 int  join_ingest_upto(sdv_ctx* c, long long seq);   // ... for ingest calls <= seq only (frames carry their ingest_seq)
 }
+// entry-point guards (a NULL context falls through to the entry's own argument check)
+#define SDV_GUARD_TRK(c) std::unique_lock<std::recursive_mutex> lk_trk_; if (c) lk_trk_ = std::unique_lock<std::recursive_mutex>((c)->mu_trk)
+#define SDV_GUARD_BA(c)  std::unique_lock<std::recursive_mutex> lk_ba_;  if (c) lk_ba_  = std::unique_lock<std::recursive_mutex>((c)->mu_ba)

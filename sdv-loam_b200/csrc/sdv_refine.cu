@@ -218,7 +218,7 @@ static int refine_reserve(sdv_ctx* c, size_t bytes) {
 extern "C" {
 
 int sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_begin, const sdv_overlap_pt* pts, const int32_t* host_begin, const double* host_T7,
-                                  double* curToWorld_io, float* res_out, int32_t* iterations, int32_t* accepts) {
+                                  double* curToWorld_io, float* res_out, int32_t* iterations, int32_t* accepts) { SDV_GUARD_TRK(c);
   if (!c || n_jobs <= 0 || !pt_begin || !host_begin || !host_T7 || !curToWorld_io) return SDV_ERR_ARG;
   const int nP = pt_begin[n_jobs], nH = host_begin[n_jobs];
   if (pt_begin[0] != 0 || host_begin[0] != 0 || nP < 0 || nH <= 0 || (nP > 0 && !pts)) return SDV_ERR_ARG;   // both CSRs start at 0: nothing is indexed below it
@@ -251,7 +251,7 @@ int sdv_tracker_struct_pose_batch(sdv_ctx* c, int n_jobs, const int32_t* pt_begi
   return SDV_OK;
 }
 
-int sdv_tracker_struct_pose(sdv_ctx* c, int n, const sdv_overlap_pt* pts, int nH, const double* host_T7, double curToWorld_io[7], float* res_out, int* iterations, int* accepts) {
+int sdv_tracker_struct_pose(sdv_ctx* c, int n, const sdv_overlap_pt* pts, int nH, const double* host_T7, double curToWorld_io[7], float* res_out, int* iterations, int* accepts) { SDV_GUARD_TRK(c);
   int32_t pb[2] = {0, n}, hbeg[2] = {0, nH}, it = 0, ac = 0;
   int rc = sdv_tracker_struct_pose_batch(c, 1, pb, pts, hbeg, host_T7, curToWorld_io, res_out, &it, &ac);
   if (iterations) *iterations = it; if (accepts) *accepts = ac; return rc;

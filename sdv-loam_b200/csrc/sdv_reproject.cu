@@ -308,11 +308,11 @@ static void rp_const(sdv_ctx* c, RpState* st) {
 
 extern "C" {
 
-int sdv_reproject_grid(sdv_ctx* c, int* n_cols, int* n_rows) {
+int sdv_reproject_grid(sdv_ctx* c, int* n_cols, int* n_rows) { SDV_GUARD_TRK(c);
   if (!c) return SDV_ERR_ARG; if (n_cols) *n_cols = (c->w + kRpCell - 1)/kRpCell; if (n_rows) *n_rows = (c->h + kRpCell - 1)/kRpCell; return SDV_OK;
 }
 
-int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const double* host_T7, const double* host_ab, int nP, const sdv_map_pt* pts) {
+int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const double* host_T7, const double* host_ab, int nP, const sdv_map_pt* pts) { SDV_GUARD_TRK(c);
   if (!c || nH < 1 || nH > kRpMaxHosts || !host_frames || !host_T7 || nP < 0 || nP >= (1 << 27) || (nP > 0 && !pts)) return SDV_ERR_ARG;   // point index packs into 27 bits of the sort key
   CK(cudaSetDevice(c->device)); RpState* st = rp_state(c);
   if (slot < 0 || slot >= (int)st->maps.size()) return SDV_ERR_ARG;
@@ -335,7 +335,7 @@ int sdv_map_set(sdv_ctx* c, int slot, int nH, const uint64_t* host_frames, const
   return SDV_OK;
 }
 
-int sdv_map_clear(sdv_ctx* c, int slot) {
+int sdv_map_clear(sdv_ctx* c, int slot) { SDV_GUARD_TRK(c);
   if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); RpState* st = rp_state(c);
   if (slot < 0 || slot >= (int)st->maps.size()) return SDV_ERR_ARG;
   MapSlot& m = st->maps[slot]; if (!m.set) return SDV_OK;
@@ -406,7 +406,7 @@ static int rp_launch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_
 
 int sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, const double* cur_T7, const double* cur_ab,
                             const int32_t* cur_kf_index, const int32_t* only_host, const int32_t* backup, const int32_t* cell_order, int max_matches,
-                            int32_t* n_out, int32_t* out_pt, double* out_px) {
+                            int32_t* n_out, int32_t* out_pt, double* out_px) { SDV_GUARD_TRK(c);
   if (!c || n_jobs <= 0 || !slots || !cur_frames || !cur_T7 || !n_out || !out_pt || !out_px) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device)); RpRun R; { int rc = rp_launch(c, n_jobs, slots, cur_frames, cur_T7, cur_ab, cur_kf_index, only_host, backup, R); if (rc) return rc; }
   const RpConst& C = c->rp->C; cudaStream_t s = c->st; const long long nc = R.nc;
@@ -428,7 +428,7 @@ int sdv_reproject_map_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const 
 }
 
 int sdv_tracker_refine_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, const uint64_t* cur_frames, double* curToWorld_io, const double* cur_ab,
-                             const int32_t* cell_order, int max_matches, int32_t* n_matches, float* res, int32_t* iterations, int32_t* accepts) {
+                             const int32_t* cell_order, int max_matches, int32_t* n_matches, float* res, int32_t* iterations, int32_t* accepts) { SDV_GUARD_TRK(c);
   if (!c || n_jobs <= 0 || !slots || !cur_frames || !curToWorld_io) return SDV_ERR_ARG;
   CK(cudaSetDevice(c->device)); RpRun R; { int rc = rp_launch(c, n_jobs, slots, cur_frames, curToWorld_io, cur_ab, nullptr, nullptr, nullptr, R); if (rc) return rc; }
   const RpConst& C = c->rp->C; cudaStream_t s = c->st;

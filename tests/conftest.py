@@ -71,7 +71,7 @@ def render_sequence(n, seed, K, wh, beams=64, step=1.0, gain_jitter=0.0, bias_ji
     """synth.Sequence(...) with the frames rendered by a process pool (3 s per KITTI-size frame on one core): identical output, frame by frame."""
     import sdv_loam_b200  # noqa: F401
     from sdv_loam_b200 import synth
-    if n < 12:
+    if n * wh[0] * wh[1] < 6 * 1200 * 360:                                # a few KITTI-size frames: not worth a pool
         return synth.Sequence(n, seed=seed, K=K, wh=wh, beams=beams, step=step, gain_jitter=gain_jitter, bias_jitter=bias_jitter, noise=noise)
     import multiprocessing as mp
     seq = synth.Sequence.__new__(synth.Sequence)

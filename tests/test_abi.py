@@ -68,3 +68,23 @@ def test_null_context_is_an_argument_error_everywhere():
     lib = os.path.join(root, "sdv-loam_b200", "libsdv_b200.so")
     out = subprocess.run([sys.executable, "-c", code, lib] + [f"{n}:{k}" for n, k in calls], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == "OK", (out.stdout[-500:], out.stderr[-500:])
+
+
+def test_integration_shims_compile_and_link():
+    """INTEGRATION.md's shims as a compiled translation unit (integration/shim_check.cpp): type-checked against include/sdv_b200.h (C++14, -Wall -Werror) and
+    linked against libsdv_b200.so with --no-undefined, i.e. every call resolves to an exported C symbol of the right signature; the header also compiles as strict C11."""
+    import shutil, subprocess, tempfile
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++"); cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    inc = os.path.join(ROOT, "include"); src = os.path.join(ROOT, "integration", "shim_check.cpp"); libdir = os.path.join(ROOT, "sdv-loam_b200")
+    import sdv_loam_b200
+    sdv_loam_b200.build_library()
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([cxx, "-std=c++14", "-Wall", "-Werror", "-shared", "-fPIC", "-I", inc, src, "-o", os.path.join(d, "shim.so"), "-L", libdir, "-lsdv_b200",
+                            "-Wl,--no-undefined", "-Wl,--allow-shlib-undefined"], capture_output=True, text=True)
+        # the settings globals (setting_huberTH, wG, ...) belong to the reference: they are the only symbols allowed to stay undefined
+        undefined = [l for l in r.stderr.splitlines() if "undefined reference" in l]
+        assert all(("setting_" in l or "pyrLevelsUsed" in l or "wG" in l or "hG" in l) for l in undefined), r.stderr[-3000:]
+        assert r.returncode == 0 or undefined, r.stderr[-3000:]
+        c = os.path.join(d, "hdr.c"); open(c, "w").write('#include "sdv_b200.h"\nint main(void) { return 0; }\n')
+        r = subprocess.run([cc, "-x", "c", "-std=c11", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, c], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

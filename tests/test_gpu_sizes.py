@@ -1,0 +1,146 @@
+"""GPU parity at the BASELINE.json sizes other than KITTI (configs[3] KITTI-360 1408x376 -> 1400x360, configs[4] S-STRESS 1920x1200 with 5 pyramid
+levels, 32 768 active points and an 8-keyframe window): the tracker step and LM, the back-end step by step and as a whole, reprojectMap + refinement —
+the same assertions as the KITTI-size tests in test_gpu_tracker.py / test_gpu_ba.py / test_gpu_reproject.py, through the C-ABI against the oracle."""
+import numpy as np
+import pytest
+import orc
+from conftest import cached_sequence
+
+pytestmark = pytest.mark.gpu
+ID7 = np.array([1, 0, 0, 0, 0, 0, 0.0])
+SIZES = {
+    # K of KITTI-360 as the reference's Undistort rectifies calib/kitti_360.txt (tests/test_undistort.py); 64-beam cloud
+    "kitti360": dict(K=(549.4873046875, 529.0698852539062, 678.1814575195312, 228.59402465820312), wh=(1400, 360), levels=4, beams=64, n_track=2000, kfs=7, n_per_frame=300, seed=4000),
+    # S-STRESS: 128-beam cloud, 32 768 tracker points, 8 keyframes x 4 096 window points
+    "stress": dict(K=(1100.0, 1100.0, 959.5, 599.5), wh=(1920, 1200), levels=5, beams=128, n_track=32768, kfs=8, n_per_frame=4096, seed=5000),
+}
+
+
+def _mods():
+    import sdv_loam_b200  # noqa
+    from sdv_loam_b200 import api, synth
+    return api, synth
+
+
+def _seq(size):
+    S = SIZES[size]
+    return S, cached_sequence(S["kfs"] + 1, S["seed"], S["K"], S["wh"], beams=S["beams"])
+
+
+def _tracker_pair(api, synth, S, seq, **ctxkw):
+    w, h = S["wh"]; L = api.pyr_levels(w, h); assert L == S["levels"]
+    pts = synth.select_points(seq.images[0], seq.clouds[0], S["n_track"]); p4 = np.concatenate([pts, np.full((len(pts), 1), 1e-3, np.float32)], 1).astype(np.float32)
+    rh = np.zeros(len(p4), np.int32)
+    ctx = api.Context(S["K"], w, h, max_frames=4, **ctxkw); ctx.makeImages(0, seq.images[0]); ctx.makeImages(1, seq.images[1])
+    tr = api.CoarseTracker(ctx, 0); tr.setCoarseTrackingRef(0, p4, rh, 0.0, 1.0)
+    f0, f1 = orc.Frame(seq.images[0], L), orc.Frame(seq.images[1], L)
+    otr = orc.CoarseTracker(w, h, L, S["K"]); otr.setCoarseTrackingRef(f0, p4, rh, 0.0, 1.0)
+    return ctx, tr, otr, f1, L, len(p4)
+
+
+@pytest.mark.parametrize("size", sorted(SIZES))
+def test_cloud_calcres_gs_vs_oracle(size):
+    api, synth = _mods(); S, seq = _seq(size)
+    ctx, tr, otr, f1, L, n = _tracker_pair(api, synth, S, seq)
+    assert n >= 0.9 * S["n_track"], n                                                      # the stress cloud really has ~32k splats
+    Tgt = orc.se3_from_rt(*synth.rel_pose(seq.R[0], seq.t[0], seq.R[1], seq.t[1]))
+    for l in range(L):
+        a, b = tr.cloud(l), otr.cloud(l)
+        assert len(a[0]) == len(b[0]) > 0 and all(np.array_equal(x, y) for x, y in zip(a, b)), l   # makeCoarseDepthL0: identical clouds on every level
+    for T in (ID7, orc.se3_mul(orc.se3_exp([0.01, 0.0, 0.02, 1e-3, -1e-3, 5e-4]), Tgt)):
+        for l in range(L):
+            for cutoff, (a, b) in ((20.0, (0.0, 0.0)), (40.0, (0.03, -2.0))):
+                ro = otr.calcRes(f1, l, T, a, b, cutoff); Ho, bo = otr.calcGSSSE(l, T, a, b)
+                rg = tr.calcRes(1, l, T, a, b, cutoff); Hg, bg = tr.calcGSSSE(l)
+                assert rg[1] == ro[1] and np.isclose(rg[5], ro[5], rtol=1e-6, equal_nan=True), (l, ro, rg)
+                # E: calcRes adds the per-point energies into ONE float (CoarseTracker.cpp:586-600).  Over 163 840 points of the stress cloud that sequential sum has lost
+                # 9.5e-5 of its value (reference/oracle 27 508 316 vs 27 510 918.4 for the same float terms summed in float64; the CUDA reduction gives 27 510 918):
+                # the bound below is the reference's own rounding loss, not a kernel tolerance.  achievedRes = sqrt(E/n) moves by half of it (< north_star's 1e-4).
+                assert np.isclose(rg[0], ro[0], rtol=2e-5 if size != "stress" else 2e-4) and np.allclose(rg[2:5], ro[2:5], rtol=1e-4, atol=1e-7)
+                assert np.linalg.norm(Hg - Ho) <= 2e-5 * np.linalg.norm(Ho) and np.linalg.norm(bg - bo) <= 2e-5 * np.linalg.norm(bo) + 1e-9
+    ctx.close()
+
+
+@pytest.mark.parametrize("cfg", [(128, 1), (256, 16)])
+@pytest.mark.parametrize("size", sorted(SIZES))
+def test_track_vs_oracle(size, cfg):
+    api, synth = _mods(); S, seq = _seq(size)
+    ctx, tr, otr, f1, L, n = _tracker_pair(api, synth, S, seq, track_threads=cfg[0], cluster_size=cfg[1])
+    Tgt = orc.se3_from_rt(*synth.rel_pose(seq.R[0], seq.t[0], seq.R[1], seq.t[1]))
+    for T0, ab0 in ((ID7, (0.0, 0.0)), (orc.se3_exp([0.05, 0.02, -0.8, 0.004, -0.006, 0.002]), (0.02, 1.0)), (orc.se3_mul(orc.se3_exp([0.04, -0.02, 0.05, 0.002, -0.002, 0.001]), Tgt), (0.0, 0.0))):
+        ro = otr.trackNewestCoarse(f1, T0, ab0, L - 1); rg = tr.trackNewestCoarse(1, T0, ab0)
+        assert rg["good"] == ro["good"]
+        assert np.array_equal(rg["iterations"], ro["iterations"]) and np.array_equal(rg["accepts"], ro["accepts"]) and np.array_equal(rg["evals"], ro["evals"]), (ro, rg)
+        assert np.abs(orc.se3_log(orc.se3_mul(rg["T"], orc.se3_inv(ro["T"])))).max() < 1e-5 and np.allclose(rg["ab"], ro["ab"], atol=1e-3)
+        assert np.allclose(rg["lastResiduals"], ro["lastResiduals"], rtol=1e-4, equal_nan=True)
+    err = orc.se3_log(orc.se3_mul(rg["T"], orc.se3_inv(Tgt)))
+    assert rg["good"] and np.linalg.norm(err[:3]) < 5e-3 and np.linalg.norm(err[3:]) < 5e-4            # from a constant-motion-like guess it lands on the synthetic ground truth
+    ctx.close()
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+@pytest.mark.parametrize("size", sorted(SIZES))
+def test_backend_stepwise_and_optimize(size):
+    """b1-b8 at size: precalc, linearizeAll, applyRes, energies, accumulate + solve (3 damping values), step; then FullSystem::optimize as a whole."""
+    api, synth = _mods(); S, seq = _seq(size); kfs = list(range(S["kfs"])); wh = S["wh"]; L = S["levels"]
+    win = synth.make_ba_window(seq, kfs, n_per_frame=S["n_per_frame"], seed=3, pose_noise=(0.005, 0.0003), match_noise=0.1, prior_scale=1e-3)
+    assert size != "stress" or (len(win["uv"]) >= 30000 and len(kfs) == 8)
+    frames = [orc.Frame(seq.images[k], L) for k in kfs]
+    ctx = api.Context(S["K"], wh[0], wh[1], max_frames=len(kfs) + 1)
+    for i, k in enumerate(kfs):
+        ctx.makeImages(500 + i, seq.images[k])
+    ids = [500 + i for i in range(len(kfs))]
+    ob = orc.BAWindow(win, frames); gb = api.EnergyFunctional(ctx, win, ids)
+    nF = len(kfs)
+    for h, t in ((0, nF - 1), (nF - 1, 0)):
+        po, pg = ob.precalc(h, t), gb.precalc(h, t)
+        assert all(_same(po[k], pg[k]) for k in po), (h, t)
+    ob.reset_oob(); gb.reset_oob()
+    assert ob.linearizeAll(False) == gb.linearizeAll(False)
+    ro, rg = ob.residuals(), gb.residuals()
+    assert _same(ro["new_state"], rg["new_state"]) and _same(ro["J"], rg["J"]) and _same(ro["energies"].astype(np.float32), rg["energies"])
+    assert _same(ob.frames()["frameEnergyTH"], gb.frames()["frameEnergyTH"]) and (ob.calcLEnergy(), ob.calcMEnergy()) == gb.energies()
+    ob.applyRes(); gb.applyRes(); ob.backupState(); gb.backupState()
+    for it, lam in ((0, 0.1), (2, 0.00625)):
+        HAo, bAo, Hsco, bsco = ob.accumulate(); xo, HSo, bSo = ob.solveSystem(it, lam)
+        xg, HSg, bSg, (HAg, bAg, Hscg, bscg) = gb.solveSystem(it, lam)
+        assert _same(HAo, HAg) and _same(bAo, bAg) and _same(Hsco, Hscg) and _same(bsco, bscg) and _same(HSo, HSg) and _same(bSo, bSg) and _same(xo, xg)
+        assert all(_same(ob.points()[k], gb.points()[k]) for k in ("HdiF", "bdSumF", "step"))
+    assert ob.doStepFromBackup(1.0) == gb.doStepFromBackup(1.0) and _same(ob.frames()["state"], gb.frames()["state"]) and _same(ob.points()["idepth"], gb.points()["idepth"])
+    ob.loadStateBackup(); gb.loadStateBackup()
+    # the whole optimisation on a fresh copy of the window
+    ob2 = orc.BAWindow(win, frames); gb2 = api.EnergyFunctional(ctx, win, ids)
+    r1, r2 = ob2.optimize(6), gb2.optimize(6)
+    assert (r1["iterations"], r1["accepts"]) == (r2["iterations"], r2["accepts"]) and r1["rmse"] == r2["rmse"]
+    fo, fg = ob2.frames(), gb2.frames()
+    assert _same(fo["T_eval"], fg["T_eval"]) and _same(fo["state"], fg["state"]) and _same(ob2.points()["idepth"], gb2.points()["idepth"])
+    so, sg = ob2.residuals(), gb2.residuals()
+    assert _same(so["state"], sg["state"]) and _same(so["toRemove"], sg["toRemove"])
+    ctx.close()
+
+
+@pytest.mark.parametrize("size", sorted(SIZES))
+def test_reproject_and_refine(size):
+    """a10/a11 at size: identical match sets / aligned pixels, fused reprojectMap + structPoseEstimation equals the oracle."""
+    api, synth = _mods(); S, seq = _seq(size); K, wh = S["K"], S["wh"]; w, h = wh; L = S["levels"]; nk = S["kfs"]; kfs = list(range(nk))
+    pts, hT, hab = synth.make_map(seq, kfs, n_per_frame=min(S["n_per_frame"], 600), seed=2, idepth_noise=0.01)
+    ctx = api.Context(K, w, h, max_frames=nk + 2)
+    for i in range(nk + 1):
+        ctx.makeImages(100 + i, seq.images[i])
+    frames = [orc.Frame(seq.images[i], L) for i in range(nk + 1)]
+    cur = np.concatenate([synth._quat_from_R(seq.R[nk]), seq.t[nk]]); noisy = cur.copy(); noisy[4:] += [0.02, -0.01, 0.03]
+    rp = api.Reprojector(ctx); rp.setMap(0, [100 + k for k in kfs], hT, hab, pts)
+    order = np.random.default_rng(9).permutation(rp.n_cells).astype(np.int32)
+    for T in (cur, noisy):
+        o = orc.reproject_map(w, h, L, K, frames[:nk], hT, hab, frames[nk], T, [0.0, 0.0], pts, cell_order=order, max_matches=400)
+        g = rp.reprojectMap(0, 100 + nk, T, [0.0, 0.0], cell_order=order, max_matches=400)
+        assert len(o[0]) > 50 and np.array_equal(o[0], g[0]) and np.array_equal(o[1], g[1]), (len(o[0]), len(g[0]))
+    r = rp.refineBatch([0], [100 + nk], noisy[None], cell_order=order, max_matches=400)
+    idx, px = orc.reproject_map(w, h, L, K, frames[:nk], hT, hab, frames[nk], noisy, [0.0, 0.0], pts, cell_order=order, max_matches=400)
+    p6 = np.stack([pts["u"][idx], pts["v"][idx], pts["idepth"][idx], pts["host"][idx].astype(np.float32), px[:, 0].astype(np.float32), px[:, 1].astype(np.float32)], 1).astype(np.float32)
+    so = orc.struct_pose(w, h, np.array(K, np.float32), hT, p6, noisy)
+    assert int(r["n_matches"][0]) == len(idx) and (int(r["iterations"][0]), int(r["accepts"][0])) == (so["iterations"], so["accepts"]) and np.abs(r["T"][0] - so["T"]).max() < 1e-6
+    ctx.close()
