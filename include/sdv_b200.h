@@ -210,6 +210,39 @@ long long sdv_launch_count(sdv_ctx* c);
 int  sdv_track_job_bytes(void);
 
 
+/* ---- immature points: candidate construction and epipolar tracing
+ *   ImmaturePoint::ImmaturePoint(int u, int v, FrameHessian* host, float type, CalibHessian*)               FullSystem/ImmaturePoint.cpp:8-36
+ *   ImmaturePointStatus ImmaturePoint::traceOn(FrameHessian* frame, const Mat33f& hostToFrame_KRKi, const Vec3f& hostToFrame_Kt,
+ *                                              const Vec2f& hostToFrame_affine, CalibHessian*, bool)           FullSystem/ImmaturePoint.cpp:50-352
+ *   called for every immature point of every active keyframe by FullSystem::traceNewCoarse                     FullSystem/FullSystem.cpp:519-552
+ * The record mirrors the members of ImmaturePoint the two functions read or write (ImmaturePoint.h:33-78); it stays with the caller (the reference keeps the
+ * points in host->immaturePoints), the device works on a copy per call.  lastTraceStatus: 0 GOOD, 1 OOB, 2 OUTLIER, 3 SKIPPED, 4 BADCONDITION, 5 UNINITIALIZED. */
+typedef struct {
+  float u, v, idepth_min, idepth_max;
+  float color[8], weights[8], gradH[4];           /* gradH: Mat22f row-major */
+  float energyTH, quality, lastTraceUV[2], lastTracePixelInterval;
+  int32_t lastTraceStatus;
+} sdv_immature_pt;
+/* constructor for n candidates at integer pixels uv[2n] of a resident keyframe (>= 3 px from the border, else SDV_ERR_ARG) */
+int  sdv_immature_init(sdv_ctx* c, uint64_t host_frame, int n, const int32_t* uv, sdv_immature_pt* out);
+/* traceOn for n_groups (host keyframe, traced frame) pairs in ONE launch: group g traces pts_io[pt_begin[g] .. pt_begin[g+1]) against frames[g] with
+ * KRKi9[9g..] = K R K^-1 (row-major), Kt3[3g..] = K t of hostToNew and aff2[2g..] = AffLight::fromToVecExposure(host, new) — what traceNewCoarse computes per host
+ * (:532-538).  Groups may belong to different sequences (batched mode).  pts_io is updated in place; status_out (n points) may be NULL. */
+int  sdv_immature_trace_batch(sdv_ctx* c, int n_groups, const uint64_t* frames, const int32_t* pt_begin, const float* KRKi9, const float* Kt3, const float* aff2,
+                              sdv_immature_pt* pts_io, int32_t* status_out);
+/* Activation — PointHessian* FullSystem::optimizeImmaturePoint(ImmaturePoint*, int minObs, ImmaturePointTemporaryResidual*)   FullSystemOptPoint.cpp:18-183
+ * over ImmaturePoint::linearizeResidual (ImmaturePoint.cpp:410-476): Gauss-Newton on the inverse depth of a candidate against every other keyframe of the window.
+ * Group g = the candidates pts[pt_begin[g] .. pt_begin[g+1]) of ONE host keyframe; its targets are entries tgt_begin[g] .. tgt_begin[g+1]) of target_frames / pre14
+ * (frameHessians without the host, window order; pre14 = host->targetPrecalc[target]: PRE_RTll[9] row-major, PRE_tTll[3], PRE_aff_mode[2]); calib6[6g..] = fxl fyl cxl cyl
+ * fxli fyli of the CalibHessian.  Outputs per candidate: status 0 = not well constrained (stays immature; the function's `return 0`), -1 = outlier / non-finite
+ * (deleted), 1 = activated with idepth_out (setIdepth/setIdepthZero) and res_state_out[k*res_stride + i] = final state of the temporary residual to target i
+ * (0 IN -> a PointFrameResidual is created, 1 OOB, 2 OUTLIER; -1 = unused).  The PointHessian / PointFrameResidual objects stay with the caller. */
+int  sdv_immature_optimize_batch(sdv_ctx* c, int n_groups, const int32_t* pt_begin, const int32_t* tgt_begin, const uint64_t* target_frames, const float* pre14, const float* calib6,
+                                 int min_obs, const sdv_immature_pt* pts, const uint8_t* is_from_sensor, int res_stride, int32_t* status_out, float* idepth_out, int32_t* res_state_out);
+
+/* frames + calibration + marginalisation prior:  EnergyFunctional::insertFrame :365-398, setAdjointsF :21-71, HM/bM :88-89.
+ * state10 / state_zero10 = FrameHessian::state / state_zero (Vec10: 6 pose, a, b, 2 unused; HessianBlocks.h:141-175),
+ * T_evalPT7 = worldToCam_evalPT, calib_value_scaled = CalibHessian::value_scaled {fx,fy,cx,cy}; HM (dim x dim, row-major), bM may be NULL. */
 /* =====================================================================================================================
  * Sliding-window back-end: EnergyFunctional + FullSystem::optimize on a FLATTENED window.
  * The reference's pointer graph (FrameHessian -> PointHessian -> PointFrameResidual and the EF* mirrors) stays on the host;
@@ -217,9 +250,6 @@ int  sdv_track_job_bytes(void);
  * host frame, EnergyFunctional.cpp:761-782), residuals grouped per point in residualsAll order (res_begin is the CSR row
  * pointer).  This is the makeIDX / insertFrame / insertPoint / insertResidual surface (EnergyFunctional.h:51-72) in one call.
  * ===================================================================================================================== */
-/* frames + calibration + marginalisation prior:  EnergyFunctional::insertFrame :365-398, setAdjointsF :21-71, HM/bM :88-89.
- * state10 / state_zero10 = FrameHessian::state / state_zero (Vec10: 6 pose, a, b, 2 unused; HessianBlocks.h:141-175),
- * T_evalPT7 = worldToCam_evalPT, calib_value_scaled = CalibHessian::value_scaled {fx,fy,cx,cy}; HM (dim x dim, row-major), bM may be NULL. */
 int  sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const double* T_evalPT7, const double* state10, const double* state_zero10,
                        const float* ab_exposure, const int32_t* frameID, const float* frameEnergyTH, const double calib_value_scaled[4],
                        const double* HM, const double* bM);

@@ -5,6 +5,7 @@
 // touch (FrameShell::id, PointHessian::{u,v,idepth,...}, SE3, AffLight, Vec5, ...) and then contains the shim bodies verbatim.  tests/test_abi.py compiles it
 // (g++ -std=c++14 -Wall -Werror -fsyntax-only) and links it against libsdv_b200.so with --no-undefined: every call in INTEGRATION.md is type-checked against
 // include/sdv_b200.h and resolves to an exported C symbol.  It is never executed.
+#include <cstddef>
 #include <cstdint>
 #include <utility>
 #include <vector>
@@ -182,11 +183,51 @@ struct FullSystem {
   }
 };
 
+// ------------------------------------------------------------------------------------------------ immature points: FullSystem::traceNewCoarse (FullSystem.cpp:519-552)
+struct Mat33f { float m[9]; }; struct Vec2f { float v[2]; };
+struct ImmaturePoint { sdv_immature_pt rec; FrameHessian* host; };            // the reference's members u,v,idepth_min/max,color,weights,gradH,energyTH,quality,lastTrace* in one record
+struct HostImmatures { FrameHessian* host; std::vector<ImmaturePoint*> immaturePoints; Mat33f KRKi; Vec3f Kt; Vec2f aff; };   // per host: what :532-538 computes
+int shim_makeNewTraces(FrameHessian* newFrame, const std::vector<int32_t>& uv /*2 per selected pixel (PixelSelector)*/, std::vector<ImmaturePoint*>& out) {
+  std::vector<sdv_immature_pt> rec(uv.size()/2);
+  int rc = sdv_immature_init(gpu, (uint64_t)newFrame->shell->id, (int)rec.size(), uv.data(), rec.data());   // ImmaturePoint::ImmaturePoint for every candidate (FullSystem.cpp:1273-1356)
+  for (std::size_t i = 0; i < rec.size() && rc == SDV_OK; i++) out.push_back(new ImmaturePoint{rec[i], newFrame});
+  return rc;
+}
+int shim_traceNewCoarse(FrameHessian* fh, std::vector<HostImmatures>& hosts) {
+  std::vector<uint64_t> frames; std::vector<int32_t> pt_begin{0}; std::vector<float> KRKi, Kt, aff; std::vector<sdv_immature_pt> pts;
+  for (HostImmatures& h : hosts) {
+    frames.push_back((uint64_t)fh->shell->id); KRKi.insert(KRKi.end(), h.KRKi.m, h.KRKi.m + 9); for (int i = 0; i < 3; i++) Kt.push_back((float)h.Kt[i]); aff.push_back(h.aff.v[0]); aff.push_back(h.aff.v[1]);
+    for (ImmaturePoint* ph : h.immaturePoints) pts.push_back(ph->rec);
+    pt_begin.push_back((int32_t)pts.size());
+  }
+  int rc = sdv_immature_trace_batch(gpu, (int)hosts.size(), frames.data(), pt_begin.data(), KRKi.data(), Kt.data(), aff.data(), pts.data(), nullptr);
+  std::size_t k = 0; for (HostImmatures& h : hosts) for (ImmaturePoint* ph : h.immaturePoints) ph->rec = pts[k++];       // lastTraceStatus etc. back into the graph
+  return rc;
+}
+
+// FullSystem::activatePointsMT -> optimizeImmaturePoint (FullSystem.cpp:569-723, FullSystemOptPoint.cpp:18-183): all candidates picked for activation, grouped by host
+struct ActivationGroup { FrameHessian* host; std::vector<ImmaturePoint*> toOptimize; std::vector<uint8_t> isFromSensor; std::vector<FrameHessian*> targets; std::vector<float> pre14; float calib6[6]; };
+int shim_activatePoints(std::vector<ActivationGroup>& groups, std::vector<int32_t>& status, std::vector<float>& idepth, std::vector<int32_t>& res_state, int res_stride) {
+  std::vector<int32_t> pt_begin{0}, tgt_begin{0}; std::vector<uint64_t> tf; std::vector<float> pre, cal; std::vector<sdv_immature_pt> pts; std::vector<uint8_t> fs;
+  for (ActivationGroup& g : groups) {
+    for (ImmaturePoint* ph : g.toOptimize) pts.push_back(ph->rec);
+    fs.insert(fs.end(), g.isFromSensor.begin(), g.isFromSensor.end());
+    for (FrameHessian* t : g.targets) tf.push_back((uint64_t)t->shell->id);
+    pre.insert(pre.end(), g.pre14.begin(), g.pre14.end()); cal.insert(cal.end(), g.calib6, g.calib6 + 6);
+    pt_begin.push_back((int32_t)pts.size()); tgt_begin.push_back((int32_t)tf.size());
+  }
+  status.resize(pts.size()); idepth.resize(pts.size()); res_state.resize(pts.size()*(std::size_t)res_stride);
+  return sdv_immature_optimize_batch(gpu, (int)groups.size(), pt_begin.data(), tgt_begin.data(), tf.data(), pre.data(), cal.data(), /*minObs*/1, pts.data(), fs.data(), res_stride,
+                                     status.data(), idepth.data(), res_state.data());     // status 1 -> new PointHessian(point) + PointFrameResidual per IN state, -1 -> delete, 0 -> keep immature
+}
+
 // referenced so that -Wunused does not hide a missing call path
 int shim_check_anchor(FullSystem& fs, FrameHessian* fh, CalibHessian& hc, const Undistort* u, const uint8_t* raw) {
   std::vector<int32_t> sel, st; Vec5 mr{}; SE3 T; AffLight a;
   int rc = shim_create(hc) | shim_set_undistort(u, nullptr, nullptr) | shim_ingest_raw(fh->shell, raw, 1.0f) | shim_makeK(&hc);
   fs.coarseTracker->setCoarseTrackingRef(fs.frameHessians); fs.coarseTracker->trackNewestCoarse(fh, T, a, 3, mr, nullptr);
+  std::vector<ImmaturePoint*> imm; std::vector<HostImmatures> hi; rc |= shim_makeNewTraces(fh, sel, imm) | shim_traceNewCoarse(fh, hi);
+  std::vector<ActivationGroup> ag; std::vector<float> idp; rc |= shim_activatePoints(ag, st, idp, sel, 7);
   fs.optimize(6); fs.set_map(0); fs.handover(sel, st); fs.trackNewCoarse(fh); fs.refine_only(fh); shim_frame_destructor(fh);
   return rc;
 }

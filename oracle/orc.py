@@ -374,3 +374,54 @@ class BAWindow:
     def __del__(self):
         if getattr(self, "p", None):
             self.L.orc_ba_destroy(self.p); self.p = None
+
+
+# ---------------------------------------------------------------------------------------------- immature points (orc_trace.cpp): ImmaturePoint ctor + traceOn
+IMM_DTYPE = np.dtype([("u", np.float32), ("v", np.float32), ("idepth_min", np.float32), ("idepth_max", np.float32), ("color", np.float32, 8), ("weights", np.float32, 8),
+                      ("gradH", np.float32, 4), ("energyTH", np.float32), ("quality", np.float32), ("lastTraceUV", np.float32, 2), ("lastTracePixelInterval", np.float32),
+                      ("lastTraceStatus", np.int32)])
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+
+
+def immature_init(host: "Frame", uv):
+    """ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:8-36) for integer pixels uv (n,2) of the host keyframe"""
+    L = lib(); L.orc_immature_init.argtypes = [C.c_void_p, C.c_int, _i32p, C.c_void_p]; L.orc_immature_bytes.restype = C.c_int
+    assert L.orc_immature_bytes() == IMM_DTYPE.itemsize
+    uv = np.ascontiguousarray(uv, np.int32).reshape(-1, 2); P = np.zeros(len(uv), IMM_DTYPE)
+    L.orc_immature_init(host.p, len(uv), uv, P.ctypes.data)
+    return P
+
+
+def immature_trace(frame: "Frame", pts, KRKi, Kt, aff):
+    """ImmaturePoint::traceOn (ImmaturePoint.cpp:50-352) of every candidate in pts (IMM_DTYPE, one host) against `frame`; updates pts in place, returns the statuses"""
+    L = lib(); L.orc_immature_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _i32p]
+    assert pts.dtype == IMM_DTYPE and pts.flags.c_contiguous
+    st = np.zeros(len(pts), np.int32)
+    L.orc_immature_trace(frame.p, len(pts), pts.ctypes.data, np.ascontiguousarray(KRKi, np.float32).reshape(-1), np.ascontiguousarray(Kt, np.float32), np.ascontiguousarray(aff, np.float32), st)
+    return st
+
+
+def trace_geometry(K4, host_c2w7, new_c2w7, host_exposure=1.0, new_exposure=1.0, host_ab=(0.0, 0.0), new_ab=(0.0, 0.0)):
+    """KRKi, Kt, aff of FullSystem::traceNewCoarse (FullSystem.cpp:525-538): hostToNew = new_worldToCam * host_camToWorld, floats as the reference casts them"""
+    fx, fy, cx, cy = [np.float32(x) for x in K4]
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    T = se3_mul(se3_inv(np.asarray(new_c2w7, np.float64)), np.asarray(host_c2w7, np.float64))
+    qw, qx, qy, qz = T[:4]
+    R = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)], [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                  [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]]).astype(np.float32)
+    Ki = np.linalg.inv(K.astype(np.float64)).astype(np.float32)
+    KRKi = (K @ R @ Ki).astype(np.float32); Kt = (K @ T[4:].astype(np.float32)).astype(np.float32)
+    a = np.exp(new_ab[0] - host_ab[0]) * new_exposure / host_exposure
+    return KRKi, Kt, np.array([a, new_ab[1] - a * host_ab[1]], np.float32)
+
+
+def immature_optimize(pts, is_from_sensor, target_frames, pre14, calib6, min_obs=1):
+    """FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:18-183) for candidates of ONE host against the target frames (window order without the host).
+    pre14 (nres,14): PRE_RTll, PRE_tTll, PRE_aff_mode of (host,target); calib6: fxl fyl cxl cyl fxli fyli.  Returns status (0 stay, -1 drop, 1 activate), idepth, res states."""
+    L = lib(); n = len(pts); nres = len(target_frames)
+    L.orc_immature_optimize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _f32p, _f32p, C.c_int, _i32p, _f32p, _i32p]
+    assert pts.dtype == IMM_DTYPE and pts.flags.c_contiguous
+    fs = np.ascontiguousarray(is_from_sensor, np.uint8); tf = (C.c_void_p * nres)(*[f.p for f in target_frames])
+    st = np.zeros(n, np.int32); idp = np.zeros(n, np.float32); rs = np.zeros((n, nres), np.int32)
+    L.orc_immature_optimize(n, pts.ctypes.data, fs.ctypes.data, nres, tf, np.ascontiguousarray(pre14, np.float32).reshape(-1), np.ascontiguousarray(calib6, np.float32), min_obs, st, idp, rs.reshape(-1))
+    return st, idp, rs

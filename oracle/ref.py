@@ -109,6 +109,13 @@ def lib():
         L.ref_sys_map.argtypes = [_vp, _i32p, _f64p, _f64p, _f32p, _f32p]
         L.ref_sys_get_track_result.argtypes = [_vp, C.c_int, _f64p]
         L.ref_reproject_map.argtypes = [C.c_int, C.POINTER(_vp), _f64p, _f64p, _vp, _f64p, _f64p, C.c_int, _f32p, C.c_uint, C.c_int, _i32p, _f64p]
+        L.ref_ba_immature_pre.argtypes = [_vp, C.c_int, _f32p, _f32p]
+        L.ref_ba_optimize_immature.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_float), _i32p]
+        L.ref_immature_create.argtypes = [_vp, C.c_int, C.c_int, C.c_float]; L.ref_immature_create.restype = _vp
+        L.ref_immature_destroy.argtypes = [_vp]; L.ref_immature_destroy.restype = None
+        L.ref_immature_get.argtypes = [_vp, _f32p, C.POINTER(C.c_int)]; L.ref_immature_get.restype = None
+        L.ref_immature_set_range.argtypes = [_vp, C.c_float, C.c_float, C.c_int]; L.ref_immature_set_range.restype = None
+        L.ref_immature_trace.argtypes = [_vp, _vp, _f32p, _f32p, _f32p]
         L.ref_undistort_create.argtypes = [C.c_char_p, _i32p, _i32p, _f64p]; L.ref_undistort_create.restype = _vp
         L.ref_undistort_destroy.argtypes = [_vp]; L.ref_undistort_destroy.restype = None
         L.ref_undistort_maps.argtypes = [_vp, _f32p, _f32p]; L.ref_undistort_maps.restype = None
@@ -287,6 +294,18 @@ class BAWindow:
         self.L.ref_ba_get_precalc(self.p, host, target, o, aH, aT, d)
         return dict(KRKi=o[:9].reshape(3, 3), Kt=o[9:12], R0=o[12:21].reshape(3, 3), t0=o[21:24], aff=o[24:26], b0=o[26], adHost=aH.reshape(6, 6), adTarget=aT.reshape(6, 6), adHTdelta=d)
 
+    def immature_pre(self, host, nF):
+        """(pre14 (nF-1,14): PRE_RTll, PRE_tTll, PRE_aff_mode of (host, every other frame in window order), calib6: fxl fyl cxl cyl fxli fyli)"""
+        pre = np.zeros((nF - 1, 14), np.float32); cal = np.zeros(6, np.float32); k = self.L.ref_ba_immature_pre(self.p, host, pre.reshape(-1), cal); assert k == nF - 1
+        return pre, cal
+
+    def optimizeImmaturePoint(self, host, u, v, idepth_min, idepth_max, is_from_sensor, min_obs, nF):
+        """FullSystem::optimizeImmaturePoint on a candidate constructed at (u,v) of keyframe `host` -> (status 0/-1/1, idepth, final temporary-residual states)"""
+        idp = C.c_float(0); rs = np.zeros(nF - 1, np.int32)
+        with _Quiet():
+            st = self.L.ref_ba_optimize_immature(self.p, host, int(u), int(v), idepth_min, idepth_max, int(is_from_sensor), min_obs, C.byref(idp), rs)
+        return st, idp.value, rs
+
     def optimize(self, its=6):
         with _Quiet():
             rmse = self.L.ref_ba_optimize(self.p, its)
@@ -428,5 +447,29 @@ class Undistort:
         try:
             if getattr(self, "p", None):
                 lib().ref_undistort_destroy(self.p); self.p = None
+        except Exception:
+            pass
+
+
+class ImmaturePoint:
+    """The reference's ImmaturePoint (FullSystem/ImmaturePoint.cpp): constructor on a host Frame, traceOn against another Frame."""
+
+    def __init__(self, host: "Frame", u: int, v: int, my_type: float = 1.0):
+        self.host = host; self.p = lib().ref_immature_create(host.p, int(u), int(v), my_type)
+
+    def record(self):
+        """(29 floats in the layout of orc.IMM_DTYPE's float fields, status)"""
+        o = np.zeros(29, np.float32); st = C.c_int(0); lib().ref_immature_get(self.p, o, C.byref(st)); return o, st.value
+
+    def set_range(self, idepth_min, idepth_max, status):
+        lib().ref_immature_set_range(self.p, idepth_min, idepth_max, status)
+
+    def traceOn(self, frame: "Frame", KRKi, Kt, aff) -> int:
+        return lib().ref_immature_trace(self.p, frame.p, np.ascontiguousarray(KRKi, np.float32).reshape(-1), np.ascontiguousarray(Kt, np.float32), np.ascontiguousarray(aff, np.float32))
+
+    def __del__(self):
+        try:
+            if getattr(self, "p", None):
+                lib().ref_immature_destroy(self.p); self.p = None
         except Exception:
             pass

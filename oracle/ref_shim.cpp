@@ -487,4 +487,51 @@ int ref_bench_ingest_track_loop(void* t, void* u, const unsigned char* const* ra
   return done;
 }
 
+// ---------------------------------------------------------------------------------------------- immature points (FullSystem/ImmaturePoint.cpp): constructor :8-36, traceOn :50-352
+// flat record = orc::ImmPt of oracle/orc_trace.cpp: u v idepth_min idepth_max color[8] weights[8] gradH[4] energyTH quality lastTraceUV[2] lastTracePixelInterval | status
+void* ref_immature_create(void* host, int u, int v, float type) { return new ImmaturePoint(u, v, ((RefFrame*)host)->fh, type, g_calib); }
+void  ref_immature_destroy(void* p) { delete (ImmaturePoint*)p; }
+void  ref_immature_get(void* pp, float* o29, int* status) {
+  ImmaturePoint* p = (ImmaturePoint*)pp; int k = 0;
+  o29[k++] = p->u; o29[k++] = p->v; o29[k++] = p->idepth_min; o29[k++] = p->idepth_max;
+  for (int i = 0; i < 8; i++) o29[k++] = p->color[i];
+  for (int i = 0; i < 8; i++) o29[k++] = p->weights[i];
+  o29[k++] = p->gradH(0, 0); o29[k++] = p->gradH(0, 1); o29[k++] = p->gradH(1, 0); o29[k++] = p->gradH(1, 1);
+  o29[k++] = p->energyTH; o29[k++] = p->quality; o29[k++] = p->lastTraceUV[0]; o29[k++] = p->lastTraceUV[1]; o29[k++] = p->lastTracePixelInterval;
+  *status = (int)p->lastTraceStatus;
+}
+void  ref_immature_set_range(void* pp, float idepth_min, float idepth_max, int status) {
+  ImmaturePoint* p = (ImmaturePoint*)pp; p->idepth_min = idepth_min; p->idepth_max = idepth_max; p->lastTraceStatus = (ImmaturePointStatus)status; }
+int   ref_immature_trace(void* pp, void* frame, const float* KRKi9, const float* Kt3, const float* aff2) {
+  Mat33f KRKi; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) KRKi(i, j) = KRKi9[i*3+j];
+  Vec3f Kt(Kt3[0], Kt3[1], Kt3[2]); Vec2f aff(aff2[0], aff2[1]);
+  return (int)((ImmaturePoint*)pp)->traceOn(((RefFrame*)frame)->fh, KRKi, Kt, aff, g_calib, false);
+}
+
+// ---- activation: FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:18-183) on the window of a RefBA (ref_ba_* above; ref_ba_init must have run: targetPrecalc)
+// pre14 out: for every target (frameHessians without the host, window order) PRE_RTll[9] PRE_tTll[3] PRE_aff_mode[2]; calib6: fxl fyl cxl cyl fxli fyli
+int ref_ba_immature_pre(void* p, int host, float* pre14, float* calib6) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs; FrameHessian* H = fs->frameHessians[host]; int k = 0;
+  for (FrameHessian* fh : fs->frameHessians) { if (fh == H) continue; const FrameFramePrecalc& c = H->targetPrecalc[fh->idx]; float* o = pre14 + 14*k++;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[i*3+j] = c.PRE_RTll(i, j);
+    for (int i = 0; i < 3; i++) o[9+i] = c.PRE_tTll[i]; o[12] = c.PRE_aff_mode[0]; o[13] = c.PRE_aff_mode[1]; }
+  CalibHessian& C = fs->Hcalib; calib6[0] = C.fxl(); calib6[1] = C.fyl(); calib6[2] = C.cxl(); calib6[3] = C.cyl(); calib6[4] = C.fxli(); calib6[5] = C.fyli();
+  return k;
+}
+// one candidate: constructed at (u,v) on the host (the constructor's colours / weights / energyTH), range and sensor flag set, then the reference's own function.
+// returns 0 / -1 / 1 like orc::optimizeImmaturePoint; res_state: final state_state of the temporary residuals (window order without the host)
+int ref_ba_optimize_immature(void* p, int host, int u, int v, float idepth_min, float idepth_max, int isFromSensor, int minObs, float* idepth_out, int* res_state) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs; FrameHessian* H = fs->frameHessians[host];
+  ImmaturePoint* ip = new ImmaturePoint(u, v, H, 1.0f, &fs->Hcalib); ip->idepth_min = idepth_min; ip->idepth_max = idepth_max; ip->isFromSensor = isFromSensor != 0; ip->idepth_fromSensor = 0;
+  ip->type = ImmaturePoint::CORNER; ip->score = 0; ip->idxInImmaturePoints = 0; ip->idepth_GT = 0; ip->lastTraceStatus = IPS_GOOD; ip->lastTraceUV = Vec2f(0, 0); ip->gradH_ev = Vec2f(0, 0);
+  int nres = (int)fs->frameHessians.size() - 1; std::vector<ImmaturePointTemporaryResidual> tr(nres);
+  PointHessian* ph = fs->optimizeImmaturePoint(ip, minObs, tr.data());
+  for (int i = 0; i < nres; i++) res_state[i] = (int)tr[i].state_state;
+  int rc;
+  if (ph == 0) rc = 0; else if (ph == (PointHessian*)((long)(-1))) rc = -1;
+  else { rc = 1; *idepth_out = ph->idepth; ph->release(); delete ph; }
+  delete ip;
+  return rc;
+}
+
 }  // extern "C"

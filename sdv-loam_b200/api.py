@@ -78,6 +78,9 @@ def _load():
     L.sdv_tracker_track.argtypes = [_vp, C.c_int, C.c_uint64, _f64p, _f64p, C.c_int, _f64p, _f64p, _f64p, C.POINTER(C.c_int), C.POINTER(sdv_track_stats)]
     L.sdv_tracker_track_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _f64p, _f64p, C.c_int, _vp, _f64p, _f64p, _i32p, C.POINTER(sdv_track_stats)]
     L.sdv_last_kernel_ms.argtypes = [_vp]; L.sdv_last_kernel_ms.restype = C.c_float
+    L.sdv_immature_init.argtypes = [_vp, C.c_uint64, C.c_int, _i32p, _vp]
+    L.sdv_immature_trace_batch.argtypes = [_vp, C.c_int, _u64p, _i32p, _f32p, _f32p, _f32p, _vp, _vp]
+    L.sdv_immature_optimize_batch.argtypes = [_vp, C.c_int, _i32p, _i32p, _u64p, _f32p, _f32p, C.c_int, _vp, _vp, C.c_int, _i32p, _f32p, _i32p]
     L.sdv_ba_last_kernel_ms.argtypes = [_vp]; L.sdv_ba_last_kernel_ms.restype = C.c_float
     return L
 
@@ -482,3 +485,41 @@ def optimize_batch(ctx: Context, windows, its: int = 6):
     rmse = np.zeros(n, np.float32); it = np.zeros(n, np.int32); acc = np.zeros(n, np.int32)
     ctx._ck(LIB.sdv_ba_optimize_batch(ctx.p, n, w, its, rmse, it, acc))
     return dict(rmse=rmse, iterations=it, accepts=acc, ms=float(LIB.sdv_ba_last_kernel_ms(ctx.p)))
+
+
+# ---------------------------------------------------------------------------------------------- immature points: ImmaturePoint ctor + traceOn (sdv_trace.cu)
+IMMATURE_PT_DTYPE = np.dtype([("u", np.float32), ("v", np.float32), ("idepth_min", np.float32), ("idepth_max", np.float32), ("color", np.float32, 8), ("weights", np.float32, 8),
+                              ("gradH", np.float32, 4), ("energyTH", np.float32), ("quality", np.float32), ("lastTraceUV", np.float32, 2), ("lastTracePixelInterval", np.float32),
+                              ("lastTraceStatus", np.int32)])
+IPS_GOOD, IPS_OOB, IPS_OUTLIER, IPS_SKIPPED, IPS_BADCONDITION, IPS_UNINITIALIZED = range(6)
+
+
+def immatureInit(ctx: Context, host_frame_id: int, uv):
+    """ImmaturePoint::ImmaturePoint (ImmaturePoint.cpp:8-36) for integer pixels uv (n,2) of a resident keyframe -> IMMATURE_PT_DTYPE array"""
+    uv = np.ascontiguousarray(uv, np.int32).reshape(-1, 2); P = np.zeros(len(uv), IMMATURE_PT_DTYPE)
+    ctx._ck(LIB.sdv_immature_init(ctx.p, host_frame_id, len(uv), uv.reshape(-1), P.ctypes.data))
+    return P
+
+
+def traceOnBatch(ctx: Context, frame_ids, pt_begin, KRKi, Kt, aff, pts):
+    """ImmaturePoint::traceOn for every candidate of every (host keyframe, traced frame) group — the loop of FullSystem::traceNewCoarse (FullSystem.cpp:519-552), batched.
+    pts (IMMATURE_PT_DTYPE) is updated in place; returns the statuses."""
+    assert pts.dtype == IMMATURE_PT_DTYPE and pts.flags.c_contiguous
+    ng = len(frame_ids); pb = np.ascontiguousarray(pt_begin, np.int32); assert len(pb) == ng + 1 and pb[-1] == len(pts)
+    st = np.zeros(len(pts), np.int32)
+    ctx._ck(LIB.sdv_immature_trace_batch(ctx.p, ng, np.ascontiguousarray(frame_ids, np.uint64), pb, np.ascontiguousarray(KRKi, np.float32).reshape(-1),
+                                         np.ascontiguousarray(Kt, np.float32).reshape(-1), np.ascontiguousarray(aff, np.float32).reshape(-1), pts.ctypes.data, st.ctypes.data))
+    return st
+
+
+def optimizeImmaturePointBatch(ctx: Context, pt_begin, tgt_begin, target_frame_ids, pre14, calib6, pts, is_from_sensor=None, min_obs=1):
+    """FullSystem::optimizeImmaturePoint (FullSystemOptPoint.cpp:18-183) for the candidates of several host keyframes in one launch (group = host; see sdv_b200.h).
+    Returns (status (n,) 0 stay / -1 drop / 1 activate, idepth (n,), res_state (n, stride) with -1 padding)."""
+    assert pts.dtype == IMMATURE_PT_DTYPE and pts.flags.c_contiguous
+    pb = np.ascontiguousarray(pt_begin, np.int32); tb = np.ascontiguousarray(tgt_begin, np.int32); ng = len(pb) - 1; n = len(pts); assert pb[-1] == n and len(tb) == ng + 1
+    stride = max(1, int(np.diff(tb).max())) if ng else 1
+    st = np.zeros(n, np.int32); idp = np.zeros(n, np.float32); rs = np.full((n, stride), -1, np.int32)
+    fs = None if is_from_sensor is None else np.ascontiguousarray(is_from_sensor, np.uint8)
+    ctx._ck(LIB.sdv_immature_optimize_batch(ctx.p, ng, pb, tb, np.ascontiguousarray(target_frame_ids, np.uint64), np.ascontiguousarray(pre14, np.float32).reshape(-1),
+                                            np.ascontiguousarray(calib6, np.float32).reshape(-1), min_obs, pts.ctypes.data, None if fs is None else fs.ctypes.data, stride, st, idp, rs.reshape(-1)))
+    return st, idp, rs

@@ -667,38 +667,77 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   for (int i = tid; i < N*N; i += kSolveThreads) { int r = i/N, c = i%N; sA[i] = sv[r]*sA[i]*sv[c]; }
   if (tid < N) sb[tid] = sv[tid]*sb[tid];
   __syncthreads();
-  // ---- pivoted LDLT, left-looking like Eigen's unblocked kernel: every dot product is evaluated by ONE thread in index order
-  for (int k = 0; k < N; k++) {
-    if (tid == 0) { int piv = k; double big = fabs(sA[k*N+k]); for (int i=k+1;i<N;i++) { double a = fabs(sA[i*N+i]); if (a > big) { big = a; piv = i; } } spiv = piv; sperm[k] = piv; }
-    __syncthreads();
-    const int piv = spiv;
-    if (piv != k) {
-      if (tid < k) { double s = sA[k*N+tid]; sA[k*N+tid] = sA[piv*N+tid]; sA[piv*N+tid] = s; }
-      else if (tid > piv && tid < N) { double s = sA[tid*N+k]; sA[tid*N+k] = sA[tid*N+piv]; sA[tid*N+piv] = s; }
-      else if (tid > k && tid < piv) { double s = sA[tid*N+k]; sA[tid*N+k] = sA[piv*N+tid]; sA[piv*N+tid] = s; }
-      else if (tid == k) { double s = sA[k*N+k]; sA[k*N+k] = sA[piv*N+piv]; sA[piv*N+piv] = s; }
-      __syncthreads();
+  // ---- pivoted LDLT, left-looking like Eigen's unblocked kernel: every dot product is evaluated by ONE thread in index order.
+  // Only the first two warps take part (one matrix row per thread, N <= 52) and meet at a 64-thread named barrier; the pivot search is a warp arg-max
+  // (first index among equal maxima, like the sequential `a > big` scan).  The other warps wait at the block barrier behind the solve.
+#define BAR64() asm volatile("bar.sync 1, 64;" ::: "memory")
+  if (tid < 64) {
+    for (int k = 0; k < N; k++) {
+      if (tid < 32) {
+        double best = -1.0; int bi = k;
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) { const int i = k + tid + 32*rep;
+          if (i < N) { const double v = fabs(sA[i*N+i]); const double a = (i == k) ? v : ((v == v) ? v : -1.0);     // a NaN diagonal entry never replaces the running maximum (a > big is false)
+            if (i == k || a > best) { best = a; bi = i; } } }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const double ob = __shfl_down_sync(0xffffffffu, best, off); const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; } }
+        if (tid == 0) { spiv = bi; sperm[k] = bi; }
+      }
+      BAR64();
+      const int piv = spiv;
+      if (piv != k) {
+        if (tid < k) { double s = sA[k*N+tid]; sA[k*N+tid] = sA[piv*N+tid]; sA[piv*N+tid] = s; }
+        else if (tid > piv && tid < N) { double s = sA[tid*N+k]; sA[tid*N+k] = sA[tid*N+piv]; sA[tid*N+piv] = s; }
+        else if (tid > k && tid < piv) { double s = sA[tid*N+k]; sA[tid*N+k] = sA[piv*N+tid]; sA[piv*N+tid] = s; }
+        else if (tid == k) { double s = sA[k*N+k]; sA[k*N+k] = sA[piv*N+piv]; sA[piv*N+piv] = s; }
+        BAR64();
+      }
+      if (tid < k) stmp[tid] = sA[tid*N+tid]*sA[k*N+tid];
+      BAR64();
+      if (tid >= k && tid < N && k > 0) {                                      // row k: the diagonal update, rows below: the column update — same loop, same order
+        const double* row = sA + tid*N; double s2 = 0;
+#pragma unroll 4
+        for (int j = 0; j < k; j++) s2 += row[j]*stmp[j];
+        sA[tid*N+k] -= s2;
+      }
+      BAR64();
+      const double akk = sA[k*N+k];
+      if (tid > k && tid < N && fabs(akk) > 0) sA[tid*N+k] /= akk;
+      BAR64();
     }
-    if (tid < k) stmp[tid] = sA[tid*N+tid]*sA[k*N+tid];
-    __syncthreads();
-    if (tid == k && k > 0) { double s = 0; for (int j=0;j<k;j++) s += sA[k*N+j]*stmp[j]; sA[k*N+k] -= s; }
-    if (tid > k && tid < N && k > 0) { double s2 = 0; for (int j=0;j<k;j++) s2 += sA[tid*N+j]*stmp[j]; sA[tid*N+k] -= s2; }
-    __syncthreads();
-    const double akk = sA[k*N+k];
-    if (tid > k && tid < N && fabs(akk) > 0) sA[tid*N+k] /= akk;
-    __syncthreads();
+    // ---- solve: P, L^-1, D^+, L^-T, P^T.  L^-1 column by column: thread i owns y_i and subtracts L_ij*y_j for j ascending — the row-wise order of the sequential loop;
+    // L^-T stays sequential (row i needs y_{i+1} first), its products do not sit on the dependency chain.
+    if (tid == 0) { for (int i=0;i<N;i++) sx[i] = sb[i]; for (int k=0;k<N;k++) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; } }
+    BAR64();
+    { double yi = (tid < N) ? sx[tid] : 0.0;
+      for (int j2 = 0; j2 < N; j2++) {
+        if (tid == j2) sx[j2] = yi;
+        BAR64();
+        if (tid > j2 && tid < N) yi -= sA[tid*N+j2]*sx[j2];
+      } }
+    BAR64();
+    if (tid < 32) {
+      double dm = 0;
+      for (int i = tid; i < N; i += 32) dm = fmax(dm, fabs(sA[i*N+i]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) dm = fmax(dm, __shfl_xor_sync(0xffffffffu, dm, off));
+      const double tol = fmax(dm*2.220446049250313e-16, 1.0/1.7976931348623157e308);
+      for (int i = tid; i < N; i += 32) { const double d = sA[i*N+i]; sx[i] = (fabs(d) > tol) ? sx[i]/d : 0.0; }
+    }
+    BAR64();
+    if (tid == 0) {
+      for (int i=N-1;i>=0;i--) { double s = sx[i];
+#pragma unroll 4
+        for (int j2=i+1;j2<N;j2++) s -= sA[j2*N+i]*sx[j2];
+        sx[i] = s; }
+      for (int k=N-1;k>=0;k--) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; }
+    }
+    BAR64();
+    if (tid < N) sx[tid] = sv[tid]*sx[tid];
   }
-  if (tid == 0) {                                                           // solve: P, L^-1, D^+, L^-T, P^T  (sequential, reference order)
-    for (int i=0;i<N;i++) sx[i] = sb[i];
-    for (int k=0;k<N;k++) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; }
-    for (int i=0;i<N;i++) { double s = sx[i]; for (int j=0;j<i;j++) s -= sA[i*N+j]*sx[j]; sx[i] = s; }
-    double dmax = 0; for (int i=0;i<N;i++) dmax = fmax(dmax, fabs(sA[i*N+i]));
-    double tol = fmax(dmax*2.220446049250313e-16, 1.0/1.7976931348623157e308);
-    for (int i=0;i<N;i++) { double d = sA[i*N+i]; sx[i] = (fabs(d) > tol) ? sx[i]/d : 0.0; }
-    for (int i=N-1;i>=0;i--) { double s = sx[i]; for (int j=i+1;j<N;j++) s -= sA[j*N+i]*sx[j]; sx[i] = s; }
-    for (int k=N-1;k>=0;k--) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; }
-    for (int i=0;i<N;i++) sx[i] = sv[i]*sx[i];
-  }
+#undef BAR64
   __syncthreads();
   // ---- orthogonalize x against the pose+scale nullspaces for iteration >= 2 (EnergyFunctional.cpp:615-648, 746-750).  The basis only
   // depends on the evaluation points, so it is computed once per linearisation point (one-sided Jacobi, same operation order as the
@@ -712,23 +751,30 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
       __syncthreads();
       if (tid < m) { double nr = 0; for (int r=0;r<N;r++) nr += A[tid*N+r]*A[tid*N+r]; nr = sqrt(nr); for (int r=0;r<N;r++) A[tid*N+r] /= nr; }
       __syncthreads();
-      for (int sweep = 0; sweep < 60; sweep++) {
-        if (tid == 0) srot[3] = 0;
-        for (int p=0;p<m;p++) for (int q=p+1;q<m;q++) {
-          __syncthreads();
-          if (tid == 0) { double al = 0; for (int r=0;r<N;r++) al += A[p*N+r]*A[p*N+r]; srot[0] = al; }
-          else if (tid == 32) { double be = 0; for (int r=0;r<N;r++) be += A[q*N+r]*A[q*N+r]; srot[1] = be; }
-          else if (tid == 64) { double ga = 0; for (int r=0;r<N;r++) ga += A[p*N+r]*A[q*N+r]; srot[2] = ga; }
-          __syncthreads();
-          const double al = srot[0], be = srot[1], ga = srot[2];
-          if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17*sqrt(al*be)) continue;
-          if (tid == 0) srot[3] = fmax(srot[3], fabs(ga)/sqrt(al*be + 1e-300));
-          const double zeta = (be-al)/(2*ga), tt = ((zeta >= 0) ? 1.0 : -1.0)/(fabs(zeta) + sqrt(1+zeta*zeta)), c = 1/sqrt(1+tt*tt), sn = c*tt;
-          if (tid < N) { double ap = A[p*N+tid], aq = A[q*N+tid]; A[p*N+tid] = c*ap - sn*aq; A[q*N+tid] = sn*ap + c*aq; }
+      // one-sided Jacobi on the first two warps (row updates: one row per thread, N <= 52), 64-thread named barrier instead of block barriers
+      if (tid < 64) {
+        for (int sweep = 0; sweep < 60; sweep++) {
+          if (tid == 0) srot[3] = 0;
+          for (int p=0;p<m;p++) for (int q=p+1;q<m;q++) {
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            if (tid == 0) { double al = 0;
+#pragma unroll 4
+              for (int r=0;r<N;r++) al += A[p*N+r]*A[p*N+r]; srot[0] = al; }
+            else if (tid == 32) { double be = 0, ga = 0;                      // two independent chains, each in index order
+#pragma unroll 4
+              for (int r=0;r<N;r++) { const double aq = A[q*N+r]; be += aq*aq; ga += A[p*N+r]*aq; }
+              srot[1] = be; srot[2] = ga; }
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            const double al = srot[0], be = srot[1], ga = srot[2];
+            if (fabs(ga) <= 1e-300 || fabs(ga) <= 1e-17*sqrt(al*be)) continue;
+            if (tid == 0) srot[3] = fmax(srot[3], fabs(ga)/sqrt(al*be + 1e-300));
+            const double zeta = (be-al)/(2*ga), tt = ((zeta >= 0) ? 1.0 : -1.0)/(fabs(zeta) + sqrt(1+zeta*zeta)), c = 1/sqrt(1+tt*tt), sn = c*tt;
+            if (tid < N) { double ap = A[p*N+tid], aq = A[q*N+tid]; A[p*N+tid] = c*ap - sn*aq; A[q*N+tid] = sn*ap + c*aq; }
+          }
+          asm volatile("bar.sync 1, 64;" ::: "memory");
+          if (srot[3] < 1e-15) break;
+          asm volatile("bar.sync 1, 64;" ::: "memory");
         }
-        __syncthreads();
-        if (srot[3] < 1e-15) break;
-        __syncthreads();
       }
       __syncthreads();
       if (tid < m) { double nr = 0; for (int r=0;r<N;r++) nr += A[tid*N+r]*A[tid*N+r]; H->orthoS[tid] = sqrt(nr); }

@@ -148,7 +148,7 @@ void sdv_destroy(sdv_ctx* c) {
   for (int i=0;i<2;i++) { cudaFree(c->pyr_batch_dev[i]); cudaFreeHost(c->pyr_batch_host[i]); } cudaFree(c->partials); cudaFree(c->ticket); cudaFree(c->totals_dev); cudaFreeHost(c->totals_host);
   cudaFree(c->tc_dev); cudaFree(c->jobs_dev); cudaFreeHost(c->jobs_host);
   for (int i=0;i<2;i++) { for (auto p : c->stage[i]) cudaFree(p); cudaFree(c->stage_u8[i]); }
-  cudaFree(c->und_buf);
+  cudaFree(c->und_buf); cudaFree(c->trace_dev);
   for (int i=0;i<sdv_ctx::kIngRing;i++) if (c->ev_ing[i]) cudaEventDestroy(c->ev_ing[i]); for (int i=0;i<2;i++) if (c->ev_cp[i]) cudaEventDestroy(c->ev_cp[i]); if (c->st_cp) cudaStreamDestroy(c->st_cp);
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);

@@ -57,6 +57,7 @@ struct sdv_ctx {
   int jobs_cap; sdv::TrackJob* jobs_dev; sdv::TrackJob* jobs_host;
   float last_ms;
   void* refine_dev = nullptr; void* refine_host = nullptr; size_t refine_cap = 0;      // staging of sdv_tracker_struct_pose_batch
+  void* trace_dev = nullptr; size_t trace_cap = 0;                                  // scratch of the immature-point calls (sdv_trace.cu)
   sdv::RpState* rp = nullptr;                   // map slots + scratch of the Reprojector path (sdv_reproject.cu)
   sdv::BAState* ba = nullptr;                   // selected back-end window
   std::vector<sdv::BAState*> ba_windows; void* ba_wins_dev = nullptr; void* ba_wins_host = nullptr; int ba_wins_cap = 0;

@@ -15,7 +15,7 @@ def test_tracking_and_mapping_threads_share_one_context():
     from sdv_loam_b200 import api, synth
     K, wh = synth.KITTI_K, synth.KITTI_WH; w, h = wh; B = 6
     seq = cached_sequence(8, 2000, K, wh)
-    ctx = api.Context(K, w, h, n_tracker_slots=B, max_frames=2 * B + 12)
+    ctx = api.Context(K, w, h, n_tracker_slots=B, max_frames=3 * B + 16)
     pts = synth.select_points(seq.images[0], seq.clouds[0], 1500); p4 = np.concatenate([pts, np.full((len(pts), 1), 1e-3, np.float32)], 1).astype(np.float32)
     for b in range(B):
         ctx.makeImages(1000 + b, seq.images[0]); api.CoarseTracker(ctx, b).setCoarseTrackingRef(1000 + b, p4, np.zeros(len(p4), np.int32))
