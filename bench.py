@@ -645,7 +645,7 @@ def main():
                  "pose_digest": mc["pose_digest"], "tracked_ok_fraction_rank0": mc["local_ok_fraction"],
                  "final_pose_err_vs_gt_m_rad": [float(max(e[:3].max() for e in mc_err)), float(max(e[3:].max() for e in mc_err))],
                  "api": "runner.run_monte_carlo over runner.GpuBackend: sequence i -> rank i mod world (dist.shard_sequences), per frame sdv_frame_upload_batch_raw_u8 + "
-                        "sdv_tracker_track_batch, next guess = constant motion from the re-run's own last two poses; no overlap of upload and tracking inside a chain step"}
+                        "sdv_tracker_track_batch, next guess = constant motion from the re-run's own last two poses; the next frame's upload overlaps the tracking of the current one"}
     clocks = sampler.stop()
     del host_u8
 
