@@ -473,13 +473,33 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": arm.kind, "threads": cores, "frames_per_s_per_thread": fps / cores,
                              "sample": "%d steps x %d threads x %d frames, one sequence per thread; %s" % (steps, cores, per, cpu_note(arm))},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 METRIC = "frames/sec (KITTI 1241x376 + 64-beam): undistort + makeImages + trackNewestCoarse per frame"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything any library prints on fd 1 from here on (NCCL's version banner, nvcc/ptxas chatter of a first build, ...) goes to stderr; the ONE JSON line of the contract is
+    written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush(); _REAL_STDOUT = os.dup(1); os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush(); os.write(_REAL_STDOUT, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -504,7 +524,7 @@ def main():
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: the B200 path has no CPU fallback"})); sys.exit(2)
+        emit({"error": "no CUDA device: the B200 path has no CPU fallback"}); sys.exit(2)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -731,7 +751,7 @@ def main():
                 line["combined"]["cpu_frames_per_s_track_refine_ba_1core"] = 1.0 / (tw / nf + refine["cpu_ms_per_frame_1core"] * 1e-3 + cms * 1e-3 / args.kf_every)
         line["cpu_baseline"] = {"value": nf / tw, "unit": "frames/s", "cores": 1, "kind": arm.kind,
                                 "sample": "%d frames (undistort + makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; %s" % (nf, tw, cpu_note(arm))}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

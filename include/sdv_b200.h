@@ -184,7 +184,8 @@ int  sdv_tracker_refine_batch(sdv_ctx* c, int n_jobs, const int32_t* slots, cons
 typedef struct {
   /* in */
   int32_t  slot;                 /* tracker slot == map slot of the sequence (coarseTracker / the active window) */
-  int32_t  poses_valid;          /* slast->poseValid && sprelast->poseValid && lastF->shell->poseValid  (:390) */
+  int32_t  poses_valid;          /* 1: slast->poseValid && sprelast->poseValid && lastF->shell->poseValid (:390) -> 31 hypotheses; 0: -> identity only (:391-394);
+                                    2: the second frame of a sequence (allFrameHistory.size() == 2, :299-331) -> identity + 52 pure rotations, no history needed */
   uint64_t frame;                /* device handle of fh */
   double   sprelast_c2w[7], slast_c2w[7], lastF_c2w[7];   /* camToWorld of allFrameHistory[size-3], [size-2], coarseTracker->lastRef->shell */
   double   aff_last[2];          /* slast->aff_g2l {a,b} */

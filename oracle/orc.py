@@ -185,6 +185,16 @@ def track_hypotheses(sprelast_c2w, slast_c2w, lastF_c2w, poses_valid):
     """lastF_2_fh_tries of FullSystem::trackNewCoarse for a running system (FullSystem.cpp:334-394)."""
     if not poses_valid:
         return [np.array([1, 0, 0, 0, 0, 0, 0.0])]
+    ROT = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (-1, 0, 0), (0, -1, 0), (0, 0, -1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (-1, 1, 0), (0, -1, 1), (-1, 0, 1), (1, -1, 0),
+           (0, 1, -1), (1, 0, -1), (-1, -1, 0), (0, -1, -1), (-1, 0, -1), (-1, -1, -1), (-1, -1, 1), (-1, 1, -1), (-1, 1, 1), (1, -1, -1), (1, -1, 1), (1, 1, -1), (1, 1, 1)]
+    if poses_valid == 2:                                                          # second frame of a sequence (FullSystem.cpp:299-331): identity + 26 rotations x {0.02f, 0.04f}
+        tries = [np.array([1, 0, 0, 0, 0, 0, 0.0])]
+        for rd in (np.float32(0.02), np.float32(0.02) + np.float32(0.02)):
+            r = float(rd)
+            for q in ROT:
+                qq = np.array([1.0, q[0] * r, q[1] * r, q[2] * r]); qq = qq / np.sqrt(qq[1] * qq[1] + qq[2] * qq[2] + qq[3] * qq[3] + qq[0] * qq[0])
+                tries.append(np.concatenate([qq, np.zeros(3)]))
+        return tries
     slast_2_sprelast = se3_mul(se3_inv(sprelast_c2w), slast_c2w); lastF_2_slast = se3_mul(se3_inv(slast_c2w), lastF_c2w)
     fh_2_slast = slast_2_sprelast; inv = se3_inv(fh_2_slast); cm = se3_mul(inv, lastF_2_slast)
     tries = [cm, se3_mul(se3_mul(inv, inv), lastF_2_slast), se3_mul(se3_inv(se3_exp(se3_log(fh_2_slast) * 0.5)), lastF_2_slast), lastF_2_slast,

@@ -204,6 +204,8 @@ __device__ __forceinline__ double lin_residual(BAHeader* __restrict__ H, BAPoint
     const float4* __restrict__ img = H->frames[tI].img0; const int wI = H->w;
     const float ids = P.idepth[pI]*1.0f; const float a0 = pc.aff[0], a1 = pc.aff[1];
     float wJI2_sum = 0, energyLeft2 = 0.0f;
+    // (Tried in round 2: all 8 projections first, then the footprints of 4 pixels fetched together — 16 independent loads in flight per thread — and accumulated in
+    // order.  Bit-identical, but 184 registers instead of 96 cut the resident warps by more than the extra memory parallelism gave: 415 -> 580 us per launch at 296 windows.)
     for (int idx = 0; idx < 8; idx++) {
       float x = uv.x + c_pattern[idx][0], y = uv.y + c_pattern[idx][1];
       float q0 = ((pc.KRKi[0]*x + pc.KRKi[1]*y) + pc.KRKi[2]*1.0f) + pc.Kt[0]*ids;
@@ -533,6 +535,14 @@ template <typename MF> __device__ __forceinline__ double triple66(const double* 
 }
 
 constexpr int kSolveThreads = 512;
+#ifdef SDV_BA_PROFILE
+__device__ long long g_ba_prof[16];
+#define BA_PROF_T(var) const long long var = clock64()
+#define BA_PROF_ADD(slot, a, b) do { if (blockIdx.y == 0 && threadIdx.x == 0) g_ba_prof[slot] += (b) - (a); } while (0)
+#else
+#define BA_PROF_T(var) do {} while (0)
+#define BA_PROF_ADD(slot, a, b) do {} while (0)
+#endif
 // Stitch the accumulated top (sA, sbA) and Schur (sS, sbS) systems from the per-bucket float accumulators.
 //   MARG = false: stitchDoubleMT as solveSystemF calls it (buckets walked k = h + nF*t ascending, priors and deltas added)
 //                 AccumulatedTopHessian.cpp:181-242 + .h:63-114, AccumulatedSCHessian.cpp:64-135 + .h:68-111
@@ -542,6 +552,7 @@ template <bool MARG>
 __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int tid, const int nF, const int N, const int nF2,
                                           double* __restrict__ sA, double* __restrict__ sS, double* __restrict__ sbA, double* __restrict__ sbS) {
 #define BK(kk) (MARG ? ((kk)/nF + nF*((kk)%nF)) : (kk))
+  BA_PROF_T(ts0);
   // ---- products shared by many output elements, in the reference's operation order: T1 = AH*M, T3 = AT*M (top buckets), AH_ij*D, AT_ij*D (Schur buckets)
   for (int task = tid; task < nF2*72; task += kSolveThreads) {
     const int k = task/72, e = task%72, which = e/36, i = (e%36)/6, q = e%6; if (H->accTopNum[k] == 0) continue;
@@ -556,6 +567,7 @@ __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int ti
     (which ? H->scT3 : H->scT1)[bk*36 + i*6 + q] = t;
   }
   __syncthreads();
+  BA_PROF_T(ts1); BA_PROF_ADD(8, ts0, ts1);
   // ---- top: frame-frame blocks (raw), frame-calib blocks, calib block, gradient
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
@@ -595,6 +607,7 @@ __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int ti
     sbA[task] = acc;
   }
   __syncthreads();
+  BA_PROF_T(ts2); BA_PROF_ADD(9, ts1, ts2);
   // symmetrise (AccumulatedTopHessian.h:100-113): calib row-blocks = transposed column-blocks; (h,t) += (t,h)^T for t>h, then mirror
   for (int task = tid; task < nF*24; task += kSolveThreads) { const int a = task/24, r = (task%24)/6, c = task%6; sA[r*N + kCP+a*6+c] = sA[(kCP+a*6+c)*N + r]; }
   for (int task = tid; task < nF2*36; task += kSolveThreads) { const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, r = e/6, c = e%6;
@@ -602,6 +615,7 @@ __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int ti
   __syncthreads();
   for (int task = tid; task < nF2*36; task += kSolveThreads) { const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, r = e/6, c = e%6;
     if (b > a) sA[(kCP+b*6+r)*N + kCP+a*6+c] = sA[(kCP+a*6+c)*N + kCP+b*6+r]; }
+  BA_PROF_T(ts3); BA_PROF_ADD(10, ts2, ts3);
   // ---- Schur complement: frame-frame blocks
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
@@ -620,6 +634,7 @@ __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int ti
       } }
     sS[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
   }
+  BA_PROF_T(ts4); BA_PROF_ADD(11, ts3, ts4);
   for (int task = tid; task < nF*24; task += kSolveThreads) {              // Hsc[frame a, calib]
     const int a = task/24, r = (task%24)/4, c = task%4; double acc = 0;
     for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
@@ -651,7 +666,9 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   __shared__ double sS[kMaxDim*kMaxDim];                                    // Hsc -> nullspace basis
   __shared__ double sv[kMaxDim], sb[kMaxDim], sx[kMaxDim], stmp[kMaxDim], sbA[kMaxDim], sbS[kMaxDim];
   __shared__ int sperm[kMaxDim]; __shared__ int spiv; __shared__ double srot[4];
+  BA_PROF_T(tb0);
   ba_stitch<false>(H, tid, nF, N, nF2, sA, sS, sbA, sbS);
+  BA_PROF_T(tb1); BA_PROF_ADD(0, tb0, tb1);
   // ---- publish HA/bA/Hsc/bsc (read-back for tests), HFinal / bFinal, damping, diagonal pre-scaling (EnergyFunctional.cpp:668-744)
   for (int i = tid; i < N*N; i += kSolveThreads) { H->HA[i] = sA[i]; H->Hsc[i] = sS[i]; double v = sA[i] + H->HM[i] - sS[i]; H->lastHS[i] = v; sA[i] = v; }
   if (tid < N) {
@@ -667,6 +684,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   for (int i = tid; i < N*N; i += kSolveThreads) { int r = i/N, c = i%N; sA[i] = sv[r]*sA[i]*sv[c]; }
   if (tid < N) sb[tid] = sv[tid]*sb[tid];
   __syncthreads();
+  BA_PROF_T(tb2); BA_PROF_ADD(1, tb1, tb2);
   // ---- pivoted LDLT, left-looking like Eigen's unblocked kernel: every dot product is evaluated by ONE thread in index order.
   // Only the first two warps take part (one matrix row per thread, N <= 52) and meet at a 64-thread named barrier; the pivot search is a warp arg-max
   // (first index among equal maxima, like the sequential `a > big` scan).  The other warps wait at the block barrier behind the solve.
@@ -707,6 +725,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
       if (tid > k && tid < N && fabs(akk) > 0) sA[tid*N+k] /= akk;
       BAR64();
     }
+    BA_PROF_T(tb3); BA_PROF_ADD(2, tb2, tb3);
     // ---- solve: P, L^-1, D^+, L^-T, P^T.  L^-1 column by column: thread i owns y_i and subtracts L_ij*y_j for j ascending — the row-wise order of the sequential loop;
     // L^-T stays sequential (row i needs y_{i+1} first), its products do not sit on the dependency chain.
     if (tid == 0) { for (int i=0;i<N;i++) sx[i] = sb[i]; for (int k=0;k<N;k++) { double s = sx[k]; sx[k] = sx[sperm[k]]; sx[sperm[k]] = s; } }
@@ -739,6 +758,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   }
 #undef BAR64
   __syncthreads();
+  BA_PROF_T(tb4); BA_PROF_ADD(3, tb2, tb4);
   // ---- orthogonalize x against the pose+scale nullspaces for iteration >= 2 (EnergyFunctional.cpp:615-648, 746-750).  The basis only
   // depends on the evaluation points, so it is computed once per linearisation point (one-sided Jacobi, same operation order as the
   // oracle: each dot product by one thread, row updates in parallel) and cached in the header.
@@ -795,6 +815,7 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
     }
     __syncthreads();
   }
+  BA_PROF_T(tb5); BA_PROF_ADD(4, tb4, tb5);
   // ---- lastX, steps, xAd (resubstituteF_MT head, EnergyFunctional.cpp:221-248)
   if (tid < N) { H->lastX[tid] = sx[tid]; H->xF[tid] = (float)sx[tid]; }
   if (tid < 4) H->calib.step[tid] = -sx[tid];
@@ -803,7 +824,19 @@ __global__ void __launch_bounds__(kSolveThreads) ba_solve_kernel(const BAWinDev*
   for (int e = tid; e < nF2*6; e += kSolveThreads) { int pr = e/6, j = e%6, h = pr / nF, t = pr % nF;       // xAd[nF*h + t]
     float s1 = 0, s2 = 0; for (int i=0;i<6;i++) { s1 += (float)sx[kCP+6*h+i]*H->adHostF[(h+nF*t)*36+i*6+j]; s2 += (float)sx[kCP+6*t+i]*H->adTargetF[(h+nF*t)*36+i*6+j]; }
     H->xAd[(nF*h+t)*6+j] = s1 + s2; }
+  BA_PROF_T(tb6); BA_PROF_ADD(5, tb5, tb6); BA_PROF_ADD(6, tb0, tb6);
+#ifdef SDV_BA_PROFILE
+  if (blockIdx.y == 0 && tid == 0) g_ba_prof[7] += 1;
+#endif
 }
+#ifdef SDV_BA_PROFILE
+extern "C" int sdv_debug_ba_profile(long long* out16, int reset) {
+  long long z[16] = {0};
+  if (out16) cudaMemcpyFromSymbol(out16, g_ba_prof, sizeof(z));
+  if (reset) cudaMemcpyToSymbol(g_ba_prof, z, sizeof(z));
+  return 0;
+}
+#endif
 
 __global__ void ba_resub_kernel(const BAWinDev* __restrict__ wins, int gate) {     // resubstituteFPt (:250-282)
   BA_WIN(gate)

@@ -1,7 +1,7 @@
 // sdv_policy.cu — FullSystem::trackNewCoarse as a batched host policy over the device kernels.
 //
-// Restates /root/reference/src/FullSystem/FullSystem.cpp:283-500 (the branch for a running system, :334-395: allFrameHistory.size() > 2;
-// the two-frame bootstrap through CoarseInitializer is out of scope):
+// Restates /root/reference/src/FullSystem/FullSystem.cpp:283-500: the branch for a running system (:334-395: allFrameHistory.size() > 2) and the hypothesis set of the
+// second frame (:299-331: identity + 2 x 26 small rotations; poses_valid == 2 — its initializeFromInitializer / setCTRefForFirstFrame bookkeeping stays with the caller):
 //   motion hypotheses lastF_2_fh_tries (constant / double / half / zero motion, zero from KF, 26 small rotations — the rotDelta loop of :357
 //   increments by 1.0, so it runs once), the re-track loop with the per-level "at least as good as the best try" abort vector (:410-462),
 //   the fallback when every try fails (:464-470), pose composition (:474-479), reprojectMap + structPoseEstimation (:481-488).
@@ -19,18 +19,25 @@ static SE3d quatT(double w, double x, double y, double z) { SE3d s; s.q = qnorma
 
 // Hypothesis i of FullSystem.cpp:346-388, generated on demand (healthy tracking only ever needs i = 0; building all 31 for every sequence of a batch
 // would cost more host time than the launch they feed).
-struct TryGen { bool valid; SE3d inv, lastF_2_slast, cm, fh_2_slast; };
+struct TryGen { bool valid; bool second_frame; SE3d inv, lastF_2_slast, cm, fh_2_slast; };
 static TryGen try_gen(const sdv_track_new_coarse_io& io) {
-  TryGen g; g.valid = io.poses_valid != 0; if (!g.valid) return g;                       // :390-394 -> {SE3()}
+  TryGen g; g.valid = io.poses_valid != 0; g.second_frame = io.poses_valid == 2; if (!g.valid || g.second_frame) return g;   // :390-394 -> {SE3()}; :299-331 needs no history
   const SE3d sprelast = se3_from7(io.sprelast_c2w), slast = se3_from7(io.slast_c2w), lastF = se3_from7(io.lastF_c2w);
   g.fh_2_slast = se3_mul(se3_inv(sprelast), slast);                                      // slast_2_sprelast, assumed equal to fh_2_slast (:343,347)
   g.lastF_2_slast = se3_mul(se3_inv(slast), lastF);                                      // :344
   g.inv = se3_inv(g.fh_2_slast); g.cm = se3_mul(g.inv, g.lastF_2_slast);
   return g;
 }
-static int n_tries(const TryGen& g) { return g.valid ? 31 : 1; }
+static const int kRotPattern[26][3] = {{1,0,0},{0,1,0},{0,0,1},{-1,0,0},{0,-1,0},{0,0,-1},{1,1,0},{0,1,1},{1,0,1},{-1,1,0},{0,-1,1},{-1,0,1},{1,-1,0},{0,1,-1},{1,0,-1},
+                                       {-1,-1,0},{0,-1,-1},{-1,0,-1},{-1,-1,-1},{-1,-1,1},{-1,1,-1},{-1,1,1},{1,-1,-1},{1,-1,1},{1,1,-1},{1,1,1}};
+static int n_tries(const TryGen& g) { return !g.valid ? 1 : (g.second_frame ? 53 : 31); }
 static SE3d make_try(const TryGen& g, int i) {
   if (!g.valid) return se3_identity();
+  if (g.second_frame) {                                                                  // allFrameHistory.size() == 2 (:299-331): identity, then 26 pure rotations for
+    if (i == 0) return se3_identity();                                                   // rotDelta = 0.02f and 0.04f (float loop `rotDelta = rotDelta + 0.02` while < 0.05)
+    const float rd = (i - 1 < 26) ? 0.02f : (0.02f + 0.02f); const double r = (double)rd; const int k = (i - 1) % 26;
+    return quatT(1, kRotPattern[k][0]*r, kRotPattern[k][1]*r, kRotPattern[k][2]*r);
+  }
   switch (i) {
     case 0: return g.cm;                                                                 // constant motion
     case 1: return se3_mul(se3_mul(g.inv, g.inv), g.lastF_2_slast);                      // double motion (left-associated like the expression :351)
@@ -40,10 +47,8 @@ static SE3d make_try(const TryGen& g, int i) {
     default: break;
   }
   const double r = (double)0.02f;                                                        // float rotDelta promoted to double in the Quaterniond ctor; the loop of :357 runs once
-  static const int q[26][3] = {{1,0,0},{0,1,0},{0,0,1},{-1,0,0},{0,-1,0},{0,0,-1},{1,1,0},{0,1,1},{1,0,1},{-1,1,0},{0,-1,1},{-1,0,1},{1,-1,0},{0,1,-1},{1,0,-1},
-                               {-1,-1,0},{0,-1,-1},{-1,0,-1},{-1,-1,-1},{-1,-1,1},{-1,1,-1},{-1,1,1},{1,-1,-1},{1,-1,1},{1,1,-1},{1,1,1}};
   const int k = i - 5;
-  return se3_mul(g.cm, quatT(1, q[k][0]*r, q[k][1]*r, q[k][2]*r));                       // (fh_2_slast^-1 * lastF_2_slast) * dR, left-associated
+  return se3_mul(g.cm, quatT(1, kRotPattern[k][0]*r, kRotPattern[k][1]*r, kRotPattern[k][2]*r));                       // (fh_2_slast^-1 * lastF_2_slast) * dR, left-associated
 }
 
 // Host-only helper (no device work): hypothesis i of the re-track loop for one job, so the generation can be checked without a GPU.
