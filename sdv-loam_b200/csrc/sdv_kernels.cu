@@ -639,8 +639,8 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
   unsigned char* ring = smem_raw;
   float4* pbuf   = reinterpret_cast<float4*>(smem_raw + kRingBytes);
   float*  red    = reinterpret_cast<float*>(smem_raw);
-  double* gather = reinterpret_cast<double*>(smem_raw + kStageBytes);                    // [2][kMaxCluster][kNAcc]
-  double* bsum   = gather + 2*kMaxCluster*kNAcc;                                         // [kNAcc]
+  double* gather = reinterpret_cast<double*>(smem_raw + kStageBytes);                    // [2][C][kNAcc] — sized by the launch's cluster size (13 KB at 16 CTAs, 0.8 KB at 1)
+  double* bsum   = gather + 2*C*kNAcc;                                                   // [kNAcc]
   double* tot    = bsum + kNAcc;                                                         // [kNAcc]
   __shared__ Ctl2 ctl;
   __shared__ TrackConst tc;
@@ -753,10 +753,10 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
         for (int k = tid; k < kNAcc*C; k += THREADS) {
           int r = k / kNAcc, e = k - r*kNAcc;
           double* dst = cluster.map_shared_rank(gather, r);
-          dst[(buf*kMaxCluster + rank)*kNAcc + e] = bsum[e];
+          dst[(buf*C + rank)*kNAcc + e] = bsum[e];
         }
         cluster.sync();
-        if (tid < kNAcc) { double s = 0; for (int r = 0; r < C; r++) s += gather[(buf*kMaxCluster + r)*kNAcc + tid]; tot[tid] = s; }
+        if (tid < kNAcc) { double s = 0; for (int r = 0; r < C; r++) s += gather[(buf*C + r)*kNAcc + tid]; tot[tid] = s; }
       } else {
         if (tid < kNAcc) tot[tid] = bsum[tid];
       }
@@ -918,9 +918,9 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
 }
 
 template <int THREADS>
-static size_t track_kernel_smem_v2() {
+static size_t track_kernel_smem_v2(int cluster_size = kMaxCluster) {
   size_t stage = (size_t)2*4*THREADS*16 + (size_t)2*kPtChunk*THREADS*16, red = (size_t)kNAcc*THREADS*sizeof(float);
-  return (stage > red ? stage : red) + (size_t)(2*kMaxCluster*kNAcc + 2*kNAcc)*sizeof(double);
+  return (stage > red ? stage : red) + (size_t)(2*cluster_size*kNAcc + 2*kNAcc)*sizeof(double);
 }
 
 template <int THREADS>
@@ -943,7 +943,7 @@ static cudaError_t launch_track_t(TrackJob* jobs_dev, int njobs, const TrackCons
   if (track_use_v1()) return launch_track_kern(track_cluster_v1_kernel<THREADS, MINB>, track_kernel_smem<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st);
   // stagger only when the grid fills the co-resident slots of the chip (otherwise there is nothing to desynchronise)
   const unsigned stag = (cluster_size == 1 && njobs > 148) ? track_stagger_ns() : 0u;
-  return launch_track_kern(track_cluster_kernel<THREADS, MINB>, track_kernel_smem_v2<THREADS>(), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st, stag);
+  return launch_track_kern(track_cluster_kernel<THREADS, MINB>, track_kernel_smem_v2<THREADS>(cluster_size), THREADS, jobs_dev, njobs, tc_dev, cluster_size, st, stag);
 }
 template <typename Kern>
 static cudaError_t track_attrs(Kern kern, size_t smem) {
@@ -952,7 +952,8 @@ static cudaError_t track_attrs(Kern kern, size_t smem) {
 }
 // threads: 128 (throughput, 4 jobs resident per SM) or 256 (latency)
 #ifndef SDV_TRACK_MINB
-#define SDV_TRACK_MINB 4                    // measured: 3 (163 regs) -18 %, 5 (96 regs, spills) -16 %, 6 (80 regs) -45 % vs 4 (128 regs, no spills)
+#define SDV_TRACK_MINB 4                    // v1 kernel: 3 (163 regs) -18 %, 5 (96 regs, spills) -16 %, 6 (80 regs) -45 % vs 4 (128 regs).  v2 kernel (gather buffers sized by the
+                                            // cluster, so 5-6 CTAs fit in shared memory): 5 (96 regs, 236 B spilled) 0.506 at 1 480 jobs vs 4: 0.509 at 1 776 / 0.490 at 1 184; 6: 0.34
 #endif
 cudaError_t launch_track_cluster(TrackJob* jobs_dev, int njobs, const TrackConst* tc_dev, int cluster_size, int threads, cudaStream_t st) {
   if (threads == 256) return launch_track_t<256, 1>(jobs_dev, njobs, tc_dev, cluster_size, st);
