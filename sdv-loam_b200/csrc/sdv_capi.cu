@@ -162,6 +162,7 @@ void sdv_destroy(sdv_ctx* c) {
 int sdv_sync(sdv_ctx* c) { SDV_GUARD_TRK(c); if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); CK(cudaStreamSynchronize(c->st_cp)); CK(cudaStreamSynchronize(c->st_in)); CK(cudaStreamSynchronize(c->st)); CK(cudaStreamSynchronize(c->st_ba)); return SDV_OK; }
 long long sdv_launch_count(sdv_ctx* c) { return c ? c->launches.load() : 0LL; }
 int sdv_track_job_bytes(void) { return (int)sizeof(TrackJob); }
+int sdv_debug_gs_entry_rc(int k) { int r, c; if (k < 0 || k >= kNH) return -1; gs_entry_rc(k, r, c); return r*16 + c; }   // test hook (host evaluation of the device index walk)
 float sdv_last_kernel_ms(sdv_ctx* c) { return c ? c->last_ms : 0.f; }
 
 // ------------------------------------------------------------------------------------------------ frames

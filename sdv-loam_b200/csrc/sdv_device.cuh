@@ -61,6 +61,14 @@ SDV_HD void finalize_gs(const double* tot, double* H /*64*/, double* b /*8*/) {
   }
 }
 
+// (r,c) of the k-th entry of the row-major upper triangle of the 9x9 system (k = 0..44).  Host+device: tests/test_abi.py walks all 45 on the CPU (a wrong walk here
+// silently mixes H entries; it once did, and only the GPU LM tests noticed).
+SDV_HD void gs_entry_rc(int k, int& r, int& c) {
+  r = 0; int base = 0; bool walking = true;
+  for (int rr = 0; rr < 8; rr++) { const int next = base + (9 - rr); if (walking && k >= next) { r = rr + 1; base = next; } else walking = false; }
+  c = r + (k - base);
+}
+
 #if defined(__CUDACC__)
 // finalize_gs spread over the 32 lanes of a warp: lane handles upper-triangle entries k = lane and lane + 32 (45 entries), same arithmetic per entry as finalize_gs
 // (CoarseTracker.cpp:468-483).  45 dependent read-convert-scale-store chains on one lane cost ~9k cycles per LM evaluation; this is ~0.5k.
@@ -73,10 +81,7 @@ __device__ __forceinline__ void finalize_gs_warp(const double* tot, double* H /*
     const int k = lane + 32*rep;
     if (k < kNH) {
       // (r,c) of the k-th entry of the row-major upper triangle of the 9x9 system
-      int r = 0, base = 0; bool walking = true;
-#pragma unroll
-      for (int rr = 0; rr < 8; rr++) { const int next = base + (9 - rr); if (walking && k >= next) { r = rr + 1; base = next; } else walking = false; }
-      const int c = r + (k - base);
+      int r, c; gs_entry_rc(k, r, c);
       const float scr = (r < 3) ? 1.0f : ((r < 6) ? 0.5f : ((r == 6) ? 10.0f : 1000.0f));   // SCALE_XI_ROT x3, SCALE_XI_TRANS x3, SCALE_A, SCALE_B
       const float scc = (c < 3) ? 1.0f : ((c < 6) ? 0.5f : ((c == 6) ? 10.0f : 1000.0f));
       const float hv = (float)tot[k];

@@ -88,3 +88,12 @@ def test_integration_shims_compile_and_link():
         c = os.path.join(d, "hdr.c"); open(c, "w").write('#include "sdv_b200.h"\nint main(void) { return 0; }\n')
         r = subprocess.run([cc, "-x", "c", "-std=c11", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, c], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_device_index_walks_on_the_host():
+    """sdv_debug_gs_entry_rc evaluates, on the host, the (row, column) walk the warp-parallel finalisation of the tracker's 9x9 system uses on the device"""
+    import ctypes as C
+    import sdv_loam_b200
+    L = C.CDLL(sdv_loam_b200.build_library()); L.sdv_debug_gs_entry_rc.argtypes = [C.c_int]
+    want = [(r, c) for r in range(9) for c in range(r, 9)]
+    assert [divmod(L.sdv_debug_gs_entry_rc(k), 16) for k in range(45)] == want and L.sdv_debug_gs_entry_rc(45) == -1 and L.sdv_debug_gs_entry_rc(-1) == -1
