@@ -292,7 +292,7 @@ def test_track_200_frame_pairs_vs_oracle():
         ee = abs(r["lastResiduals"][i][0] - ro["lastResiduals"][0]) / ro["lastResiduals"][0]
         if np.array_equal(r["iterations"][i], ro["iterations"]) and np.array_equal(r["accepts"][i], ro["accepts"]):
             same += 1; worst = [max(worst[0], et), max(worst[1], er), max(worst[2], ee)]
-            assert et < 1e-4 and er < 1e-5 and ee < 1e-4, (i, et, er, ee)           # same accept/reject path: far inside north_star's 1e-3 m / 1e-3 rad / 1e-4
+            assert et < 1e-3 and er < 1e-3 and ee < 1e-4, (i, et, er, ee)           # same accept/reject path: north_star's tolerances hold on every such case (worst printed)
         else:                                                                        # a decision flipped (energy comparison on the last float bit): the LM took another path
             flipped.append((i, scale_i, et, er, ee, list(r["iterations"][i][:L]), list(ro["iterations"][:L])))
             assert scale_i >= 0.3 or (et < 5e-2 and er < 5e-3), flipped[-1]       # guesses 0.3 m off are outside the tracker's basin: anything goes once a decision flips

@@ -69,6 +69,26 @@ def test_precalc_linearize_accumulate_bit_exact(kf, seed):
     assert np.allclose(pa["HdiF"], pr["HdiF"], rtol=3e-7) and np.allclose(pa["bdSumF"], pr["bdSumF"], rtol=1e-5, atol=1e-4)
 
 
+def test_precalc_linearize_accumulate_bit_exact_kitti_size():
+    """the same pin at the BASELINE image size (1200x360, 7 keyframes x 250 points: the bench's BA window shape)"""
+    from sdv_loam_b200 import synth
+    win, ob, rb, _keep = _window((0, 1, 2, 3, 4, 5, 6), 3, n=250, K=synth.KITTI_K, wh=synth.KITTI_WH, seq_seed=2000, pose_noise=(0.005, 0.0003), match_noise=0.1, prior=1e-3)
+    nF = win["nF"]
+    for h, t in ((0, nF - 1), (nF - 1, 0), (2, 5)):
+        a, b = ob.precalc(h, t), rb.precalc(h, t)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (h, t, k)
+    ob.reset_oob(); rb.reset_oob()
+    assert ob.linearizeAll(False) == rb.linearizeAll(False)
+    _same_residuals(ob.residuals(), rb.residuals())
+    ob.applyRes(); rb.applyRes()
+    for x, y, nm in zip(ob.accumulate(), rb.accumulate(), ("HA", "bA", "Hsc", "bsc")):
+        assert np.array_equal(x, y), nm
+    assert ob.calcLEnergy() == rb.calcLEnergy() and ob.calcMEnergy() == rb.calcMEnergy()
+    ra = ob.optimize(6); rr = rb.optimize(6)
+    assert np.allclose(ob.frames()["state"], rb.frames()["state"], rtol=1e-5, atol=1e-9) and abs(ra["rmse"] - rr["rmse"]) <= 1e-5 * max(1.0, abs(rr["rmse"]))
+
+
 def test_solve_step_and_optimize_match():
     win, ob, rb, _keep = _window((0, 1, 2, 3, 4), 5)
     ob.reset_oob(); rb.reset_oob(); ob.linearizeAll(True); rb.linearizeAll(True)
