@@ -523,3 +523,12 @@ def optimizeImmaturePointBatch(ctx: Context, pt_begin, tgt_begin, target_frame_i
     ctx._ck(LIB.sdv_immature_optimize_batch(ctx.p, ng, pb, tb, np.ascontiguousarray(target_frame_ids, np.uint64), np.ascontiguousarray(pre14, np.float32).reshape(-1),
                                             np.ascontiguousarray(calib6, np.float32).reshape(-1), min_obs, pts.ctypes.data, None if fs is None else fs.ctypes.data, stride, st, idp, rs.reshape(-1)))
     return st, idp, rs
+
+
+def coarseTrackingLogLine(frame_id: int, timestamp: float, ab_exposure: float, result: dict) -> str:
+    """One line of the reference's coarseTrackingLog (FullSystem.cpp:500-513, written when setting_logStuff is on):
+    id timestamp ab_exposure camToWorld.log()[6] a b achievedRes[0] tryIterations — `result` is one element of trackNewCoarseBatch's return."""
+    from . import synth
+    lg = synth.se3_log7(np.asarray(result["camToWorld"], np.float64))
+    vals = [frame_id, timestamp, ab_exposure, *lg, result["aff_g2l"][0], result["aff_g2l"][1], result["lastCoarseRMSE"][0], result["tries"]]
+    return " ".join(("%d" % v) if isinstance(v, (int, np.integer)) else ("%.16g" % v) for v in vals)

@@ -876,6 +876,7 @@ __global__ void __launch_bounds__(THREADS, MINB) track_cluster_kernel(TrackJob* 
       SDV_PROF_T(tq4);
       EvalParams ep;
       if (new_ep) make_eval_params(ep_pose, ep_a, ep_b, J.refExposure, J.newExposure, J.ref_a, J.ref_b, tc.geom[ep_lvl], ep_lvl, tc.coarseCutoffTH*ep_lcr, tc.huberTH, ep);
+      __syncwarp();                                          // every lane has read the old control state (racecheck: warp-level WAR on ctl.incn / ctl.haveRepeated otherwise)
       if (L0) {                                              // publish (plain predicated stores; nothing collective follows inside this block)
         ctl.cur = cur; ctl.a_cur = a_cur; ctl.b_cur = b_cur; ctl.cand = cand; ctl.a_cand = a_cand; ctl.b_cand = b_cand;
 #pragma unroll
