@@ -435,3 +435,115 @@ def immature_optimize(pts, is_from_sensor, target_frames, pre14, calib6, min_obs
     st = np.zeros(n, np.int32); idp = np.zeros(n, np.float32); rs = np.zeros((n, nres), np.int32)
     L.orc_immature_optimize(n, pts.ctypes.data, fs.ctypes.data, nres, tf, np.ascontiguousarray(pre14, np.float32).reshape(-1), np.ascontiguousarray(calib6, np.float32), min_obs, st, idp, rs.reshape(-1))
     return st, idp, rs
+
+
+# ---------------------------------------------------------------------------------------------- candidate management (orc_select.cpp): PixelSelector, makeNewTraces, CoarseDistanceMap
+NEW_TRACE_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("my_type", "<f4"), ("score", "<f4"), ("idepth_fromSensor", "<f4"), ("isFromSensor", "<i4"), ("type", "<i4")])
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def libc_random_pattern(w: int, h: int):
+    """PixelSelector::PixelSelector (PixelSelector2.cpp:14-16): srand(3141592); randomPattern[i] = rand() & 0xFF — glibc's rand(), through ctypes"""
+    libc = C.CDLL(None); libc.srand(3141592)
+    return np.array([libc.rand() & 0xFF for _ in range(w * h)], np.uint8)
+
+
+def _cloud(cloud3):
+    return None if cloud3 is None else np.ascontiguousarray(cloud3, np.float64).reshape(-1, 3)
+
+
+class Selector:
+    """PixelSelector (FullSystem/PixelSelector2.cpp) on orc Frames; state = currentPotential + the histogram thresholds of the last frame."""
+
+    def __init__(self, w, h, random_pattern):
+        L = lib(); self.w, self.h = w, h
+        L.orc_selector_create.restype = C.c_void_p; L.orc_selector_create.argtypes = [C.c_int, C.c_int, _u8p]
+        L.orc_selector_destroy.argtypes = [C.c_void_p]; L.orc_selector_set_potential.argtypes = [C.c_void_p, C.c_int]; L.orc_selector_get_potential.argtypes = [C.c_void_p]
+        L.orc_selector_make_hists.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p]
+        L.orc_selector_select.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.c_int, C.c_float, C.c_void_p, C.c_int, _i32p]
+        L.orc_selector_make_maps.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_int]
+        L.orc_make_new_traces.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, _f32p, C.c_void_p, C.c_int, _i32p, _i32p]
+        L.orc_shi_tomasi.restype = C.c_float; L.orc_shi_tomasi.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        self.p = L.orc_selector_create(w, h, np.ascontiguousarray(random_pattern, np.uint8))
+
+    @property
+    def currentPotential(self): return lib().orc_selector_get_potential(self.p)
+    @currentPotential.setter
+    def currentPotential(self, v): lib().orc_selector_set_potential(self.p, int(v))
+
+    def makeHists(self, frame):
+        n = (self.w // 32) * (self.h // 32); a = np.zeros(n, np.float32); b = np.zeros(n, np.float32); lib().orc_selector_make_hists(self.p, frame.p, a, b); return a, b
+
+    def select(self, frame, pot, thFactor=1.0, cloud3=None):
+        """one pass of select (cloud3 None: map over pixels) / selectFromLidar (map over cloud rows); makeHists must have run.  -> map, (n2, n3, n4)"""
+        c = _cloud(cloud3); m = np.zeros(self.w * self.h if c is None else max(len(c), 1), np.float32); n3 = np.zeros(3, np.int32)
+        lib().orc_selector_select(self.p, frame.p, m, pot, thFactor, None if c is None else c.ctypes.data, 0 if c is None else len(c), n3)
+        return (m.reshape(self.h, self.w) if c is None else m[:len(c)]), n3
+
+    def makeMaps(self, frame, density, recursionsLeft=1, thFactor=1.0, cloud3=None):
+        """makeMaps / makeMapsFromLidar (makeHists included) -> map, numHaveSub"""
+        c = _cloud(cloud3); m = np.zeros(self.w * self.h if c is None else max(len(c), 1), np.float32)
+        n = lib().orc_selector_make_maps(self.p, frame.p, m, density, recursionsLeft, thFactor, None if c is None else c.ctypes.data, 0 if c is None else len(c))
+        return (m.reshape(self.h, self.w) if c is None else m[:len(c)]), n
+
+    def makeNewTraces(self, frame, cloud3, densityLidar, densityDense, addFeaturePoint, selectionMap, cap=1 << 16):
+        """FullSystem::makeNewTraces; selectionMap (h, w) float32 is updated in place when addFeaturePoint.  -> NEW_TRACE_DTYPE records, (numPointLidar, numPointMonocular), passes"""
+        assert lib().orc_new_trace_bytes() == NEW_TRACE_DTYPE.itemsize and selectionMap.dtype == np.float32 and selectionMap.flags.c_contiguous
+        c = _cloud(cloud3); out = np.zeros(cap, NEW_TRACE_DTYPE); num = np.zeros(2, np.int32); passes = np.zeros(2, np.int32)
+        m = lib().orc_make_new_traces(self.p, frame.p, c.ctypes.data, len(c), densityLidar, densityDense, int(addFeaturePoint), selectionMap.reshape(-1), out.ctypes.data, cap, num, passes)
+        assert m <= cap
+        return out[:m], num, passes
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            _LIB.orc_selector_destroy(self.p); self.p = None
+
+
+def shi_tomasi(frame, u, v):
+    L = lib(); L.orc_shi_tomasi.restype = C.c_float; L.orc_shi_tomasi.argtypes = [C.c_void_p, C.c_int, C.c_int]; return L.orc_shi_tomasi(frame.p, int(u), int(v))
+
+
+def lidar_density(lrud, wh, desiredImmatureDensity):
+    """((float)lidarArea/(float)imageArea) * setting_desiredImmatureDensity (FullSystem.cpp:1287-1290), in float like the reference"""
+    area = (lrud[1] - lrud[0]) * (lrud[3] - lrud[2])
+    return float(np.float32(np.float32(area) / np.float32(wh[0] * wh[1])) * np.float32(desiredImmatureDensity))
+
+
+def distmap_geometry(K4, host_c2w7, new_c2w7):
+    """KRKi = K[1] R Ki[0], Kt = K[1] t of host -> newest (FullSystem.cpp:606-608 / CoarseTracker.cpp:1156-1158), floats as the reference casts them; level-1 K per CoarseDistanceMap::makeK"""
+    fx, fy, cx, cy = [np.float32(k) for k in K4]
+    K0 = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+    fx1, fy1 = np.float32(np.float64(fx) * 0.5), np.float32(np.float64(fy) * 0.5)
+    cx1, cy1 = np.float32((np.float64(cx) + 0.5) / 2 - 0.5), np.float32((np.float64(cy) + 0.5) / 2 - 0.5)
+    K1 = np.array([[fx1, 0, cx1], [0, fy1, cy1], [0, 0, 1]], np.float32)
+    return K0, K1
+
+
+class DistMap:
+    """CoarseDistanceMap (CoarseTracker.cpp:1139-1282) at level-1 resolution, and the candidate walk of activatePointsMT"""
+
+    def __init__(self, w1, h1):
+        L = lib(); self.w1, self.h1 = w1, h1
+        L.orc_distmap_create.restype = C.c_void_p; L.orc_distmap_create.argtypes = [C.c_int, C.c_int]; L.orc_distmap_destroy.argtypes = [C.c_void_p]
+        L.orc_distmap_make.argtypes = [C.c_void_p, C.c_int, _i32p, _f32p, _f32p, _f32p]; L.orc_distmap_add.argtypes = [C.c_void_p, C.c_int, C.c_int]; L.orc_distmap_get.argtypes = [C.c_void_p, _f32p]
+        L.orc_activate_select.argtypes = [C.c_void_p, C.c_int, _i32p, _f32p, _f32p, _f32p, C.c_float, _i32p]
+        self.p = L.orc_distmap_create(w1, h1)
+
+    def make(self, pt_begin, KRKi, Kt, uvid):
+        pt_begin = np.ascontiguousarray(pt_begin, np.int32)
+        lib().orc_distmap_make(self.p, len(pt_begin) - 1, pt_begin, np.ascontiguousarray(KRKi, np.float32).reshape(-1), np.ascontiguousarray(Kt, np.float32).reshape(-1), np.ascontiguousarray(uvid, np.float32).reshape(-1))
+
+    def add(self, u, v): lib().orc_distmap_add(self.p, int(u), int(v))
+
+    def get(self):
+        o = np.zeros(self.w1 * self.h1, np.float32); lib().orc_distmap_get(self.p, o); return o.reshape(self.h1, self.w1)
+
+    def activateSelect(self, cand_begin, KRKi, Kt, cand4, currentMinActDist):
+        cand_begin = np.ascontiguousarray(cand_begin, np.int32); dec = np.zeros(cand_begin[-1], np.int32)
+        lib().orc_activate_select(self.p, len(cand_begin) - 1, cand_begin, np.ascontiguousarray(KRKi, np.float32).reshape(-1), np.ascontiguousarray(Kt, np.float32).reshape(-1),
+                                  np.ascontiguousarray(cand4, np.float32).reshape(-1), currentMinActDist, dec)
+        return dec
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            _LIB.orc_distmap_destroy(self.p); self.p = None

@@ -473,3 +473,88 @@ class ImmaturePoint:
                 lib().ref_immature_destroy(self.p); self.p = None
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------- candidate management: PixelSelector, makeNewTraces, CoarseDistanceMap (the reference's own)
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+
+
+def _sel_protos(L):
+    L.ref_selector_create.restype = _vp; L.ref_selector_create.argtypes = []; L.ref_selector_destroy.argtypes = [_vp]; L.ref_selector_destroy.restype = None
+    L.ref_selector_random_pattern.argtypes = [_vp, _u8p]; L.ref_selector_set_potential.argtypes = [_vp, C.c_int]; L.ref_selector_get_potential.argtypes = [_vp]
+    L.ref_selector_make_hists.argtypes = [_vp, _vp, _f32p, _f32p]
+    L.ref_selector_select.argtypes = [_vp, _vp, _f32p, C.c_int, C.c_float, _vp, C.c_int, _i32p]
+    L.ref_selector_make_maps.argtypes = [_vp, _vp, _f32p, C.c_float, C.c_int, C.c_float, _vp, C.c_int]
+    L.ref_ba_selector.restype = _vp; L.ref_ba_selector.argtypes = [_vp]
+    L.ref_shi_tomasi.restype = C.c_float; L.ref_shi_tomasi.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.ref_make_new_traces.argtypes = [_vp, _vp, _vp, C.c_int, _i32p, C.c_int, C.c_float, _f32p, _f32p, C.c_int]
+    L.ref_distmap_make.argtypes = [_vp, C.c_int]; L.ref_distmap_add.argtypes = [_vp, C.c_int, C.c_int]; L.ref_distmap_get.argtypes = [_vp, _f32p]
+    L.ref_distmap_geometry.argtypes = [_vp, C.c_int, C.c_int, _f32p, _f32p]
+    L.ref_activate_select.argtypes = [_vp, C.c_int, C.c_int, _i32p, _i32p, _f32p, C.c_float, _i32p]
+    return L
+
+
+class Selector:
+    """The reference's PixelSelector (own object, or the one inside a BAWindow's FullSystem when `owner` is given)."""
+
+    def __init__(self, wh, owner=None):
+        L = _sel_protos(lib()); self.w, self.h = wh; self.owner = owner
+        self.p = L.ref_ba_selector(owner.p) if owner is not None else L.ref_selector_create()
+
+    def randomPattern(self):
+        o = np.zeros(self.w * self.h, np.uint8); lib().ref_selector_random_pattern(self.p, o); return o
+
+    @property
+    def currentPotential(self): return lib().ref_selector_get_potential(self.p)
+    @currentPotential.setter
+    def currentPotential(self, v): lib().ref_selector_set_potential(self.p, int(v))
+
+    def makeHists(self, frame):
+        n = (self.w // 32) * (self.h // 32); a = np.zeros(n, np.float32); b = np.zeros(n, np.float32); lib().ref_selector_make_hists(self.p, frame.p, a, b); return a, b
+
+    def select(self, frame, pot, thFactor=1.0, cloud3=None):
+        c = None if cloud3 is None else np.ascontiguousarray(cloud3, np.float64).reshape(-1, 3)
+        m = np.zeros(self.w * self.h if c is None else max(len(c), 1), np.float32); n3 = np.zeros(3, np.int32)
+        lib().ref_selector_select(self.p, frame.p, m, pot, thFactor, None if c is None else c.ctypes.data, 0 if c is None else len(c), n3)
+        return (m.reshape(self.h, self.w) if c is None else m[:len(c)]), n3
+
+    def makeMaps(self, frame, density, recursionsLeft=1, thFactor=1.0, cloud3=None):
+        c = None if cloud3 is None else np.ascontiguousarray(cloud3, np.float64).reshape(-1, 3)
+        m = np.zeros(self.w * self.h if c is None else max(len(c), 1), np.float32)
+        n = lib().ref_selector_make_maps(self.p, frame.p, m, density, recursionsLeft, thFactor, None if c is None else c.ctypes.data, 0 if c is None else len(c))
+        return (m.reshape(self.h, self.w) if c is None else m[:len(c)]), n
+
+    def __del__(self):
+        if self.owner is None and getattr(self, "p", None) and _LIB is not None:
+            _LIB.ref_selector_destroy(self.p); self.p = None
+
+
+def shi_tomasi(ba: "BAWindow", frame: "Frame", u, v):
+    return _sel_protos(lib()).ref_shi_tomasi(ba.p, frame.p, int(u), int(v))
+
+
+def make_new_traces(ba: "BAWindow", frame: "Frame", cloud3, lrud, addFeaturePoint, desiredImmatureDensity, selectionMap, cap=1 << 16):
+    """FullSystem::makeNewTraces of the BAWindow's FullSystem on `frame` -> rows {u, v, my_type, score, idepth_fromSensor, isFromSensor, type}; selectionMap updated in place"""
+    L = _sel_protos(lib()); c = np.ascontiguousarray(cloud3, np.float64).reshape(-1, 3); out = np.zeros((cap, 7), np.float32)
+    with _Quiet():
+        m = L.ref_make_new_traces(ba.p, frame.p, c.ctypes.data, len(c), np.ascontiguousarray(lrud, np.int32), int(addFeaturePoint), desiredImmatureDensity, selectionMap.reshape(-1), out.reshape(-1), cap)
+    assert m <= cap
+    return out[:m]
+
+
+class DistMap:
+    """CoarseDistanceMap of a BAWindow's FullSystem (sources: the window's ACTIVE points), newest = frame index `frame_idx`"""
+
+    def __init__(self, ba: "BAWindow", frame_idx: int, wh):
+        self.ba, self.frame_idx = ba, frame_idx; self.w1, self.h1 = wh[0] >> 1, wh[1] >> 1; _sel_protos(lib())
+
+    def make(self): lib().ref_distmap_make(self.ba.p, self.frame_idx)
+    def add(self, u, v): lib().ref_distmap_add(self.ba.p, int(u), int(v))
+    def get(self):
+        o = np.zeros(self.w1 * self.h1, np.float32); lib().ref_distmap_get(self.ba.p, o); return o.reshape(self.h1, self.w1)
+    def geometry(self, host_idx):
+        a = np.zeros(9, np.float32); b = np.zeros(3, np.float32); lib().ref_distmap_geometry(self.ba.p, host_idx, self.frame_idx, a, b); return a, b
+    def activateSelect(self, host_idx, cand_begin, cand4, currentMinActDist):
+        cand_begin = np.ascontiguousarray(cand_begin, np.int32); dec = np.zeros(cand_begin[-1], np.int32)
+        lib().ref_activate_select(self.ba.p, self.frame_idx, len(host_idx), np.ascontiguousarray(host_idx, np.int32), cand_begin, np.ascontiguousarray(cand4, np.float32).reshape(-1), currentMinActDist, dec)
+        return dec

@@ -95,6 +95,11 @@ void* ref_frame_create(const float* color, float exposure) {
   f->fh = new FrameHessian(); f->fh->shell = f->shell; f->fh->ab_exposure = exposure;
   std::vector<float> c(color, color + (size_t)wG[0]*hG[0]);
   f->fh->makeImages(c.data(), g_calib);
+  // makeImages never writes the first and the last row of absSquaredGrad[lvl] / of the gradient channels (HessianBlocks.cpp:147: idx in [wl, wl*(hl-1))) and the
+  // arrays come from new[]: PixelSelector reads the last level-2 row for pixels of row h-4 (PixelSelector2.cpp:306).  Define those rows as zero (what a fresh
+  // heap page holds) so the pins are deterministic; nothing the reference computes is changed.
+  for (int l = 0; l < pyrLevelsUsed; l++) { int wl = wG[l], hl = hG[l]; float* a = f->fh->absSquaredGrad[l]; Eigen::Vector3f* d = f->fh->dIp[l];
+    for (int x = 0; x < wl; x++) { a[x] = 0; a[(size_t)wl*(hl-1)+x] = 0; d[x][1] = d[x][2] = 0; d[(size_t)wl*(hl-1)+x][1] = d[(size_t)wl*(hl-1)+x][2] = 0; } }
   f->fh->setEvalPT_scaled(SE3(), AffLight(0, 0));
   return f;
 }
@@ -532,6 +537,79 @@ int ref_ba_optimize_immature(void* p, int host, int u, int v, float idepth_min, 
   else { rc = 1; *idepth_out = ph->idepth; ph->release(); delete ph; }
   delete ip;
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- candidate management at keyframe rate (SURVEY §8f rank 4 + the caller half of rank 2)
+// PixelSelector (FullSystem/PixelSelector2.cpp), FullSystem::makeNewTraces / shiTomasiScore (FullSystem.cpp:1273-1356, 1540-1583), CoarseDistanceMap (CoarseTracker.cpp:1139-1282).
+// The reference's selector reads thsSmoothed past its (h/32) rows for the last image rows and never initialises that tail (PixelSelector2.cpp:18-20, 268): the shim zeroes the
+// selector's heap arrays once after construction so the pin is deterministic (a fresh heap block reads as zero too).
+static void selector_zero(PixelSelector* s) { int n = (wG[0]/32)*(hG[0]/32)+100; memset(s->ths, 0, n*sizeof(float)); memset(s->thsSmoothed, 0, n*sizeof(float));
+  memset(s->gradHist, 0, sizeof(int)*100*(1+wG[0]/32)*(1+hG[0]/32)); }
+void* ref_selector_create() { PixelSelector* s = new PixelSelector(wG[0], hG[0]); selector_zero(s); return s; }      // srand(3141592) + w*h rand() calls (PixelSelector2.cpp:14-16)
+void  ref_selector_destroy(void* s) { delete (PixelSelector*)s; }
+void  ref_selector_random_pattern(void* s, unsigned char* out) { memcpy(out, ((PixelSelector*)s)->randomPattern, (size_t)wG[0]*hG[0]); }
+void  ref_selector_set_potential(void* s, int p) { ((PixelSelector*)s)->currentPotential = p; }
+int   ref_selector_get_potential(void* s) { return ((PixelSelector*)s)->currentPotential; }
+void  ref_selector_make_hists(void* s, void* frame, float* ths, float* thsSmoothed) { PixelSelector* S = (PixelSelector*)s; S->makeHists(((RefFrame*)frame)->fh);
+  int n = (wG[0]/32)*(hG[0]/32); if (ths) memcpy(ths, S->ths, n*sizeof(float)); if (thsSmoothed) memcpy(thsSmoothed, S->thsSmoothed, n*sizeof(float)); }
+typedef std::vector<Eigen::Vector3d, Eigen::aligned_allocator<Eigen::Vector3d> > CloudPx;
+static CloudPx cloud_of(const double* c3, int n) { CloudPx v(n); for (int i = 0; i < n; i++) v[i] = Eigen::Vector3d(c3[3*i], c3[3*i+1], c3[3*i+2]); return v; }
+// PixelSelector::select (cloud3 == NULL) / selectFromLidar: one pass at potential `pot`; makeHists must have run on this frame
+void  ref_selector_select(void* s, void* frame, float* map_out, int pot, float thFactor, const double* cloud3, int n, int n3[3]) {
+  PixelSelector* S = (PixelSelector*)s; FrameHessian* fh = ((RefFrame*)frame)->fh; Eigen::Vector3i r;
+  if (cloud3) { CloudPx v = cloud_of(cloud3, n); r = S->selectFromLidar(fh, map_out, pot, thFactor, v); } else r = S->select(fh, map_out, pot, thFactor);
+  n3[0] = r[0]; n3[1] = r[1]; n3[2] = r[2];
+}
+int   ref_selector_make_maps(void* s, void* frame, float* map_out, float density, int recursionsLeft, float thFactor, const double* cloud3, int n) {
+  PixelSelector* S = (PixelSelector*)s; FrameHessian* fh = ((RefFrame*)frame)->fh; S->gradHistFrame = 0;
+  if (cloud3) { CloudPx v = cloud_of(cloud3, n); return S->makeMapsFromLidar(fh, map_out, density, recursionsLeft, false, thFactor, v); }
+  return S->makeMaps(fh, map_out, density, recursionsLeft, false, thFactor);
+}
+void* ref_ba_selector(void* p) { PixelSelector* s = ((RefBA*)p)->fs->pixelSelector; selector_zero(s); return s; }
+float ref_shi_tomasi(void* p, void* frame, int u, int v) { return ((RefBA*)p)->fs->shiTomasiScore(((RefFrame*)frame)->fh->dI, u, v); }
+// FullSystem::makeNewTraces on `frame` with the LiDAR pixels cloud3 {Ku, Kv, depth}; lidar box = the members main.cpp fills (left/right/up/down); selectionMap_io = the
+// FullSystem's persistent monocular selection map (w*h floats).  out rows: {u, v, my_type, score, idepth_fromSensor, isFromSensor, type}; returns the number of immature points.
+int ref_make_new_traces(void* p, void* frame, const double* cloud3, int n, const int lrud[4], int addFeaturePoint, float desiredImmatureDensity, float* selectionMap_io, float* out7, int cap) {
+  RefBA* b = (RefBA*)p; FullSystem* fs = b->fs; RefFrame* F = (RefFrame*)frame; FrameHessian* fh = F->fh; size_t wh = (size_t)wG[0]*hG[0];
+  fs->left = lrud[0]; fs->right = lrud[1]; fs->up = lrud[2]; fs->down = lrud[3]; fs->addFeaturePoint = addFeaturePoint != 0; float keep = setting_desiredImmatureDensity; setting_desiredImmatureDensity = desiredImmatureDensity;
+  memcpy(fs->selectionMap, selectionMap_io, wh*sizeof(float));
+  F->shell->timestamp = 1.0; fs->qCloudPixel.push(cloud_of(cloud3, n)); fs->qTimeLidarCloud.push(1.0);
+  fs->pixelSelector->gradHistFrame = 0;
+  fs->makeNewTraces(fh, 0);
+  fs->qCloudPixel.pop(); fs->qTimeLidarCloud.pop(); setting_desiredImmatureDensity = keep;
+  memcpy(selectionMap_io, fs->selectionMap, wh*sizeof(float));
+  int m = 0;
+  for (ImmaturePoint* ip : fh->immaturePoints) { if (m < cap) { float* o = out7 + 7*m; o[0] = ip->u; o[1] = ip->v; o[2] = ip->my_type; o[3] = ip->isFromSensor ? ip->score : 0.f;
+      o[4] = ip->isFromSensor ? ip->idepth_fromSensor : 0.f; o[5] = ip->isFromSensor ? 1.f : 0.f; o[6] = ip->isFromSensor ? (float)(int)ip->type : -1.f; } m++; delete ip; }
+  fh->immaturePoints.clear();
+  return m;
+}
+// CoarseDistanceMap of the RefBA's FullSystem: makeK + makeDistanceMap(frameHessians, frameHessians[frame_idx]) — the window's ACTIVE PointHessians are the sources
+void ref_distmap_make(void* p, int frame_idx) { FullSystem* fs = ((RefBA*)p)->fs; fs->coarseDistanceMap->makeK(&fs->Hcalib); fs->coarseDistanceMap->makeDistanceMap(fs->frameHessians, fs->frameHessians[frame_idx]); }
+void ref_distmap_add(void* p, int u, int v) { ((RefBA*)p)->fs->coarseDistanceMap->addIntoDistFinal(u, v); }
+void ref_distmap_get(void* p, float* out) { CoarseDistanceMap* d = ((RefBA*)p)->fs->coarseDistanceMap; memcpy(out, d->fwdWarpedIDDistFinal, sizeof(float)*(size_t)d->w[1]*d->h[1]); }
+// KRKi = K[1] R Ki[0], Kt = K[1] t of host -> newest as FullSystem::activatePointsMT forms them (FullSystem.cpp:606-608)
+void ref_distmap_geometry(void* p, int host_idx, int frame_idx, float KRKi9[9], float Kt3[3]) {
+  FullSystem* fs = ((RefBA*)p)->fs; FrameHessian* host = fs->frameHessians[host_idx]; FrameHessian* newest = fs->frameHessians[frame_idx]; CoarseDistanceMap* d = fs->coarseDistanceMap;
+  SE3 fhToNew = newest->PRE_worldToCam * host->PRE_camToWorld;
+  Mat33f KRKi = (d->K[1] * fhToNew.rotationMatrix().cast<float>() * d->Ki[0]); Vec3f Kt = (d->K[1] * fhToNew.translation().cast<float>());
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) KRKi9[3*i+j] = KRKi(i, j); Kt3[i] = Kt[i]; }
+}
+// the candidate walk of activatePointsMT (FullSystem.cpp:600-671) over flat candidates, on the reference's own distance map (its BFS does the work); the ten lines of
+// loop control are shim code.  cand rows {u, v, 0.5f*(idepth_max+idepth_min), my_type} grouped by host (window order)
+void ref_activate_select(void* p, int frame_idx, int nHosts, const int* host_idx, const int* cand_begin, const float* cand4, float currentMinActDist, int* decision) {
+  FullSystem* fs = ((RefBA*)p)->fs; CoarseDistanceMap* D = fs->coarseDistanceMap; FrameHessian* newestHs = fs->frameHessians[frame_idx];
+  for (int hI = 0; hI < nHosts; hI++) { FrameHessian* host = fs->frameHessians[host_idx[hI]];
+    SE3 fhToNew = newestHs->PRE_worldToCam * host->PRE_camToWorld;
+    Mat33f KRKi = (D->K[1] * fhToNew.rotationMatrix().cast<float>() * D->Ki[0]); Vec3f Kt = (D->K[1] * fhToNew.translation().cast<float>());
+    for (int c = cand_begin[hI]; c < cand_begin[hI+1]; c++) {
+      Vec3f ptp = KRKi * Vec3f(cand4[4*c], cand4[4*c+1], 1) + Kt*cand4[4*c+2];
+      int u = ptp[0] / ptp[2] + 0.5f; int v = ptp[1] / ptp[2] + 0.5f;
+      if ((u > 0 && v > 0 && u < wG[1] && v < hG[1])) {
+        float dist = D->fwdWarpedIDDistFinal[u+wG[1]*v] + (ptp[0]-floorf((float)(ptp[0])));
+        if (dist >= currentMinActDist*cand4[4*c+3]) { D->addIntoDistFinal(u, v); decision[c] = 1; } else decision[c] = 0;
+      } else decision[c] = -1;
+    } }
 }
 
 }  // extern "C"
