@@ -309,6 +309,46 @@ int  sdv_ba_get_linearized(sdv_ctx* c, float* res_toZero2, int32_t* isLinearized
 int  sdv_ba_get_system(sdv_ctx* c, double* HA, double* bA, double* Hsc, double* bsc, double* lastHS, double* lastbS);
 int  sdv_ba_get_precalc(sdv_ctx* c, int host, int target, float out27[27], double adHost36[36], double adTarget36[36], float adHTdelta6[6]);
 
+/* =====================================================================================================================
+ * Candidate management at keyframe rate (SURVEY.md §8f rank 4 and the caller half of rank 2).  Tracker call domain.
+ *   PixelSelector                         FullSystem/PixelSelector2.cpp:11-26 (ctor), :47-106 makeHists, :354-622 makeMapsFromLidar / selectFromLidar,
+ *                                         :108-352 makeMaps / select
+ *   FullSystem::makeNewTraces             FullSystem/FullSystem.cpp:1273-1356 (+ shiTomasiScore :1540-1583, setMask :1261-1271, ImmaturePoint ctor)
+ *   CoarseDistanceMap, activatePointsMT   FullSystem/CoarseTracker.cpp:1139-1282, FullSystem/FullSystem.cpp:600-671
+ * A selector SLOT stands for one PixelSelector / FullSystem::selectionMap pair, i.e. one resident sequence: it carries currentPotential (initially 3) and the
+ * persistent monocular selection map (w*h bytes, values 0 / 1 / 2 / 4 — the reference's float map; zero at birth where the reference's is uninitialised).
+ * random_pattern: the w*h bytes of PixelSelector::randomPattern — the caller generates them exactly like the constructor does (srand(3141592); rand() & 0xFF), so the
+ * library never touches the process-wide rand() stream.  Reads of thsSmoothed past its (h/32) rows — the reference indexes its uninitialised tail for the last
+ * image rows — see zeros here.  LiDAR pixels are rows {Ku, Kv, depth} of doubles, as main.cpp:810-848 pushes them into FullSystem::qCloudPixel. */
+typedef struct { float u, v, my_type, score, idepth_fromSensor; int32_t isFromSensor, type; } sdv_new_trace;   /* type: 0 CORNER, 1 EDGELET (ImmaturePoint.h), -1 not assigned (monocular points) */
+int  sdv_selector_init(sdv_ctx* c, const uint8_t* random_pattern, int n_slots);
+int  sdv_selector_potential(sdv_ctx* c, int slot, int set_to /* <= 0: leave */, int* out);
+int  sdv_selector_get_map(sdv_ctx* c, int slot, uint8_t* out_wh);
+/* void PixelSelector::makeHists(const FrameHessian*): ths / thsSmoothed of the (w/32) x (h/32) blocks */
+int  sdv_selector_make_hists(sdv_ctx* c, uint64_t frame, float* ths_out, float* thsSmoothed_out);
+/* int PixelSelector::makeMapsFromLidar(fh, map_out, density, recursionsLeft, plot, thFactor, vCloudPixel) for n (slot, frame) pairs at once when cloud_begin != NULL
+ * (job j owns cloud rows cloud_begin[j] .. cloud_begin[j+1]; maps_out = the n maps back to back, one byte per cloud row), and
+ * int PixelSelector::makeMaps(fh, map_out, density, recursionsLeft, plot, thFactor) when cloud_begin == NULL (maps_out = n maps of w*h bytes; the slot's persistent map
+ * is the one written).  makeHists runs first, like `if(fh != gradHistFrame) makeHists(fh)`.  num_have_out[j] = the return value; the slot's currentPotential is updated. */
+int  sdv_selector_make_maps_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* frames, const int32_t* cloud_begin, const double* cloud3, const float* density,
+                                  const int32_t* recursions_left, const float* th_factor, uint8_t* maps_out, int32_t* num_have_out);
+/* void FullSystem::makeNewTraces(FrameHessian* newFrame, float*) for n new keyframes (one per sequence / slot) in one call.  density_lidar[j] =
+ * ((float)lidarArea/(float)imageArea) * setting_desiredImmatureDensity (:1287-1290), density_dense[j] = setting_desiredImmatureDensity (:1293), add_feature_point[j] =
+ * FullSystem::addFeaturePoint (off: the slot's map of an EARLIER keyframe is walked again, as in the reference).  Per job up to `cap` points come back in creation order
+ * (LiDAR points in cloud order, then monocular points in raster order): out[j*cap ..] and, if imm_out != NULL, the constructed ImmaturePoint records imm_out[j*cap ..];
+ * n_out[j] = how many; num_points2[2j..] = {numPointLidar, numPointMonocular}.  SDV_ERR_CAPACITY when cap is too small. */
+int  sdv_make_new_traces_batch(sdv_ctx* c, int n, const int32_t* slots, const uint64_t* frames, const int32_t* cloud_begin, const double* cloud3, const float* density_lidar,
+                               const float* density_dense, const int32_t* add_feature_point, int cap, sdv_new_trace* out, sdv_immature_pt* imm_out, int32_t* n_out, int32_t* num_points2);
+/* The selection half of void FullSystem::activatePointsMT() for n sequences: CoarseDistanceMap::makeDistanceMap from the ACTIVE points of the other keyframes, then the
+ * candidate walk :600-671 with addIntoDistFinal after every accept.  Sequence j owns source keyframes host_begin[j] .. host_begin[j+1] (their points: uvid rows
+ * pt_begin[k] .. pt_begin[k+1] = {u, v, idepth_scaled}; KRKi9 / Kt3 per keyframe = K[1] R K[0]^-1, K[1] t of host -> newest, FullSystem.cpp:606-608) and candidate
+ * keyframes cand_host_begin[j] .. (their candidates: cand4 rows {u, v, 0.5f*(idepth_max+idepth_min), my_type} that passed the deletion / canActivate tests of
+ * :618-645, which are pointer-graph bookkeeping).  decision_out per candidate: 1 = handed to optimizeImmaturePoint (sdv_immature_optimize_batch), 0 = too close to
+ * existing points, -1 = projects outside the level-1 image (deleted).  dist_map_out (optional): n maps of (w/2)*(h/2) floats = fwdWarpedIDDistFinal after the walk. */
+int  sdv_activate_select_batch(sdv_ctx* c, int n, const int32_t* host_begin, const int32_t* pt_begin, const float* KRKi9, const float* Kt3, const float* uvid,
+                               const int32_t* cand_host_begin, const int32_t* cand_begin, const float* cKRKi9, const float* cKt3, const float* cand4, const float* min_act_dist,
+                               int32_t* decision_out, float* dist_map_out);
+
 #ifdef __cplusplus
 }
 #endif

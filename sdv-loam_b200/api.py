@@ -82,6 +82,13 @@ def _load():
     L.sdv_immature_trace_batch.argtypes = [_vp, C.c_int, _u64p, _i32p, _f32p, _f32p, _f32p, _vp, _vp]
     L.sdv_immature_optimize_batch.argtypes = [_vp, C.c_int, _i32p, _i32p, _u64p, _f32p, _f32p, C.c_int, _vp, _vp, C.c_int, _i32p, _f32p, _i32p]
     L.sdv_ba_last_kernel_ms.argtypes = [_vp]; L.sdv_ba_last_kernel_ms.restype = C.c_float
+    L.sdv_selector_init.argtypes = [_vp, _vp, C.c_int]
+    L.sdv_selector_potential.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    L.sdv_selector_get_map.argtypes = [_vp, C.c_int, _vp]
+    L.sdv_selector_make_hists.argtypes = [_vp, C.c_uint64, _vp, _vp]
+    L.sdv_selector_make_maps_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _vp, _vp, _f32p, _i32p, _f32p, _vp, _i32p]
+    L.sdv_make_new_traces_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _i32p, _vp, _f32p, _f32p, _i32p, C.c_int, _vp, _vp, _i32p, _i32p]
+    L.sdv_activate_select_batch.argtypes = [_vp, C.c_int, _i32p, _i32p, _vp, _vp, _vp, _i32p, _i32p, _vp, _vp, _vp, _f32p, _vp, _vp]
     return L
 
 
@@ -532,3 +539,82 @@ def coarseTrackingLogLine(frame_id: int, timestamp: float, ab_exposure: float, r
     lg = synth.se3_log7(np.asarray(result["camToWorld"], np.float64))
     vals = [frame_id, timestamp, ab_exposure, *lg, result["aff_g2l"][0], result["aff_g2l"][1], result["lastCoarseRMSE"][0], result["tries"]]
     return " ".join(("%d" % v) if isinstance(v, (int, np.integer)) else ("%.16g" % v) for v in vals)
+
+
+# ---------------------------------------------------------------------------------------------- candidate management at keyframe rate (sdv_select.cu)
+NEW_TRACE_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("my_type", "<f4"), ("score", "<f4"), ("idepth_fromSensor", "<f4"), ("isFromSensor", "<i4"), ("type", "<i4")])
+
+
+def random_pattern(w: int, h: int):
+    """PixelSelector::randomPattern (PixelSelector2.cpp:14-16): srand(3141592); rand() & 0xFF, w*h times — the C library's generator, like the reference.
+    NB: re-seeds the process-wide rand() stream exactly as constructing a PixelSelector does."""
+    libc = C.CDLL(None); libc.srand(3141592)
+    return np.array([libc.rand() & 0xFF for _ in range(w * h)], np.uint8)
+
+
+def lidar_density(lrud, wh, desiredImmatureDensity):
+    """((float)lidarArea/(float)imageArea) * setting_desiredImmatureDensity with lidarArea = (right-left)*(down-up)   FullSystem.cpp:1287-1290"""
+    area = (lrud[1] - lrud[0]) * (lrud[3] - lrud[2])
+    return float(np.float32(np.float32(area) / np.float32(wh[0] * wh[1])) * np.float32(desiredImmatureDensity))
+
+
+class PixelSelector:
+    """n_slots PixelSelector + selectionMap pairs (one per resident sequence) of a context: FullSystem/PixelSelector2.cpp, FullSystem.cpp:180-186"""
+
+    def __init__(self, ctx: Context, n_slots: int = 1, pattern=None):
+        self.ctx = ctx; self.n_slots = n_slots
+        self.pattern = np.ascontiguousarray(pattern if pattern is not None else random_pattern(ctx.w, ctx.h), np.uint8); assert self.pattern.size == ctx.w * ctx.h
+        ctx._ck(LIB.sdv_selector_init(ctx.p, self.pattern.ctypes.data, n_slots))
+
+    def potential(self, slot=0, set_to=None) -> int:
+        o = C.c_int(0); self.ctx._ck(LIB.sdv_selector_potential(self.ctx.p, slot, int(set_to) if set_to else 0, C.byref(o))); return o.value
+
+    def selectionMap(self, slot=0):
+        o = np.zeros((self.ctx.h, self.ctx.w), np.uint8); self.ctx._ck(LIB.sdv_selector_get_map(self.ctx.p, slot, o.ctypes.data)); return o
+
+    def makeHists(self, frame_id):
+        n = (self.ctx.w // 32) * (self.ctx.h // 32); a = np.zeros(n, np.float32); b = np.zeros(n, np.float32)
+        self.ctx._ck(LIB.sdv_selector_make_hists(self.ctx.p, frame_id, a.ctypes.data, b.ctypes.data)); return a, b
+
+    def makeMapsBatch(self, slots, frame_ids, density, recursionsLeft=1, thFactor=1.0, clouds=None):
+        """makeMapsFromLidar (clouds: one (n,3) float64 array {Ku,Kv,depth} per job) or makeMaps (clouds None) for several (slot, frame) pairs -> maps, numHaveSub"""
+        n = len(slots); sl = np.ascontiguousarray(slots, np.int32); fr = np.ascontiguousarray(frame_ids, np.uint64)
+        de = np.ascontiguousarray(np.broadcast_to(density, n), np.float32); rc = np.ascontiguousarray(np.broadcast_to(recursionsLeft, n), np.int32); th = np.ascontiguousarray(np.broadcast_to(thFactor, n), np.float32)
+        num = np.zeros(n, np.int32)
+        if clouds is None:
+            maps = np.zeros((n, self.ctx.h, self.ctx.w), np.uint8)
+            self.ctx._ck(LIB.sdv_selector_make_maps_batch(self.ctx.p, n, sl, fr, None, None, de, rc, th, maps.ctypes.data, num)); return maps, num
+        cl = [np.ascontiguousarray(c, np.float64).reshape(-1, 3) for c in clouds]; cb = np.concatenate([[0], np.cumsum([len(c) for c in cl])]).astype(np.int32)
+        allc = np.ascontiguousarray(np.concatenate(cl) if cb[-1] else np.zeros((1, 3))); maps = np.zeros(max(int(cb[-1]), 1), np.uint8)
+        self.ctx._ck(LIB.sdv_selector_make_maps_batch(self.ctx.p, n, sl, fr, cb.ctypes.data, allc.ctypes.data, de, rc, th, maps.ctypes.data, num))
+        return [maps[cb[j]:cb[j + 1]] for j in range(n)], num
+
+    def makeNewTracesBatch(self, slots, frame_ids, clouds, density_lidar, density_dense, add_feature_point, cap=1 << 14):
+        """FullSystem::makeNewTraces for one new keyframe per slot -> per job (sdv_new_trace records, sdv_immature_pt records), numPoints (n,2)"""
+        n = len(slots); cl = [np.ascontiguousarray(c, np.float64).reshape(-1, 3) for c in clouds]; cb = np.concatenate([[0], np.cumsum([len(c) for c in cl])]).astype(np.int32)
+        allc = np.ascontiguousarray(np.concatenate(cl) if cb[-1] else np.zeros((1, 3)))
+        out = np.zeros((n, cap), NEW_TRACE_DTYPE); imm = np.zeros((n, cap), IMMATURE_PT_DTYPE); n_out = np.zeros(n, np.int32); num = np.zeros(2 * n, np.int32)
+        self.ctx._ck(LIB.sdv_make_new_traces_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(frame_ids, np.uint64), cb, allc.ctypes.data,
+                                                  np.ascontiguousarray(np.broadcast_to(density_lidar, n), np.float32), np.ascontiguousarray(np.broadcast_to(density_dense, n), np.float32),
+                                                  np.ascontiguousarray(np.broadcast_to(add_feature_point, n), np.int32), cap, out.ctypes.data, imm.ctypes.data, n_out, num))
+        return [(out[j, :n_out[j]], imm[j, :n_out[j]]) for j in range(n)], num.reshape(n, 2)
+
+
+def activateSelectBatch(ctx: Context, seqs, want_maps=False):
+    """CoarseDistanceMap::makeDistanceMap + the candidate walk of FullSystem::activatePointsMT for several sequences.  seqs: list of dicts with pt_begin / KRKi / Kt / uvid
+    (source keyframes) and cand_begin / cKRKi / cKt / cand4 / minActDist (candidate keyframes; may be absent).  -> per sequence decisions (+ distance maps)"""
+    n = len(seqs); hb, pb, gb, cb = [0], [0], [0], [0]; A, B, U, cA, cB, c4, md = [], [], [], [], [], [], []
+    f = lambda a, t: np.ascontiguousarray(a, t)
+    for q in seqs:
+        p = f(q["pt_begin"], np.int32); hb.append(hb[-1] + len(p) - 1); pb += list(pb[-1] + p[1:]); A.append(f(q["KRKi"], np.float32).reshape(-1, 9)); B.append(f(q["Kt"], np.float32).reshape(-1, 3)); U.append(f(q["uvid"], np.float32).reshape(-1, 3))
+        g = f(q.get("cand_begin", [0]), np.int32); gb.append(gb[-1] + len(g) - 1); cb += list(cb[-1] + g[1:]); md.append(q.get("minActDist", 0.0))
+        if len(g) > 1: cA.append(f(q["cKRKi"], np.float32).reshape(-1, 9)); cB.append(f(q["cKt"], np.float32).reshape(-1, 3)); c4.append(f(q["cand4"], np.float32).reshape(-1, 4))
+    cat = lambda xs, k: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros((1, k), np.float32))
+    A, B, U, cA, cB, c4 = cat(A, 9), cat(B, 3), cat(U, 3), cat(cA, 9), cat(cB, 3), cat(c4, 4)
+    dec = np.zeros(max(cb[-1], 1), np.int32); maps = np.zeros((n, ctx.h >> 1, ctx.w >> 1), np.float32) if want_maps else None
+    ctx._ck(LIB.sdv_activate_select_batch(ctx.p, n, f(hb, np.int32), f(pb, np.int32), A.ctypes.data, B.ctypes.data, U.ctypes.data, f(gb, np.int32), f(cb, np.int32), cA.ctypes.data, cB.ctypes.data,
+                                          c4.ctypes.data, f(md, np.float32), dec.ctypes.data, maps.ctypes.data if want_maps else None))
+    out = []; k = 0
+    for j in range(n):
+        nc = cb[gb[j + 1]] - cb[gb[j]]; out.append(dec[k:k + nc]); k += nc
+    return (out, maps) if want_maps else out
