@@ -547,3 +547,29 @@ class DistMap:
     def __del__(self):
         if getattr(self, "p", None) and _LIB is not None:
             _LIB.orc_distmap_destroy(self.p); self.p = None
+
+
+# ---------------------------------------------------------------------------------------------- LiDAR front-end of the node (orc_lidar.cpp): src/main.cpp:563-858
+class LidarFrontEnd:
+    """projectPointCloud -> groundRemoval -> cloudSegmentation -> pixel projection of lidarCloudHandler; lrud = FullSystem::left/right/up/down (running box)"""
+
+    def __init__(self, n_scan=64, horizon=1800, ang_res_x=0.2, ang_res_y=0.427, ang_bottom=24.9, groundScanInd=50):
+        L = lib(); self.n_scan, self.horizon = n_scan, horizon
+        L.orc_lidar_create.restype = C.c_void_p; L.orc_lidar_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]; L.orc_lidar_destroy.argtypes = [C.c_void_p]
+        L.orc_lidar_handler.argtypes = [C.c_void_p, _f32p, C.c_int, _f64p, _f64p, _f32p, C.c_int, C.c_int, _i32p, _f64p, C.c_int, _i32p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.p = L.orc_lidar_create(n_scan, horizon, ang_res_x, ang_res_y, ang_bottom, groundScanInd)
+
+    def handle(self, xyzi, Rlc, tlc, K4, wh, lrud, images=False):
+        xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4); cap = self.n_scan * self.horizon; out = np.zeros((cap, 3)); flags = np.zeros(4, np.int32)
+        lrud = np.ascontiguousarray(lrud, np.int32).copy(); m = self.n_scan * self.horizon
+        rng, lab, gnd = (np.zeros(m, np.float32), np.zeros(m, np.int32), np.zeros(m, np.int8)) if images else (None, None, None)
+        k = lib().orc_lidar_handler(self.p, xyzi.reshape(-1), len(xyzi), np.ascontiguousarray(Rlc, np.float64).reshape(-1), np.ascontiguousarray(tlc, np.float64), np.ascontiguousarray(K4, np.float32),
+                                    wh[0], wh[1], lrud, out.reshape(-1), cap, flags, *(a.ctypes.data if a is not None else None for a in (rng, lab, gnd)))
+        assert k >= 0
+        r = dict(cloud_px=out[:k].copy(), lrud=lrud, addFeaturePoint=int(flags[0]), numGround=int(flags[1]), numAll=int(flags[2]), n_segmented=int(flags[3]))
+        if images: r.update(range=rng.reshape(self.n_scan, self.horizon), label=lab.reshape(self.n_scan, self.horizon), ground=gnd.reshape(self.n_scan, self.horizon))
+        return r
+
+    def __del__(self):
+        if getattr(self, "p", None) and _LIB is not None:
+            _LIB.orc_lidar_destroy(self.p); self.p = None

@@ -558,3 +558,19 @@ class DistMap:
         cand_begin = np.ascontiguousarray(cand_begin, np.int32); dec = np.zeros(cand_begin[-1], np.int32)
         lib().ref_activate_select(self.ba.p, self.frame_idx, len(host_idx), np.ascontiguousarray(host_idx, np.int32), cand_begin, np.ascontiguousarray(cand4, np.float32).reshape(-1), currentMinActDist, dec)
         return dec
+
+
+def lidar_handler(ba: "BAWindow", xyzi, Rlc, tlc, K4, lrud, images=False):
+    """The reference's own lidarCloudHandler (src/main.cpp:785-858: projectPointCloud, groundRemoval, cloudSegmentation, pixel projection) on one decoded XYZI sweep, with the
+    FullSystem of `ba` as the node's global system (extrinsics, intrinsics, running pixel box).  Image size = the global calibration (set_calib)."""
+    L = lib(); L.ref_lidar_handler.argtypes = [_vp, _f32p, C.c_int, _f64p, _f64p, _f32p, _i32p, _f64p, C.c_int, _i32p, _vp, _vp, _vp]; L.ref_lidar_dims.argtypes = [_i32p, _i32p]
+    a = np.zeros(1, np.int32); b = np.zeros(1, np.int32); L.ref_lidar_dims(a, b); n_scan, horizon = int(a[0]), int(b[0]); m = n_scan * horizon
+    xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4); out = np.zeros((m, 3)); flags = np.zeros(4, np.int32); lrud = np.ascontiguousarray(lrud, np.int32).copy()
+    rng, lab, gnd = (np.zeros(m, np.float32), np.zeros(m, np.int32), np.zeros(m, np.int8)) if images else (None, None, None)
+    with _Quiet():
+        k = L.ref_lidar_handler(ba.p, xyzi.reshape(-1), len(xyzi), np.ascontiguousarray(Rlc, np.float64).reshape(-1), np.ascontiguousarray(tlc, np.float64), np.ascontiguousarray(K4, np.float32), lrud,
+                                out.reshape(-1), m, flags, *(x.ctypes.data if x is not None else None for x in (rng, lab, gnd)))
+    assert k >= 0
+    r = dict(cloud_px=out[:k].copy(), lrud=lrud, addFeaturePoint=int(flags[0]), n_segmented=int(flags[3]))
+    if images: r.update(range=rng.reshape(n_scan, horizon), label=lab.reshape(n_scan, horizon), ground=gnd.reshape(n_scan, horizon))
+    return r

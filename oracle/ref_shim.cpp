@@ -32,6 +32,9 @@
 #include "sensor_msgs/Image.h"
 #include "sensor_msgs/PointCloud2.h"
 #include "cv_bridge/cv_bridge.h"
+#include "pcl/point_cloud.h"
+#include "pcl_conversions/pcl_conversions.h"
+#include "pcl/filters/filter.h"
 #define private public                                     // the reference keeps calcRes / calcGSSSE / linearizeAll ... private; the shim calls them directly
 #define protected public
 #include "FullSystem/FullSystem.h"
@@ -611,5 +614,46 @@ void ref_activate_select(void* p, int frame_idx, int nHosts, const int* host_idx
       } else decision[c] = -1;
     } }
 }
+
+// ---------------------------------------------------------------------------------------------- LiDAR front-end of the ROS node (src/main.cpp:537-858), compiled unmodified (oracle/Makefile)
+// main.cpp keeps its state in globals (range / label / ground images, fullCloud, segmentedCloud) and reads the extrinsics / intrinsics from the global FullSystem.
+// The shim feeds lidarCloudHandler one decoded XYZI sweep (the stand-in PointCloud2 carries the rows pcl::fromROSMsg would decode) and reads the results back.
+void ref_unavailable() { fprintf(stderr, "oracle/_ref: a GUI / image-decoding entry of the reference was called; it is not part of this build\n"); abort(); }
+}  // extern "C"
+typedef pcl::PointXYZI RefPointType;
+extern FullSystem* fullSystem;
+extern pcl::PointCloud<RefPointType>::Ptr laserCloudIn, fullCloud, fullInfoCloud, groundCloud, segmentedCloud, segmentedCloudPure, outlierCloud;
+extern cv::Mat rangeMat, labelMat, groundMat;
+extern const int N_SCAN, Horizon_SCAN;
+void allocateMemory(); void resetParameters(); void lidarCloudHandler(const sensor_msgs::PointCloud2ConstPtr& lidarCloudMsg);
+void projectPointCloud(); void groundRemoval(); void cloudSegmentation();
+extern "C" {
+static bool g_lidar_ready = false;
+// Rlc (row-major 3x3), tlc: LiDAR -> camera; K4 = fx fy cx cy (FullSystem members main.cpp:368-377 fills from the sensor file); lrud_io = FullSystem::left/right/up/down (running box)
+// out rows {Ku, Kv, depth}; returns the number of pixels pushed into qCloudPixel (or -1 if cap is too small); flags_out = {addFeaturePoint, numGround, numAll, size of segmentedCloud}
+int ref_lidar_handler(void* ba, const float* xyzi, int n, const double* Rlc9, const double* tlc3, const float* K4, int* lrud_io, double* out3, int cap, int* flags_out, float* range_out, int* label_out, signed char* ground_out) {
+  RefBA* b = (RefBA*)ba; FullSystem* fs = b->fs; fullSystem = fs;
+  if (!g_lidar_ready) { allocateMemory(); resetParameters(); g_lidar_ready = true; }
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) fs->Rlc(i, j) = Rlc9[3*i+j]; fs->tlc[i] = tlc3[i]; }
+  fs->fx = K4[0]; fs->fy = K4[1]; fs->cx = K4[2]; fs->cy = K4[3]; fs->left = lrud_io[0]; fs->right = lrud_io[1]; fs->up = lrud_io[2]; fs->down = lrud_io[3];
+  std::shared_ptr<sensor_msgs::PointCloud2> msg = std::make_shared<sensor_msgs::PointCloud2>(); msg->xyzi.assign(xyzi, xyzi + 4*(size_t)n); msg->header.stamp.t = 1.0;
+  if (range_out || label_out || ground_out) {                                  // the images are reset at the end of the handler: run the three stages by hand first to read them
+    pcl::fromROSMsg(*msg, *laserCloudIn); std::vector<int> idx; pcl::removeNaNFromPointCloud(*laserCloudIn, *laserCloudIn, idx);
+    projectPointCloud(); groundRemoval(); cloudSegmentation();
+    size_t m = (size_t)N_SCAN*Horizon_SCAN;
+    if (range_out) memcpy(range_out, rangeMat.data, m*sizeof(float));
+    if (label_out) memcpy(label_out, labelMat.data, m*sizeof(int));
+    if (ground_out) memcpy(ground_out, groundMat.data, m);
+    flags_out[3] = (int)segmentedCloud->points.size();
+    resetParameters();
+  }
+  lidarCloudHandler(msg);
+  const auto& v = fs->qCloudPixel.back(); int m = (int)v.size();
+  lrud_io[0] = fs->left; lrud_io[1] = fs->right; lrud_io[2] = fs->up; lrud_io[3] = fs->down; flags_out[0] = fs->addFeaturePoint ? 1 : 0;
+  if (m <= cap) for (int i = 0; i < m; i++) { out3[3*i] = v[i][0]; out3[3*i+1] = v[i][1]; out3[3*i+2] = v[i][2]; }
+  while (!fs->qCloudPixel.empty()) fs->qCloudPixel.pop(); while (!fs->qTimeLidarCloud.empty()) fs->qTimeLidarCloud.pop();
+  return m <= cap ? m : -1;
+}
+int ref_lidar_dims(int* n_scan, int* horizon) { *n_scan = N_SCAN; *horizon = Horizon_SCAN; return 0; }
 
 }  // extern "C"

@@ -135,6 +135,39 @@ def lidar_pixels(world: World, R, t, K=KITTI_K, wh=KITTI_WH, beams: int = 64, az
     return np.stack([Ku[keep], Kv[keep], pc[keep, 2]], -1)
 
 
+
+# LiDAR -> camera extrinsics of a KITTI-like rig (Velodyne: x forward, y left, z up; camera: z forward, x right, y down): p_cam = RLC p_lidar + TLC   (sensor/00.txt role)
+RLC = np.array([[0.0, -1.0, 0.0], [0.0, 0.0, -1.0], [1.0, 0.0, 0.0]])
+TLC = np.array([0.0, -0.08, -0.27])
+
+
+def lidar_sweep(world: World, R, t, beams: int = 64, az: int = 1800, seed: int = 0, Rlc=RLC, tlc=TLC, objects: int = 40, dropout: float = 0.03, speckle: int = 60, range_noise: float = 0.004):
+    """One raw sweep in the LiDAR frame as the node receives it (sensor_msgs/PointCloud2 XYZI rows, main.cpp:785-792): `beams` rings x `az` azimuths cast into the world,
+    plus what makes the front-end's branches run: box-like objects in front of the planes (range steps -> segment borders), isolated speckle returns (infeasible
+    segments), dropouts (empty cells), a few NaN rows and near returns (< 0.1 m), jittered firing angles (two returns in one cell: the later one wins)."""
+    rng = np.random.default_rng(seed)
+    elev = np.deg2rad(-24.9 + 0.427 * (np.arange(beams) + 0.5) * (64.0 / beams))          # ring centres (main.cpp:103-107: ang_bottom, ang_res_y)
+    azim = np.deg2rad(-180.0 + 0.2 * (np.arange(az) + 0.5) * (1800.0 / az))
+    E, A = np.meshgrid(elev, azim, indexing="ij")
+    E = E + rng.normal(0, np.deg2rad(0.03), E.shape); A = A + rng.normal(0, np.deg2rad(0.03), A.shape)
+    dl = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], -1).reshape(-1, 3)   # LiDAR frame
+    o = t + R @ tlc; dw = (dl @ Rlc.T) @ R.T                                               # world rays from the LiDAR origin
+    lam, idx = world.cast(o, dw); lam = np.where(idx >= 0, lam, np.nan)
+    Ef, Af = E.reshape(-1), A.reshape(-1)
+    for _ in range(objects):                                                               # angular boxes at a shorter range
+        a0, e0 = rng.uniform(-np.pi, np.pi), np.deg2rad(rng.uniform(-20, 0)); da, de = np.deg2rad(rng.uniform(0.5, 8)), np.deg2rad(rng.uniform(1, 8)); r = rng.uniform(3, 35)
+        m = (np.abs(np.angle(np.exp(1j * (Af - a0)))) < da) & (np.abs(Ef - e0) < de) & ~(lam < r)
+        lam = np.where(m, r / np.maximum(np.cos(Ef - e0) * np.cos(np.angle(np.exp(1j * (Af - a0)))), 0.3), lam)
+    lam = lam * (1.0 + rng.normal(0, range_noise, lam.shape))
+    sp = rng.choice(len(lam), speckle, replace=False); lam[sp] = rng.uniform(2, 60, speckle)   # isolated returns
+    lam[rng.uniform(size=len(lam)) < dropout] = np.nan
+    keep = np.isfinite(lam) & (lam < 120.0)
+    pts = (dl[keep] * lam[keep, None]).astype(np.float32); inten = rng.uniform(0, 1, len(pts)).astype(np.float32)
+    cloud = np.concatenate([pts, inten[:, None]], 1)
+    extra = np.array([[np.nan, 1, 1, 0], [1, np.inf, 0, 0], [0.01, 0.02, -0.01, 0.5], [0.03, -0.05, 0.0, 0.5]], np.float32)
+    cloud = np.concatenate([cloud[: len(cloud) // 2], extra, cloud[len(cloud) // 2:]])
+    return np.ascontiguousarray(cloud[rng.permutation(len(cloud))] if seed % 2 else cloud)
+
 def select_points(img, cloud_px, n_target: int, seed: int = 0, cell: int = 12):
     """Stand-in for the LiDAR-aware pixel selector (PixelSelector2.cpp:354-622, out of scope): keep, per grid cell,
     the LiDAR pixels with the largest image gradient until ~n_target remain. Returns rows {u,v,idepth}."""
