@@ -349,6 +349,20 @@ int  sdv_activate_select_batch(sdv_ctx* c, int n, const int32_t* host_begin, con
                                const int32_t* cand_host_begin, const int32_t* cand_begin, const float* cKRKi9, const float* cKt3, const float* cand4, const float* min_act_dist,
                                int32_t* decision_out, float* dist_map_out);
 
+/* =====================================================================================================================
+ * LiDAR front-end of the node (second half): void lidarCloudHandler(const sensor_msgs::PointCloud2ConstPtr&)   src/main.cpp:785-858
+ *   -> projectPointCloud :563-607, groundRemoval :609-655, cloudSegmentation / labelComponents :657-783, projection into the image :806-849.  Tracker call domain.
+ * sdv_lidar_init: the sensor constants of main.cpp:103-108 (N_SCAN, Horizon_SCAN, ang_res_x, ang_res_y, ang_bottom, groundScanInd; Velodyne-64: 64, 1800, 0.2, 0.427, 24.9, 50).
+ * sdv_lidar_handler_batch: n raw sweeps (one per resident sequence), sweep j = XYZI rows sweep_begin[j] .. sweep_begin[j+1] of xyzi (the decoded PointCloud2, what
+ * pcl::fromROSMsg yields; rows with a non-finite coordinate are dropped like pcl::removeNaNFromPointCloud does).  Per sweep: Rlc9 (row-major) / tlc3 = FullSystem::Rlc, tlc
+ * (LiDAR -> camera), K4 = FullSystem::fx fy cx cy, lrud_io = FullSystem::left, right, up, down (the running pixel box; 10000, -1, 10000, -1 at start).  The image
+ * size is the context's.  Out, per sweep: up to cap rows {Ku, Kv, depth} (doubles, the vCloudPixel pushed into FullSystem::qCloudPixel, same order) at
+ * cloud3_out[3*j*cap ..], n_out[j] rows, add_feature_point_out[j] = FullSystem::addFeaturePoint (ground ratio > 0.8), stats_out[2j..] = {numGround, size of
+ * segmentedCloud} (may be NULL).  The rows feed sdv_make_new_traces_batch and the LiDAR-depth splats of sdv_tracker_set_ref. */
+int  sdv_lidar_init(sdv_ctx* c, int n_scan, int horizon_scan, float ang_res_x, float ang_res_y, float ang_bottom, int ground_scan_ind);
+int  sdv_lidar_handler_batch(sdv_ctx* c, int n, const int32_t* sweep_begin, const float* xyzi, const double* Rlc9, const double* tlc3, const float* K4, int32_t* lrud_io, int cap,
+                             double* cloud3_out, int32_t* n_out, int32_t* add_feature_point_out, int32_t* stats_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ def _load():
     L.sdv_selector_make_hists.argtypes = [_vp, C.c_uint64, _vp, _vp]
     L.sdv_selector_make_maps_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _vp, _vp, _f32p, _i32p, _f32p, _vp, _i32p]
     L.sdv_make_new_traces_batch.argtypes = [_vp, C.c_int, _i32p, _u64p, _i32p, _vp, _f32p, _f32p, _i32p, C.c_int, _vp, _vp, _i32p, _i32p]
+    L.sdv_lidar_init.argtypes = [_vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]
+    L.sdv_lidar_handler_batch.argtypes = [_vp, C.c_int, _i32p, _vp, _f64p, _f64p, _f32p, _i32p, C.c_int, _vp, _i32p, _i32p, _i32p]
     L.sdv_activate_select_batch.argtypes = [_vp, C.c_int, _i32p, _i32p, _vp, _vp, _vp, _i32p, _i32p, _vp, _vp, _vp, _f32p, _vp, _vp]
     return L
 
@@ -618,3 +620,22 @@ def activateSelectBatch(ctx: Context, seqs, want_maps=False):
     for j in range(n):
         nc = cb[gb[j + 1]] - cb[gb[j]]; out.append(dec[k:k + nc]); k += nc
     return (out, maps) if want_maps else out
+
+
+# ---------------------------------------------------------------------------------------------- LiDAR front-end (sdv_lidar.cu): lidarCloudHandler, src/main.cpp:785-858
+class LidarFrontEnd:
+    """projectPointCloud -> groundRemoval -> cloudSegmentation -> projection into the image, for a batch of raw XYZI sweeps (one per sequence)"""
+
+    def __init__(self, ctx: Context, n_scan=64, horizon=1800, ang_res_x=0.2, ang_res_y=0.427, ang_bottom=24.9, groundScanInd=50):
+        self.ctx = ctx; self.n_scan, self.horizon = n_scan, horizon
+        ctx._ck(LIB.sdv_lidar_init(ctx.p, n_scan, horizon, ang_res_x, ang_res_y, ang_bottom, groundScanInd))
+
+    def handle(self, sweeps, Rlc, tlc, K4, lruds, cap=None):
+        """sweeps: list of (n,4) float32 XYZI arrays; Rlc (3,3) / tlc (3,) / K4 shared or per sweep; lruds (n,4) running pixel boxes -> list of dicts like the oracle's"""
+        n = len(sweeps); sw = [np.ascontiguousarray(s, np.float32).reshape(-1, 4) for s in sweeps]; sb = np.concatenate([[0], np.cumsum([len(s) for s in sw])]).astype(np.int32)
+        allp = np.ascontiguousarray(np.concatenate(sw) if sb[-1] else np.zeros((1, 4), np.float32)); cap = cap or self.n_scan * self.horizon
+        R = np.ascontiguousarray(np.broadcast_to(np.asarray(Rlc, np.float64).reshape(-1, 9), (n, 9))).reshape(-1); t = np.ascontiguousarray(np.broadcast_to(np.asarray(tlc, np.float64).reshape(-1, 3), (n, 3))).reshape(-1)
+        K = np.ascontiguousarray(np.broadcast_to(np.asarray(K4, np.float32).reshape(-1, 4), (n, 4))).reshape(-1); lr = np.ascontiguousarray(lruds, np.int32).reshape(n, 4).copy()
+        out = np.zeros((n, cap, 3)); n_out = np.zeros(n, np.int32); add = np.zeros(n, np.int32); st = np.zeros(2 * n, np.int32)
+        self.ctx._ck(LIB.sdv_lidar_handler_batch(self.ctx.p, n, sb, allp.ctypes.data, R, t, K, lr.reshape(-1), cap, out.ctypes.data, n_out, add, st))
+        return [dict(cloud_px=out[j, :n_out[j]].copy(), lrud=lr[j], numGround=int(st[2 * j]), n_segmented=int(st[2 * j + 1]), addFeaturePoint=int(add[j])) for j in range(n)]

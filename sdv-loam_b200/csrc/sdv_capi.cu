@@ -153,6 +153,7 @@ void sdv_destroy(sdv_ctx* c) {
   cudaFree(c->refine_dev); cudaFreeHost(c->refine_host);
   rp_destroy(c);
   sel_destroy(c);
+  lidar_destroy(c);
   ba_destroy(c);
   if (c->ba_ev0) cudaEventDestroy(c->ba_ev0); if (c->ba_ev1) cudaEventDestroy(c->ba_ev1); if (c->ev_xdom) cudaEventDestroy(c->ev_xdom); if (c->st_ba) cudaStreamDestroy(c->st_ba);
   if (c->ev0) cudaEventDestroy(c->ev0); if (c->ev1) cudaEventDestroy(c->ev1); if (c->ev_in) cudaEventDestroy(c->ev_in); if (c->st) cudaStreamDestroy(c->st); if (c->st_in) cudaStreamDestroy(c->st_in);

@@ -58,6 +58,7 @@ struct sdv_ctx {
   float last_ms;
   void* refine_dev = nullptr; void* refine_host = nullptr; size_t refine_cap = 0;      // staging of sdv_tracker_struct_pose_batch
   void* trace_dev = nullptr; size_t trace_cap = 0;                                  // scratch of the immature-point calls (sdv_trace.cu)
+  void* lidar = nullptr;                        // sdv::LidarState: engine of the LiDAR front-end (sdv_lidar.cu)
   void* sel = nullptr;                          // sdv::SelState: PixelSelector slots + engine of the candidate management (sdv_select.cu)
   sdv::RpState* rp = nullptr;                   // map slots + scratch of the Reprojector path (sdv_reproject.cu)
   sdv::BAState* ba = nullptr;                   // selected back-end window
@@ -70,6 +71,7 @@ struct sdv_ctx {
 namespace sdv {
 void rp_destroy(sdv_ctx* c);
 void sel_destroy(sdv_ctx* c);
+void lidar_destroy(sdv_ctx* c);
 void rp_calib_changed(sdv_ctx* c);             // the Reprojector constants (K, K^-1) are rebuilt from the context calibration at the next call
 int ctx_fail(sdv_ctx* c, int code, const char* fmt, ...);
 void ba_destroy(sdv_ctx* c);

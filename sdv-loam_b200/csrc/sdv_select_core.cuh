@@ -20,19 +20,7 @@
 // for the host against a small CUDA emulation (tests/emu/cuda_emu.hpp) and checks it against the oracle (tests/test_select_emu_cpu.py); sdv_select.cu compiles it
 // with nvcc and binds it to the context (frames, streams) behind the C-ABI.
 #pragma once
-#include <stdint.h>
-#include <math.h>
-#include <vector>
-#include <algorithm>
-#include <string>
-#include <limits.h>
-#include <string.h>
-#ifndef SDV_EMU
-#include <cuda_runtime.h>
-#define SDV_LAUNCH(kern, grid, block, st, ...)      kern<<<grid, block, 0, st>>>(__VA_ARGS__)
-#define SDV_LAUNCH_SYNC(kern, grid, block, st, ...) kern<<<grid, block, 0, st>>>(__VA_ARGS__)
-#define SDV_DEVCONST static __constant__
-#endif
+#include "sdv_core_common.cuh"
 
 namespace sdv { namespace sel {
 
@@ -52,7 +40,6 @@ struct SelJob {                          // one select pass of one frame
   int charTH;                            // random sub-selection threshold, -1 = none
 };
 
-__device__ __forceinline__ int imin_(int a, int b) { return a < b ? a : b; }
 SDV_DEVCONST float kSelDirs[16][2] = {{0,1.0000f},{0.3827f,0.9239f},{0.1951f,0.9808f},{0.9239f,0.3827f},{0.7071f,0.7071f},{0.3827f,-0.9239f},{0.8315f,0.5556f},{0.8315f,-0.5556f},
                                       {0.5556f,-0.8315f},{0.9808f,0.1951f},{0.9239f,-0.3827f},{0.7071f,-0.7071f},{0.5556f,0.8315f},{0.9808f,-0.1951f},{1.0000f,0.0000f},{0.1951f,-0.9808f}};
 SDV_DEVCONST int kSelPat[8][2] = {{0,-2},{-1,-1},{1,-1},{-2,0},{0,0},{2,0},{-1,1},{0,2}};
@@ -145,14 +132,6 @@ __global__ void __launch_bounds__(128) sel_point_kernel(const SelJob* __restrict
     atomicAdd(&J.cnt[slot], 1);
   }
   J.rec[i] = r; J.slot_of[i] = slot;
-}
-// exclusive prefix sum of a block's values through shared memory (Hillis-Steele); every thread of the CTA must call it
-__device__ __forceinline__ int block_excl_scan(int v, int* sm /* 2*blockDim */, int& total) {
-  const int t = threadIdx.x, n = blockDim.x; int cur = 0;
-  sm[t] = v; __syncthreads();
-  for (int d = 1; d < n; d <<= 1) { const int x = sm[cur*n + t] + (t >= d ? sm[cur*n + t - d] : 0); sm[(cur^1)*n + t] = x; cur ^= 1; __syncthreads(); }
-  const int incl = sm[cur*n + t]; total = sm[cur*n + n-1]; __syncthreads();
-  return incl - v;
 }
 __global__ void __launch_bounds__(256) sel_scan_kernel(const SelJob* __restrict__ jobs) {                                 // CTA per job: off = exclusive scan of cnt over the slots
   const SelJob J = jobs[blockIdx.x]; if (!J.active || !J.cloud) return;
@@ -528,17 +507,6 @@ __global__ void __launch_bounds__(64) act_walk_kernel(const DistJob* __restrict_
 }
 
 // ================================================================================================ host engine
-#define SEL_CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { err = std::string(#call) + " -> " + cudaGetErrorString(e_); return -1; } } while (0)
-
-struct Scratch {                                             // grow-only device buffer carved into aligned pieces
-  char* p = nullptr; size_t cap = 0, used = 0;
-  int reserve(size_t bytes, cudaStream_t st) { if (bytes <= cap) return 0; cudaStreamSynchronize(st); if (p) cudaFree(p); p = nullptr; cap = 0; if (cudaMalloc((void**)&p, bytes + bytes/4) != cudaSuccess) return -1; cap = bytes + bytes/4; return 0; }
-  void reset() { used = 0; }
-  template <class T> T* take(size_t n) { used = (used + 255) & ~(size_t)255; T* r = (T*)(p + used); used += n*sizeof(T); return r; }
-  static size_t need(size_t n, size_t sz) { return ((n*sz + 255) & ~(size_t)255) + 256; }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
 // host-side state of one PixelSelector (one per resident sequence): currentPotential + the persistent monocular selection map
 struct SelectorSlot { int currentPotential = 3; unsigned char* mapD = nullptr; };
 

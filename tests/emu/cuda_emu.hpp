@@ -80,3 +80,5 @@ using std::isfinite;
 #define SDV_DEVCONST static const
 static inline int __float_as_int(float f) { int b; memcpy(&b, &f, 4); return b; }
 static inline float __int_as_float(int b) { float f; memcpy(&f, &b, 4); return f; }
+static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

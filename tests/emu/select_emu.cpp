@@ -4,6 +4,7 @@
 #define SDV_EMU_IMPL 1
 #include "cuda_emu.hpp"
 #include "../../sdv-loam_b200/csrc/sdv_select_core.cuh"
+#include "../../sdv-loam_b200/csrc/sdv_lidar_core.cuh"
 using namespace sdv::sel;
 
 extern "C" {
@@ -53,4 +54,18 @@ int emu_activate(void* ep, int nHosts, const int* pt_begin, const float* KRKi, c
   return e->activate(J);
 }
 long long emu_engine_launches(void* e) { return ((SelEngine*)e)->launches; }
+// ---- LiDAR front-end (sdv_lidar_core.cuh)
+float emu_atan2f(float y, float x) { return sdv::lidar::emu_lib_atan2f(y, x); }
+void* emu_lidar_create(int n_scan, int horizon, float ang_res_x, float ang_res_y, float ang_bottom, int groundScanInd) { sdv::lidar::LidarEngine* e = new sdv::lidar::LidarEngine(); e->init(n_scan, horizon, ang_res_x, ang_res_y, ang_bottom, groundScanInd, nullptr); return e; }
+void emu_lidar_destroy(void* e) { ((sdv::lidar::LidarEngine*)e)->destroy(); delete (sdv::lidar::LidarEngine*)e; }
+const char* emu_lidar_error(void* e) { return ((sdv::lidar::LidarEngine*)e)->err.c_str(); }
+// nj sweeps in one batch: xyzi pointers / sizes per sweep, shared extrinsics; lrud (4 per sweep) in/out; out3: nj x cap x 3; res: per sweep {n_out, numGround, n_segmented, addFeaturePoint}
+int emu_lidar_handle(void* ep, int nj, const float* const* xyzi, const int* n, const double* R9, const double* t3, const float* K4, int w, int h, int* lrud, double* out3, int cap, int* res) {
+  sdv::lidar::LidarEngine* e = (sdv::lidar::LidarEngine*)ep; std::vector<sdv::lidar::LidarEngine::Sweep> S(nj);
+  for (int j = 0; j < nj; j++) { S[j].xyzi_host = xyzi[j]; S[j].n = n[j]; for (int k = 0; k < 9; k++) S[j].R[k] = R9[k]; for (int k = 0; k < 3; k++) S[j].t[k] = t3[k]; for (int k = 0; k < 4; k++) { S[j].K[k] = K4[k]; S[j].lrud[k] = lrud[4*j+k]; }
+    S[j].w = w; S[j].h = h; S[j].out3_host = out3 + (size_t)j*cap*3; S[j].cap = cap; }
+  int rc = e->handle(S);
+  for (int j = 0; j < nj; j++) { for (int k = 0; k < 4; k++) lrud[4*j+k] = S[j].lrud[k]; res[4*j] = S[j].n_out; res[4*j+1] = S[j].numGround; res[4*j+2] = S[j].n_segmented; res[4*j+3] = S[j].addFeaturePoint; }
+  return rc;
+}
 }

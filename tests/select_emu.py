@@ -16,7 +16,7 @@ IMM_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("idepth_min", "<f4"), ("idept
 def lib():
     global _LIB
     if _LIB is None:
-        srcs = [os.path.join(_HERE, "emu", "select_emu.cpp"), os.path.join(_HERE, "emu", "cuda_emu.hpp"), os.path.join(_HERE, "..", "sdv-loam_b200", "csrc", "sdv_select_core.cuh")]
+        srcs = [os.path.join(_HERE, "emu", "select_emu.cpp"), os.path.join(_HERE, "emu", "cuda_emu.hpp"), os.path.join(_HERE, "..", "sdv-loam_b200", "csrc", "sdv_select_core.cuh"), os.path.join(_HERE, "..", "sdv-loam_b200", "csrc", "sdv_lidar_core.cuh"), os.path.join(_HERE, "..", "sdv-loam_b200", "csrc", "sdv_core_common.cuh")]
         if not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
             subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-o", _SO, srcs[0]])
         L = C.CDLL(_SO)
@@ -29,6 +29,10 @@ def lib():
         L.emu_slot_get_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.emu_make_new_traces.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11 + [C.c_int] + [C.c_void_p] * 3
         L.emu_activate.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+        L.emu_atan2f.restype = C.c_float; L.emu_atan2f.argtypes = [C.c_float, C.c_float]
+        L.emu_lidar_create.restype = C.c_void_p; L.emu_lidar_create.argtypes = [C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int]; L.emu_lidar_destroy.argtypes = [C.c_void_p]
+        L.emu_lidar_error.restype = C.c_char_p; L.emu_lidar_error.argtypes = [C.c_void_p]
+        L.emu_lidar_handle.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -89,3 +93,17 @@ class Slot:
     def currentPotential(self, v): lib().emu_slot_set_potential(self.p, int(v))
     def map(self, w, h):
         o = np.zeros(w * h, np.uint8); lib().emu_slot_get_map(self.p, o.ctypes.data, w * h); return o.reshape(h, w)
+
+
+class LidarEngine:
+    """sdv_lidar_core.cuh on the host: the whole lidarCloudHandler for a batch of raw XYZI sweeps"""
+    def __init__(self, n_scan=64, horizon=1800, ang_res_x=0.2, ang_res_y=0.427, ang_bottom=24.9, groundScanInd=50):
+        self.n_scan, self.horizon = n_scan, horizon; self.p = lib().emu_lidar_create(n_scan, horizon, ang_res_x, ang_res_y, ang_bottom, groundScanInd)
+
+    def handle(self, sweeps, Rlc, tlc, K4, wh, lruds):
+        nj = len(sweeps); sw = [np.ascontiguousarray(s, np.float32).reshape(-1, 4) for s in sweeps]; cap = self.n_scan * self.horizon
+        ptrs = (C.c_void_p * nj)(*[s.ctypes.data for s in sw]); n = np.array([len(s) for s in sw], np.int32); lr = np.ascontiguousarray(lruds, np.int32).reshape(nj, 4).copy()
+        out = np.zeros((nj, cap, 3)); res = np.zeros((nj, 4), np.int32); R = np.ascontiguousarray(Rlc, np.float64).reshape(-1); t = np.ascontiguousarray(tlc, np.float64); K = np.ascontiguousarray(K4, np.float32)
+        rc = lib().emu_lidar_handle(self.p, nj, ptrs, n.ctypes.data, R.ctypes.data, t.ctypes.data, K.ctypes.data, wh[0], wh[1], lr.ctypes.data, out.ctypes.data, cap, res.ctypes.data)
+        if rc: raise RuntimeError(lib().emu_lidar_error(self.p).decode())
+        return [dict(cloud_px=out[j, :res[j, 0]].copy(), lrud=lr[j], numGround=int(res[j, 1]), n_segmented=int(res[j, 2]), addFeaturePoint=int(res[j, 3])) for j in range(nj)]

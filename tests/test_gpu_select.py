@@ -93,3 +93,29 @@ def test_distance_map_and_activation_walk_batch():
         assert np.array_equal(maps[j], od.get()), d
         assert (do == 1).sum() > 15 and (do == -1).sum() >= 8
     ctx.close()
+
+
+def test_lidar_front_end_batch():
+    """the node's lidarCloudHandler on raw XYZI sweeps (three sequences per call, pixel box carried over a second call): rows {Ku, Kv, depth}, box, ground count, segmented
+    size and addFeaturePoint identical to the oracle (pinned on the reference's own src/main.cpp, tests/test_ref_pin_lidar.py); then the rows feed makeNewTraces"""
+    from test_ref_pin_lidar import sweeps
+    api, seq, of, ctx, rp = _scene(SMALL_WH, SMALL_K, 3000); synth, S = sweeps(3)
+    fe = orc.LidarFrontEnd(); G = api.LidarFrontEnd(ctx); lr0 = [[10000, -1, 10000, -1]] * 3
+    for rnd in range(2):
+        tlc = synth.TLC if rnd == 0 else np.array([0.0, -0.08, 0.35])
+        res = G.handle(S, synth.RLC, tlc, SMALL_K, lr0)
+        for j in range(3):
+            o = fe.handle(S[j], synth.RLC, tlc, SMALL_K, SMALL_WH, lr0[j])
+            assert np.array_equal(o["cloud_px"], res[j]["cloud_px"]) and len(o["cloud_px"]) > 3000, (rnd, j, len(o["cloud_px"]), len(res[j]["cloud_px"]))
+            assert np.array_equal(o["lrud"], res[j]["lrud"]) and o["numGround"] == res[j]["numGround"] and o["n_segmented"] == res[j]["n_segmented"] and o["addFeaturePoint"] == res[j]["addFeaturePoint"]
+        lr0 = [r["lrud"] for r in res]
+    for cloud in (np.zeros((0, 4), np.float32), np.array([[np.nan, 0, 0, 0], [0.01, 0.01, 0, 0]], np.float32), S[0][::7]):
+        o = fe.handle(cloud, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = G.handle([cloud], synth.RLC, synth.TLC, SMALL_K, [[10000, -1, 10000, -1]])[0]
+        assert np.array_equal(o["cloud_px"], g["cloud_px"]) and np.array_equal(o["lrud"], g["lrud"]) and o["addFeaturePoint"] == g["addFeaturePoint"] and o["n_segmented"] == g["n_segmented"]
+    # front-end -> selector: the device-produced pixel rows drive makeNewTraces of the same keyframe
+    w, h = SMALL_WH; res = G.handle([S[0]], synth.RLC, synth.TLC, SMALL_K, [[10000, -1, 10000, -1]])[0]
+    ps = api.PixelSelector(ctx, 1, rp); osel = orc.Selector(w, h, rp); dl = api.lidar_density(res["lrud"], SMALL_WH, 600.0)
+    (T, I), num = ps.makeNewTracesBatch([0], [10], [res["cloud_px"]], dl, 600.0, res["addFeaturePoint"])[0][0], None
+    To, _, _ = osel.makeNewTraces(of[0], res["cloud_px"], dl, 600.0, res["addFeaturePoint"], np.zeros((h, w), np.float32))
+    assert To.tobytes() == T.tobytes() and len(T) > 100
+    ctx.close()

@@ -107,3 +107,32 @@ def test_distance_map_and_activation_walk(scene):
         assert np.array_equal(m[0], od.get()) and np.array_equal(m[1], od.get())
         assert (do == 1).sum() > 15 and (do == -1).sum() >= 8
     assert (do == 0).sum() > 100
+
+
+# ---------------------------------------------------------------------------------------------- LiDAR front-end (sdv_lidar_core.cuh)
+def test_atan2f_matches_libm():
+    """the device carries the C library's atan2f (fdlibm, float operations only): identical bits to this box's libm on random and special arguments"""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6"); libm.atan2f.restype = C.c_float; libm.atan2f.argtypes = [C.c_float, C.c_float]; L = se.lib()
+    rng = np.random.default_rng(0); y = (rng.uniform(-1, 1, 60000) * 10.0 ** rng.uniform(-6, 3, 60000)).astype(np.float32); x = (rng.uniform(-1, 1, 60000) * 10.0 ** rng.uniform(-6, 3, 60000)).astype(np.float32)
+    sp = np.array([0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, np.nan, 1e-38, 3e38], np.float32); y[:81] = np.repeat(sp, 9); x[:81] = np.tile(sp, 9)
+    a = np.array([libm.atan2f(float(p), float(q)) for p, q in zip(y, x)], np.float32); b = np.array([L.emu_atan2f(float(p), float(q)) for p, q in zip(y, x)], np.float32)
+    assert np.array_equal(a.view(np.uint32)[~np.isnan(a)], b.view(np.uint32)[~np.isnan(a)]) and np.array_equal(np.isnan(a), np.isnan(b))
+
+
+def test_lidar_front_end_batch():
+    """three raw sweeps in one batch + a second call carrying the pixel box over: pixel rows {Ku, Kv, depth}, box, counts, addFeaturePoint identical to the oracle"""
+    from test_ref_pin_lidar import sweeps
+    synth, S = sweeps(3); fe = orc.LidarFrontEnd(); E = se.LidarEngine()
+    lr0 = [[10000, -1, 10000, -1]] * 3
+    for rnd in range(2):
+        tlc = synth.TLC if rnd == 0 else np.array([0.0, -0.08, 0.35])
+        G = E.handle(S, synth.RLC, tlc, SMALL_K, SMALL_WH, lr0)
+        for j in range(3):
+            o = fe.handle(S[j], synth.RLC, tlc, SMALL_K, SMALL_WH, lr0[j])
+            assert np.array_equal(o["cloud_px"], G[j]["cloud_px"]) and len(o["cloud_px"]) > 3000, (rnd, j, len(o["cloud_px"]), len(G[j]["cloud_px"]))
+            assert np.array_equal(o["lrud"], G[j]["lrud"]) and o["numGround"] == G[j]["numGround"] and o["n_segmented"] == G[j]["n_segmented"] and o["addFeaturePoint"] == G[j]["addFeaturePoint"]
+        lr0 = [g["lrud"] for g in G]
+    for cloud in (np.zeros((0, 4), np.float32), np.array([[np.nan, 0, 0, 0], [0.01, 0.01, 0, 0]], np.float32), S[0][::7]):
+        o = fe.handle(cloud, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = E.handle([cloud], synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [[10000, -1, 10000, -1]])[0]
+        assert np.array_equal(o["cloud_px"], g["cloud_px"]) and np.array_equal(o["lrud"], g["lrud"]) and o["addFeaturePoint"] == g["addFeaturePoint"] and o["n_segmented"] == g["n_segmented"]
