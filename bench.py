@@ -341,6 +341,56 @@ def refine_leg(ctx, api, synth, B, reps=6, warm=2, seed=11, cpu=True):
             "note": "sdv_tracker_refine_batch: reprojectMap (grid 25 px, warp-per-cell direct alignment) + structPoseEstimation, device resident; exact parity vs the CPU oracle (tests/test_gpu_reproject.py)"}
 
 
+def keyframe_leg(ctx, api, synth, B, reps=3, warm=1, cpu=True):
+    """Keyframe-rate candidate management for B sequences per call (SURVEY §8f ranks 3b, 4 and the caller half of 2), each stage through the C-ABI with host buffers:
+    lidarCloudHandler on a raw 64-beam XYZI sweep (sdv_lidar_handler_batch) -> FullSystem::makeNewTraces on the new keyframe (sdv_make_new_traces_batch: makeHists,
+    makeMapsFromLidar, makeMaps, Shi-Tomasi typing, ImmaturePoint records) -> makeDistanceMap + the activatePointsMT candidate walk (sdv_activate_select_batch).
+    Wall time of the calls (H2D of sweeps / clouds / candidates and D2H of the results inside); the CPU oracle on one core beside it (bounded sample)."""
+    from conftest import cached_sequence
+    w, h = synth.KITTI_WH; K = synth.KITTI_K
+    seq8 = cached_sequence(8, 2000, K, synth.KITTI_WH); world = synth.World(2000)
+    base = 1 << 43; kf = base + 1; ctx.makeImages(kf, seq8.images[7])
+    sweep = synth.lidar_sweep(world, seq8.R[7], seq8.t[7], seed=4)
+    fe = api.LidarFrontEnd(ctx); rp = api.random_pattern(w, h); ps = api.PixelSelector(ctx, B, rp)
+    lr0 = [[10000, -1, 10000, -1]] * B; out = {"sequences": B, "sweep_points": int(len(sweep))}
+    def timed(fn):
+        ts = []
+        for rep in range(warm + reps):
+            ctx.sync(); t0 = time.perf_counter(); r = fn(); t1 = time.perf_counter()
+            if rep >= warm: ts.append(t1 - t0)
+        return r, float(np.mean(ts))
+    res, t_l = timed(lambda: fe.handle([sweep] * B, synth.RLC, synth.TLC, K, lr0))
+    cloud = res[0]["cloud_px"]; dl = api.lidar_density(res[0]["lrud"], synth.KITTI_WH, 600.0)
+    out["lidar_front_end"] = {"ms_per_batch_wall": 1e3 * t_l, "sweeps_per_s": B / t_l, "pixels_out": int(len(cloud)), "h2d_bytes_per_batch": int(B * sweep.nbytes)}
+    def traces():
+        for j in range(B): ps.potential(j, 3)
+        return ps.makeNewTracesBatch(list(range(B)), [kf] * B, [cloud] * B, dl, 600.0, 1, cap=1 << 13)
+    (tr, num), t_t = timed(traces)
+    out["make_new_traces"] = {"ms_per_batch_wall": 1e3 * t_t, "keyframes_per_s": B / t_t, "points_per_keyframe": int(len(tr[0][0])), "lidar_monocular": [int(num[0][0]), int(num[0][1])]}
+    pts, hT, hab = synth.make_map(seq8, list(range(7)), n_per_frame=300, seed=2)
+    K0 = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32); K1 = np.array([[K[0] / 2, 0, (K[2] + 0.5) / 2 - 0.5], [0, K[1] / 2, (K[3] + 0.5) / 2 - 0.5], [0, 0, 1]], np.float32)
+    Ki0 = np.linalg.inv(K0.astype(np.float64)).astype(np.float32); KRKi = []; Kt = []; uvid = []; pb = [0]
+    for k in range(7):
+        R, t = synth.rel_pose(seq8.R[k], seq8.t[k], seq8.R[7], seq8.t[7]); KRKi.append(K1 @ R.astype(np.float32) @ Ki0); Kt.append(K1 @ t.astype(np.float32))
+        m = pts["host"] == k; uvid.append(np.stack([pts["u"][m], pts["v"][m], pts["idepth"][m]], 1)); pb.append(pb[-1] + int(m.sum()))
+    rng = np.random.default_rng(5); cand = []; cb = [0]
+    for k in range(7):
+        c = seq8.clouds[k]; pick = rng.choice(len(c), 400, replace=False)
+        cand.append(np.stack([np.floor(c[pick, 0]), np.floor(c[pick, 1]), 1.0 / c[pick, 2], rng.choice([1.0, 2.0, 4.0], 400)], 1)); cb.append(cb[-1] + 400)
+    q = dict(pt_begin=pb, KRKi=np.stack(KRKi), Kt=np.stack(Kt), uvid=np.concatenate(uvid).astype(np.float32), cand_begin=cb, cKRKi=np.stack(KRKi), cKt=np.stack(Kt), cand4=np.concatenate(cand).astype(np.float32), minActDist=2.0)
+    dec, t_a = timed(lambda: api.activateSelectBatch(ctx, [q] * B))
+    out["activate_select"] = {"ms_per_batch_wall": 1e3 * t_a, "sequences_per_s": B / t_a, "candidates": int(cb[-1]), "accepted": int((dec[0] == 1).sum()), "map_points": int(pb[-1])}
+    if cpu:
+        orc = se3_helpers(); L = 4; fo = orc.Frame(seq8.images[7], L); fe_o = orc.LidarFrontEnd(); sel_o = orc.Selector(w, h, rp); dm = orc.DistMap(w >> 1, h >> 1)
+        t0 = time.perf_counter(); o = fe_o.handle(sweep, synth.RLC, synth.TLC, K, synth.KITTI_WH, lr0[0]); t1 = time.perf_counter()
+        To, _, _ = sel_o.makeNewTraces(fo, cloud, dl, 600.0, 1, np.zeros((h, w), np.float32)); t2 = time.perf_counter()
+        dm.make(pb, q["KRKi"], q["Kt"], q["uvid"]); do = dm.activateSelect(cb, q["cKRKi"], q["cKt"], q["cand4"], 2.0); t3 = time.perf_counter()
+        out["cpu_ms_1core"] = {"lidar_front_end": 1e3 * (t1 - t0), "make_new_traces": 1e3 * (t2 - t1), "activate_select": 1e3 * (t3 - t2)}
+        out["identical_to_cpu"] = bool(np.array_equal(o["cloud_px"], cloud) and To.tobytes() == tr[0][0].tobytes() and np.array_equal(do, dec[0]))
+    out["note"] = "B sequences per call; every stage bit-identical to the CPU path (tests/test_gpu_select.py)"
+    return out
+
+
 def ba_cpu_ms(synth):
     """oracle optimize() on one host core, ms per window"""
     orc = se3_helpers()
@@ -703,6 +753,12 @@ def main():
     ctx = api.Context(synth.KITTI_K, w, h, device=local_rank, n_tracker_slots=Bref, track_threads=args.track_threads, max_frames=Bref + 32 + 8 * WBA, max_kf_images=max(12, 7 * WBA))
     ba = ba_leg(ctx, api, synth, local_rank, WBA) if WBA > 0 else None
     refine = refine_leg(ctx, api, synth, Bref, cpu=not args.no_cpu_baseline) if not args.no_refine else None
+    keyframe = None
+    if not args.no_refine and rank == 0:
+        try:
+            keyframe = keyframe_leg(ctx, api, synth, min(Bref, 148), cpu=not args.no_cpu_baseline)
+        except Exception as e:                                            # an auxiliary leg must not take the headline measurement down
+            keyframe = {"error": repr(e)[:300]}
     h2d_local = B * ho * wo * NB / t_e2e_u8 / 1e9                          # this rank's raw-frame H2D rate over the e2e leg
     hv = torch.tensor([h2d_local], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -772,6 +828,8 @@ def main():
     if refine is not None:
         refine["frames_per_s_device"] *= world; refine["frames_per_s_wall"] *= world
         line["refine"] = refine
+    if keyframe is not None:
+        line["keyframe_rate"] = keyframe
     if not args.no_cpu_baseline:
         arm = make_cpu_arm(seq, synth, p4, 1); arm.run(3)
         nf, tw = arm.run(10 ** 9, budget_s=12.0)

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <utility>
 #include <vector>
+#include <cstdlib>
 #include "sdv_b200.h"
 
 // ------------------------------------------------------------------------------------------------ stand-ins for the reference's types (names as in the reference)
@@ -221,6 +222,42 @@ int shim_activatePoints(std::vector<ActivationGroup>& groups, std::vector<int32_
                                      status.data(), idepth.data(), res_state.data());     // status 1 -> new PointHessian(point) + PointFrameResidual per IN state, -1 -> delete, 0 -> keep immature
 }
 
+// ------------------------------------------------------------------------------------------------ §3e keyframe-rate candidate management
+// PixelSelector::PixelSelector (PixelSelector2.cpp:11-26): the selector's random pattern is generated where the reference generates it and handed to the library once
+struct PixelSelector { unsigned char* randomPattern; int currentPotential; };
+int shim_selector_ctor(PixelSelector& ps) {
+  ps.randomPattern = new unsigned char[(std::size_t)wG[0]*hG[0]]; std::srand(3141592); for (int i = 0; i < wG[0]*hG[0]; i++) ps.randomPattern[i] = std::rand() & 0xFF;   // :14-16
+  ps.currentPotential = 3; return sdv_selector_init(gpu, ps.randomPattern, /*slots: one per FullSystem*/1);
+}
+// void lidarCloudHandler(const sensor_msgs::PointCloud2ConstPtr&)  main.cpp:785-858: the decoded XYZI rows of one sweep in, vCloudPixel + addFeaturePoint out
+struct LidarRig { double Rlc[9], tlc[3]; float fx, fy, cx, cy; int left, right, up, down; bool addFeaturePoint; };           // the FullSystem members main.cpp:368-377, :834-854 touches
+int shim_lidarCloudHandler(LidarRig& fsys, const float* xyzi, int n, std::vector<double>& vCloudPixel3) {
+  static bool once = false; if (!once) { int rc = sdv_lidar_init(gpu, /*N_SCAN*/64, /*Horizon_SCAN*/1800, 0.2f, 0.427f, 24.9f, /*groundScanInd*/50); if (rc) return rc; once = true; }   // main.cpp:103-108
+  const int32_t sweep_begin[2] = {0, n}; const float K4[4] = {fsys.fx, fsys.fy, fsys.cx, fsys.cy}; int32_t lrud[4] = {fsys.left, fsys.right, fsys.up, fsys.down}, n_out = 0, add = 0;
+  const int cap = 64*1800; vCloudPixel3.resize(3*(std::size_t)cap);
+  int rc = sdv_lidar_handler_batch(gpu, 1, sweep_begin, xyzi, fsys.Rlc, fsys.tlc, K4, lrud, cap, vCloudPixel3.data(), &n_out, &add, nullptr);
+  fsys.left = lrud[0]; fsys.right = lrud[1]; fsys.up = lrud[2]; fsys.down = lrud[3]; fsys.addFeaturePoint = add != 0; vCloudPixel3.resize(3*(std::size_t)n_out);           // -> fullSystem->qCloudPixel.push(vCloudPixel)
+  return rc;
+}
+// void FullSystem::makeNewTraces(FrameHessian* newFrame, float*)  FullSystem.cpp:1273-1356, whole: selection, Shi-Tomasi typing, occupancy mask, ImmaturePoint construction
+int shim_makeNewTraces_whole(FrameHessian* newFrame, const LidarRig& fsys, const std::vector<double>& vCloudPixel3, std::vector<sdv_new_trace>& traces, std::vector<sdv_immature_pt>& recs) {
+  const int32_t slot = 0, cloud_begin[2] = {0, (int32_t)(vCloudPixel3.size()/3)}, add = fsys.addFeaturePoint ? 1 : 0; const uint64_t id = (uint64_t)newFrame->shell->id;
+  const int lidarArea = (fsys.right - fsys.left)*(fsys.down - fsys.up), imageArea = wG[0]*hG[0];
+  const float dl = ((float)lidarArea/(float)imageArea) * setting_desiredImmatureDensity, dd = setting_desiredImmatureDensity;                                                   // :1287-1293
+  const int cap = 1 << 14; traces.resize(cap); recs.resize(cap); int32_t n_out = 0, num[2];
+  int rc = sdv_make_new_traces_batch(gpu, 1, &slot, &id, cloud_begin, vCloudPixel3.data(), &dl, &dd, &add, cap, traces.data(), recs.data(), &n_out, num);
+  traces.resize(n_out); recs.resize(n_out);   // per row: new ImmaturePoint{rec}, my_type, score, type, isFromSensor, idepth_fromSensor (:1307-1325, :1343-1352) -> newFrame->immaturePoints
+  return rc;
+}
+// the selection half of void FullSystem::activatePointsMT()  FullSystem.cpp:600-671 (makeDistanceMap + candidate walk); the survivors go to shim_activatePoints
+struct ActivationInputs { std::vector<int32_t> pt_begin, cand_begin; std::vector<float> KRKi9, Kt3, uvid, cKRKi9, cKt3, cand4; float currentMinActDist; };   // per keyframe: K[1] R K[0]^-1, K[1] t (:606-608)
+int shim_activateSelect(const ActivationInputs& in, std::vector<int32_t>& decision) {
+  const int32_t host_begin[2] = {0, (int32_t)in.pt_begin.size() - 1}, cand_host_begin[2] = {0, (int32_t)in.cand_begin.size() - 1};
+  decision.resize(in.cand_begin.back());
+  return sdv_activate_select_batch(gpu, 1, host_begin, in.pt_begin.data(), in.KRKi9.data(), in.Kt3.data(), in.uvid.data(), cand_host_begin, in.cand_begin.data(), in.cKRKi9.data(), in.cKt3.data(),
+                                   in.cand4.data(), &in.currentMinActDist, decision.data(), nullptr);   // 1 -> toOptimize.push_back(ph), 0 -> skipped, -1 -> delete ph (:653-669)
+}
+
 // referenced so that -Wunused does not hide a missing call path
 int shim_check_anchor(FullSystem& fs, FrameHessian* fh, CalibHessian& hc, const Undistort* u, const uint8_t* raw) {
   std::vector<int32_t> sel, st; Vec5 mr{}; SE3 T; AffLight a;
@@ -228,6 +265,8 @@ int shim_check_anchor(FullSystem& fs, FrameHessian* fh, CalibHessian& hc, const 
   fs.coarseTracker->setCoarseTrackingRef(fs.frameHessians); fs.coarseTracker->trackNewestCoarse(fh, T, a, 3, mr, nullptr);
   std::vector<ImmaturePoint*> imm; std::vector<HostImmatures> hi; rc |= shim_makeNewTraces(fh, sel, imm) | shim_traceNewCoarse(fh, hi);
   std::vector<ActivationGroup> ag; std::vector<float> idp; rc |= shim_activatePoints(ag, st, idp, sel, 7);
+  PixelSelector ps; LidarRig rig{}; std::vector<double> px; std::vector<sdv_new_trace> tr; std::vector<sdv_immature_pt> rc2; ActivationInputs ai; ai.pt_begin = {0}; ai.cand_begin = {0}; ai.currentMinActDist = 2;
+  rc |= shim_selector_ctor(ps) | shim_lidarCloudHandler(rig, nullptr, 0, px) | shim_makeNewTraces_whole(fh, rig, px, tr, rc2) | shim_activateSelect(ai, st);
   fs.optimize(6); fs.set_map(0); fs.handover(sel, st); fs.trackNewCoarse(fh); fs.refine_only(fh); shim_frame_destructor(fh);
   return rc;
 }
