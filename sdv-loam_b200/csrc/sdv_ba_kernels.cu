@@ -571,13 +571,22 @@ __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int ti
   // ---- top: frame-frame blocks (raw), frame-calib blocks, calib block, gradient
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
-    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk);
-      const int h = k % nF, t = k / nF; if (!((a == h || a == t) && (b == h || b == t))) continue;
-      if (H->accTopNum[k] == 0) continue;                                  // empty bucket contributes exact zeros
+    auto term = [&](int k) {                                               // the contribution of bucket k = h + nF*t to cell (a,b), in the reference's order hh, tt, ht
+      const int h = k % nF, t = k / nF;
+      if (H->accTopNum[k] == 0) return;                                    // empty bucket contributes exact zeros
       const double* AH = H->adHost + k*36; const double* AT = H->adTarget + k*36; const double* T1 = H->topT1 + k*36 + i*6; const double* T3 = H->topT3 + k*36 + i*6;
       if (a == h && b == h) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AH[j*6+q]; acc += s2; }
       if (a == t && b == t) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*AT[j*6+q]; acc += s2; }
       if (a == h && b == t) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AT[j*6+q]; acc += s2; }
+    };
+    if (MARG) {
+      for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int h = k % nF, t = k / nF; if (!((a == h || a == t) && (b == h || b == t))) continue; term(k); }
+    } else if (a != b) {                                                   // only the buckets (a,b) and (b,a) touch an off-diagonal cell: visit them in ascending k
+      const int k1 = a + nF*b, k2 = b + nF*a; term(k1 < k2 ? k1 : k2); term(k1 < k2 ? k2 : k1);
+    } else {                                                               // diagonal cell: buckets with h == a or t == a, ascending k = h + nF*t
+      for (int t = 0; t < a; t++) term(a + nF*t);
+      for (int h = 0; h < nF; h++) term(h + nF*a);
+      for (int t = a+1; t < nF; t++) term(a + nF*t);
     }
     if (!MARG && a == b && i == j) acc += H->frames[a].prior[i];
     sA[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
@@ -619,19 +628,36 @@ __device__ __forceinline__ void ba_stitch(BAHeader* __restrict__ H, const int ti
   // ---- Schur complement: frame-frame blocks
   for (int task = tid; task < nF2*36; task += kSolveThreads) {
     const int blk = task/36, e = task%36, a = blk/nF, b = blk%nF, i = e/6, j = e%6; double acc = 0;
-    for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
-      for (int k2 = 0; k2 < nF; k2++) {
-        const bool c1 = (a == fi && b == fi), c2 = (a == fj && b == k2), c3 = (a == fj && b == fi), c4 = (a == fi && b == k2);
-        if (!(c1 || c2 || c3 || c4)) continue;
-        const int bk = k + k2*nF2; if (H->accDNum[bk] == 0) continue;
-        const int ik = fi + nF*k2;
-        const double* AHik = H->adHost + ik*36 + j*6; const double* ATik = H->adTarget + ik*36 + j*6;
-        const double* T1 = H->scT1 + bk*36 + i*6; const double* T3 = H->scT3 + bk*36 + i*6;
-        if (c1) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AHik[q]; acc += s2; }
-        if (c2) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*ATik[q]; acc += s2; }
-        if (c3) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*AHik[q]; acc += s2; }
-        if (c4) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*ATik[q]; acc += s2; }
-      } }
+    auto term = [&](int fi, int fj, int k2) {                              // bucket (k = fi + nF*fj, k2) -> cell (a,b), conditions in the reference's order
+      const int k = fi + nF*fj;
+      const bool c1 = (a == fi && b == fi), c2 = (a == fj && b == k2), c3 = (a == fj && b == fi), c4 = (a == fi && b == k2);
+      if (!(c1 || c2 || c3 || c4)) return;
+      const int bk = k + k2*nF2; if (H->accDNum[bk] == 0) return;
+      const int ik = fi + nF*k2;
+      const double* AHik = H->adHost + ik*36 + j*6; const double* ATik = H->adTarget + ik*36 + j*6;
+      const double* T1 = H->scT1 + bk*36 + i*6; const double* T3 = H->scT3 + bk*36 + i*6;
+      if (c1) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*AHik[q]; acc += s2; }
+      if (c2) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*ATik[q]; acc += s2; }
+      if (c3) { double s2 = 0; for (int q=0;q<6;q++) s2 += T3[q]*AHik[q]; acc += s2; }
+      if (c4) { double s2 = 0; for (int q=0;q<6;q++) s2 += T1[q]*ATik[q]; acc += s2; }
+    };
+    if (MARG) {
+      for (int kk = 0; kk < nF2; kk++) { const int k = BK(kk); const int fi = k % nF, fj = k / nF; if (a != fi && a != fj) continue;
+        for (int k2 = 0; k2 < nF; k2++) term(fi, fj, k2); }
+    } else {
+      // same visiting order as the full scan (fj outer, fi inner, k2 innermost), restricted to the (fi, fj, k2) that can satisfy one of the four conditions:
+      //   fi == a: c1 needs b == a (any k2), c4 needs k2 == b;   fj == a: c2 needs k2 == b, c3 needs fi == b (any k2)
+      for (int fj = 0; fj < nF; fj++) {
+        if (fj != a) {                                                     // only fi == a can match (c1 / c4)
+          if (a == b) { for (int k2 = 0; k2 < nF; k2++) term(a, fj, k2); } else term(a, fj, b);
+        } else {
+          for (int fi = 0; fi < nF; fi++) {
+            const bool all_k2 = (fi == b) || (fi == a && a == b);          // c3, or c1
+            if (all_k2) { for (int k2 = 0; k2 < nF; k2++) term(fi, fj, k2); } else term(fi, fj, b);   // c2 (and c4 when fi == a) at k2 == b only
+          }
+        }
+      }
+    }
     sS[(kCP+a*6+i)*N + kCP+b*6+j] = acc;
   }
   BA_PROF_T(ts4); BA_PROF_ADD(11, ts3, ts4);

@@ -480,42 +480,17 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait1()  { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0()  { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// ---- packed two-lane fp32 arithmetic (sm_100a: FADD2 / FMUL2 / FFMA2, one issue slot for two IEEE operations; every lane rounds exactly like the scalar
-// instruction, so results are bit-identical to the scalar code).  A pair lives in an aligned 64-bit register pair; pk2 / upk2 are register renames.
-#ifndef SDV_F32X2
-#define SDV_F32X2 0
-#endif
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) { f32x2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-// acc[k0], acc[k1] += a * b lane-wise (two of the 45 upper-triangle sums in one FFMA2; each sum still receives exactly its own fmaf sequence)
-#define SDV_ACC2(k0, k1, A, B) do { f32x2_t c_ = fma2((A), (B), pk2(acc[k0], acc[k1])); upk2(c_, acc[k0], acc[k1]); } while (0)
-
 struct PtState { float u, v, nid, dx, dy, col; bool ok; };     // what the accumulate stage needs of a projected point (its taps are in the thread's smem slot)
 
 // calcRes, first half (CoarseTracker.cpp:525-575): projection + bounds, then launch the gather of the 2x2 (level 0: 12-tap) footprint into `slot`.
 template <int THREADS, bool LVL0>
 __device__ __forceinline__ PtState stage_project(const float4 p, const LevelGeom& g, const EvalParams& ep, const float4* __restrict__ img, const float* __restrict__ I0, uint32_t slot) {
   PtState s; const float x = p.x, y = p.y, id = p.z; s.col = p.w;
-#if SDV_F32X2
-  float pt0, pt1, Ku, Kv;                                   // rows 0 and 1 of the projection as one pair: same operations, same order, two lanes per instruction
-  { const f32x2_t xx = pk2(x, x), yy = pk2(y, y), ii = pk2(id, id);
-    const f32x2_t p01 = add2(add2(add2(mul2(pk2(ep.RKi[0], ep.RKi[3]), xx), mul2(pk2(ep.RKi[1], ep.RKi[4]), yy)), mul2(pk2(ep.RKi[2], ep.RKi[5]), pk2(1.0f, 1.0f))), mul2(pk2(ep.t[0], ep.t[1]), ii));
-    upk2(p01, pt0, pt1); }
-  float pt2 = ((ep.RKi[6]*x + ep.RKi[7]*y) + ep.RKi[8]*1.0f) + ep.t[2]*id;
-  s.u = pt0 / pt2; s.v = pt1 / pt2;
-  { const f32x2_t k = add2(mul2(pk2(g.fx, g.fy), pk2(s.u, s.v)), pk2(g.cx, g.cy)); upk2(k, Ku, Kv); }
-#else
   float pt0 = ((ep.RKi[0]*x + ep.RKi[1]*y) + ep.RKi[2]*1.0f) + ep.t[0]*id;
   float pt1 = ((ep.RKi[3]*x + ep.RKi[4]*y) + ep.RKi[5]*1.0f) + ep.t[1]*id;
   float pt2 = ((ep.RKi[6]*x + ep.RKi[7]*y) + ep.RKi[8]*1.0f) + ep.t[2]*id;
   s.u = pt0 / pt2; s.v = pt1 / pt2;
   const float Ku = g.fx*s.u + g.cx, Kv = g.fy*s.v + g.cy;
-#endif
   s.nid = id / pt2;
   s.ok = (Ku > 2 && Kv > 2 && Ku < (float)(g.w-3) && Kv < (float)(g.h-3) && s.nid > 0);
   s.dx = 0.f; s.dy = 0.f;
@@ -539,34 +514,6 @@ __device__ __forceinline__ PtState stage_project(const float4 p, const LevelGeom
 template <int THREADS, bool LVL0>
 __device__ __forceinline__ void stage_accumulate(const PtState s, const LevelGeom& g, const EvalParams& ep, const unsigned char* slot, float (&acc)[kNAcc]) {
   if (!s.ok) return;
-  const float dx = s.dx, dy = s.dy, dxdy = dx*dy, u = s.u, v = s.v, new_idepth = s.nid, refColor = s.col;
-  const float w11 = dxdy, w01 = dy-dxdy, w10 = dx-dxdy, w00 = 1-dx-dy+dxdy;
-  float hit0, hit1, hit2;
-#if SDV_F32X2
-  if (LVL0) {                                              // gradients of the four texels as (dx, dy) pairs: 0.5f*(a - b) lane-wise, then the guard of makeImages
-    const float* t = reinterpret_cast<const float*>(slot);
-    const float a_m1_0 = t[0*THREADS], a_m1_1 = t[1*THREADS];
-    const float a_0_m1 = t[2*THREADS], a_0_0 = t[3*THREADS], a_0_1 = t[4*THREADS], a_0_2 = t[5*THREADS];
-    const float a_1_m1 = t[6*THREADS], a_1_0 = t[7*THREADS], a_1_1 = t[8*THREADS], a_1_2 = t[9*THREADS];
-    const float a_2_0 = t[10*THREADS], a_2_1 = t[11*THREADS];
-    const f32x2_t half2 = pk2(0.5f, 0.5f);
-    f32x2_t g00 = mul2(half2, sub2(pk2(a_0_1, a_1_0), pk2(a_0_m1, a_m1_0)));
-    f32x2_t g10 = mul2(half2, sub2(pk2(a_0_2, a_1_1), pk2(a_0_0, a_m1_1)));
-    f32x2_t g01 = mul2(half2, sub2(pk2(a_1_1, a_2_0), pk2(a_1_m1, a_0_0)));
-    f32x2_t g11 = mul2(half2, sub2(pk2(a_1_2, a_2_1), pk2(a_1_0, a_0_1)));
-    { float x_, y_; upk2(g00, x_, y_); g00 = pk2(grad_guard(x_), grad_guard(y_)); upk2(g10, x_, y_); g10 = pk2(grad_guard(x_), grad_guard(y_));
-      upk2(g01, x_, y_); g01 = pk2(grad_guard(x_), grad_guard(y_)); upk2(g11, x_, y_); g11 = pk2(grad_guard(x_), grad_guard(y_)); }
-    hit0 = ((w11*a_1_1 + w01*a_1_0) + w10*a_0_1) + w00*a_0_0;
-    const f32x2_t h12 = add2(add2(add2(mul2(pk2(w11, w11), g11), mul2(pk2(w01, w01), g01)), mul2(pk2(w10, w10), g10)), mul2(pk2(w00, w00), g00));
-    upk2(h12, hit1, hit2);
-  } else {                                                 // packed texels {I, dx, dy, |grad|^2}: (I, dx) is an aligned register pair of the 128-bit load
-    const float4* t = reinterpret_cast<const float4*>(slot);
-    const float4 p00 = t[0*THREADS], p10 = t[1*THREADS], p01 = t[2*THREADS], p11 = t[3*THREADS];
-    const f32x2_t h01 = add2(add2(add2(mul2(pk2(w11, w11), pk2(p11.x, p11.y)), mul2(pk2(w01, w01), pk2(p01.x, p01.y))), mul2(pk2(w10, w10), pk2(p10.x, p10.y))), mul2(pk2(w00, w00), pk2(p00.x, p00.y)));
-    upk2(h01, hit0, hit1);
-    hit2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
-  }
-#else
   float4 p00, p10, p01, p11;
   if (LVL0) {
     const float* t = reinterpret_cast<const float*>(slot);
@@ -582,10 +529,11 @@ __device__ __forceinline__ void stage_accumulate(const PtState s, const LevelGeo
     const float4* t = reinterpret_cast<const float4*>(slot);
     p00 = t[0*THREADS]; p10 = t[1*THREADS]; p01 = t[2*THREADS]; p11 = t[3*THREADS];
   }
-  hit0 = ((w11*p11.x + w01*p01.x) + w10*p10.x) + w00*p00.x;
-  hit1 = ((w11*p11.y + w01*p01.y) + w10*p10.y) + w00*p00.y;
-  hit2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
-#endif
+  const float dx = s.dx, dy = s.dy, dxdy = dx*dy, u = s.u, v = s.v, new_idepth = s.nid, refColor = s.col;
+  float w11 = dxdy, w01 = dy-dxdy, w10 = dx-dxdy, w00 = 1-dx-dy+dxdy;
+  float hit0 = ((w11*p11.x + w01*p01.x) + w10*p10.x) + w00*p00.x;
+  float hit1 = ((w11*p11.y + w01*p01.y) + w10*p10.y) + w00*p00.y;
+  float hit2 = ((w11*p11.z + w01*p01.z) + w10*p10.z) + w00*p00.z;
   if (!isfinite(hit0)) return;
   float residual = hit0 - (ep.aLL*refColor + ep.bLL);
   float ar = fabsf(residual);
@@ -604,24 +552,6 @@ __device__ __forceinline__ void stage_accumulate(const PtState s, const LevelGeo
   J[6] = ep.aLL*(ep.b0 - refColor);
   J[7] = -1.0f;
   J[8] = residual;
-#if SDV_F32X2
-  // acc[] holds the upper triangle of the 9x9 sum row by row: entry (r,c) at k_r + c - r, k_r = {0, 9, 17, 24, 30, 35, 39, 42, 44}.  acc(r,c) = fmaf(J[r]*hw, J[c], acc(r,c)).
-  const f32x2_t hw2 = pk2(hw, hw), J01 = pk2(J[0], J[1]), J23 = pk2(J[2], J[3]), J45 = pk2(J[4], J[5]), J67 = pk2(J[6], J[7]), J88 = pk2(J[8], J[8]);
-  const f32x2_t W01 = mul2(J01, hw2), W23 = mul2(J23, hw2), W45 = mul2(J45, hw2), W67 = mul2(J67, hw2);
-  float Jw[9]; upk2(W01, Jw[0], Jw[1]); upk2(W23, Jw[2], Jw[3]); upk2(W45, Jw[4], Jw[5]); upk2(W67, Jw[6], Jw[7]); Jw[8] = J[8]*hw;
-  // diagonal (r,r): lane-wise Jw * J
-  SDV_ACC2(0, 9, W01, J01); SDV_ACC2(17, 24, W23, J23); SDV_ACC2(30, 35, W45, J45); SDV_ACC2(39, 42, W67, J67);
-  // last column (r,8): Jw pairs times J[8]
-  SDV_ACC2(8, 16, W01, J88); SDV_ACC2(23, 29, W23, J88); SDV_ACC2(34, 38, W45, J88); SDV_ACC2(41, 43, W67, J88); acc[44] = fmaf(Jw[8], J[8], acc[44]);
-  // strictly upper part, columns 1..7: one row's Jw broadcast against the fixed column pairs (2,3) (4,5) (6,7); the four entries (r, r+1) of the even rows stay scalar
-  { const f32x2_t b = pk2(Jw[0], Jw[0]); acc[1] = fmaf(Jw[0], J[1], acc[1]); SDV_ACC2(2, 3, b, J23); SDV_ACC2(4, 5, b, J45); SDV_ACC2(6, 7, b, J67); }
-  { const f32x2_t b = pk2(Jw[1], Jw[1]); SDV_ACC2(10, 11, b, J23); SDV_ACC2(12, 13, b, J45); SDV_ACC2(14, 15, b, J67); }
-  { const f32x2_t b = pk2(Jw[2], Jw[2]); acc[18] = fmaf(Jw[2], J[3], acc[18]); SDV_ACC2(19, 20, b, J45); SDV_ACC2(21, 22, b, J67); }
-  { const f32x2_t b = pk2(Jw[3], Jw[3]); SDV_ACC2(25, 26, b, J45); SDV_ACC2(27, 28, b, J67); }
-  { const f32x2_t b = pk2(Jw[4], Jw[4]); acc[31] = fmaf(Jw[4], J[5], acc[31]); SDV_ACC2(32, 33, b, J67); }
-  { const f32x2_t b = pk2(Jw[5], Jw[5]); SDV_ACC2(36, 37, b, J67); }
-  acc[40] = fmaf(Jw[6], J[7], acc[40]);
-#else
   int k = 0;
 #pragma unroll
   for (int r = 0; r < 9; r++) {
@@ -629,7 +559,6 @@ __device__ __forceinline__ void stage_accumulate(const PtState s, const LevelGeo
 #pragma unroll
     for (int c = r; c < 9; c++) { acc[k] = fmaf(Jw, J[c], acc[k]); k++; }
   }
-#endif
 }
 // flow indicators of one level-0 point with index % 32 == 0 (CoarseTracker.cpp:538-566); same expressions as eval_point
 __device__ __forceinline__ void flow_point(const float4 p, const LevelGeom& g, const EvalParams& ep, float (&acc)[kNAcc]) {
