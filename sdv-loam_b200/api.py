@@ -632,10 +632,17 @@ class LidarFrontEnd:
 
     def handle(self, sweeps, Rlc, tlc, K4, lruds, cap=None):
         """sweeps: list of (n,4) float32 XYZI arrays; Rlc (3,3) / tlc (3,) / K4 shared or per sweep; lruds (n,4) running pixel boxes -> list of dicts like the oracle's"""
-        n = len(sweeps); sw = [np.ascontiguousarray(s, np.float32).reshape(-1, 4) for s in sweeps]; sb = np.concatenate([[0], np.cumsum([len(s) for s in sw])]).astype(np.int32)
-        allp = np.ascontiguousarray(np.concatenate(sw) if sb[-1] else np.zeros((1, 4), np.float32)); cap = cap or self.n_scan * self.horizon
+        sw = [np.ascontiguousarray(s, np.float32).reshape(-1, 4) for s in sweeps]; sb = np.concatenate([[0], np.cumsum([len(s) for s in sw])]).astype(np.int32)
+        allp = np.ascontiguousarray(np.concatenate(sw) if sb[-1] else np.zeros((1, 4), np.float32))
+        return self.handle_packed(allp, sb, Rlc, tlc, K4, lruds, cap)
+
+    def handle_packed(self, xyzi_all, sweep_begin, Rlc, tlc, K4, lruds, cap=None):
+        """the same with the sweeps already back to back in ONE host buffer (pinned or not) and their row offsets: nothing is copied on the host"""
+        sb = np.ascontiguousarray(sweep_begin, np.int32); n = len(sb) - 1; allp = xyzi_all; assert allp.dtype == np.float32 and allp.flags.c_contiguous
+        cap = cap or self.n_scan * self.horizon
         R = np.ascontiguousarray(np.broadcast_to(np.asarray(Rlc, np.float64).reshape(-1, 9), (n, 9))).reshape(-1); t = np.ascontiguousarray(np.broadcast_to(np.asarray(tlc, np.float64).reshape(-1, 3), (n, 3))).reshape(-1)
         K = np.ascontiguousarray(np.broadcast_to(np.asarray(K4, np.float32).reshape(-1, 4), (n, 4))).reshape(-1); lr = np.ascontiguousarray(lruds, np.int32).reshape(n, 4).copy()
-        out = np.zeros((n, cap, 3)); n_out = np.zeros(n, np.int32); add = np.zeros(n, np.int32); st = np.zeros(2 * n, np.int32)
+        if getattr(self, "_out", None) is None or self._out.shape != (n, cap, 3): self._out = np.zeros((n, cap, 3))
+        out = self._out; n_out = np.zeros(n, np.int32); add = np.zeros(n, np.int32); st = np.zeros(2 * n, np.int32)
         self.ctx._ck(LIB.sdv_lidar_handler_batch(self.ctx.p, n, sb, allp.ctypes.data, R, t, K, lr.reshape(-1), cap, out.ctypes.data, n_out, add, st))
         return [dict(cloud_px=out[j, :n_out[j]].copy(), lrud=lr[j], numGround=int(st[2 * j]), n_segmented=int(st[2 * j + 1]), addFeaturePoint=int(add[j])) for j in range(n)]

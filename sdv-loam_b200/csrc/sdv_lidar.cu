@@ -44,6 +44,7 @@ int sdv_lidar_handler_batch(sdv_ctx* c, int n, const int32_t* sweep_begin, const
   CK(cudaEventRecord(c->ev0, c->st));
   { int rc = s->eng.handle(S); if (rc) return ctx_fail(c, rc == -2 ? SDV_ERR_CAPACITY : SDV_ERR_CUDA, "lidar_handler: %s", s->eng.err.c_str()); }
   CK(cudaEventRecord(c->ev1, c->st)); CK(cudaStreamSynchronize(c->st)); CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+  if (s->eng.have_ev) c->last_ms = s->eng.last_kernel_ms;                                  // sdv_last_kernel_ms: the nine kernels of the front-end, copies excluded
   c->launches += s->eng.launches - l0;
   for (int j = 0; j < n; j++) { n_out[j] = S[j].n_out; for (int k = 0; k < 4; k++) lrud_io[4*j+k] = S[j].lrud[k]; if (add_feature_point_out) add_feature_point_out[j] = S[j].addFeaturePoint;
     if (stats_out) { stats_out[2*j] = S[j].numGround; stats_out[2*j+1] = S[j].n_segmented; } }

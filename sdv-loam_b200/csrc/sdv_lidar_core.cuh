@@ -188,13 +188,15 @@ __global__ void __launch_bounds__(128) lf_emit_kernel(const LidarJob* __restrict
 // ================================================================================================ host engine
 struct LidarEngine {
   LidarSet S; cudaStream_t st = nullptr; std::string err; Scratch io; long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool have_ev = false; float last_kernel_ms = 0.f;   // device time of the nine launches of the last handle() (copies excluded)
   // sinf / cosf of the two angular resolutions come from the host's libm (only these four values are ever needed)
   void init(int n_scan, int horizon, float ang_res_x, float ang_res_y, float ang_bottom, int groundScanInd, cudaStream_t st_) {
+    if (!have_ev) { have_ev = (cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess); }
     st = st_; S.N = n_scan; S.H = horizon; S.ang_res_x = ang_res_x; S.ang_res_y = ang_res_y; S.ang_bottom = ang_bottom; S.groundScanInd = groundScanInd; S.sensorMountAngle = 0.0f;
     S.segmentTheta = (float)(60.0/180.0*M_PI); const float ax = (float)(ang_res_x / 180.0 * M_PI), ay = (float)(ang_res_y / 180.0 * M_PI);           // main.cpp:118-122
     S.sinX = sinf(ax); S.cosX = cosf(ax); S.sinY = sinf(ay); S.cosY = cosf(ay); S.validPointNum = 5; S.validLineNum = 3;
   }
-  void destroy() { io.release(); }
+  void destroy() { io.release(); if (have_ev) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); have_ev = false; } }
   struct Sweep { const float* xyzi_host; int n; double R[9], t[3]; float K[4]; int w, h; int lrud[4];      // in (lrud: FullSystem::left/right/up/down, updated)
                  double* out3_host; int cap; int n_out, numGround, n_segmented, addFeaturePoint; };        // out
   int handle(std::vector<Sweep>& sw) {
@@ -202,20 +204,32 @@ struct LidarEngine {
     if (S.N > 128 || S.groundScanInd >= S.N) { err = "lidar: at most 128 rings, groundScanInd < rings"; return -1; }
     const size_t m = (size_t)S.N*S.H; size_t bytes = Scratch::need(nj, sizeof(LidarJob)) + 1024;
     for (auto& s : sw) bytes += Scratch::need(std::max(s.n, 1), 16) + 5*Scratch::need(m, 4) + Scratch::need(m, 16) + 2*Scratch::need(m, 1) + Scratch::need(2*m, 8) + Scratch::need(2*m, 4)
-                              + Scratch::need(3*(size_t)s.cap, 8) + Scratch::need(8, 4);
+                              + Scratch::need(3*(size_t)s.cap, 8) + Scratch::need(8, 4) + 1024;
     if (io.reserve(bytes, st)) { err = "scratch"; return -1; }
     io.reset(); std::vector<LidarJob> J(nj); LidarJob* dJ = io.take<LidarJob>(nj); int maxN = 0;
+    // per-type arrays of all sweeps back to back: one memset / one counter upload / one counter read-back per call instead of one per sweep
+    int* cellIdx_all = io.take<int>(m*nj); int* counters_all = io.take<int>((size_t)8*nj); std::vector<int> c0((size_t)8*nj, 0);
+    size_t tot_pts = 0; for (auto& s : sw) tot_pts += (size_t)std::max(s.n, 0);
+    float4* pts_all = io.take<float4>(std::max(tot_pts, (size_t)1)); size_t off = 0;
     for (int j = 0; j < nj; j++) { Sweep& s = sw[j]; LidarJob& L = J[j];
-      float4* pts = io.take<float4>(std::max(s.n, 1)); if (s.n) SEL_CK(cudaMemcpyAsync(pts, s.xyzi_host, (size_t)s.n*16, cudaMemcpyHostToDevice, st));
-      L.pts = pts; L.n = s.n; L.cellIdx = io.take<int>(m); L.range = io.take<float>(m); L.cloud = io.take<float4>(m); L.ground = io.take<signed char>(m); L.parent = io.take<int>(m); L.csize = io.take<int>(m);
+      float4* pts = pts_all + off;
+      if (s.n) {                                              // sweeps that follow each other in host memory (the C-ABI's layout) travel in ONE copy
+        int j2 = j; size_t run = (size_t)s.n;
+        const bool starts_run = (j == 0) || !(sw[j-1].n > 0 && sw[j-1].xyzi_host + 4*(size_t)sw[j-1].n == s.xyzi_host);
+        if (starts_run) { while (j2 + 1 < nj && sw[j2+1].n > 0 && sw[j2].xyzi_host + 4*(size_t)sw[j2].n == sw[j2+1].xyzi_host) { j2++; run += (size_t)sw[j2].n; }
+          SEL_CK(cudaMemcpyAsync(pts, s.xyzi_host, run*16, cudaMemcpyHostToDevice, st)); }
+      }
+      off += (size_t)std::max(s.n, 0);
+      L.pts = pts; L.n = s.n; L.cellIdx = cellIdx_all + (size_t)j*m; L.range = io.take<float>(m); L.cloud = io.take<float4>(m); L.ground = io.take<signed char>(m); L.parent = io.take<int>(m); L.csize = io.take<int>(m);
       L.rowmask = io.take<unsigned long long>(2*m); L.flag = io.take<unsigned char>(m); L.pos = io.take<int>(m); L.kuv = io.take<float>(2*m);
       for (int k = 0; k < 9; k++) L.R[k] = s.R[k]; for (int k = 0; k < 3; k++) L.t[k] = s.t[k]; L.fx = s.K[0]; L.fy = s.K[1]; L.cx = s.K[2]; L.cy = s.K[3]; L.w = s.w; L.h = s.h;
-      L.out3 = io.take<double>(3*(size_t)std::max(s.cap, 1)); L.cap = s.cap; L.counters = io.take<int>(8);
-      const int c0[8] = {0, 0, s.lrud[0], s.lrud[1], s.lrud[2], s.lrud[3], 0, 0};
-      SEL_CK(cudaMemcpyAsync(L.counters, c0, sizeof(c0), cudaMemcpyHostToDevice, st)); SEL_CK(cudaMemsetAsync(L.cellIdx, 0xFF, m*sizeof(int), st));
+      L.out3 = io.take<double>(3*(size_t)std::max(s.cap, 1)); L.cap = s.cap; L.counters = counters_all + 8*j;
+      for (int k = 0; k < 4; k++) c0[8*j+2+k] = s.lrud[k];
       maxN = std::max(maxN, s.n); }
+    SEL_CK(cudaMemcpyAsync(counters_all, c0.data(), c0.size()*sizeof(int), cudaMemcpyHostToDevice, st)); SEL_CK(cudaMemsetAsync(cellIdx_all, 0xFF, m*nj*sizeof(int), st));
     SEL_CK(cudaMemcpyAsync(dJ, J.data(), nj*sizeof(LidarJob), cudaMemcpyHostToDevice, st));
     const dim3 gc((unsigned)((m + 127)/128), nj), b128(128);
+    if (have_ev) cudaEventRecord(ev0, st);
     if (maxN > 0) SDV_LAUNCH(lf_project_kernel, dim3((maxN + 127)/128, nj), b128, st, dJ, S);
     SDV_LAUNCH(lf_gather_kernel, gc, b128, st, dJ, S);
     SDV_LAUNCH(lf_ground_kernel, dim3((S.H + 127)/128, nj), b128, st, dJ, S);
@@ -225,10 +239,12 @@ struct LidarEngine {
     SDV_LAUNCH(lf_keep_kernel, gc, b128, st, dJ, S);
     SDV_LAUNCH_SYNC(lf_scan_kernel, dim3(nj), dim3(256), st, dJ, S);
     SDV_LAUNCH(lf_emit_kernel, gc, b128, st, dJ, S);
+    if (have_ev) cudaEventRecord(ev1, st);
     launches += 9; SEL_CK(cudaGetLastError());
     std::vector<int> cnt((size_t)nj*8);
-    for (int j = 0; j < nj; j++) SEL_CK(cudaMemcpyAsync(&cnt[8*j], J[j].counters, 8*sizeof(int), cudaMemcpyDeviceToHost, st));
+    SEL_CK(cudaMemcpyAsync(cnt.data(), counters_all, cnt.size()*sizeof(int), cudaMemcpyDeviceToHost, st));
     SEL_CK(cudaStreamSynchronize(st));
+    if (have_ev) cudaEventElapsedTime(&last_kernel_ms, ev0, ev1);
     for (int j = 0; j < nj; j++) { Sweep& s = sw[j]; const int* c = &cnt[8*j]; s.n_out = c[0]; s.numGround = c[1]; for (int k = 0; k < 4; k++) s.lrud[k] = c[2+k]; s.n_segmented = c[6];
       s.addFeaturePoint = ((float)s.numGround / (float)s.n_out > 0.8) ? 1 : 0;                                 // :851-854
       if (s.n_out > s.cap) { err = "lidar: output capacity too small"; return -2; }

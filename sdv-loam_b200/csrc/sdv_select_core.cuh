@@ -520,15 +520,17 @@ struct SelEngine {
   int w = 0, h = 0; SelSet S; cudaStream_t st = nullptr; std::string err;
   unsigned char* rp = nullptr;           // randomPattern (device)
   Scratch scr, scr2; long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool have_ev = false; float last_kernel_ms = 0.f;   // device time of the launches of the last activate() (copies excluded)
   size_t max_scratch = (size_t)1 << 30;
 
   int init(int w_, int h_, const SelSet& S_, const unsigned char* random_pattern_host, cudaStream_t st_) {
     w = w_; h = h_; S = S_; st = st_;
+    if (!have_ev) have_ev = (cudaEventCreate(&ev0) == cudaSuccess && cudaEventCreate(&ev1) == cudaSuccess);
     if (rp) cudaFree(rp);
     SEL_CK(cudaMalloc((void**)&rp, (size_t)w*h)); SEL_CK(cudaMemcpyAsync(rp, random_pattern_host, (size_t)w*h, cudaMemcpyHostToDevice, st)); SEL_CK(cudaStreamSynchronize(st));
     return 0;
   }
-  void destroy() { if (rp) cudaFree(rp); rp = nullptr; scr.release(); scr2.release(); }
+  void destroy() { if (rp) cudaFree(rp); rp = nullptr; scr.release(); scr2.release(); if (have_ev) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); have_ev = false; } }
   size_t ths_floats() const { const int w32 = w/32, h32 = h/32; return (size_t)w32*(h32+1) + 101; }   // thsSmoothed is read up to one block row / column past its end (zero there)
 
   // PixelSelector::makeHists for nj frames: ths / thsSm are device arrays of ths_floats() floats per job, zero-initialised by the caller
@@ -722,11 +724,13 @@ struct SelEngine {
       maxP = std::max(maxP, np); maxC = std::max(maxC, nc); }
     SEL_CK(cudaMemcpyAsync(dD, D.data(), nj*sizeof(DistJob), cudaMemcpyHostToDevice, st));
     const int gpx = (int)std::min<size_t>((n1 + 255)/256, 1024);
+    if (have_ev) cudaEventRecord(ev0, st);
     SDV_LAUNCH(dm_fill_kernel, dim3(gpx, nj), dim3(256), st, dD);
     if (maxP > 0) SDV_LAUNCH(dm_source_kernel, dim3((maxP + 127)/128, nj), dim3(128), st, dD);
     for (int k = 1; k < 40; k++) SDV_LAUNCH(dm_ring_kernel, dim3(gpx, nj), dim3(256), st, dD, k);
     launches += 41;
     if (maxC > 0) { SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD); SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD); launches += 2; }
+    if (have_ev) cudaEventRecord(ev1, st);
     SEL_CK(cudaGetLastError());
     std::vector<std::vector<int>> maps(nj);
     for (int j = 0; j < nj; j++) { ActJob& a = jobs[j]; const int nc = a.nCandHosts ? a.cand_begin[a.nCandHosts] : 0;
@@ -734,6 +738,7 @@ struct SelEngine {
       if (a.map_host) { maps[j].resize(n1); SEL_CK(cudaMemcpyAsync(maps[j].data(), D[j].d, n1*sizeof(int), cudaMemcpyDeviceToHost, st)); } }
     SEL_CK(cudaStreamSynchronize(st));
     for (int j = 0; j < nj; j++) if (jobs[j].map_host) for (size_t i = 0; i < n1; i++) jobs[j].map_host[i] = (float)maps[j][i];
+    if (have_ev) cudaEventElapsedTime(&last_kernel_ms, ev0, ev1);
     return 0;
   }
 };

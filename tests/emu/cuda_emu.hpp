@@ -82,3 +82,9 @@ static inline int __float_as_int(float f) { int b; memcpy(&b, &f, 4); return b; 
 static inline float __int_as_float(int b) { float f; memcpy(&f, &b, 4); return f; }
 static inline unsigned long long atomicOr(unsigned long long* p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+typedef void* cudaEvent_t;
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }

@@ -102,7 +102,8 @@ class LidarEngine:
 
     def handle(self, sweeps, Rlc, tlc, K4, wh, lruds):
         nj = len(sweeps); sw = [np.ascontiguousarray(s, np.float32).reshape(-1, 4) for s in sweeps]; cap = self.n_scan * self.horizon
-        ptrs = (C.c_void_p * nj)(*[s.ctypes.data for s in sw]); n = np.array([len(s) for s in sw], np.int32); lr = np.ascontiguousarray(lruds, np.int32).reshape(nj, 4).copy()
+        allp = np.ascontiguousarray(np.concatenate(sw)) if nj else np.zeros((0, 4), np.float32); offs = np.concatenate([[0], np.cumsum([len(s) for s in sw])])   # back to back, like the C-ABI hands them over
+        ptrs = (C.c_void_p * nj)(*[allp.ctypes.data + 16 * int(offs[j]) for j in range(nj)]); n = np.array([len(s) for s in sw], np.int32); lr = np.ascontiguousarray(lruds, np.int32).reshape(nj, 4).copy()
         out = np.zeros((nj, cap, 3)); res = np.zeros((nj, 4), np.int32); R = np.ascontiguousarray(Rlc, np.float64).reshape(-1); t = np.ascontiguousarray(tlc, np.float64); K = np.ascontiguousarray(K4, np.float32)
         rc = lib().emu_lidar_handle(self.p, nj, ptrs, n.ctypes.data, R.ctypes.data, t.ctypes.data, K.ctypes.data, wh[0], wh[1], lr.ctypes.data, out.ctypes.data, cap, res.ctypes.data)
         if rc: raise RuntimeError(lib().emu_lidar_error(self.p).decode())

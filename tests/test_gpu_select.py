@@ -112,6 +112,12 @@ def test_lidar_front_end_batch():
     for cloud in (np.zeros((0, 4), np.float32), np.array([[np.nan, 0, 0, 0], [0.01, 0.01, 0, 0]], np.float32), S[0][::7]):
         o = fe.handle(cloud, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = G.handle([cloud], synth.RLC, synth.TLC, SMALL_K, [[10000, -1, 10000, -1]])[0]
         assert np.array_equal(o["cloud_px"], g["cloud_px"]) and np.array_equal(o["lrud"], g["lrud"]) and o["addFeaturePoint"] == g["addFeaturePoint"] and o["n_segmented"] == g["n_segmented"]
+    # S-STRESS sensor: 128 rings (the sensor constants are parameters of sdv_lidar_init)
+    world = synth.World(3000); Rt = synth.trajectory(1, 3000); sw128 = synth.lidar_sweep(world, Rt[0][0], Rt[1][0], beams=128, seed=3)
+    args = dict(n_scan=128, horizon=1800, ang_res_x=0.2, ang_res_y=0.427 / 2, ang_bottom=24.9, groundScanInd=100)
+    o = orc.LidarFrontEnd(**args).handle(sw128, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = api.LidarFrontEnd(ctx, **args).handle([sw128, sw128[::3]], synth.RLC, synth.TLC, SMALL_K, [[10000, -1, 10000, -1]] * 2)[0]
+    assert np.array_equal(o["cloud_px"], g["cloud_px"]) and len(o["cloud_px"]) > 6000 and np.array_equal(o["lrud"], g["lrud"]) and o["n_segmented"] == g["n_segmented"]
+    G = api.LidarFrontEnd(ctx)
     # front-end -> selector: the device-produced pixel rows drive makeNewTraces of the same keyframe
     w, h = SMALL_WH; res = G.handle([S[0]], synth.RLC, synth.TLC, SMALL_K, [[10000, -1, 10000, -1]])[0]
     ps = api.PixelSelector(ctx, 1, rp); osel = orc.Selector(w, h, rp); dl = api.lidar_density(res["lrud"], SMALL_WH, 600.0)

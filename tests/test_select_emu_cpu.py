@@ -136,3 +136,13 @@ def test_lidar_front_end_batch():
     for cloud in (np.zeros((0, 4), np.float32), np.array([[np.nan, 0, 0, 0], [0.01, 0.01, 0, 0]], np.float32), S[0][::7]):
         o = fe.handle(cloud, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = E.handle([cloud], synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [[10000, -1, 10000, -1]])[0]
         assert np.array_equal(o["cloud_px"], g["cloud_px"]) and np.array_equal(o["lrud"], g["lrud"]) and o["addFeaturePoint"] == g["addFeaturePoint"] and o["n_segmented"] == g["n_segmented"]
+
+
+def test_lidar_front_end_128_beams():
+    """S-STRESS sensor (BASELINE config #5: 128 beams over the same elevation span): sensor constants are parameters here (the reference hard-codes N_SCAN = 64, main.cpp:103)"""
+    import sdv_loam_b200  # noqa
+    from sdv_loam_b200 import synth
+    world = synth.World(3000); R, t = synth.trajectory(1, 3000); sw = synth.lidar_sweep(world, R[0], t[0], beams=128, seed=3)
+    args = dict(n_scan=128, horizon=1800, ang_res_x=0.2, ang_res_y=0.427 / 2, ang_bottom=24.9, groundScanInd=100)
+    o = orc.LidarFrontEnd(**args).handle(sw, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = se.LidarEngine(**args).handle([sw], synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [[10000, -1, 10000, -1]])[0]
+    assert np.array_equal(o["cloud_px"], g["cloud_px"]) and len(o["cloud_px"]) > 6000 and np.array_equal(o["lrud"], g["lrud"]) and o["n_segmented"] == g["n_segmented"] and o["numGround"] == g["numGround"]
