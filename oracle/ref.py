@@ -356,6 +356,26 @@ class System:
         with _Quiet():
             return lib().ref_sys_add_frame(self.p, img, exposure, timestamp, cl, len(cl))
 
+    # ---- PixelSelector / makeNewTraces state of the running system (tests/test_sequence_select.py)
+    def selector_zero(self): lib().ref_sys_selector_zero.argtypes = [_vp]; lib().ref_sys_selector_zero(self.p)
+    def selector_state(self, wh, with_map=True):
+        L = lib(); L.ref_sys_selector_state.argtypes = [_vp, _vp]; m = np.zeros((wh[1], wh[0]), np.float32) if with_map else None
+        return L.ref_sys_selector_state(self.p, m.ctypes.data if with_map else None), m
+    def set_selection_map(self, m): lib().ref_sys_set_selection_map.argtypes = [_vp, _f32p]; lib().ref_sys_set_selection_map(self.p, np.ascontiguousarray(m, np.float32).reshape(-1))
+    def set_lidar_state(self, lrud, addFeaturePoint): lib().ref_sys_set_lidar_state.argtypes = [_vp, _i32p, C.c_int]; lib().ref_sys_set_lidar_state(self.p, np.ascontiguousarray(lrud, np.int32), int(addFeaturePoint))
+    def newest_kf_immature(self, cap=1 << 16):
+        L = lib(); L.ref_sys_newest_kf_immature.argtypes = [_vp, _f32p, C.c_int, C.POINTER(C.c_int)]; o = np.zeros((cap, 7), np.float32); k = C.c_int(-1)
+        m = L.ref_sys_newest_kf_immature(self.p, o.reshape(-1), cap, C.byref(k)); assert m <= cap
+        return (o[:m], k.value) if m >= 0 else (None, -1)
+
+    def probe_new_traces(self, frame: "Frame", cloud3, cap=1 << 16):
+        """FullSystem::makeNewTraces of the running system on `frame` with its live selector state, state restored afterwards -> rows {u,v,my_type,score,idepth_fromSensor,isFromSensor,type}"""
+        L = lib(); L.ref_sys_probe_new_traces.argtypes = [_vp, _vp, _vp, C.c_int, _f32p, C.c_int, C.c_int]; c = np.ascontiguousarray(cloud3, np.float64).reshape(-1, 3); o = np.zeros((cap, 7), np.float32)
+        with _Quiet():
+            m = L.ref_sys_probe_new_traces(self.p, frame.p, c.ctypes.data, len(c), o.reshape(-1), cap, 0)
+        assert m <= cap
+        return o[:m]
+
     def num_frames(self): return lib().ref_sys_num_frames(self.p)
     def num_keyframes(self): return lib().ref_sys_num_keyframes(self.p)
 

@@ -656,4 +656,38 @@ int ref_lidar_handler(void* ba, const float* xyzi, int n, const double* Rlc9, co
 }
 int ref_lidar_dims(int* n_scan, int* horizon) { *n_scan = N_SCAN; *horizon = Horizon_SCAN; return 0; }
 
+// ---- sequence level: the PixelSelector / makeNewTraces state of a RUNNING system (tests/test_sequence_select.py).  makeNewTraces is the last thing makeKeyFrame does
+// (FullSystem.cpp:1165), so after addActiveFrame returns the newest keyframe's immaturePoints ARE its output; the selector state is read before the call.
+void ref_sys_selector_zero(void* p) { selector_zero(((RefSys*)p)->fs->pixelSelector); }
+int  ref_sys_selector_state(void* p, float* selectionMap_out) { FullSystem* fs = ((RefSys*)p)->fs; if (selectionMap_out) memcpy(selectionMap_out, fs->selectionMap, sizeof(float)*(size_t)wG[0]*hG[0]); return fs->pixelSelector->currentPotential; }
+void ref_sys_set_selection_map(void* p, const float* m) { memcpy(((RefSys*)p)->fs->selectionMap, m, sizeof(float)*(size_t)wG[0]*hG[0]); }
+void ref_sys_set_lidar_state(void* p, const int lrud[4], int addFeaturePoint) { FullSystem* fs = ((RefSys*)p)->fs; fs->left = lrud[0]; fs->right = lrud[1]; fs->up = lrud[2]; fs->down = lrud[3]; fs->addFeaturePoint = addFeaturePoint != 0; }
+// immature points of the newest keyframe: rows {u, v, my_type, score, idepth_fromSensor, isFromSensor, type}; returns the count (-1: no keyframe yet), *kf_shell_id = its frame id
+int  ref_sys_newest_kf_immature(void* p, float* out7, int cap, int* kf_shell_id) {
+  FullSystem* fs = ((RefSys*)p)->fs; if (fs->frameHessians.empty()) return -1; FrameHessian* fh = fs->frameHessians.back(); *kf_shell_id = fh->shell->id; int m = 0;
+  for (ImmaturePoint* ip : fh->immaturePoints) { if (m < cap) { float* o = out7 + 7*m; o[0] = ip->u; o[1] = ip->v; o[2] = ip->my_type; o[3] = ip->isFromSensor ? ip->score : 0.f;
+      o[4] = ip->isFromSensor ? ip->idepth_fromSensor : 0.f; o[5] = ip->isFromSensor ? 1.f : 0.f; o[6] = ip->isFromSensor ? (float)(int)ip->type : -1.f; } m++; }
+  return m;
+}
+
+// makeNewTraces of the RUNNING system on a probe frame (a RefFrame of the image that is about to be added), with the system's live selector state; the state
+// (currentPotential, selectionMap) is put back afterwards, so the run itself is not disturbed.  In this reference makeNewTraces runs BEFORE activatePointsMT
+// (FullSystem.cpp:1080 vs :1102), so its output cannot be read off the keyframe after the fact: the probe is how the complete list is obtained.
+// commit != 0 keeps the new state instead (used to check the state the real call leaves behind).
+int ref_sys_probe_new_traces(void* p, void* frame, const double* cloud3, int n, float* out7, int cap, int commit) {
+  FullSystem* fs = ((RefSys*)p)->fs; RefFrame* F = (RefFrame*)frame; FrameHessian* fh = F->fh; size_t wh = (size_t)wG[0]*hG[0];
+  int pot = fs->pixelSelector->currentPotential; std::vector<float> keep(fs->selectionMap, fs->selectionMap + wh);
+  F->shell->timestamp = 12345.0; fs->qCloudPixel.push(cloud_of(cloud3, n)); fs->qTimeLidarCloud.push(12345.0);
+  // put the probe's data at the FRONT of the queues makeNewTraces reads (they are empty between frames in this harness)
+  fs->pixelSelector->gradHistFrame = 0;
+  fs->makeNewTraces(fh, 0);
+  fs->qCloudPixel.pop(); fs->qTimeLidarCloud.pop(); fs->pixelSelector->gradHistFrame = 0;
+  int m = 0;
+  for (ImmaturePoint* ip : fh->immaturePoints) { if (m < cap) { float* o = out7 + 7*m; o[0] = ip->u; o[1] = ip->v; o[2] = ip->my_type; o[3] = ip->isFromSensor ? ip->score : 0.f;
+      o[4] = ip->isFromSensor ? ip->idepth_fromSensor : 0.f; o[5] = ip->isFromSensor ? 1.f : 0.f; o[6] = ip->isFromSensor ? (float)(int)ip->type : -1.f; } m++; delete ip; }
+  fh->immaturePoints.clear();
+  if (!commit) { fs->pixelSelector->currentPotential = pot; memcpy(fs->selectionMap, keep.data(), wh*sizeof(float)); }
+  return m;
+}
+
 }  // extern "C"
