@@ -13,6 +13,9 @@
 #define SDV_LAUNCH(kern, grid, block, st, ...)      kern<<<grid, block, 0, st>>>(__VA_ARGS__)
 #define SDV_LAUNCH_SYNC(kern, grid, block, st, ...) kern<<<grid, block, 0, st>>>(__VA_ARGS__)
 #define SDV_DEVCONST static __constant__
+#define SDV_DYN_SMEM(T, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; T* name = reinterpret_cast<T*>(name##_raw_)
+#define SDV_SET_SMEM(kern, bytes) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#define SDV_LAUNCH_SYNC_SMEM(kern, grid, block, smem, st, ...) kern<<<grid, block, smem, st>>>(__VA_ARGS__)
 #endif
 
 namespace sdv { namespace sel {

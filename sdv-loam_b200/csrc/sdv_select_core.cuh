@@ -246,6 +246,42 @@ template <bool LIDAR> __global__ void __launch_bounds__(128) sel_block_kernel(co
   if (n3) atomicAdd(&J.counters[1], n3);
   if (n4) atomicAdd(&J.counters[2], n4);
 }
+// Dense pass (select over all pixels), one WARP per 4x4-cell block: the block's (4 pot)^2 pixels are walked in the reference's order in chunks of 32 — every lane
+// gathers the record of one pixel (threshold, level-0 gradient, the two coarser gradient magnitudes: the scattered loads, now 32 wide), then all lanes replay the
+// three-level state machine over the chunk from shared memory, redundantly and identically (no divergence; lane 0 writes).  The thread-per-block version spent 3.4 ms per
+// call walking 144 pixels per thread with dependent loads (ncu launch list, profiles/r2b_keyframe_launches_summary.txt).
+__global__ void __launch_bounds__(32) sel_block_dense_kernel(const SelJob* __restrict__ jobs, const unsigned char* __restrict__ rp, int w, int h, int dirDist, float dw1) {
+  const SelJob J = jobs[blockIdx.y]; if (!J.active || J.cloud != nullptr) return;
+  const int blk = blockIdx.x; if (blk >= J.nbx4*J.nby4) return;
+  const int bx = blk % J.nbx4, by = blk / J.nbx4, pot = J.pot, pp = pot*pot, npx = 16*pp, lane = threadIdx.x; const float dw2 = dw1*dw1;
+  __shared__ PtRec recs[32];
+  Best B; B.i2 = B.i3 = B.i4 = -1; B.v2 = B.v3 = B.v4 = 0; int n3 = 0, n4 = 0;
+  const float* dir4 = kSelDirs[rp[J.n2start[blk << 4]] & 0xF]; const float* dir3 = dir4; const float* dir2 = dir4;
+  for (int p0 = 0; p0 < npx; p0 += 32) {
+    { const int p = p0 + lane; PtRec r; r.valid = 0; r.out = 0; r.dx = r.dy = r.ag0 = r.ag1 = r.ag2 = r.th0 = 0;
+      if (p < npx) { const int ci = p / pp, k = p - ci*pp, y1 = k / pot, x1 = k - y1*pot;
+        const int cx = bx*4 + ((ci>>2)&1)*2 + (ci&1), cy = by*4 + (ci>>3)*2 + ((ci>>1)&1), xf = cx*pot + x1, yf = cy*pot + y1;
+        if (xf < w && yf < h && !(xf < 4 || xf >= w-5 || yf < 4 || yf > h-4)) r = make_rec(J.img, J.thsSm, w, h, (float)xf, (float)yf, xf + w*yf, xf + w*yf); }
+      recs[lane] = r; }
+    __syncthreads();
+    const int cnt = imin_(32, npx - p0);
+    for (int l = 0; l < cnt; l++) {
+      const int p = p0 + l, ci = p / pp, k = p - ci*pp;
+      if (k == 0) {                                                                      // a cell begins (and with it, possibly, a sub-block)
+        if ((ci & 3) == 0) { B.i3 = -1; B.v3 = 0; dir3 = kSelDirs[rp[J.n2start[(blk << 4) | ci]] & 0xF]; }
+        B.i2 = -1; B.v2 = 0; dir2 = kSelDirs[rp[J.n2start[(blk << 4) | ci]] & 0xF];
+      }
+      if (recs[l].valid) test_rec(recs[l], J.thFactor, dw1, dw2, dirDist, dir2, dir3, dir4, B);
+      if (k == pp-1) {                                                                   // the cell ends
+        if (B.i2 > 0) { if (lane == 0) J.map[B.i2] = 1; B.v3 = 1e10f; }
+        if ((ci & 3) == 3) { if (B.i3 > 0) { if (lane == 0) J.map[B.i3] = 2; B.v4 = 1e10f; n3++; } }
+      }
+    }
+    __syncthreads();
+  }
+  if (B.i4 > 0) { if (lane == 0) J.map[B.i4] = 4; n4++; }
+  if (lane == 0) { if (n3) atomicAdd(&J.counters[1], n3); if (n4) atomicAdd(&J.counters[2], n4); }
+}
 // random sub-selection (PixelSelector2.cpp:405-423 LiDAR: the pattern is indexed by the pixel; :156-172 dense: by the rank among the selected pixels)
 __global__ void __launch_bounds__(128) sel_sub_lidar_kernel(const SelJob* __restrict__ jobs, const unsigned char* __restrict__ rp, int w) {
   const SelJob J = jobs[blockIdx.y]; if (J.charTH < 0 || !J.cloud) return;
@@ -506,6 +542,62 @@ __global__ void __launch_bounds__(64) act_walk_kernel(const DistJob* __restrict_
   }
 }
 
+// The same walk with the distance map in SHARED memory (one byte per level-1 pixel: 105 KB for KITTI, two CTAs per SM): the judge reads and the ring claims no longer
+// make an L2 round trip each (the global-memory version spends 19 us per accepted candidate; ncu: 62 % of the keyframe-rate device time).  A claim is a compare-and-swap
+// on the 32-bit word holding the byte, so every pixel is still taken exactly once per ring.  255 stands for "farther than 39" (1000 in the reference).
+__device__ __forceinline__ int smap_get(const unsigned int* m, int cell) { return (m[cell >> 2] >> ((cell & 3)*8)) & 255; }
+__device__ __forceinline__ bool smap_claim(unsigned int* m, int cell, int k) {
+  unsigned int* wp = m + (cell >> 2); const int sh = (cell & 3)*8;
+  for (;;) { const unsigned int old = *(volatile unsigned int*)wp; if ((int)((old >> sh) & 255u) <= k) return false;
+    const unsigned int nw = (old & ~(255u << sh)) | ((unsigned int)k << sh); if (atomicCAS(wp, old, nw) == old) return true; }
+}
+__global__ void __launch_bounds__(64) act_walk_smem_kernel(const DistJob* __restrict__ jobs) {
+  const DistJob J = jobs[blockIdx.x]; const int w1 = J.w1, h1 = J.h1, n1 = w1*h1, nc = J.cand_begin[J.nCandHosts];
+  SDV_DYN_SMEM(unsigned int, dsm);
+  unsigned int* smap = dsm; int* listA = (int*)(dsm + ((n1 + 3) >> 2)); int* listB = listA + 1024;
+  __shared__ int nA, nB, first;
+  for (int i = threadIdx.x; i < ((n1 + 3) >> 2); i += blockDim.x) {                       // four cells per word
+    unsigned int wv = 0; for (int b = 0; b < 4; b++) { const int c = 4*i + b; const int d = (c < n1) ? J.d[c] : 1000; wv |= (unsigned int)(d > 254 ? 255 : d) << (8*b); }
+    smap[i] = wv; }
+  __syncthreads();
+  for (int c0 = 0; c0 < nc; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x; bool live = c < nc; int uv = -1; float frac = 0, thr = 0;
+    if (live) { uv = J.proj[3*c]; frac = __int_as_float(J.proj[3*c+1]); thr = __int_as_float(J.proj[3*c+2]); if (uv < 0) { J.decision[c] = -1; live = false; } }
+    for (;;) {
+      if (threadIdx.x == 0) first = INT_MAX;
+      __syncthreads();
+      if (live) { const int b = smap_get(smap, (uv & 0xFFFF) + w1*(uv >> 16)); const float dist = (float)(b == 255 ? 1000 : b) + frac; if (dist >= thr) atomicMin(&first, (int)threadIdx.x); }
+      __syncthreads();
+      const int f = first;
+      if (f == INT_MAX) { if (live) J.decision[c] = 0; break; }
+      if (live && (int)threadIdx.x < f) { J.decision[c] = 0; live = false; }
+      if ((int)threadIdx.x == f) { J.decision[c] = 1; live = false; const int cell = (uv & 0xFFFF) + w1*(uv >> 16); const int sh = (cell & 3)*8; smap[cell >> 2] &= ~(255u << sh); listA[0] = uv; nA = 1; }
+      __syncthreads();
+      int* A = listA; int* Bq = listB;
+      for (int k = 1; k < 40; k++) {
+        if (threadIdx.x == 0) nB = 0;
+        __syncthreads();
+        const int na = nA;
+        for (int i = threadIdx.x; i < na; i += blockDim.x) {
+          const int x = A[i] & 0xFFFF, y = A[i] >> 16; if (x == 0 || y == 0 || x == w1-1 || y == h1-1) continue;
+          for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+            if ((dx == 0 && dy == 0) || ((k&1) == 0 && dx != 0 && dy != 0)) continue;
+            if (smap_claim(smap, (x+dx) + (y+dy)*w1, k)) { const int q = atomicAdd(&nB, 1); if (q < 1024) Bq[q] = (x+dx) | ((y+dy) << 16); }
+          }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) nA = imin_(nB, 1024);
+        __syncthreads();
+        int* T = A; A = Bq; Bq = T;
+        if (nA == 0) break;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n1; i += blockDim.x) { const int b = smap_get(smap, i); J.d[i] = (b == 255) ? 1000 : b; }
+}
+
 // ================================================================================================ host engine
 // host-side state of one PixelSelector (one per resident sequence): currentPotential + the persistent monocular selection map
 struct SelectorSlot { int currentPotential = 3; unsigned char* mapD = nullptr; };
@@ -522,6 +614,7 @@ struct SelEngine {
   Scratch scr, scr2; long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool have_ev = false; float last_kernel_ms = 0.f;   // device time of the launches of the last activate() (copies excluded)
   size_t max_scratch = (size_t)1 << 30;
+  size_t max_walk_smem = 200*1024;          // the activation walk keeps its distance map in shared memory up to this size (227 KB per CTA on sm_100)
 
   int init(int w_, int h_, const SelSet& S_, const unsigned char* random_pattern_host, cudaStream_t st_) {
     w = w_; h = h_; S = S_; st = st_;
@@ -586,7 +679,7 @@ struct SelEngine {
       } else {
         SDV_LAUNCH(sel_cell_kernel<false>, dim3((maxSlots + 127)/128, nc), dim3(128), st, d, w, h, dd);
         SDV_LAUNCH_SYNC(sel_n2_kernel, dim3(nc), dim3(256), st, d, rp);
-        SDV_LAUNCH(sel_block_kernel<false>, dim3((maxBlk + 127)/128, nc), dim3(128), st, d, rp, w, h, dd, S.gradDownweightPerLevel);
+        SDV_LAUNCH_SYNC(sel_block_dense_kernel, dim3(maxBlk, nc), dim3(32), st, d, rp, w, h, dd, S.gradDownweightPerLevel);
         launches += 3;
       }
       SEL_CK(cudaGetLastError());
@@ -729,7 +822,12 @@ struct SelEngine {
     if (maxP > 0) SDV_LAUNCH(dm_source_kernel, dim3((maxP + 127)/128, nj), dim3(128), st, dD);
     for (int k = 1; k < 40; k++) SDV_LAUNCH(dm_ring_kernel, dim3(gpx, nj), dim3(256), st, dD, k);
     launches += 41;
-    if (maxC > 0) { SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD); SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD); launches += 2; }
+    if (maxC > 0) {
+      SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD);
+      const size_t walk_smem = (((n1 + 3) >> 2) + 2048)*sizeof(int);                       // byte map + the two frontier lists
+      if (walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0) SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(64), walk_smem, st, dD);
+      else SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD);                   // image too large for the shared-memory map (or attribute refused): global-memory walk
+      launches += 2; }
     if (have_ev) cudaEventRecord(ev1, st);
     SEL_CK(cudaGetLastError());
     std::vector<std::vector<int>> maps(nj);

@@ -88,3 +88,12 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+namespace emu { extern unsigned char* g_dyn;
+#ifdef SDV_EMU_IMPL
+unsigned char* g_dyn = nullptr;
+#endif
+}
+static inline unsigned int atomicCAS(unsigned int* p, unsigned int cmp, unsigned int val) { __atomic_compare_exchange_n(p, &cmp, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST); return cmp; }
+#define SDV_DYN_SMEM(T, name) T* name = reinterpret_cast<T*>(emu::g_dyn)
+#define SDV_SET_SMEM(kern, bytes) 0
+#define SDV_LAUNCH_SYNC_SMEM(kern, grid, block, smem, st, ...) do { emu::g_dyn = (unsigned char*)calloc((smem) + 16, 1); emu::launch(true, grid, block, [&] { kern(__VA_ARGS__); }); free(emu::g_dyn); emu::g_dyn = nullptr; } while (0)
