@@ -743,21 +743,31 @@ struct SelEngine {
   int make_new_traces(std::vector<NewTracesJob>& jobs) {
     const int nj = (int)jobs.size(); if (!nj) return 0;
     const size_t wh = (size_t)w*h, tf = ths_floats();
-    size_t bytes = Scratch::need(nj, sizeof(TraceJob)) + Scratch::need(nj, sizeof(HistJob)) + 1024;
+    size_t bytes = Scratch::need(nj, sizeof(TraceJob)) + Scratch::need(nj, sizeof(HistJob)) + 8192;
     for (auto& j : jobs) bytes += Scratch::need((size_t)3*j.n, 8) + Scratch::need(std::max(j.n, 1), 1) + 2*Scratch::need(tf, 4) + 3*Scratch::need(j.n, 4) + 2*Scratch::need(wh, 1)
                               + Scratch::need(j.cap, 4) + Scratch::need(j.cap, sizeof(NewTrace)) + Scratch::need(j.cap, sizeof(ImmPt)) + Scratch::need(4, 4);
     if (io.reserve(bytes, st)) { err = "scratch"; return -1; }
     io.reset(); std::vector<TraceJob> T(nj); std::vector<HistJob> Hj(nj); std::vector<MapsJobHost> ML, MD;
     TraceJob* dT = io.take<TraceJob>(nj);
+    // per-type arrays of all jobs back to back: one memset / one upload per call instead of one per keyframe
+    float* ths_all = io.take<float>(2*tf*nj); unsigned char* occ_all = io.take<unsigned char>(wh*nj); int* counts_all = io.take<int>((size_t)4*nj);
+    size_t tot_cl = 0; for (auto& j : jobs) tot_cl += (size_t)3*std::max(j.n, 0);
+    double* cl_all = io.take<double>(std::max(tot_cl, (size_t)1)); size_t off = 0;
+    SEL_CK(cudaMemsetAsync(ths_all, 0, 2*tf*nj*sizeof(float), st)); SEL_CK(cudaMemsetAsync(occ_all, 0, wh*nj, st));
+    std::vector<int> c0((size_t)4*nj, 0); for (int j = 0; j < nj; j++) c0[4*j+3] = float_order_bits_host(-1000.0f);
+    SEL_CK(cudaMemcpyAsync(counts_all, c0.data(), c0.size()*sizeof(int), cudaMemcpyHostToDevice, st));
     for (int j = 0; j < nj; j++) { NewTracesJob& N = jobs[j]; TraceJob& J = T[j];
       if (!N.slot->mapD) { SEL_CK(cudaMalloc((void**)&N.slot->mapD, wh)); SEL_CK(cudaMemsetAsync(N.slot->mapD, 0, wh, st)); }   // FullSystem::selectionMap: persistent; zero at birth (the reference: uninitialised)
-      double* cl = io.take<double>((size_t)3*N.n); unsigned char* mapL = io.take<unsigned char>(std::max(N.n, 1)); float* ths = io.take<float>(tf); float* thsSm = io.take<float>(tf);
-      if (N.n) SEL_CK(cudaMemcpyAsync(cl, N.cloud_host, (size_t)3*N.n*sizeof(double), cudaMemcpyHostToDevice, st));
-      SEL_CK(cudaMemsetAsync(ths, 0, tf*sizeof(float), st)); SEL_CK(cudaMemsetAsync(thsSm, 0, tf*sizeof(float), st));
+      double* cl = cl_all + off; unsigned char* mapL = io.take<unsigned char>(std::max(N.n, 1)); float* ths = ths_all + (size_t)2*tf*j; float* thsSm = ths + tf;
+      if (N.n) {                                              // clouds that follow each other in host memory (the C-ABI's layout) travel in ONE copy
+        const bool starts_run = (j == 0) || !(jobs[j-1].n > 0 && jobs[j-1].cloud_host + 3*(size_t)jobs[j-1].n == N.cloud_host);
+        if (starts_run) { int j2 = j; size_t run = (size_t)3*N.n; while (j2 + 1 < nj && jobs[j2+1].n > 0 && jobs[j2].cloud_host + 3*(size_t)jobs[j2].n == jobs[j2+1].cloud_host) { j2++; run += (size_t)3*jobs[j2].n; }
+          SEL_CK(cudaMemcpyAsync(cl, N.cloud_host, run*sizeof(double), cudaMemcpyHostToDevice, st)); }
+      }
+      off += (size_t)3*std::max(N.n, 0);
       J.img = N.img; J.cloud = cl; J.n = N.n; J.mapL = mapL; J.mapD = N.slot->mapD; J.score = io.take<float>(N.n); J.flag = io.take<int>(N.n); J.pos = io.take<int>(N.n);
-      J.occ = io.take<unsigned char>(wh); J.state = io.take<unsigned char>(wh); J.cand = io.take<int>(N.cap); J.ncand_cap = N.cap;
-      J.out = io.take<NewTrace>(N.cap); J.imm = io.take<ImmPt>(N.cap); J.cap = N.cap; J.counts = io.take<int>(4);
-      SEL_CK(cudaMemsetAsync(J.occ, 0, wh, st));
+      J.occ = occ_all + wh*j; J.state = io.take<unsigned char>(wh); J.cand = io.take<int>(N.cap); J.ncand_cap = N.cap;
+      J.out = io.take<NewTrace>(N.cap); J.imm = io.take<ImmPt>(N.cap); J.cap = N.cap; J.counts = counts_all + 4*j;
       Hj[j] = HistJob{N.img.I0, ths, thsSm};
       MapsJobHost M; M.img = N.img; M.thsSm = thsSm; M.cloud_dev = cl; M.n = N.n; M.map = mapL; M.density = N.densityLidar; M.recursionsLeft = 1; M.thFactor = 1; M.currentPotential = &N.slot->currentPotential;
       M.numHaveSub = 0; M.passes = 0; ML.push_back(M);
@@ -769,8 +779,8 @@ struct SelEngine {
       if (jobs[j].addFeaturePoint) { MapsJobHost M = ML[j]; M.map = jobs[j].slot->mapD; M.density = jobs[j].densityDense; MD.push_back(M); dj.push_back(j); } }
     if (make_maps(MD, false)) return -1;                                                  // makeMaps(newFrame, selectionMap, setting_desiredImmatureDensity)   :1293
     for (size_t k = 0; k < dj.size(); k++) { jobs[dj[k]].numPoints[1] = MD[k].numHaveSub; jobs[dj[k]].passes[1] = MD[k].passes; }
-    int maxN = 0; const int init_counts[4] = {0, 0, 0, float_order_bits_host(-1000.0f)};
-    for (int j = 0; j < nj; j++) { T[j].pot = jobs[j].slot->currentPotential; maxN = std::max(maxN, T[j].n); SEL_CK(cudaMemcpyAsync(T[j].counts, init_counts, sizeof(init_counts), cudaMemcpyHostToDevice, st)); }
+    int maxN = 0;
+    for (int j = 0; j < nj; j++) { T[j].pot = jobs[j].slot->currentPotential; maxN = std::max(maxN, T[j].n); }
     SEL_CK(cudaMemcpyAsync(dT, T.data(), nj*sizeof(TraceJob), cudaMemcpyHostToDevice, st));
     if (maxN > 0) SDV_LAUNCH(nt_lidar_score_kernel, dim3((maxN + 127)/128, nj), dim3(128), st, dT, w, h, S);
     SDV_LAUNCH_SYNC(nt_scan_kernel, dim3(nj), dim3(256), st, dT);
@@ -779,7 +789,7 @@ struct SelEngine {
     SDV_LAUNCH_SYNC(nt_dense_resolve_kernel, dim3(nj), dim3(256), st, dT, w, h, S);
     launches += 5; SEL_CK(cudaGetLastError());
     std::vector<int> counts((size_t)nj*4);
-    for (int j = 0; j < nj; j++) SEL_CK(cudaMemcpyAsync(&counts[4*j], T[j].counts, 4*sizeof(int), cudaMemcpyDeviceToHost, st));
+    SEL_CK(cudaMemcpyAsync(counts.data(), counts_all, counts.size()*sizeof(int), cudaMemcpyDeviceToHost, st));
     SEL_CK(cudaStreamSynchronize(st));
     for (int j = 0; j < nj; j++) { NewTracesJob& N = jobs[j]; N.n_out = counts[4*j] + counts[4*j+1];
       if (counts[4*j+2] >= N.cap || N.n_out > N.cap) { err = "make_new_traces: output capacity too small"; return -2; }

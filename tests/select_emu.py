@@ -68,9 +68,10 @@ class Engine:
         nj = len(slots); cl = [np.ascontiguousarray(c, np.float64).reshape(-1, 3) for c in clouds]
         arr = lambda xs: (C.c_void_p * nj)(*xs)
         out = np.zeros((nj, cap), NEW_TRACE_DTYPE); imm = np.zeros((nj, cap), IMM_DTYPE); n_out = np.zeros(nj, np.int32); num = np.zeros((nj, 2), np.int32); passes = np.zeros((nj, 2), np.int32)
+        allc = np.ascontiguousarray(np.concatenate(cl)) if nj else np.zeros((0, 3)); offs = np.concatenate([[0], np.cumsum([len(c) for c in cl])])      # back to back, like the C-ABI hands them over
         n = np.array([len(c) for c in cl], np.int32); dl = np.ascontiguousarray(densL, np.float32); dd = np.ascontiguousarray(densD, np.float32); ad = np.ascontiguousarray(add, np.int32)
         self._ck(lib().emu_make_new_traces(self.p, nj, arr([s.p for s in slots]), arr([F.I0.ctypes.data for F in Fs]), arr([F.L[0].ctypes.data for F in Fs]), arr([F.L[1].ctypes.data for F in Fs]),
-                                           arr([c.ctypes.data for c in cl]), n.ctypes.data, dl.ctypes.data, dd.ctypes.data, ad.ctypes.data, out.ctypes.data, imm.ctypes.data, cap,
+                                           arr([allc.ctypes.data + 24 * int(offs[j]) for j in range(nj)]), n.ctypes.data, dl.ctypes.data, dd.ctypes.data, ad.ctypes.data, out.ctypes.data, imm.ctypes.data, cap,
                                            n_out.ctypes.data, num.ctypes.data, passes.ctypes.data))
         return [out[j, :n_out[j]] for j in range(nj)], [imm[j, :n_out[j]] for j in range(nj)], num, passes
 
