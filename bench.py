@@ -366,7 +366,7 @@ def keyframe_leg(ctx, api, synth, B, reps=3, warm=1, cpu=True):
     out["lidar_front_end"] = {"ms_per_batch_device_kernels": ctx.last_kernel_ms(), "ms_per_batch_wall": 1e3 * t_l, "sweeps_per_s": B / t_l, "pixels_out": int(len(cloud)), "h2d_bytes_per_batch": int(B * sweep.nbytes)}
     def traces():
         for j in range(B): ps.potential(j, 3)
-        return ps.makeNewTracesBatch(list(range(B)), [kf] * B, [cloud] * B, dl, 600.0, 1, cap=1 << 13)
+        return ps.makeNewTracesBatch(list(range(B)), [kf] * B, [cloud] * B, dl, 600.0, 1, cap=1 << 11)
     (tr, num), t_t = timed(traces)
     out["make_new_traces"] = {"ms_per_batch_device_incl_copies": ctx.last_kernel_ms(), "ms_per_batch_wall": 1e3 * t_t, "keyframes_per_s": B / t_t, "points_per_keyframe": int(len(tr[0][0])), "lidar_monocular": [int(num[0][0]), int(num[0][1])]}
     pts, hT, hab = synth.make_map(seq8, list(range(7)), n_per_frame=300, seed=2)

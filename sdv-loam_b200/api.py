@@ -595,11 +595,11 @@ class PixelSelector:
         """FullSystem::makeNewTraces for one new keyframe per slot -> per job (sdv_new_trace records, sdv_immature_pt records), numPoints (n,2)"""
         n = len(slots); cl = [np.ascontiguousarray(c, np.float64).reshape(-1, 3) for c in clouds]; cb = np.concatenate([[0], np.cumsum([len(c) for c in cl])]).astype(np.int32)
         allc = np.ascontiguousarray(np.concatenate(cl) if cb[-1] else np.zeros((1, 3)))
-        out = np.zeros((n, cap), NEW_TRACE_DTYPE); imm = np.zeros((n, cap), IMMATURE_PT_DTYPE); n_out = np.zeros(n, np.int32); num = np.zeros(2 * n, np.int32)
+        out = np.empty((n, cap), NEW_TRACE_DTYPE); imm = np.empty((n, cap), IMMATURE_PT_DTYPE); n_out = np.zeros(n, np.int32); num = np.zeros(2 * n, np.int32)      # only the first n_out[j] rows of a job are written / returned
         self.ctx._ck(LIB.sdv_make_new_traces_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(frame_ids, np.uint64), cb, allc.ctypes.data,
                                                   np.ascontiguousarray(np.broadcast_to(density_lidar, n), np.float32), np.ascontiguousarray(np.broadcast_to(density_dense, n), np.float32),
                                                   np.ascontiguousarray(np.broadcast_to(add_feature_point, n), np.int32), cap, out.ctypes.data, imm.ctypes.data, n_out, num))
-        return [(out[j, :n_out[j]], imm[j, :n_out[j]]) for j in range(n)], num.reshape(n, 2)
+        return [(out[j, :n_out[j]].copy(), imm[j, :n_out[j]].copy()) for j in range(n)], num.reshape(n, 2)
 
 
 def activateSelectBatch(ctx: Context, seqs, want_maps=False):

@@ -199,7 +199,7 @@ template <bool LIDAR> __global__ void __launch_bounds__(128) sel_cell_kernel(con
 // a chunk holding such a cell is walked by one thread: d = randomPattern[n2] & 15, n2 += (mask >> d) & 1
 __global__ void __launch_bounds__(256) sel_n2_kernel(const SelJob* __restrict__ jobs, const unsigned char* __restrict__ rp) {
   const SelJob J = jobs[blockIdx.x]; if (!J.active) return;
-  __shared__ int sm[512]; __shared__ int base;
+  __shared__ int sm[512]; __shared__ int base; __shared__ int smm[2048], smn[2048];      // masks / resolved counts of one chunk for the sequential walk
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
   const int chunk = blockDim.x*8;                                                        // 8 consecutive cells per thread
@@ -211,10 +211,14 @@ __global__ void __launch_bounds__(256) sel_n2_kernel(const SelJob* __restrict__ 
       for (int k = 0; k < 8; k++) { if (s+k < J.nslots) J.n2start[s+k] = ex; ex += (m[k] == 0xFFFF); }
       __syncthreads();
       if (threadIdx.x == 0) base += total;
-    } else if (threadIdx.x == 0) {
-      int b = base; const int e = imin_(s0 + chunk, J.nslots);
-      for (int t = s0; t < e; t++) { const int mm = J.mask[t]; J.n2start[t] = b; if (mm) b += (mm >> (rp[b] & 0xF)) & 1; }
-      base = b;
+    } else {                                                                             // a direction-dependent cell in this chunk: one thread walks the chunk from shared memory
+      for (int k = 0; k < 8; k++) smm[threadIdx.x*8 + k] = m[k];
+      __syncthreads();
+      if (threadIdx.x == 0) { int b = base; const int e = imin_(chunk, J.nslots - s0);
+        for (int t = 0; t < e; t++) { const int mm = smm[t]; smn[t] = b; if (mm) b += (mm == 0xFFFF) ? 1 : ((mm >> (rp[b] & 0xF)) & 1); }
+        base = b; }
+      __syncthreads();
+      for (int k = 0; k < 8; k++) if (s+k < J.nslots) J.n2start[s+k] = smn[threadIdx.x*8 + k];
     }
     __syncthreads();
   }
@@ -394,13 +398,11 @@ __global__ void __launch_bounds__(128) nt_lidar_emit_kernel(const TraceJob* __re
 }
 // monocular loop (:1337-1353): candidates = selected pixels of the persistent map inside the pattern padding, in raster order.  A candidate is dropped when its
 // pattern is not finite or the occupancy mask is set at its pixel — by a LiDAR point, or by a monocular candidate accepted EARLIER in raster order (greedy).
-__global__ void __launch_bounds__(128) nt_dense_state_kernel(const TraceJob* __restrict__ jobs, int w, int h, SelSet S) {   // thread per image row: state + candidate list of the row
-  const TraceJob J = jobs[blockIdx.y]; const int y = blockIdx.x*blockDim.x + threadIdx.x; if (y >= h) return;
-  for (int x = 0; x < w; x++) {
-    const int i = x + y*w; unsigned char st = 0;
-    if (y >= 3 && y < h-4 && x >= 3 && x < w-4 && J.mapD[i] != 0) { ImmPt p; st = (imm_construct(J.img.I0, w, x, y, S, p) && J.occ[i] == 0) ? 1 : 3; }
-    J.state[i] = st;
-  }
+__global__ void __launch_bounds__(128) nt_dense_state_kernel(const TraceJob* __restrict__ jobs, int w, int h, SelSet S) {   // thread per pixel: state of the monocular candidates
+  const TraceJob J = jobs[blockIdx.y]; const int i = blockIdx.x*blockDim.x + threadIdx.x; if (i >= w*h) return;
+  const int y = i / w, x = i - y*w; unsigned char st = 0;
+  if (y >= 3 && y < h-4 && x >= 3 && x < w-4 && J.mapD[i] != 0) { ImmPt p; st = (imm_construct(J.img.I0, w, x, y, S, p) && J.occ[i] == 0) ? 1 : 3; }
+  J.state[i] = st;
 }
 __global__ void __launch_bounds__(256) nt_dense_resolve_kernel(const TraceJob* __restrict__ jobs, int w, int h, SelSet S) {   // CTA per job
   const TraceJob J = jobs[blockIdx.x];
@@ -785,7 +787,7 @@ struct SelEngine {
     if (maxN > 0) SDV_LAUNCH(nt_lidar_score_kernel, dim3((maxN + 127)/128, nj), dim3(128), st, dT, w, h, S);
     SDV_LAUNCH_SYNC(nt_scan_kernel, dim3(nj), dim3(256), st, dT);
     if (maxN > 0) SDV_LAUNCH(nt_lidar_emit_kernel, dim3((maxN + 127)/128, nj), dim3(128), st, dT, w, h, S);
-    SDV_LAUNCH(nt_dense_state_kernel, dim3((h + 127)/128, nj), dim3(128), st, dT, w, h, S);
+    SDV_LAUNCH(nt_dense_state_kernel, dim3((w*h + 127)/128, nj), dim3(128), st, dT, w, h, S);
     SDV_LAUNCH_SYNC(nt_dense_resolve_kernel, dim3(nj), dim3(256), st, dT, w, h, S);
     launches += 5; SEL_CK(cudaGetLastError());
     std::vector<int> counts((size_t)nj*4);

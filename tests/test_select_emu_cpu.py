@@ -147,3 +147,12 @@ def test_lidar_front_end_128_beams():
     args = dict(n_scan=128, horizon=1800, ang_res_x=0.2, ang_res_y=0.427 / 2, ang_bottom=24.9, groundScanInd=100)
     o = orc.LidarFrontEnd(**args).handle(sw, synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [10000, -1, 10000, -1]); g = se.LidarEngine(**args).handle([sw], synth.RLC, synth.TLC, SMALL_K, SMALL_WH, [[10000, -1, 10000, -1]])[0]
     assert np.array_equal(o["cloud_px"], g["cloud_px"]) and len(o["cloud_px"]) > 6000 and np.array_equal(o["lrud"], g["lrud"]) and o["n_segmented"] == g["n_segmented"] and o["numGround"] == g["numGround"]
+
+
+def test_make_new_traces_without_lidar_pixels(scene):
+    """a keyframe whose sweep left no pixel in the image (empty cloud): the LiDAR selection recurses on zero picks, the monocular selection still runs"""
+    seq, rp, of, F = scene; E = se.Engine(W, H, rp); slot = se.Slot(3); osel = orc.Selector(W, H, rp); omap = np.zeros((H, W), np.float32)
+    empty = np.zeros((0, 3)); outs, imms, num, passes = E.makeNewTraces([slot], [F[0]], [empty], [300.0], [600.0], [1])
+    T, onum, opass = osel.makeNewTraces(of[0], empty, 300.0, 600.0, 1, omap)
+    assert T.tobytes() == outs[0].tobytes() and np.array_equal(onum, num[0]) and osel.currentPotential == slot.currentPotential and len(T) > 100 and (T["isFromSensor"] == 0).all()
+    assert np.array_equal(omap.astype(np.uint8), slot.map(W, H))
