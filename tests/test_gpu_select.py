@@ -125,3 +125,17 @@ def test_lidar_front_end_batch():
     To, _, _ = osel.makeNewTraces(of[0], res["cloud_px"], dl, 600.0, res["addFeaturePoint"], np.zeros((h, w), np.float32))
     assert To.tobytes() == T.tobytes() and len(T) > 100
     ctx.close()
+
+
+def test_error_behaviour():
+    """the reference's asserts become error codes: calls before init, bad slots, a slot twice in one batch, an output capacity that is too small"""
+    api, seq, of, ctx, rp = _scene(SMALL_WH, SMALL_K, 3000, nfr=1); cloud = seq.clouds[0]
+    with pytest.raises(api.SdvError): api.activateSelectBatch(ctx, [dict(pt_begin=[0], KRKi=np.zeros((0, 9)), Kt=np.zeros((0, 3)), uvid=np.zeros((0, 3)))])        # no selector yet
+    with pytest.raises(api.SdvError): api.LidarFrontEnd(ctx, n_scan=200)                                                                                          # more rings than the row mask holds
+    ps = api.PixelSelector(ctx, 2, rp)
+    with pytest.raises(api.SdvError): ps.potential(5)
+    with pytest.raises(api.SdvError): ps.makeNewTracesBatch([0, 0], [10, 10], [cloud, cloud], 300.0, 600.0, 1)                                                  # one selector cannot serve two keyframes at once
+    with pytest.raises(api.SdvError): ps.makeNewTracesBatch([0], [999], [cloud], 300.0, 600.0, 1)                                                               # unknown frame
+    with pytest.raises(api.SdvError): ps.makeNewTracesBatch([1], [10], [cloud], 300.0, 600.0, 1, cap=16)                                                        # SDV_ERR_CAPACITY
+    res, num = ps.makeNewTracesBatch([1], [10], [cloud], 300.0, 600.0, 1); assert len(res[0][0]) > 100                                                           # the context is still usable
+    ctx.close()
