@@ -832,6 +832,13 @@ def main():
         line["refine"] = refine
     if keyframe is not None:
         line["keyframe_rate"] = keyframe
+        if "error" not in keyframe and ba is not None and refine is not None:
+            # every stage of the per-frame path together, each measured separately on this GPU through the C-ABI: tracking + refinement every frame, the LiDAR front-end every
+            # frame (one sweep per image, main.cpp:785), makeNewTraces + activation walk + FullSystem::optimize every kf_every-th frame
+            kfe = args.kf_every; per_frame = 1.0 / line["value"] + 1.0 / refine["frames_per_s_device"] + 1.0 / (kfe * ba["windows_per_s"]) \
+                + (1.0 / keyframe["lidar_front_end"]["sweeps_per_s"] + (1.0 / keyframe["make_new_traces"]["keyframes_per_s"] + 1.0 / keyframe["activate_select"]["sequences_per_s"]) / kfe) / world
+            line["combined"]["frames_per_s_all_stages"] = 1.0 / per_frame
+            line["combined"]["all_stages_note"] = "tracking + refinement + LiDAR front-end every frame; makeNewTraces + activation walk + optimize every kf_every-th frame; legs measured separately (keyframe-rate legs: wall time of the Python/ctypes call incl. host buffers)"
     if not args.no_cpu_baseline:
         arm = make_cpu_arm(seq, synth, p4, 1); arm.run(3)
         nf, tw = arm.run(10 ** 9, budget_s=12.0)
@@ -842,6 +849,10 @@ def main():
             line["combined"]["cpu_frames_per_s_track_plus_ba_1core"] = 1.0 / (tw / nf + cms * 1e-3 / args.kf_every)
             if refine is not None:
                 line["combined"]["cpu_frames_per_s_track_refine_ba_1core"] = 1.0 / (tw / nf + refine["cpu_ms_per_frame_1core"] * 1e-3 + cms * 1e-3 / args.kf_every)
+                if keyframe is not None and "cpu_ms_1core" in keyframe:
+                    kc = keyframe["cpu_ms_1core"]
+                    line["combined"]["cpu_frames_per_s_all_stages_1core"] = 1.0 / (tw / nf + refine["cpu_ms_per_frame_1core"] * 1e-3 + kc["lidar_front_end"] * 1e-3
+                                                                                   + (cms + kc["make_new_traces"] + kc["activate_select"]) * 1e-3 / args.kf_every)
         line["cpu_baseline"] = {"value": nf / tw, "unit": "frames/s", "cores": 1, "kind": arm.kind,
                                 "sample": "%d frames (undistort + makeImages + trackNewestCoarse, same inputs/inits distribution) in %.1f s on 1 host core; %s" % (nf, tw, cpu_note(arm))}
     emit(line)

@@ -40,9 +40,9 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 #define __ldcg(p) (*(p))
 
 namespace emu {
-extern thread_local dim3 t_threadIdx, t_blockIdx; extern dim3 g_blockDim, g_gridDim; extern pthread_barrier_t g_bar; extern int g_or_flag[2];
+extern thread_local dim3 t_threadIdx, t_blockIdx; extern dim3 g_blockDim, g_gridDim; extern pthread_barrier_t g_bar, g_bar_warp0; extern int g_or_flag[2];
 #ifdef SDV_EMU_IMPL
-thread_local dim3 t_threadIdx, t_blockIdx; dim3 g_blockDim, g_gridDim; pthread_barrier_t g_bar; int g_or_flag[2];
+thread_local dim3 t_threadIdx, t_blockIdx; dim3 g_blockDim, g_gridDim; pthread_barrier_t g_bar, g_bar_warp0; int g_or_flag[2];
 #endif
 static inline void launch(bool barriers, dim3 grid, dim3 block, const std::function<void()>& body) {
   g_blockDim = block; g_gridDim = grid;
@@ -51,13 +51,13 @@ static inline void launch(bool barriers, dim3 grid, dim3 block, const std::funct
       for (unsigned tx = 0; tx < block.x; tx++) { t_threadIdx = dim3(tx); body(); } }
     return;
   }
-  pthread_barrier_init(&g_bar, nullptr, block.x); g_or_flag[0] = g_or_flag[1] = 0;
+  pthread_barrier_init(&g_bar, nullptr, block.x); pthread_barrier_init(&g_bar_warp0, nullptr, block.x < 32 ? block.x : 32); g_or_flag[0] = g_or_flag[1] = 0;
   std::vector<std::thread> th;
   for (unsigned tx = 0; tx < block.x; tx++) th.emplace_back([&, tx] {
     t_threadIdx = dim3(tx);
     for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) { t_blockIdx = dim3(bx, by); body(); pthread_barrier_wait(&g_bar); } });
   for (auto& t : th) t.join();
-  pthread_barrier_destroy(&g_bar);
+  pthread_barrier_destroy(&g_bar); pthread_barrier_destroy(&g_bar_warp0);
 }
 }
 #define threadIdx emu::t_threadIdx
@@ -65,6 +65,8 @@ static inline void launch(bool barriers, dim3 grid, dim3 block, const std::funct
 #define blockDim emu::g_blockDim
 #define gridDim emu::g_gridDim
 static inline void __syncthreads() { pthread_barrier_wait(&emu::g_bar); }
+// only warp 0 of a block may call it in this emulation (the kernels that use it keep their warp-synchronous part in warp 0)
+static inline void __syncwarp() { if (emu::t_threadIdx.x < 32) pthread_barrier_wait(&emu::g_bar_warp0); }
 static inline int __syncthreads_or(int p) {          // two flags used alternately would race with a fast thread's next call; three barriers keep it simple
   if (p) __atomic_store_n(&emu::g_or_flag[0], 1, __ATOMIC_SEQ_CST);
   pthread_barrier_wait(&emu::g_bar); int r = __atomic_load_n(&emu::g_or_flag[0], __ATOMIC_SEQ_CST); pthread_barrier_wait(&emu::g_bar);
