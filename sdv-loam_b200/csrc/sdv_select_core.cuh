@@ -553,9 +553,9 @@ __device__ __forceinline__ bool smap_claim(unsigned int* m, int cell, int k) {
   for (;;) { const unsigned int old = *(volatile unsigned int*)wp; if ((int)((old >> sh) & 255u) <= k) return false;
     const unsigned int nw = (old & ~(255u << sh)) | ((unsigned int)k << sh); if (atomicCAS(wp, old, nw) == old) return true; }
 }
-// Launched with 128 threads: all of them load / store the map, ONE warp walks (the first capture of the 64-thread version showed 44 % of the issue cycles waiting at
-// block barriers for a second warp that rarely has a frontier pixel to work on: frontiers hold a few dozen pixels).  Inside the walk only __syncwarp() orders the lanes.
-__global__ void __launch_bounds__(128) act_walk_smem_kernel(const DistJob* __restrict__ jobs) {
+// (A one-warp walk with 128 threads for the map load / store — tried because ncu shows 44 % of the issue cycles of this kernel at the block barrier — is SLOWER: 12.5 ms
+// against 9.1 ms per 148 sequences; the second warp does shorten the frontier and judge loops.  Measured on the B200, profiles/README.md.)
+__global__ void __launch_bounds__(64) act_walk_smem_kernel(const DistJob* __restrict__ jobs) {
   const DistJob J = jobs[blockIdx.x]; const int w1 = J.w1, h1 = J.h1, n1 = w1*h1, nc = J.cand_begin[J.nCandHosts];
   SDV_DYN_SMEM(unsigned int, dsm);
   unsigned int* smap = dsm; int* listA = (int*)(dsm + ((n1 + 3) >> 2)); int* listB = listA + 1024;
@@ -564,45 +564,41 @@ __global__ void __launch_bounds__(128) act_walk_smem_kernel(const DistJob* __res
     unsigned int wv = 0; for (int b = 0; b < 4; b++) { const int c = 4*i + b; const int d = (c < n1) ? J.d[c] : 1000; wv |= (unsigned int)(d > 254 ? 255 : d) << (8*b); }
     smap[i] = wv; }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int c0 = 0; c0 < nc; c0 += 32) {
-      const int c = c0 + lane; bool live = c < nc; int uv = -1; float frac = 0, thr = 0;
-      if (live) { uv = J.proj[3*c]; frac = __int_as_float(J.proj[3*c+1]); thr = __int_as_float(J.proj[3*c+2]); if (uv < 0) { J.decision[c] = -1; live = false; } }
-      for (;;) {
-        if (lane == 0) first = INT_MAX;
-        __syncwarp();
-        if (live) { const int b = smap_get(smap, (uv & 0xFFFF) + w1*(uv >> 16)); const float dist = (float)(b == 255 ? 1000 : b) + frac; if (dist >= thr) atomicMin(&first, lane); }
-        __syncwarp();
-        const int f = first;
-        __syncwarp();                                                                      // everyone has read `first` before lane 0 resets it in the next round
-        if (f == INT_MAX) { if (live) J.decision[c] = 0; break; }
-        if (live && lane < f) { J.decision[c] = 0; live = false; }
-        if (lane == f) { J.decision[c] = 1; live = false; const int cell = (uv & 0xFFFF) + w1*(uv >> 16); const int sh = (cell & 3)*8; smap[cell >> 2] &= ~(255u << sh); listA[0] = uv; nA = 1; }
-        __syncwarp();
-        int* A = listA; int* Bq = listB;
-        for (int k = 1; k < 40; k++) {
-          if (lane == 0) nB = 0;
-          __syncwarp();
-          const int na = nA;
-          for (int i = lane; i < na; i += 32) {
-            const int x = A[i] & 0xFFFF, y = A[i] >> 16; if (x == 0 || y == 0 || x == w1-1 || y == h1-1) continue;
-            for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
-              if ((dx == 0 && dy == 0) || ((k&1) == 0 && dx != 0 && dy != 0)) continue;
-              if (smap_claim(smap, (x+dx) + (y+dy)*w1, k)) { const int q = atomicAdd(&nB, 1); if (q < 1024) Bq[q] = (x+dx) | ((y+dy) << 16); }
-            }
+  for (int c0 = 0; c0 < nc; c0 += blockDim.x) {
+    const int c = c0 + threadIdx.x; bool live = c < nc; int uv = -1; float frac = 0, thr = 0;
+    if (live) { uv = J.proj[3*c]; frac = __int_as_float(J.proj[3*c+1]); thr = __int_as_float(J.proj[3*c+2]); if (uv < 0) { J.decision[c] = -1; live = false; } }
+    for (;;) {
+      if (threadIdx.x == 0) first = INT_MAX;
+      __syncthreads();
+      if (live) { const int b = smap_get(smap, (uv & 0xFFFF) + w1*(uv >> 16)); const float dist = (float)(b == 255 ? 1000 : b) + frac; if (dist >= thr) atomicMin(&first, (int)threadIdx.x); }
+      __syncthreads();
+      const int f = first;
+      if (f == INT_MAX) { if (live) J.decision[c] = 0; break; }
+      if (live && (int)threadIdx.x < f) { J.decision[c] = 0; live = false; }
+      if ((int)threadIdx.x == f) { J.decision[c] = 1; live = false; const int cell = (uv & 0xFFFF) + w1*(uv >> 16); const int sh = (cell & 3)*8; smap[cell >> 2] &= ~(255u << sh); listA[0] = uv; nA = 1; }
+      __syncthreads();
+      int* A = listA; int* Bq = listB;
+      for (int k = 1; k < 40; k++) {
+        if (threadIdx.x == 0) nB = 0;
+        __syncthreads();
+        const int na = nA;
+        for (int i = threadIdx.x; i < na; i += blockDim.x) {
+          const int x = A[i] & 0xFFFF, y = A[i] >> 16; if (x == 0 || y == 0 || x == w1-1 || y == h1-1) continue;
+          for (int dy = -1; dy <= 1; dy++) for (int dx = -1; dx <= 1; dx++) {
+            if ((dx == 0 && dy == 0) || ((k&1) == 0 && dx != 0 && dy != 0)) continue;
+            if (smap_claim(smap, (x+dx) + (y+dy)*w1, k)) { const int q = atomicAdd(&nB, 1); if (q < 1024) Bq[q] = (x+dx) | ((y+dy) << 16); }
           }
-          __syncwarp();
-          if (lane == 0) nA = imin_(nB, 1024);
-          __syncwarp();
-          int* T = A; A = Bq; Bq = T;
-          if (nA == 0) break;
         }
-        __syncwarp();
+        __syncthreads();
+        if (threadIdx.x == 0) nA = imin_(nB, 1024);
+        __syncthreads();
+        int* T = A; A = Bq; Bq = T;
+        if (nA == 0) break;
       }
+      __syncthreads();
     }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < n1; i += blockDim.x) { const int b = smap_get(smap, i); J.d[i] = (b == 255) ? 1000 : b; }
 }
 
@@ -843,7 +839,7 @@ struct SelEngine {
     if (maxC > 0) {
       SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD);
       const size_t walk_smem = (((n1 + 3) >> 2) + 2048)*sizeof(int);                       // byte map + the two frontier lists
-      if (walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0) SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(128), walk_smem, st, dD);
+      if (walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0) SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(64), walk_smem, st, dD);
       else SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD);                   // image too large for the shared-memory map (or attribute refused): global-memory walk
       launches += 2; }
     if (have_ev) cudaEventRecord(ev1, st);

@@ -148,3 +148,30 @@ def test_reproject_and_refine(size):
     so = orc.struct_pose(w, h, np.array(K, np.float32), hT, p6, noisy)
     assert int(r["n_matches"][0]) == len(idx) and (int(r["iterations"][0]), int(r["accepts"][0])) == (so["iterations"], so["accepts"]) and np.abs(r["T"][0] - so["T"]).max() < 1e-6
     ctx.close()
+
+
+@pytest.mark.parametrize("size", ["kitti360", "stress"])
+def test_candidate_management_at_size(size):
+    """FullSystem::makeNewTraces (PixelSelector incl. both recursion directions, Shi-Tomasi typing, monocular mask) and makeDistanceMap + the activation walk at the
+    KITTI-360 and S-STRESS image sizes (the 960x600 level-1 distance map of S-STRESS does not fit in shared memory: the global-memory walk runs there)"""
+    api, synth = _mods(); S, seq = _seq(size); w, h = S["wh"]; L = S["levels"]
+    ctx = api.Context(S["K"], w, h, max_frames=4); ctx.makeImages(0, seq.images[0]); ctx.makeImages(1, seq.images[1]); of = [orc.Frame(seq.images[k], L) for k in range(2)]
+    rp = api.random_pattern(w, h); ps = api.PixelSelector(ctx, 2, rp); osel = [orc.Selector(w, h, rp) for _ in range(2)]; omap = [np.zeros((h, w), np.float32) for _ in range(2)]
+    dens = [S["n_per_frame"] * 2.0, 150.0]; ps.potential(0, 3); ps.potential(1, 6); osel[1].currentPotential = 6
+    clouds = [seq.clouds[0], seq.clouds[1]]; lr = [[int(c[:, 0].min()), int(c[:, 0].max()), int(c[:, 1].min()), int(c[:, 1].max())] for c in clouds]
+    dl = [api.lidar_density(lr[j], S["wh"], dens[j]) for j in range(2)]
+    res, num = ps.makeNewTracesBatch([0, 1], [0, 1], clouds, dl, dens, [1, 1], cap=1 << 16)
+    for j in range(2):
+        T, onum, _ = osel[j].makeNewTraces(of[j], clouds[j], dl[j], dens[j], 1, omap[j])
+        assert T.tobytes() == res[j][0].tobytes() and np.array_equal(onum, num[j]) and osel[j].currentPotential == ps.potential(j) and len(T) > 100, (size, j, len(T), len(res[j][0]))
+        assert np.array_equal(omap[j].astype(np.uint8), ps.selectionMap(j))
+    # distance map + walk: sources = the immature points just created on keyframe 0 (as if activated), candidates = those of keyframe 1, identity geometry at level-1 intrinsics
+    K = S["K"]; K0 = np.array([[K[0], 0, K[2]], [0, K[1], K[3]], [0, 0, 1]], np.float32); K1 = np.array([[K[0] / 2, 0, (K[2] + 0.5) / 2 - 0.5], [0, K[1] / 2, (K[3] + 0.5) / 2 - 0.5], [0, 0, 1]], np.float32)
+    KRKi = (K1 @ np.linalg.inv(K0.astype(np.float64)).astype(np.float32)).astype(np.float32)[None]; Kt = np.zeros((1, 3), np.float32)
+    T0, T1 = res[0][0], res[1][0]; uvid = np.stack([T0["u"], T0["v"], np.full(len(T0), 0.1, np.float32)], 1).astype(np.float32)
+    cand = np.stack([T1["u"], T1["v"], np.full(len(T1), 0.1, np.float32), T1["my_type"]], 1).astype(np.float32)
+    q = dict(pt_begin=[0, len(uvid)], KRKi=KRKi, Kt=Kt, uvid=uvid, cand_begin=[0, len(cand)], cKRKi=KRKi, cKt=Kt, cand4=cand, minActDist=1.5)
+    dec, maps = api.activateSelectBatch(ctx, [q, q], want_maps=True)
+    od = orc.DistMap(w >> 1, h >> 1); od.make(q["pt_begin"], KRKi, Kt, uvid); do = od.activateSelect(q["cand_begin"], KRKi, Kt, cand, 1.5)
+    assert np.array_equal(dec[0], do) and np.array_equal(dec[1], do) and np.array_equal(maps[0], od.get()) and (do == 1).sum() > 10
+    ctx.close()
