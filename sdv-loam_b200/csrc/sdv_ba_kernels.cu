@@ -534,7 +534,7 @@ template <typename MF> __device__ __forceinline__ double triple66(const double* 
   return s;
 }
 
-constexpr int kSolveThreads = 1024;
+constexpr int kSolveThreads = 512;
 #ifdef SDV_BA_PROFILE
 __device__ long long g_ba_prof[16];
 #define BA_PROF_T(var) const long long var = clock64()
