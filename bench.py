@@ -364,9 +364,10 @@ def keyframe_leg(ctx, api, synth, B, reps=3, warm=1, cpu=True):
     res, t_l = timed(lambda: fe.handle_packed(pinned, sb, synth.RLC, synth.TLC, K, lr0, cap=1 << 14))      # B raw sweeps back to back in pinned host memory, as a driver would hand them over
     cloud = res[0]["cloud_px"]; dl = api.lidar_density(res[0]["lrud"], synth.KITTI_WH, 600.0)
     out["lidar_front_end"] = {"ms_per_batch_device_kernels": ctx.last_kernel_ms(), "ms_per_batch_wall": 1e3 * t_l, "sweeps_per_s": B / t_l, "pixels_out": int(len(cloud)), "h2d_bytes_per_batch": int(B * sweep.nbytes)}
+    cloud_all = np.ascontiguousarray(np.tile(cloud, (B, 1))); cbeg = (np.arange(B + 1) * len(cloud)).astype(np.int32)    # the B keyframes' pixel rows back to back
     def traces():
         for j in range(B): ps.potential(j, 3)
-        return ps.makeNewTracesBatch(list(range(B)), [kf] * B, [cloud] * B, dl, 600.0, 1, cap=1 << 11)
+        return ps.makeNewTracesPacked(list(range(B)), [kf] * B, cloud_all, cbeg, dl, 600.0, 1, cap=1 << 11)
     (tr, num), t_t = timed(traces)
     out["make_new_traces"] = {"ms_per_batch_device_incl_copies": ctx.last_kernel_ms(), "ms_per_batch_wall": 1e3 * t_t, "keyframes_per_s": B / t_t, "points_per_keyframe": int(len(tr[0][0])), "lidar_monocular": [int(num[0][0]), int(num[0][1])]}
     pts, hT, hab = synth.make_map(seq8, list(range(7)), n_per_frame=300, seed=2)
@@ -380,7 +381,8 @@ def keyframe_leg(ctx, api, synth, B, reps=3, warm=1, cpu=True):
         c = seq8.clouds[k]; pick = rng.choice(len(c), 400, replace=False)
         cand.append(np.stack([np.floor(c[pick, 0]), np.floor(c[pick, 1]), 1.0 / c[pick, 2], rng.choice([1.0, 2.0, 4.0], 400)], 1)); cb.append(cb[-1] + 400)
     q = dict(pt_begin=pb, KRKi=np.stack(KRKi), Kt=np.stack(Kt), uvid=np.concatenate(uvid).astype(np.float32), cand_begin=cb, cKRKi=np.stack(KRKi), cKt=np.stack(Kt), cand4=np.concatenate(cand).astype(np.float32), minActDist=2.0)
-    dec, t_a = timed(lambda: api.activateSelectBatch(ctx, [q] * B))
+    packed = api.packActivation([q] * B)
+    dec, t_a = timed(lambda: api.activateSelectPacked(ctx, packed))
     out["activate_select"] = {"ms_per_batch_device_kernels": ctx.last_kernel_ms(), "ms_per_batch_wall": 1e3 * t_a, "sequences_per_s": B / t_a, "candidates": int(cb[-1]), "accepted": int((dec[0] == 1).sum()), "map_points": int(pb[-1])}
     if cpu:
         orc = se3_helpers(); L = 4; fo = orc.Frame(seq8.images[7], L); fe_o = orc.LidarFrontEnd(); sel_o = orc.Selector(w, h, rp); dm = orc.DistMap(w >> 1, h >> 1)

@@ -593,33 +593,52 @@ class PixelSelector:
 
     def makeNewTracesBatch(self, slots, frame_ids, clouds, density_lidar, density_dense, add_feature_point, cap=1 << 14):
         """FullSystem::makeNewTraces for one new keyframe per slot -> per job (sdv_new_trace records, sdv_immature_pt records), numPoints (n,2)"""
-        n = len(slots); cl = [np.ascontiguousarray(c, np.float64).reshape(-1, 3) for c in clouds]; cb = np.concatenate([[0], np.cumsum([len(c) for c in cl])]).astype(np.int32)
+        cl = [np.ascontiguousarray(c, np.float64).reshape(-1, 3) for c in clouds]; cb = np.concatenate([[0], np.cumsum([len(c) for c in cl])]).astype(np.int32)
         allc = np.ascontiguousarray(np.concatenate(cl) if cb[-1] else np.zeros((1, 3)))
-        out = np.empty((n, cap), NEW_TRACE_DTYPE); imm = np.empty((n, cap), IMMATURE_PT_DTYPE); n_out = np.zeros(n, np.int32); num = np.zeros(2 * n, np.int32)      # only the first n_out[j] rows of a job are written / returned
-        self.ctx._ck(LIB.sdv_make_new_traces_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(frame_ids, np.uint64), cb, allc.ctypes.data,
+        res, num = self.makeNewTracesPacked(slots, frame_ids, allc, cb, density_lidar, density_dense, add_feature_point, cap)
+        return [(t.copy(), i.copy()) for t, i in res], num
+
+    def makeNewTracesPacked(self, slots, frame_ids, cloud_all, cloud_begin, density_lidar, density_dense, add_feature_point, cap=1 << 14):
+        """the same with the pixel rows of all jobs already back to back in ONE float64 (N,3) host array and their row offsets; the returned record arrays are VIEWS into
+        buffers this object reuses (valid until the next call) — nothing is copied or zeroed on the host"""
+        n = len(slots); cb = np.ascontiguousarray(cloud_begin, np.int32); assert cloud_all.dtype == np.float64 and cloud_all.flags.c_contiguous and len(cb) == n + 1
+        if getattr(self, "_nt_buf", None) is None or self._nt_buf[0].shape != (n, cap):
+            self._nt_buf = (np.empty((n, cap), NEW_TRACE_DTYPE), np.empty((n, cap), IMMATURE_PT_DTYPE))
+        out, imm = self._nt_buf; n_out = np.zeros(n, np.int32); num = np.zeros(2 * n, np.int32)
+        self.ctx._ck(LIB.sdv_make_new_traces_batch(self.ctx.p, n, np.ascontiguousarray(slots, np.int32), np.ascontiguousarray(frame_ids, np.uint64), cb, cloud_all.ctypes.data,
                                                   np.ascontiguousarray(np.broadcast_to(density_lidar, n), np.float32), np.ascontiguousarray(np.broadcast_to(density_dense, n), np.float32),
                                                   np.ascontiguousarray(np.broadcast_to(add_feature_point, n), np.int32), cap, out.ctypes.data, imm.ctypes.data, n_out, num))
-        return [(out[j, :n_out[j]].copy(), imm[j, :n_out[j]].copy()) for j in range(n)], num.reshape(n, 2)
+        return [(out[j, :n_out[j]], imm[j, :n_out[j]]) for j in range(n)], num.reshape(n, 2)
 
 
-def activateSelectBatch(ctx: Context, seqs, want_maps=False):
-    """CoarseDistanceMap::makeDistanceMap + the candidate walk of FullSystem::activatePointsMT for several sequences.  seqs: list of dicts with pt_begin / KRKi / Kt / uvid
-    (source keyframes) and cand_begin / cKRKi / cKt / cand4 / minActDist (candidate keyframes; may be absent).  -> per sequence decisions (+ distance maps)"""
-    n = len(seqs); hb, pb, gb, cb = [0], [0], [0], [0]; A, B, U, cA, cB, c4, md = [], [], [], [], [], [], []
+def packActivation(seqs):
+    """the flat arrays sdv_activate_select_batch takes, from per-sequence dicts with pt_begin / KRKi / Kt / uvid (source keyframes) and cand_begin / cKRKi / cKt / cand4 /
+    minActDist (candidate keyframes; may be absent)"""
+    hb, pb, gb, cb = [0], [0], [0], [0]; A, B, U, cA, cB, c4, md = [], [], [], [], [], [], []
     f = lambda a, t: np.ascontiguousarray(a, t)
     for q in seqs:
         p = f(q["pt_begin"], np.int32); hb.append(hb[-1] + len(p) - 1); pb += list(pb[-1] + p[1:]); A.append(f(q["KRKi"], np.float32).reshape(-1, 9)); B.append(f(q["Kt"], np.float32).reshape(-1, 3)); U.append(f(q["uvid"], np.float32).reshape(-1, 3))
         g = f(q.get("cand_begin", [0]), np.int32); gb.append(gb[-1] + len(g) - 1); cb += list(cb[-1] + g[1:]); md.append(q.get("minActDist", 0.0))
         if len(g) > 1: cA.append(f(q["cKRKi"], np.float32).reshape(-1, 9)); cB.append(f(q["cKt"], np.float32).reshape(-1, 3)); c4.append(f(q["cand4"], np.float32).reshape(-1, 4))
     cat = lambda xs, k: np.ascontiguousarray(np.concatenate(xs) if xs else np.zeros((1, k), np.float32))
-    A, B, U, cA, cB, c4 = cat(A, 9), cat(B, 3), cat(U, 3), cat(cA, 9), cat(cB, 3), cat(c4, 4)
-    dec = np.zeros(max(cb[-1], 1), np.int32); maps = np.zeros((n, ctx.h >> 1, ctx.w >> 1), np.float32) if want_maps else None
-    ctx._ck(LIB.sdv_activate_select_batch(ctx.p, n, f(hb, np.int32), f(pb, np.int32), A.ctypes.data, B.ctypes.data, U.ctypes.data, f(gb, np.int32), f(cb, np.int32), cA.ctypes.data, cB.ctypes.data,
-                                          c4.ctypes.data, f(md, np.float32), dec.ctypes.data, maps.ctypes.data if want_maps else None))
-    out = []; k = 0
-    for j in range(n):
-        nc = cb[gb[j + 1]] - cb[gb[j]]; out.append(dec[k:k + nc]); k += nc
+    return dict(n=len(seqs), hb=f(hb, np.int32), pb=f(pb, np.int32), A=cat(A, 9), B=cat(B, 3), U=cat(U, 3), gb=f(gb, np.int32), cb=f(cb, np.int32), cA=cat(cA, 9), cB=cat(cB, 3), c4=cat(c4, 4),
+                md=f(md, np.float32), dec=np.zeros(max(cb[-1], 1), np.int32))
+
+
+def activateSelectPacked(ctx: Context, P, want_maps=False):
+    """sdv_activate_select_batch on arrays packed by packActivation (the decisions land in P['dec'], reused between calls) -> per-sequence views of the decisions (+ maps)"""
+    n = P["n"]; maps = np.zeros((n, ctx.h >> 1, ctx.w >> 1), np.float32) if want_maps else None
+    ctx._ck(LIB.sdv_activate_select_batch(ctx.p, n, P["hb"], P["pb"], P["A"].ctypes.data, P["B"].ctypes.data, P["U"].ctypes.data, P["gb"], P["cb"], P["cA"].ctypes.data, P["cB"].ctypes.data,
+                                          P["c4"].ctypes.data, P["md"], P["dec"].ctypes.data, maps.ctypes.data if want_maps else None))
+    cb, gb = P["cb"], P["gb"]; out = [P["dec"][cb[gb[j]]:cb[gb[j + 1]]] for j in range(n)]
     return (out, maps) if want_maps else out
+
+
+def activateSelectBatch(ctx: Context, seqs, want_maps=False):
+    """CoarseDistanceMap::makeDistanceMap + the candidate walk of FullSystem::activatePointsMT for several sequences.  seqs: list of dicts with pt_begin / KRKi / Kt / uvid
+    (source keyframes) and cand_begin / cKRKi / cKt / cand4 / minActDist (candidate keyframes; may be absent).  -> per sequence decisions (+ distance maps)"""
+    r = activateSelectPacked(ctx, packActivation(seqs), want_maps)
+    return ([d.copy() for d in r[0]], r[1]) if want_maps else [d.copy() for d in r]
 
 
 # ---------------------------------------------------------------------------------------------- LiDAR front-end (sdv_lidar.cu): lidarCloudHandler, src/main.cpp:785-858
