@@ -39,3 +39,5 @@ def test_committed_b200_line_has_every_contract_key():
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["value"] != d["value"]
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["gpu_launches"] > 0 and d["vs_baseline"] is None
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and "workload" in d["config"] and d["scaling"] == "weak"
+    if "keyframe_rate" in d:                                                 # the keyframe-rate leg ran and its device results were identical to the CPU path
+        k = d["keyframe_rate"]; assert "error" not in k and k["identical_to_cpu"] is True and k["lidar_front_end"]["sweeps_per_s"] > 0 and k["make_new_traces"]["keyframes_per_s"] > 0
