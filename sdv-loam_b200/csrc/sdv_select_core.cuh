@@ -555,14 +555,37 @@ __device__ __forceinline__ bool smap_claim(unsigned int* m, int cell, int k) {
 }
 // (A one-warp walk with 128 threads for the map load / store — tried because ncu shows 44 % of the issue cycles of this kernel at the block barrier — is SLOWER: 12.5 ms
 // against 9.1 ms per 148 sequences; the second warp does shorten the frontier and judge loops.  Measured on the B200, profiles/README.md.)
-__global__ void __launch_bounds__(64) act_walk_smem_kernel(const DistJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(256) act_walk_smem_kernel(const DistJob* __restrict__ jobs, int build_map) {
   const DistJob J = jobs[blockIdx.x]; const int w1 = J.w1, h1 = J.h1, n1 = w1*h1, nc = J.cand_begin[J.nCandHosts];
   SDV_DYN_SMEM(unsigned int, dsm);
   unsigned int* smap = dsm; int* listA = (int*)(dsm + ((n1 + 3) >> 2)); int* listB = listA + 1024;
   __shared__ int nA, nB, first;
-  for (int i = threadIdx.x; i < ((n1 + 3) >> 2); i += blockDim.x) {                       // four cells per word
-    unsigned int wv = 0; for (int b = 0; b < 4; b++) { const int c = 4*i + b; const int d = (c < n1) ? J.d[c] : 1000; wv |= (unsigned int)(d > 254 ? 255 : d) << (8*b); }
-    smap[i] = wv; }
+  if (build_map) {                                                                       // makeDistanceMap in shared memory: fill, sources, 39 pull rings (same rule as dm_ring_kernel)
+    unsigned char* bm = reinterpret_cast<unsigned char*>(smap);
+    for (int i = threadIdx.x; i < ((n1 + 3) >> 2); i += blockDim.x) smap[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    const int np = J.pt_begin[J.nHosts];
+    for (int p = threadIdx.x; p < np; p += blockDim.x) { int hI = 0; while (p >= J.pt_begin[hI+1]) hI++;
+      int u, v; float px; if (dm_project(J.KRKi + 9*hI, J.Kt + 3*hI, J.uvid[3*p], J.uvid[3*p+1], J.uvid[3*p+2], w1, h1, u, v, px)) bm[u + w1*v] = 0; }
+    __syncthreads();
+    for (int k = 1; k < 40; k++) {
+      for (int i = threadIdx.x; i < n1; i += blockDim.x) {
+        if ((int)bm[i] <= k) continue;
+        const int y = i / w1, x = i - y*w1; bool hit = false;
+        for (int dy = -1; dy <= 1 && !hit; dy++) for (int dx = -1; dx <= 1; dx++) {
+          if ((dx == 0 && dy == 0) || ((k&1) == 0 && dx != 0 && dy != 0)) continue;
+          const int qx = x+dx, qy = y+dy; if (qx <= 0 || qy <= 0 || qx >= w1-1 || qy >= h1-1) continue;
+          if ((int)bm[qx + qy*w1] == k-1) { hit = true; break; }
+        }
+        if (hit) bm[i] = (unsigned char)k;
+      }
+      __syncthreads();
+    }
+  } else {
+    for (int i = threadIdx.x; i < ((n1 + 3) >> 2); i += blockDim.x) {                     // four cells per word
+      unsigned int wv = 0; for (int b = 0; b < 4; b++) { const int c = 4*i + b; const int d = (c < n1) ? J.d[c] : 1000; wv |= (unsigned int)(d > 254 ? 255 : d) << (8*b); }
+      smap[i] = wv; }
+  }
   __syncthreads();
   for (int c0 = 0; c0 < nc; c0 += blockDim.x) {
     const int c = c0 + threadIdx.x; bool live = c < nc; int uv = -1; float frac = 0, thr = 0;
@@ -618,6 +641,7 @@ struct SelEngine {
   Scratch scr, scr2; long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool have_ev = false; float last_kernel_ms = 0.f;   // device time of the launches of the last activate() (copies excluded)
   size_t max_scratch = (size_t)1 << 30;
+  int walk_threads = 256;                   // CTA size of the fused shared-memory map + walk kernel (the rings want threads; the walk is indifferent: 64 / 128 / 256 measured equal)
   size_t max_walk_smem = 200*1024;          // the activation walk keeps its distance map in shared memory up to this size (227 KB per CTA on sm_100)
 
   int init(int w_, int h_, const SelSet& S_, const unsigned char* random_pattern_host, cudaStream_t st_) {
@@ -832,16 +856,18 @@ struct SelEngine {
     SEL_CK(cudaMemcpyAsync(dD, D.data(), nj*sizeof(DistJob), cudaMemcpyHostToDevice, st));
     const int gpx = (int)std::min<size_t>((n1 + 255)/256, 1024);
     if (have_ev) cudaEventRecord(ev0, st);
-    SDV_LAUNCH(dm_fill_kernel, dim3(gpx, nj), dim3(256), st, dD);
-    if (maxP > 0) SDV_LAUNCH(dm_source_kernel, dim3((maxP + 127)/128, nj), dim3(128), st, dD);
-    for (int k = 1; k < 40; k++) SDV_LAUNCH(dm_ring_kernel, dim3(gpx, nj), dim3(256), st, dD, k);
-    launches += 41;
-    if (maxC > 0) {
-      SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD);
-      const size_t walk_smem = (((n1 + 3) >> 2) + 2048)*sizeof(int);                       // byte map + the two frontier lists
-      if (walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0) SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(64), walk_smem, st, dD);
-      else SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD);                   // image too large for the shared-memory map (or attribute refused): global-memory walk
-      launches += 2; }
+    const size_t walk_smem = (((n1 + 3) >> 2) + 2048)*sizeof(int);                         // byte map + the two frontier lists
+    const bool fused = walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0;
+    if (maxC > 0) SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD);
+    if (fused) {                                                                         // ONE kernel per call: distance map built, walked and written back from shared memory
+      SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(walk_threads), walk_smem, st, dD, 1); launches += 2;
+    } else {                                                                             // image too large for the shared-memory map: 41 launches for the map, global-memory walk
+      SDV_LAUNCH(dm_fill_kernel, dim3(gpx, nj), dim3(256), st, dD);
+      if (maxP > 0) SDV_LAUNCH(dm_source_kernel, dim3((maxP + 127)/128, nj), dim3(128), st, dD);
+      for (int k = 1; k < 40; k++) SDV_LAUNCH(dm_ring_kernel, dim3(gpx, nj), dim3(256), st, dD, k);
+      launches += 41;
+      if (maxC > 0) { SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD); launches += 2; }
+    }
     if (have_ev) cudaEventRecord(ev1, st);
     SEL_CK(cudaGetLastError());
     std::vector<std::vector<int>> maps(nj);

@@ -10,7 +10,9 @@ using namespace sdv::sel;
 extern "C" {
 void* emu_engine_create(int w, int h, const unsigned char* rp, int dirDist) {
   SelEngine* e = new SelEngine(); SelSet S; S.minGradHistCut = 0.5f; S.minGradHistAdd = 3; S.gradDownweightPerLevel = 0.75f; S.selectDirectionDistribution = dirDist;
-  S.outlierTH = 12*12; S.outlierTHSumComponent = 50*50; S.overallEnergyTHWeight = 1; e->init(w, h, S, rp, nullptr); return e; }
+  S.outlierTH = 12*12; S.outlierTHSumComponent = 50*50; S.overallEnergyTHWeight = 1; e->init(w, h, S, rp, nullptr);
+  e->walk_threads = 64;                               // one OS thread per CUDA thread here: keep the emulated CTA small (the result does not depend on the CTA size)
+  return e; }
 void emu_engine_destroy(void* e) { ((SelEngine*)e)->destroy(); delete (SelEngine*)e; }
 const char* emu_engine_error(void* e) { return ((SelEngine*)e)->err.c_str(); }
 void emu_engine_max_scratch(void* e, long long b) { ((SelEngine*)e)->max_scratch = (size_t)b; }
