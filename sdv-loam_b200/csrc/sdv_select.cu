@@ -44,7 +44,8 @@ int sdv_selector_init(sdv_ctx* c, const uint8_t* random_pattern, int n_slots) { 
   S.outlierTH = c->set.outlierTH; S.outlierTHSumComponent = c->set.outlierTHSumComponent; S.overallEnergyTHWeight = 1;
   if (s->eng.init(c->w, c->h, S, random_pattern, c->st)) { int rc = sel_fail(c, s, -1, "selector_init"); sel_destroy(c); return rc; }
   s->slots.resize(n_slots);
-  if (const char* e = getenv("SDV_WALK_THREADS")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) s->eng.walk_threads = t; }   // tuning knob
+  if (const char* e = getenv("SDV_WALK_THREADS")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128 || t == 256) s->eng.walk_threads = t; }   // tuning knobs
+  if (const char* e = getenv("SDV_FUSE_MAP")) s->eng.fuse_map = atoi(e) != 0;
   return SDV_OK;
 }
 int sdv_selector_potential(sdv_ctx* c, int slot, int set_to, int* out) { SDV_GUARD_TRK(c);

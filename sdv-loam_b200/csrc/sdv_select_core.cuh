@@ -641,7 +641,9 @@ struct SelEngine {
   Scratch scr, scr2; long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool have_ev = false; float last_kernel_ms = 0.f;   // device time of the launches of the last activate() (copies excluded)
   size_t max_scratch = (size_t)1 << 30;
-  int walk_threads = 256;                   // CTA size of the fused shared-memory map + walk kernel (the rings want threads; the walk is indifferent: 64 / 128 / 256 measured equal)
+  int walk_threads = 64;                    // CTA size of the shared-memory walk kernel (64 / 128 / 256 measured equal: the walk is a latency chain)
+  bool fuse_map = false;                    // build the distance map inside the walk kernel (fill, sources, 39 rings in shared memory; SDV_FUSE_MAP=1).  Correct (GPU tests green) but
+                                            // measured SLOWER at 148 sequences: 10.9 ms against 9.1 ms — full-map sweeps by one CTA per sequence lose against 39 grid-wide launches
   size_t max_walk_smem = 200*1024;          // the activation walk keeps its distance map in shared memory up to this size (227 KB per CTA on sm_100)
 
   int init(int w_, int h_, const SelSet& S_, const unsigned char* random_pattern_host, cudaStream_t st_) {
@@ -857,16 +859,19 @@ struct SelEngine {
     const int gpx = (int)std::min<size_t>((n1 + 255)/256, 1024);
     if (have_ev) cudaEventRecord(ev0, st);
     const size_t walk_smem = (((n1 + 3) >> 2) + 2048)*sizeof(int);                         // byte map + the two frontier lists
-    const bool fused = walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0;
+    const bool smem_ok = walk_smem <= max_walk_smem && SDV_SET_SMEM(act_walk_smem_kernel, walk_smem) == 0, fused = smem_ok && fuse_map;
     if (maxC > 0) SDV_LAUNCH(act_project_kernel, dim3((maxC + 127)/128, nj), dim3(128), st, dD);
     if (fused) {                                                                         // ONE kernel per call: distance map built, walked and written back from shared memory
       SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(walk_threads), walk_smem, st, dD, 1); launches += 2;
-    } else {                                                                             // image too large for the shared-memory map: 41 launches for the map, global-memory walk
+    } else {                                                                             // 41 launches for the map (all SMs per ring), then the walk
       SDV_LAUNCH(dm_fill_kernel, dim3(gpx, nj), dim3(256), st, dD);
       if (maxP > 0) SDV_LAUNCH(dm_source_kernel, dim3((maxP + 127)/128, nj), dim3(128), st, dD);
       for (int k = 1; k < 40; k++) SDV_LAUNCH(dm_ring_kernel, dim3(gpx, nj), dim3(256), st, dD, k);
       launches += 41;
-      if (maxC > 0) { SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD); launches += 2; }
+      if (maxC > 0) {
+        if (smem_ok) SDV_LAUNCH_SYNC_SMEM(act_walk_smem_kernel, dim3(nj), dim3(walk_threads), walk_smem, st, dD, 0);
+        else SDV_LAUNCH_SYNC(act_walk_kernel, dim3(nj), dim3(64), st, dD);               // image too large for the shared-memory map: global-memory walk
+        launches += 2; }
     }
     if (have_ev) cudaEventRecord(ev1, st);
     SEL_CK(cudaGetLastError());

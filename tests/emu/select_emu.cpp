@@ -14,6 +14,7 @@ void* emu_engine_create(int w, int h, const unsigned char* rp, int dirDist) {
   e->walk_threads = 64;                               // one OS thread per CUDA thread here: keep the emulated CTA small (the result does not depend on the CTA size)
   return e; }
 void emu_engine_destroy(void* e) { ((SelEngine*)e)->destroy(); delete (SelEngine*)e; }
+void emu_engine_fuse_map(void* e, int f) { ((SelEngine*)e)->fuse_map = f != 0; }
 const char* emu_engine_error(void* e) { return ((SelEngine*)e)->err.c_str(); }
 void emu_engine_max_scratch(void* e, long long b) { ((SelEngine*)e)->max_scratch = (size_t)b; }
 int emu_make_hists(void* ep, const float* I0, float* ths_out, float* thsSm_out) {

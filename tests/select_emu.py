@@ -22,7 +22,7 @@ def lib():
         L = C.CDLL(_SO)
         L.emu_engine_create.restype = C.c_void_p; L.emu_engine_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.emu_engine_destroy.argtypes = [C.c_void_p]; L.emu_engine_error.restype = C.c_char_p; L.emu_engine_error.argtypes = [C.c_void_p]
-        L.emu_engine_max_scratch.argtypes = [C.c_void_p, C.c_longlong]; L.emu_engine_launches.restype = C.c_longlong; L.emu_engine_launches.argtypes = [C.c_void_p]
+        L.emu_engine_fuse_map.argtypes = [C.c_void_p, C.c_int]; L.emu_engine_max_scratch.argtypes = [C.c_void_p, C.c_longlong]; L.emu_engine_launches.restype = C.c_longlong; L.emu_engine_launches.argtypes = [C.c_void_p]
         L.emu_make_hists.argtypes = [C.c_void_p] * 4
         L.emu_make_maps.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7
         L.emu_slot_create.restype = C.c_void_p; L.emu_slot_destroy.argtypes = [C.c_void_p]; L.emu_slot_set_potential.argtypes = [C.c_void_p, C.c_int]; L.emu_slot_get_potential.argtypes = [C.c_void_p]

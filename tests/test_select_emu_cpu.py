@@ -101,7 +101,8 @@ def test_distance_map_and_activation_walk(scene):
         cand.append(np.stack([u, v, idm, rng.choice([1.0, 2.0, 4.0], n)], 1).astype(np.float32)); cb.append(cb[-1] + n)
     cand = np.concatenate(cand); K0, K1 = orc.distmap_geometry(SMALL_K, None, None)
     cK = np.concatenate([KRKi, [(K1 @ np.linalg.inv(K0.astype(np.float64)).astype(np.float32)).astype(np.float32)]]); ct = np.concatenate([Kt, np.zeros((1, 3), np.float32)])
-    for minDist, copies in ((1.0, 1), (2.5, 2)):                              # the emulated walk is slow (one OS thread per CUDA thread); the GPU test runs four distances
+    for minDist, copies in ((1.0, 1), (2.5, 2)):
+        se.lib().emu_engine_fuse_map(E.p, int(copies == 2))                     # both ways of building the map: 41 launches, or inside the walk kernel (SDV_FUSE_MAP)                              # the emulated walk is slow (one OS thread per CUDA thread); the GPU test runs four distances
         od.make(pb, KRKi, Kt, uvid); do = od.activateSelect(cb, cK, ct, cand, minDist)
         dec, m = E.activate(pb, KRKi, Kt, uvid, cb, cK, ct, cand, minDist, copies=copies)
         assert all(np.array_equal(dec[c], do) for c in range(copies)), minDist
