@@ -376,6 +376,17 @@ class System:
         assert m <= cap
         return o[:m]
 
+    def immature_dump(self, cap=1 << 16):
+        """every ImmaturePoint of every keyframe of the window -> list of (shell id, records (n,29) float32, status (n,) int32), window order"""
+        L = lib(); L.ref_sys_immature_dump.argtypes = [_vp, _i32p, _i32p, _f32p, _i32p, C.c_int]; ids = np.zeros(16, np.int32); cnt = np.zeros(16, np.int32)
+        rec = np.zeros((cap, 29), np.float32); st = np.zeros(cap, np.int32); nk = L.ref_sys_immature_dump(self.p, ids, cnt, rec.reshape(-1), st, cap); assert nk >= 0
+        out = []; o = 0
+        for k in range(nk): out.append((int(ids[k]), rec[o:o + cnt[k]].copy(), st[o:o + cnt[k]].copy())); o += int(cnt[k])
+        return out
+    def trace_geometry(self, host_idx, new_c2w7):
+        L = lib(); L.ref_sys_trace_geometry.argtypes = [_vp, C.c_int, _f64p, _f32p, _f32p]; a = np.zeros(9, np.float32); b = np.zeros(3, np.float32)
+        L.ref_sys_trace_geometry(self.p, host_idx, np.ascontiguousarray(new_c2w7, np.float64), a, b); return a.reshape(3, 3), b
+
     def num_frames(self): return lib().ref_sys_num_frames(self.p)
     def num_keyframes(self): return lib().ref_sys_num_keyframes(self.p)
 

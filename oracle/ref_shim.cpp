@@ -690,4 +690,21 @@ int ref_sys_probe_new_traces(void* p, void* frame, const double* cloud3, int n, 
   return m;
 }
 
+// ---- sequence level, immature points: every candidate of every keyframe of the RUNNING system, before / after a frame (FullSystem::traceNewCoarse runs in makeNonKeyFrame
+// and makeKeyFrame).  rec29 / status as ref_immature_get; returns the number of keyframes, counts[k] candidates of keyframe k (window order), shell ids in host_ids.
+int ref_sys_immature_dump(void* p, int* host_ids, int* counts, float* rec29, int* status, int cap) {
+  FullSystem* fs = ((RefSys*)p)->fs; int nk = 0, m = 0;
+  for (FrameHessian* fh : fs->frameHessians) { host_ids[nk] = fh->shell->id; counts[nk] = (int)fh->immaturePoints.size(); nk++;
+    for (ImmaturePoint* ip : fh->immaturePoints) { if (ip && m < cap) ref_immature_get(ip, rec29 + 29*(size_t)m, status + m); m++; } }
+  return (m <= cap) ? nk : -1;
+}
+// KRKi, Kt of host keyframe (window index) -> a frame with camToWorld new_c2w7, formed like FullSystem::traceNewCoarse forms them (FullSystem.cpp:525-535) with the current CalibHessian
+void ref_sys_trace_geometry(void* p, int host_idx, const double new_c2w7[7], float KRKi9[9], float Kt3[3]) {
+  FullSystem* fs = ((RefSys*)p)->fs; FrameHessian* host = fs->frameHessians[host_idx];
+  Mat33f K = Mat33f::Identity(); K(0,0) = fs->Hcalib.fxl(); K(1,1) = fs->Hcalib.fyl(); K(0,2) = fs->Hcalib.cxl(); K(1,2) = fs->Hcalib.cyl();
+  SE3 hostToNew = se3_from(new_c2w7).inverse() * host->PRE_camToWorld;
+  Mat33f KRKi = K * hostToNew.rotationMatrix().cast<float>() * K.inverse(); Vec3f Kt = K * hostToNew.translation().cast<float>();
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) KRKi9[3*i+j] = KRKi(i, j); Kt3[i] = Kt[i]; }
+}
+
 }  // extern "C"

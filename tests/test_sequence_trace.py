@@ -1,0 +1,39 @@
+"""Sequence-level parity of the immature-point tracing on the reference's OWN running pipeline: the reference's FullSystem (oracle/_ref) runs the
+synthetic KITTI drive; around every frame that does NOT become a keyframe (makeNonKeyFrame -> traceNewCoarse -> ImmaturePoint::traceOn for every candidate of every keyframe of
+the window) all candidates are read back before and after, and the restatement, started from the "before" records with the geometry the reference forms (K R K^-1, K t of
+host -> new frame from the tracked pose), must reproduce the "after" records BIT FOR BIT — every field, every status — for thousands of candidates in whatever state the
+running system left them (fresh, converged, skipped, out of bounds, outliers)."""
+import numpy as np
+import pytest
+import orc
+import ref
+from conftest import cached_sequence
+import seq_replay as sr
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built and /root/reference absent")
+N_FRAMES = 60
+
+
+def test_oracle_follows_reference_trace_new_coarse():
+    from sdv_loam_b200 import synth
+    seq = cached_sequence(200, 1000, synth.KITTI_K, synth.KITTI_WH, step=0.5); w, h = seq.wh
+    L = ref.set_calib(w, h, seq.K); run = sr.ReferenceRun(seq, L); S = run.S
+    frames = 0; cands = 0; seen = set(); aff = np.array([1.0, 0.0], np.float32)      # perfect-image mode: exposures 1, affine parameters fixed at 0 -> fromToVecExposure = (1, 0)
+    for i in range(N_FRAMES):
+        pre = S.immature_dump() if i >= 3 else None
+        nkf = S.num_keyframes(); _, _, res = run.step(); assert res["rc"] == 0, i
+        if pre is None or S.num_keyframes() != nkf: continue                        # bootstrap, or the frame became a keyframe (candidates get activated / deleted there)
+        post = S.immature_dump(); assert [p[0] for p in pre] == [p[0] for p in post] and [len(p[1]) for p in pre] == [len(p[1]) for p in post], i
+        fo = orc.Frame(seq.images[i], L)
+        for hidx, ((kid, rec0, st0), (_, rec1, st1)) in enumerate(zip(pre, post)):
+            if len(rec0) == 0: continue
+            KRKi, Kt = S.trace_geometry(hidx, res["camToWorld"])
+            P = np.zeros(len(rec0), orc.IMM_DTYPE); P.view(np.float32).reshape(len(rec0), -1)[:, :29] = rec0; P["lastTraceStatus"] = st0
+            so = orc.immature_trace(fo, P, KRKi, Kt, aff)
+            got = P.view(np.float32).reshape(len(rec0), -1)[:, :29]
+            assert np.array_equal(so, st1) and np.array_equal(P["lastTraceStatus"], st1), (i, kid, np.nonzero(so != st1)[0][:5])
+            assert np.array_equal(got.view(np.uint32), rec1.view(np.uint32)), (i, kid, np.argwhere(got.view(np.uint32) != rec1.view(np.uint32))[:5])
+            cands += len(rec0); seen |= set(int(s) for s in st1)
+        frames += 1
+    assert frames >= 15 and cands > 20000 and {orc.IPS_GOOD, orc.IPS_OOB, orc.IPS_SKIPPED} <= seen, (frames, cands, seen)
+    print(f"traceNewCoarse: {frames} non-keyframe frames of the reference run, {cands} candidate traces identical; statuses seen {sorted(seen)}")
