@@ -254,6 +254,10 @@ int  sdv_immature_optimize_batch(sdv_ctx* c, int n_groups, const int32_t* pt_beg
 int  sdv_ba_set_window(sdv_ctx* c, int nF, const uint64_t* frame_ids, const double* T_evalPT7, const double* state10, const double* state_zero10,
                        const float* ab_exposure, const int32_t* frameID, const float* frameEnergyTH, const double calib_value_scaled[4],
                        const double* HM, const double* bM);
+/* CalibHessian::value_zero (HessianBlocks.h:273-289) of a live system: sdv_ba_set_window takes value_zero = value (a fresh CalibHessian); after the first bundle adjustment the two
+ * differ and value - value_zero is what the marginalisation prior acts on (EnergyFunctional.cpp:144).  Optional; between sdv_ba_set_window and sdv_ba_set_points.  Units of
+ * CalibHessian::value (= value_scaled / SCALE_F resp. SCALE_C).  Oracle side: orc_ba_set_calib_zero, exercised on live windows by tests/test_sequence_ba.py. */
+int  sdv_ba_set_calib_zero(sdv_ctx* c, const double value_zero[4]);
 /* points + residuals: PointHessian {u,v,idepth,idepth_zero,color[8],weights[8],hasDepthPrior,isFromSensor} (HessianBlocks.h:361-465),
  * PointFrameResidual {host,target,hasMatcher,matcher,isNew} (Residuals.h:30-83).  Runs setPrecalcValues (FullSystem.cpp:1358-1368). */
 int  sdv_ba_set_points(sdv_ctx* c, int nP, const float* uv, const float* idepth, const float* idepth_zero, const float* color8, const float* weights8,

@@ -42,7 +42,7 @@ struct FrameHessian {                                                          /
   AffLight aff_g2l() const { return shell->aff_g2l; }
   void makeImages(float* color, struct CalibHessian* HCalib);
 };
-struct CalibHessian { VecC value_scaled; float fxl() const { return (float)value_scaled.v[0]; } float fyl() const { return (float)value_scaled.v[1]; }
+struct CalibHessian { VecC value_scaled, value_zero; float fxl() const { return (float)value_scaled.v[0]; } float fyl() const { return (float)value_scaled.v[1]; }
                       float cxl() const { return (float)value_scaled.v[2]; } float cyl() const { return (float)value_scaled.v[3]; } };
 struct Undistort { int wOrg, hOrg; float* remapX; float* remapY; };           // util/Undistort.h (remapX/remapY: protected there — one friend declaration or two getters)
 namespace IOWrap { struct Output3DWrapper; }
@@ -132,6 +132,7 @@ struct FullSystem {
       res_begin.push_back((int32_t)r_point.size());
     }
     int rc = sdv_ba_set_window(gpu, nF, ids.data(), T_eval.data(), state.data(), state_zero.data(), exposure.data(), frameID.data(), energyTH.data(), Hcalib.value_scaled.data(), HM.data(), bM.data());
+    if (rc == SDV_OK) rc = sdv_ba_set_calib_zero(gpu, Hcalib.value_zero.data());                   // the linearisation point of the intrinsics stays at the initial K (HessianBlocks.h:287)
     if (rc == SDV_OK) rc = sdv_ba_set_points(gpu, (int)host.size(), uv.data(), idepth.data(), idepth_zero.data(), color.data(), weights.data(), host.data(), hasPrior.data(), fromSensor.data(),
                                              res_begin.data(), (int)r_point.size(), r_point.data(), r_host.data(), r_target.data(), r_hasM.data(), r_matcher.data(), r_isNew.data());
     float rmse = 0; int32_t its = 0, acc = 0;

@@ -305,6 +305,7 @@ class BAWindow:
         w, h = win["wh"]; self.nF = win["nF"]; self.nP = len(win["uv"]); self.nR = len(win["r_point"]); self.n = 4 + 6 * self.nF
         self.p = L.orc_ba_create(w, h)
         L.orc_ba_set_calib(self.p, np.ascontiguousarray(win["K"], np.float64))
+        if "K_zero" in win: L.orc_ba_set_calib_zero.argtypes = [C.c_void_p, _f64p]; L.orc_ba_set_calib_zero(self.p, np.ascontiguousarray(win["K_zero"], np.float64))   # live window: value_zero = initial intrinsics
         for i in range(self.nF):
             L.orc_ba_add_frame(self.p, frames[i].p, np.ascontiguousarray(win["T_eval"][i]), np.ascontiguousarray(win["state"][i]),
                                np.ascontiguousarray(win["state_zero"][i]), float(win["ab_exposure"][i]), int(win["frameID"][i]), float(win["frameEnergyTH"][i]))

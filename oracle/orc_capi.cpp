@@ -97,6 +97,8 @@ extern "C" {
 void* orc_ba_create(int w, int h) { BAWindow* b = new BAWindow(); b->w=w; b->h=h; return b; }
 void orc_ba_destroy(void* p) { delete (BAWindow*)p; }
 void orc_ba_set_calib(void* p, const double vs[4]) { ((BAWindow*)p)->setCalibScaled(vs); }
+// CalibHessian::value_zero of a LIVE system stays at the initial intrinsics (HessianBlocks.h:287) while value moves with every bundle adjustment
+void orc_ba_set_calib_zero(void* p, const double vz[4]) { BAWindow* b=(BAWindow*)p; for (int i=0;i<4;i++) { b->c_value_zero[i]=vz[i]; b->c_vmvz[i]=b->c_value[i]-vz[i]; } }
 void orc_ba_add_frame(void* p, void* img, const double T_eval[7], const double state[10], const double state_zero[10], float ab_exposure, int frameID, float frameEnergyTH) {
   BAWindow* b=(BAWindow*)p; BAFrame f; f.worldToCam_evalPT = se3_from(T_eval);
   for (int i=0;i<10;i++) { f.state[i]=state[i]; f.state_zero[i]=state_zero[i]; f.state_backup[i]=state[i]; f.step[i]=0; }

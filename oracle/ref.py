@@ -387,6 +387,23 @@ class System:
         L = lib(); L.ref_sys_trace_geometry.argtypes = [_vp, C.c_int, _f64p, _f32p, _f32p]; a = np.zeros(9, np.float32); b = np.zeros(3, np.float32)
         L.ref_sys_trace_geometry(self.p, host_idx, np.ascontiguousarray(new_c2w7, np.float64), a, b); return a.reshape(3, 3), b
 
+    def export_window(self, wh):
+        """the LIVE sliding window flattened into the layout of synth.make_ba_window (frames / points / residuals in EnergyFunctional order) + shell ids"""
+        L = lib(); sz = np.zeros(3, np.int32); L.ref_sys_window_sizes.argtypes = [_vp, _i32p]; L.ref_sys_window_sizes(self.p, sz); nF, nP, nR = [int(x) for x in sz]; n = 4 + 6 * nF
+        f32 = lambda *sh: np.zeros(sh, np.float32); i32 = lambda *sh: np.zeros(sh, np.int32); f64 = lambda *sh: np.zeros(sh, np.float64)
+        a = dict(shell_ids=i32(nF), T_eval=f64(nF, 7), state=f64(nF, 10), state_zero=f64(nF, 10), ab_exposure=f32(nF), frameID=i32(nF), frameEnergyTH=f32(nF), K=f64(4), K_zero=f64(4),
+                 uv=f32(nP, 2), idepth=f32(nP), idepth_zero=f32(nP), color=f32(nP, 8), weights=f32(nP, 8), host=i32(nP), hasDepthPrior=i32(nP), isFromSensor=i32(nP), res_begin=i32(nP + 1),
+                 r_point=i32(nR), r_host=i32(nR), r_target=i32(nR), r_hasMatcher=i32(nR), r_matcher=f32(nR, 2), r_isNew=i32(nR), HM=f64(n, n), bM=f64(n))
+        L.ref_sys_export_window.argtypes = [_vp] + [C.c_void_p] * 26
+        L.ref_sys_export_window(self.p, *[a[k].ctypes.data for k in ("shell_ids", "T_eval", "state", "state_zero", "ab_exposure", "frameID", "frameEnergyTH", "K", "K_zero", "uv", "idepth", "idepth_zero",
+                                                                     "color", "weights", "host", "hasDepthPrior", "isFromSensor", "res_begin", "r_point", "r_host", "r_target", "r_hasMatcher", "r_matcher",
+                                                                     "r_isNew", "HM", "bM")])
+        a.update(nF=nF, wh=tuple(wh), kf_idx=[int(x) for x in a["shell_ids"]]); return a
+    def optimize(self, its=6):
+        L = lib(); L.ref_sys_optimize.restype = C.c_float; L.ref_sys_optimize.argtypes = [_vp, C.c_int]
+        with _Quiet():
+            return L.ref_sys_optimize(self.p, its)
+
     def num_frames(self): return lib().ref_sys_num_frames(self.p)
     def num_keyframes(self): return lib().ref_sys_num_keyframes(self.p)
 

@@ -707,4 +707,29 @@ void ref_sys_trace_geometry(void* p, int host_idx, const double new_c2w7[7], flo
   for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) KRKi9[3*i+j] = KRKi(i, j); Kt3[i] = Kt[i]; }
 }
 
+// ---- sequence level, back-end: the LIVE sliding window of a running system flattened into the layout of synth.make_ba_window / orc_ba_* (frames = ef->frames, points =
+// ef order per host, residuals = EFPoint::residualsAll order), and FullSystem::optimize run on that live window (tests/test_sequence_ba.py)
+void ref_sys_window_sizes(void* p, int sizes[3]) { FullSystem* fs = ((RefSys*)p)->fs; EnergyFunctional* ef = fs->ef; int nP = 0, nR = 0;
+  for (EFFrame* f : ef->frames) for (EFPoint* q : f->points) { nP++; nR += (int)q->residualsAll.size(); }
+  sizes[0] = (int)ef->frames.size(); sizes[1] = nP; sizes[2] = nR; }
+void ref_sys_export_window(void* p, int* shell_ids, double* T_eval7, double* state10, double* state_zero10, float* ab_exposure, int* frameID, float* frameEnergyTH,
+                           double* calib_value_scaled4, double* calib_value_zero4, float* uv, float* idepth, float* idepth_zero, float* color8, float* weights8, int* host,
+                           int* hasDepthPrior, int* isFromSensor, int* res_begin, int* r_point, int* r_host, int* r_target, int* r_hasMatcher, float* r_matcher2, int* r_isNew,
+                           double* HM, double* bM) {
+  FullSystem* fs = ((RefSys*)p)->fs; EnergyFunctional* ef = fs->ef; int nF = (int)ef->frames.size();
+  for (int i = 0; i < nF; i++) { FrameHessian* fh = ef->frames[i]->data; shell_ids[i] = fh->shell->id; se3_to(fh->worldToCam_evalPT, T_eval7 + 7*i);
+    for (int k = 0; k < 10; k++) { state10[10*i+k] = fh->state[k]; state_zero10[10*i+k] = fh->state_zero[k]; }
+    ab_exposure[i] = fh->ab_exposure; frameID[i] = fh->frameID; frameEnergyTH[i] = fh->frameEnergyTH; }
+  for (int k = 0; k < 4; k++) { calib_value_scaled4[k] = fs->Hcalib.value_scaled[k]; calib_value_zero4[k] = fs->Hcalib.value_zero[k]; }
+  int ip = 0, ir = 0; res_begin[0] = 0;
+  for (int i = 0; i < nF; i++) for (EFPoint* q : ef->frames[i]->points) { PointHessian* ph = q->data;
+    uv[2*ip] = ph->u; uv[2*ip+1] = ph->v; idepth[ip] = ph->idepth; idepth_zero[ip] = ph->idepth_zero; for (int k = 0; k < 8; k++) { color8[8*ip+k] = ph->color[k]; weights8[8*ip+k] = ph->weights[k]; }
+    host[ip] = i; hasDepthPrior[ip] = ph->hasDepthPrior ? 1 : 0; isFromSensor[ip] = ph->isFromSensor ? 1 : 0;
+    for (EFResidual* er : q->residualsAll) { PointFrameResidual* r = er->data; r_point[ir] = ip; r_host[ir] = r->host->idx; r_target[ir] = r->target->idx; r_hasMatcher[ir] = r->hasMatcher ? 1 : 0;
+      r_matcher2[2*ir] = r->matcher[0]; r_matcher2[2*ir+1] = r->matcher[1]; r_isNew[ir] = er->isLinearized ? -1 : (r->isNew ? 1 : 0); ir++; }
+    ip++; res_begin[ip] = ir; }
+  int n = (int)ef->HM.rows(); for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) HM[(size_t)i*n+j] = ef->HM(i, j); bM[i] = ef->bM[i]; }
+}
+float ref_sys_optimize(void* p, int its) { return ((RefSys*)p)->fs->optimize(its); }
+
 }  // extern "C"

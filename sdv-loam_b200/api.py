@@ -405,6 +405,8 @@ class EnergyFunctional:
         ctx._ck(LIB.sdv_ba_set_window(ctx.p, self.nF, np.ascontiguousarray(frame_ids, np.uint64), c("T_eval", np.float64), c("state", np.float64),
                                       c("state_zero", np.float64), c("ab_exposure", np.float32), c("frameID", np.int32), c("frameEnergyTH", np.float32),
                                       c("K", np.float64), c("HM", np.float64), c("bM", np.float64)))
+        if "K_zero" in win:                                                  # live window: CalibHessian::value_zero is not value any more
+            LIB.sdv_ba_set_calib_zero.argtypes = [_vp, _f64p]; ctx._ck(LIB.sdv_ba_set_calib_zero(ctx.p, c("K_zero", np.float64)))
         ctx._ck(LIB.sdv_ba_set_points(ctx.p, self.nP, c("uv", np.float32), c("idepth", np.float32), c("idepth_zero", np.float32), c("color", np.float32),
                                       c("weights", np.float32), c("host", np.int32), c("hasDepthPrior", np.int32), c("isFromSensor", np.int32), c("res_begin", np.int32),
                                       self.nR, c("r_point", np.int32), c("r_host", np.int32), c("r_target", np.int32), c("r_hasMatcher", np.int32),

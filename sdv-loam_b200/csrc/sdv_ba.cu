@@ -198,6 +198,16 @@ int sdv_ba_clear(sdv_ctx* c) { SDV_GUARD_BA(c);               // empties the sel
 }
 int sdv_ba_select(sdv_ctx* c, int window) { SDV_GUARD_BA(c); if (!c) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); return ba_select(c, window); }
 
+// CalibHessian::value_zero of a LIVE system: the linearisation point of the intrinsics stays where the CalibHessian was constructed (HessianBlocks.h:287) while value moves with
+// every bundle adjustment; sdv_ba_set_window assumes value_zero == value (a fresh CalibHessian).  Call this between sdv_ba_set_window and sdv_ba_set_points when they differ:
+// value_minus_value_zero (-> cDeltaF, EnergyFunctional.cpp:144) is what the marginalisation prior HM / bM acts on.  value_zero in CalibHessian::value units (value_scaled / SCALE).
+int sdv_ba_set_calib_zero(sdv_ctx* c, const double value_zero[4]) { SDV_GUARD_BA(c);
+  if (!c || !c->ba || !value_zero) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; BACalibDev& cal = b->hdr_host->calib;
+  for (int i=0;i<4;i++) { cal.value_zero[i] = value_zero[i]; cal.vmvz[i] = cal.value[i] - value_zero[i]; }
+  CK(cudaMemcpyAsync(&b->hdr->calib, &cal, sizeof(BACalibDev), cudaMemcpyHostToDevice, c->st_ba)); CK(cudaStreamSynchronize(c->st_ba));
+  return SDV_OK;
+}
+
 int sdv_ba_reset_oob(sdv_ctx* c) { SDV_GUARD_BA(c); if (!c || !c->ba) return SDV_ERR_ARG; CK(cudaSetDevice(c->device)); BAState* b = c->ba; WIN1(); launch_ba_reset_oob(wins, 1, maxR, c->st_ba); c->launches++; return SDV_OK; }
 
 int sdv_ba_linearize(sdv_ctx* c, int fix, double* energy) { SDV_GUARD_BA(c);
